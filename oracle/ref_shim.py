@@ -1,0 +1,108 @@
+"""Import the LIVE reference (read-only /root/reference) for golden generation (TEST INFRASTRUCTURE).
+
+Only usable in the build container: /root/reference does not exist on the GPU box, so nothing
+under tests -m gpu / smoke() / bench.py may call this.  Recipe = SURVEY.md Appendix A: stub the
+three missing third-party imports, pre-seed bare `ultralytics` / `ultralytics.nn` namespace
+modules so the heavy package __init__ files are skipped, then import the hot-path modules.
+Nothing under /root/reference is modified or copied.
+"""
+import contextlib
+import os
+import sys
+import tempfile
+import types
+
+REF_ROOT = os.environ.get("SARPOST_REFERENCE", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "ultralytics"))
+
+
+def _stub_third_party():
+    if "matplotlib" not in sys.modules:
+        try:
+            import matplotlib  # noqa: F401
+        except Exception:
+            mpl = types.ModuleType("matplotlib")
+            mpl.__version__ = "3.8.0"
+            mpl.__path__ = []
+            mpl.use = lambda *a, **k: None
+            plt = types.ModuleType("matplotlib.pyplot")
+            plt.get_backend = lambda: "agg"
+            plt.switch_backend = lambda *a, **k: None
+            plt.close = lambda *a, **k: None
+            plt.rc = lambda *a, **k: None
+            plt.rc_context = lambda *a, **k: contextlib.nullcontext()
+            mpl.pyplot = plt
+            sys.modules["matplotlib"] = mpl
+            sys.modules["matplotlib.pyplot"] = plt
+    if "thop" not in sys.modules:
+        thop = types.ModuleType("thop")
+
+        def _profile(*a, **k):
+            raise RuntimeError("thop stub")
+
+        thop.profile = _profile
+        sys.modules["thop"] = thop
+    if "pytorch_metric_learning" not in sys.modules:
+        pml = types.ModuleType("pytorch_metric_learning")
+        pml.__path__ = []
+        for s in ("miners", "distances", "losses", "reducers"):
+            m = types.ModuleType("pytorch_metric_learning." + s)
+            setattr(pml, s, m)
+            sys.modules["pytorch_metric_learning." + s] = m
+        sys.modules["pytorch_metric_learning"] = pml
+
+
+_CACHE = None
+
+
+def load():
+    """Returns (ops, tal, head) modules of the live reference."""
+    global _CACHE
+    if _CACHE is not None:
+        return _CACHE
+    if not available():
+        raise RuntimeError(f"reference not present at {REF_ROOT}")
+    _stub_third_party()
+    os.environ.setdefault("YOLO_CONFIG_DIR", tempfile.mkdtemp(prefix="sarpost_yolo_cfg_"))
+    os.environ.setdefault("YOLO_OFFLINE", "1")
+    root = os.path.join(REF_ROOT, "ultralytics")
+    if "ultralytics" not in sys.modules:
+        u = types.ModuleType("ultralytics")
+        u.__path__ = [root]
+        u.__version__ = "8.3.63"
+        sys.modules["ultralytics"] = u
+        n = types.ModuleType("ultralytics.nn")
+        n.__path__ = [os.path.join(root, "nn")]
+        sys.modules["ultralytics.nn"] = n
+    import ultralytics.nn.modules.head as head
+    import ultralytics.utils.ops as ops
+    import ultralytics.utils.tal as tal
+
+    _CACHE = (ops, tal, head)
+    return _CACHE
+
+
+def ref_decode(levels, strides, nc, embed_dim=0, state_classes=0):
+    """Run the reference's own Detect/JDE._inference (head.py:100-131 / :214-249) on raw level logits."""
+    import torch
+
+    _, _, head = load()
+    ch = tuple(64 for _ in levels)
+    with torch.no_grad():
+        if embed_dim:
+            m = head.JDE(nc=nc, embed_dim=embed_dim, state_classes=(state_classes or None), ch=ch)
+        else:
+            m = head.Detect(nc=nc, ch=ch)
+        m.stride = torch.tensor([float(s) for s in strides])
+        m.eval()
+        return m._inference([x.clone() for x in levels])
+
+
+def ref_nms(prediction, **kw):
+    """Run the reference's own ops.non_max_suppression (utils/ops.py:167-316) on a clone of `prediction`."""
+    ops, _, _ = load()
+    kw.setdefault("max_time_img", 1e9)  # never hit the soft time limit (ops.py:312-314)
+    return ops.non_max_suppression(prediction.clone(), **kw)
