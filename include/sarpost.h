@@ -1,0 +1,160 @@
+/*
+ * sarpost.h — C ABI of libsarpost.so: B200 (sm_100a) detection post-processing for SAR-YOLO.
+ *
+ * The reference (HaoqianSong/SAR-YOLO, an Ultralytics 8.3.63 fork) has no FFI on this path: the
+ * boundary is two Python callables.  Each entry point below names the reference interface it
+ * replaces (paths relative to /root/reference/ultralytics).  INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; device buffers are raw `void*` / typed pointers, streams are `void*`
+ *     holding a cudaStream_t (NULL = legacy default stream);
+ *   - every function returns 0 on success, a negative SARPOST_E* code on failure; the message is
+ *     available (per thread) from sarpost_last_error();
+ *   - no function synchronises the device except the *_host entry points; all work is enqueued on
+ *     the given stream; the library keeps no global mutable state (re-entrant, one workspace per call);
+ *   - all tensors fp32, contiguous, row-major.
+ */
+#ifndef SARPOST_H_
+#define SARPOST_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SARPOST_VERSION 100 /* 0.1.0 */
+#define SARPOST_MAX_LEVELS 8
+#define SARPOST_MAX_CLASSES 2048 /* upper bound for nc (class-filter bitmap lives in kernel params) */
+
+#define SARPOST_OK 0
+#define SARPOST_EINVAL (-1)    /* bad argument */
+#define SARPOST_ECUDA (-2)     /* CUDA runtime error (message holds cudaGetErrorString) */
+#define SARPOST_EWORKSPACE (-3)/* workspace too small */
+#define SARPOST_EUNSUPPORTED (-4)
+
+/*
+ * Raw Detect/JDE head output: the list `x` handed to Detect._inference (nn/modules/head.py:100) /
+ * JDE._inference (:214) — one (B, no, H_l, W_l) tensor per level, channel order
+ * box[4*reg_max] | cls[nc] | extras_raw[n_extra_raw] | extras_sigmoid[n_extra_sigmoid]
+ * (head.py:204-206, :232-235; JDE: 256 raw embedding + 6 state logits).
+ */
+typedef struct sarpost_head {
+    int32_t nl;              /* number of levels, 1..SARPOST_MAX_LEVELS */
+    int32_t batch;           /* B */
+    int32_t no;              /* channels per anchor = 4*reg_max + nc + n_extra_raw + n_extra_sigmoid */
+    int32_t nc;              /* number of classes */
+    int32_t reg_max;         /* DFL bins per side; only 16 is supported (head.py:39) */
+    int32_t n_extra_raw;     /* extras copied through unchanged (JDE embedding, head.py:247) */
+    int32_t n_extra_sigmoid; /* extras passed through sigmoid (JDE state, head.py:247) */
+    int32_t h[SARPOST_MAX_LEVELS];
+    int32_t w[SARPOST_MAX_LEVELS];
+    float stride[SARPOST_MAX_LEVELS]; /* Detect.stride (head.py:41) */
+    const void *data[SARPOST_MAX_LEVELS]; /* device (or, for *_host calls, host) pointers */
+} sarpost_head_t;
+
+/* Keyword arguments of ops.non_max_suppression (utils/ops.py:167-182). */
+typedef struct sarpost_nms_params {
+    float conf_thres;      /* compared in fp32: score > (float)conf_thres (ops.py:234,271,275) */
+    double iou_thres;      /* compared in double against the fp32 IoU (torchvision CPU nms) */
+    int32_t agnostic;      /* ops.py:289 */
+    int32_t multi_label;   /* ops.py:239,270-272 (only effective when nc > 1) */
+    int32_t max_det;       /* ops.py:297 */
+    int32_t max_nms;       /* ops.py:285-286 */
+    float max_wh;          /* ops.py:289,295 class offset = cls * max_wh */
+    const int32_t *classes;/* HOST pointer to the `classes` filter (ops.py:278-279) or NULL */
+    int32_t n_classes;
+} sarpost_nms_params_t;
+
+/* Last error message of the calling thread ("" if none). */
+const char *sarpost_last_error(void);
+int32_t sarpost_version(void);
+
+/*
+ * Bytes of device scratch sarpost_nms_decoded / sarpost_fused need (an upper bound valid for any
+ * split of `anchors` = total anchors A per image into <= SARPOST_MAX_LEVELS levels), and the same
+ * for sarpost_merge_tiles.  Negative = error code.
+ */
+int64_t sarpost_workspace_bytes(int32_t batch, int64_t anchors, int32_t nc, int32_t multi_label,
+                                int32_t max_det);
+int64_t sarpost_merge_workspace_bytes(int32_t n_frames, int32_t tiles_per_frame, int32_t dets_per_tile,
+                                      int32_t max_det);
+
+/*
+ * Replaces Detect._inference / JDE._inference (nn/modules/head.py:100-131, :214-249) including
+ * DFL (nn/modules/block.py:77-80), make_anchors and dist2bbox (utils/tal.py:366-390).
+ * y: device (B, 4 + nc + n_extra_raw + n_extra_sigmoid, A) fp32, A = sum_l H_l*W_l.
+ */
+int32_t sarpost_decode(const sarpost_head_t *head, float *y, void *stream);
+
+/*
+ * Replaces ops.non_max_suppression (utils/ops.py:167-316, non-rotated branch) on an already
+ * decoded prediction (B, C, A), C = 4 + nc + nm, rows cx,cy,w,h | nc probabilities | nm extras.
+ *   out        device (B, max_det, 6 + nm): x1,y1,x2,y2,conf,cls,extras — rows [0, counts[b]) valid,
+ *              in descending confidence; rows beyond are left untouched
+ *   counts     device (B) int32
+ *   kept_index device (B, max_det) int32 or NULL: anchor*nc + class of every output row
+ * The input is not modified (the reference rewrites prediction[..., :4] in place, ops.py:243-244).
+ */
+int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t channels, int64_t anchors,
+                            int32_t nc, const sarpost_nms_params_t *params, float *out, int32_t *counts,
+                            int32_t *kept_index, void *workspace, int64_t workspace_bytes, void *stream);
+
+/*
+ * Decode + non_max_suppression in one pass from the raw level logits (head.py:214-249 followed by
+ * ops.py:167-316) without materialising y.  Output as sarpost_nms_decoded with
+ * nm = n_extra_raw + n_extra_sigmoid (extras are gathered only for the kept rows).
+ */
+int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *params, float *out,
+                      int32_t *counts, int32_t *kept_index, void *workspace, int64_t workspace_bytes,
+                      void *stream);
+
+/*
+ * Cross-tile merge for sliced (SAHI-style) inference: per frame, shift every tile's detections by
+ * the tile origin and run the same class-offset NMS (ops.py:289-297 semantics).
+ *   dets        device (n_frames*tiles_per_frame, dets_per_tile, row_len) rows x1,y1,x2,y2,conf,cls,...
+ *   det_counts  device (n_frames*tiles_per_frame) int32 valid rows per tile
+ *   origins     device (n_frames*tiles_per_frame, 2) fp32 (x0, y0) of each tile in frame pixels
+ *   out         device (n_frames, max_det, row_len); counts device (n_frames)
+ *   kept_index  device (n_frames, max_det) int32 or NULL: tile_in_frame*dets_per_tile + row
+ * conf_thres / multi_label / classes of `params` are ignored (rows were filtered per tile).
+ */
+int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const float *origins,
+                            int32_t n_frames, int32_t tiles_per_frame, int32_t dets_per_tile,
+                            int32_t row_len, const sarpost_nms_params_t *params, float *out,
+                            int32_t *counts, int32_t *kept_index, void *workspace,
+                            int64_t workspace_bytes, void *stream);
+
+/*
+ * End-to-end entry with HOST buffers (what a caller holding CPU tensors uses; timed as `e2e` by
+ * bench.py).  A context owns pinned staging, device buffers and streams for one head geometry.
+ * sarpost_fused_host copies only the channels the path reads (box + cls) host->device, runs the
+ * fused pipeline, copies counts/boxes/indices back, gathers the extras of the kept rows from the
+ * host tensors, and returns after the stream is idle.
+ *   head->data[l]  HOST pointers (pinned or pageable)
+ *   out            HOST (B, max_det, 6 + nm); counts HOST (B); kept_index HOST (B, max_det) or NULL
+ */
+typedef struct sarpost_host_ctx sarpost_host_ctx_t;
+int32_t sarpost_host_ctx_create(int32_t device, sarpost_host_ctx_t **ctx);
+void sarpost_host_ctx_destroy(sarpost_host_ctx_t *ctx);
+int32_t sarpost_fused_host(sarpost_host_ctx_t *ctx, const sarpost_head_t *head,
+                           const sarpost_nms_params_t *params, float *out, int32_t *counts,
+                           int32_t *kept_index);
+/* bytes moved by the last sarpost_fused_host call */
+int32_t sarpost_host_ctx_last_traffic(const sarpost_host_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
+
+/*
+ * Introspection for benchmarks/tests: number of kernels the last call on this thread launched, and
+ * optional per-stage CUDA-event timing.  When stage timing is enabled the calls record events around
+ * every stage on the caller's stream; sarpost_stage_times() synchronises those events and returns
+ * milliseconds for {candidates(K1), select+sort(K2), nms(K4), gather(K5)}.
+ */
+int32_t sarpost_last_launch_count(void);
+int32_t sarpost_set_stage_timing(int32_t enabled);
+int32_t sarpost_stage_times(float *ms4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SARPOST_H_ */

@@ -137,7 +137,8 @@ def non_max_suppression_ref(prediction: torch.Tensor, conf_thres: float = 0.25, 
     `return_index=True` additionally returns, per image, an int64 (n_i, 2) tensor of (anchor, class)
     identifying each output row in the input — the "kept-index set" the GPU path is checked against.
     """
-    nms_fn = nms_fn or nms_ref
+    if nms_fn is None:  # early stop after max_det keeps == truncating the full result (ops.py:297)
+        nms_fn = lambda b_, s_, t_: nms_ref(b_, s_, t_, max_keep=max_det)
     assert 0 <= conf_thres <= 1 and 0 <= iou_thres <= 1  # ops.py:217-218
     if isinstance(prediction, (list, tuple)):
         prediction = prediction[0]  # ops.py:219-220

@@ -1,0 +1,92 @@
+"""ctypes binding of libsarpost.so (C ABI declared in include/sarpost.h).
+
+The library is the product: if it is missing or does not load, importing this module raises —
+there is no Python/torch fallback for any entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsarpost.so")
+
+MAX_LEVELS = 8
+MAX_CLASSES = 2048
+
+OK, EINVAL, ECUDA, EWORKSPACE, EUNSUPPORTED = 0, -1, -2, -3, -4
+
+
+class Head(C.Structure):
+    """sarpost_head_t"""
+    _fields_ = [
+        ("nl", C.c_int32), ("batch", C.c_int32), ("no", C.c_int32), ("nc", C.c_int32), ("reg_max", C.c_int32),
+        ("n_extra_raw", C.c_int32), ("n_extra_sigmoid", C.c_int32),
+        ("h", C.c_int32 * MAX_LEVELS), ("w", C.c_int32 * MAX_LEVELS), ("stride", C.c_float * MAX_LEVELS),
+        ("data", C.c_void_p * MAX_LEVELS),
+    ]
+
+
+class NmsParams(C.Structure):
+    """sarpost_nms_params_t"""
+    _fields_ = [
+        ("conf_thres", C.c_float), ("iou_thres", C.c_double), ("agnostic", C.c_int32), ("multi_label", C.c_int32),
+        ("max_det", C.c_int32), ("max_nms", C.c_int32), ("max_wh", C.c_float),
+        ("classes", C.POINTER(C.c_int32)), ("n_classes", C.c_int32),
+    ]
+
+
+class SarpostError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsarpost error {code}: {msg}")
+        self.code = code
+
+
+# name -> (restype, argtypes); every symbol include/sarpost.h declares
+SYMBOLS = {
+    "sarpost_last_error": (C.c_char_p, []),
+    "sarpost_version": (C.c_int32, []),
+    "sarpost_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
+    "sarpost_merge_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "sarpost_decode": (C.c_int32, [C.POINTER(Head), C.c_void_p, C.c_void_p]),
+    "sarpost_nms_decoded": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(NmsParams),
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "sarpost_fused": (C.c_int32, [C.POINTER(Head), C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int64, C.c_void_p]),
+    "sarpost_merge_tiles": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_void_p]),
+    "sarpost_host_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
+    "sarpost_host_ctx_destroy": (None, [C.c_void_p]),
+    "sarpost_fused_host": (C.c_int32, [C.c_void_p, C.POINTER(Head), C.POINTER(NmsParams), C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+    "sarpost_host_ctx_last_traffic": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sarpost_last_launch_count": (C.c_int32, []),
+    "sarpost_set_stage_timing": (C.c_int32, [C.c_int32]),
+    "sarpost_stage_times": (C.c_int32, [C.POINTER(C.c_float)]),
+}
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"(nvcc -gencode arch=compute_100a,code=sm_100a). sarpost has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    return (lib.sarpost_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise SarpostError(int(rc), last_error())

@@ -1,0 +1,202 @@
+// host_ctx.inl — end-to-end entry with HOST buffers (included at the end of sarpost.cu).
+//
+// sarpost_fused_host: H2D of the box+cls channels only (the 262 JDE extras channels of every anchor
+// never cross PCIe), fused pipeline on the context's stream, D2H of counts / rows / indices; when the
+// head has extras, the raw extras of the <= max_det kept rows are packed from the host tensors (pure
+// memcpy, no arithmetic), sent to the device, finished there (sigmoid of the state channels,
+// head.py:247) and returned inside the output rows.
+
+namespace sarpost {
+
+struct ExtrasFinishParams {
+    const float *rows6;   // [B, max_det, 6]
+    const float *extras;  // [B, max_det, nm] raw
+    const int32_t *counts;
+    float *out;           // [B, max_det, 6+nm]
+    int32_t max_det, nm, n_extra_raw;
+};
+
+__global__ void __launch_bounds__(256) k_extras_finish(const __grid_constant__ ExtrasFinishParams p) {
+    const int b = blockIdx.y;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= p.max_det || r >= p.counts[b]) return;
+    const int64_t row = static_cast<int64_t>(b) * p.max_det + r;
+    float *o = p.out + row * (6 + p.nm);
+    if (lane < 6) o[lane] = p.rows6[row * 6 + lane];
+    for (int c = lane; c < p.nm; c += 32) {
+        const float v = p.extras[row * p.nm + c];
+        o[6 + c] = c < p.n_extra_raw ? v : sigmoid_rn(v);
+    }
+}
+
+struct Buf {
+    void *p = nullptr;
+    int64_t bytes = 0;
+    bool host = false;
+    int ensure(int64_t need) {
+        if (need <= bytes) return SARPOST_OK;
+        if (p) {
+            if (host) cudaFreeHost(p); else cudaFree(p);
+            p = nullptr;
+            bytes = 0;
+        }
+        const int64_t cap = need + need / 8;
+        cudaError_t e = host ? cudaMallocHost(&p, cap) : cudaMalloc(&p, cap);
+        if (e != cudaSuccess) return fail(SARPOST_ECUDA, "allocation of %lld bytes failed: %s", (long long)cap, cudaGetErrorString(e));
+        bytes = cap;
+        return SARPOST_OK;
+    }
+    void release() {
+        if (p) { if (host) cudaFreeHost(p); else cudaFree(p); }
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+}  // namespace sarpost
+
+struct sarpost_host_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    sarpost::Buf d_levels, d_ws, d_rows6, d_counts, d_kidx, d_extras, d_out;
+    sarpost::Buf h_rows6, h_counts, h_kidx, h_extras;
+    int64_t last_h2d = 0, last_d2h = 0;
+};
+
+extern "C" {
+
+int32_t sarpost_host_ctx_create(int32_t device, sarpost_host_ctx_t **ctx) {
+    if (!ctx) return fail(SARPOST_EINVAL, "ctx is NULL");
+    CUDA_TRY(cudaSetDevice(device));
+    sarpost_host_ctx *c = new sarpost_host_ctx();
+    c->device = device;
+    c->h_rows6.host = c->h_counts.host = c->h_kidx.host = c->h_extras.host = true;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return fail(SARPOST_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
+    *ctx = c;
+    return SARPOST_OK;
+}
+
+void sarpost_host_ctx_destroy(sarpost_host_ctx_t *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (sarpost::Buf *b : {&c->d_levels, &c->d_ws, &c->d_rows6, &c->d_counts, &c->d_kidx, &c->d_extras, &c->d_out,
+                            &c->h_rows6, &c->h_counts, &c->h_kidx, &c->h_extras})
+        b->release();
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int32_t sarpost_host_ctx_last_traffic(const sarpost_host_ctx_t *c, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (!c) return fail(SARPOST_EINVAL, "ctx is NULL");
+    if (h2d_bytes) *h2d_bytes = c->last_h2d;
+    if (d2h_bytes) *d2h_bytes = c->last_d2h;
+    return SARPOST_OK;
+}
+
+int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, const sarpost_nms_params_t *params,
+                           float *out, int32_t *counts, int32_t *kept_index) {
+    if (!c) return fail(SARPOST_EINVAL, "ctx is NULL");
+    HeadGeom g;
+    int64_t anchors = 0;
+    if (int rc = fill_geom(head, &g, &anchors)) return rc;
+    if (int rc = check_params(params, g.nc)) return rc;
+    if (!out || !counts) return fail(SARPOST_EINVAL, "NULL output pointer");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int B = g.batch, nch = 4 * kRegMax + g.nc, nm = g.n_extra_raw + g.n_extra_sig, max_det = params->max_det;
+    c->last_h2d = c->last_d2h = 0;
+
+    // device copy of the box+cls channels of every level
+    int64_t off[kMaxLevels + 1];
+    off[0] = 0;
+    for (int l = 0; l < g.nl; ++l) off[l + 1] = align_up(off[l] + static_cast<int64_t>(B) * nch * g.lvl_hw[l] * 4, 256);
+    if (int rc = c->d_levels.ensure(off[g.nl])) return rc;
+    sarpost_head_t hd = *head;
+    hd.no = nch;
+    hd.n_extra_raw = hd.n_extra_sigmoid = 0;
+    for (int l = 0; l < g.nl; ++l) {
+        char *dst = static_cast<char *>(c->d_levels.p) + off[l];
+        const int64_t width = static_cast<int64_t>(nch) * g.lvl_hw[l] * 4;
+        CUDA_TRY(cudaMemcpy2DAsync(dst, width, head->data[l], static_cast<int64_t>(g.no) * g.lvl_hw[l] * 4, width, B,
+                                   cudaMemcpyHostToDevice, s));
+        c->last_h2d += width * B;
+        hd.data[l] = dst;
+    }
+    const int64_t ws_bytes = sarpost_workspace_bytes(B, anchors, g.nc, params->multi_label, max_det);
+    if (ws_bytes < 0) return static_cast<int32_t>(ws_bytes);
+    if (int rc = c->d_ws.ensure(ws_bytes)) return rc;
+    const int64_t rows = static_cast<int64_t>(B) * max_det;
+    if (int rc = c->d_rows6.ensure(rows * 6 * 4)) return rc;
+    if (int rc = c->d_counts.ensure(B * 4)) return rc;
+    if (int rc = c->d_kidx.ensure(rows * 4)) return rc;
+    if (int rc = c->h_rows6.ensure(rows * 6 * 4)) return rc;
+    if (int rc = c->h_counts.ensure(B * 4)) return rc;
+    if (int rc = c->h_kidx.ensure(rows * 4)) return rc;
+
+    const int saved_launches_base = 0;
+    (void)saved_launches_base;
+    if (int rc = sarpost_fused(&hd, params, static_cast<float *>(c->d_rows6.p), static_cast<int32_t *>(c->d_counts.p),
+                               static_cast<int32_t *>(c->d_kidx.p), c->d_ws.p, c->d_ws.bytes, s))
+        return rc;
+    int launches = g_launches;
+    CUDA_TRY(cudaMemcpyAsync(c->h_counts.p, c->d_counts.p, B * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(c->h_kidx.p, c->d_kidx.p, rows * 4, cudaMemcpyDeviceToHost, s));
+    c->last_d2h += B * 4 + rows * 4;
+    if (nm == 0) {
+        CUDA_TRY(cudaMemcpyAsync(c->h_rows6.p, c->d_rows6.p, rows * 6 * 4, cudaMemcpyDeviceToHost, s));
+        c->last_d2h += rows * 6 * 4;
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    const int32_t *hc = static_cast<const int32_t *>(c->h_counts.p);
+    const int32_t *hk = static_cast<const int32_t *>(c->h_kidx.p);
+    memcpy(counts, hc, B * 4);
+    if (kept_index) memcpy(kept_index, hk, rows * 4);
+    if (nm == 0) {
+        memcpy(out, c->h_rows6.p, rows * 6 * 4);
+        g_launches = launches;
+        return SARPOST_OK;
+    }
+    // pack the raw extras of the kept rows from the host tensors (memcpy only)
+    if (int rc = c->h_extras.ensure(rows * nm * 4)) return rc;
+    if (int rc = c->d_extras.ensure(rows * nm * 4)) return rc;
+    if (int rc = c->d_out.ensure(rows * (6 + nm) * 4)) return rc;
+    float *he = static_cast<float *>(c->h_extras.p);
+    for (int b = 0; b < B; ++b) {
+        for (int r = 0; r < hc[b]; ++r) {
+            const uint32_t key = static_cast<uint32_t>(hk[static_cast<int64_t>(b) * max_det + r]);
+            const uint32_t anchor = key / static_cast<uint32_t>(g.nc);
+            int l = 0;
+            while (l + 1 < g.nl && anchor >= static_cast<uint32_t>(g.lvl_aoff[l + 1])) ++l;
+            const int64_t hw = g.lvl_hw[l];
+            const float *src = static_cast<const float *>(head->data[l]) + (static_cast<int64_t>(b) * g.no + nch) * hw + (anchor - g.lvl_aoff[l]);
+            float *dst = he + (static_cast<int64_t>(b) * max_det + r) * nm;
+            for (int m = 0; m < nm; ++m) dst[m] = src[static_cast<int64_t>(m) * hw];
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->d_extras.p, he, rows * nm * 4, cudaMemcpyHostToDevice, s));
+    c->last_h2d += rows * nm * 4;
+    ExtrasFinishParams ep;
+    ep.rows6 = static_cast<const float *>(c->d_rows6.p);
+    ep.extras = static_cast<const float *>(c->d_extras.p);
+    ep.counts = static_cast<const int32_t *>(c->d_counts.p);
+    ep.out = static_cast<float *>(c->d_out.p);
+    ep.max_det = max_det;
+    ep.nm = nm;
+    ep.n_extra_raw = g.n_extra_raw;
+    k_extras_finish<<<dim3((max_det + 7) / 8, B), 256, 0, s>>>(ep);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, c->d_out.p, rows * (6 + nm) * 4, cudaMemcpyDeviceToHost, s));
+    c->last_d2h += rows * (6 + nm) * 4;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    g_launches = launches;
+    return SARPOST_OK;
+}
+
+}  // extern "C"

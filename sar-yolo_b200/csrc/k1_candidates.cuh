@@ -1,0 +1,345 @@
+// k1_candidates.cuh — stage K1: raw head logits (or a decoded prediction) -> candidate store.
+//
+// Replaces, in one pass over the logits:
+//   head.py:218-249   level concat, DFL softmax-expectation (block.py:77-80), make_anchors
+//                     (tal.py:366-378), dist2bbox (tal.py:381-390), * stride, cls.sigmoid()
+//   ops.py:234        candidate mask  amax(cls) > conf
+//   ops.py:241-246    xywh -> xyxy (ops.py:416-433)
+//   ops.py:268-279    best-class (first max) or multi-label expansion, `classes` filter
+// Output = tile-segmented candidate store (common.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace sarpost {
+
+struct HeadGeom {
+    int32_t nl, batch, no, nc, n_extra_raw, n_extra_sig;
+    int32_t tpi;                           // tiles per image (levels never share a tile)
+    int32_t lvl_tile_begin[kMaxLevels + 1];
+    int32_t lvl_hw[kMaxLevels];
+    int32_t lvl_w[kMaxLevels];
+    int32_t lvl_aoff[kMaxLevels + 1];      // first global anchor index of the level; [nl] = A
+    float lvl_stride[kMaxLevels];
+    const float *lvl_ptr[kMaxLevels];
+};
+
+struct CandFilter {
+    float conf;            // (float)conf_thres
+    int32_t multi_label;   // already AND-ed with nc > 1 (ops.py:239)
+    int32_t has_cls_filter;
+    uint32_t cls_allow[kClsWords];
+};
+
+__device__ __forceinline__ bool cls_allowed(const CandFilter &f, int j) {
+    return !f.has_cls_filter || ((f.cls_allow[j >> 5] >> (j & 31)) & 1u);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// DFL expectation of one box side from 16 logits (block.py:77-80): sum_k k*softmax_k.
+// exp(v-m) is evaluated as 2^(v*L - m*L) with one FFMA + one MUFU.EX2; the common factor
+// 2^(rounding of m*L) cancels in the ratio.
+template <class Acc>
+__device__ __forceinline__ float dfl_side(const Acc &acc, int c0) {
+    float v[kRegMax];
+#pragma unroll
+    for (int k = 0; k < kRegMax; ++k) v[k] = acc(c0 + k);
+    float m = v[0];
+#pragma unroll
+    for (int k = 1; k < kRegMax; ++k) m = fmaxf(m, v[k]);
+    constexpr float kLog2e = 1.4426950408889634f;
+    const float nml = -m * kLog2e;
+    float sum = 0.0f, wsum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kRegMax; ++k) {
+        const float e = ex2_approx(fmaf(v[k], kLog2e, nml));
+        sum += e;
+        wsum = fmaf(static_cast<float>(k), e, wsum);
+    }
+    return __fdiv_rn(wsum, sum);
+}
+
+// Anchor/stride decode in the reference's operation order (tal.py:381-390, head.py:245), every
+// step an individually rounded fp32 op.  Returns xywh in pixels.
+template <class Acc>
+__device__ __forceinline__ float4 decode_xywh(const Acc &acc, int x, int y, float stride) {
+    const float dl = dfl_side(acc, 0), dt = dfl_side(acc, kRegMax), dr = dfl_side(acc, 2 * kRegMax),
+                db = dfl_side(acc, 3 * kRegMax);
+    const float ax = __fadd_rn(static_cast<float>(x), 0.5f), ay = __fadd_rn(static_cast<float>(y), 0.5f);
+    const float x1 = __fsub_rn(ax, dl), y1 = __fsub_rn(ay, dt);
+    const float x2 = __fadd_rn(ax, dr), y2 = __fadd_rn(ay, db);
+    float4 o;
+    o.x = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), stride);
+    o.y = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), stride);
+    o.z = __fmul_rn(__fsub_rn(x2, x1), stride);
+    o.w = __fmul_rn(__fsub_rn(y2, y1), stride);
+    return o;
+}
+
+// ops.py:416-433
+__device__ __forceinline__ float4 xywh2xyxy_rn(const float4 c) {
+    const float hw = __fmul_rn(c.z, 0.5f), hh = __fmul_rn(c.w, 0.5f);
+    return make_float4(__fsub_rn(c.x, hw), __fsub_rn(c.y, hh), __fadd_rn(c.x, hw), __fadd_rn(c.y, hh));
+}
+
+// Block-wide (kTileA threads) ordered emission of this tile's candidates.
+//   score(j): class probability j of this thread's anchor.
+// scratch: int[8] shared.  Contains two __syncthreads().
+template <class ScoreFn>
+__device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, uint32_t anchor, int nc,
+                                                const CandFilter &f, const ScoreFn &score, const CandStore &st,
+                                                int b, int tile_in_image, int *scratch) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cnt = 0;
+    float best = 0.0f;
+    int bj = 0;
+    if (valid) {
+        if (f.multi_label) {
+            for (int j = 0; j < nc; ++j) cnt += (score(j) > f.conf) && cls_allowed(f, j);
+        } else {
+            best = score(0);
+            for (int j = 1; j < nc; ++j) {
+                const float p = score(j);
+                if (p > best) { best = p; bj = j; }  // strict >: first max wins (ops.py:274)
+            }
+            cnt = (best > f.conf) && cls_allowed(f, bj);
+        }
+    }
+    // exclusive scan of cnt over the block
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += n;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int w = 0; w < kTileA / 32; ++w) base += (w < warp) ? scratch[w] : 0;
+    if (tid == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kTileA / 32; ++w) tot += scratch[w];
+        st.tile_count[static_cast<int64_t>(b) * st.tpi + tile_in_image] = tot;
+    }
+    int64_t pos = static_cast<int64_t>(b) * st.cap + static_cast<int64_t>(tile_in_image) * st.region + base + (inc - cnt);
+    if (cnt) {
+        if (f.multi_label) {
+            for (int j = 0; j < nc; ++j) {
+                const float p = score(j);
+                if ((p > f.conf) && cls_allowed(f, j)) {
+                    st.box[pos] = xyxy;
+                    st.score[pos] = p;
+                    st.key[pos] = anchor * static_cast<uint32_t>(nc) + static_cast<uint32_t>(j);
+                    ++pos;
+                }
+            }
+        } else {
+            st.box[pos] = xyxy;
+            st.score[pos] = best;
+            st.key[pos] = anchor * static_cast<uint32_t>(nc) + static_cast<uint32_t>(bj);
+        }
+    }
+    __syncthreads();  // scratch reusable, and (TMA kernel) every read of the stage buffer is done
+}
+
+// Which level does tile r (index within an image) belong to.
+__device__ __forceinline__ int tile_level(const HeadGeom &g, int r) {
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i) l += (i < g.nl && r >= g.lvl_tile_begin[i]) ? 1 : 0;
+    return l;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 (TMA): persistent CTAs, kTileA threads, multi-stage mbarrier ring.  One TMA box per tile =
+// {kTileA anchors, 4*reg_max + nc channels, 1 image} landing as smem[channel][anchor]: thread t
+// reads column t -> conflict-free, and the extras channels are never fetched.
+// ---------------------------------------------------------------------------------------------
+struct K1TmaParams {
+    CUtensorMap maps[kMaxLevels];
+    HeadGeom g;
+    CandFilter f;
+    CandStore st;
+    int32_t stages;
+    int32_t n_tiles;  // B * tpi
+};
+
+constexpr int kMaxStages = 8;
+
+__global__ void __launch_bounds__(kTileA, 3) k1_fused_tma(const __grid_constant__ K1TmaParams p) {
+    extern __shared__ unsigned char dyn_smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ int scratch[8];
+    const int tid = threadIdx.x;
+    const int nch = 4 * kRegMax + p.g.nc;
+    const uint32_t stage_bytes = static_cast<uint32_t>(nch) * kTileA * sizeof(float);
+    unsigned char *dyn = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn_smem_raw) + 127) & ~uintptr_t(127));
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) mbar_init(&full_bar[s], 1);
+        fence_barrier_init();
+        for (int l = 0; l < p.g.nl; ++l) tma_prefetch_desc(&p.maps[l]);
+    }
+    __syncthreads();
+
+    const int first = blockIdx.x, step = gridDim.x;
+    const int n_my = first < p.n_tiles ? (p.n_tiles - first + step - 1) / step : 0;
+
+    auto issue = [&](int k) {
+        const int t = first + k * step;
+        const int b = t / p.g.tpi, r = t - b * p.g.tpi;
+        const int l = tile_level(p.g, r);
+        const int a0 = (r - p.g.lvl_tile_begin[l]) * kTileA;
+        const int s = k % p.stages;
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        tma_load_3d(dyn + static_cast<size_t>(s) * stage_bytes, &p.maps[l], a0, 0, b, &full_bar[s]);
+    };
+    if (tid == 0)
+        for (int k = 0; k < p.stages && k < n_my; ++k) issue(k);
+
+    for (int k = 0; k < n_my; ++k) {
+        const int t = first + k * step;
+        const int b = t / p.g.tpi, r = t - b * p.g.tpi;
+        const int l = tile_level(p.g, r);
+        const int pos = (r - p.g.lvl_tile_begin[l]) * kTileA + tid;  // position inside the level
+        const bool valid = pos < p.g.lvl_hw[l];
+        const int s = k % p.stages;
+        mbar_wait(&full_bar[s], static_cast<uint32_t>((k / p.stages) & 1));
+        const float *buf = reinterpret_cast<const float *>(dyn + static_cast<size_t>(s) * stage_bytes) + tid;
+        auto acc = [&](int c) { return buf[c * kTileA]; };
+        const int w = p.g.lvl_w[l];
+        const int yy = pos / w, xx = pos - yy * w;
+        const float4 xyxy = xywh2xyxy_rn(decode_xywh(acc, xx, yy, p.g.lvl_stride[l]));
+        auto score = [&](int j) { return sigmoid_rn(buf[(4 * kRegMax + j) * kTileA]); };
+        emit_candidates(valid, xyxy, static_cast<uint32_t>(p.g.lvl_aoff[l] + pos), p.g.nc, p.f, score, p.st, b, r, scratch);
+        // emit_candidates ended with __syncthreads(): stage s is free again
+        if (tid == 0 && k + p.stages < n_my) issue(k + p.stages);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 (LDG): same math with direct coalesced global loads; used when a level cannot be described
+// by a tensor map (H*W*4 not a multiple of 16 bytes — odd rect-inference levels — unaligned base,
+// or 4*reg_max + nc > 256 box rows).  grid = (tpi, B).
+// ---------------------------------------------------------------------------------------------
+struct K1LdgParams {
+    HeadGeom g;
+    CandFilter f;
+    CandStore st;
+};
+
+__global__ void __launch_bounds__(kTileA) k1_fused_ldg(const __grid_constant__ K1LdgParams p) {
+    __shared__ int scratch[8];
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int l = tile_level(p.g, r);
+    const int hw = p.g.lvl_hw[l];
+    const int pos = (r - p.g.lvl_tile_begin[l]) * kTileA + threadIdx.x;
+    const bool valid = pos < hw;
+    const int pc = valid ? pos : hw - 1;
+    const float *base = p.g.lvl_ptr[l] + static_cast<int64_t>(b) * p.g.no * hw + pc;
+    auto acc = [&](int c) { return __ldg(base + static_cast<int64_t>(c) * hw); };
+    const int w = p.g.lvl_w[l];
+    const int yy = pc / w, xx = pc - yy * w;
+    const float4 xyxy = xywh2xyxy_rn(decode_xywh(acc, xx, yy, p.g.lvl_stride[l]));
+    auto score = [&](int j) { return sigmoid_rn(acc(4 * kRegMax + j)); };
+    emit_candidates(valid, xyxy, static_cast<uint32_t>(p.g.lvl_aoff[l] + pc), p.g.nc, p.f, score, p.st, b, r, scratch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 (decoded): candidates from an already decoded prediction (B, C, A) — the tensor
+// ops.non_max_suppression receives (ops.py:167).  grid = (ceil(A/kTileA), B).
+// ---------------------------------------------------------------------------------------------
+struct K1DecodedParams {
+    const float *pred;
+    int32_t channels, nc;
+    int64_t anchors;
+    CandFilter f;
+    CandStore st;
+};
+
+__global__ void __launch_bounds__(kTileA) k1_decoded(const __grid_constant__ K1DecodedParams p) {
+    __shared__ int scratch[8];
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int64_t a = static_cast<int64_t>(r) * kTileA + threadIdx.x;
+    const bool valid = a < p.anchors;
+    const int64_t ac = valid ? a : p.anchors - 1;
+    const float *base = p.pred + static_cast<int64_t>(b) * p.channels * p.anchors + ac;
+    const float4 xywh = make_float4(__ldg(base), __ldg(base + p.anchors), __ldg(base + 2 * p.anchors),
+                                    __ldg(base + 3 * p.anchors));
+    const float4 xyxy = xywh2xyxy_rn(xywh);
+    auto score = [&](int j) { return __ldg(base + static_cast<int64_t>(4 + j) * p.anchors); };
+    emit_candidates(valid, xyxy, static_cast<uint32_t>(ac), p.nc, p.f, score, p.st, b, r, scratch);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 (merge): candidates for the cross-tile merge — one block per SAHI tile; rows are already
+// filtered detections (x1,y1,x2,y2,conf,cls,...) which are shifted by the tile origin.
+// grid = (tiles_per_frame, n_frames), blockDim = 128.
+// ---------------------------------------------------------------------------------------------
+struct K1MergeParams {
+    const float *dets;
+    const int32_t *det_counts;
+    const float *origins;
+    int32_t dets_per_tile, row_len;
+    float *cls;     // [n_frames*cap] class id of every slot (NMS class offset)
+    CandStore st;   // region = dets_per_tile, tpi = tiles_per_frame
+};
+
+__global__ void __launch_bounds__(128) k1_merge(const __grid_constant__ K1MergeParams p) {
+    const int t = blockIdx.x, f = blockIdx.y;
+    const int64_t tile = static_cast<int64_t>(f) * p.st.tpi + t;
+    int n = p.det_counts[tile];
+    n = n < 0 ? 0 : (n > p.dets_per_tile ? p.dets_per_tile : n);
+    const float ox = p.origins[2 * tile], oy = p.origins[2 * tile + 1];
+    const int64_t base = static_cast<int64_t>(f) * p.st.cap + static_cast<int64_t>(t) * p.st.region;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float *row = p.dets + (tile * p.dets_per_tile + i) * p.row_len;
+        p.st.box[base + i] = make_float4(__fadd_rn(row[0], ox), __fadd_rn(row[1], oy), __fadd_rn(row[2], ox),
+                                         __fadd_rn(row[3], oy));
+        p.st.score[base + i] = row[4];
+        p.cls[base + i] = row[5];
+        p.st.key[base + i] = static_cast<uint32_t>(t) * p.dets_per_tile + i;
+    }
+    if (threadIdx.x == 0) p.st.tile_count[tile] = n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decode to y (API-exact Detect._inference / JDE._inference, head.py:100-131, :214-249):
+// y (B, 4+nc+n_extra_raw+n_extra_sig, A).  grid = (tpi, B), blockDim = kTileA.
+// ---------------------------------------------------------------------------------------------
+struct DecodeYParams {
+    HeadGeom g;
+    float *y;
+    int64_t anchors;
+};
+
+__global__ void __launch_bounds__(kTileA) k_decode_y(const __grid_constant__ DecodeYParams p) {
+    const int r = blockIdx.x, b = blockIdx.y;
+    const int l = tile_level(p.g, r);
+    const int hw = p.g.lvl_hw[l];
+    const int pos = (r - p.g.lvl_tile_begin[l]) * kTileA + threadIdx.x;
+    if (pos >= hw) return;
+    const float *base = p.g.lvl_ptr[l] + static_cast<int64_t>(b) * p.g.no * hw + pos;
+    auto acc = [&](int c) { return __ldg(base + static_cast<int64_t>(c) * hw); };
+    const int w = p.g.lvl_w[l];
+    const int yy = pos / w, xx = pos - yy * w;
+    const float4 o = decode_xywh(acc, xx, yy, p.g.lvl_stride[l]);
+    const int cout = 4 + p.g.nc + p.g.n_extra_raw + p.g.n_extra_sig;
+    float *yo = p.y + static_cast<int64_t>(b) * cout * p.anchors + p.g.lvl_aoff[l] + pos;
+    yo[0] = o.x;
+    yo[p.anchors] = o.y;
+    yo[2 * p.anchors] = o.z;
+    yo[3 * p.anchors] = o.w;
+    int ci = 4 * kRegMax, co = 4;
+    for (int j = 0; j < p.g.nc; ++j, ++ci, ++co) yo[co * p.anchors] = sigmoid_rn(acc(ci));
+    for (int j = 0; j < p.g.n_extra_raw; ++j, ++ci, ++co) yo[co * p.anchors] = acc(ci);
+    for (int j = 0; j < p.g.n_extra_sig; ++j, ++ci, ++co) yo[co * p.anchors] = sigmoid_rn(acc(ci));
+}
+
+}  // namespace sarpost

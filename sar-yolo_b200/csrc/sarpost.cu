@@ -1,0 +1,514 @@
+// sarpost.cu — C ABI (include/sarpost.h) and host-side orchestration of the K1..K5 pipeline.
+//
+//   K1 candidates   k1_fused_tma | k1_fused_ldg | k1_decoded | k1_merge     (k1_candidates.cuh)
+//   K2 select+sort  k2_select_sort                                           (k2_select_sort.cuh)
+//   K4 NMS          k4_nms                                                   (k4_nms.cuh)
+//   K5 gather       k5_gather                                                (k4_nms.cuh)
+//
+// No torch types, no exceptions across the ABI, no global mutable state (thread-local error string and
+// instrumentation only).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "k1_candidates.cuh"
+#include "k2_select_sort.cuh"
+#include "k4_nms.cuh"
+
+namespace sarpost {
+
+// ------------------------------------------------------------------------------------------------
+// thread-local error / instrumentation state
+// ------------------------------------------------------------------------------------------------
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+thread_local int g_timing = 0;
+thread_local cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+thread_local int g_ev_valid = 0;
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(SARPOST_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+static void stage_mark(int i, cudaStream_t s) {
+    if (!g_timing) return;
+    if (!g_ev[0])
+        for (auto &e : g_ev) cudaEventCreate(&e);
+    cudaEventRecord(g_ev[i], s);
+    g_ev_valid = i;
+}
+
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------------
+struct Layout {
+    int64_t box, score, key, cls, key_a, val_a, key_b, val_b, tile_count, tile_off, n_sorted, kept_slot, total;
+};
+
+static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_det, bool with_cls) {
+    Layout L;
+    int64_t o = 0;
+    auto take = [&](int64_t bytes) {
+        const int64_t at = o;
+        o = align_up(o + bytes, 256);
+        return at;
+    };
+    const int64_t slots = batch * cap;
+    L.box = take(slots * 16);
+    L.score = take(slots * 4);
+    L.key = take(slots * 4);
+    L.cls = with_cls ? take(slots * 4) : -1;
+    L.key_a = take(slots * 4);
+    L.val_a = take(slots * 4);
+    L.key_b = take(slots * 4);
+    L.val_b = take(slots * 4);
+    L.tile_count = take(batch * tpi * 4);
+    L.tile_off = take(batch * (tpi + 1) * 4);
+    L.n_sorted = take(batch * 4);
+    L.kept_slot = take(batch * max_det * 4);
+    L.total = o;
+    return L;
+}
+
+struct Pipeline {
+    CandStore st;
+    uint32_t *key_a, *val_a, *key_b, *val_b;
+    int32_t *tile_off, *n_sorted;
+    uint32_t *kept_slot;
+    float *cls;
+};
+
+static int bind_workspace(void *ws, int64_t ws_bytes, int64_t batch, int64_t cap, int64_t tpi, int64_t region,
+                          int64_t max_det, bool with_cls, Pipeline *P) {
+    const Layout L = make_layout(batch, cap, tpi, max_det, with_cls);
+    if (!ws) return fail(SARPOST_EINVAL, "workspace is NULL");
+    if (reinterpret_cast<uintptr_t>(ws) % 256) return fail(SARPOST_EINVAL, "workspace must be 256-byte aligned");
+    if (ws_bytes < L.total) return fail(SARPOST_EWORKSPACE, "workspace too small: %lld < %lld bytes", (long long)ws_bytes, (long long)L.total);
+    char *base = static_cast<char *>(ws);
+    P->st.box = reinterpret_cast<float4 *>(base + L.box);
+    P->st.score = reinterpret_cast<float *>(base + L.score);
+    P->st.key = reinterpret_cast<uint32_t *>(base + L.key);
+    P->st.tile_count = reinterpret_cast<int32_t *>(base + L.tile_count);
+    P->st.cap = cap;
+    P->st.tpi = static_cast<int32_t>(tpi);
+    P->st.region = static_cast<int32_t>(region);
+    P->key_a = reinterpret_cast<uint32_t *>(base + L.key_a);
+    P->val_a = reinterpret_cast<uint32_t *>(base + L.val_a);
+    P->key_b = reinterpret_cast<uint32_t *>(base + L.key_b);
+    P->val_b = reinterpret_cast<uint32_t *>(base + L.val_b);
+    P->tile_off = reinterpret_cast<int32_t *>(base + L.tile_off);
+    P->n_sorted = reinterpret_cast<int32_t *>(base + L.n_sorted);
+    P->kept_slot = reinterpret_cast<uint32_t *>(base + L.kept_slot);
+    P->cls = with_cls ? reinterpret_cast<float *>(base + L.cls) : nullptr;
+    return SARPOST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// parameter checking helpers
+// ------------------------------------------------------------------------------------------------
+static int check_params(const sarpost_nms_params_t *p, int nc) {
+    if (!p) return fail(SARPOST_EINVAL, "params is NULL");
+    if (!(p->conf_thres >= 0.f && p->conf_thres <= 1.f)) return fail(SARPOST_EINVAL, "Invalid Confidence threshold %g, valid values are between 0.0 and 1.0", p->conf_thres);
+    if (!(p->iou_thres >= 0.0 && p->iou_thres <= 1.0)) return fail(SARPOST_EINVAL, "Invalid IoU %g, valid values are between 0.0 and 1.0", p->iou_thres);
+    if (p->max_det < 1 || p->max_det > 4096) return fail(SARPOST_EUNSUPPORTED, "max_det %d outside [1, 4096]", p->max_det);
+    if (p->max_nms < 1) return fail(SARPOST_EINVAL, "max_nms %d < 1", p->max_nms);
+    if (nc < 1 || nc > SARPOST_MAX_CLASSES) return fail(SARPOST_EUNSUPPORTED, "nc %d outside [1, %d]", nc, SARPOST_MAX_CLASSES);
+    if (p->n_classes < 0 || (p->n_classes > 0 && !p->classes)) return fail(SARPOST_EINVAL, "classes pointer/count mismatch");
+    return SARPOST_OK;
+}
+
+static void make_filter(const sarpost_nms_params_t *p, int nc, CandFilter *f) {
+    memset(f, 0, sizeof(*f));
+    f->conf = p->conf_thres;
+    f->multi_label = (p->multi_label && nc > 1) ? 1 : 0;  // ops.py:239
+    f->has_cls_filter = p->classes != nullptr ? 1 : 0;    // classes=[] keeps nothing, like (x[:,5:6]==classes).any(1)
+    for (int i = 0; i < p->n_classes; ++i) {
+        const int c = p->classes[i];
+        if (c >= 0 && c < nc) f->cls_allow[c >> 5] |= 1u << (c & 31);
+    }
+}
+
+// largest float <= thr : (double)iou > thr  <=>  iou > iou_thr_float(thr) for fp32 iou
+static float iou_thr_float(double thr) {
+    float t = static_cast<float>(thr);
+    if (static_cast<double>(t) > thr) t = nextafterf(t, -INFINITY);
+    return t;
+}
+
+static int fill_geom(const sarpost_head_t *h, HeadGeom *g, int64_t *anchors) {
+    if (!h) return fail(SARPOST_EINVAL, "head is NULL");
+    if (h->nl < 1 || h->nl > kMaxLevels) return fail(SARPOST_EINVAL, "nl %d outside [1, %d]", h->nl, kMaxLevels);
+    if (h->reg_max != kRegMax) return fail(SARPOST_EUNSUPPORTED, "reg_max %d unsupported (only 16, head.py:39)", h->reg_max);
+    if (h->batch < 1) return fail(SARPOST_EINVAL, "batch %d < 1", h->batch);
+    if (h->nc < 1 || h->nc > SARPOST_MAX_CLASSES) return fail(SARPOST_EUNSUPPORTED, "nc %d outside [1, %d]", h->nc, SARPOST_MAX_CLASSES);
+    if (h->n_extra_raw < 0 || h->n_extra_sigmoid < 0 || h->no != 4 * kRegMax + h->nc + h->n_extra_raw + h->n_extra_sigmoid)
+        return fail(SARPOST_EINVAL, "no %d != 4*reg_max + nc + extras (%d)", h->no, 4 * kRegMax + h->nc + h->n_extra_raw + h->n_extra_sigmoid);
+    memset(g, 0, sizeof(*g));
+    g->nl = h->nl;
+    g->batch = h->batch;
+    g->no = h->no;
+    g->nc = h->nc;
+    g->n_extra_raw = h->n_extra_raw;
+    g->n_extra_sig = h->n_extra_sigmoid;
+    int64_t a = 0, t = 0;
+    for (int l = 0; l < h->nl; ++l) {
+        if (h->h[l] < 1 || h->w[l] < 1) return fail(SARPOST_EINVAL, "level %d has empty shape %dx%d", l, h->h[l], h->w[l]);
+        if (!h->data[l]) return fail(SARPOST_EINVAL, "level %d data pointer is NULL", l);
+        const int64_t hw = static_cast<int64_t>(h->h[l]) * h->w[l];
+        g->lvl_tile_begin[l] = static_cast<int32_t>(t);
+        g->lvl_hw[l] = static_cast<int32_t>(hw);
+        g->lvl_w[l] = h->w[l];
+        g->lvl_aoff[l] = static_cast<int32_t>(a);
+        g->lvl_stride[l] = h->stride[l];
+        g->lvl_ptr[l] = static_cast<const float *>(h->data[l]);
+        a += hw;
+        t += (hw + kTileA - 1) / kTileA;
+    }
+    for (int l = h->nl; l <= kMaxLevels; ++l) g->lvl_tile_begin[l] = static_cast<int32_t>(t);
+    for (int l = h->nl; l <= kMaxLevels; ++l) g->lvl_aoff[l] = static_cast<int32_t>(a);
+    g->tpi = static_cast<int32_t>(t);
+    if (a * h->nc >= (1ll << 32)) return fail(SARPOST_EUNSUPPORTED, "anchors*nc = %lld does not fit 32 bits", (long long)(a * h->nc));
+    *anchors = a;
+    return SARPOST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point resolved through the runtime: no link against libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<PFN_encodeTiled>(p);
+    }();
+    return fn;
+}
+
+static bool tma_eligible(const HeadGeom &g) {
+    if (4 * kRegMax + g.nc > 256) return false;
+    for (int l = 0; l < g.nl; ++l) {
+        if ((static_cast<int64_t>(g.lvl_hw[l]) * 4) % 16) return false;
+        if (reinterpret_cast<uintptr_t>(g.lvl_ptr[l]) % 16) return false;
+    }
+    return get_encode_fn() != nullptr;
+}
+
+static int device_sm_count(int *sms, int *smem_optin) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    return SARPOST_OK;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stages
+// ------------------------------------------------------------------------------------------------
+static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandStore &st, cudaStream_t s) {
+    const int nch = 4 * kRegMax + g.nc;
+    const int64_t stage_bytes = static_cast<int64_t>(nch) * kTileA * 4;
+    int sms = 0, smem_optin = 0;
+    if (int rc = device_sm_count(&sms, &smem_optin)) return rc;
+    bool use_tma = tma_eligible(g) && !env_int("SARPOST_K1_FORCE_LDG", 0);
+    int stages = 0, ctas = 0;
+    if (use_tma) {
+        const int64_t sm_smem = 228 * 1024;
+        const int want_ctas = env_int("SARPOST_K1_CTAS", 3);
+        for (ctas = want_ctas; ctas >= 1; --ctas) {
+            const int64_t per_cta = sm_smem / ctas - 1024 /*driver reserve*/ - 512 /*static + align*/;
+            stages = static_cast<int>(per_cta / stage_bytes);
+            if (stages > kMaxStages) stages = kMaxStages;
+            if (stages >= 2) break;
+        }
+        const int forced = env_int("SARPOST_K1_STAGES", 0);
+        if (forced > 0) stages = forced > kMaxStages ? kMaxStages : forced;
+        if (ctas < 1 || stages < 2 || stages * stage_bytes + 128 > smem_optin) use_tma = false;
+    }
+    if (use_tma) {
+        K1TmaParams p;
+        memset(&p, 0, sizeof(p));
+        p.g = g;
+        p.f = f;
+        p.st = st;
+        p.stages = stages;
+        p.n_tiles = g.batch * g.tpi;
+        PFN_encodeTiled enc = get_encode_fn();
+        for (int l = 0; l < g.nl; ++l) {
+            const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.lvl_hw[l]), static_cast<cuuint64_t>(g.no), static_cast<cuuint64_t>(g.batch)};
+            const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lvl_hw[l]) * 4, static_cast<cuuint64_t>(g.lvl_hw[l]) * g.no * 4};
+            const cuuint32_t box[3] = {kTileA, static_cast<cuuint32_t>(nch), 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            const CUresult r = enc(&p.maps[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(g.lvl_ptr[l]), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(SARPOST_ECUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, static_cast<int>(r));
+        }
+        const int smem = static_cast<int>(stages * stage_bytes + 128);
+        CUDA_TRY(cudaFuncSetAttribute(k1_fused_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int grid = sms * ctas;
+        if (grid > p.n_tiles) grid = p.n_tiles;
+        k1_fused_tma<<<grid, kTileA, smem, s>>>(p);
+    } else {
+        K1LdgParams p;
+        memset(&p, 0, sizeof(p));
+        p.g = g;
+        p.f = f;
+        p.st = st;
+        k1_fused_ldg<<<dim3(g.tpi, g.batch), kTileA, 0, s>>>(p);
+    }
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return SARPOST_OK;
+}
+
+// K2 + K4 + K5 on a filled candidate store.
+static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, int nc, GatherParams gp, float *out,
+                    int32_t *counts, int32_t *kept_index, cudaStream_t s) {
+    SortParams sp;
+    sp.st = P.st;
+    sp.key_a = P.key_a;
+    sp.val_a = P.val_a;
+    sp.key_b = P.key_b;
+    sp.val_b = P.val_b;
+    sp.tile_off = P.tile_off;
+    sp.n_sorted = P.n_sorted;
+    sp.max_nms = prm->max_nms;
+    k2_select_sort<<<batch, kSortThreads, 0, s>>>(sp);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    stage_mark(2, s);
+
+    NmsParams np;
+    np.st = P.st;
+    np.sorted = P.val_a;
+    np.n_sorted = P.n_sorted;
+    np.kept_slot = P.kept_slot;
+    np.counts = counts;
+    np.max_det = prm->max_det;
+    np.nc = nc;
+    np.cls_override = P.cls;
+    np.max_wh = prm->agnostic ? 0.0f : prm->max_wh;
+    np.thr = iou_thr_float(prm->iou_thres);
+    const int nms_smem = prm->max_det * 24;
+    CUDA_TRY(cudaFuncSetAttribute(k4_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 24));
+    k4_nms<<<batch, kNmsThreads, nms_smem, s>>>(np);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    stage_mark(3, s);
+
+    gp.st = P.st;
+    gp.kept_slot = P.kept_slot;
+    gp.counts = counts;
+    gp.out = out;
+    gp.kept_index = kept_index;
+    gp.max_det = prm->max_det;
+    gp.nc = nc;
+    k5_gather<<<dim3((prm->max_det + kGatherWarps - 1) / kGatherWarps, batch), kGatherWarps * 32, 0, s>>>(gp);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    stage_mark(4, s);
+    return SARPOST_OK;
+}
+
+static int64_t tpi_upper_bound(int64_t anchors) { return (anchors + kTileA - 1) / kTileA + kMaxLevels; }
+
+}  // namespace sarpost
+
+using namespace sarpost;
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char *sarpost_last_error(void) { return g_err; }
+int32_t sarpost_version(void) { return SARPOST_VERSION; }
+int32_t sarpost_last_launch_count(void) { return g_launches; }
+
+int32_t sarpost_set_stage_timing(int32_t enabled) {
+    g_timing = enabled ? 1 : 0;
+    g_ev_valid = 0;
+    return SARPOST_OK;
+}
+
+int32_t sarpost_stage_times(float *ms4) {
+    if (!ms4) return fail(SARPOST_EINVAL, "ms4 is NULL");
+    if (!g_timing || g_ev_valid != 4) return fail(SARPOST_EINVAL, "no timed call recorded on this thread");
+    CUDA_TRY(cudaEventSynchronize(g_ev[4]));
+    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventElapsedTime(&ms4[i], g_ev[i], g_ev[i + 1]));
+    return SARPOST_OK;
+}
+
+int64_t sarpost_workspace_bytes(int32_t batch, int64_t anchors, int32_t nc, int32_t multi_label, int32_t max_det) {
+    if (batch < 1 || anchors < 1 || nc < 1 || max_det < 1) return fail(SARPOST_EINVAL, "bad workspace query");
+    const int64_t nc_eff = (multi_label && nc > 1) ? nc : 1;
+    const int64_t tpi = tpi_upper_bound(anchors);
+    return make_layout(batch, tpi * kTileA * nc_eff, tpi, max_det, false).total;
+}
+
+int64_t sarpost_merge_workspace_bytes(int32_t n_frames, int32_t tiles_per_frame, int32_t dets_per_tile, int32_t max_det) {
+    if (n_frames < 1 || tiles_per_frame < 1 || dets_per_tile < 1 || max_det < 1) return fail(SARPOST_EINVAL, "bad workspace query");
+    return make_layout(n_frames, static_cast<int64_t>(tiles_per_frame) * dets_per_tile, tiles_per_frame, max_det, true).total;
+}
+
+int32_t sarpost_decode(const sarpost_head_t *head, float *y, void *stream) {
+    g_launches = 0;
+    HeadGeom g;
+    int64_t anchors = 0;
+    if (int rc = fill_geom(head, &g, &anchors)) return rc;
+    if (!y) return fail(SARPOST_EINVAL, "y is NULL");
+    DecodeYParams p;
+    p.g = g;
+    p.y = y;
+    p.anchors = anchors;
+    k_decode_y<<<dim3(g.tpi, g.batch), kTileA, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return SARPOST_OK;
+}
+
+int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t channels, int64_t anchors, int32_t nc,
+                            const sarpost_nms_params_t *params, float *out, int32_t *counts, int32_t *kept_index,
+                            void *workspace, int64_t workspace_bytes, void *stream) {
+    g_launches = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (int rc = check_params(params, nc)) return rc;
+    if (!prediction || !out || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
+    if (batch < 1 || anchors < 1) return fail(SARPOST_EINVAL, "empty prediction (batch %d, anchors %lld)", batch, (long long)anchors);
+    if (channels < 4 + nc) return fail(SARPOST_EINVAL, "channels %d < 4 + nc (%d)", channels, 4 + nc);
+    if (anchors * nc >= (1ll << 32)) return fail(SARPOST_EUNSUPPORTED, "anchors*nc does not fit 32 bits");
+    CandFilter f;
+    make_filter(params, nc, &f);
+    const int64_t nc_eff = f.multi_label ? nc : 1;
+    const int64_t tpi = (anchors + kTileA - 1) / kTileA;
+    const int64_t region = kTileA * nc_eff;
+    Pipeline P;
+    if (int rc = bind_workspace(workspace, workspace_bytes, batch, tpi * region, tpi, region, params->max_det, false, &P)) return rc;
+
+    stage_mark(0, s);
+    K1DecodedParams kp;
+    kp.pred = prediction;
+    kp.channels = channels;
+    kp.nc = nc;
+    kp.anchors = anchors;
+    kp.f = f;
+    kp.st = P.st;
+    k1_decoded<<<dim3(static_cast<unsigned>(tpi), batch), kTileA, 0, s>>>(kp);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    stage_mark(1, s);
+
+    GatherParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.mode = 0;
+    gp.nm = channels - 4 - nc;
+    gp.pred = prediction;
+    gp.channels = channels;
+    gp.anchors = anchors;
+    return run_tail(P, batch, params, nc, gp, out, counts, kept_index, s);
+}
+
+int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *params, float *out, int32_t *counts,
+                      int32_t *kept_index, void *workspace, int64_t workspace_bytes, void *stream) {
+    g_launches = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    HeadGeom g;
+    int64_t anchors = 0;
+    if (int rc = fill_geom(head, &g, &anchors)) return rc;
+    if (int rc = check_params(params, g.nc)) return rc;
+    if (!out || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
+    CandFilter f;
+    make_filter(params, g.nc, &f);
+    const int64_t nc_eff = f.multi_label ? g.nc : 1;
+    const int64_t region = kTileA * nc_eff;
+    Pipeline P;
+    if (int rc = bind_workspace(workspace, workspace_bytes, g.batch, g.tpi * region, g.tpi, region, params->max_det, false, &P)) return rc;
+
+    stage_mark(0, s);
+    if (int rc = launch_k1_fused(g, f, P.st, s)) return rc;
+    stage_mark(1, s);
+
+    GatherParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.mode = 1;
+    gp.nm = g.n_extra_raw + g.n_extra_sig;
+    gp.nl = g.nl;
+    gp.no = g.no;
+    gp.n_extra_raw = g.n_extra_raw;
+    for (int l = 0; l <= kMaxLevels; ++l) gp.lvl_aoff[l] = g.lvl_aoff[l];
+    for (int l = 0; l < kMaxLevels; ++l) {
+        gp.lvl_hw[l] = g.lvl_hw[l];
+        gp.lvl_ptr[l] = g.lvl_ptr[l];
+    }
+    return run_tail(P, g.batch, params, g.nc, gp, out, counts, kept_index, s);
+}
+
+int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const float *origins, int32_t n_frames,
+                            int32_t tiles_per_frame, int32_t dets_per_tile, int32_t row_len,
+                            const sarpost_nms_params_t *params, float *out, int32_t *counts, int32_t *kept_index,
+                            void *workspace, int64_t workspace_bytes, void *stream) {
+    g_launches = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (int rc = check_params(params, 1)) return rc;
+    if (!dets || !det_counts || !origins || !out || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
+    if (n_frames < 1 || tiles_per_frame < 1 || dets_per_tile < 1 || row_len < 6) return fail(SARPOST_EINVAL, "bad merge geometry");
+    Pipeline P;
+    const int64_t cap = static_cast<int64_t>(tiles_per_frame) * dets_per_tile;
+    if (cap >= (1ll << 31)) return fail(SARPOST_EUNSUPPORTED, "too many detections per frame");
+    if (int rc = bind_workspace(workspace, workspace_bytes, n_frames, cap, tiles_per_frame, dets_per_tile, params->max_det, true, &P)) return rc;
+
+    stage_mark(0, s);
+    K1MergeParams kp;
+    kp.dets = dets;
+    kp.det_counts = det_counts;
+    kp.origins = origins;
+    kp.dets_per_tile = dets_per_tile;
+    kp.row_len = row_len;
+    kp.cls = P.cls;
+    kp.st = P.st;
+    k1_merge<<<dim3(tiles_per_frame, n_frames), 128, 0, s>>>(kp);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    stage_mark(1, s);
+
+    GatherParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.mode = 2;
+    gp.nm = row_len - 6;
+    gp.dets = dets;
+    gp.dets_per_tile = dets_per_tile;
+    gp.row_len = row_len;
+    return run_tail(P, n_frames, params, 1, gp, out, counts, kept_index, s);
+}
+
+}  // extern "C"
+
+#include "host_ctx.inl"

@@ -1,0 +1,84 @@
+"""Multi-GPU plumbing: batch / tile sharding and the one real exchange step.
+
+Images are independent, so ranks post-process disjoint slices of the batch with no data-path
+collective.  The only exchange is an all-gather of the per-image detection counts and the padded
+`(B/W, max_det, row_len)` detection rows — the fused gather kernel (K5) writes its rows directly into
+this rank's slot of the all-gather buffer, so there is no staging copy before NCCL.  For sliced
+inference the tiles of a frame are kept on one rank whenever possible so the cross-tile merge is
+rank-local; otherwise tile detections are all-gathered and every rank merges the frames it owns.
+Works with backend "nccl" (GPU) and "gloo" (CPU tensors, used by the host-logic tests).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous balanced slice [lo, hi) of `n_items` owned by `rank` (first `n % world` ranks get one more)."""
+    base, rem = divmod(int(n_items), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_frames(n_frames: int, tiles_per_frame: int, rank: int, world: int) -> Tuple[int, int]:
+    """Tile range [lo, hi) for `rank` when whole frames are assigned to ranks (merge stays rank-local)."""
+    f_lo, f_hi = shard_range(n_frames, rank, world)
+    return f_lo * tiles_per_frame, f_hi * tiles_per_frame
+
+
+def sahi_grid(frame_w: int, frame_h: int, tile: int = 640, overlap: float = 0.2) -> torch.Tensor:
+    """Tile origins (T, 2) as (x0, y0) of a SAHI-style slicing grid: step = tile*(1-overlap), last
+    row/column snapped back to the border (4000x3000 -> 8 x 6 = 48 tiles)."""
+    step = int(tile * (1.0 - overlap))
+
+    def axis(n):
+        if n <= tile:
+            return [0]
+        xs = list(range(0, n - tile, step))
+        xs.append(n - tile)
+        return xs
+
+    xs, ys = axis(frame_w), axis(frame_h)
+    return torch.tensor([(x, y) for y in ys for x in xs], dtype=torch.float32)
+
+
+def allgather_detections(out: torch.Tensor, counts: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather padded detections.  `out (b, max_det, row_len)`, `counts (b,)` with the same `b` on
+    every rank -> `(W*b, max_det, row_len)`, `(W*b,)` ordered by rank."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return out, counts
+    g_out = torch.empty((world,) + tuple(out.shape), dtype=out.dtype, device=out.device)
+    g_cnt = torch.empty((world,) + tuple(counts.shape), dtype=counts.dtype, device=counts.device)
+    dist.all_gather_into_tensor(g_out, out.contiguous(), group=group)
+    dist.all_gather_into_tensor(g_cnt, counts.contiguous(), group=group)
+    return g_out.flatten(0, 1), g_cnt.flatten(0, 1)
+
+
+class GatherBuffer:
+    """Pre-allocated all-gather destination whose slot `rank` is handed to the gather kernel as its
+    output buffer: K5 writes straight into the send region and NCCL runs in place."""
+
+    def __init__(self, per_rank_batch: int, max_det: int, row_len: int, device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.out = torch.empty((self.world, per_rank_batch, max_det, row_len), dtype=torch.float32, device=device)
+        self.counts = torch.zeros((self.world, per_rank_batch), dtype=torch.int32, device=device)
+
+    @property
+    def local_out(self) -> torch.Tensor:
+        return self.out[self.rank]
+
+    @property
+    def local_counts(self) -> torch.Tensor:
+        return self.counts[self.rank]
+
+    def exchange(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.out, self.out[self.rank], group=self.group)
+            dist.all_gather_into_tensor(self.counts, self.counts[self.rank], group=self.group)
+        return self.out.flatten(0, 1), self.counts.flatten(0, 1)

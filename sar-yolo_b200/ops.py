@@ -1,0 +1,371 @@
+"""Host-side mirror of the reference's post-processing interface, backed by libsarpost.so.
+
+Same names, argument meaning and error behaviour as the reference so it drops in:
+  * non_max_suppression   ultralytics/utils/ops.py:167-316
+  * decode                ultralytics/nn/modules/head.py:100-131 (Detect._inference), :214-249 (JDE._inference)
+  * postprocess_fused     decode + non_max_suppression in one pass from the raw level logits
+  * merge_tiles           cross-tile merge for sliced inference (no reference counterpart)
+  * postprocess_host      the fused path for HOST tensors (H2D / D2H included) — the `e2e` entry
+
+PyTorch is used for device memory, streams and the final list-of-views only.  CUDA tensors are
+required: there is no CPU fallback (`RuntimeError`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Head, NmsParams, lib
+
+__all__ = ["HeadSpec", "non_max_suppression", "decode", "postprocess_fused", "merge_tiles", "postprocess_host",
+           "HostContext", "last_launch_count", "stage_timing", "stage_times"]
+
+
+@dataclass(frozen=True)
+class HeadSpec:
+    """The attributes read from `model.model[-1]` (head.py:37-41, :180-188)."""
+    nc: int
+    strides: Tuple[float, ...]
+    reg_max: int = 16
+    embed_dim: int = 0        # JDE raw embedding channels (head.py:180)
+    state_classes: int = 0    # JDE state logits, sigmoid on output (head.py:181,247)
+
+    @property
+    def no(self) -> int:
+        return 4 * self.reg_max + self.nc + self.embed_dim + self.state_classes
+
+    @property
+    def nm(self) -> int:
+        return self.embed_dim + self.state_classes
+
+    @staticmethod
+    def from_module(m) -> "HeadSpec":
+        """Build from a reference Detect/JDE module instance."""
+        return HeadSpec(nc=int(m.nc), strides=tuple(float(s) for s in m.stride), reg_max=int(m.reg_max),
+                        embed_dim=int(getattr(m, "embed_dim", 0) or 0),
+                        state_classes=int(getattr(m, "state_classes", 0) or 0))
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"sarpost: {what} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"sarpost: {what} is on {t.device}; only CUDA tensors are supported "
+                           "(no CPU fallback — the reference path is the CPU implementation)")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh):
+    p = NmsParams()
+    p.conf_thres = float(conf_thres)
+    p.iou_thres = float(iou_thres)
+    p.agnostic = int(bool(agnostic))
+    p.multi_label = int(bool(multi_label))
+    p.max_det = int(max_det)
+    p.max_nms = int(max_nms)
+    p.max_wh = float(max_wh)
+    keep = None
+    if classes is not None:
+        cl = [int(c) for c in (classes.tolist() if isinstance(classes, torch.Tensor) else classes)]
+        keep = (C.c_int32 * max(len(cl), 1))(*cl)
+        p.classes = C.cast(keep, C.POINTER(C.c_int32))
+        p.n_classes = len(cl)
+    else:
+        p.classes = None
+        p.n_classes = 0
+    return p, keep
+
+
+def _make_head(levels: Sequence[torch.Tensor], spec: HeadSpec, host: bool = False) -> Head:
+    if len(levels) != len(spec.strides):
+        raise ValueError(f"sarpost: {len(levels)} level tensors but {len(spec.strides)} strides")
+    if len(levels) > _lib.MAX_LEVELS:
+        raise ValueError(f"sarpost: at most {_lib.MAX_LEVELS} levels")
+    h = Head()
+    h.nl = len(levels)
+    h.batch = int(levels[0].shape[0])
+    h.no = spec.no
+    h.nc = spec.nc
+    h.reg_max = spec.reg_max
+    h.n_extra_raw = spec.embed_dim
+    h.n_extra_sigmoid = spec.state_classes
+    for i, x in enumerate(levels):
+        if x.dim() != 4 or x.shape[0] != h.batch or x.shape[1] != spec.no:
+            raise ValueError(f"sarpost: level {i} has shape {tuple(x.shape)}, expected (B={h.batch}, no={spec.no}, H, W)")
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            raise ValueError("sarpost: level tensors must be contiguous float32 (convert before the call)")
+        if host == x.is_cuda:
+            raise RuntimeError(f"sarpost: level {i} is on {x.device}, expected {'host' if host else 'CUDA'} memory")
+        h.h[i] = int(x.shape[2])
+        h.w[i] = int(x.shape[3])
+        h.stride[i] = float(spec.strides[i])
+        h.data[i] = x.data_ptr()
+    return h
+
+
+def _prep_levels(levels: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    out = []
+    for x in levels:
+        _require_cuda(x, "level tensor")
+        if x.dtype != torch.float32:
+            x = x.float()
+        out.append(x.contiguous())
+    return out
+
+
+def _split(out: torch.Tensor, counts: torch.Tensor) -> List[torch.Tensor]:
+    # one D2H of B ints (the reference syncs several times per image, ops.py:253,275)
+    n = counts.tolist()
+    return [out[b, : n[b]] for b in range(out.shape[0])]
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def non_max_suppression(
+    prediction,
+    conf_thres=0.25,
+    iou_thres=0.45,
+    classes=None,
+    agnostic=False,
+    multi_label=False,
+    labels=(),
+    max_det=300,
+    nc=0,  # number of classes (optional)
+    max_time_img=0.05,
+    max_nms=30000,
+    max_wh=7680,
+    in_place=True,
+    rotated=False,
+    return_index=False,
+):
+    """Drop-in for `ultralytics.utils.ops.non_max_suppression` (utils/ops.py:167-316) on CUDA tensors.
+
+    Same arguments and result: a list of length batch with one `(n_i, 6 + nm)` tensor per image, columns
+    `x1, y1, x2, y2, confidence, class, extras...`, rows in descending confidence, `n_i <= max_det`.
+    Kept sets are bit-exact to the reference (torchvision CPU NMS semantics).  Documented deviations
+    (SURVEY.md Appendix B.10): the input is never modified (`in_place` is accepted and ignored), the
+    wall-clock limit `max_time_img` is accepted and ignored (nothing here can time out), score ties at
+    the `max_nms` cut resolve to the lower anchor index (the reference's order there is torch-version
+    defined).  `rotated=True` and non-empty `labels` raise NotImplementedError.
+    `return_index=True` (extension) also returns per image the int32 `anchor*nc + class` of each row.
+    """
+    # Checks (ops.py:217-220)
+    assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+    assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+    if isinstance(prediction, (list, tuple)):  # YOLOv8 model in validation model, output = (inference_out, loss_out)
+        prediction = prediction[0]  # select only inference output
+    _require_cuda(prediction, "prediction")
+    if rotated:
+        raise NotImplementedError("sarpost: rotated=True (OBB probiou NMS, ops.py:146-164) is outside the accelerated path")
+    if labels and any(len(lb) for lb in labels):
+        raise NotImplementedError("sarpost: apriori `labels` (save_hybrid, ops.py:256-261) are not supported")
+
+    if prediction.shape[-1] == 6:  # end-to-end model (BNC, i.e. 1,300,6): no NMS at all (ops.py:224-228)
+        output = [pred[pred[:, 4] > conf_thres][:max_det] for pred in prediction]
+        if classes is not None:
+            cls_t = torch.tensor(classes, device=prediction.device)
+            output = [pred[(pred[:, 5:6] == cls_t).any(1)] for pred in output]
+        return output
+
+    in_dtype = prediction.dtype
+    pred = prediction if in_dtype == torch.float32 else prediction.float()
+    pred = pred.contiguous()
+    bs, ch, na = (int(s) for s in pred.shape)
+    nc = int(nc) or (ch - 4)  # number of classes (ops.py:231)
+    nm = ch - nc - 4  # number of masks / extras
+    dev = pred.device
+    if bs == 0 or na == 0:
+        empty = [torch.zeros((0, 6 + nm), device=dev)] * bs
+        return (empty, [torch.zeros((0,), dtype=torch.int32, device=dev)] * bs) if return_index else empty
+
+    params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+    with torch.cuda.device(dev):
+        ws_bytes = lib.sarpost_workspace_bytes(bs, na, nc, int(bool(multi_label)), int(max_det))
+        if ws_bytes < 0:
+            _lib.check(int(ws_bytes))
+        ws = _workspace(ws_bytes, dev)
+        out = torch.empty((bs, int(max_det), 6 + nm), dtype=torch.float32, device=dev)
+        counts = torch.empty((bs,), dtype=torch.int32, device=dev)
+        kidx = torch.empty((bs, int(max_det)), dtype=torch.int32, device=dev) if return_index else None
+        _lib.check(lib.sarpost_nms_decoded(pred.data_ptr(), bs, ch, na, nc, C.byref(params), out.data_ptr(),
+                                           counts.data_ptr(), kidx.data_ptr() if return_index else None,
+                                           ws.data_ptr(), ws_bytes, _stream_ptr(dev)))
+        ws.record_stream(torch.cuda.current_stream(dev))
+    if in_dtype != torch.float32:
+        out = out.to(in_dtype)
+    rows = _split(out, counts)
+    if return_index:
+        n = [r.shape[0] for r in rows]
+        return rows, [kidx[b, : n[b]] for b in range(bs)]
+    return rows
+
+
+def decode(levels: Sequence[torch.Tensor], spec: HeadSpec) -> torch.Tensor:
+    """`Detect._inference` / `JDE._inference` (head.py:100-131, :214-249): raw level logits ->
+    `y (B, 4 + nc + embed_dim + state_classes, A)` with xywh boxes in pixels, class probabilities, raw
+    embedding and sigmoid state."""
+    levels = _prep_levels(levels)
+    head = _make_head(levels, spec)
+    dev = levels[0].device
+    anchors = sum(int(x.shape[2]) * int(x.shape[3]) for x in levels)
+    with torch.cuda.device(dev):
+        y = torch.empty((head.batch, 4 + spec.nc + spec.nm, anchors), dtype=torch.float32, device=dev)
+        _lib.check(lib.sarpost_decode(C.byref(head), y.data_ptr(), _stream_ptr(dev)))
+    return y
+
+
+def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres=0.25, iou_thres=0.45, classes=None,
+                      agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=7680,
+                      return_index=False, return_padded=False):
+    """decode + non_max_suppression in one pass (never materialises y; the extras channels are read only
+    for the kept rows).  Result as `non_max_suppression`; `return_padded=True` returns the raw
+    `(out (B, max_det, 6+nm), counts (B,) int32[, kept_index])` device tensors without any host sync."""
+    assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+    assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+    levels = _prep_levels(levels)
+    head = _make_head(levels, spec)
+    dev = levels[0].device
+    anchors = sum(int(x.shape[2]) * int(x.shape[3]) for x in levels)
+    bs = head.batch
+    params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+    with torch.cuda.device(dev):
+        ws_bytes = lib.sarpost_workspace_bytes(bs, anchors, spec.nc, int(bool(multi_label)), int(max_det))
+        if ws_bytes < 0:
+            _lib.check(int(ws_bytes))
+        ws = _workspace(ws_bytes, dev)
+        out = torch.empty((bs, int(max_det), 6 + spec.nm), dtype=torch.float32, device=dev)
+        counts = torch.empty((bs,), dtype=torch.int32, device=dev)
+        want_idx = return_index
+        kidx = torch.empty((bs, int(max_det)), dtype=torch.int32, device=dev) if want_idx else None
+        _lib.check(lib.sarpost_fused(C.byref(head), C.byref(params), out.data_ptr(), counts.data_ptr(),
+                                     kidx.data_ptr() if want_idx else None, ws.data_ptr(), ws_bytes, _stream_ptr(dev)))
+        ws.record_stream(torch.cuda.current_stream(dev))
+    if return_padded:
+        return (out, counts, kidx) if want_idx else (out, counts)
+    rows = _split(out, counts)
+    if return_index:
+        n = [r.shape[0] for r in rows]
+        return rows, [kidx[b, : n[b]] for b in range(bs)]
+    return rows
+
+
+def merge_tiles(dets: torch.Tensor, det_counts: torch.Tensor, origins: torch.Tensor, tiles_per_frame: int,
+                iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000, max_wh=7680, return_index=False,
+                return_padded=False):
+    """Cross-tile merge of sliced inference: `dets (T, D, row_len)` padded per-tile detections
+    (x1,y1,x2,y2,conf,cls,extras...), `det_counts (T,)` int32, `origins (T, 2)` tile offsets in frame
+    pixels; T = n_frames * tiles_per_frame with the tiles of a frame contiguous.  Per frame: shift by
+    the tile origin, then the same class-offset NMS as ops.py:289-297.  Returns a list of per-frame
+    `(n_f, row_len)` tensors."""
+    _require_cuda(dets, "dets")
+    dets = dets.float().contiguous()
+    det_counts = det_counts.to(device=dets.device, dtype=torch.int32).contiguous()
+    origins = origins.to(device=dets.device, dtype=torch.float32).contiguous()
+    t, d, row_len = (int(s) for s in dets.shape)
+    if t % tiles_per_frame:
+        raise ValueError("sarpost: number of tiles is not a multiple of tiles_per_frame")
+    nf = t // tiles_per_frame
+    dev = dets.device
+    params, _keep = _make_params(0.0, iou_thres, None, agnostic, False, max_det, max_nms, max_wh)
+    with torch.cuda.device(dev):
+        ws_bytes = lib.sarpost_merge_workspace_bytes(nf, tiles_per_frame, d, int(max_det))
+        if ws_bytes < 0:
+            _lib.check(int(ws_bytes))
+        ws = _workspace(ws_bytes, dev)
+        out = torch.empty((nf, int(max_det), row_len), dtype=torch.float32, device=dev)
+        counts = torch.empty((nf,), dtype=torch.int32, device=dev)
+        kidx = torch.empty((nf, int(max_det)), dtype=torch.int32, device=dev) if return_index else None
+        _lib.check(lib.sarpost_merge_tiles(dets.data_ptr(), det_counts.data_ptr(), origins.data_ptr(), nf,
+                                           tiles_per_frame, d, row_len, C.byref(params), out.data_ptr(),
+                                           counts.data_ptr(), kidx.data_ptr() if return_index else None,
+                                           ws.data_ptr(), ws_bytes, _stream_ptr(dev)))
+        ws.record_stream(torch.cuda.current_stream(dev))
+    if return_padded:
+        return (out, counts, kidx) if return_index else (out, counts)
+    rows = _split(out, counts)
+    if return_index:
+        n = [r.shape[0] for r in rows]
+        return rows, [kidx[b, : n[b]] for b in range(nf)]
+    return rows
+
+
+class HostContext:
+    """Owns the device buffers, pinned staging and stream of the HOST-buffer entry point
+    (`sarpost_host_ctx_*`).  One per caller thread / device."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        self.device = int(device)
+        _lib.check(lib.sarpost_host_ctx_create(self.device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib.sarpost_host_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_traffic(self) -> Tuple[int, int]:
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(lib.sarpost_host_ctx_last_traffic(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def postprocess(self, levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres=0.25, iou_thres=0.45,
+                    classes=None, agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=7680,
+                    out: Optional[torch.Tensor] = None, return_index=False):
+        """Fused post-processing of HOST level tensors; returns a list of per-image CPU tensors."""
+        assert 0 <= conf_thres <= 1 and 0 <= iou_thres <= 1
+        head = _make_head(levels, spec, host=True)
+        bs = head.batch
+        params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+        if out is None:
+            out = torch.empty((bs, int(max_det), 6 + spec.nm), dtype=torch.float32)
+        counts = torch.empty((bs,), dtype=torch.int32)
+        kidx = torch.empty((bs, int(max_det)), dtype=torch.int32) if return_index else None
+        _lib.check(lib.sarpost_fused_host(self._h, C.byref(head), C.byref(params), out.data_ptr(), counts.data_ptr(),
+                                          kidx.data_ptr() if return_index else None))
+        n = counts.tolist()
+        rows = [out[b, : n[b]] for b in range(bs)]
+        if return_index:
+            return rows, [kidx[b, : n[b]] for b in range(bs)]
+        return rows
+
+
+_HOST_CTX = {}
+
+
+def postprocess_host(levels: Sequence[torch.Tensor], spec: HeadSpec, device: int = 0, **kw):
+    """Convenience wrapper: fused post-processing of CPU level tensors on GPU `device` (cached context)."""
+    ctx = _HOST_CTX.get(device)
+    if ctx is None:
+        ctx = _HOST_CTX[device] = HostContext(device)
+    return ctx.postprocess(levels, spec, **kw)
+
+
+def last_launch_count() -> int:
+    """Kernels launched by the last libsarpost call on this thread."""
+    return int(lib.sarpost_last_launch_count())
+
+
+def stage_timing(enabled: bool) -> None:
+    _lib.check(lib.sarpost_set_stage_timing(int(bool(enabled))))
+
+
+def stage_times() -> Tuple[float, float, float, float]:
+    """Milliseconds of (K1 candidates, K2 select+sort, K4 nms, K5 gather) of the last timed call."""
+    buf = (C.c_float * 4)()
+    _lib.check(lib.sarpost_stage_times(buf))
+    return tuple(float(v) for v in buf)

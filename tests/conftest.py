@@ -1,0 +1,37 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Make sure libsarpost.so and the oracle's C library exist (nvcc / gcc cross-compile without a GPU)."""
+    import __graft_entry__ as g
+
+    g.build()
+    yield
+
+
+@pytest.fixture(scope="session")
+def sarpost(_built):
+    import sarpost as sp
+
+    return sp
+
+
+@pytest.fixture(scope="session")
+def cuda(_built):
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")

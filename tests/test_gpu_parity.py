@@ -1,0 +1,300 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * NMS kept rows / kept indices / class ids: bit-exact when both sides get the same decoded input;
+  * decoded boxes: |err| <= 1e-5*|ref| + 1e-5*stride (fp32; SURVEY §7 hard part 3), scores likewise 1e-5 relative;
+  * end-to-end from raw logits: mismatching detections < 1e-4 of all detections.
+"""
+import pytest
+import torch
+
+from oracle import postprocess_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _nms_both(sarpost, y_cpu, dev, **kw):
+    rows, idx = sarpost.non_max_suppression(y_cpu.to(dev), return_index=True, **kw)
+    ref_rows, ref_idx = R.non_max_suppression_ref(y_cpu, return_index=True, **kw)
+    return rows, idx, ref_rows, ref_idx
+
+
+def _assert_same(rows, idx, ref_rows, ref_idx, nc):
+    assert len(rows) == len(ref_rows)
+    for b, (r, i, rr, ri) in enumerate(zip(rows, idx, ref_rows, ref_idx)):
+        assert tuple(r.shape) == tuple(rr.shape), f"image {b}: {tuple(r.shape)} vs {tuple(rr.shape)}"
+        i = i.cpu().long()
+        assert torch.equal(i // nc, ri[:, 0]), f"image {b}: kept anchor indices differ"
+        assert torch.equal(i % nc, ri[:, 1]), f"image {b}: kept class ids differ"
+        assert torch.equal(r.cpu(), rr), f"image {b}: rows differ"
+
+
+@pytest.mark.parametrize("bs,na,nc,nm,kw", [
+    (1, 8400, 1, 0, dict(conf_thres=0.25, iou_thres=0.7)),
+    (3, 8400, 6, 0, dict(conf_thres=0.25, iou_thres=0.7)),
+    (2, 8400, 1, 262, dict(conf_thres=0.25, iou_thres=0.7)),                      # JDE layout
+    (2, 8400, 6, 5, dict(conf_thres=0.001, iou_thres=0.7, multi_label=True)),      # > max_nms after expansion
+    (2, 6000, 6, 0, dict(conf_thres=0.001, iou_thres=0.7, multi_label=True, max_nms=3000)),
+    (2, 5000, 4, 0, dict(conf_thres=0.05, iou_thres=0.6, agnostic=True)),          # thr whose float rounds up
+    (2, 5000, 5, 3, dict(conf_thres=0.05, iou_thres=0.45, classes=[0, 3])),
+    (2, 5000, 5, 0, dict(conf_thres=0.05, iou_thres=0.45, classes=[1], multi_label=True)),
+    (1, 1000, 2, 0, dict(conf_thres=0.9999, iou_thres=0.5)),                       # (almost) nothing passes
+    (1, 37, 3, 0, dict(conf_thres=0.0, iou_thres=0.5, max_det=5)),                 # tiny, ragged tile
+    (2, 3000, 1, 0, dict(conf_thres=0.01, iou_thres=0.7, max_det=1000, nc=1)),
+    (1, 70000, 1, 0, dict(conf_thres=0.001, iou_thres=0.7)),                       # top-k cut engaged (n > 30000)
+])
+def test_nms_decoded_bit_exact(sarpost, cuda, bs, na, nc, nm, kw):
+    y = sarpost.synth.decoded_prediction(bs, na, nc, nm, seed=na + nc, score_pow=2.0 if kw["conf_thres"] < 0.01 else 4.0)
+    rows, idx, ref_rows, ref_idx = _nms_both(sarpost, y, cuda, **kw)
+    _assert_same(rows, idx, ref_rows, ref_idx, nc)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_nms_decoded_clustered_heavy_suppression(sarpost, cuda, seed):
+    """Clustered boxes: thousands of candidates, most suppressed, many chunks walked by K4."""
+    y = sarpost.synth.decoded_prediction(2, 12000, 3, 0, seed=seed, clustered=True, score_pow=1.0)
+    for kw in (dict(conf_thres=0.05, iou_thres=0.7), dict(conf_thres=0.05, iou_thres=0.3, agnostic=True, max_det=100),
+               dict(conf_thres=0.001, iou_thres=0.5, multi_label=True)):
+        rows, idx, ref_rows, ref_idx = _nms_both(sarpost, y, cuda, **kw)
+        _assert_same(rows, idx, ref_rows, ref_idx, 3)
+
+
+def test_nms_ties_stable_order(sarpost, cuda):
+    """Heavy score ties (scores quantised to 1/16): equal scores must resolve lower-index-first,
+    including at the max_nms cut."""
+    y = sarpost.synth.decoded_prediction(2, 9000, 2, 0, seed=11)
+    y[:, 4:6] = (y[:, 4:6] * 16).floor() / 16 + 1 / 32
+    for kw in (dict(conf_thres=0.01, iou_thres=0.7), dict(conf_thres=0.01, iou_thres=0.7, multi_label=True, max_nms=2500),
+               dict(conf_thres=0.01, iou_thres=0.7, max_nms=100, max_det=50)):
+        rows, idx, ref_rows, ref_idx = _nms_both(sarpost, y, cuda, **kw)
+        _assert_same(rows, idx, ref_rows, ref_idx, 2)
+
+
+def test_nms_all_scores_equal(sarpost, cuda):
+    """Pathological whole-model random-init case: every score identical."""
+    y = sarpost.synth.decoded_prediction(1, 40000, 1, 0, seed=5)
+    y[:, 4] = 0.0124
+    kw = dict(conf_thres=0.001, iou_thres=0.7)
+    rows, idx, ref_rows, ref_idx = _nms_both(sarpost, y, cuda, **kw)
+    _assert_same(rows, idx, ref_rows, ref_idx, 1)
+
+
+def test_nms_known_answers(sarpost, cuda):
+    """SURVEY §8c known-answer vectors (probed behaviour of the reference)."""
+    def run(boxes_xyxy, scores, thr):
+        b = torch.tensor(boxes_xyxy, dtype=torch.float32)
+        xywh = torch.stack(((b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]), 1)
+        y = torch.cat((xywh, torch.tensor(scores, dtype=torch.float32)[:, None]), 1).t()[None].contiguous()
+        rows, idx = sarpost.non_max_suppression(y.to(cuda), conf_thres=0.1, iou_thres=thr, return_index=True)
+        ref = R.non_max_suppression_ref(y, conf_thres=0.1, iou_thres=thr, return_index=True)
+        assert torch.equal(idx[0].cpu().long(), ref[1][0][:, 0])
+        return idx[0].cpu().tolist()
+    assert run([[0, 0, 10, 10]] * 3, [0.5, 0.5, 0.5], 0.5) == [0]                       # identical boxes, equal scores
+    assert run([[0, 0, 6, 1], [0, 0, 3.6000001, 1]], [0.9, 0.8], 0.6) == [0]            # IoU == 0.6f, double compare suppresses
+    assert run([[0, 0, 6, 1], [0, 0, 3.6000001, 1]], [0.9, 0.8], 0.7) == [0, 1]
+    assert run([[5, 5, 5, 5], [5, 5, 5, 5]], [0.9, 0.8], 0.5) == [0, 1]                 # zero-area: 0/0 never suppresses
+
+
+def test_nms_fma_discriminating_pairs(sarpost, cuda):
+    """Pairs whose IoU sits within an ulp of the threshold: an FMA-contracted IoU would flip them."""
+    g = torch.Generator().manual_seed(123)
+    n = 4000
+    a = torch.rand(n, 2, generator=g) * 100
+    wh = 10 + torch.rand(n, 2, generator=g) * 50
+    boxes = []
+    scores = []
+    for i in range(n):
+        x1, y1 = a[i].tolist()
+        w, h = wh[i].tolist()
+        boxes.append([x1 + 1000.0 * i, y1, x1 + w + 1000.0 * i, y1 + h])
+        # partner shifted so IoU is close to 0.7: overlap fraction f with f/(2-f) = 0.7 -> f = 0.8235
+        dx = w * (1 - 0.823529411)
+        boxes.append([x1 + dx + 1000.0 * i, y1, x1 + dx + w + 1000.0 * i, y1 + h])
+        scores += [0.9, 0.8]
+    b = torch.tensor(boxes, dtype=torch.float32)
+    xywh = torch.stack(((b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2, b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]), 1)
+    y = torch.cat((xywh, torch.tensor(scores)[:, None]), 1).t()[None].contiguous()
+    kw = dict(conf_thres=0.1, iou_thres=0.7, max_det=4096, max_wh=0)
+    rows, idx, ref_rows, ref_idx = _nms_both(sarpost, y, cuda, **kw)
+    _assert_same(rows, idx, ref_rows, ref_idx, 1)
+    assert 2 * n * 0.2 < rows[0].shape[0] <= 4096
+
+
+HEADS = [
+    # (imgsz, strides, nc, embed_dim, state_classes, batch)
+    (640, (8, 16, 32), 1, 256, 6, 2),      # cfg1/cfg2 SAR posture JDE head (no = 327)
+    (640, (8, 16, 32), 6, 0, 0, 3),        # posture-as-class Detect head (no = 70)
+    (320, (4, 8, 16, 32), 1, 16, 0, 2),    # P2 head, JDE without state
+    ((96, 160), (8, 16, 32), 3, 0, 0, 2),  # rect
+    ((88, 88), (8, 16, 32), 2, 8, 6, 2),   # 11x11 / odd levels: H*W*4 not 16-byte aligned -> LDG path
+]
+
+
+@pytest.mark.parametrize("imgsz,strides,nc,ed,sc,bs", HEADS)
+def test_decode_matches_oracle(sarpost, cuda, imgsz, strides, nc, ed, sc, bs):
+    shapes = sarpost.synth.level_shapes(imgsz, strides)
+    levels = sarpost.synth.head_outputs(bs, shapes, nc, ed, sc, seed=3)
+    spec = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=sc)
+    y = sarpost.decode([x.to(cuda) for x in levels], spec).cpu()
+    y_ref = R.decode_ref(levels, strides, nc, 16, ed, sc)
+    assert y.shape == y_ref.shape
+    st = torch.cat([torch.full((h * w,), float(s)) for (h, w), s in zip(shapes, strides)])
+    # boxes: rtol 1e-5 / atol 1e-5*stride (tolerance stated by north_star, evaluated per SURVEY §7.3)
+    err = (y[:, :4] - y_ref[:, :4]).abs()
+    assert bool((err <= 1e-5 * y_ref[:, :4].abs() + 1e-5 * st).all()), err.max().item()
+    # class probabilities and sigmoid state: 1e-5 relative (+1e-7 absolute floor)
+    assert torch.allclose(y[:, 4:4 + nc], y_ref[:, 4:4 + nc], rtol=1e-5, atol=1e-7)
+    if ed:
+        assert torch.equal(y[:, 4 + nc:4 + nc + ed], y_ref[:, 4 + nc:4 + nc + ed])  # raw embedding: pure copy
+    if sc:
+        assert torch.allclose(y[:, 4 + nc + ed:], y_ref[:, 4 + nc + ed:], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("imgsz,strides,nc,ed,sc,bs", HEADS)
+@pytest.mark.parametrize("mode", ["predict", "val", "val_multi"])
+def test_fused_equals_decode_then_nms(sarpost, cuda, imgsz, strides, nc, ed, sc, bs, mode):
+    """Fused kernels vs oracle NMS fed OUR decoded y: rows, indices and extras bit-exact
+    (isolates candidate generation / compaction / extras gather from decode rounding)."""
+    shapes = sarpost.synth.level_shapes(imgsz, strides)
+    levels = [x.to(cuda) for x in sarpost.synth.head_outputs(bs, shapes, nc, ed, sc, seed=9)]
+    spec = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=sc)
+    kw = {"predict": dict(conf_thres=0.25, iou_thres=0.7), "val": dict(conf_thres=0.001, iou_thres=0.7),
+          "val_multi": dict(conf_thres=0.001, iou_thres=0.7, multi_label=True)}[mode]
+    rows, idx = sarpost.postprocess_fused(levels, spec, return_index=True, **kw)
+    y = sarpost.decode(levels, spec).cpu()
+    ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=nc, return_index=True, **kw)
+    _assert_same(rows, idx, ref_rows, ref_idx, nc)
+
+
+def test_fused_tma_and_ldg_paths_agree(sarpost, cuda, monkeypatch):
+    strides = (8, 16, 32)
+    shapes = sarpost.synth.level_shapes(640, strides)
+    levels = [x.to(cuda) for x in sarpost.synth.head_outputs(2, shapes, 6, 0, 0, seed=21)]
+    spec = sarpost.HeadSpec(nc=6, strides=strides)
+    kw = dict(conf_thres=0.001, iou_thres=0.7, multi_label=True)
+    a = sarpost.postprocess_fused(levels, spec, **kw)
+    monkeypatch.setenv("SARPOST_K1_FORCE_LDG", "1")
+    b = sarpost.postprocess_fused(levels, spec, **kw)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("imgsz,strides,nc,bs,conf", [
+    (640, (8, 16, 32), 1, 8, 0.25), (640, (8, 16, 32), 6, 4, 0.25), (1280, (4, 8, 16, 32), 1, 1, 0.001)])
+def test_end_to_end_mismatch_budget(sarpost, cuda, imgsz, strides, nc, bs, conf):
+    """Raw logits -> detections: CUDA fused path vs oracle decode + oracle NMS.  Detections are matched
+    by (anchor, class); a detection counts as a mismatch if it is missing on either side or its box /
+    score is outside the decode tolerance.  Budget: < 1e-4 of all detections (north_star)."""
+    shapes = sarpost.synth.level_shapes(imgsz, strides)
+    total = bad = 0
+    for seed in range(3):
+        levels = sarpost.synth.head_outputs(bs, shapes, nc, 0, 0, seed=100 + seed, blobs=20)
+        spec = sarpost.HeadSpec(nc=nc, strides=strides)
+        rows, idx = sarpost.postprocess_fused([x.to(cuda) for x in levels], spec, conf_thres=conf, iou_thres=0.7,
+                                              return_index=True)
+        y_ref = R.decode_ref(levels, strides, nc)
+        ref_rows, ref_idx = R.non_max_suppression_ref(y_ref, conf_thres=conf, iou_thres=0.7, nc=nc, return_index=True)
+        for b in range(bs):
+            ours = {int(k): r for k, r in zip(idx[b].cpu().tolist(), rows[b].cpu())}
+            ref = {int(a) * nc + int(c): r for (a, c), r in zip(ref_idx[b].tolist(), ref_rows[b])}
+            total += max(len(ours), len(ref))
+            for k in set(ours) | set(ref):
+                if k not in ours or k not in ref:
+                    bad += 1
+                elif not torch.allclose(ours[k], ref[k], rtol=1e-5, atol=1e-5 * max(strides)):
+                    bad += 1
+    assert total > 0
+    assert bad <= max(1e-4 * total, 0), f"{bad} mismatching detections out of {total}"
+
+
+def test_full_size_properties_cfg3(sarpost, cuda):
+    """BASELINE cfg3 at full size (1280x1280 P2, 136 000 anchors, val thresholds, B=4): size-independent
+    properties — descending scores, counts <= max_det, idempotence of NMS on its own output, no kept
+    pair above the IoU threshold within a class."""
+    strides = (4, 8, 16, 32)
+    shapes = sarpost.synth.level_shapes(1280, strides)
+    levels = sarpost.synth.head_outputs(4, shapes, 1, 256, 6, seed=3000, device=cuda, blobs=30)
+    spec = sarpost.HeadSpec(nc=1, strides=strides, embed_dim=256, state_classes=6)
+    rows = sarpost.postprocess_fused(levels, spec, conf_thres=0.001, iou_thres=0.7)
+    assert len(rows) == 4
+    for r in rows:
+        assert 0 < r.shape[0] <= 300 and r.shape[1] == 268
+        s = r[:, 4]
+        assert bool((s[:-1] >= s[1:]).all())
+        assert bool((s > 0.001).all())
+        b = r[:, :4].cpu()
+        keep = R.nms_ref(b, s.cpu(), 0.7)
+        assert keep.tolist() == list(range(r.shape[0])), "NMS output is not a fixed point of NMS"
+
+
+def test_merge_tiles_matches_oracle(sarpost, cuda):
+    """Cross-tile merge = shift by origin + class-offset NMS per frame (SURVEY §8c definition)."""
+    g = torch.Generator().manual_seed(4)
+    origins = sarpost.dist.sahi_grid(4000, 3000)
+    tpf, d, row_len, nf = origins.shape[0], 60, 8, 3
+    dets = torch.zeros(nf * tpf, d, row_len)
+    cnt = torch.randint(0, d + 1, (nf * tpf,), generator=g, dtype=torch.int32)
+    xy = torch.rand(nf * tpf, d, 2, generator=g) * 560
+    wh = 20 + torch.rand(nf * tpf, d, 2, generator=g) * 120
+    dets[..., 0:2] = xy
+    dets[..., 2:4] = xy + wh
+    dets[..., 4] = torch.rand(nf * tpf, d, generator=g).sort(dim=1, descending=True).values
+    dets[..., 5] = torch.randint(0, 3, (nf * tpf, d), generator=g).float()
+    dets[..., 6:] = torch.randn(nf * tpf, d, 2, generator=g)
+    org = origins.repeat(nf, 1)
+    rows, idx = sarpost.merge_tiles(dets.to(cuda), cnt.to(cuda), org.to(cuda), tpf, iou_thres=0.5, max_det=500, return_index=True)
+    for f in range(nf):
+        cand, src = [], []
+        for t in range(tpf):
+            k = f * tpf + t
+            n = int(cnt[k])
+            r = dets[k, :n].clone()
+            r[:, 0] += org[k, 0]; r[:, 2] += org[k, 0]; r[:, 1] += org[k, 1]; r[:, 3] += org[k, 1]
+            cand.append(r)
+            src.append(torch.arange(n) + t * d)
+        x = torch.cat(cand)
+        src = torch.cat(src)
+        keep = R.nms_ref(x[:, :4] + x[:, 5:6] * 7680, x[:, 4], 0.5)[:500]
+        assert torch.equal(rows[f].cpu(), x[keep])
+        assert torch.equal(idx[f].cpu().long(), src[keep])
+
+
+def test_host_entry_matches_device_entry(sarpost, cuda):
+    strides = (8, 16, 32)
+    shapes = sarpost.synth.level_shapes(640, strides)
+    spec = sarpost.HeadSpec(nc=1, strides=strides, embed_dim=256, state_classes=6)
+    levels = [x.pin_memory() for x in sarpost.synth.head_outputs(4, shapes, 1, 256, 6, seed=77)]
+    kw = dict(conf_thres=0.25, iou_thres=0.7)
+    dev_rows = sarpost.postprocess_fused([x.to(cuda) for x in levels], spec, **kw)
+    ctx = sarpost.HostContext(0)
+    host_rows = ctx.postprocess(levels, spec, **kw)
+    h2d, d2h = ctx.last_traffic()
+    assert h2d > 0 and d2h > 0
+    for a, b in zip(dev_rows, host_rows):
+        assert torch.equal(a.cpu(), b)
+    ctx.close()
+
+
+def test_errors_and_api_contract(sarpost, cuda):
+    y = sarpost.synth.decoded_prediction(1, 100, 2, 0, seed=0)
+    with pytest.raises(RuntimeError):
+        sarpost.non_max_suppression(y)  # CPU tensor: no fallback
+    with pytest.raises(AssertionError):
+        sarpost.non_max_suppression(y.to(cuda), conf_thres=1.5)
+    with pytest.raises(AssertionError):
+        sarpost.non_max_suppression(y.to(cuda), iou_thres=-0.1)
+    with pytest.raises(NotImplementedError):
+        sarpost.non_max_suppression(y.to(cuda), rotated=True)
+    yc = y.to(cuda)
+    before = yc.clone()
+    out = sarpost.non_max_suppression((yc, None), conf_thres=0.1)  # tuple input (ops.py:219-220)
+    assert torch.equal(yc, before), "input must not be modified"
+    assert isinstance(out, list) and len(out) == 1 and out[0].shape[1] == 6
+    out[0][:, :4] *= 2  # callers mutate outputs in place (jde/predict.py:49)
+    empty = sarpost.non_max_suppression(yc, conf_thres=1.0)
+    assert empty[0].shape == (0, 6)
+    # end-to-end (B, N, 6) branch (ops.py:224-228)
+    e2e = torch.rand(2, 300, 6, device=cuda)
+    o = sarpost.non_max_suppression(e2e, conf_thres=0.5, max_det=10)
+    assert all(t.shape[0] <= 10 and bool((t[:, 4] > 0.5).all()) for t in o)
+    assert sarpost.ops.last_launch_count() >= 0
