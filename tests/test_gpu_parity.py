@@ -45,6 +45,7 @@ def _assert_same(rows, idx, ref_rows, ref_idx, nc):
 ])
 def test_nms_decoded_bit_exact(sarpost, cuda, bs, na, nc, nm, kw):
     y = sarpost.synth.decoded_prediction(bs, na, nc, nm, seed=na + nc, score_pow=2.0 if kw["conf_thres"] < 0.01 else 4.0)
+    kw = dict(kw, nc=nc)
     rows, idx, ref_rows, ref_idx = _nms_both(sarpost, y, cuda, **kw)
     _assert_same(rows, idx, ref_rows, ref_idx, nc)
 
