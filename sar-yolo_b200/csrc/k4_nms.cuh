@@ -1,141 +1,403 @@
-// k4_nms.cuh — stage K4: class-offset greedy NMS with early exit, and K5: max_det gather.
+// k4_nms.cuh — stage K3/K4: lazy stable sort + class-offset greedy NMS with early exit; K5: gather.
 //
-// Replaces ops.py:289-297 (`c = cls*max_wh; boxes = box + c; i = torchvision.ops.nms(...)[:max_det]`)
-// and ops.py:311 (`output[xi] = x[i]`).  Bit-exact to torchvision's CPU kernel (oracle/nms_greedy.c).
+// Replaces the stable descending sort and greedy suppression of torchvision.ops.nms called at
+// ops.py:296 on the class-offset boxes of ops.py:289,295, the `[:max_det]` cut (ops.py:297) and the
+// row gather (ops.py:311).  Bit-exact to torchvision's CPU kernel (oracle/nms_greedy.c).
 //
-// Greedy NMS only ever compares a candidate with boxes that were KEPT before it, and the result is
-// cut at max_det (ops.py:297), so at most n*max_det pair tests are needed instead of n^2/2.
-// One CTA per image walks the sorted candidates in chunks of kChunk:
-//   phase 1  every candidate of the chunk is tested against the kept list (<= max_det boxes, smem);
-//   phase 2  the survivors are compacted and an upper-triangular 64-bit suppression mask is built
-//            among them (tiled IoU bitmask, all threads);
-//   sweep    one warp resolves the chunk sequentially on the bitmask — one step per KEPT box, not
-//            per candidate — appending to the kept list; stops at max_det.
+// Greedy NMS compares a candidate only with boxes KEPT before it, and stops at max_det keeps — so at
+// most n*max_det pair tests are needed, not n^2/2, and usually only the head of the sorted order is
+// ever looked at.  One CTA per image walks the bucket-partitioned candidates (k2_select_sort.cuh):
+//   chunk     the next run of whole score buckets that fits shared memory is sorted there (bitonic
+//             network on the 64-bit composite score|~slot = descending score, source order on ties);
+//             a single bucket larger than that falls back to a stable LSD radix sort in global memory;
+//   phase 1   a sub-chunk of <= 256 sorted candidates is tested against the kept list (smem);
+//   phase 2   an upper-triangular suppression bitmask is built among the survivors (tiled IoU
+//             bitmask, all threads);
+//   sweep     one warp resolves the sub-chunk on the bitmask, 32 candidates per step when no two live
+//             candidates of the group overlap, else one step per KEPT box; appends to the kept list.
 #pragma once
 #include "common.cuh"
+#include "k2_select_sort.cuh"
 
 namespace sarpost {
 
 constexpr int kNmsThreads = 512;
-constexpr int kChunk = 512;
-constexpr int kChunkWords = kChunk / 64;
+constexpr int kNmsWarps = kNmsThreads / 32;
+constexpr int kSortCap = 1024;   // candidates sorted in shared memory at once
+constexpr int kSub = 256;        // candidates per NMS sub-chunk
+constexpr int kSubWords = kSub / 32;
 
 struct NmsParams {
     CandStore st;
-    const uint32_t *sorted;   // [B*cap] candidate slots in descending-score order
-    const int32_t *n_sorted;  // [B]
-    uint32_t *kept_slot;      // [B*max_det]
-    int32_t *counts;          // [B]
-    int32_t max_det;
-    int32_t nc;               // key % nc = class (merge: class comes from cls_override)
-    const float *cls_override;// merge path: class id per slot (float) or nullptr
-    float max_wh;             // 0 when agnostic
-    float thr;                // largest float <= iou_thres
+    uint32_t *part_key, *part_val;   // [B*cap] from K2 (may be permuted in place by the fallback sort)
+    uint32_t *tmp_key, *tmp_val;     // [B*cap] scratch for the fallback sort
+    const int32_t *bstart;           // [B*(kBuckets+1)]
+    uint32_t *kept_slot;             // [B*max_det]
+    int32_t *counts;                 // [B]
+    int32_t max_det, max_nms;
+    int32_t nc;                      // key % nc = class (merge: class comes from cls_override)
+    const float *cls_override;       // merge path: class id per slot (float) or nullptr
+    float max_wh;                    // 0 when agnostic
+    float thr;                       // largest float <= iou_thres
 };
 
-// dynamic smem layout: kept_box[max_det] float4 | kept_area[max_det] | kept_slot[max_det]
+// IoU(a,b) > thr, bit-exact to the fp32 division of the reference but without paying for it on
+// every pair: a 2-instruction approximate quotient decides unless it lands within a few ulp of
+// the threshold, in which case the correctly rounded division is evaluated.
+__device__ __forceinline__ bool iou_gt_fast(const float4 a, const float area_a, const float4 b, const float area_b,
+                                            const float thr, const float band) {
+    const float xx1 = fmaxf(a.x, b.x);
+    const float yy1 = fmaxf(a.y, b.y);
+    const float xx2 = fminf(a.z, b.z);
+    const float yy2 = fminf(a.w, b.w);
+    const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
+    const float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(w, h);
+    const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    const float q = __fdividef(inter, uni);  // <= 2 ulp for |uni| < 2^126
+    bool gt = q > thr;
+    if (fabsf(__fsub_rn(q, thr)) <= band) gt = __fdiv_rn(inter, uni) > thr;  // NaN skips this and stays false
+    return gt;
+}
+
+// One stable LSD radix pass (8-bit digit) over n (key,val) pairs in global memory, kNmsThreads threads.
+// Warp w owns the contiguous share [w*per_warp, (w+1)*per_warp) so relative order is preserved.
+template <class DigitFn>
+__device__ __forceinline__ void radix_pass_global(const uint32_t *in_key, const uint32_t *in_val, uint32_t *out_key,
+                                                  uint32_t *out_val, int n, const DigitFn &digit, int *cnt, int *warp_tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kStride = kNmsWarps + 1;
+    for (int i = threadIdx.x; i < 256 * kStride; i += kNmsThreads) cnt[i] = 0;
+    __syncthreads();
+    const int per_warp = (n + kNmsWarps - 1) / kNmsWarps;
+    const int iters = (per_warp + 31) / 32;
+    for (int it = 0; it < iters; ++it) {
+        const int o = it * 32 + lane, i = warp * per_warp + o;
+        const bool ok = o < per_warp && i < n;
+        const uint32_t d = ok ? digit(in_key[i], in_val[i]) : 256u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if (ok && (peers & lanemask_lt()) == 0) cnt[d * kStride + warp] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // exclusive scan over (digit-major, warp-minor): 256*16 = 4096 entries, 8 per thread
+    int local[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = threadIdx.x * 8 + i;
+        local[i] = cnt[(e / kNmsWarps) * kStride + (e % kNmsWarps)];
+        sum += local[i];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += v;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    int run = inc - sum;
+    for (int w = 0; w < warp; ++w) run += warp_tot[w];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int e = threadIdx.x * 8 + i;
+        cnt[(e / kNmsWarps) * kStride + (e % kNmsWarps)] = run;
+        run += local[i];
+    }
+    __syncthreads();
+    for (int it = 0; it < iters; ++it) {
+        const int o = it * 32 + lane, i = warp * per_warp + o;
+        const bool ok = o < per_warp && i < n;
+        uint32_t key = 0, val = 0;
+        if (ok) {
+            key = in_key[i];
+            val = in_val[i];
+        }
+        const uint32_t d = ok ? digit(key, val) : 256u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        int base = 0;
+        if (ok) base = cnt[d * kStride + warp];
+        __syncwarp();
+        if (ok) {
+            const int rank = __popc(peers & lanemask_lt());
+            if (rank == 0) cnt[d * kStride + warp] = base + __popc(peers);
+            out_key[base + rank] = key;
+            out_val[base + rank] = val;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+}
+
+// shared-memory carve-up (dynamic): see k4_nms
+struct NmsSmem {
+    float4 *kept_box;
+    float *kept_area;
+    uint32_t *kept_slot;
+    int32_t *bstart;               // [kBuckets + 1]
+    unsigned long long *skey;      // [kSortCap] composite keys
+    float4 *a_box;                 // [kSub] sub-chunk candidates (class-offset boxes)
+    float *a_area;                 // [kSub]
+    uint32_t *a_slot;              // [kSub]
+    int32_t *a_alive;              // [kSub]
+    float4 *c_box;                 // [kSub] survivors
+    float *c_area;
+    uint32_t *c_slot;
+    uint32_t *mask;                // [kSub * kSubWords]
+    int32_t *misc;                 // [32]
+};
+
+__host__ __device__ inline size_t nms_smem_bytes(int max_det) {
+    size_t b = 0;
+    b += static_cast<size_t>(max_det) * 16 + static_cast<size_t>(max_det) * 4 * 2;
+    b = (b + 15) / 16 * 16;
+    b += (kBuckets + 1 + 3) / 4 * 4 * 4;
+    b += kSortCap * 8;
+    b += kSub * (16 + 4 + 4 + 4);
+    b += kSub * (16 + 4 + 4);
+    b += kSub * kSubWords * 4;
+    b += 32 * 4;
+    return b + 16;
+}
+
 __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__ NmsParams p) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
-    float4 *kept_box = reinterpret_cast<float4 *>(nms_smem);
-    float *kept_area = reinterpret_cast<float *>(kept_box + p.max_det);
-    uint32_t *kept_slot = reinterpret_cast<uint32_t *>(kept_area + p.max_det);
-    __shared__ float4 ch_box[kChunk];
-    __shared__ float ch_area[kChunk];
-    __shared__ uint32_t ch_slot[kChunk];
-    __shared__ unsigned long long mask[kChunk * kChunkWords];
-    __shared__ int warp_tot[kNmsThreads / 32];
-    __shared__ int s_kept, s_m;
-
+    NmsSmem S;
+    {
+        unsigned char *q = nms_smem;
+        S.kept_box = reinterpret_cast<float4 *>(q); q += static_cast<size_t>(p.max_det) * 16;
+        S.kept_area = reinterpret_cast<float *>(q); q += static_cast<size_t>(p.max_det) * 4;
+        S.kept_slot = reinterpret_cast<uint32_t *>(q); q += static_cast<size_t>(p.max_det) * 4;
+        q = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(q) + 15) & ~uintptr_t(15));
+        S.bstart = reinterpret_cast<int32_t *>(q); q += (kBuckets + 1 + 3) / 4 * 4 * 4;
+        S.skey = reinterpret_cast<unsigned long long *>(q); q += kSortCap * 8;  // fallback sort aliases skey..c_slot
+        S.a_box = reinterpret_cast<float4 *>(q); q += kSub * 16;
+        S.c_box = reinterpret_cast<float4 *>(q); q += kSub * 16;
+        S.a_area = reinterpret_cast<float *>(q); q += kSub * 4;
+        S.a_slot = reinterpret_cast<uint32_t *>(q); q += kSub * 4;
+        S.a_alive = reinterpret_cast<int32_t *>(q); q += kSub * 4;
+        S.c_area = reinterpret_cast<float *>(q); q += kSub * 4;
+        S.c_slot = reinterpret_cast<uint32_t *>(q); q += kSub * 4;
+        S.mask = reinterpret_cast<uint32_t *>(q); q += kSub * kSubWords * 4;
+        S.misc = reinterpret_cast<int32_t *>(q);
+    }
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = p.n_sorted[b];
     const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
-    const uint32_t *sorted = p.sorted + seg;
-    int kept = 0;
+    uint32_t *pkey = p.part_key + seg, *pval = p.part_val + seg;
+    uint32_t *tkey = p.tmp_key + seg, *tval = p.tmp_val + seg;
+    const float band = fmaxf(p.thr * 2e-6f, 1e-37f);
 
-    for (int start = 0; start < n && kept < p.max_det; start += kChunk) {
-        // ---- load chunk, build class-offset boxes (ops.py:289,295), phase 1 ----
-        const int i = start + tid;
-        bool alive = i < n;
-        float4 ob = make_float4(0.f, 0.f, 0.f, 0.f);
-        float area = 0.f;
-        uint32_t slot = 0;
-        if (alive) {
-            slot = sorted[i];
-            const float4 bx = p.st.box[seg + slot];
-            const float cls = p.cls_override ? p.cls_override[seg + slot]
-                                             : static_cast<float>(p.st.key[seg + slot] % static_cast<uint32_t>(p.nc));
-            const float off = __fmul_rn(cls, p.max_wh);
-            ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
-            area = box_area_rn(ob);
-        }
-        for (int k = 0; k < kept; ++k) {
-            if (!__any_sync(0xffffffffu, alive)) break;
-            if (alive && iou_gt(kept_box[k], kept_area[k], ob, area, p.thr)) alive = false;
-        }
-        // ---- ordered compaction of survivors ----
-        const uint32_t bal = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) warp_tot[warp] = __popc(bal);
-        __syncthreads();
-        int base = 0, m = 0;
+    for (int i = tid; i <= kBuckets; i += kNmsThreads) S.bstart[i] = p.bstart[static_cast<int64_t>(b) * (kBuckets + 1) + i];
+    __syncthreads();
+    const int n_sel = S.bstart[kBuckets];
+    const int n_limit = min(n_sel, p.max_nms);
+    int kept = 0;
+    int pos = 0, d = 0;
+
+    // Walks `cnt` sorted candidates whose slots are produced by slot_at(i), i in [0,cnt).
+    auto process_sorted = [&](auto slot_at, int cnt) {
+        int pdone = 0;
+        while (pdone < cnt && kept < p.max_det) {
+            const int need = p.max_det - kept;
+            const int sub = min(cnt - pdone, min(kSub, max(64, 2 * need)));
+            // ---- load sub-chunk: class-offset boxes (ops.py:289,295) ----
+            if (tid < sub) {
+                const uint32_t slot = slot_at(pdone + tid);
+                const float4 bx = p.st.box[seg + slot];
+                const float cls = p.cls_override ? p.cls_override[seg + slot]
+                                                 : static_cast<float>(p.st.key[seg + slot] % static_cast<uint32_t>(p.nc));
+                const float off = __fmul_rn(cls, p.max_wh);
+                const float4 ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
+                S.a_box[tid] = ob;
+                S.a_area[tid] = box_area_rn(ob);
+                S.a_slot[tid] = slot;
+                S.a_alive[tid] = 1;
+            }
+            __syncthreads();
+            // ---- phase 1: candidates x kept list, kNmsThreads/sub_p2 threads per candidate ----
+            if (kept > 0) {
+                int sub_p2 = 64;
+                while (sub_p2 < sub) sub_p2 <<= 1;
+                const int cand = tid & (sub_p2 - 1), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
+                if (cand < sub) {
+                    const float4 ob = S.a_box[cand];
+                    const float oa = S.a_area[cand];
+                    bool dead = false;
+                    for (int k = part; k < kept; k += nparts)
+                        dead |= iou_gt_fast(S.kept_box[k], S.kept_area[k], ob, oa, p.thr, band);
+                    if (dead) S.a_alive[cand] = 0;
+                }
+                __syncthreads();
+            }
+            // ---- ordered compaction of survivors (first kSub threads = 8 warps) ----
+            bool alive = false;
+            uint32_t bal = 0;
+            if (tid < kSub) {
+                alive = tid < sub && S.a_alive[tid];
+                bal = __ballot_sync(0xffffffffu, alive);
+                if (lane == 0) S.misc[warp] = __popc(bal);
+            }
+            __syncthreads();
+            int m = 0;
 #pragma unroll
-        for (int w = 0; w < kNmsThreads / 32; ++w) {
-            const int c = warp_tot[w];
-            base += (w < warp) ? c : 0;
-            m += c;
-        }
-        if (alive) {
-            const int pos = base + __popc(bal & lanemask_lt());
-            ch_box[pos] = ob;
-            ch_area[pos] = area;
-            ch_slot[pos] = slot;
-        }
-        __syncthreads();
-        // ---- phase 2: suppression bitmask among the m survivors (row i, bits j > i) ----
-        const int words = (m + 63) >> 6;
-        for (int item = tid; item < m * words; item += kNmsThreads) {
-            const int r = item / words, w = item - r * words;
-            if (w < (r >> 6)) continue;
-            const float4 rb = ch_box[r];
-            const float ra = ch_area[r];
-            unsigned long long bits = 0ull;
-            const int j0 = w << 6;
-            const int jn = min(64, m - j0);
-            for (int jj = max(0, r + 1 - j0); jj < jn; ++jj)
-                if (iou_gt(rb, ra, ch_box[j0 + jj], ch_area[j0 + jj], p.thr)) bits |= 1ull << jj;
-            mask[r * kChunkWords + w] = bits;
-        }
-        __syncthreads();
-        // ---- sweep (warp 0): lane w accumulates removal word w ----
-        if (warp == 0) {
-            unsigned long long remv = 0ull;
-            for (int g = 0; g < words && kept < p.max_det; ++g) {
-                const unsigned long long cur = __shfl_sync(0xffffffffu, remv, g);
-                const int nvalid = min(64, m - (g << 6));
-                unsigned long long live = ~cur & (nvalid == 64 ? ~0ull : ((1ull << nvalid) - 1ull));
-                while (live) {
-                    const int j = __ffsll(static_cast<long long>(live)) - 1;
-                    const int r = (g << 6) + j;
-                    if (lane == 0) {
-                        kept_box[kept] = ch_box[r];
-                        kept_area[kept] = ch_area[r];
-                        kept_slot[kept] = ch_slot[r];
+            for (int w = 0; w < kSubWords; ++w) m += S.misc[w];
+            if (alive) {
+                int base = 0;
+                for (int w = 0; w < warp; ++w) base += S.misc[w];
+                const int at = base + __popc(bal & lanemask_lt());
+                S.c_box[at] = S.a_box[tid];
+                S.c_area[at] = S.a_area[tid];
+                S.c_slot[at] = S.a_slot[tid];
+            }
+            __syncthreads();
+            // ---- phase 2: suppression bitmask among the m survivors (row r, bits j > r) ----
+            const int words = (m + 31) >> 5;
+            for (int item = tid; item < m * words; item += kNmsThreads) {
+                const int r = item / words, w = item - r * words;
+                if (w < (r >> 5)) continue;
+                const float4 rb = S.c_box[r];
+                const float ra = S.c_area[r];
+                uint32_t bits = 0u;
+                const int j0 = w << 5;
+                const int jn = min(32, m - j0);
+                for (int jj = max(0, r + 1 - j0); jj < jn; ++jj)
+                    if (iou_gt_fast(rb, ra, S.c_box[j0 + jj], S.c_area[j0 + jj], p.thr, band)) bits |= 1u << jj;
+                S.mask[r * kSubWords + w] = bits;
+            }
+            __syncthreads();
+            // ---- sweep (warp 0): lane w accumulates removal word w ----
+            if (warp == 0) {
+                uint32_t remv = 0u;
+                int kl = kept;
+                for (int g = 0; g < words && kl < p.max_det; ++g) {
+                    const uint32_t cur = __shfl_sync(0xffffffffu, remv, g);
+                    const int nvalid = min(32, m - (g << 5));
+                    const uint32_t live = ~cur & (nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u));
+                    const int r = (g << 5) + lane;
+                    const uint32_t diag = lane < nvalid ? S.mask[r * kSubWords + g] : 0u;
+                    uint32_t keptm;
+                    if (!__any_sync(0xffffffffu, ((live >> lane) & 1u) && (diag & live))) {
+                        keptm = live;  // no two live candidates of this group overlap: all are kept at once
+                    } else {
+                        keptm = 0u;
+                        uint32_t l = live;
+                        while (l) {
+                            const int j = __ffs(static_cast<int>(l)) - 1;
+                            keptm |= 1u << j;
+                            const uint32_t dj = __shfl_sync(0xffffffffu, diag, j);
+                            l &= ~dj;
+                            l &= l - 1u;
+                        }
                     }
-                    ++kept;
-                    if (kept >= p.max_det) break;
-                    const unsigned long long row = (lane >= g && lane < words) ? mask[r * kChunkWords + lane] : 0ull;
-                    remv |= row;
-                    const unsigned long long diag = __shfl_sync(0xffffffffu, row, g);
-                    live &= ~diag;
-                    live &= live - 1ull;  // drop bit j itself (lowest set bit; diag never has bits <= j)
+                    int c = __popc(keptm);
+                    if (kl + c > p.max_det) {  // keep only the first (max_det - kl) of them
+                        const int allow = p.max_det - kl;
+                        uint32_t t = keptm, res = 0u;
+                        for (int q = 0; q < allow; ++q) {
+                            const uint32_t low = t & (0u - t);
+                            res |= low;
+                            t ^= low;
+                        }
+                        keptm = res;
+                        c = allow;
+                    }
+                    if ((keptm >> lane) & 1u) {
+                        const int idx = kl + __popc(keptm & lanemask_lt());
+                        S.kept_box[idx] = S.c_box[r];
+                        S.kept_area[idx] = S.c_area[r];
+                        S.kept_slot[idx] = S.c_slot[r];
+                    }
+                    kl += c;
+                    if (lane > g && lane < words) {
+                        uint32_t t = keptm;
+                        while (t) {
+                            const int j = __ffs(static_cast<int>(t)) - 1;
+                            t &= t - 1u;
+                            remv |= S.mask[((g << 5) + j) * kSubWords + lane];
+                        }
+                    }
+                }
+                if (lane == 0) S.misc[16] = kl;
+            }
+            __syncthreads();
+            kept = S.misc[16];
+            pdone += sub;
+            __syncthreads();
+        }
+    };
+
+    while (pos < n_limit && kept < p.max_det) {
+        // ---- next chunk: largest run of whole buckets [d, d1) with <= kSortCap candidates ----
+        if (tid == 0) {
+            int lo = d + 1, hi = kBuckets;  // find largest d1 in [d+1, kBuckets] with bstart[d1] - pos <= kSortCap
+            if (S.bstart[lo] - pos > kSortCap) {
+                hi = lo;  // a single oversized bucket
+            } else {
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (S.bstart[mid] - pos <= kSortCap) lo = mid; else hi = mid - 1;
                 }
             }
-            if (lane == 0) s_kept = kept;
+            S.misc[17] = hi;
         }
         __syncthreads();
-        kept = s_kept;
+        const int d1 = S.misc[17];
+        const int end = S.bstart[d1];
+        const int m = end - pos;
+        __syncthreads();
+        if (m <= kSortCap) {
+            if (m > 0) {
+                int pw = 64;
+                while (pw < m) pw <<= 1;
+                for (int i = tid; i < pw; i += kNmsThreads)
+                    S.skey[i] = i < m ? ((static_cast<unsigned long long>(pkey[pos + i]) << 32) | (0xffffffffu - pval[pos + i])) : 0ull;
+                __syncthreads();
+                for (int k = 2; k <= pw; k <<= 1) {
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        for (int t = tid; t < (pw >> 1); t += kNmsThreads) {
+                            const int i = ((t / j) * 2 * j) + (t % j), q = i + j;
+                            const bool desc = (i & k) == 0;
+                            const unsigned long long x = S.skey[i], y = S.skey[q];
+                            if ((x < y) == desc) {
+                                S.skey[i] = y;
+                                S.skey[q] = x;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                }
+                process_sorted([&](int i) { return 0xffffffffu - static_cast<uint32_t>(S.skey[i]); }, min(m, n_limit - pos));
+            }
+        } else {
+            // ---- oversized bucket: stable LSD radix sort in global memory on (score bits desc, slot asc) ----
+            int *cnt = reinterpret_cast<int *>(S.skey);  // 256*17*4 = 17408 B <= skey..c_slot (21504 B), all idle during the sort
+            int *wt = S.misc;
+            const uint32_t *ik = pkey + pos, *iv = pval + pos;
+            uint32_t *ok = tkey + pos, *ov = tval + pos;
+            int slot_bits = 1;
+            while ((static_cast<int64_t>(1) << slot_bits) < p.st.cap) ++slot_bits;
+            const int passes_slot = (slot_bits + 7) / 8;
+            for (int ps = 0; ps < passes_slot + 4; ++ps) {
+                const int sh = ps < passes_slot ? ps * 8 : (ps - passes_slot) * 8;
+                if (ps < passes_slot)
+                    radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t, uint32_t v) { return (v >> sh) & 255u; }, cnt, wt);
+                else
+                    radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t k, uint32_t) { return ((~k) >> sh) & 255u; }, cnt, wt);
+                const uint32_t *tk = ik, *tv = iv;
+                ik = ok; iv = ov;
+                ok = const_cast<uint32_t *>(tk); ov = const_cast<uint32_t *>(tv);
+            }
+            const uint32_t *sorted = iv;
+            const int lim = min(m, n_limit - pos);
+            for (int piece = 0; piece < lim && kept < p.max_det; piece += kSortCap) {
+                process_sorted([&](int i) { return sorted[piece + i]; }, min(kSortCap, lim - piece));
+            }
+        }
+        pos = end;
+        d = d1;
     }
     // ---- publish ----
-    for (int k = tid; k < kept; k += kNmsThreads) p.kept_slot[static_cast<int64_t>(b) * p.max_det + k] = kept_slot[k];
+    for (int k = tid; k < kept; k += kNmsThreads) p.kept_slot[static_cast<int64_t>(b) * p.max_det + k] = S.kept_slot[k];
     if (tid == 0) p.counts[b] = kept;
 }
 
@@ -151,7 +413,7 @@ struct GatherParams {
     float *out;                 // [B, max_det, 6+nm]
     int32_t *kept_index;        // [B*max_det] or nullptr
     int32_t max_det, nc, nm;
-    int32_t mode;               // 0 decoded, 1 fused, 2 merge, 3 none (boxes only)
+    int32_t mode;               // 0 decoded, 1 fused, 2 merge
     // mode 0
     const float *pred;
     int32_t channels;

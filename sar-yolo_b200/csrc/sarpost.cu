@@ -59,7 +59,7 @@ static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * 
 // workspace layout
 // ------------------------------------------------------------------------------------------------
 struct Layout {
-    int64_t box, score, key, cls, key_a, val_a, key_b, val_b, tile_count, tile_off, n_sorted, kept_slot, total;
+    int64_t box, score, key, cls, key_a, val_a, key_b, val_b, tile_count, bstart, kept_slot, total;
 };
 
 static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_det, bool with_cls) {
@@ -80,8 +80,7 @@ static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_d
     L.key_b = take(slots * 4);
     L.val_b = take(slots * 4);
     L.tile_count = take(batch * tpi * 4);
-    L.tile_off = take(batch * (tpi + 1) * 4);
-    L.n_sorted = take(batch * 4);
+    L.bstart = take(batch * (kBuckets + 1) * 4);
     L.kept_slot = take(batch * max_det * 4);
     L.total = o;
     return L;
@@ -90,7 +89,7 @@ static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_d
 struct Pipeline {
     CandStore st;
     uint32_t *key_a, *val_a, *key_b, *val_b;
-    int32_t *tile_off, *n_sorted;
+    int32_t *bstart;
     uint32_t *kept_slot;
     float *cls;
 };
@@ -113,8 +112,7 @@ static int bind_workspace(void *ws, int64_t ws_bytes, int64_t batch, int64_t cap
     P->val_a = reinterpret_cast<uint32_t *>(base + L.val_a);
     P->key_b = reinterpret_cast<uint32_t *>(base + L.key_b);
     P->val_b = reinterpret_cast<uint32_t *>(base + L.val_b);
-    P->tile_off = reinterpret_cast<int32_t *>(base + L.tile_off);
-    P->n_sorted = reinterpret_cast<int32_t *>(base + L.n_sorted);
+    P->bstart = reinterpret_cast<int32_t *>(base + L.bstart);
     P->kept_slot = reinterpret_cast<uint32_t *>(base + L.kept_slot);
     P->cls = with_cls ? reinterpret_cast<float *>(base + L.cls) : nullptr;
     return SARPOST_OK;
@@ -292,33 +290,34 @@ static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandSto
 // K2 + K4 + K5 on a filled candidate store.
 static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, int nc, GatherParams gp, float *out,
                     int32_t *counts, int32_t *kept_index, cudaStream_t s) {
-    SortParams sp;
+    PartParams sp;
     sp.st = P.st;
-    sp.key_a = P.key_a;
-    sp.val_a = P.val_a;
-    sp.key_b = P.key_b;
-    sp.val_b = P.val_b;
-    sp.tile_off = P.tile_off;
-    sp.n_sorted = P.n_sorted;
+    sp.part_key = P.key_a;
+    sp.part_val = P.val_a;
+    sp.bstart = P.bstart;
     sp.max_nms = prm->max_nms;
-    k2_select_sort<<<batch, kSortThreads, 0, s>>>(sp);
+    k2_select_partition<<<batch, kPartThreads, 0, s>>>(sp);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     stage_mark(2, s);
 
     NmsParams np;
     np.st = P.st;
-    np.sorted = P.val_a;
-    np.n_sorted = P.n_sorted;
+    np.part_key = P.key_a;
+    np.part_val = P.val_a;
+    np.tmp_key = P.key_b;
+    np.tmp_val = P.val_b;
+    np.bstart = P.bstart;
     np.kept_slot = P.kept_slot;
     np.counts = counts;
     np.max_det = prm->max_det;
+    np.max_nms = prm->max_nms;
     np.nc = nc;
     np.cls_override = P.cls;
     np.max_wh = prm->agnostic ? 0.0f : prm->max_wh;
     np.thr = iou_thr_float(prm->iou_thres);
-    const int nms_smem = prm->max_det * 24;
-    CUDA_TRY(cudaFuncSetAttribute(k4_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 24));
+    const int nms_smem = static_cast<int>(nms_smem_bytes(prm->max_det));
+    CUDA_TRY(cudaFuncSetAttribute(k4_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(nms_smem_bytes(4096))));
     k4_nms<<<batch, kNmsThreads, nms_smem, s>>>(np);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
