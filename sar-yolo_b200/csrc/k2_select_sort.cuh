@@ -71,27 +71,45 @@ __device__ __forceinline__ int block_excl_scan_1024(int v, int *warp_tot /*[kPar
     return res;
 }
 
-// Visit every candidate of the image: fn(slot, score_bits).  Warp per tile; when the tile region is
-// exactly kTileA slots each lane fetches its 4 scores with one 128-bit load.
+// Visit every candidate of the image: fn(slot, score_bits).  Each warp owns a contiguous run of tiles;
+// the tile counts of the run are fetched with one coalesced load and, when the tile region is exactly
+// kTileA slots, the scores of kUnroll tiles are fetched with independent 128-bit loads before any of
+// them is consumed (the loop is latency-bound: one CTA per image, data in L2).
 template <class Fn>
 __device__ __forceinline__ void for_each_candidate(const CandStore &st, const int32_t *tcount, const float *score,
                                                    const Fn &fn) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int tpw = (st.tpi + nwarps - 1) / nwarps;
+    const int t_begin = warp * tpw, t_end = min(st.tpi, t_begin + tpw);
     if (st.region == kTileA) {
-        for (int t = warp; t < st.tpi; t += nwarps) {
-            const int c = tcount[t];
-            const int i0 = lane * 4;
-            if (i0 < c) {
-                const uint32_t slot = static_cast<uint32_t>(t) * kTileA + i0;
-                const uint4 v = *reinterpret_cast<const uint4 *>(score + slot);
-                fn(slot, v.x);
-                if (i0 + 1 < c) fn(slot + 1, v.y);
-                if (i0 + 2 < c) fn(slot + 2, v.z);
-                if (i0 + 3 < c) fn(slot + 3, v.w);
+        constexpr int kUnroll = 8;
+        for (int tb = t_begin; tb < t_end; tb += 32) {
+            const int my_c = (tb + lane < t_end) ? tcount[tb + lane] : 0;
+            const int nt = min(32, t_end - tb);
+            for (int u0 = 0; u0 < nt; u0 += kUnroll) {
+                uint4 v[kUnroll];
+                int c[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    c[u] = __shfl_sync(0xffffffffu, my_c, (u0 + u) & 31);
+                    if (u0 + u >= nt) c[u] = 0;
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (lane * 4 < c[u])
+                        v[u] = *reinterpret_cast<const uint4 *>(score + static_cast<size_t>(tb + u0 + u) * kTileA + lane * 4);
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int i0 = lane * 4;
+                    const uint32_t slot = static_cast<uint32_t>(tb + u0 + u) * kTileA + i0;
+                    if (i0 < c[u]) fn(slot, v[u].x);
+                    if (i0 + 1 < c[u]) fn(slot + 1, v[u].y);
+                    if (i0 + 2 < c[u]) fn(slot + 2, v[u].z);
+                    if (i0 + 3 < c[u]) fn(slot + 3, v[u].w);
+                }
             }
         }
     } else {
-        for (int t = warp; t < st.tpi; t += nwarps) {
+        for (int t = t_begin; t < t_end; ++t) {
             const int c = tcount[t];
             for (int i = lane; i < c; i += 32) {
                 const uint32_t slot = static_cast<uint32_t>(t) * st.region + i;

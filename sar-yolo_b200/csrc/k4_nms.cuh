@@ -21,6 +21,20 @@
 
 namespace sarpost {
 
+#ifdef SARPOST_PHASE_PROF
+__device__ unsigned long long g_phase[16];
+#define PROF_MARK(i)                                                         \
+    do {                                                                     \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                           \
+            const long long _t = clock64();                                  \
+            g_phase[i] += static_cast<unsigned long long>(_t - prof_t);      \
+            prof_t = _t;                                                     \
+        }                                                                    \
+    } while (0)
+#else
+#define PROF_MARK(i) do {} while (0)
+#endif
+
 constexpr int kNmsThreads = 512;
 constexpr int kNmsWarps = kNmsThreads / 32;
 constexpr int kSortCap = 1024;   // candidates sorted in shared memory at once
@@ -41,11 +55,12 @@ struct NmsParams {
     float thr;                       // largest float <= iou_thres
 };
 
-// IoU(a,b) > thr, bit-exact to the fp32 division of the reference but without paying for it on
-// every pair: a 2-instruction approximate quotient decides unless it lands within a few ulp of
-// the threshold, in which case the correctly rounded division is evaluated.
-__device__ __forceinline__ bool iou_gt_fast(const float4 a, const float area_a, const float4 b, const float area_b,
-                                            const float thr, const float band) {
+// IoU(a,b) > thr, bit-exact to the fp32 division of the reference but without paying for it on every
+// pair: a 2-instruction approximate quotient decides unless it lands within a few ulp of the threshold
+// (`border`), in which case the caller re-evaluates the pair with the correctly rounded division
+// (common.cuh iou_gt).  Branch-free so that callers can keep several pairs in flight.
+__device__ __forceinline__ bool iou_gt_approx(const float4 a, const float area_a, const float4 b, const float area_b,
+                                              const float thr, const float band, bool &border) {
     const float xx1 = fmaxf(a.x, b.x);
     const float yy1 = fmaxf(a.y, b.y);
     const float xx2 = fminf(a.z, b.z);
@@ -55,9 +70,8 @@ __device__ __forceinline__ bool iou_gt_fast(const float4 a, const float area_a, 
     const float inter = __fmul_rn(w, h);
     const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
     const float q = __fdividef(inter, uni);  // <= 2 ulp for |uni| < 2^126
-    bool gt = q > thr;
-    if (fabsf(__fsub_rn(q, thr)) <= band) gt = __fdiv_rn(inter, uni) > thr;  // NaN skips this and stays false
-    return gt;
+    border = fabsf(__fsub_rn(q, thr)) <= band;  // false for NaN
+    return q > thr;
 }
 
 // One stable LSD radix pass (8-bit digit) over n (key,val) pairs in global memory, kNmsThreads threads.
@@ -129,67 +143,42 @@ __device__ __forceinline__ void radix_pass_global(const uint32_t *in_key, const 
     __syncthreads();
 }
 
-// shared-memory carve-up (dynamic): see k4_nms
-struct NmsSmem {
-    float4 *kept_box;
-    float *kept_area;
-    uint32_t *kept_slot;
-    int32_t *bstart;               // [kBuckets + 1]
-    unsigned long long *skey;      // [kSortCap] composite keys
-    float4 *a_box;                 // [kSub] sub-chunk candidates (class-offset boxes)
-    float *a_area;                 // [kSub]
-    uint32_t *a_slot;              // [kSub]
-    int32_t *a_alive;              // [kSub]
-    float4 *c_box;                 // [kSub] survivors
-    float *c_area;
-    uint32_t *c_slot;
-    uint32_t *mask;                // [kSub * kSubWords]
-    int32_t *misc;                 // [32]
-};
-
-__host__ __device__ inline size_t nms_smem_bytes(int max_det) {
-    size_t b = 0;
-    b += static_cast<size_t>(max_det) * 16 + static_cast<size_t>(max_det) * 4 * 2;
-    b = (b + 15) / 16 * 16;
-    b += (kBuckets + 1 + 3) / 4 * 4 * 4;
-    b += kSortCap * 8;
-    b += kSub * (16 + 4 + 4 + 4);
-    b += kSub * (16 + 4 + 4);
-    b += kSub * kSubWords * 4;
-    b += 32 * 4;
-    return b + 16;
-}
+// dynamic shared memory: kept_box[max_det] float4 | kept_area[max_det] | kept_slot[max_det]
+__host__ __device__ inline size_t nms_smem_bytes(int max_det) { return static_cast<size_t>(max_det) * 24; }
 
 __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__ NmsParams p) {
-    extern __shared__ __align__(16) unsigned char nms_smem[];
-    NmsSmem S;
-    {
-        unsigned char *q = nms_smem;
-        S.kept_box = reinterpret_cast<float4 *>(q); q += static_cast<size_t>(p.max_det) * 16;
-        S.kept_area = reinterpret_cast<float *>(q); q += static_cast<size_t>(p.max_det) * 4;
-        S.kept_slot = reinterpret_cast<uint32_t *>(q); q += static_cast<size_t>(p.max_det) * 4;
-        q = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(q) + 15) & ~uintptr_t(15));
-        S.bstart = reinterpret_cast<int32_t *>(q); q += (kBuckets + 1 + 3) / 4 * 4 * 4;
-        S.skey = reinterpret_cast<unsigned long long *>(q); q += kSortCap * 8;  // fallback sort aliases skey..c_slot
-        S.a_box = reinterpret_cast<float4 *>(q); q += kSub * 16;
-        S.c_box = reinterpret_cast<float4 *>(q); q += kSub * 16;
-        S.a_area = reinterpret_cast<float *>(q); q += kSub * 4;
-        S.a_slot = reinterpret_cast<uint32_t *>(q); q += kSub * 4;
-        S.a_alive = reinterpret_cast<int32_t *>(q); q += kSub * 4;
-        S.c_area = reinterpret_cast<float *>(q); q += kSub * 4;
-        S.c_slot = reinterpret_cast<uint32_t *>(q); q += kSub * 4;
-        S.mask = reinterpret_cast<uint32_t *>(q); q += kSub * kSubWords * 4;
-        S.misc = reinterpret_cast<int32_t *>(q);
-    }
+    // All shared arrays are referenced through their symbols (never through pointers kept in
+    // structs) so every access compiles to LDS/STS rather than a generic LD/ST.
+    extern __shared__ float4 dyn_kept[];
+    __shared__ int32_t s_bstart[kBuckets + 4];
+    __shared__ uint32_t s_mask[kSub * kSubWords];
+    __shared__ float s_a_area[kSub], s_c_area[kSub];
+    __shared__ uint32_t s_a_slot[kSub], s_c_slot[kSub];
+    __shared__ int32_t s_a_alive[kSub];
+    __shared__ int32_t s_misc[32];
+    // union region: skey[kSortCap] u64 | a_box[kSub] | c_box[kSub]; the fallback radix sort aliases all of it
+    __shared__ __align__(16) unsigned char s_uni[256 * (kNmsWarps + 1) * 4];
+    static_assert(sizeof(s_uni) >= kSortCap * 8 + 2 * kSub * 16, "union region too small");
+#define KEPT_BOX (dyn_kept)
+#define KEPT_AREA (reinterpret_cast<float *>(dyn_kept + p.max_det))
+#define KEPT_SLOT (reinterpret_cast<uint32_t *>(dyn_kept + p.max_det) + p.max_det)
+#define SKEY (reinterpret_cast<unsigned long long *>(s_uni))
+#define A_BOX (reinterpret_cast<float4 *>(s_uni + kSortCap * 8))
+#define C_BOX (reinterpret_cast<float4 *>(s_uni + kSortCap * 8 + kSub * 16))
+
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
     uint32_t *pkey = p.part_key + seg, *pval = p.part_val + seg;
     uint32_t *tkey = p.tmp_key + seg, *tval = p.tmp_val + seg;
     const float band = fmaxf(p.thr * 2e-6f, 1e-37f);
+#ifdef SARPOST_PHASE_PROF
+    long long prof_t = clock64();
+#endif
 
-    for (int i = tid; i <= kBuckets; i += kNmsThreads) S.bstart[i] = p.bstart[static_cast<int64_t>(b) * (kBuckets + 1) + i];
+    for (int i = tid; i <= kBuckets; i += kNmsThreads) s_bstart[i] = p.bstart[static_cast<int64_t>(b) * (kBuckets + 1) + i];
     __syncthreads();
-    const int n_sel = S.bstart[kBuckets];
+    PROF_MARK(0);
+    const int n_sel = s_bstart[kBuckets];
     const int n_limit = min(n_sel, p.max_nms);
     int kept = 0;
     int pos = 0, d = 0;
@@ -208,170 +197,211 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                                                  : static_cast<float>(p.st.key[seg + slot] % static_cast<uint32_t>(p.nc));
                 const float off = __fmul_rn(cls, p.max_wh);
                 const float4 ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
-                S.a_box[tid] = ob;
-                S.a_area[tid] = box_area_rn(ob);
-                S.a_slot[tid] = slot;
-                S.a_alive[tid] = 1;
+                A_BOX[tid] = ob;
+                s_a_area[tid] = box_area_rn(ob);
+                s_a_slot[tid] = slot;
+                s_a_alive[tid] = 1;
             }
             __syncthreads();
+            PROF_MARK(3);
             // ---- phase 1: candidates x kept list, kNmsThreads/sub_p2 threads per candidate ----
             if (kept > 0) {
                 int sub_p2 = 64;
                 while (sub_p2 < sub) sub_p2 <<= 1;
                 const int cand = tid & (sub_p2 - 1), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
                 if (cand < sub) {
-                    const float4 ob = S.a_box[cand];
-                    const float oa = S.a_area[cand];
-                    bool dead = false;
-                    for (int k = part; k < kept; k += nparts)
-                        dead |= iou_gt_fast(S.kept_box[k], S.kept_area[k], ob, oa, p.thr, band);
-                    if (dead) S.a_alive[cand] = 0;
+                    const float4 ob = A_BOX[cand];
+                    const float oa = s_a_area[cand];
+                    bool dead = false, any_border = false;
+#pragma unroll 4
+                    for (int k = part; k < kept; k += nparts) {
+                        bool bd;
+                        dead |= iou_gt_approx(KEPT_BOX[k], KEPT_AREA[k], ob, oa, p.thr, band, bd);
+                        any_border |= bd;
+                    }
+                    if (any_border && !dead)  // rare: a quotient within a few ulp of the threshold
+                        for (int k = part; k < kept; k += nparts) dead |= iou_gt(KEPT_BOX[k], KEPT_AREA[k], ob, oa, p.thr);
+                    if (dead) s_a_alive[cand] = 0;
                 }
                 __syncthreads();
             }
+            PROF_MARK(4);
             // ---- ordered compaction of survivors (first kSub threads = 8 warps) ----
             bool alive = false;
             uint32_t bal = 0;
             if (tid < kSub) {
-                alive = tid < sub && S.a_alive[tid];
+                alive = tid < sub && s_a_alive[tid];
                 bal = __ballot_sync(0xffffffffu, alive);
-                if (lane == 0) S.misc[warp] = __popc(bal);
+                if (lane == 0) s_misc[warp] = __popc(bal);
             }
             __syncthreads();
             int m = 0;
 #pragma unroll
-            for (int w = 0; w < kSubWords; ++w) m += S.misc[w];
+            for (int w = 0; w < kSubWords; ++w) m += s_misc[w];
             if (alive) {
                 int base = 0;
-                for (int w = 0; w < warp; ++w) base += S.misc[w];
+                for (int w = 0; w < warp; ++w) base += s_misc[w];
                 const int at = base + __popc(bal & lanemask_lt());
-                S.c_box[at] = S.a_box[tid];
-                S.c_area[at] = S.a_area[tid];
-                S.c_slot[at] = S.a_slot[tid];
+                C_BOX[at] = A_BOX[tid];
+                s_c_area[at] = s_a_area[tid];
+                s_c_slot[at] = s_a_slot[tid];
             }
             __syncthreads();
+            PROF_MARK(5);
             // ---- phase 2: suppression bitmask among the m survivors (row r, bits j > r) ----
+            // one warp per (row, 32-candidate word): lane j tests the pair (r, 32w + j), a ballot packs the word
             const int words = (m + 31) >> 5;
-            for (int item = tid; item < m * words; item += kNmsThreads) {
-                const int r = item / words, w = item - r * words;
-                if (w < (r >> 5)) continue;
-                const float4 rb = S.c_box[r];
-                const float ra = S.c_area[r];
-                uint32_t bits = 0u;
-                const int j0 = w << 5;
-                const int jn = min(32, m - j0);
-                for (int jj = max(0, r + 1 - j0); jj < jn; ++jj)
-                    if (iou_gt_fast(rb, ra, S.c_box[j0 + jj], S.c_area[j0 + jj], p.thr, band)) bits |= 1u << jj;
-                S.mask[r * kSubWords + w] = bits;
-            }
-            __syncthreads();
-            // ---- sweep (warp 0): lane w accumulates removal word w ----
-            if (warp == 0) {
-                uint32_t remv = 0u;
-                int kl = kept;
-                for (int g = 0; g < words && kl < p.max_det; ++g) {
-                    const uint32_t cur = __shfl_sync(0xffffffffu, remv, g);
-                    const int nvalid = min(32, m - (g << 5));
-                    const uint32_t live = ~cur & (nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u));
-                    const int r = (g << 5) + lane;
-                    const uint32_t diag = lane < nvalid ? S.mask[r * kSubWords + g] : 0u;
-                    uint32_t keptm;
-                    if (!__any_sync(0xffffffffu, ((live >> lane) & 1u) && (diag & live))) {
-                        keptm = live;  // no two live candidates of this group overlap: all are kept at once
-                    } else {
-                        keptm = 0u;
-                        uint32_t l = live;
-                        while (l) {
-                            const int j = __ffs(static_cast<int>(l)) - 1;
-                            keptm |= 1u << j;
-                            const uint32_t dj = __shfl_sync(0xffffffffu, diag, j);
-                            l &= ~dj;
-                            l &= l - 1u;
+            {
+                const int n_items = m * words;
+                for (int it0 = warp; it0 < n_items; it0 += 4 * kNmsWarps) {
+                    bool gt[4], bd[4];
+                    int rr[4], ww[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int item = it0 + u * kNmsWarps;
+                        rr[u] = item / words;
+                        ww[u] = item - rr[u] * words;
+                        gt[u] = bd[u] = false;
+                        if (item < n_items && ww[u] >= (rr[u] >> 5)) {
+                            const int j = (ww[u] << 5) + lane;
+                            if (j > rr[u] && j < m)
+                                gt[u] = iou_gt_approx(C_BOX[rr[u]], s_c_area[rr[u]], C_BOX[j], s_c_area[j], p.thr, band, bd[u]);
                         }
                     }
-                    int c = __popc(keptm);
-                    if (kl + c > p.max_det) {  // keep only the first (max_det - kl) of them
-                        const int allow = p.max_det - kl;
-                        uint32_t t = keptm, res = 0u;
-                        for (int q = 0; q < allow; ++q) {
-                            const uint32_t low = t & (0u - t);
-                            res |= low;
-                            t ^= low;
-                        }
-                        keptm = res;
-                        c = allow;
-                    }
-                    if ((keptm >> lane) & 1u) {
-                        const int idx = kl + __popc(keptm & lanemask_lt());
-                        S.kept_box[idx] = S.c_box[r];
-                        S.kept_area[idx] = S.c_area[r];
-                        S.kept_slot[idx] = S.c_slot[r];
-                    }
-                    kl += c;
-                    if (lane > g && lane < words) {
-                        uint32_t t = keptm;
-                        while (t) {
-                            const int j = __ffs(static_cast<int>(t)) - 1;
-                            t &= t - 1u;
-                            remv |= S.mask[((g << 5) + j) * kSubWords + lane];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int item = it0 + u * kNmsWarps;
+                        if (item < n_items && ww[u] >= (rr[u] >> 5)) {  // warp-uniform
+                            if (bd[u]) {
+                                const int j = (ww[u] << 5) + lane;
+                                gt[u] = iou_gt(C_BOX[rr[u]], s_c_area[rr[u]], C_BOX[j], s_c_area[j], p.thr);
+                            }
+                            const uint32_t bits = __ballot_sync(0xffffffffu, gt[u]);
+                            if (lane == 0) s_mask[rr[u] * kSubWords + ww[u]] = bits;
                         }
                     }
                 }
-                if (lane == 0) S.misc[16] = kl;
             }
             __syncthreads();
-            kept = S.misc[16];
+            PROF_MARK(6);
+            // ---- sweep (warp 0) ----
+            if (warp == 0) {
+                uint32_t km[kSubWords];  // kept bits of the groups resolved so far (warp-uniform)
+#pragma unroll
+                for (int g = 0; g < kSubWords; ++g) km[g] = 0u;
+                int kl = kept;
+#pragma unroll
+                for (int g = 0; g < kSubWords; ++g) {
+                    if (g < words && kl < p.max_det) {
+                        // removal word of group g = OR over the rows kept in earlier groups (lane = row)
+                        uint32_t rem = 0u;
+#pragma unroll
+                        for (int g2 = 0; g2 < g; ++g2)
+                            if ((km[g2] >> lane) & 1u) rem |= s_mask[((g2 << 5) + lane) * kSubWords + g];
+                        rem = __reduce_or_sync(0xffffffffu, rem);
+                        const int nvalid = min(32, m - (g << 5));
+                        const uint32_t live = ~rem & (nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u));
+                        const int r = (g << 5) + lane;
+                        const uint32_t diag = lane < nvalid ? s_mask[r * kSubWords + g] : 0u;
+                        uint32_t keptm;
+                        if (!__any_sync(0xffffffffu, ((live >> lane) & 1u) && (diag & live))) {
+                            keptm = live;  // no two live candidates of this group overlap: all are kept at once
+                        } else {
+                            keptm = 0u;
+                            uint32_t l = live;
+                            while (l) {
+                                const int j = __ffs(static_cast<int>(l)) - 1;
+                                keptm |= 1u << j;
+                                const uint32_t dj = __shfl_sync(0xffffffffu, diag, j);
+                                l &= ~dj;
+                                l &= l - 1u;
+                            }
+                        }
+                        int c = __popc(keptm);
+                        if (kl + c > p.max_det) {  // keep only the first (max_det - kl) of them
+                            const int allow = p.max_det - kl;
+                            uint32_t t = keptm, res = 0u;
+                            for (int q = 0; q < allow; ++q) {
+                                const uint32_t low = t & (0u - t);
+                                res |= low;
+                                t ^= low;
+                            }
+                            keptm = res;
+                            c = allow;
+                        }
+                        if ((keptm >> lane) & 1u) {
+                            const int idx = kl + __popc(keptm & lanemask_lt());
+                            KEPT_BOX[idx] = C_BOX[r];
+                            KEPT_AREA[idx] = s_c_area[r];
+                            KEPT_SLOT[idx] = s_c_slot[r];
+                        }
+                        kl += c;
+                        km[g] = keptm;
+                    }
+                }
+                if (lane == 0) s_misc[16] = kl;
+            }
+            __syncthreads();
+            kept = s_misc[16];
             pdone += sub;
             __syncthreads();
+            PROF_MARK(7);
         }
     };
 
     while (pos < n_limit && kept < p.max_det) {
         // ---- next chunk: largest run of whole buckets [d, d1) with <= kSortCap candidates ----
         if (tid == 0) {
-            int lo = d + 1, hi = kBuckets;  // find largest d1 in [d+1, kBuckets] with bstart[d1] - pos <= kSortCap
-            if (S.bstart[lo] - pos > kSortCap) {
-                hi = lo;  // a single oversized bucket
+            // largest d1 in [d+1, kBuckets] with bstart[d1] - pos <= cap; the first chunk is smaller because
+            // NMS usually finishes inside it (max_det keeps) and sorting cost grows with the chunk
+            const int cap = pos == 0 ? min(kSortCap, max(256, 2 * p.max_det)) : kSortCap;
+            int lo = d + 1, hi = kBuckets;
+            if (s_bstart[lo] - pos > cap) {
+                hi = lo;  // even one bucket exceeds the target (it is still sorted in smem if it fits kSortCap)
             } else {
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
-                    if (S.bstart[mid] - pos <= kSortCap) lo = mid; else hi = mid - 1;
+                    if (s_bstart[mid] - pos <= cap) lo = mid; else hi = mid - 1;
                 }
             }
-            S.misc[17] = hi;
+            s_misc[17] = hi;
         }
         __syncthreads();
-        const int d1 = S.misc[17];
-        const int end = S.bstart[d1];
+        const int d1 = s_misc[17];
+        const int end = s_bstart[d1];
         const int m = end - pos;
         __syncthreads();
+        PROF_MARK(1);
         if (m <= kSortCap) {
             if (m > 0) {
-                int pw = 64;
-                while (pw < m) pw <<= 1;
+                int lpw = 6;
+                while ((1 << lpw) < m) ++lpw;
+                const int pw = 1 << lpw;
                 for (int i = tid; i < pw; i += kNmsThreads)
-                    S.skey[i] = i < m ? ((static_cast<unsigned long long>(pkey[pos + i]) << 32) | (0xffffffffu - pval[pos + i])) : 0ull;
+                    SKEY[i] = i < m ? ((static_cast<unsigned long long>(pkey[pos + i]) << 32) | (0xffffffffu - pval[pos + i])) : 0ull;
                 __syncthreads();
-                for (int k = 2; k <= pw; k <<= 1) {
-                    for (int j = k >> 1; j > 0; j >>= 1) {
+                // bitonic network, descending
+                for (int lk = 1; lk <= lpw; ++lk) {
+                    for (int lj = lk - 1; lj >= 0; --lj) {
                         for (int t = tid; t < (pw >> 1); t += kNmsThreads) {
-                            const int i = ((t / j) * 2 * j) + (t % j), q = i + j;
-                            const bool desc = (i & k) == 0;
-                            const unsigned long long x = S.skey[i], y = S.skey[q];
+                            const int i = ((t >> lj) << (lj + 1)) | (t & ((1 << lj) - 1)), q = i | (1 << lj);
+                            const bool desc = ((i >> lk) & 1) == 0;
+                            const unsigned long long x = SKEY[i], y = SKEY[q];
                             if ((x < y) == desc) {
-                                S.skey[i] = y;
-                                S.skey[q] = x;
+                                SKEY[i] = y;
+                                SKEY[q] = x;
                             }
                         }
                         __syncthreads();
                     }
                 }
-                process_sorted([&](int i) { return 0xffffffffu - static_cast<uint32_t>(S.skey[i]); }, min(m, n_limit - pos));
+                PROF_MARK(2);
+                process_sorted([&](int i) { return 0xffffffffu - static_cast<uint32_t>(SKEY[i]); }, min(m, n_limit - pos));
             }
         } else {
             // ---- oversized bucket: stable LSD radix sort in global memory on (score bits desc, slot asc) ----
-            int *cnt = reinterpret_cast<int *>(S.skey);  // 256*17*4 = 17408 B <= skey..c_slot (21504 B), all idle during the sort
-            int *wt = S.misc;
+            int *cnt = reinterpret_cast<int *>(s_uni);
+            int *wt = s_misc;
             const uint32_t *ik = pkey + pos, *iv = pval + pos;
             uint32_t *ok = tkey + pos, *ov = tval + pos;
             int slot_bits = 1;
@@ -397,8 +427,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         d = d1;
     }
     // ---- publish ----
-    for (int k = tid; k < kept; k += kNmsThreads) p.kept_slot[static_cast<int64_t>(b) * p.max_det + k] = S.kept_slot[k];
+    for (int k = tid; k < kept; k += kNmsThreads) p.kept_slot[static_cast<int64_t>(b) * p.max_det + k] = KEPT_SLOT[k];
     if (tid == 0) p.counts[b] = kept;
+    PROF_MARK(8);
+#undef KEPT_BOX
+#undef KEPT_AREA
+#undef KEPT_SLOT
+#undef SKEY
+#undef A_BOX
+#undef C_BOX
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -508,6 +508,19 @@ int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const 
     return run_tail(P, n_frames, params, 1, gp, out, counts, kept_index, s);
 }
 
+#ifdef SARPOST_PHASE_PROF
+// debug builds only (not part of include/sarpost.h): cycles per K4 phase of block 0, accumulated
+int32_t sarpost_debug_phase_cycles(unsigned long long *out16, int32_t reset) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (out16) CUDA_TRY(cudaMemcpyFromSymbol(out16, g_phase, sizeof(unsigned long long) * 16));
+    if (reset) {
+        unsigned long long z[16] = {0};
+        CUDA_TRY(cudaMemcpyToSymbol(g_phase, z, sizeof(z)));
+    }
+    return SARPOST_OK;
+}
+#endif
+
 }  // extern "C"
 
 #include "host_ctx.inl"
