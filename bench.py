@@ -274,7 +274,7 @@ def main():
                 "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md 6.65 TB/s)",
                 "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                 "bytes_per_launch": k1_bytes, "ms_per_launch": stage[0], "traffic": None,
-                "stage_ms": {"k1_candidates": stage[0], "k2_select_sort": stage[1], "k4_nms": stage[2], "k5_gather": stage[3]}}
+                "stage_ms": {"k1_candidates": stage[0], "k2_k4_select_sort_nms": stage[1], "k5_gather": stage[2], "whole_call": stage[3]}}
     prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(prof):
         try:

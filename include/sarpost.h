@@ -148,7 +148,7 @@ int32_t sarpost_host_ctx_last_traffic(const sarpost_host_ctx_t *ctx, int64_t *h2
  * Introspection for benchmarks/tests: number of kernels the last call on this thread launched, and
  * optional per-stage CUDA-event timing.  When stage timing is enabled the calls record events around
  * every stage on the caller's stream; sarpost_stage_times() synchronises those events and returns
- * milliseconds for {candidates(K1), select+sort(K2), nms(K4), gather(K5)}.
+ * milliseconds for {K1 candidates (incl. histogram memset), K2-K4 select+sort+NMS, K5 gather, whole call}.
  */
 int32_t sarpost_last_launch_count(void);
 int32_t sarpost_set_stage_timing(int32_t enabled);

@@ -24,10 +24,23 @@ struct CandStore {
     float *score;       // [B*cap]
     uint32_t *key;      // [B*cap] anchor*nc + cls  (merge: tile*dets_per_tile + row)
     int32_t *tile_count;// [B*tpi]
+    int32_t *hist;      // [B*kBuckets] per-image SAMPLED histogram of score_bucket(): candidates of every
+                        // kHistSample-th anchor (zeroed before K1); only steers chunk sizes, never results
     int64_t cap;        // slots per image
     int32_t tpi;        // tiles per image
     int32_t region;     // slots per tile region
 };
+
+// Monotone score -> bucket map used for top-k selection and lazy sorting: 16 octaves below 1.0 at
+// 8 mantissa bits (relative width 0.4 %); everything lower shares bucket 0, everything >= 1.0 bucket 4095.
+constexpr int kBuckets = 4096;
+constexpr int kHistSample = 8;  // K1 histograms the candidates of anchors with (anchor % kHistSample) == 0
+constexpr int kBucketShift = 15;
+constexpr int kBucketBase = (0x3F800000 >> kBucketShift) - (kBuckets - 1);
+__device__ __forceinline__ int score_bucket(uint32_t bits) {
+    const int b = static_cast<int>(bits >> kBucketShift) - kBucketBase;
+    return min(max(b, 0), kBuckets - 1);
+}
 
 // fp32 sigmoid as torch computes it: 1 / (1 + exp(-x)), each step rounded (head.py:131,249).
 __device__ __forceinline__ float sigmoid_rn(float x) {

@@ -128,6 +128,8 @@ __device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, u
         st.tile_count[static_cast<int64_t>(b) * st.tpi + tile_in_image] = tot;
     }
     int64_t pos = static_cast<int64_t>(b) * st.cap + static_cast<int64_t>(tile_in_image) * st.region + base + (inc - cnt);
+    int32_t *hist = st.hist + static_cast<int64_t>(b) * kBuckets;
+    const bool sampled = (anchor % kHistSample) == 0;  // 1-in-8 sample keeps the RED traffic negligible
     if (cnt) {
         if (f.multi_label) {
             for (int j = 0; j < nc; ++j) {
@@ -136,6 +138,7 @@ __device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, u
                     st.box[pos] = xyxy;
                     st.score[pos] = p;
                     st.key[pos] = anchor * static_cast<uint32_t>(nc) + static_cast<uint32_t>(j);
+                    if (sampled) atomicAdd(hist + score_bucket(__float_as_uint(p)), 1);  // RED.ADD, result unused
                     ++pos;
                 }
             }
@@ -143,6 +146,7 @@ __device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, u
             st.box[pos] = xyxy;
             st.score[pos] = best;
             st.key[pos] = anchor * static_cast<uint32_t>(nc) + static_cast<uint32_t>(bj);
+            if (sampled) atomicAdd(hist + score_bucket(__float_as_uint(best)), 1);
         }
     }
     __syncthreads();  // scratch reusable, and (TMA kernel) every read of the stage buffer is done
@@ -303,6 +307,7 @@ __global__ void __launch_bounds__(128) k1_merge(const __grid_constant__ K1MergeP
         p.st.box[base + i] = make_float4(__fadd_rn(row[0], ox), __fadd_rn(row[1], oy), __fadd_rn(row[2], ox),
                                          __fadd_rn(row[3], oy));
         p.st.score[base + i] = row[4];
+        if ((i % kHistSample) == 0) atomicAdd(p.st.hist + static_cast<int64_t>(f) * kBuckets + score_bucket(__float_as_uint(row[4])), 1);
         p.cls[base + i] = row[5];
         p.st.key[base + i] = static_cast<uint32_t>(t) * p.dets_per_tile + i;
     }

@@ -6,10 +6,12 @@
 //
 // Greedy NMS compares a candidate only with boxes KEPT before it, and stops at max_det keeps — so at
 // most n*max_det pair tests are needed, not n^2/2, and usually only the head of the sorted order is
-// ever looked at.  One CTA per image walks the bucket-partitioned candidates (k2_select_sort.cuh):
-//   chunk     the next run of whole score buckets that fits shared memory is sorted there (bitonic
-//             network on the 64-bit composite score|~slot = descending score, source order on ties);
-//             a single bucket larger than that falls back to a stable LSD radix sort in global memory;
+// ever looked at.  One CTA per image (selection scheme: k2_select_sort.cuh):
+//   select    the per-image score histogram written by K1 is scanned from the top; the next run of
+//             whole score buckets that fits shared memory is collected by streaming the image's
+//             candidate scores once, and sorted there (bitonic network on the 64-bit composite
+//             score|~slot = descending score, source order on ties); a single bucket larger than that
+//             falls back to a stable LSD radix sort in global memory;
 //   phase 1   a sub-chunk of <= 256 sorted candidates is tested against the kept list (smem);
 //   phase 2   an upper-triangular suppression bitmask is built among the survivors (tiled IoU
 //             bitmask, all threads);
@@ -43,9 +45,8 @@ constexpr int kSubWords = kSub / 32;
 
 struct NmsParams {
     CandStore st;
-    uint32_t *part_key, *part_val;   // [B*cap] from K2 (may be permuted in place by the fallback sort)
-    uint32_t *tmp_key, *tmp_val;     // [B*cap] scratch for the fallback sort
-    const int32_t *bstart;           // [B*(kBuckets+1)]
+    uint32_t *tmp_key_a, *tmp_val_a; // [B*cap] scratch for the oversized-bucket fallback sort
+    uint32_t *tmp_key_b, *tmp_val_b; // [B*cap]
     uint32_t *kept_slot;             // [B*max_det]
     int32_t *counts;                 // [B]
     int32_t max_det, max_nms;
@@ -168,20 +169,57 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
-    uint32_t *pkey = p.part_key + seg, *pval = p.part_val + seg;
-    uint32_t *tkey = p.tmp_key + seg, *tval = p.tmp_val + seg;
+    const int32_t *tcount = p.st.tile_count + static_cast<int64_t>(b) * p.st.tpi;
+    const float *score = p.st.score + seg;
     const float band = fmaxf(p.thr * 2e-6f, 1e-37f);
 #ifdef SARPOST_PHASE_PROF
     long long prof_t = clock64();
 #endif
 
-    for (int i = tid; i <= kBuckets; i += kNmsThreads) s_bstart[i] = p.bstart[static_cast<int64_t>(b) * (kBuckets + 1) + i];
+    // ---- descending exclusive scan of the sampled score histogram: s_bstart[d] ~ estimated rank of the first
+    //      candidate of bucket 4095-d in the sorted order (x kHistSample).  Estimates only steer how many
+    //      buckets a chunk spans; membership, ranks and results are exact.  n_all = exact candidate count. ----
+    {
+        const int32_t *hist = p.st.hist + static_cast<int64_t>(b) * kBuckets;
+        constexpr int kPer = kBuckets / kNmsThreads;  // 8 consecutive d per thread
+        int loc[kPer], sum = 0;
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            loc[i] = hist[kBuckets - 1 - (tid * kPer + i)] * kHistSample;
+            sum += loc[i];
+        }
+        int tot = 0;
+        for (int t = tid; t < p.st.tpi; t += kNmsThreads) tot += tcount[t];
+        int inc = sum;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, inc, dd);
+            if (lane >= dd) inc += v;
+        }
+        tot = __reduce_add_sync(0xffffffffu, tot);
+        if (lane == 31) s_misc[warp] = inc;
+        if (lane == 0) s_misc[16 + warp] = tot;
+        __syncthreads();
+        int run = inc - sum;
+        for (int w = 0; w < warp; ++w) run += s_misc[w];
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+            s_bstart[tid * kPer + i] = run;
+            run += loc[i];
+        }
+        if (tid == kNmsThreads - 1) s_bstart[kBuckets] = run;
+        tot = 0;
+#pragma unroll
+        for (int w = 0; w < kNmsWarps; ++w) tot += s_misc[16 + w];
+        __syncthreads();
+        if (tid == 0) s_misc[19] = tot;
+    }
     __syncthreads();
     PROF_MARK(0);
-    const int n_sel = s_bstart[kBuckets];
-    const int n_limit = min(n_sel, p.max_nms);
+    const int n_all = s_misc[19];
+    const int n_limit = min(n_all, p.max_nms);  // ops.py:285-286: only the top max_nms ranks are eligible
     int kept = 0;
-    int pos = 0, d = 0;
+    int pos = 0, d = 0;  // pos = exact number of candidates consumed (all buckets above descending index d)
 
     // Walks `cnt` sorted candidates whose slots are produced by slot_at(i), i in [0,cnt).
     auto process_sorted = [&](auto slot_at, int cnt) {
@@ -249,36 +287,27 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             __syncthreads();
             PROF_MARK(5);
             // ---- phase 2: suppression bitmask among the m survivors (row r, bits j > r) ----
-            // one warp per (row, 32-candidate word): lane j tests the pair (r, 32w + j), a ballot packs the word
+            // warp per row r, lane j tests the pair (r, 32w + j) for every word w >= r/32; a ballot packs the word
             const int words = (m + 31) >> 5;
-            {
-                const int n_items = m * words;
-                for (int it0 = warp; it0 < n_items; it0 += 4 * kNmsWarps) {
-                    bool gt[4], bd[4];
-                    int rr[4], ww[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int item = it0 + u * kNmsWarps;
-                        rr[u] = item / words;
-                        ww[u] = item - rr[u] * words;
-                        gt[u] = bd[u] = false;
-                        if (item < n_items && ww[u] >= (rr[u] >> 5)) {
-                            const int j = (ww[u] << 5) + lane;
-                            if (j > rr[u] && j < m)
-                                gt[u] = iou_gt_approx(C_BOX[rr[u]], s_c_area[rr[u]], C_BOX[j], s_c_area[j], p.thr, band, bd[u]);
-                        }
+            for (int r = warp; r < m; r += kNmsWarps) {
+                const float4 rb = C_BOX[r];
+                const float ra = s_c_area[r];
+                for (int w = r >> 5; w < words; w += 2) {
+                    const int j0 = (w << 5) + lane, j1 = j0 + 32;
+                    const bool v0 = j0 > r && j0 < m, v1 = (w + 1 < words) && j1 < m;
+                    bool bd0 = false, bd1 = false;
+                    const int jc0 = v0 ? j0 : r, jc1 = v1 ? j1 : r;
+                    bool g0 = iou_gt_approx(rb, ra, C_BOX[jc0], s_c_area[jc0], p.thr, band, bd0);
+                    bool g1 = iou_gt_approx(rb, ra, C_BOX[jc1], s_c_area[jc1], p.thr, band, bd1);
+                    if (__any_sync(0xffffffffu, (bd0 && v0) || (bd1 && v1))) {  // rare: quotient within a few ulp of thr
+                        if (bd0) g0 = iou_gt(rb, ra, C_BOX[jc0], s_c_area[jc0], p.thr);
+                        if (bd1) g1 = iou_gt(rb, ra, C_BOX[jc1], s_c_area[jc1], p.thr);
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int item = it0 + u * kNmsWarps;
-                        if (item < n_items && ww[u] >= (rr[u] >> 5)) {  // warp-uniform
-                            if (bd[u]) {
-                                const int j = (ww[u] << 5) + lane;
-                                gt[u] = iou_gt(C_BOX[rr[u]], s_c_area[rr[u]], C_BOX[j], s_c_area[j], p.thr);
-                            }
-                            const uint32_t bits = __ballot_sync(0xffffffffu, gt[u]);
-                            if (lane == 0) s_mask[rr[u] * kSubWords + ww[u]] = bits;
-                        }
+                    const uint32_t bits0 = __ballot_sync(0xffffffffu, g0 && v0);
+                    const uint32_t bits1 = __ballot_sync(0xffffffffu, g1 && v1);
+                    if (lane == 0) {
+                        s_mask[r * kSubWords + w] = bits0;
+                        if (w + 1 < words) s_mask[r * kSubWords + w + 1] = bits1;
                     }
                 }
             }
@@ -349,36 +378,56 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         }
     };
 
-    while (pos < n_limit && kept < p.max_det) {
-        // ---- next chunk: largest run of whole buckets [d, d1) with <= kSortCap candidates ----
+    auto collect_smem = [&](uint32_t b_lo, uint32_t b_hi) {  // members of score buckets [b_lo, b_hi] -> SKEY, count -> s_misc[18]
+        for_each_candidate(p.st, tcount, score, [&](uint32_t slot, uint32_t bits, bool valid) {
+            const uint32_t bk = static_cast<uint32_t>(score_bucket(bits));
+            const bool take = valid && bk >= b_lo && bk <= b_hi;
+            const uint32_t bal = __ballot_sync(0xffffffffu, take);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_misc[18], __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int at = base + __popc(bal & lanemask_lt());
+                if (take && at < kSortCap) SKEY[at] = (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - slot);
+            }
+        });
+    };
+
+    while (d < kBuckets && pos < n_limit && kept < p.max_det) {
+        // ---- next chunk: a run of whole buckets [d, d1) whose ESTIMATED population fits the target ----
         if (tid == 0) {
-            // largest d1 in [d+1, kBuckets] with bstart[d1] - pos <= cap; the first chunk is smaller because
-            // NMS usually finishes inside it (max_det keeps) and sorting cost grows with the chunk
-            const int cap = pos == 0 ? min(kSortCap, max(256, 2 * p.max_det)) : kSortCap;
+            // the first chunk is smaller: NMS usually finishes inside it and sorting cost grows with the chunk
+            const int target = pos == 0 ? min(kSortCap / 2, max(256, 2 * p.max_det)) : (kSortCap * 3) / 4;
+            const int base = s_bstart[d];
             int lo = d + 1, hi = kBuckets;
-            if (s_bstart[lo] - pos > cap) {
-                hi = lo;  // even one bucket exceeds the target (it is still sorted in smem if it fits kSortCap)
-            } else {
+            if (s_bstart[lo] - base <= target) {
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
-                    if (s_bstart[mid] - pos <= cap) lo = mid; else hi = mid - 1;
+                    if (s_bstart[mid] - base <= target) lo = mid; else hi = mid - 1;
                 }
             }
-            s_misc[17] = hi;
+            s_misc[17] = lo;
         }
         __syncthreads();
-        const int d1 = s_misc[17];
-        const int end = s_bstart[d1];
-        const int m = end - pos;
-        __syncthreads();
+        int d1 = s_misc[17];
+        int m = 0;
+        for (;;) {  // collect; if the real population overflows shared memory, halve the bucket run and retry
+            __syncthreads();
+            if (tid == 0) s_misc[18] = 0;
+            __syncthreads();
+            collect_smem(static_cast<uint32_t>(kBuckets - d1), static_cast<uint32_t>(kBuckets - 1 - d));
+            __syncthreads();
+            m = s_misc[18];
+            if (m <= kSortCap || d1 - d == 1) break;
+            d1 = d + (d1 - d) / 2;
+        }
         PROF_MARK(1);
         if (m <= kSortCap) {
             if (m > 0) {
                 int lpw = 6;
                 while ((1 << lpw) < m) ++lpw;
                 const int pw = 1 << lpw;
-                for (int i = tid; i < pw; i += kNmsThreads)
-                    SKEY[i] = i < m ? ((static_cast<unsigned long long>(pkey[pos + i]) << 32) | (0xffffffffu - pval[pos + i])) : 0ull;
+                for (int i = m + tid; i < pw; i += kNmsThreads) SKEY[i] = 0ull;
                 __syncthreads();
                 // bitonic network, descending
                 for (int lk = 1; lk <= lpw; ++lk) {
@@ -399,11 +448,32 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 process_sorted([&](int i) { return 0xffffffffu - static_cast<uint32_t>(SKEY[i]); }, min(m, n_limit - pos));
             }
         } else {
-            // ---- oversized bucket: stable LSD radix sort in global memory on (score bits desc, slot asc) ----
+            // ---- a single bucket larger than shared memory: collect to global scratch, stable LSD radix sort
+            //      on (score bits desc, slot asc), then stream it through the suppression phases ----
+            uint32_t *ka = p.tmp_key_a + seg, *va = p.tmp_val_a + seg, *kb = p.tmp_key_b + seg, *vb = p.tmp_val_b + seg;
+            const uint32_t b_one = static_cast<uint32_t>(kBuckets - 1 - d);
+            __syncthreads();
+            if (tid == 0) s_misc[18] = 0;
+            __syncthreads();
+            for_each_candidate(p.st, tcount, score, [&](uint32_t slot, uint32_t bits, bool valid) {
+                const bool take = valid && static_cast<uint32_t>(score_bucket(bits)) == b_one;
+                const uint32_t bal = __ballot_sync(0xffffffffu, take);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_misc[18], __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (take) {
+                        const int at = base + __popc(bal & lanemask_lt());
+                        ka[at] = bits;
+                        va[at] = slot;
+                    }
+                }
+            });
+            __syncthreads();
             int *cnt = reinterpret_cast<int *>(s_uni);
             int *wt = s_misc;
-            const uint32_t *ik = pkey + pos, *iv = pval + pos;
-            uint32_t *ok = tkey + pos, *ov = tval + pos;
+            const uint32_t *ik = ka, *iv = va;
+            uint32_t *ok = kb, *ov = vb;
             int slot_bits = 1;
             while ((static_cast<int64_t>(1) << slot_bits) < p.st.cap) ++slot_bits;
             const int passes_slot = (slot_bits + 7) / 8;
@@ -423,10 +493,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 process_sorted([&](int i) { return sorted[piece + i]; }, min(kSortCap, lim - piece));
             }
         }
-        pos = end;
+        pos += m;
         d = d1;
     }
     // ---- publish ----
+    __syncthreads();
     for (int k = tid; k < kept; k += kNmsThreads) p.kept_slot[static_cast<int64_t>(b) * p.max_det + k] = KEPT_SLOT[k];
     if (tid == 0) p.counts[b] = kept;
     PROF_MARK(8);

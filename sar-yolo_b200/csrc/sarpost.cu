@@ -1,8 +1,7 @@
 // sarpost.cu — C ABI (include/sarpost.h) and host-side orchestration of the K1..K5 pipeline.
 //
 //   K1 candidates   k1_fused_tma | k1_fused_ldg | k1_decoded | k1_merge     (k1_candidates.cuh)
-//   K2 select+sort  k2_select_sort                                           (k2_select_sort.cuh)
-//   K4 NMS          k4_nms                                                   (k4_nms.cuh)
+//   K2/K3/K4        k4_nms: histogram scan, lazy top-k selection + sort, NMS  (k2_select_sort.cuh, k4_nms.cuh)
 //   K5 gather       k5_gather                                                (k4_nms.cuh)
 //
 // No torch types, no exceptions across the ABI, no global mutable state (thread-local error string and
@@ -27,7 +26,7 @@ namespace sarpost {
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 thread_local int g_timing = 0;
-thread_local cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+thread_local cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 thread_local int g_ev_valid = 0;
 
 static int fail(int code, const char *fmt, ...) {
@@ -59,7 +58,7 @@ static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * 
 // workspace layout
 // ------------------------------------------------------------------------------------------------
 struct Layout {
-    int64_t box, score, key, cls, key_a, val_a, key_b, val_b, tile_count, bstart, kept_slot, total;
+    int64_t box, score, key, cls, key_a, val_a, key_b, val_b, tile_count, hist, kept_slot, total;
 };
 
 static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_det, bool with_cls) {
@@ -80,7 +79,7 @@ static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_d
     L.key_b = take(slots * 4);
     L.val_b = take(slots * 4);
     L.tile_count = take(batch * tpi * 4);
-    L.bstart = take(batch * (kBuckets + 1) * 4);
+    L.hist = take(batch * kBuckets * 4);
     L.kept_slot = take(batch * max_det * 4);
     L.total = o;
     return L;
@@ -89,7 +88,6 @@ static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_d
 struct Pipeline {
     CandStore st;
     uint32_t *key_a, *val_a, *key_b, *val_b;
-    int32_t *bstart;
     uint32_t *kept_slot;
     float *cls;
 };
@@ -112,7 +110,7 @@ static int bind_workspace(void *ws, int64_t ws_bytes, int64_t batch, int64_t cap
     P->val_a = reinterpret_cast<uint32_t *>(base + L.val_a);
     P->key_b = reinterpret_cast<uint32_t *>(base + L.key_b);
     P->val_b = reinterpret_cast<uint32_t *>(base + L.val_b);
-    P->bstart = reinterpret_cast<int32_t *>(base + L.bstart);
+    P->st.hist = reinterpret_cast<int32_t *>(base + L.hist);
     P->kept_slot = reinterpret_cast<uint32_t *>(base + L.kept_slot);
     P->cls = with_cls ? reinterpret_cast<float *>(base + L.cls) : nullptr;
     return SARPOST_OK;
@@ -290,24 +288,12 @@ static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandSto
 // K2 + K4 + K5 on a filled candidate store.
 static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, int nc, GatherParams gp, float *out,
                     int32_t *counts, int32_t *kept_index, cudaStream_t s) {
-    PartParams sp;
-    sp.st = P.st;
-    sp.part_key = P.key_a;
-    sp.part_val = P.val_a;
-    sp.bstart = P.bstart;
-    sp.max_nms = prm->max_nms;
-    k2_select_partition<<<batch, kPartThreads, 0, s>>>(sp);
-    ++g_launches;
-    CUDA_TRY(cudaGetLastError());
-    stage_mark(2, s);
-
     NmsParams np;
     np.st = P.st;
-    np.part_key = P.key_a;
-    np.part_val = P.val_a;
-    np.tmp_key = P.key_b;
-    np.tmp_val = P.val_b;
-    np.bstart = P.bstart;
+    np.tmp_key_a = P.key_a;
+    np.tmp_val_a = P.val_a;
+    np.tmp_key_b = P.key_b;
+    np.tmp_val_b = P.val_b;
     np.kept_slot = P.kept_slot;
     np.counts = counts;
     np.max_det = prm->max_det;
@@ -321,7 +307,7 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     k4_nms<<<batch, kNmsThreads, nms_smem, s>>>(np);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
-    stage_mark(3, s);
+    stage_mark(2, s);
 
     gp.st = P.st;
     gp.kept_slot = P.kept_slot;
@@ -333,7 +319,13 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     k5_gather<<<dim3((prm->max_det + kGatherWarps - 1) / kGatherWarps, batch), kGatherWarps * 32, 0, s>>>(gp);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
-    stage_mark(4, s);
+    stage_mark(3, s);
+    return SARPOST_OK;
+}
+
+// the per-image score histogram must be zero before K1 accumulates into it
+static int zero_hist(const Pipeline &P, int batch, cudaStream_t s) {
+    CUDA_TRY(cudaMemsetAsync(P.st.hist, 0, static_cast<size_t>(batch) * kBuckets * sizeof(int32_t), s));
     return SARPOST_OK;
 }
 
@@ -360,9 +352,10 @@ int32_t sarpost_set_stage_timing(int32_t enabled) {
 
 int32_t sarpost_stage_times(float *ms4) {
     if (!ms4) return fail(SARPOST_EINVAL, "ms4 is NULL");
-    if (!g_timing || g_ev_valid != 4) return fail(SARPOST_EINVAL, "no timed call recorded on this thread");
-    CUDA_TRY(cudaEventSynchronize(g_ev[4]));
-    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventElapsedTime(&ms4[i], g_ev[i], g_ev[i + 1]));
+    if (!g_timing || g_ev_valid != 3) return fail(SARPOST_EINVAL, "no timed call recorded on this thread");
+    CUDA_TRY(cudaEventSynchronize(g_ev[3]));
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms4[i], g_ev[i], g_ev[i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&ms4[3], g_ev[0], g_ev[3]));
     return SARPOST_OK;
 }
 
@@ -413,6 +406,7 @@ int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t chan
     if (int rc = bind_workspace(workspace, workspace_bytes, batch, tpi * region, tpi, region, params->max_det, false, &P)) return rc;
 
     stage_mark(0, s);
+    if (int rc = zero_hist(P, batch, s)) return rc;
     K1DecodedParams kp;
     kp.pred = prediction;
     kp.channels = channels;
@@ -452,6 +446,7 @@ int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *pa
     if (int rc = bind_workspace(workspace, workspace_bytes, g.batch, g.tpi * region, g.tpi, region, params->max_det, false, &P)) return rc;
 
     stage_mark(0, s);
+    if (int rc = zero_hist(P, g.batch, s)) return rc;
     if (int rc = launch_k1_fused(g, f, P.st, s)) return rc;
     stage_mark(1, s);
 
@@ -485,6 +480,7 @@ int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const 
     if (int rc = bind_workspace(workspace, workspace_bytes, n_frames, cap, tiles_per_frame, dets_per_tile, params->max_det, true, &P)) return rc;
 
     stage_mark(0, s);
+    if (int rc = zero_hist(P, n_frames, s)) return rc;
     K1MergeParams kp;
     kp.dets = dets;
     kp.det_counts = det_counts;

@@ -365,7 +365,8 @@ def stage_timing(enabled: bool) -> None:
 
 
 def stage_times() -> Tuple[float, float, float, float]:
-    """Milliseconds of (K1 candidates, K2 select+sort, K4 nms, K5 gather) of the last timed call."""
+    """Milliseconds of (K1 candidates incl. histogram memset, K2-K4 select+sort+NMS, K5 gather, whole call)
+    of the last timed call."""
     buf = (C.c_float * 4)()
     _lib.check(lib.sarpost_stage_times(buf))
     return tuple(float(v) for v in buf)

@@ -15,7 +15,7 @@ buf=(C.c_ulonglong*16)(); f(buf,1)
 N=20
 for _ in range(N): sarpost.postprocess_fused(levels,spec,return_padded=True,**kw)
 f(buf,1)
-names=['bstart_load','chunk_search','load+bitonic','sub_load','phase1','compact','mask','sweep','publish']
+names=['hist_scan','chunk_search','collect+bitonic','sub_load','phase1','compact','mask','sweep','publish']
 tot=sum(buf[i] for i in range(9))
 for i,n in enumerate(names): print(f"{n:14s} {buf[i]/N:10.0f} cyc  {buf[i]/tot*100:5.1f}%")
 print("total cyc/launch", tot/N)
