@@ -24,6 +24,7 @@ struct CandStore {
     float *score;       // [B*cap]
     uint32_t *key;      // [B*cap] anchor*nc + cls  (merge: tile*dets_per_tile + row)
     int32_t *tile_count;// [B*tpi]
+    uint32_t *tile_max; // [B*tpi] largest score bit pattern among the tile's candidates (0 if none)
     int32_t *hist;      // [B*kBuckets] per-image SAMPLED histogram of score_bucket(): candidates of every
                         // kHistSample-th anchor (zeroed before K1); only steers chunk sizes, never results
     int64_t cap;        // slots per image
@@ -40,6 +41,11 @@ constexpr int kBucketBase = (0x3F800000 >> kBucketShift) - (kBuckets - 1);
 __device__ __forceinline__ int score_bucket(uint32_t bits) {
     const int b = static_cast<int>(bits >> kBucketShift) - kBucketBase;
     return min(max(b, 0), kBuckets - 1);
+}
+
+// Smallest score bit pattern that maps to bucket >= b (score_bucket is monotone in the bit pattern).
+__host__ __device__ __forceinline__ uint32_t bucket_floor_bits(int b) {
+    return b <= 0 ? 0u : static_cast<uint32_t>(b + kBucketBase) << kBucketShift;
 }
 
 // fp32 sigmoid as torch computes it: 1 / (1 + exp(-x)), each step rounded (head.py:131,249).

@@ -109,6 +109,19 @@ __device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, u
             cnt = (best > f.conf) && cls_allowed(f, bj);
         }
     }
+    // largest candidate score of the tile (lets the selection scan skip whole tiles)
+    float tmax = 0.0f;
+    if (cnt) {
+        if (f.multi_label) {
+            for (int j = 0; j < nc; ++j) {
+                const float p = score(j);
+                if ((p > f.conf) && cls_allowed(f, j)) tmax = fmaxf(tmax, p);
+            }
+        } else {
+            tmax = best;
+        }
+    }
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(tmax, 0.0f)));
     // exclusive scan of cnt over the block
     int inc = cnt;
 #pragma unroll
@@ -117,6 +130,7 @@ __device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, u
         if (lane >= d) inc += n;
     }
     if (lane == 31) scratch[warp] = inc;
+    if (lane == 0) scratch[4 + warp] = static_cast<int>(wmax);
     __syncthreads();
     int base = 0;
 #pragma unroll
@@ -126,6 +140,10 @@ __device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, u
 #pragma unroll
         for (int w = 0; w < kTileA / 32; ++w) tot += scratch[w];
         st.tile_count[static_cast<int64_t>(b) * st.tpi + tile_in_image] = tot;
+        uint32_t mx = 0u;
+#pragma unroll
+        for (int w = 0; w < kTileA / 32; ++w) mx = max(mx, static_cast<uint32_t>(scratch[4 + w]));
+        st.tile_max[static_cast<int64_t>(b) * st.tpi + tile_in_image] = mx;
     }
     int64_t pos = static_cast<int64_t>(b) * st.cap + static_cast<int64_t>(tile_in_image) * st.region + base + (inc - cnt);
     int32_t *hist = st.hist + static_cast<int64_t>(b) * kBuckets;
@@ -302,6 +320,7 @@ __global__ void __launch_bounds__(128) k1_merge(const __grid_constant__ K1MergeP
     n = n < 0 ? 0 : (n > p.dets_per_tile ? p.dets_per_tile : n);
     const float ox = p.origins[2 * tile], oy = p.origins[2 * tile + 1];
     const int64_t base = static_cast<int64_t>(f) * p.st.cap + static_cast<int64_t>(t) * p.st.region;
+    if (threadIdx.x == 0) p.st.tile_max[tile] = n > 0 ? 0xffffffffu : 0u;  // no pruning on the merge path
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float *row = p.dets + (tile * p.dets_per_tile + i) * p.row_len;
         p.st.box[base + i] = make_float4(__fadd_rn(row[0], ox), __fadd_rn(row[1], oy), __fadd_rn(row[2], ox),

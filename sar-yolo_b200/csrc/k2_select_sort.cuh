@@ -25,52 +25,58 @@
 
 namespace sarpost {
 
-// Visit every candidate of the image: fn(slot, score_bits).  Each warp owns a contiguous run of tiles;
-// the tile counts of the run are fetched with one coalesced load and, when the tile region is exactly
-// kTileA slots, the scores of kUnroll tiles are fetched with independent 128-bit loads before any of
-// them is consumed (the loop is latency-bound: one CTA per image, data in L2).
+// Visit every candidate of the image whose score bit pattern lies in [lo_bits, hi_bits]: fn(slot, bits).
+// The scan is instruction-bound (one CTA streams every candidate score of its image out of L2), so the
+// common case — no member among a lane's four scores — costs one 128-bit load, four range tests and a
+// single branch.  Each warp owns a contiguous run of tiles; the tile counts of the run are fetched with
+// one coalesced load and, when the tile region is exactly kTileA slots, kUnroll tiles are in flight.
+// Tiles whose best score (tile_max, written by K1) is below the range are skipped without touching them.
 template <class Fn>
-__device__ __forceinline__ void for_each_candidate(const CandStore &st, const int32_t *tcount, const float *score,
-                                                   const Fn &fn) {
+__device__ __forceinline__ void for_each_candidate_in(const CandStore &st, const int32_t *tcount, const uint32_t *tmax,
+                                                      const float *score,
+                                                      uint32_t lo_bits, uint32_t hi_bits, const Fn &fn) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int tpw = (st.tpi + nwarps - 1) / nwarps;
     const int t_begin = warp * tpw, t_end = min(st.tpi, t_begin + tpw);
+    const uint32_t span = hi_bits - lo_bits;  // in range  <=>  (bits - lo_bits) <= span  (unsigned)
     if (st.region == kTileA) {
         constexpr int kUnroll = 8;
         for (int tb = t_begin; tb < t_end; tb += 32) {
-            const int my_c = (tb + lane < t_end) ? tcount[tb + lane] : 0;
+            // a tile whose best score is below the range has no member: treat it as empty
+            const int my_c = (tb + lane < t_end && tmax[tb + lane] >= lo_bits) ? tcount[tb + lane] : 0;
             const int nt = min(32, t_end - tb);
             for (int u0 = 0; u0 < nt; u0 += kUnroll) {
                 uint4 v[kUnroll];
                 int c[kUnroll];
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    c[u] = __shfl_sync(0xffffffffu, my_c, (u0 + u) & 31);
+                    c[u] = __shfl_sync(0xffffffffu, my_c, (u0 + u) & 31) - lane * 4;  // valid entries of this lane
                     if (u0 + u >= nt) c[u] = 0;
                     v[u] = make_uint4(0u, 0u, 0u, 0u);
-                    if (lane * 4 < c[u])
+                    if (c[u] > 0)
                         v[u] = *reinterpret_cast<const uint4 *>(score + static_cast<size_t>(tb + u0 + u) * kTileA + lane * 4);
                 }
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    const int i0 = lane * 4;
-                    const uint32_t slot = static_cast<uint32_t>(tb + u0 + u) * kTileA + i0;
-                    // fn(slot, bits, valid) is called by all 32 lanes (it may vote)
-                    fn(slot, v[u].x, i0 < c[u]);
-                    fn(slot + 1, v[u].y, i0 + 1 < c[u]);
-                    fn(slot + 2, v[u].z, i0 + 2 < c[u]);
-                    fn(slot + 3, v[u].w, i0 + 3 < c[u]);
+                    const bool t0 = (v[u].x - lo_bits) <= span && c[u] > 0, t1 = (v[u].y - lo_bits) <= span && c[u] > 1;
+                    const bool t2 = (v[u].z - lo_bits) <= span && c[u] > 2, t3 = (v[u].w - lo_bits) <= span && c[u] > 3;
+                    if (t0 | t1 | t2 | t3) {
+                        const uint32_t slot = static_cast<uint32_t>(tb + u0 + u) * kTileA + lane * 4;
+                        if (t0) fn(slot, v[u].x);
+                        if (t1) fn(slot + 1, v[u].y);
+                        if (t2) fn(slot + 2, v[u].z);
+                        if (t3) fn(slot + 3, v[u].w);
+                    }
                 }
             }
         }
     } else {
         for (int t = t_begin; t < t_end; ++t) {
-            const int c = tcount[t];
-            for (int i0 = 0; i0 < c; i0 += 32) {
-                const int i = i0 + lane;
+            const int c = tmax[t] >= lo_bits ? tcount[t] : 0;
+            for (int i = lane; i < c; i += 32) {
                 const uint32_t slot = static_cast<uint32_t>(t) * st.region + i;
-                const bool valid = i < c;
-                fn(slot, valid ? __float_as_uint(score[slot]) : 0u, valid);
+                const uint32_t bits = __float_as_uint(score[slot]);
+                if ((bits - lo_bits) <= span) fn(slot, bits);
             }
         }
     }

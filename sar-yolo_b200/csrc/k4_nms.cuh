@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
     const int32_t *tcount = p.st.tile_count + static_cast<int64_t>(b) * p.st.tpi;
+    const uint32_t *tmaxv = p.st.tile_max + static_cast<int64_t>(b) * p.st.tpi;
     const float *score = p.st.score + seg;
     const float band = fmaxf(p.thr * 2e-6f, 1e-37f);
 #ifdef SARPOST_PHASE_PROF
@@ -378,18 +379,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         }
     };
 
-    auto collect_smem = [&](uint32_t b_lo, uint32_t b_hi) {  // members of score buckets [b_lo, b_hi] -> SKEY, count -> s_misc[18]
-        for_each_candidate(p.st, tcount, score, [&](uint32_t slot, uint32_t bits, bool valid) {
-            const uint32_t bk = static_cast<uint32_t>(score_bucket(bits));
-            const bool take = valid && bk >= b_lo && bk <= b_hi;
-            const uint32_t bal = __ballot_sync(0xffffffffu, take);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_misc[18], __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int at = base + __popc(bal & lanemask_lt());
-                if (take && at < kSortCap) SKEY[at] = (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - slot);
-            }
+    // members of score buckets [b_lo, b_hi] -> SKEY (first kSortCap of them), exact count -> s_misc[18]
+    auto collect_smem = [&](int b_lo, int b_hi) {
+        const uint32_t lo_bits = bucket_floor_bits(b_lo);
+        const uint32_t hi_bits = b_hi >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_hi + 1) - 1u;
+        for_each_candidate_in(p.st, tcount, tmaxv, score, lo_bits, hi_bits, [&](uint32_t slot, uint32_t bits) {
+            const int at = atomicAdd(&s_misc[18], 1);  // members are rare (a few hundred per image)
+            if (at < kSortCap) SKEY[at] = (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - slot);
         });
     };
 
@@ -415,7 +411,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             __syncthreads();
             if (tid == 0) s_misc[18] = 0;
             __syncthreads();
-            collect_smem(static_cast<uint32_t>(kBuckets - d1), static_cast<uint32_t>(kBuckets - 1 - d));
+            collect_smem(kBuckets - d1, kBuckets - 1 - d);
             __syncthreads();
             m = s_misc[18];
             if (m <= kSortCap || d1 - d == 1) break;
@@ -451,24 +447,17 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             // ---- a single bucket larger than shared memory: collect to global scratch, stable LSD radix sort
             //      on (score bits desc, slot asc), then stream it through the suppression phases ----
             uint32_t *ka = p.tmp_key_a + seg, *va = p.tmp_val_a + seg, *kb = p.tmp_key_b + seg, *vb = p.tmp_val_b + seg;
-            const uint32_t b_one = static_cast<uint32_t>(kBuckets - 1 - d);
+            const int b_one = kBuckets - 1 - d;
             __syncthreads();
             if (tid == 0) s_misc[18] = 0;
             __syncthreads();
-            for_each_candidate(p.st, tcount, score, [&](uint32_t slot, uint32_t bits, bool valid) {
-                const bool take = valid && static_cast<uint32_t>(score_bucket(bits)) == b_one;
-                const uint32_t bal = __ballot_sync(0xffffffffu, take);
-                if (bal) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&s_misc[18], __popc(bal));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (take) {
-                        const int at = base + __popc(bal & lanemask_lt());
-                        ka[at] = bits;
-                        va[at] = slot;
-                    }
-                }
-            });
+            for_each_candidate_in(p.st, tcount, tmaxv, score, bucket_floor_bits(b_one),
+                                  b_one >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_one + 1) - 1u,
+                                  [&](uint32_t slot, uint32_t bits) {
+                                      const int at = atomicAdd(&s_misc[18], 1);
+                                      ka[at] = bits;
+                                      va[at] = slot;
+                                  });
             __syncthreads();
             int *cnt = reinterpret_cast<int *>(s_uni);
             int *wt = s_misc;

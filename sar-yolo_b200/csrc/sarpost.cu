@@ -26,7 +26,7 @@ namespace sarpost {
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 thread_local int g_timing = 0;
-thread_local cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+thread_local cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 thread_local int g_ev_valid = 0;
 
 static int fail(int code, const char *fmt, ...) {
@@ -58,7 +58,7 @@ static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * 
 // workspace layout
 // ------------------------------------------------------------------------------------------------
 struct Layout {
-    int64_t box, score, key, cls, key_a, val_a, key_b, val_b, tile_count, hist, kept_slot, total;
+    int64_t box, score, key, cls, key_a, val_a, key_b, val_b, tile_count, tile_max, hist, kept_slot, total;
 };
 
 static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_det, bool with_cls) {
@@ -79,6 +79,7 @@ static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_d
     L.key_b = take(slots * 4);
     L.val_b = take(slots * 4);
     L.tile_count = take(batch * tpi * 4);
+    L.tile_max = take(batch * tpi * 4);
     L.hist = take(batch * kBuckets * 4);
     L.kept_slot = take(batch * max_det * 4);
     L.total = o;
@@ -103,6 +104,7 @@ static int bind_workspace(void *ws, int64_t ws_bytes, int64_t batch, int64_t cap
     P->st.score = reinterpret_cast<float *>(base + L.score);
     P->st.key = reinterpret_cast<uint32_t *>(base + L.key);
     P->st.tile_count = reinterpret_cast<int32_t *>(base + L.tile_count);
+    P->st.tile_max = reinterpret_cast<uint32_t *>(base + L.tile_max);
     P->st.cap = cap;
     P->st.tpi = static_cast<int32_t>(tpi);
     P->st.region = static_cast<int32_t>(region);
@@ -307,7 +309,7 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     k4_nms<<<batch, kNmsThreads, nms_smem, s>>>(np);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
-    stage_mark(2, s);
+    stage_mark(3, s);
 
     gp.st = P.st;
     gp.kept_slot = P.kept_slot;
@@ -319,13 +321,14 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     k5_gather<<<dim3((prm->max_det + kGatherWarps - 1) / kGatherWarps, batch), kGatherWarps * 32, 0, s>>>(gp);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
-    stage_mark(3, s);
+    stage_mark(4, s);
     return SARPOST_OK;
 }
 
 // the per-image score histogram must be zero before K1 accumulates into it
 static int zero_hist(const Pipeline &P, int batch, cudaStream_t s) {
     CUDA_TRY(cudaMemsetAsync(P.st.hist, 0, static_cast<size_t>(batch) * kBuckets * sizeof(int32_t), s));
+    stage_mark(1, s);
     return SARPOST_OK;
 }
 
@@ -352,10 +355,10 @@ int32_t sarpost_set_stage_timing(int32_t enabled) {
 
 int32_t sarpost_stage_times(float *ms4) {
     if (!ms4) return fail(SARPOST_EINVAL, "ms4 is NULL");
-    if (!g_timing || g_ev_valid != 3) return fail(SARPOST_EINVAL, "no timed call recorded on this thread");
-    CUDA_TRY(cudaEventSynchronize(g_ev[3]));
-    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms4[i], g_ev[i], g_ev[i + 1]));
-    CUDA_TRY(cudaEventElapsedTime(&ms4[3], g_ev[0], g_ev[3]));
+    if (!g_timing || g_ev_valid != 4) return fail(SARPOST_EINVAL, "no timed call recorded on this thread");
+    CUDA_TRY(cudaEventSynchronize(g_ev[4]));
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms4[i], g_ev[i + 1], g_ev[i + 2]));
+    CUDA_TRY(cudaEventElapsedTime(&ms4[3], g_ev[0], g_ev[4]));
     return SARPOST_OK;
 }
 
@@ -417,7 +420,7 @@ int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t chan
     k1_decoded<<<dim3(static_cast<unsigned>(tpi), batch), kTileA, 0, s>>>(kp);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
-    stage_mark(1, s);
+    stage_mark(2, s);
 
     GatherParams gp;
     memset(&gp, 0, sizeof(gp));
@@ -448,7 +451,7 @@ int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *pa
     stage_mark(0, s);
     if (int rc = zero_hist(P, g.batch, s)) return rc;
     if (int rc = launch_k1_fused(g, f, P.st, s)) return rc;
-    stage_mark(1, s);
+    stage_mark(2, s);
 
     GatherParams gp;
     memset(&gp, 0, sizeof(gp));
@@ -492,7 +495,7 @@ int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const 
     k1_merge<<<dim3(tiles_per_frame, n_frames), 128, 0, s>>>(kp);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
-    stage_mark(1, s);
+    stage_mark(2, s);
 
     GatherParams gp;
     memset(&gp, 0, sizeof(gp));
