@@ -51,11 +51,11 @@ def allgather_detections(out: torch.Tensor, counts: torch.Tensor, group=None) ->
     world = dist.get_world_size(group)
     if world == 1:
         return out, counts
-    g_out = torch.empty((world,) + tuple(out.shape), dtype=out.dtype, device=out.device)
-    g_cnt = torch.empty((world,) + tuple(counts.shape), dtype=counts.dtype, device=counts.device)
+    g_out = torch.empty((world * out.shape[0],) + tuple(out.shape[1:]), dtype=out.dtype, device=out.device)
+    g_cnt = torch.empty((world * counts.shape[0],), dtype=counts.dtype, device=counts.device)
     dist.all_gather_into_tensor(g_out, out.contiguous(), group=group)
     dist.all_gather_into_tensor(g_cnt, counts.contiguous(), group=group)
-    return g_out.flatten(0, 1), g_cnt.flatten(0, 1)
+    return g_out, g_cnt
 
 
 class GatherBuffer:
@@ -66,19 +66,22 @@ class GatherBuffer:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.out = torch.empty((self.world, per_rank_batch, max_det, row_len), dtype=torch.float32, device=device)
-        self.counts = torch.zeros((self.world, per_rank_batch), dtype=torch.int32, device=device)
+        self.per = int(per_rank_batch)
+        self.out = torch.empty((self.world * self.per, max_det, row_len), dtype=torch.float32, device=device)
+        self.counts = torch.zeros((self.world * self.per,), dtype=torch.int32, device=device)
 
     @property
     def local_out(self) -> torch.Tensor:
-        return self.out[self.rank]
+        return self.out[self.rank * self.per:(self.rank + 1) * self.per]
 
     @property
     def local_counts(self) -> torch.Tensor:
-        return self.counts[self.rank]
+        return self.counts[self.rank * self.per:(self.rank + 1) * self.per]
 
     def exchange(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """In-place all-gather (send buffer = this rank's slice of the receive buffer, the layout NCCL's
+        in-place all-gather expects)."""
         if self.world > 1:
-            dist.all_gather_into_tensor(self.out, self.out[self.rank], group=self.group)
-            dist.all_gather_into_tensor(self.counts, self.counts[self.rank], group=self.group)
-        return self.out.flatten(0, 1), self.counts.flatten(0, 1)
+            dist.all_gather_into_tensor(self.out, self.local_out, group=self.group)
+            dist.all_gather_into_tensor(self.counts, self.local_counts, group=self.group)
+        return self.out, self.counts

@@ -1,0 +1,139 @@
+"""CPU: host-side logic — API contract on CPU tensors, plugin patching, sharding, SAHI grid, gloo all-gather."""
+import os
+import subprocess
+import sys
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cpu_tensors_raise_no_fallback(sarpost):
+    y = sarpost.synth.decoded_prediction(1, 64, 2, 0, seed=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sarpost.non_max_suppression(y)
+    spec = sarpost.HeadSpec(nc=1, strides=(8,))
+    with pytest.raises(RuntimeError):
+        sarpost.decode([torch.zeros(1, 65, 4, 4)], spec)
+    with pytest.raises(RuntimeError):
+        sarpost.postprocess_fused([torch.zeros(1, 65, 4, 4)], spec)
+    with pytest.raises(AssertionError, match="Invalid Confidence threshold"):
+        sarpost.non_max_suppression(y, conf_thres=2.0)
+    with pytest.raises(AssertionError, match="Invalid IoU"):
+        sarpost.non_max_suppression(y, iou_thres=-1)
+
+
+def test_headspec_from_module(sarpost):
+    m = types.SimpleNamespace(nc=1, stride=torch.tensor([8.0, 16.0, 32.0]), reg_max=16, embed_dim=256, state_classes=6)
+    s = sarpost.HeadSpec.from_module(m)
+    assert (s.no, s.nm, s.strides) == (327, 262, (8.0, 16.0, 32.0))
+    d = sarpost.HeadSpec.from_module(types.SimpleNamespace(nc=6, stride=[8, 16, 32], reg_max=16))
+    assert (d.no, d.nm) == (70, 0)
+    j = sarpost.HeadSpec.from_module(types.SimpleNamespace(nc=1, stride=[8], reg_max=16, embed_dim=128, state_classes=None))
+    assert (j.no, j.nm) == (193, 128)
+
+
+def test_level_shapes_and_anchor_counts(sarpost):
+    s = sarpost.synth.level_shapes(640, (8, 16, 32))
+    assert s == [(80, 80), (40, 40), (20, 20)] and sum(h * w for h, w in s) == 8400
+    p2 = sarpost.synth.level_shapes(1280, (4, 8, 16, 32))
+    assert sum(h * w for h, w in p2) == 136000
+    pts, st = sarpost.head.make_anchors([torch.zeros(1, 1, 2, 3), torch.zeros(1, 1, 1, 2)], [8, 16])
+    assert pts.tolist() == [[0.5, 0.5], [1.5, 0.5], [2.5, 0.5], [0.5, 1.5], [1.5, 1.5], [2.5, 1.5], [0.5, 0.5], [1.5, 0.5]]
+    assert st.flatten().tolist() == [8.0] * 6 + [16.0] * 2
+
+
+def test_plugin_patch_and_unpatch_forward_unaccelerated_calls(sarpost):
+    calls = []
+
+    def ref_nms(prediction, *a, **k):
+        calls.append("nms")
+        return ["ref"]
+
+    class Detect:
+        export = False
+        reg_max = 16
+
+        def _inference(self, x):
+            calls.append("detect")
+            return "ref-y"
+
+    class JDE(Detect):
+        def _inference(self, x):
+            calls.append("jde")
+            return "ref-y"
+
+    ops_mod = types.SimpleNamespace(non_max_suppression=ref_nms)
+    head_mod = types.SimpleNamespace(Detect=Detect, JDE=JDE)
+    sarpost.patch(ops_mod, head_mod)
+    try:
+        assert sarpost.plugin.is_patched()
+        assert ops_mod.non_max_suppression is not ref_nms
+        # CPU tensors, rotated boxes and apriori labels go to the reference's own function
+        y = torch.zeros(1, 6, 10)
+        assert ops_mod.non_max_suppression(y) == ["ref"]
+        assert ops_mod.non_max_suppression((y, None), 0.25, 0.45, None, False, False, (), 300, 0, 0.05, 30000, 7680, True, True) == ["ref"]
+        assert Detect()._inference([torch.zeros(1, 65, 2, 2)]) == "ref-y"
+        assert JDE()._inference([torch.zeros(1, 65, 2, 2)]) == "ref-y"
+        assert calls == ["nms", "nms", "detect", "jde"]
+    finally:
+        sarpost.unpatch()
+    assert ops_mod.non_max_suppression is ref_nms and not sarpost.plugin.is_patched()
+    assert Detect._inference(Detect(), [torch.zeros(1)]) == "ref-y"
+
+
+def test_shard_ranges_cover_everything_once(sarpost):
+    for n in (0, 1, 7, 64, 512, 513):
+        for w in (1, 2, 3, 8):
+            r = [sarpost.dist.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
+    assert sarpost.dist.shard_frames(10, 48, 1, 4) == (3 * 48, 6 * 48)
+
+
+def test_sahi_grid_cfg4(sarpost):
+    g = sarpost.dist.sahi_grid(4000, 3000, 640, 0.2)
+    assert g.shape == (48, 2)  # 8 x 6 tiles
+    assert g[:, 0].max().item() == 4000 - 640 and g[:, 1].max().item() == 3000 - 640
+    assert sarpost.dist.sahi_grid(600, 500).tolist() == [[0.0, 0.0]]
+
+
+GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import sarpost
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=rank, world_size=world)
+per, max_det, row = 3, 5, 6
+out = torch.full((per, max_det, row), float(rank + 1))
+counts = torch.tensor([rank + 1, 0, max_det], dtype=torch.int32)
+g_out, g_cnt = sarpost.dist.allgather_detections(out, counts)
+assert g_out.shape == (world * per, max_det, row) and g_cnt.tolist() == [1, 0, 5, 2, 0, 5]
+assert bool((g_out[:per] == 1).all()) and bool((g_out[per:] == 2).all())
+buf = sarpost.dist.GatherBuffer(per, max_det, row, "cpu")
+buf.local_out.fill_(10.0 * (rank + 1)); buf.local_counts.copy_(counts)
+o, c = buf.exchange()
+assert bool((o[:per] == 10).all()) and bool((o[per:] == 20).all()) and c.tolist() == [1, 0, 5, 2, 0, 5]
+lo, hi = sarpost.dist.shard_range(7, rank, world)
+assert (lo, hi) == ((0, 4) if rank == 0 else (4, 7))
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_allgather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT, port], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"ok {r}" in o, o
