@@ -9,7 +9,7 @@ SOURCES = ["sarpost.cu"]
 DEPS = ["sarpost.cu", "common.cuh", "k1_candidates.cuh", "k2_select_sort.cuh", "k4_nms.cuh", "host_ctx.inl",
         os.path.join("..", "..", "include", "sarpost.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fopenmp", "-shared", "-cudart", "static", "-lgomp"]
 
 
 def nvcc_path() -> str:

@@ -58,7 +58,8 @@ struct Buf {
 
 struct sarpost_host_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t s_copy = nullptr, s_main = nullptr, s_fin = nullptr;
+    std::vector<cudaEvent_t> ev_copied, ev_done;
     sarpost::Buf d_levels, d_ws, d_rows6, d_counts, d_kidx, d_extras, d_out;
     sarpost::Buf h_rows6, h_counts, h_kidx, h_extras;
     int64_t last_h2d = 0, last_d2h = 0;
@@ -72,10 +73,12 @@ int32_t sarpost_host_ctx_create(int32_t device, sarpost_host_ctx_t **ctx) {
     sarpost_host_ctx *c = new sarpost_host_ctx();
     c->device = device;
     c->h_rows6.host = c->h_counts.host = c->h_kidx.host = c->h_extras.host = true;
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) {
-        delete c;
-        return fail(SARPOST_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    for (cudaStream_t *st : {&c->s_copy, &c->s_main, &c->s_fin}) {
+        cudaError_t e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            sarpost_host_ctx_destroy(c);
+            return fail(SARPOST_ECUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+        }
     }
     *ctx = c;
     return SARPOST_OK;
@@ -84,11 +87,15 @@ int32_t sarpost_host_ctx_create(int32_t device, sarpost_host_ctx_t **ctx) {
 void sarpost_host_ctx_destroy(sarpost_host_ctx_t *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    for (cudaStream_t st : {c->s_copy, c->s_main, c->s_fin})
+        if (st) cudaStreamSynchronize(st);
     for (sarpost::Buf *b : {&c->d_levels, &c->d_ws, &c->d_rows6, &c->d_counts, &c->d_kidx, &c->d_extras, &c->d_out,
                             &c->h_rows6, &c->h_counts, &c->h_kidx, &c->h_extras})
         b->release();
-    cudaStreamDestroy(c->stream);
+    for (cudaEvent_t e : c->ev_copied) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_done) cudaEventDestroy(e);
+    for (cudaStream_t st : {c->s_copy, c->s_main, c->s_fin})
+        if (st) cudaStreamDestroy(st);
     delete c;
 }
 
@@ -99,6 +106,12 @@ int32_t sarpost_host_ctx_last_traffic(const sarpost_host_ctx_t *c, int64_t *h2d_
     return SARPOST_OK;
 }
 
+// Pipelined over chunks of images on three streams:
+//   s_copy  H2D of the chunk's box+cls channels (one contiguous copy per image and level)
+//   s_main  fused pipeline of the chunk, D2H of its counts / indices (/ rows when there are no extras)
+//   s_fin   H2D of the packed extras of the chunk's kept rows, finish kernel, D2H of the final rows
+// While the copy engine streams chunk k+1, the GPU post-processes chunk k and the host packs the extras of
+// chunk k-1 (OpenMP), so the call costs about the PCIe time of the inputs.
 int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, const sarpost_nms_params_t *params,
                            float *out, int32_t *counts, int32_t *kept_index) {
     if (!c) return fail(SARPOST_EINVAL, "ctx is NULL");
@@ -108,27 +121,29 @@ int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, co
     if (int rc = check_params(params, g.nc)) return rc;
     if (!out || !counts) return fail(SARPOST_EINVAL, "NULL output pointer");
     CUDA_TRY(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
     const int B = g.batch, nch = 4 * kRegMax + g.nc, nm = g.n_extra_raw + g.n_extra_sig, max_det = params->max_det;
     c->last_h2d = c->last_d2h = 0;
+    int launches = 0;
 
-    // device copy of the box+cls channels of every level
+    // chunking: ~128 MB of input per chunk, at least 1 image
+    int64_t img_bytes = 0;
+    for (int l = 0; l < g.nl; ++l) img_bytes += static_cast<int64_t>(nch) * g.lvl_hw[l] * 4;
+    int chunk = static_cast<int>((128ll << 20) / (img_bytes > 0 ? img_bytes : 1));
+    chunk = chunk < 1 ? 1 : (chunk > B ? B : chunk);
+    const int n_chunks = (B + chunk - 1) / chunk;
+    while (static_cast<int>(c->ev_copied.size()) < n_chunks) {
+        cudaEvent_t a, b;
+        CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->ev_copied.push_back(a);
+        c->ev_done.push_back(b);
+    }
+
     int64_t off[kMaxLevels + 1];
     off[0] = 0;
     for (int l = 0; l < g.nl; ++l) off[l + 1] = align_up(off[l] + static_cast<int64_t>(B) * nch * g.lvl_hw[l] * 4, 256);
     if (int rc = c->d_levels.ensure(off[g.nl])) return rc;
-    sarpost_head_t hd = *head;
-    hd.no = nch;
-    hd.n_extra_raw = hd.n_extra_sigmoid = 0;
-    for (int l = 0; l < g.nl; ++l) {
-        char *dst = static_cast<char *>(c->d_levels.p) + off[l];
-        const int64_t width = static_cast<int64_t>(nch) * g.lvl_hw[l] * 4;
-        CUDA_TRY(cudaMemcpy2DAsync(dst, width, head->data[l], static_cast<int64_t>(g.no) * g.lvl_hw[l] * 4, width, B,
-                                   cudaMemcpyHostToDevice, s));
-        c->last_h2d += width * B;
-        hd.data[l] = dst;
-    }
-    const int64_t ws_bytes = sarpost_workspace_bytes(B, anchors, g.nc, params->multi_label, max_det);
+    const int64_t ws_bytes = sarpost_workspace_bytes(chunk, anchors, g.nc, params->multi_label, max_det);
     if (ws_bytes < 0) return static_cast<int32_t>(ws_bytes);
     if (int rc = c->d_ws.ensure(ws_bytes)) return rc;
     const int64_t rows = static_cast<int64_t>(B) * max_det;
@@ -138,37 +153,62 @@ int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, co
     if (int rc = c->h_rows6.ensure(rows * 6 * 4)) return rc;
     if (int rc = c->h_counts.ensure(B * 4)) return rc;
     if (int rc = c->h_kidx.ensure(rows * 4)) return rc;
+    if (nm > 0) {
+        if (int rc = c->h_extras.ensure(rows * nm * 4)) return rc;
+        if (int rc = c->d_extras.ensure(rows * nm * 4)) return rc;
+        if (int rc = c->d_out.ensure(rows * (6 + nm) * 4)) return rc;
+    }
+    float *d_rows6 = static_cast<float *>(c->d_rows6.p);
+    int32_t *d_counts = static_cast<int32_t *>(c->d_counts.p), *d_kidx = static_cast<int32_t *>(c->d_kidx.p);
+    int32_t *hc = static_cast<int32_t *>(c->h_counts.p), *hk = static_cast<int32_t *>(c->h_kidx.p);
 
-    const int saved_launches_base = 0;
-    (void)saved_launches_base;
-    if (int rc = sarpost_fused(&hd, params, static_cast<float *>(c->d_rows6.p), static_cast<int32_t *>(c->d_counts.p),
-                               static_cast<int32_t *>(c->d_kidx.p), c->d_ws.p, c->d_ws.bytes, s))
-        return rc;
-    int launches = g_launches;
-    CUDA_TRY(cudaMemcpyAsync(c->h_counts.p, c->d_counts.p, B * 4, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(c->h_kidx.p, c->d_kidx.p, rows * 4, cudaMemcpyDeviceToHost, s));
-    c->last_d2h += B * 4 + rows * 4;
-    if (nm == 0) {
-        CUDA_TRY(cudaMemcpyAsync(c->h_rows6.p, c->d_rows6.p, rows * 6 * 4, cudaMemcpyDeviceToHost, s));
-        c->last_d2h += rows * 6 * 4;
+    // ---- enqueue copy + compute of every chunk ----
+    for (int k = 0; k < n_chunks; ++k) {
+        const int b0 = k * chunk, nb = (b0 + chunk <= B) ? chunk : B - b0;
+        sarpost_head_t hd = *head;
+        hd.batch = nb;
+        hd.no = nch;
+        hd.n_extra_raw = hd.n_extra_sigmoid = 0;
+        for (int l = 0; l < g.nl; ++l) {
+            const int64_t width = static_cast<int64_t>(nch) * g.lvl_hw[l] * 4;
+            const int64_t spitch = static_cast<int64_t>(g.no) * g.lvl_hw[l] * 4;
+            char *dst = static_cast<char *>(c->d_levels.p) + off[l] + b0 * width;
+            // one contiguous copy per image: a pitched 2-D copy of these 0.4-27 MB rows runs at half the PCIe rate
+            for (int b = 0; b < nb; ++b)
+                CUDA_TRY(cudaMemcpyAsync(dst + b * width, static_cast<const char *>(head->data[l]) + (b0 + b) * spitch, width,
+                                         cudaMemcpyHostToDevice, c->s_copy));
+            c->last_h2d += width * nb;
+            hd.data[l] = dst;
+        }
+        CUDA_TRY(cudaEventRecord(c->ev_copied[k], c->s_copy));
+        CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_copied[k], 0));
+        if (int rc = sarpost_fused(&hd, params, d_rows6 + static_cast<int64_t>(b0) * max_det * 6, d_counts + b0,
+                                   d_kidx + static_cast<int64_t>(b0) * max_det, c->d_ws.p, c->d_ws.bytes, c->s_main))
+            return rc;
+        launches += g_launches;
+        CUDA_TRY(cudaMemcpyAsync(hc + b0, d_counts + b0, nb * 4, cudaMemcpyDeviceToHost, c->s_main));
+        CUDA_TRY(cudaMemcpyAsync(hk + static_cast<int64_t>(b0) * max_det, d_kidx + static_cast<int64_t>(b0) * max_det,
+                                 static_cast<int64_t>(nb) * max_det * 4, cudaMemcpyDeviceToHost, c->s_main));
+        c->last_d2h += nb * 4 + static_cast<int64_t>(nb) * max_det * 4;
+        if (nm == 0) {
+            CUDA_TRY(cudaMemcpyAsync(static_cast<float *>(c->h_rows6.p) + static_cast<int64_t>(b0) * max_det * 6,
+                                     d_rows6 + static_cast<int64_t>(b0) * max_det * 6, static_cast<int64_t>(nb) * max_det * 24,
+                                     cudaMemcpyDeviceToHost, c->s_main));
+            c->last_d2h += static_cast<int64_t>(nb) * max_det * 24;
+        }
+        CUDA_TRY(cudaEventRecord(c->ev_done[k], c->s_main));
     }
-    CUDA_TRY(cudaStreamSynchronize(s));
-    const int32_t *hc = static_cast<const int32_t *>(c->h_counts.p);
-    const int32_t *hk = static_cast<const int32_t *>(c->h_kidx.p);
-    memcpy(counts, hc, B * 4);
-    if (kept_index) memcpy(kept_index, hk, rows * 4);
-    if (nm == 0) {
-        memcpy(out, c->h_rows6.p, rows * 6 * 4);
-        g_launches = launches;
-        return SARPOST_OK;
-    }
-    // pack the raw extras of the kept rows from the host tensors (memcpy only)
-    if (int rc = c->h_extras.ensure(rows * nm * 4)) return rc;
-    if (int rc = c->d_extras.ensure(rows * nm * 4)) return rc;
-    if (int rc = c->d_out.ensure(rows * (6 + nm) * 4)) return rc;
+    // ---- per chunk: wait, pack the raw extras of the kept rows from the host tensors (memcpy only), finish ----
     float *he = static_cast<float *>(c->h_extras.p);
-    for (int b = 0; b < B; ++b) {
-        for (int r = 0; r < hc[b]; ++r) {
+    for (int k = 0; k < n_chunks; ++k) {
+        const int b0 = k * chunk, nb = (b0 + chunk <= B) ? chunk : B - b0;
+        CUDA_TRY(cudaEventSynchronize(c->ev_done[k]));
+        if (nm == 0) continue;
+        const int64_t n_rows = static_cast<int64_t>(nb) * max_det;
+#pragma omp parallel for schedule(static) num_threads(8)
+        for (int64_t q = 0; q < n_rows; ++q) {
+            const int b = b0 + static_cast<int>(q / max_det), r = static_cast<int>(q % max_det);
+            if (r >= hc[b]) continue;
             const uint32_t key = static_cast<uint32_t>(hk[static_cast<int64_t>(b) * max_det + r]);
             const uint32_t anchor = key / static_cast<uint32_t>(g.nc);
             int l = 0;
@@ -178,23 +218,28 @@ int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, co
             float *dst = he + (static_cast<int64_t>(b) * max_det + r) * nm;
             for (int m = 0; m < nm; ++m) dst[m] = src[static_cast<int64_t>(m) * hw];
         }
+        const int64_t o_e = static_cast<int64_t>(b0) * max_det * nm, o_o = static_cast<int64_t>(b0) * max_det * (6 + nm);
+        CUDA_TRY(cudaMemcpyAsync(static_cast<float *>(c->d_extras.p) + o_e, he + o_e, n_rows * nm * 4, cudaMemcpyHostToDevice, c->s_fin));
+        c->last_h2d += n_rows * nm * 4;
+        ExtrasFinishParams ep;
+        ep.rows6 = d_rows6 + static_cast<int64_t>(b0) * max_det * 6;
+        ep.extras = static_cast<const float *>(c->d_extras.p) + o_e;
+        ep.counts = d_counts + b0;
+        ep.out = static_cast<float *>(c->d_out.p) + o_o;
+        ep.max_det = max_det;
+        ep.nm = nm;
+        ep.n_extra_raw = g.n_extra_raw;
+        k_extras_finish<<<dim3((max_det + 7) / 8, nb), 256, 0, c->s_fin>>>(ep);
+        ++launches;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(out + o_o, static_cast<float *>(c->d_out.p) + o_o, n_rows * (6 + nm) * 4, cudaMemcpyDeviceToHost, c->s_fin));
+        c->last_d2h += n_rows * (6 + nm) * 4;
     }
-    CUDA_TRY(cudaMemcpyAsync(c->d_extras.p, he, rows * nm * 4, cudaMemcpyHostToDevice, s));
-    c->last_h2d += rows * nm * 4;
-    ExtrasFinishParams ep;
-    ep.rows6 = static_cast<const float *>(c->d_rows6.p);
-    ep.extras = static_cast<const float *>(c->d_extras.p);
-    ep.counts = static_cast<const int32_t *>(c->d_counts.p);
-    ep.out = static_cast<float *>(c->d_out.p);
-    ep.max_det = max_det;
-    ep.nm = nm;
-    ep.n_extra_raw = g.n_extra_raw;
-    k_extras_finish<<<dim3((max_det + 7) / 8, B), 256, 0, s>>>(ep);
-    ++launches;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(out, c->d_out.p, rows * (6 + nm) * 4, cudaMemcpyDeviceToHost, s));
-    c->last_d2h += rows * (6 + nm) * 4;
-    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaStreamSynchronize(c->s_fin));
+    CUDA_TRY(cudaStreamSynchronize(c->s_main));
+    memcpy(counts, hc, B * 4);
+    if (kept_index) memcpy(kept_index, hk, rows * 4);
+    if (nm == 0) memcpy(out, c->h_rows6.p, rows * 6 * 4);
     g_launches = launches;
     return SARPOST_OK;
 }
