@@ -36,6 +36,10 @@ WORKLOADS = {
     "cfg1": (640, (8, 16, 32), 1, 256, 6, 1,
              dict(conf_thres=0.25, iou_thres=0.7, max_det=300, max_nms=30000, multi_label=False), -4.0,
              "batch 1 at 640x640 (8400 anchors), JDE nc=1 no=327, conf 0.25 / iou 0.7"),
+    "cfg4": (640, (8, 16, 32), 1, 256, 6, 512,
+             dict(conf_thres=0.25, iou_thres=0.7, max_det=300, max_nms=30000, multi_label=False), -4.0,
+             "SAHI-style 640 tiles of 4000x3000 frames (48 tiles/frame), 512 tiles in total sharded over the GPUs "
+             "(strong scaling), per-tile post-process + all-gather of counts/boxes + cross-tile merge per frame"),
     "cfg5": (640, (8, 16, 32), 6, 0, 0, 32,
              dict(conf_thres=0.001, iou_thres=0.7, max_det=300, max_nms=30000, multi_label=True), -4.0,
              "val-mode multi_label sweep at 640x640, Detect nc=6 no=70, conf 0.001, 32 images per GPU"),
@@ -205,14 +209,49 @@ def main():
 
     imgsz, strides, nc, ed, sc, bs, kw, cls_mean, desc = WORKLOADS[args.workload]
     bs = args.batch or bs
+    sahi = args.workload == "cfg4"
+    scaling = "weak"
+    if sahi:  # strong scaling: a fixed total of tiles is sharded over the ranks
+        scaling = "strong"
+        total_tiles = bs
+        if total_tiles % n_gpus:
+            raise SystemExit("cfg4 needs the tile count to divide by the number of GPUs")
+        bs = total_tiles // n_gpus
+        args.no_e2e = True
     spec = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=sc)
     shapes = synth.level_shapes(imgsz, strides)
     anchors = sum(h * w for h, w in shapes)
     levels = synth.head_outputs(bs, shapes, nc, ed, sc, cls_mean=cls_mean, seed=1000 * 3 + rank, device=dev)
     torch.cuda.synchronize()
 
-    def step():
-        return sarpost.postprocess_fused(levels, spec, return_padded=True, **kw)
+    if sahi:
+        origins1 = sarpost.dist.sahi_grid(4000, 3000, 640, 0.2).to(dev)  # (48, 2)
+        tpf = origins1.shape[0]
+        n_frames = -(-total_tiles // tpf)
+        f_lo, f_hi = sarpost.dist.shard_range(n_frames, rank, world)
+        # gathered detections of ALL tiles (6 columns), padded with empty tiles up to whole frames
+        g_rows = torch.zeros((n_frames * tpf, kw["max_det"], 6), dtype=torch.float32, device=dev)
+        g_cnt = torch.zeros((n_frames * tpf,), dtype=torch.int32, device=dev)
+        origins = origins1.repeat(n_frames, 1)
+        lo = rank * bs
+
+        def step():
+            # boxes only: the extras of the few rows that survive the merge are fetched afterwards from the rank
+            # that owns the tile (sarpost.gather_extras), not for 300 rows of every tile
+            out, counts = sarpost.postprocess_fused(levels, spec, return_padded=True, with_extras=False, **kw)
+            g_rows[lo:lo + bs].copy_(out)
+            g_cnt[lo:lo + bs].copy_(counts)
+            if world > 1:
+                dist.all_gather_into_tensor(g_rows[:total_tiles], g_rows[lo:lo + bs])
+                dist.all_gather_into_tensor(g_cnt[:total_tiles], g_cnt[lo:lo + bs])
+            if f_hi > f_lo:
+                return sarpost.merge_tiles(g_rows[f_lo * tpf:f_hi * tpf], g_cnt[f_lo * tpf:f_hi * tpf],
+                                           origins[f_lo * tpf:f_hi * tpf], tpf, iou_thres=kw["iou_thres"],
+                                           max_det=kw["max_det"], return_padded=True)
+            return out, counts
+    else:
+        def step():
+            return sarpost.postprocess_fused(levels, spec, return_padded=True, **kw)
 
     def barrier():
         if world > 1:
@@ -222,7 +261,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         out, counts = step()
     barrier()
-    launches_per_step = sarpost.ops.last_launch_count()
+    launches_per_step = sarpost.ops.last_launch_count() + (3 if sahi else 0)  # cfg4: fused (3) + merge (3)
 
     # ---- timed region: K steps, CUDA events on the launching (current) stream ----
     clocks = ClockSampler(local)
@@ -248,6 +287,9 @@ def main():
     ms = float(t_ms.item())
     value = bs * n_gpus * args.steps / (ms / 1e3)
     n_det = int(counts.sum().item())
+    if sahi:
+        def step():  # stage timing / roofline below look at the per-tile fused call only
+            return sarpost.postprocess_fused(levels, spec, return_padded=True, with_extras=False, **kw)
 
     # ---- per-stage durations (library CUDA events around each stage, same stream), K1 roofline ----
     sarpost.ops.stage_timing(True)
@@ -323,9 +365,10 @@ def main():
         line = {
             "metric": "post-processed images/sec (decode+NMS)", "value": value, "unit": "images/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "images_per_gpu": bs, "global_batch": bs * n_gpus,
-                       "anchors": anchors, "channels": spec.no, "parallelism": f"batch-sharded x{n_gpus}, no data-path collective",
+                       "anchors": anchors, "channels": spec.no, "parallelism": (f"tiles sharded x{n_gpus}, NCCL all-gather of counts+boxes, frames merged by their owner rank" if sahi
+                                       else f"batch-sharded x{n_gpus}, no data-path collective"),
                        "l2": "one batch of inputs (hot channels %.0f MB) exceeds the 126 MB L2; no flush" % (bs * anchors * (64 + nc) * 4 / 1e6),
                        "candidates_per_image": n_cand / bs, "detections_per_image": n_det / bs},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

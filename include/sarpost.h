@@ -43,7 +43,9 @@ extern "C" {
 typedef struct sarpost_head {
     int32_t nl;              /* number of levels, 1..SARPOST_MAX_LEVELS */
     int32_t batch;           /* B */
-    int32_t no;              /* channels per anchor = 4*reg_max + nc + n_extra_raw + n_extra_sigmoid */
+    int32_t no;              /* channels per anchor in memory, >= 4*reg_max + nc + n_extra_raw + n_extra_sigmoid
+                                (trailing channels beyond the declared extras are ignored: declare 0 extras to
+                                get 6-column rows from a JDE head) */
     int32_t nc;              /* number of classes */
     int32_t reg_max;         /* DFL bins per side; only 16 is supported (head.py:39) */
     int32_t n_extra_raw;     /* extras copied through unchanged (JDE embedding, head.py:247) */
@@ -109,6 +111,14 @@ int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t chan
 int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *params, float *out,
                       int32_t *counts, int32_t *kept_index, void *workspace, int64_t workspace_bytes,
                       void *stream);
+
+/*
+ * Extras (raw embedding + sigmoid state, head.py:247) of an explicit list of n (image, anchor) pairs,
+ * for callers that learn which rows need them only later (e.g. after sarpost_merge_tiles).
+ *   image_index, anchor_index  device (n) int32;  out  device (n, n_extra_raw + n_extra_sigmoid)
+ */
+int32_t sarpost_gather_extras(const sarpost_head_t *head, const int32_t *image_index, const int32_t *anchor_index,
+                              int32_t n, float *out, void *stream);
 
 /*
  * Cross-tile merge for sliced (SAHI-style) inference: per frame, shift every tile's detections by

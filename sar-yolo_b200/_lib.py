@@ -53,6 +53,7 @@ SYMBOLS = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "sarpost_fused": (C.c_int32, [C.POINTER(Head), C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int64, C.c_void_p]),
+    "sarpost_gather_extras": (C.c_int32, [C.POINTER(Head), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "sarpost_merge_tiles": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_void_p]),

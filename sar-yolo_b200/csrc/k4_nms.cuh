@@ -572,4 +572,36 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
     }
 }
 
+// Extras (raw embedding, sigmoid state; head.py:247) of an explicit list of (image, anchor) pairs — used when
+// the rows that need them are only known after a later stage (cross-tile merge).  One warp per pair.
+struct GatherExtrasParams {
+    const int32_t *image_index, *anchor_index;
+    int32_t n;
+    float *out;  // [n, nm]
+    int32_t nl, no, nc, batch, n_extra_raw, nm;
+    int32_t lvl_aoff[kMaxLevels + 1];
+    int32_t lvl_hw[kMaxLevels];
+    const float *lvl_ptr[kMaxLevels];
+};
+
+__global__ void __launch_bounds__(kGatherWarps * 32) k_gather_extras(const __grid_constant__ GatherExtrasParams p) {
+    const int q = blockIdx.x * kGatherWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (q >= p.n) return;
+    const int b = p.image_index[q], a = p.anchor_index[q];
+    float *o = p.out + static_cast<int64_t>(q) * p.nm;
+    if (b < 0 || b >= p.batch || a < 0 || a >= p.lvl_aoff[p.nl]) {  // out-of-range pair: zero row
+        for (int c = lane; c < p.nm; c += 32) o[c] = 0.0f;
+        return;
+    }
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i) l += (i < p.nl && a >= p.lvl_aoff[i]) ? 1 : 0;
+    const int hw = p.lvl_hw[l];
+    const float *src = p.lvl_ptr[l] + (static_cast<int64_t>(b) * p.no + 4 * kRegMax + p.nc) * hw + (a - p.lvl_aoff[l]);
+    for (int c = lane; c < p.nm; c += 32) {
+        const float v = __ldg(src + static_cast<int64_t>(c) * hw);
+        o[c] = c < p.n_extra_raw ? v : sigmoid_rn(v);
+    }
+}
+
 }  // namespace sarpost

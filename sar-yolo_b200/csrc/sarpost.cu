@@ -156,8 +156,8 @@ static int fill_geom(const sarpost_head_t *h, HeadGeom *g, int64_t *anchors) {
     if (h->reg_max != kRegMax) return fail(SARPOST_EUNSUPPORTED, "reg_max %d unsupported (only 16, head.py:39)", h->reg_max);
     if (h->batch < 1) return fail(SARPOST_EINVAL, "batch %d < 1", h->batch);
     if (h->nc < 1 || h->nc > SARPOST_MAX_CLASSES) return fail(SARPOST_EUNSUPPORTED, "nc %d outside [1, %d]", h->nc, SARPOST_MAX_CLASSES);
-    if (h->n_extra_raw < 0 || h->n_extra_sigmoid < 0 || h->no != 4 * kRegMax + h->nc + h->n_extra_raw + h->n_extra_sigmoid)
-        return fail(SARPOST_EINVAL, "no %d != 4*reg_max + nc + extras (%d)", h->no, 4 * kRegMax + h->nc + h->n_extra_raw + h->n_extra_sigmoid);
+    if (h->n_extra_raw < 0 || h->n_extra_sigmoid < 0 || h->no < 4 * kRegMax + h->nc + h->n_extra_raw + h->n_extra_sigmoid)
+        return fail(SARPOST_EINVAL, "no %d < 4*reg_max + nc + extras (%d)", h->no, 4 * kRegMax + h->nc + h->n_extra_raw + h->n_extra_sigmoid);
     memset(g, 0, sizeof(*g));
     g->nl = h->nl;
     g->batch = h->batch;
@@ -505,6 +505,37 @@ int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const 
     gp.dets_per_tile = dets_per_tile;
     gp.row_len = row_len;
     return run_tail(P, n_frames, params, 1, gp, out, counts, kept_index, s);
+}
+
+int32_t sarpost_gather_extras(const sarpost_head_t *head, const int32_t *image_index, const int32_t *anchor_index,
+                              int32_t n, float *out, void *stream) {
+    g_launches = 0;
+    HeadGeom g;
+    int64_t anchors = 0;
+    if (int rc = fill_geom(head, &g, &anchors)) return rc;
+    if (n < 0 || (n > 0 && (!image_index || !anchor_index || !out))) return fail(SARPOST_EINVAL, "bad gather arguments");
+    if (n == 0 || g.n_extra_raw + g.n_extra_sig == 0) return SARPOST_OK;
+    GatherExtrasParams p;
+    memset(&p, 0, sizeof(p));
+    p.image_index = image_index;
+    p.anchor_index = anchor_index;
+    p.n = n;
+    p.out = out;
+    p.nl = g.nl;
+    p.no = g.no;
+    p.nc = g.nc;
+    p.batch = g.batch;
+    p.n_extra_raw = g.n_extra_raw;
+    p.nm = g.n_extra_raw + g.n_extra_sig;
+    for (int l = 0; l <= kMaxLevels; ++l) p.lvl_aoff[l] = g.lvl_aoff[l];
+    for (int l = 0; l < kMaxLevels; ++l) {
+        p.lvl_hw[l] = g.lvl_hw[l];
+        p.lvl_ptr[l] = g.lvl_ptr[l];
+    }
+    k_gather_extras<<<(n + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return SARPOST_OK;
 }
 
 #ifdef SARPOST_PHASE_PROF

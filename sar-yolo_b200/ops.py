@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import Head, NmsParams, lib
 
-__all__ = ["HeadSpec", "non_max_suppression", "decode", "postprocess_fused", "merge_tiles", "postprocess_host",
+__all__ = ["HeadSpec", "non_max_suppression", "decode", "postprocess_fused", "merge_tiles", "gather_extras", "postprocess_host",
            "HostContext", "last_launch_count", "stage_timing", "stage_times"]
 
 
@@ -83,7 +83,7 @@ def _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det,
     return p, keep
 
 
-def _make_head(levels: Sequence[torch.Tensor], spec: HeadSpec, host: bool = False) -> Head:
+def _make_head(levels: Sequence[torch.Tensor], spec: HeadSpec, host: bool = False, with_extras: bool = True) -> Head:
     if len(levels) != len(spec.strides):
         raise ValueError(f"sarpost: {len(levels)} level tensors but {len(spec.strides)} strides")
     if len(levels) > _lib.MAX_LEVELS:
@@ -94,8 +94,8 @@ def _make_head(levels: Sequence[torch.Tensor], spec: HeadSpec, host: bool = Fals
     h.no = spec.no
     h.nc = spec.nc
     h.reg_max = spec.reg_max
-    h.n_extra_raw = spec.embed_dim
-    h.n_extra_sigmoid = spec.state_classes
+    h.n_extra_raw = spec.embed_dim if with_extras else 0
+    h.n_extra_sigmoid = spec.state_classes if with_extras else 0
     for i, x in enumerate(levels):
         if x.dim() != 4 or x.shape[0] != h.batch or x.shape[1] != spec.no:
             raise ValueError(f"sarpost: level {i} has shape {tuple(x.shape)}, expected (B={h.batch}, no={spec.no}, H, W)")
@@ -225,14 +225,17 @@ def decode(levels: Sequence[torch.Tensor], spec: HeadSpec) -> torch.Tensor:
 
 def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres=0.25, iou_thres=0.45, classes=None,
                       agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=7680,
-                      return_index=False, return_padded=False):
+                      return_index=False, return_padded=False, with_extras=True):
     """decode + non_max_suppression in one pass (never materialises y; the extras channels are read only
     for the kept rows).  Result as `non_max_suppression`; `return_padded=True` returns the raw
-    `(out (B, max_det, 6+nm), counts (B,) int32[, kept_index])` device tensors without any host sync."""
+    `(out (B, max_det, 6+nm), counts (B,) int32[, kept_index])` device tensors without any host sync.
+    `with_extras=False` returns 6-column rows even for a JDE head (use `gather_extras` later for the rows that
+    survive a subsequent stage such as the cross-tile merge)."""
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     levels = _prep_levels(levels)
-    head = _make_head(levels, spec)
+    head = _make_head(levels, spec, with_extras=with_extras)
+    nm = spec.nm if with_extras else 0
     dev = levels[0].device
     anchors = sum(int(x.shape[2]) * int(x.shape[3]) for x in levels)
     bs = head.batch
@@ -242,7 +245,7 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
         if ws_bytes < 0:
             _lib.check(int(ws_bytes))
         ws = _workspace(ws_bytes, dev)
-        out = torch.empty((bs, int(max_det), 6 + spec.nm), dtype=torch.float32, device=dev)
+        out = torch.empty((bs, int(max_det), 6 + nm), dtype=torch.float32, device=dev)
         counts = torch.empty((bs,), dtype=torch.int32, device=dev)
         want_idx = return_index
         kidx = torch.empty((bs, int(max_det)), dtype=torch.int32, device=dev) if want_idx else None
@@ -256,6 +259,23 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
         n = [r.shape[0] for r in rows]
         return rows, [kidx[b, : n[b]] for b in range(bs)]
     return rows
+
+
+def gather_extras(levels: Sequence[torch.Tensor], spec: HeadSpec, image_index: torch.Tensor,
+                  anchor_index: torch.Tensor) -> torch.Tensor:
+    """Extras (raw embedding + sigmoid state, head.py:247) of explicit `(image, anchor)` pairs -> `(n, nm)`."""
+    levels = _prep_levels(levels)
+    head = _make_head(levels, spec)
+    dev = levels[0].device
+    ii = image_index.to(device=dev, dtype=torch.int32).contiguous()
+    ai = anchor_index.to(device=dev, dtype=torch.int32).contiguous()
+    if ii.shape != ai.shape or ii.dim() != 1:
+        raise ValueError("sarpost: image_index and anchor_index must be 1-D tensors of equal length")
+    out = torch.empty((ii.shape[0], spec.nm), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sarpost_gather_extras(C.byref(head), ii.data_ptr(), ai.data_ptr(), int(ii.shape[0]), out.data_ptr(),
+                                             _stream_ptr(dev)))
+    return out
 
 
 def merge_tiles(dets: torch.Tensor, det_counts: torch.Tensor, origins: torch.Tensor, tiles_per_frame: int,

@@ -73,6 +73,6 @@ def test_argument_errors_do_not_need_a_gpu(sarpost):
     h = L.Head()
     h.nl, h.batch, h.no, h.nc, h.reg_max = 1, 1, 70, 6, 8
     assert lib.sarpost_decode(C.byref(h), ptr, None) == L.EUNSUPPORTED  # reg_max != 16
-    h.reg_max, h.no = 16, 71
-    assert lib.sarpost_decode(C.byref(h), ptr, None) == L.EINVAL and "no 71" in L.last_error()
+    h.reg_max, h.no = 16, 69  # fewer channels than 4*reg_max + nc
+    assert lib.sarpost_decode(C.byref(h), ptr, None) == L.EINVAL and "no 69" in L.last_error()
     assert lib.sarpost_stage_times(None) == L.EINVAL

@@ -299,3 +299,47 @@ def test_errors_and_api_contract(sarpost, cuda):
     o = sarpost.non_max_suppression(e2e, conf_thres=0.5, max_det=10)
     assert all(t.shape[0] <= 10 and bool((t[:, 4] > 0.5).all()) for t in o)
     assert sarpost.ops.last_launch_count() >= 0
+
+
+def test_sharded_tiles_then_merge_equals_single_device(sarpost, cuda):
+    """cfg4 in miniature: 2 emulated ranks post-process disjoint tile ranges, their padded detections are
+    concatenated (what the all-gather produces) and merged per frame; must equal one device doing it all."""
+    strides = (8, 16, 32)
+    shapes = sarpost.synth.level_shapes(320, strides)
+    spec = sarpost.HeadSpec(nc=2, strides=strides, embed_dim=4, state_classes=0)
+    origins = sarpost.dist.sahi_grid(900, 600, 320, 0.2).to(cuda)
+    tpf = origins.shape[0]
+    n_frames = 2
+    levels = sarpost.synth.head_outputs(n_frames * tpf, shapes, 2, 4, 0, seed=55, blobs=3)
+    kw = dict(conf_thres=0.25, iou_thres=0.7, max_det=50)
+    full_out, full_cnt = sarpost.postprocess_fused([x.to(cuda) for x in levels], spec, return_padded=True, **kw)
+    parts = []
+    for r in range(2):
+        lo, hi = sarpost.dist.shard_range(n_frames * tpf, r, 2)
+        parts.append(sarpost.postprocess_fused([x[lo:hi].to(cuda) for x in levels], spec, return_padded=True, **kw))
+    g_out = torch.cat([p[0] for p in parts])
+    g_cnt = torch.cat([p[1] for p in parts])
+    assert torch.equal(g_cnt, full_cnt)
+    org = origins.repeat(n_frames, 1)
+    a = sarpost.merge_tiles(full_out, full_cnt, org, tpf, iou_thres=0.5, max_det=100)
+    b = sarpost.merge_tiles(g_out, g_cnt, org, tpf, iou_thres=0.5, max_det=100)
+    assert len(a) == n_frames
+    for x, y in zip(a, b):
+        assert x.shape[0] > 0 and torch.equal(x, y)
+
+
+def test_boxes_only_and_gather_extras(sarpost, cuda):
+    """with_extras=False gives the same 6 columns; gather_extras reproduces the extras of the kept rows."""
+    strides = (8, 16, 32)
+    shapes = sarpost.synth.level_shapes(320, strides)
+    spec = sarpost.HeadSpec(nc=1, strides=strides, embed_dim=32, state_classes=6)
+    levels = [x.to(cuda) for x in sarpost.synth.head_outputs(3, shapes, 1, 32, 6, seed=8)]
+    kw = dict(conf_thres=0.25, iou_thres=0.7, max_det=80)
+    full, idx = sarpost.postprocess_fused(levels, spec, return_index=True, **kw)
+    lean = sarpost.postprocess_fused(levels, spec, with_extras=False, **kw)
+    for b in range(3):
+        assert lean[b].shape[1] == 6 and torch.equal(lean[b], full[b][:, :6])
+    img = torch.cat([torch.full((i.shape[0],), b, dtype=torch.int32, device=cuda) for b, i in enumerate(idx)])
+    anc = torch.cat(idx) // spec.nc
+    ex = sarpost.gather_extras(levels, spec, img, anc)
+    assert torch.equal(ex, torch.cat([f[:, 6:] for f in full]))
