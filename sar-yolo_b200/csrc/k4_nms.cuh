@@ -43,6 +43,38 @@ constexpr int kSortCap = 1024;   // candidates sorted in shared memory at once
 constexpr int kSub = 256;        // candidates per NMS sub-chunk
 constexpr int kSubWords = kSub / 32;
 
+// Where the extras columns of an output row live (K5 gathers them; K4 prefetches them into L2).
+struct ExtrasSrc {
+    int32_t mode;               // 0 decoded prediction, 1 raw level tensors, 2 source detection rows (merge)
+    int32_t nm, nc;
+    // mode 0
+    const float *pred;
+    int32_t channels;
+    int64_t anchors;
+    // mode 1
+    int32_t nl, no, n_extra_raw;
+    int32_t lvl_aoff[kMaxLevels + 1];
+    int32_t lvl_hw[kMaxLevels];
+    const float *lvl_ptr[kMaxLevels];
+    // mode 2
+    const float *dets;
+    int32_t dets_per_tile, row_len;
+};
+
+// address of extras channel 0 of (image b, anchor) and the element stride between channels
+__device__ __forceinline__ const float *extras_base(const ExtrasSrc &e, int b, uint32_t anchor, int64_t *stride) {
+    if (e.mode == 0) {
+        *stride = e.anchors;
+        return e.pred + (static_cast<int64_t>(b) * e.channels + 4 + e.nc) * e.anchors + anchor;
+    }
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxLevels; ++i) l += (i < e.nl && anchor >= static_cast<uint32_t>(e.lvl_aoff[i])) ? 1 : 0;
+    const int hw = e.lvl_hw[l];
+    *stride = hw;
+    return e.lvl_ptr[l] + (static_cast<int64_t>(b) * e.no + 4 * kRegMax + e.nc) * hw + (anchor - e.lvl_aoff[l]);
+}
+
 struct NmsParams {
     CandStore st;
     uint32_t *tmp_key_a, *tmp_val_a; // [B*cap] scratch for the oversized-bucket fallback sort
@@ -505,24 +537,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 // ---------------------------------------------------------------------------------------------
 struct GatherParams {
     CandStore st;
+    ExtrasSrc ex;
     const uint32_t *kept_slot;  // [B*max_det]
     const int32_t *counts;      // [B]
     float *out;                 // [B, max_det, 6+nm]
     int32_t *kept_index;        // [B*max_det] or nullptr
-    int32_t max_det, nc, nm;
-    int32_t mode;               // 0 decoded, 1 fused, 2 merge
-    // mode 0
-    const float *pred;
-    int32_t channels;
-    int64_t anchors;
-    // mode 1
-    int32_t nl, no, n_extra_raw;
-    int32_t lvl_aoff[kMaxLevels + 1];
-    int32_t lvl_hw[kMaxLevels];
-    const float *lvl_ptr[kMaxLevels];
-    // mode 2
-    const float *dets;
-    int32_t dets_per_tile, row_len;
+    int32_t max_det;
 };
 
 constexpr int kGatherWarps = 8;
@@ -535,17 +555,17 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
     const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
     const uint32_t slot = p.kept_slot[static_cast<int64_t>(b) * p.max_det + r];
     const uint32_t key = p.st.key[seg + slot];
-    const int row_len = 6 + p.nm;
+    const int row_len = 6 + p.ex.nm;
     float *o = p.out + (static_cast<int64_t>(b) * p.max_det + r) * row_len;
-    if (p.mode == 2) {
-        const float *src = p.dets + (static_cast<int64_t>(b) * p.st.tpi * p.dets_per_tile + key) * p.row_len;
+    if (p.ex.mode == 2) {
+        const float *src = p.ex.dets + (static_cast<int64_t>(b) * p.st.tpi * p.ex.dets_per_tile + key) * p.ex.row_len;
         const float4 bx = p.st.box[seg + slot];
         for (int c = lane; c < row_len; c += 32)
             o[c] = c == 0 ? bx.x : c == 1 ? bx.y : c == 2 ? bx.z : c == 3 ? bx.w : src[c];
         if (lane == 0 && p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
         return;
     }
-    const uint32_t anchor = key / static_cast<uint32_t>(p.nc), cls = key - anchor * static_cast<uint32_t>(p.nc);
+    const uint32_t anchor = key / static_cast<uint32_t>(p.ex.nc), cls = key - anchor * static_cast<uint32_t>(p.ex.nc);
     if (lane == 0) {
         const float4 bx = p.st.box[seg + slot];
         o[0] = bx.x;
@@ -556,18 +576,13 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
         o[5] = static_cast<float>(cls);
         if (p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
     }
-    if (p.mode == 0) {
-        const float *src = p.pred + (static_cast<int64_t>(b) * p.channels + 4 + p.nc) * p.anchors + anchor;
-        for (int c = lane; c < p.nm; c += 32) o[6 + c] = __ldg(src + static_cast<int64_t>(c) * p.anchors);
-    } else if (p.mode == 1) {
-        int l = 0;
-#pragma unroll
-        for (int i = 1; i < kMaxLevels; ++i) l += (i < p.nl && anchor >= static_cast<uint32_t>(p.lvl_aoff[i])) ? 1 : 0;
-        const int hw = p.lvl_hw[l];
-        const float *src = p.lvl_ptr[l] + (static_cast<int64_t>(b) * p.no + 4 * kRegMax + p.nc) * hw + (anchor - p.lvl_aoff[l]);
-        for (int c = lane; c < p.nm; c += 32) {
-            const float v = __ldg(src + static_cast<int64_t>(c) * hw);
-            o[6 + c] = c < p.n_extra_raw ? v : sigmoid_rn(v);
+    if (p.ex.nm > 0) {
+        int64_t stride;
+        const float *src = extras_base(p.ex, b, anchor, &stride);
+        const int n_raw = p.ex.mode == 0 ? p.ex.nm : p.ex.n_extra_raw;  // a decoded prediction is copied verbatim
+        for (int c = lane; c < p.ex.nm; c += 32) {
+            const float v = __ldg(src + c * stride);
+            o[6 + c] = c < n_raw ? v : sigmoid_rn(v);
         }
     }
 }

@@ -288,7 +288,7 @@ static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandSto
 }
 
 // K2 + K4 + K5 on a filled candidate store.
-static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, int nc, GatherParams gp, float *out,
+static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, int nc, const ExtrasSrc &ex, float *out,
                     int32_t *counts, int32_t *kept_index, cudaStream_t s) {
     NmsParams np;
     np.st = P.st;
@@ -311,13 +311,14 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     CUDA_TRY(cudaGetLastError());
     stage_mark(3, s);
 
+    GatherParams gp;
     gp.st = P.st;
+    gp.ex = ex;
     gp.kept_slot = P.kept_slot;
     gp.counts = counts;
     gp.out = out;
     gp.kept_index = kept_index;
     gp.max_det = prm->max_det;
-    gp.nc = nc;
     k5_gather<<<dim3((prm->max_det + kGatherWarps - 1) / kGatherWarps, batch), kGatherWarps * 32, 0, s>>>(gp);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
@@ -422,14 +423,15 @@ int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t chan
     CUDA_TRY(cudaGetLastError());
     stage_mark(2, s);
 
-    GatherParams gp;
-    memset(&gp, 0, sizeof(gp));
-    gp.mode = 0;
-    gp.nm = channels - 4 - nc;
-    gp.pred = prediction;
-    gp.channels = channels;
-    gp.anchors = anchors;
-    return run_tail(P, batch, params, nc, gp, out, counts, kept_index, s);
+    ExtrasSrc ex;
+    memset(&ex, 0, sizeof(ex));
+    ex.mode = 0;
+    ex.nc = nc;
+    ex.nm = channels - 4 - nc;
+    ex.pred = prediction;
+    ex.channels = channels;
+    ex.anchors = anchors;
+    return run_tail(P, batch, params, nc, ex, out, counts, kept_index, s);
 }
 
 int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *params, float *out, int32_t *counts,
@@ -453,19 +455,20 @@ int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *pa
     if (int rc = launch_k1_fused(g, f, P.st, s)) return rc;
     stage_mark(2, s);
 
-    GatherParams gp;
-    memset(&gp, 0, sizeof(gp));
-    gp.mode = 1;
-    gp.nm = g.n_extra_raw + g.n_extra_sig;
-    gp.nl = g.nl;
-    gp.no = g.no;
-    gp.n_extra_raw = g.n_extra_raw;
-    for (int l = 0; l <= kMaxLevels; ++l) gp.lvl_aoff[l] = g.lvl_aoff[l];
+    ExtrasSrc ex;
+    memset(&ex, 0, sizeof(ex));
+    ex.mode = 1;
+    ex.nc = g.nc;
+    ex.nm = g.n_extra_raw + g.n_extra_sig;
+    ex.nl = g.nl;
+    ex.no = g.no;
+    ex.n_extra_raw = g.n_extra_raw;
+    for (int l = 0; l <= kMaxLevels; ++l) ex.lvl_aoff[l] = g.lvl_aoff[l];
     for (int l = 0; l < kMaxLevels; ++l) {
-        gp.lvl_hw[l] = g.lvl_hw[l];
-        gp.lvl_ptr[l] = g.lvl_ptr[l];
+        ex.lvl_hw[l] = g.lvl_hw[l];
+        ex.lvl_ptr[l] = g.lvl_ptr[l];
     }
-    return run_tail(P, g.batch, params, g.nc, gp, out, counts, kept_index, s);
+    return run_tail(P, g.batch, params, g.nc, ex, out, counts, kept_index, s);
 }
 
 int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const float *origins, int32_t n_frames,
@@ -497,14 +500,15 @@ int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const 
     CUDA_TRY(cudaGetLastError());
     stage_mark(2, s);
 
-    GatherParams gp;
-    memset(&gp, 0, sizeof(gp));
-    gp.mode = 2;
-    gp.nm = row_len - 6;
-    gp.dets = dets;
-    gp.dets_per_tile = dets_per_tile;
-    gp.row_len = row_len;
-    return run_tail(P, n_frames, params, 1, gp, out, counts, kept_index, s);
+    ExtrasSrc ex;
+    memset(&ex, 0, sizeof(ex));
+    ex.mode = 2;
+    ex.nc = 1;
+    ex.nm = row_len - 6;
+    ex.dets = dets;
+    ex.dets_per_tile = dets_per_tile;
+    ex.row_len = row_len;
+    return run_tail(P, n_frames, params, 1, ex, out, counts, kept_index, s);
 }
 
 int32_t sarpost_gather_extras(const sarpost_head_t *head, const int32_t *image_index, const int32_t *anchor_index,
