@@ -67,6 +67,10 @@ typedef struct sarpost_nms_params {
     float max_wh;          /* ops.py:289,295 class offset = cls * max_wh */
     const int32_t *classes;/* HOST pointer to the `classes` filter (ops.py:278-279) or NULL */
     int32_t n_classes;
+    int32_t workspace_clean;/* 0: the call zeroes the score-histogram head of the workspace itself (one memset node).
+                              1: the caller guarantees the first sarpost_workspace_clean_bytes(batch) bytes are zero —
+                              true after sarpost_workspace_prepare and after every successful call that used the
+                              workspace with the SAME batch (each call leaves that region zeroed again). */
 } sarpost_nms_params_t;
 
 /* Last error message of the calling thread ("" if none). */
@@ -82,6 +86,10 @@ int64_t sarpost_workspace_bytes(int32_t batch, int64_t anchors, int32_t nc, int3
                                 int32_t max_det);
 int64_t sarpost_merge_workspace_bytes(int32_t n_frames, int32_t tiles_per_frame, int32_t dets_per_tile,
                                       int32_t max_det);
+/* Persistent workspaces (see sarpost_nms_params_t.workspace_clean): size of the region that must be zero on
+ * entry for `batch` images (frames for the merge), and a helper that zeroes it on `stream`. */
+int64_t sarpost_workspace_clean_bytes(int32_t batch);
+int32_t sarpost_workspace_prepare(void *workspace, int64_t workspace_bytes, int32_t batch, void *stream);
 
 /*
  * Replaces Detect._inference / JDE._inference (nn/modules/head.py:100-131, :214-249) including

@@ -32,7 +32,7 @@ class NmsParams(C.Structure):
     _fields_ = [
         ("conf_thres", C.c_float), ("iou_thres", C.c_double), ("agnostic", C.c_int32), ("multi_label", C.c_int32),
         ("max_det", C.c_int32), ("max_nms", C.c_int32), ("max_wh", C.c_float),
-        ("classes", C.POINTER(C.c_int32)), ("n_classes", C.c_int32),
+        ("classes", C.POINTER(C.c_int32)), ("n_classes", C.c_int32), ("workspace_clean", C.c_int32),
     ]
 
 
@@ -48,6 +48,8 @@ SYMBOLS = {
     "sarpost_version": (C.c_int32, []),
     "sarpost_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "sarpost_merge_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "sarpost_workspace_clean_bytes": (C.c_int64, [C.c_int32]),
+    "sarpost_workspace_prepare": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "sarpost_decode": (C.c_int32, [C.POINTER(Head), C.c_void_p, C.c_void_p]),
     "sarpost_nms_decoded": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(NmsParams),
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

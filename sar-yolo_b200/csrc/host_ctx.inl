@@ -162,6 +162,8 @@ int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, co
     int32_t *d_counts = static_cast<int32_t *>(c->d_counts.p), *d_kidx = static_cast<int32_t *>(c->d_kidx.p);
     int32_t *hc = static_cast<int32_t *>(c->h_counts.p), *hk = static_cast<int32_t *>(c->h_kidx.p);
 
+    sarpost_nms_params_t prm = *params;
+    prm.workspace_clean = 0;  // chunks of different sizes share the context's workspace: let each call zero its histogram
     // ---- enqueue copy + compute of every chunk ----
     for (int k = 0; k < n_chunks; ++k) {
         const int b0 = k * chunk, nb = (b0 + chunk <= B) ? chunk : B - b0;
@@ -182,7 +184,7 @@ int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, co
         }
         CUDA_TRY(cudaEventRecord(c->ev_copied[k], c->s_copy));
         CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_copied[k], 0));
-        if (int rc = sarpost_fused(&hd, params, d_rows6 + static_cast<int64_t>(b0) * max_det * 6, d_counts + b0,
+        if (int rc = sarpost_fused(&hd, &prm, d_rows6 + static_cast<int64_t>(b0) * max_det * 6, d_counts + b0,
                                    d_kidx + static_cast<int64_t>(b0) * max_det, c->d_ws.p, c->d_ws.bytes, c->s_main))
             return rc;
         launches += g_launches;

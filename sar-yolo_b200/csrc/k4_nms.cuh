@@ -176,6 +176,63 @@ __device__ __forceinline__ void radix_pass_global(const uint32_t *in_key, const 
     __syncthreads();
 }
 
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int lane_mask) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), lane_mask);
+    const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), lane_mask);
+    return (static_cast<unsigned long long>(hi) << 32) | lo;
+}
+
+// Bitonic sorting network (descending) over 2^lpw <= 1024 keys in shared memory, blockDim = kNmsThreads.
+// Thread t owns the adjacent pair (2t, 2t+1): compare-exchange strides 1..32 stay inside a warp (registers +
+// shuffles, no barrier); only strides >= 64 go through shared memory.  15 barriers for 1024 keys instead of 55.
+__device__ __forceinline__ void bitonic_sort_desc(unsigned long long *key, int lpw) {
+    const int t = threadIdx.x, half_n = 1 << (lpw - 1);
+    auto reg_steps = [&](unsigned long long &a, unsigned long long &b, int lk, int lj_hi) {
+        const bool desc = ((t >> (lk - 1)) & 1) == 0;  // = ((2t >> lk) & 1) == 0, identical for 2t+1
+        for (int lj = lj_hi; lj >= 1; --lj) {
+            const int h = 1 << (lj - 1);  // partner thread = t ^ h
+            const unsigned long long pa = shfl_xor_u64(a, h), pb = shfl_xor_u64(b, h);
+            const bool keep_max = ((t & h) == 0) == desc;
+            a = keep_max ? (a > pa ? a : pa) : (a < pa ? a : pa);
+            b = keep_max ? (b > pb ? b : pb) : (b < pb ? b : pb);
+        }
+        if ((a < b) == desc) {
+            const unsigned long long x = a;
+            a = b;
+            b = x;
+        }
+    };
+    if (t < half_n) {  // warp-uniform: half_n is a multiple of 32
+        unsigned long long a = key[2 * t], b = key[2 * t + 1];
+        const int first = lpw < 6 ? lpw : 6;
+        for (int lk = 1; lk <= first; ++lk) reg_steps(a, b, lk, lk - 1);
+        key[2 * t] = a;
+        key[2 * t + 1] = b;
+    }
+    __syncthreads();
+    for (int lk = 7; lk <= lpw; ++lk) {
+        for (int lj = lk - 1; lj >= 6; --lj) {
+            if (t < half_n) {
+                const int i = ((t >> lj) << (lj + 1)) | (t & ((1 << lj) - 1)), q = i | (1 << lj);
+                const bool desc = ((i >> lk) & 1) == 0;
+                const unsigned long long x = key[i], y = key[q];
+                if ((x < y) == desc) {
+                    key[i] = y;
+                    key[q] = x;
+                }
+            }
+            __syncthreads();
+        }
+        if (t < half_n) {
+            unsigned long long a = key[2 * t], b = key[2 * t + 1];
+            reg_steps(a, b, lk, 5);
+            key[2 * t] = a;
+            key[2 * t + 1] = b;
+        }
+        __syncthreads();
+    }
+}
+
 // dynamic shared memory: kept_box[max_det] float4 | kept_area[max_det] | kept_slot[max_det]
 __host__ __device__ inline size_t nms_smem_bytes(int max_det) { return static_cast<size_t>(max_det) * 24; }
 
@@ -213,12 +270,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     //      candidate of bucket 4095-d in the sorted order (x kHistSample).  Estimates only steer how many
     //      buckets a chunk spans; membership, ranks and results are exact.  n_all = exact candidate count. ----
     {
-        const int32_t *hist = p.st.hist + static_cast<int64_t>(b) * kBuckets;
+        int32_t *hist = p.st.hist + static_cast<int64_t>(b) * kBuckets;
         constexpr int kPer = kBuckets / kNmsThreads;  // 8 consecutive d per thread
         int loc[kPer], sum = 0;
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
             loc[i] = hist[kBuckets - 1 - (tid * kPer + i)] * kHistSample;
+            hist[kBuckets - 1 - (tid * kPer + i)] = 0;  // leave the histogram zeroed for the next call (workspace_clean)
             sum += loc[i];
         }
         int tot = 0;
@@ -457,21 +515,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 const int pw = 1 << lpw;
                 for (int i = m + tid; i < pw; i += kNmsThreads) SKEY[i] = 0ull;
                 __syncthreads();
-                // bitonic network, descending
-                for (int lk = 1; lk <= lpw; ++lk) {
-                    for (int lj = lk - 1; lj >= 0; --lj) {
-                        for (int t = tid; t < (pw >> 1); t += kNmsThreads) {
-                            const int i = ((t >> lj) << (lj + 1)) | (t & ((1 << lj) - 1)), q = i | (1 << lj);
-                            const bool desc = ((i >> lk) & 1) == 0;
-                            const unsigned long long x = SKEY[i], y = SKEY[q];
-                            if ((x < y) == desc) {
-                                SKEY[i] = y;
-                                SKEY[q] = x;
-                            }
-                        }
-                        __syncthreads();
-                    }
-                }
+                bitonic_sort_desc(SKEY, lpw);
                 PROF_MARK(2);
                 process_sorted([&](int i) { return 0xffffffffu - static_cast<uint32_t>(SKEY[i]); }, min(m, n_limit - pos));
             }

@@ -70,6 +70,7 @@ static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_d
         return at;
     };
     const int64_t slots = batch * cap;
+    L.hist = take(batch * kBuckets * 4);  // first: the only region with an entry contract (see workspace_clean)
     L.box = take(slots * 16);
     L.score = take(slots * 4);
     L.key = take(slots * 4);
@@ -80,7 +81,6 @@ static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_d
     L.val_b = take(slots * 4);
     L.tile_count = take(batch * tpi * 4);
     L.tile_max = take(batch * tpi * 4);
-    L.hist = take(batch * kBuckets * 4);
     L.kept_slot = take(batch * max_det * 4);
     L.total = o;
     return L;
@@ -327,8 +327,9 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
 }
 
 // the per-image score histogram must be zero before K1 accumulates into it
-static int zero_hist(const Pipeline &P, int batch, cudaStream_t s) {
-    CUDA_TRY(cudaMemsetAsync(P.st.hist, 0, static_cast<size_t>(batch) * kBuckets * sizeof(int32_t), s));
+static int zero_hist(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, cudaStream_t s) {
+    if (!prm->workspace_clean)
+        CUDA_TRY(cudaMemsetAsync(P.st.hist, 0, static_cast<size_t>(batch) * kBuckets * sizeof(int32_t), s));
     stage_mark(1, s);
     return SARPOST_OK;
 }
@@ -375,6 +376,19 @@ int64_t sarpost_merge_workspace_bytes(int32_t n_frames, int32_t tiles_per_frame,
     return make_layout(n_frames, static_cast<int64_t>(tiles_per_frame) * dets_per_tile, tiles_per_frame, max_det, true).total;
 }
 
+int64_t sarpost_workspace_clean_bytes(int32_t batch) {
+    if (batch < 1) return fail(SARPOST_EINVAL, "batch %d < 1", batch);
+    return static_cast<int64_t>(batch) * kBuckets * 4;
+}
+
+int32_t sarpost_workspace_prepare(void *workspace, int64_t workspace_bytes, int32_t batch, void *stream) {
+    if (!workspace || batch < 1) return fail(SARPOST_EINVAL, "bad workspace_prepare arguments");
+    const int64_t n = static_cast<int64_t>(batch) * kBuckets * 4;
+    if (workspace_bytes < n) return fail(SARPOST_EWORKSPACE, "workspace too small: %lld < %lld bytes", (long long)workspace_bytes, (long long)n);
+    CUDA_TRY(cudaMemsetAsync(workspace, 0, static_cast<size_t>(n), static_cast<cudaStream_t>(stream)));
+    return SARPOST_OK;
+}
+
 int32_t sarpost_decode(const sarpost_head_t *head, float *y, void *stream) {
     g_launches = 0;
     HeadGeom g;
@@ -410,7 +424,7 @@ int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t chan
     if (int rc = bind_workspace(workspace, workspace_bytes, batch, tpi * region, tpi, region, params->max_det, false, &P)) return rc;
 
     stage_mark(0, s);
-    if (int rc = zero_hist(P, batch, s)) return rc;
+    if (int rc = zero_hist(P, batch, params, s)) return rc;
     K1DecodedParams kp;
     kp.pred = prediction;
     kp.channels = channels;
@@ -451,7 +465,7 @@ int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *pa
     if (int rc = bind_workspace(workspace, workspace_bytes, g.batch, g.tpi * region, g.tpi, region, params->max_det, false, &P)) return rc;
 
     stage_mark(0, s);
-    if (int rc = zero_hist(P, g.batch, s)) return rc;
+    if (int rc = zero_hist(P, g.batch, params, s)) return rc;
     if (int rc = launch_k1_fused(g, f, P.st, s)) return rc;
     stage_mark(2, s);
 
@@ -486,7 +500,7 @@ int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const 
     if (int rc = bind_workspace(workspace, workspace_bytes, n_frames, cap, tiles_per_frame, dets_per_tile, params->max_det, true, &P)) return rc;
 
     stage_mark(0, s);
-    if (int rc = zero_hist(P, n_frames, s)) return rc;
+    if (int rc = zero_hist(P, n_frames, params, s)) return rc;
     K1MergeParams kp;
     kp.dets = dets;
     kp.det_counts = det_counts;

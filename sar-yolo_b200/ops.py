@@ -71,6 +71,7 @@ def _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det,
     p.max_det = int(max_det)
     p.max_nms = int(max_nms)
     p.max_wh = float(max_wh)
+    p.workspace_clean = 1  # every device entry point below uses a persistent, prepared _Workspace
     keep = None
     if classes is not None:
         cl = [int(c) for c in (classes.tolist() if isinstance(classes, torch.Tensor) else classes)]
@@ -126,8 +127,37 @@ def _split(out: torch.Tensor, counts: torch.Tensor) -> List[torch.Tensor]:
     return [out[b, : n[b]] for b in range(out.shape[0])]
 
 
-def _workspace(nbytes: int, device) -> torch.Tensor:
-    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+_WS_CACHE = {}  # (device index, stream, nbytes, batch) -> persistent workspace whose histogram head is clean
+_WS_CACHE_MAX = 8
+
+
+class _Workspace:
+    """Workspace for one call.  Persistent per (device, stream, size, batch): the library leaves the score
+    histogram at the head of the buffer zeroed after every successful call, so only the first use pays a
+    memset (`sarpost_workspace_prepare`).  Stream order makes reuse on the same stream safe; a failed call
+    drops the entry."""
+
+    def __init__(self, nbytes: int, batch: int, device: torch.device):
+        self.key = (device.index, _stream_ptr(device), int(nbytes), int(batch))
+        self.nbytes = int(nbytes)
+        ent = _WS_CACHE.pop(self.key, None)
+        if ent is None:
+            ent = torch.empty(self.nbytes, dtype=torch.uint8, device=device)
+            _lib.check(lib.sarpost_workspace_prepare(ent.data_ptr(), self.nbytes, int(batch), _stream_ptr(device)))
+        self.buf = ent
+
+    def ptr(self) -> int:
+        return self.buf.data_ptr()
+
+    def release(self) -> None:
+        """Call after a successful launch: the buffer goes back to the cache (most recently used last)."""
+        _WS_CACHE[self.key] = self.buf
+        while len(_WS_CACHE) > _WS_CACHE_MAX:
+            _WS_CACHE.pop(next(iter(_WS_CACHE)))
+
+
+def clear_workspace_cache() -> None:
+    _WS_CACHE.clear()
 
 
 def non_max_suppression(
@@ -192,14 +222,14 @@ def non_max_suppression(
         ws_bytes = lib.sarpost_workspace_bytes(bs, na, nc, int(bool(multi_label)), int(max_det))
         if ws_bytes < 0:
             _lib.check(int(ws_bytes))
-        ws = _workspace(ws_bytes, dev)
+        ws = _Workspace(ws_bytes, bs, dev)
         out = torch.empty((bs, int(max_det), 6 + nm), dtype=torch.float32, device=dev)
         counts = torch.empty((bs,), dtype=torch.int32, device=dev)
         kidx = torch.empty((bs, int(max_det)), dtype=torch.int32, device=dev) if return_index else None
         _lib.check(lib.sarpost_nms_decoded(pred.data_ptr(), bs, ch, na, nc, C.byref(params), out.data_ptr(),
                                            counts.data_ptr(), kidx.data_ptr() if return_index else None,
-                                           ws.data_ptr(), ws_bytes, _stream_ptr(dev)))
-        ws.record_stream(torch.cuda.current_stream(dev))
+                                           ws.ptr(), ws_bytes, _stream_ptr(dev)))
+        ws.release()
     if in_dtype != torch.float32:
         out = out.to(in_dtype)
     rows = _split(out, counts)
@@ -244,14 +274,14 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
         ws_bytes = lib.sarpost_workspace_bytes(bs, anchors, spec.nc, int(bool(multi_label)), int(max_det))
         if ws_bytes < 0:
             _lib.check(int(ws_bytes))
-        ws = _workspace(ws_bytes, dev)
+        ws = _Workspace(ws_bytes, bs, dev)
         out = torch.empty((bs, int(max_det), 6 + nm), dtype=torch.float32, device=dev)
         counts = torch.empty((bs,), dtype=torch.int32, device=dev)
         want_idx = return_index
         kidx = torch.empty((bs, int(max_det)), dtype=torch.int32, device=dev) if want_idx else None
         _lib.check(lib.sarpost_fused(C.byref(head), C.byref(params), out.data_ptr(), counts.data_ptr(),
-                                     kidx.data_ptr() if want_idx else None, ws.data_ptr(), ws_bytes, _stream_ptr(dev)))
-        ws.record_stream(torch.cuda.current_stream(dev))
+                                     kidx.data_ptr() if want_idx else None, ws.ptr(), ws_bytes, _stream_ptr(dev)))
+        ws.release()
     if return_padded:
         return (out, counts, kidx) if want_idx else (out, counts)
     rows = _split(out, counts)
@@ -300,15 +330,15 @@ def merge_tiles(dets: torch.Tensor, det_counts: torch.Tensor, origins: torch.Ten
         ws_bytes = lib.sarpost_merge_workspace_bytes(nf, tiles_per_frame, d, int(max_det))
         if ws_bytes < 0:
             _lib.check(int(ws_bytes))
-        ws = _workspace(ws_bytes, dev)
+        ws = _Workspace(ws_bytes, nf, dev)
         out = torch.empty((nf, int(max_det), row_len), dtype=torch.float32, device=dev)
         counts = torch.empty((nf,), dtype=torch.int32, device=dev)
         kidx = torch.empty((nf, int(max_det)), dtype=torch.int32, device=dev) if return_index else None
         _lib.check(lib.sarpost_merge_tiles(dets.data_ptr(), det_counts.data_ptr(), origins.data_ptr(), nf,
                                            tiles_per_frame, d, row_len, C.byref(params), out.data_ptr(),
                                            counts.data_ptr(), kidx.data_ptr() if return_index else None,
-                                           ws.data_ptr(), ws_bytes, _stream_ptr(dev)))
-        ws.record_stream(torch.cuda.current_stream(dev))
+                                           ws.ptr(), ws_bytes, _stream_ptr(dev)))
+        ws.release()
     if return_padded:
         return (out, counts, kidx) if return_index else (out, counts)
     rows = _split(out, counts)
