@@ -26,60 +26,89 @@
 namespace sarpost {
 
 // Visit every candidate of the image whose score bit pattern lies in [lo_bits, hi_bits]: fn(slot, bits).
-// The scan is instruction-bound (one CTA streams every candidate score of its image out of L2), so the
-// common case — no member among a lane's four scores — costs one 128-bit load, four range tests and a
-// single branch.  Each warp owns a contiguous run of tiles; the tile counts of the run are fetched with
-// one coalesced load and, when the tile region is exactly kTileA slots, kUnroll tiles are in flight.
-// Tiles whose best score (tile_max, written by K1) is below the range are skipped without touching them.
+// Block-wide (contains __syncthreads).  The scan is instruction-bound (one CTA streams candidate scores of
+// its image out of L2), so
+//   1. tiles whose best score (tile_max, written by K1) is below the range, or that are empty, are dropped
+//      up front: the surviving tile ids are compacted into `tile_list` (shared memory, kTileListCap entries
+//      per round);
+//   2. warps then walk that list with kUnroll tiles in flight; when the tile region is exactly kTileA slots a
+//      lane fetches its four scores with one 128-bit load, and the common case — no member among them —
+//      costs four range tests and a single branch.
+constexpr int kTileListCap = 2048;
+
 template <class Fn>
 __device__ __forceinline__ void for_each_candidate_in(const CandStore &st, const int32_t *tcount, const uint32_t *tmax,
-                                                      const float *score,
-                                                      uint32_t lo_bits, uint32_t hi_bits, const Fn &fn) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int tpw = (st.tpi + nwarps - 1) / nwarps;
-    const int t_begin = warp * tpw, t_end = min(st.tpi, t_begin + tpw);
+                                                      const float *score, uint32_t lo_bits, uint32_t hi_bits,
+                                                      uint32_t *tile_list /*[kTileListCap] smem*/, int *list_n /*smem*/,
+                                                      const Fn &fn) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const uint32_t span = hi_bits - lo_bits;  // in range  <=>  (bits - lo_bits) <= span  (unsigned)
-    if (st.region == kTileA) {
-        constexpr int kUnroll = 8;
-        for (int tb = t_begin; tb < t_end; tb += 32) {
-            // a tile whose best score is below the range has no member: treat it as empty
-            const int my_c = (tb + lane < t_end && tmax[tb + lane] >= lo_bits) ? tcount[tb + lane] : 0;
-            const int nt = min(32, t_end - tb);
-            for (int u0 = 0; u0 < nt; u0 += kUnroll) {
+    for (int t0 = 0; t0 < st.tpi; t0 += kTileListCap) {
+        __syncthreads();
+        if (tid == 0) *list_n = 0;
+        __syncthreads();
+        const int t1 = min(st.tpi, t0 + kTileListCap);
+        for (int tb = t0 + warp * 32; tb < t1; tb += nwarps * 32) {
+            const int t = tb + lane;
+            const int c = (t < t1 && tmax[t] >= lo_bits) ? tcount[t] : 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, c > 0);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(list_n, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (c > 0) tile_list[base + __popc(bal & lanemask_lt())] = static_cast<uint32_t>(t);
+            }
+        }
+        __syncthreads();
+        const int n_act = *list_n;
+        if (st.region == kTileA) {
+            constexpr int kUnroll = 8;
+            for (int e0 = warp * kUnroll; e0 < n_act; e0 += nwarps * kUnroll) {
                 uint4 v[kUnroll];
                 int c[kUnroll];
+                uint32_t tt[kUnroll];
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    c[u] = __shfl_sync(0xffffffffu, my_c, (u0 + u) & 31) - lane * 4;  // valid entries of this lane
-                    if (u0 + u >= nt) c[u] = 0;
+                    const bool on = e0 + u < n_act;
+                    tt[u] = on ? tile_list[e0 + u] : 0u;
+                    c[u] = on ? tcount[tt[u]] - lane * 4 : 0;  // valid entries of this lane
                     v[u] = make_uint4(0u, 0u, 0u, 0u);
-                    if (c[u] > 0)
-                        v[u] = *reinterpret_cast<const uint4 *>(score + static_cast<size_t>(tb + u0 + u) * kTileA + lane * 4);
+                    if (c[u] > 0) v[u] = *reinterpret_cast<const uint4 *>(score + static_cast<size_t>(tt[u]) * kTileA + lane * 4);
                 }
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    const bool t0 = (v[u].x - lo_bits) <= span && c[u] > 0, t1 = (v[u].y - lo_bits) <= span && c[u] > 1;
-                    const bool t2 = (v[u].z - lo_bits) <= span && c[u] > 2, t3 = (v[u].w - lo_bits) <= span && c[u] > 3;
-                    if (t0 | t1 | t2 | t3) {
-                        const uint32_t slot = static_cast<uint32_t>(tb + u0 + u) * kTileA + lane * 4;
-                        if (t0) fn(slot, v[u].x);
-                        if (t1) fn(slot + 1, v[u].y);
-                        if (t2) fn(slot + 2, v[u].z);
-                        if (t3) fn(slot + 3, v[u].w);
+                    const bool h0 = (v[u].x - lo_bits) <= span && c[u] > 0, h1 = (v[u].y - lo_bits) <= span && c[u] > 1;
+                    const bool h2 = (v[u].z - lo_bits) <= span && c[u] > 2, h3 = (v[u].w - lo_bits) <= span && c[u] > 3;
+                    if (h0 | h1 | h2 | h3) {
+                        const uint32_t slot = tt[u] * kTileA + lane * 4;
+                        if (h0) fn(slot, v[u].x);
+                        if (h1) fn(slot + 1, v[u].y);
+                        if (h2) fn(slot + 2, v[u].z);
+                        if (h3) fn(slot + 3, v[u].w);
+                    }
+                }
+            }
+        } else {
+            for (int e = warp; e < n_act; e += nwarps) {
+                const uint32_t t = tile_list[e];
+                const int c = tcount[t];
+                for (int i0 = 0; i0 < c; i0 += 128) {
+                    uint32_t bits[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * 32 + lane;
+                        bits[u] = i < c ? __float_as_uint(score[static_cast<size_t>(t) * st.region + i]) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * 32 + lane;
+                        if (i < c && (bits[u] - lo_bits) <= span) fn(t * static_cast<uint32_t>(st.region) + i, bits[u]);
                     }
                 }
             }
         }
-    } else {
-        for (int t = t_begin; t < t_end; ++t) {
-            const int c = tmax[t] >= lo_bits ? tcount[t] : 0;
-            for (int i = lane; i < c; i += 32) {
-                const uint32_t slot = static_cast<uint32_t>(t) * st.region + i;
-                const uint32_t bits = __float_as_uint(score[slot]);
-                if ((bits - lo_bits) <= span) fn(slot, bits);
-            }
-        }
     }
+    __syncthreads();
 }
 
 }  // namespace sarpost

@@ -255,6 +255,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #define SKEY (reinterpret_cast<unsigned long long *>(s_uni))
 #define A_BOX (reinterpret_cast<float4 *>(s_uni + kSortCap * 8))
 #define C_BOX (reinterpret_cast<float4 *>(s_uni + kSortCap * 8 + kSub * 16))
+#define TILE_LIST (reinterpret_cast<uint32_t *>(s_uni + kSortCap * 8))  /* aliases A_BOX|C_BOX, idle while collecting */
+    static_assert(kTileListCap * 4 <= 2 * kSub * 16, "tile list must fit the a_box|c_box region");
 
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     auto collect_smem = [&](int b_lo, int b_hi) {
         const uint32_t lo_bits = bucket_floor_bits(b_lo);
         const uint32_t hi_bits = b_hi >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_hi + 1) - 1u;
-        for_each_candidate_in(p.st, tcount, tmaxv, score, lo_bits, hi_bits, [&](uint32_t slot, uint32_t bits) {
+        for_each_candidate_in(p.st, tcount, tmaxv, score, lo_bits, hi_bits, TILE_LIST, &s_misc[20], [&](uint32_t slot, uint32_t bits) {
             const int at = atomicAdd(&s_misc[18], 1);  // members are rare (a few hundred per image)
             if (at < kSortCap) SKEY[at] = (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - slot);
         });
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             if (tid == 0) s_misc[18] = 0;
             __syncthreads();
             for_each_candidate_in(p.st, tcount, tmaxv, score, bucket_floor_bits(b_one),
-                                  b_one >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_one + 1) - 1u,
+                                  b_one >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_one + 1) - 1u, TILE_LIST, &s_misc[20],
                                   [&](uint32_t slot, uint32_t bits) {
                                       const int at = atomicAdd(&s_misc[18], 1);
                                       ka[at] = bits;
@@ -572,6 +574,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #undef SKEY
 #undef A_BOX
 #undef C_BOX
+#undef TILE_LIST
 }
 
 // ---------------------------------------------------------------------------------------------
