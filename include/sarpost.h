@@ -67,6 +67,10 @@ typedef struct sarpost_nms_params {
     float max_wh;          /* ops.py:289,295 class offset = cls * max_wh */
     const int32_t *classes;/* HOST pointer to the `classes` filter (ops.py:278-279) or NULL */
     int32_t n_classes;
+    const float *rescale;  /* DEVICE pointer (B, 5) = pad_x, pad_y, gain, w0, h0 per image, or NULL.  When set the gather
+                              kernel applies ops.scale_boxes + clip_boxes (utils/ops.py:92-127, :319-338) to the output
+                              boxes: x = clamp((x - pad_x) / gain, 0, w0), y likewise with pad_y, h0 — the per-image
+                              loop of models/yolo/jde/predict.py:49 (ignored by sarpost_merge_tiles). */
     int32_t workspace_clean;/* 0: the call zeroes the score-histogram head of the workspace itself (one memset node).
                               1: the caller guarantees the first sarpost_workspace_clean_bytes(batch) bytes are zero —
                               true after sarpost_workspace_prepare and after every successful call that used the

@@ -194,3 +194,20 @@ def non_max_suppression_ref(prediction: torch.Tensor, conf_thres: float = 0.25, 
         output[xi] = x[i]  # ops.py:311
         index[xi] = src[i]
     return (output, index) if return_index else output
+
+
+def scale_boxes_ref(img1_shape, boxes: torch.Tensor, img0_shape) -> torch.Tensor:
+    """utils/ops.py:92-127 (ratio_pad=None, padding=True, xyxy) + clip_boxes :319-338, on a copy."""
+    boxes = boxes.clone()
+    gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+    pad = (round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1), round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1))
+    boxes[..., 0] -= pad[0]
+    boxes[..., 1] -= pad[1]
+    boxes[..., 2] -= pad[0]
+    boxes[..., 3] -= pad[1]
+    boxes[..., :4] /= gain
+    boxes[..., 0] = boxes[..., 0].clamp(0, img0_shape[1])
+    boxes[..., 1] = boxes[..., 1].clamp(0, img0_shape[0])
+    boxes[..., 2] = boxes[..., 2].clamp(0, img0_shape[1])
+    boxes[..., 3] = boxes[..., 3].clamp(0, img0_shape[0])
+    return boxes

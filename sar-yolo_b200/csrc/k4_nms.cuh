@@ -390,11 +390,23 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                     const bool v0 = j0 > r && j0 < m, v1 = (w + 1 < words) && j1 < m;
                     bool bd0 = false, bd1 = false;
                     const int jc0 = v0 ? j0 : r, jc1 = v1 ? j1 : r;
-                    bool g0 = iou_gt_approx(rb, ra, C_BOX[jc0], s_c_area[jc0], p.thr, band, bd0);
-                    bool g1 = iou_gt_approx(rb, ra, C_BOX[jc1], s_c_area[jc1], p.thr, band, bd1);
+                    const float4 cb0 = C_BOX[jc0], cb1 = C_BOX[jc1];
+                    // disjoint boxes have inter = 0 -> IoU 0 (or NaN), never > thr >= 0: skip the arithmetic when no
+                    // lane of the warp sees an overlap (the usual case for boxes spread over the image)
+                    const bool ov0 = v0 && fminf(rb.z, cb0.z) > fmaxf(rb.x, cb0.x) && fminf(rb.w, cb0.w) > fmaxf(rb.y, cb0.y);
+                    const bool ov1 = v1 && fminf(rb.z, cb1.z) > fmaxf(rb.x, cb1.x) && fminf(rb.w, cb1.w) > fmaxf(rb.y, cb1.y);
+                    if (!__any_sync(0xffffffffu, ov0 || ov1)) {
+                        if (lane == 0) {
+                            s_mask[r * kSubWords + w] = 0u;
+                            if (w + 1 < words) s_mask[r * kSubWords + w + 1] = 0u;
+                        }
+                        continue;
+                    }
+                    bool g0 = iou_gt_approx(rb, ra, cb0, s_c_area[jc0], p.thr, band, bd0);
+                    bool g1 = iou_gt_approx(rb, ra, cb1, s_c_area[jc1], p.thr, band, bd1);
                     if (__any_sync(0xffffffffu, (bd0 && v0) || (bd1 && v1))) {  // rare: quotient within a few ulp of thr
-                        if (bd0) g0 = iou_gt(rb, ra, C_BOX[jc0], s_c_area[jc0], p.thr);
-                        if (bd1) g1 = iou_gt(rb, ra, C_BOX[jc1], s_c_area[jc1], p.thr);
+                        if (bd0) g0 = iou_gt(rb, ra, cb0, s_c_area[jc0], p.thr);
+                        if (bd1) g1 = iou_gt(rb, ra, cb1, s_c_area[jc1], p.thr);
                     }
                     const uint32_t bits0 = __ballot_sync(0xffffffffu, g0 && v0);
                     const uint32_t bits1 = __ballot_sync(0xffffffffu, g1 && v1);
@@ -425,19 +437,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                         const uint32_t live = ~rem & (nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u));
                         const int r = (g << 5) + lane;
                         const uint32_t diag = lane < nvalid ? s_mask[r * kSubWords + g] : 0u;
-                        uint32_t keptm;
-                        if (!__any_sync(0xffffffffu, ((live >> lane) & 1u) && (diag & live))) {
-                            keptm = live;  // no two live candidates of this group overlap: all are kept at once
-                        } else {
-                            keptm = 0u;
-                            uint32_t l = live;
-                            while (l) {
-                                const int j = __ffs(static_cast<int>(l)) - 1;
-                                keptm |= 1u << j;
-                                const uint32_t dj = __shfl_sync(0xffffffffu, diag, j);
-                                l &= ~dj;
-                                l &= l - 1u;
-                            }
+                        // rows that overlap a later live row of the group are the only ones whose fate matters to
+                        // others: walk just those in order (usually none or a handful of the 32)
+                        uint32_t pending = __ballot_sync(0xffffffffu, ((live >> lane) & 1u) && (diag & live));
+                        uint32_t keptm = live;
+                        while (pending) {
+                            const int j = __ffs(static_cast<int>(pending)) - 1;
+                            pending &= pending - 1u;
+                            const uint32_t dj = __shfl_sync(0xffffffffu, diag, j);
+                            if ((keptm >> j) & 1u) keptm &= ~dj;  // j is still alive: it suppresses its overlaps
                         }
                         int c = __popc(keptm);
                         if (kl + c > p.max_det) {  // keep only the first (max_det - kl) of them
@@ -488,7 +496,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             const int target = pos == 0 ? min(kSortCap / 2, max(256, 2 * p.max_det)) : (kSortCap * 3) / 4;
             const int base = s_bstart[d];
             int lo = d + 1, hi = kBuckets;
-            if (s_bstart[lo] - base <= target) {
+            if (n_all - pos <= kSortCap) {
+                lo = kBuckets;  // everything that is left fits shared memory: one chunk, no estimate needed
+            } else if (s_bstart[lo] - base <= target) {
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
                     if (s_bstart[mid] - base <= target) lo = mid; else hi = mid - 1;
@@ -589,8 +599,20 @@ struct GatherParams {
     const int32_t *counts;      // [B]
     float *out;                 // [B, max_det, 6+nm]
     int32_t *kept_index;        // [B*max_det] or nullptr
+    const float *rescale;       // [B,5] pad_x, pad_y, gain, w0, h0 or nullptr (ops.scale_boxes + clip_boxes)
     int32_t max_det;
 };
+
+// ops.scale_boxes (utils/ops.py:92-127, padding=True, xyxy) followed by clip_boxes (:319-338), in torch's fp32
+// operation order: subtract the pad, true division by the gain, clamp to the original image.
+__device__ __forceinline__ float4 rescale_box(float4 b, const float *rs) {
+    const float px = rs[0], py = rs[1], gain = rs[2], w0 = rs[3], h0 = rs[4];
+    b.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.x, px), gain), 0.0f), w0);
+    b.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.y, py), gain), 0.0f), h0);
+    b.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.z, px), gain), 0.0f), w0);
+    b.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.w, py), gain), 0.0f), h0);
+    return b;
+}
 
 constexpr int kGatherWarps = 8;
 
@@ -614,7 +636,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
     }
     const uint32_t anchor = key / static_cast<uint32_t>(p.ex.nc), cls = key - anchor * static_cast<uint32_t>(p.ex.nc);
     if (lane == 0) {
-        const float4 bx = p.st.box[seg + slot];
+        float4 bx = p.st.box[seg + slot];
+        if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
         o[0] = bx.x;
         o[1] = bx.y;
         o[2] = bx.z;

@@ -318,6 +318,7 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     gp.counts = counts;
     gp.out = out;
     gp.kept_index = kept_index;
+    gp.rescale = ex.mode == 2 ? nullptr : prm->rescale;
     gp.max_det = prm->max_det;
     k5_gather<<<dim3((prm->max_det + kGatherWarps - 1) / kGatherWarps, batch), kGatherWarps * 32, 0, s>>>(gp);
     ++g_launches;

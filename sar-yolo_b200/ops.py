@@ -62,8 +62,21 @@ def _stream_ptr(device: torch.device) -> int:
     return int(torch.cuda.current_stream(device).cuda_stream)
 
 
-def _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh):
+def scale_params(img1_shape, img0_shapes, device) -> torch.Tensor:
+    """Per-image `(pad_x, pad_y, gain, w0, h0)` of `ops.scale_boxes(img1_shape, boxes, img0_shape)` with
+    `ratio_pad=None, padding=True` (utils/ops.py:110-116) — the host part of that function, evaluated exactly
+    like the reference (Python floats, `round`); the arithmetic on the boxes runs in the gather kernel."""
+    rows = []
+    for s0 in img0_shapes:
+        gain = min(img1_shape[0] / s0[0], img1_shape[1] / s0[1])  # gain  = old / new
+        pad = (round((img1_shape[1] - s0[1] * gain) / 2 - 0.1), round((img1_shape[0] - s0[0] * gain) / 2 - 0.1))
+        rows.append([float(pad[0]), float(pad[1]), float(gain), float(s0[1]), float(s0[0])])
+    return torch.tensor(rows, dtype=torch.float32).to(device, non_blocking=True)
+
+
+def _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, rescale=None):
     p = NmsParams()
+    p.rescale = rescale.data_ptr() if rescale is not None else None
     p.conf_thres = float(conf_thres)
     p.iou_thres = float(iou_thres)
     p.agnostic = int(bool(agnostic))
@@ -255,12 +268,15 @@ def decode(levels: Sequence[torch.Tensor], spec: HeadSpec) -> torch.Tensor:
 
 def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres=0.25, iou_thres=0.45, classes=None,
                       agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=7680,
-                      return_index=False, return_padded=False, with_extras=True):
+                      return_index=False, return_padded=False, with_extras=True, scale_to=None):
     """decode + non_max_suppression in one pass (never materialises y; the extras channels are read only
     for the kept rows).  Result as `non_max_suppression`; `return_padded=True` returns the raw
     `(out (B, max_det, 6+nm), counts (B,) int32[, kept_index])` device tensors without any host sync.
     `with_extras=False` returns 6-column rows even for a JDE head (use `gather_extras` later for the rows that
-    survive a subsequent stage such as the cross-tile merge)."""
+    survive a subsequent stage such as the cross-tile merge).
+    `scale_to=(img1_shape, [img0_shape, ...])` additionally applies `ops.scale_boxes` + `clip_boxes` per image
+    (the loop of models/yolo/jde/predict.py:48-49) inside the gather kernel: `img1_shape` = (h, w) of the network
+    input, one (h, w[, c]) per original image."""
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     levels = _prep_levels(levels)
@@ -269,7 +285,13 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
     dev = levels[0].device
     anchors = sum(int(x.shape[2]) * int(x.shape[3]) for x in levels)
     bs = head.batch
-    params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+    rescale = None
+    if scale_to is not None:
+        img1_shape, img0_shapes = scale_to
+        if len(img0_shapes) != bs:
+            raise ValueError(f"sarpost: scale_to has {len(img0_shapes)} original shapes for a batch of {bs}")
+        rescale = scale_params(img1_shape, img0_shapes, dev)
+    params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, rescale)
     with torch.cuda.device(dev):
         ws_bytes = lib.sarpost_workspace_bytes(bs, anchors, spec.nc, int(bool(multi_label)), int(max_det))
         if ws_bytes < 0:

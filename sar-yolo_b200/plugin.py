@@ -74,7 +74,7 @@ def is_patched() -> bool:
     return bool(_SAVED)
 
 
-def fused_postprocess(preds, head_module, **nms_kwargs):
+def fused_postprocess(preds, head_module, img_shape=None, orig_shapes=None, **nms_kwargs):
     """For custom predictors/validators (`Model.predict(predictor=...)`, engine/model.py:505,552):
     `preds` is what the PyTorch model returns, `[y, x_levels]` (head.py:212, nn/autobackend.py:700-704);
     the raw per-level logits `preds[1]` go straight through the fused kernels and `y` is ignored."""
@@ -83,4 +83,6 @@ def fused_postprocess(preds, head_module, **nms_kwargs):
         raise NotImplementedError("sarpost: end2end heads are not on the accelerated path")
     spec = _ops.HeadSpec.from_module(head_module)
     nms_kwargs.pop("nc", None)
+    if img_shape is not None and orig_shapes is not None:  # fold predict.py:49 (scale_boxes + clip) into the gather
+        nms_kwargs["scale_to"] = (tuple(img_shape), [tuple(s) for s in orig_shapes])
     return _ops.postprocess_fused(levels, spec, **nms_kwargs)

@@ -343,3 +343,21 @@ def test_boxes_only_and_gather_extras(sarpost, cuda):
     anc = torch.cat(idx) // spec.nc
     ex = sarpost.gather_extras(levels, spec, img, anc)
     assert torch.equal(ex, torch.cat([f[:, 6:] for f in full]))
+
+
+def test_fused_scale_boxes_and_clip(sarpost, cuda):
+    """§8f row 1: ops.scale_boxes + clip_boxes folded into the gather kernel, bit-exact to the torch ops."""
+    strides = (8, 16, 32)
+    img1 = (384, 640)
+    shapes = sarpost.synth.level_shapes(img1, strides)
+    spec = sarpost.HeadSpec(nc=3, strides=strides)
+    levels = [x.to(cuda) for x in sarpost.synth.head_outputs(3, shapes, 3, 0, 0, seed=31)]
+    orig = [(1080, 1920, 3), (3000, 4000, 3), (480, 640, 3)]
+    kw = dict(conf_thres=0.25, iou_thres=0.7)
+    plain = sarpost.postprocess_fused(levels, spec, **kw)
+    scaled = sarpost.postprocess_fused(levels, spec, scale_to=(img1, orig), **kw)
+    for r0, r1, s0 in zip(plain, scaled, orig):
+        ref = r0.cpu().clone()
+        ref[:, :4] = R.scale_boxes_ref(img1, ref[:, :4], s0)
+        assert torch.equal(r1.cpu(), ref)
+        assert float(r1[:, 2].max()) <= s0[1] and float(r1[:, 3].max()) <= s0[0] and float(r1[:, :4].min()) >= 0

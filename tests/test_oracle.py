@@ -107,3 +107,14 @@ def test_empty_and_degenerate_inputs():
     y[0, 4, :3] = torch.tensor([0.9, 0.8, 0.7])
     out = R.non_max_suppression_ref(y, conf_thres=0.25, iou_thres=0.5)
     assert out[0].shape[0] == 3
+
+
+def test_scale_boxes_ref_matches_live_reference():
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ops, _, _ = ref_shim.load()
+    g = torch.Generator().manual_seed(3)
+    b = torch.rand(500, 4, generator=g) * 700 - 30
+    for img1, img0 in [((384, 640), (1080, 1920, 3)), ((640, 640), (3000, 4000, 3)), ((1280, 1280), (480, 640))]:
+        assert torch.equal(R.scale_boxes_ref(img1, b, img0), ops.scale_boxes(img1, b.clone(), img0))
