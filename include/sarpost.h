@@ -13,7 +13,7 @@
  *     available (per thread) from sarpost_last_error();
  *   - no function synchronises the device except the *_host entry points; all work is enqueued on
  *     the given stream; the library keeps no global mutable state (re-entrant, one workspace per call);
- *   - all tensors fp32, contiguous, row-major.
+ *   - tensors are contiguous, row-major, fp32 unless a dtype field says otherwise.
  */
 #ifndef SARPOST_H_
 #define SARPOST_H_
@@ -27,6 +27,9 @@ extern "C" {
 #define SARPOST_VERSION 100 /* 0.1.0 */
 #define SARPOST_MAX_LEVELS 8
 #define SARPOST_MAX_CLASSES 2048 /* upper bound for nc (class-filter bitmap lives in kernel params) */
+
+#define SARPOST_F32 0
+#define SARPOST_F16 1
 
 #define SARPOST_OK 0
 #define SARPOST_EINVAL (-1)    /* bad argument */
@@ -50,6 +53,9 @@ typedef struct sarpost_head {
     int32_t reg_max;         /* DFL bins per side; only 16 is supported (head.py:39) */
     int32_t n_extra_raw;     /* extras copied through unchanged (JDE embedding, head.py:247) */
     int32_t n_extra_sigmoid; /* extras passed through sigmoid (JDE state, head.py:247) */
+    int32_t dtype;           /* element type of the level tensors: SARPOST_F32 (0) or SARPOST_F16 (1, `half=True`
+                                pipelines: engine/validator.py:115-117).  fp16 logits are upcast exactly and all
+                                arithmetic stays fp32; sarpost_decode then writes y in the same type as the input */
     int32_t h[SARPOST_MAX_LEVELS];
     int32_t w[SARPOST_MAX_LEVELS];
     float stride[SARPOST_MAX_LEVELS]; /* Detect.stride (head.py:41) */
@@ -98,9 +104,9 @@ int32_t sarpost_workspace_prepare(void *workspace, int64_t workspace_bytes, int3
 /*
  * Replaces Detect._inference / JDE._inference (nn/modules/head.py:100-131, :214-249) including
  * DFL (nn/modules/block.py:77-80), make_anchors and dist2bbox (utils/tal.py:366-390).
- * y: device (B, 4 + nc + n_extra_raw + n_extra_sigmoid, A) fp32, A = sum_l H_l*W_l.
+ * y: device (B, 4 + nc + n_extra_raw + n_extra_sigmoid, A), A = sum_l H_l*W_l, same element type as head->dtype.
  */
-int32_t sarpost_decode(const sarpost_head_t *head, float *y, void *stream);
+int32_t sarpost_decode(const sarpost_head_t *head, void *y, void *stream);
 
 /*
  * Replaces ops.non_max_suppression (utils/ops.py:167-316, non-rotated branch) on an already

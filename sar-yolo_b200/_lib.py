@@ -21,7 +21,7 @@ class Head(C.Structure):
     """sarpost_head_t"""
     _fields_ = [
         ("nl", C.c_int32), ("batch", C.c_int32), ("no", C.c_int32), ("nc", C.c_int32), ("reg_max", C.c_int32),
-        ("n_extra_raw", C.c_int32), ("n_extra_sigmoid", C.c_int32),
+        ("n_extra_raw", C.c_int32), ("n_extra_sigmoid", C.c_int32), ("dtype", C.c_int32),
         ("h", C.c_int32 * MAX_LEVELS), ("w", C.c_int32 * MAX_LEVELS), ("stride", C.c_float * MAX_LEVELS),
         ("data", C.c_void_p * MAX_LEVELS),
     ]

@@ -120,6 +120,7 @@ int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, co
     if (int rc = fill_geom(head, &g, &anchors)) return rc;
     if (int rc = check_params(params, g.nc)) return rc;
     if (!out || !counts) return fail(SARPOST_EINVAL, "NULL output pointer");
+    if (g.is_half) return fail(SARPOST_EUNSUPPORTED, "sarpost_fused_host takes fp32 host tensors");
     CUDA_TRY(cudaSetDevice(c->device));
     const int B = g.batch, nch = 4 * kRegMax + g.nc, nm = g.n_extra_raw + g.n_extra_sig, max_det = params->max_det;
     c->last_h2d = c->last_d2h = 0;

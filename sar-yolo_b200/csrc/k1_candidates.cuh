@@ -8,6 +8,8 @@
 //   ops.py:268-279    best-class (first max) or multi-label expansion, `classes` filter
 // Output = tile-segmented candidate store (common.cuh).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace sarpost {
@@ -20,8 +22,14 @@ struct HeadGeom {
     int32_t lvl_w[kMaxLevels];
     int32_t lvl_aoff[kMaxLevels + 1];      // first global anchor index of the level; [nl] = A
     float lvl_stride[kMaxLevels];
-    const float *lvl_ptr[kMaxLevels];
+    const void *lvl_ptr[kMaxLevels];  // elements of type float or __half (kernel template parameter)
+    int32_t is_half;
 };
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+__device__ __forceinline__ void from_f32(float v, float *o) { *o = v; }
+__device__ __forceinline__ void from_f32(float v, __half *o) { *o = __float2half_rn(v); }
 
 struct CandFilter {
     float conf;            // (float)conf_thres
@@ -194,13 +202,14 @@ struct K1TmaParams {
 
 constexpr int kMaxStages = 8;
 
+template <typename T>
 __global__ void __launch_bounds__(kTileA, 3) k1_fused_tma(const __grid_constant__ K1TmaParams p) {
     extern __shared__ unsigned char dyn_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ int scratch[8];
     const int tid = threadIdx.x;
     const int nch = 4 * kRegMax + p.g.nc;
-    const uint32_t stage_bytes = static_cast<uint32_t>(nch) * kTileA * sizeof(float);
+    const uint32_t stage_bytes = static_cast<uint32_t>(nch) * kTileA * sizeof(T);
     unsigned char *dyn = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn_smem_raw) + 127) & ~uintptr_t(127));
 
     if (tid == 0) {
@@ -233,12 +242,12 @@ __global__ void __launch_bounds__(kTileA, 3) k1_fused_tma(const __grid_constant_
         const bool valid = pos < p.g.lvl_hw[l];
         const int s = k % p.stages;
         mbar_wait(&full_bar[s], static_cast<uint32_t>((k / p.stages) & 1));
-        const float *buf = reinterpret_cast<const float *>(dyn + static_cast<size_t>(s) * stage_bytes) + tid;
-        auto acc = [&](int c) { return buf[c * kTileA]; };
+        const T *buf = reinterpret_cast<const T *>(dyn + static_cast<size_t>(s) * stage_bytes) + tid;
+        auto acc = [&](int c) { return to_f32(buf[c * kTileA]); };
         const int w = p.g.lvl_w[l];
         const int yy = pos / w, xx = pos - yy * w;
         const float4 xyxy = xywh2xyxy_rn(decode_xywh(acc, xx, yy, p.g.lvl_stride[l]));
-        auto score = [&](int j) { return sigmoid_rn(buf[(4 * kRegMax + j) * kTileA]); };
+        auto score = [&](int j) { return sigmoid_rn(to_f32(buf[(4 * kRegMax + j) * kTileA])); };
         emit_candidates(valid, xyxy, static_cast<uint32_t>(p.g.lvl_aoff[l] + pos), p.g.nc, p.f, score, p.st, b, r, scratch);
         // emit_candidates ended with __syncthreads(): stage s is free again
         if (tid == 0 && k + p.stages < n_my) issue(k + p.stages);
@@ -256,6 +265,7 @@ struct K1LdgParams {
     CandStore st;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(kTileA) k1_fused_ldg(const __grid_constant__ K1LdgParams p) {
     __shared__ int scratch[8];
     const int r = blockIdx.x, b = blockIdx.y;
@@ -264,8 +274,8 @@ __global__ void __launch_bounds__(kTileA) k1_fused_ldg(const __grid_constant__ K
     const int pos = (r - p.g.lvl_tile_begin[l]) * kTileA + threadIdx.x;
     const bool valid = pos < hw;
     const int pc = valid ? pos : hw - 1;
-    const float *base = p.g.lvl_ptr[l] + static_cast<int64_t>(b) * p.g.no * hw + pc;
-    auto acc = [&](int c) { return __ldg(base + static_cast<int64_t>(c) * hw); };
+    const T *base = static_cast<const T *>(p.g.lvl_ptr[l]) + static_cast<int64_t>(b) * p.g.no * hw + pc;
+    auto acc = [&](int c) { return to_f32(__ldg(base + static_cast<int64_t>(c) * hw)); };
     const int w = p.g.lvl_w[l];
     const int yy = pc / w, xx = pc - yy * w;
     const float4 xyxy = xywh2xyxy_rn(decode_xywh(acc, xx, yy, p.g.lvl_stride[l]));
@@ -339,31 +349,32 @@ __global__ void __launch_bounds__(128) k1_merge(const __grid_constant__ K1MergeP
 // ---------------------------------------------------------------------------------------------
 struct DecodeYParams {
     HeadGeom g;
-    float *y;
+    void *y;  // same element type as the levels
     int64_t anchors;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(kTileA) k_decode_y(const __grid_constant__ DecodeYParams p) {
     const int r = blockIdx.x, b = blockIdx.y;
     const int l = tile_level(p.g, r);
     const int hw = p.g.lvl_hw[l];
     const int pos = (r - p.g.lvl_tile_begin[l]) * kTileA + threadIdx.x;
     if (pos >= hw) return;
-    const float *base = p.g.lvl_ptr[l] + static_cast<int64_t>(b) * p.g.no * hw + pos;
-    auto acc = [&](int c) { return __ldg(base + static_cast<int64_t>(c) * hw); };
+    const T *base = static_cast<const T *>(p.g.lvl_ptr[l]) + static_cast<int64_t>(b) * p.g.no * hw + pos;
+    auto acc = [&](int c) { return to_f32(__ldg(base + static_cast<int64_t>(c) * hw)); };
     const int w = p.g.lvl_w[l];
     const int yy = pos / w, xx = pos - yy * w;
     const float4 o = decode_xywh(acc, xx, yy, p.g.lvl_stride[l]);
     const int cout = 4 + p.g.nc + p.g.n_extra_raw + p.g.n_extra_sig;
-    float *yo = p.y + static_cast<int64_t>(b) * cout * p.anchors + p.g.lvl_aoff[l] + pos;
-    yo[0] = o.x;
-    yo[p.anchors] = o.y;
-    yo[2 * p.anchors] = o.z;
-    yo[3 * p.anchors] = o.w;
+    T *yo = static_cast<T *>(p.y) + static_cast<int64_t>(b) * cout * p.anchors + p.g.lvl_aoff[l] + pos;
+    from_f32(o.x, yo);
+    from_f32(o.y, yo + p.anchors);
+    from_f32(o.z, yo + 2 * p.anchors);
+    from_f32(o.w, yo + 3 * p.anchors);
     int ci = 4 * kRegMax, co = 4;
-    for (int j = 0; j < p.g.nc; ++j, ++ci, ++co) yo[co * p.anchors] = sigmoid_rn(acc(ci));
-    for (int j = 0; j < p.g.n_extra_raw; ++j, ++ci, ++co) yo[co * p.anchors] = acc(ci);
-    for (int j = 0; j < p.g.n_extra_sig; ++j, ++ci, ++co) yo[co * p.anchors] = sigmoid_rn(acc(ci));
+    for (int j = 0; j < p.g.nc; ++j, ++ci, ++co) from_f32(sigmoid_rn(acc(ci)), yo + co * p.anchors);
+    for (int j = 0; j < p.g.n_extra_raw; ++j, ++ci, ++co) yo[co * p.anchors] = __ldg(base + static_cast<int64_t>(ci) * hw);
+    for (int j = 0; j < p.g.n_extra_sig; ++j, ++ci, ++co) from_f32(sigmoid_rn(acc(ci)), yo + co * p.anchors);
 }
 
 }  // namespace sarpost

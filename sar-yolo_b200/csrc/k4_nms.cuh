@@ -18,6 +18,8 @@
 //   sweep     one warp resolves the sub-chunk on the bitmask, 32 candidates per step when no two live
 //             candidates of the group overlap, else one step per KEPT box; appends to the kept list.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "k2_select_sort.cuh"
 
@@ -55,24 +57,32 @@ struct ExtrasSrc {
     int32_t nl, no, n_extra_raw;
     int32_t lvl_aoff[kMaxLevels + 1];
     int32_t lvl_hw[kMaxLevels];
-    const float *lvl_ptr[kMaxLevels];
+    const void *lvl_ptr[kMaxLevels];
+    int32_t is_half;            // element type of the level tensors (mode 1)
     // mode 2
     const float *dets;
     int32_t dets_per_tile, row_len;
 };
 
-// address of extras channel 0 of (image b, anchor) and the element stride between channels
-__device__ __forceinline__ const float *extras_base(const ExtrasSrc &e, int b, uint32_t anchor, int64_t *stride) {
+// element index (from the start of its tensor) of extras channel 0 of (image b, anchor), the element stride
+// between channels, and the tensor base pointer
+__device__ __forceinline__ int64_t extras_base(const ExtrasSrc &e, int b, uint32_t anchor, int64_t *stride, const void **base) {
     if (e.mode == 0) {
         *stride = e.anchors;
-        return e.pred + (static_cast<int64_t>(b) * e.channels + 4 + e.nc) * e.anchors + anchor;
+        *base = e.pred;
+        return (static_cast<int64_t>(b) * e.channels + 4 + e.nc) * e.anchors + anchor;
     }
     int l = 0;
 #pragma unroll
     for (int i = 1; i < kMaxLevels; ++i) l += (i < e.nl && anchor >= static_cast<uint32_t>(e.lvl_aoff[i])) ? 1 : 0;
     const int hw = e.lvl_hw[l];
     *stride = hw;
-    return e.lvl_ptr[l] + (static_cast<int64_t>(b) * e.no + 4 * kRegMax + e.nc) * hw + (anchor - e.lvl_aoff[l]);
+    *base = e.lvl_ptr[l];
+    return (static_cast<int64_t>(b) * e.no + 4 * kRegMax + e.nc) * hw + (anchor - e.lvl_aoff[l]);
+}
+
+__device__ __forceinline__ float load_elem(const void *base, int64_t idx, bool is_half) {
+    return is_half ? __half2float(__ldg(static_cast<const __half *>(base) + idx)) : __ldg(static_cast<const float *>(base) + idx);
 }
 
 struct NmsParams {
@@ -648,10 +658,12 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
     }
     if (p.ex.nm > 0) {
         int64_t stride;
-        const float *src = extras_base(p.ex, b, anchor, &stride);
+        const void *base;
+        const int64_t at = extras_base(p.ex, b, anchor, &stride, &base);
+        const bool hf = p.ex.mode == 1 && p.ex.is_half;
         const int n_raw = p.ex.mode == 0 ? p.ex.nm : p.ex.n_extra_raw;  // a decoded prediction is copied verbatim
         for (int c = lane; c < p.ex.nm; c += 32) {
-            const float v = __ldg(src + c * stride);
+            const float v = load_elem(base, at + c * stride, hf);
             o[6 + c] = c < n_raw ? v : sigmoid_rn(v);
         }
     }
@@ -666,7 +678,8 @@ struct GatherExtrasParams {
     int32_t nl, no, nc, batch, n_extra_raw, nm;
     int32_t lvl_aoff[kMaxLevels + 1];
     int32_t lvl_hw[kMaxLevels];
-    const float *lvl_ptr[kMaxLevels];
+    const void *lvl_ptr[kMaxLevels];
+    int32_t is_half;
 };
 
 __global__ void __launch_bounds__(kGatherWarps * 32) k_gather_extras(const __grid_constant__ GatherExtrasParams p) {
@@ -682,9 +695,9 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k_gather_extras(const __gri
 #pragma unroll
     for (int i = 1; i < kMaxLevels; ++i) l += (i < p.nl && a >= p.lvl_aoff[i]) ? 1 : 0;
     const int hw = p.lvl_hw[l];
-    const float *src = p.lvl_ptr[l] + (static_cast<int64_t>(b) * p.no + 4 * kRegMax + p.nc) * hw + (a - p.lvl_aoff[l]);
+    const int64_t at = (static_cast<int64_t>(b) * p.no + 4 * kRegMax + p.nc) * hw + (a - p.lvl_aoff[l]);
     for (int c = lane; c < p.nm; c += 32) {
-        const float v = __ldg(src + static_cast<int64_t>(c) * hw);
+        const float v = load_elem(p.lvl_ptr[l], at + static_cast<int64_t>(c) * hw, p.is_half != 0);
         o[c] = c < p.n_extra_raw ? v : sigmoid_rn(v);
     }
 }

@@ -155,6 +155,7 @@ static int fill_geom(const sarpost_head_t *h, HeadGeom *g, int64_t *anchors) {
     if (h->nl < 1 || h->nl > kMaxLevels) return fail(SARPOST_EINVAL, "nl %d outside [1, %d]", h->nl, kMaxLevels);
     if (h->reg_max != kRegMax) return fail(SARPOST_EUNSUPPORTED, "reg_max %d unsupported (only 16, head.py:39)", h->reg_max);
     if (h->batch < 1) return fail(SARPOST_EINVAL, "batch %d < 1", h->batch);
+    if (h->dtype != SARPOST_F32 && h->dtype != SARPOST_F16) return fail(SARPOST_EUNSUPPORTED, "dtype %d unsupported (0 = f32, 1 = f16)", h->dtype);
     if (h->nc < 1 || h->nc > SARPOST_MAX_CLASSES) return fail(SARPOST_EUNSUPPORTED, "nc %d outside [1, %d]", h->nc, SARPOST_MAX_CLASSES);
     if (h->n_extra_raw < 0 || h->n_extra_sigmoid < 0 || h->no < 4 * kRegMax + h->nc + h->n_extra_raw + h->n_extra_sigmoid)
         return fail(SARPOST_EINVAL, "no %d < 4*reg_max + nc + extras (%d)", h->no, 4 * kRegMax + h->nc + h->n_extra_raw + h->n_extra_sigmoid);
@@ -165,6 +166,7 @@ static int fill_geom(const sarpost_head_t *h, HeadGeom *g, int64_t *anchors) {
     g->nc = h->nc;
     g->n_extra_raw = h->n_extra_raw;
     g->n_extra_sig = h->n_extra_sigmoid;
+    g->is_half = h->dtype == SARPOST_F16;
     int64_t a = 0, t = 0;
     for (int l = 0; l < h->nl; ++l) {
         if (h->h[l] < 1 || h->w[l] < 1) return fail(SARPOST_EINVAL, "level %d has empty shape %dx%d", l, h->h[l], h->w[l]);
@@ -175,7 +177,7 @@ static int fill_geom(const sarpost_head_t *h, HeadGeom *g, int64_t *anchors) {
         g->lvl_w[l] = h->w[l];
         g->lvl_aoff[l] = static_cast<int32_t>(a);
         g->lvl_stride[l] = h->stride[l];
-        g->lvl_ptr[l] = static_cast<const float *>(h->data[l]);
+        g->lvl_ptr[l] = h->data[l];
         a += hw;
         t += (hw + kTileA - 1) / kTileA;
     }
@@ -208,7 +210,7 @@ static PFN_encodeTiled get_encode_fn() {
 static bool tma_eligible(const HeadGeom &g) {
     if (4 * kRegMax + g.nc > 256) return false;
     for (int l = 0; l < g.nl; ++l) {
-        if ((static_cast<int64_t>(g.lvl_hw[l]) * 4) % 16) return false;
+        if ((static_cast<int64_t>(g.lvl_hw[l]) * (g.is_half ? 2 : 4)) % 16) return false;
         if (reinterpret_cast<uintptr_t>(g.lvl_ptr[l]) % 16) return false;
     }
     return get_encode_fn() != nullptr;
@@ -232,14 +234,17 @@ static int env_int(const char *name, int dflt) {
 // ------------------------------------------------------------------------------------------------
 static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandStore &st, cudaStream_t s) {
     const int nch = 4 * kRegMax + g.nc;
-    const int64_t stage_bytes = static_cast<int64_t>(nch) * kTileA * 4;
+    const int esz = g.is_half ? 2 : 4;
+    const int64_t stage_bytes = static_cast<int64_t>(nch) * kTileA * esz;
     int sms = 0, smem_optin = 0;
     if (int rc = device_sm_count(&sms, &smem_optin)) return rc;
     bool use_tma = tma_eligible(g) && !env_int("SARPOST_K1_FORCE_LDG", 0);
     int stages = 0, ctas = 0;
     if (use_tma) {
         const int64_t sm_smem = 228 * 1024;
-        const int want_ctas = env_int("SARPOST_K1_CTAS", 3);
+        // fp32 tiles: 3 CTAs x 2 stages of 33 KB fill the SM's shared memory and reach the HBM roofline; fp16 tiles
+        // are half the size and the kernel turns issue-bound, so more resident warps (6 CTAs) pay off (measured)
+        const int want_ctas = env_int("SARPOST_K1_CTAS", g.is_half ? 6 : 3);
         for (ctas = want_ctas; ctas >= 1; --ctas) {
             const int64_t per_cta = sm_smem / ctas - 1024 /*driver reserve*/ - 512 /*static + align*/;
             stages = static_cast<int>(per_cta / stage_bytes);
@@ -261,26 +266,32 @@ static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandSto
         PFN_encodeTiled enc = get_encode_fn();
         for (int l = 0; l < g.nl; ++l) {
             const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.lvl_hw[l]), static_cast<cuuint64_t>(g.no), static_cast<cuuint64_t>(g.batch)};
-            const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lvl_hw[l]) * 4, static_cast<cuuint64_t>(g.lvl_hw[l]) * g.no * 4};
+            const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lvl_hw[l]) * esz, static_cast<cuuint64_t>(g.lvl_hw[l]) * g.no * esz};
             const cuuint32_t box[3] = {kTileA, static_cast<cuuint32_t>(nch), 1};
             const cuuint32_t estr[3] = {1, 1, 1};
-            const CUresult r = enc(&p.maps[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(g.lvl_ptr[l]), dims, strides, box, estr,
+            const CUresult r = enc(&p.maps[l], g.is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(g.lvl_ptr[l]), dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(SARPOST_ECUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, static_cast<int>(r));
         }
         const int smem = static_cast<int>(stages * stage_bytes + 128);
-        CUDA_TRY(cudaFuncSetAttribute(k1_fused_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int grid = sms * ctas;
         if (grid > p.n_tiles) grid = p.n_tiles;
-        k1_fused_tma<<<grid, kTileA, smem, s>>>(p);
+        if (g.is_half) {
+            CUDA_TRY(cudaFuncSetAttribute(k1_fused_tma<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k1_fused_tma<__half><<<grid, kTileA, smem, s>>>(p);
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(k1_fused_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k1_fused_tma<float><<<grid, kTileA, smem, s>>>(p);
+        }
     } else {
         K1LdgParams p;
         memset(&p, 0, sizeof(p));
         p.g = g;
         p.f = f;
         p.st = st;
-        k1_fused_ldg<<<dim3(g.tpi, g.batch), kTileA, 0, s>>>(p);
+        if (g.is_half) k1_fused_ldg<__half><<<dim3(g.tpi, g.batch), kTileA, 0, s>>>(p);
+        else k1_fused_ldg<float><<<dim3(g.tpi, g.batch), kTileA, 0, s>>>(p);
     }
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
@@ -390,7 +401,7 @@ int32_t sarpost_workspace_prepare(void *workspace, int64_t workspace_bytes, int3
     return SARPOST_OK;
 }
 
-int32_t sarpost_decode(const sarpost_head_t *head, float *y, void *stream) {
+int32_t sarpost_decode(const sarpost_head_t *head, void *y, void *stream) {
     g_launches = 0;
     HeadGeom g;
     int64_t anchors = 0;
@@ -400,7 +411,8 @@ int32_t sarpost_decode(const sarpost_head_t *head, float *y, void *stream) {
     p.g = g;
     p.y = y;
     p.anchors = anchors;
-    k_decode_y<<<dim3(g.tpi, g.batch), kTileA, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    if (g.is_half) k_decode_y<__half><<<dim3(g.tpi, g.batch), kTileA, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    else k_decode_y<float><<<dim3(g.tpi, g.batch), kTileA, 0, static_cast<cudaStream_t>(stream)>>>(p);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return SARPOST_OK;
@@ -483,6 +495,7 @@ int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *pa
         ex.lvl_hw[l] = g.lvl_hw[l];
         ex.lvl_ptr[l] = g.lvl_ptr[l];
     }
+    ex.is_half = g.is_half;
     return run_tail(P, g.batch, params, g.nc, ex, out, counts, kept_index, s);
 }
 
@@ -551,6 +564,7 @@ int32_t sarpost_gather_extras(const sarpost_head_t *head, const int32_t *image_i
         p.lvl_hw[l] = g.lvl_hw[l];
         p.lvl_ptr[l] = g.lvl_ptr[l];
     }
+    p.is_half = g.is_half;
     k_gather_extras<<<(n + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());

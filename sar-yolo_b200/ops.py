@@ -110,11 +110,12 @@ def _make_head(levels: Sequence[torch.Tensor], spec: HeadSpec, host: bool = Fals
     h.reg_max = spec.reg_max
     h.n_extra_raw = spec.embed_dim if with_extras else 0
     h.n_extra_sigmoid = spec.state_classes if with_extras else 0
+    h.dtype = 1 if levels[0].dtype == torch.float16 else 0
     for i, x in enumerate(levels):
         if x.dim() != 4 or x.shape[0] != h.batch or x.shape[1] != spec.no:
             raise ValueError(f"sarpost: level {i} has shape {tuple(x.shape)}, expected (B={h.batch}, no={spec.no}, H, W)")
-        if x.dtype != torch.float32 or not x.is_contiguous():
-            raise ValueError("sarpost: level tensors must be contiguous float32 (convert before the call)")
+        if x.dtype != levels[0].dtype or x.dtype not in (torch.float32, torch.float16) or not x.is_contiguous():
+            raise ValueError("sarpost: level tensors must be contiguous and all float32 or all float16")
         if host == x.is_cuda:
             raise RuntimeError(f"sarpost: level {i} is on {x.device}, expected {'host' if host else 'CUDA'} memory")
         h.h[i] = int(x.shape[2])
@@ -126,9 +127,10 @@ def _make_head(levels: Sequence[torch.Tensor], spec: HeadSpec, host: bool = Fals
 
 def _prep_levels(levels: Sequence[torch.Tensor]) -> List[torch.Tensor]:
     out = []
+    half = all(x.dtype == torch.float16 for x in levels)  # `half=True` pipelines: fp16 logits are read as they are
     for x in levels:
         _require_cuda(x, "level tensor")
-        if x.dtype != torch.float32:
+        if not half and x.dtype != torch.float32:
             x = x.float()
         out.append(x.contiguous())
     return out
@@ -261,7 +263,7 @@ def decode(levels: Sequence[torch.Tensor], spec: HeadSpec) -> torch.Tensor:
     dev = levels[0].device
     anchors = sum(int(x.shape[2]) * int(x.shape[3]) for x in levels)
     with torch.cuda.device(dev):
-        y = torch.empty((head.batch, 4 + spec.nc + spec.nm, anchors), dtype=torch.float32, device=dev)
+        y = torch.empty((head.batch, 4 + spec.nc + spec.nm, anchors), dtype=levels[0].dtype, device=dev)
         _lib.check(lib.sarpost_decode(C.byref(head), y.data_ptr(), _stream_ptr(dev)))
     return y
 

@@ -361,3 +361,27 @@ def test_fused_scale_boxes_and_clip(sarpost, cuda):
         ref[:, :4] = R.scale_boxes_ref(img1, ref[:, :4], s0)
         assert torch.equal(r1.cpu(), ref)
         assert float(r1[:, 2].max()) <= s0[1] and float(r1[:, 3].max()) <= s0[0] and float(r1[:, :4].min()) >= 0
+
+
+@pytest.mark.parametrize("imgsz,strides,nc,ed,sc", [(640, (8, 16, 32), 1, 256, 6), ((96, 160), (8, 16, 32), 3, 0, 0),
+                                                     ((88, 120), (8, 16, 32), 2, 8, 6)])
+def test_fp16_level_tensors(sarpost, cuda, imgsz, strides, nc, ed, sc):
+    """§8f row 4 (`half=True`): fp16 logits are upcast exactly and processed in fp32, so feeding the fp16
+    tensors must give bit-identical rows to feeding their fp32 upcast; decode returns y in fp16."""
+    shapes = sarpost.synth.level_shapes(imgsz, strides)
+    spec = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=sc)
+    lv16 = [x.to(cuda).half() for x in sarpost.synth.head_outputs(2, shapes, nc, ed, sc, seed=41)]
+    lv32 = [x.float() for x in lv16]
+    for kw in (dict(conf_thres=0.25, iou_thres=0.7), dict(conf_thres=0.001, iou_thres=0.7, multi_label=True)):
+        a, ia = sarpost.postprocess_fused(lv16, spec, return_index=True, **kw)
+        b, ib = sarpost.postprocess_fused(lv32, spec, return_index=True, **kw)
+        for x, y, i, j in zip(a, b, ia, ib):
+            assert x.dtype == torch.float32 and torch.equal(x, y) and torch.equal(i, j)
+    y16 = sarpost.decode(lv16, spec)
+    y32 = sarpost.decode(lv32, spec)
+    assert y16.dtype == torch.float16 and torch.equal(y16, y32.half())
+    # and the fp32 path on the upcast inputs is within tolerance of the oracle (same check as test_decode_matches_oracle)
+    y_ref = R.decode_ref([x.cpu() for x in lv32], strides, nc, 16, ed, sc)
+    st = torch.cat([torch.full((h * w,), float(s)) for (h, w), s in zip(shapes, strides)])
+    err = (y32.cpu()[:, :4] - y_ref[:, :4]).abs()
+    assert bool((err <= 1e-5 * y_ref[:, :4].abs() + 1e-5 * st).all())
