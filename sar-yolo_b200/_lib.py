@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsarpost.so")
+LIB_PATH = os.environ.get("SARPOST_LIB_PATH") or os.path.join(HERE, "libsarpost.so")  # env override: A/B builds
 
 MAX_LEVELS = 8
 MAX_CLASSES = 2048

@@ -24,7 +24,16 @@ struct HeadGeom {
     float lvl_stride[kMaxLevels];
     const void *lvl_ptr[kMaxLevels];  // elements of type float or __half (kernel template parameter)
     int32_t is_half;
+    uint32_t lvl_w_magic[kMaxLevels];  // ceil(2^32 / W_l): y = pos / W_l without an integer division
 };
+
+// floor(n / d) for n*d < 2^32-ish operands via a precomputed magic = ceil(2^32 / d) and one correction step
+__device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
+    int q = static_cast<int>(__umulhi(static_cast<uint32_t>(n), magic));
+    if (q * d > n) --q;               // magic rounds up: the estimate can be one too large
+    else if ((q + 1) * d <= n) ++q;   // (only when magic was clamped, d == 1)
+    return q;
+}
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
@@ -182,7 +191,7 @@ __device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, u
 __device__ __forceinline__ int tile_level(const HeadGeom &g, int r) {
     int l = 0;
 #pragma unroll
-    for (int i = 1; i < kMaxLevels; ++i) l += (i < g.nl && r >= g.lvl_tile_begin[i]) ? 1 : 0;
+    for (int i = 1; i < kMaxLevels; ++i) l += (r >= g.lvl_tile_begin[i]) ? 1 : 0;  // entries >= nl hold tpi (never reached)
     return l;
 }
 
@@ -203,7 +212,7 @@ struct K1TmaParams {
 constexpr int kMaxStages = 8;
 
 template <typename T>
-__global__ void __launch_bounds__(kTileA, 3) k1_fused_tma(const __grid_constant__ K1TmaParams p) {
+__global__ void __launch_bounds__(kTileA, sizeof(T) == 2 ? 6 : 3) k1_fused_tma(const __grid_constant__ K1TmaParams p) {
     extern __shared__ unsigned char dyn_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ int scratch[8];
@@ -221,36 +230,48 @@ __global__ void __launch_bounds__(kTileA, 3) k1_fused_tma(const __grid_constant_
 
     const int first = blockIdx.x, step = gridDim.x;
     const int n_my = first < p.n_tiles ? (p.n_tiles - first + step - 1) / step : 0;
+    // tile k of this CTA is t = first + k*step = image b, tile r: walked incrementally (no division per tile)
+    const int step_b = step / p.g.tpi, step_r = step - step_b * p.g.tpi;
+    auto advance = [&](int &b, int &r) {
+        b += step_b;
+        r += step_r;
+        if (r >= p.g.tpi) { r -= p.g.tpi; ++b; }
+    };
 
-    auto issue = [&](int k) {
-        const int t = first + k * step;
-        const int b = t / p.g.tpi, r = t - b * p.g.tpi;
+    auto issue = [&](int s, int b, int r) {
         const int l = tile_level(p.g, r);
         const int a0 = (r - p.g.lvl_tile_begin[l]) * kTileA;
-        const int s = k % p.stages;
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
         tma_load_3d(dyn + static_cast<size_t>(s) * stage_bytes, &p.maps[l], a0, 0, b, &full_bar[s]);
     };
+    int ib = first / p.g.tpi, ir = first - ib * p.g.tpi;  // next tile to issue (thread 0)
     if (tid == 0)
-        for (int k = 0; k < p.stages && k < n_my; ++k) issue(k);
+        for (int k = 0; k < p.stages && k < n_my; ++k) {
+            issue(k, ib, ir);
+            advance(ib, ir);
+        }
 
+    int b = first / p.g.tpi, r = first - b * p.g.tpi, s = 0;
+    uint32_t phase = 0;
     for (int k = 0; k < n_my; ++k) {
-        const int t = first + k * step;
-        const int b = t / p.g.tpi, r = t - b * p.g.tpi;
         const int l = tile_level(p.g, r);
         const int pos = (r - p.g.lvl_tile_begin[l]) * kTileA + tid;  // position inside the level
         const bool valid = pos < p.g.lvl_hw[l];
-        const int s = k % p.stages;
-        mbar_wait(&full_bar[s], static_cast<uint32_t>((k / p.stages) & 1));
+        mbar_wait(&full_bar[s], phase);
         const T *buf = reinterpret_cast<const T *>(dyn + static_cast<size_t>(s) * stage_bytes) + tid;
         auto acc = [&](int c) { return to_f32(buf[c * kTileA]); };
         const int w = p.g.lvl_w[l];
-        const int yy = pos / w, xx = pos - yy * w;
+        const int yy = fast_div(pos, w, p.g.lvl_w_magic[l]), xx = pos - yy * w;
         const float4 xyxy = xywh2xyxy_rn(decode_xywh(acc, xx, yy, p.g.lvl_stride[l]));
         auto score = [&](int j) { return sigmoid_rn(to_f32(buf[(4 * kRegMax + j) * kTileA])); };
         emit_candidates(valid, xyxy, static_cast<uint32_t>(p.g.lvl_aoff[l] + pos), p.g.nc, p.f, score, p.st, b, r, scratch);
         // emit_candidates ended with __syncthreads(): stage s is free again
-        if (tid == 0 && k + p.stages < n_my) issue(k + p.stages);
+        if (tid == 0 && k + p.stages < n_my) {
+            issue(s, ib, ir);
+            advance(ib, ir);
+        }
+        advance(b, r);
+        if (++s == p.stages) { s = 0; phase ^= 1u; }
     }
 }
 
@@ -277,7 +298,7 @@ __global__ void __launch_bounds__(kTileA) k1_fused_ldg(const __grid_constant__ K
     const T *base = static_cast<const T *>(p.g.lvl_ptr[l]) + static_cast<int64_t>(b) * p.g.no * hw + pc;
     auto acc = [&](int c) { return to_f32(__ldg(base + static_cast<int64_t>(c) * hw)); };
     const int w = p.g.lvl_w[l];
-    const int yy = pc / w, xx = pc - yy * w;
+    const int yy = fast_div(pc, w, p.g.lvl_w_magic[l]), xx = pc - yy * w;
     const float4 xyxy = xywh2xyxy_rn(decode_xywh(acc, xx, yy, p.g.lvl_stride[l]));
     auto score = [&](int j) { return sigmoid_rn(acc(4 * kRegMax + j)); };
     emit_candidates(valid, xyxy, static_cast<uint32_t>(p.g.lvl_aoff[l] + pc), p.g.nc, p.f, score, p.st, b, r, scratch);
@@ -363,7 +384,7 @@ __global__ void __launch_bounds__(kTileA) k_decode_y(const __grid_constant__ Dec
     const T *base = static_cast<const T *>(p.g.lvl_ptr[l]) + static_cast<int64_t>(b) * p.g.no * hw + pos;
     auto acc = [&](int c) { return to_f32(__ldg(base + static_cast<int64_t>(c) * hw)); };
     const int w = p.g.lvl_w[l];
-    const int yy = pos / w, xx = pos - yy * w;
+    const int yy = fast_div(pos, w, p.g.lvl_w_magic[l]), xx = pos - yy * w;
     const float4 o = decode_xywh(acc, xx, yy, p.g.lvl_stride[l]);
     const int cout = 4 + p.g.nc + p.g.n_extra_raw + p.g.n_extra_sig;
     T *yo = static_cast<T *>(p.y) + static_cast<int64_t>(b) * cout * p.anchors + p.g.lvl_aoff[l] + pos;

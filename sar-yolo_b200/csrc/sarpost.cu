@@ -170,11 +170,13 @@ static int fill_geom(const sarpost_head_t *h, HeadGeom *g, int64_t *anchors) {
     int64_t a = 0, t = 0;
     for (int l = 0; l < h->nl; ++l) {
         if (h->h[l] < 1 || h->w[l] < 1) return fail(SARPOST_EINVAL, "level %d has empty shape %dx%d", l, h->h[l], h->w[l]);
+        if (static_cast<int64_t>(h->h[l]) * h->w[l] >= (1 << 24)) return fail(SARPOST_EUNSUPPORTED, "level %d has more than 2^24 anchors", l);
         if (!h->data[l]) return fail(SARPOST_EINVAL, "level %d data pointer is NULL", l);
         const int64_t hw = static_cast<int64_t>(h->h[l]) * h->w[l];
         g->lvl_tile_begin[l] = static_cast<int32_t>(t);
         g->lvl_hw[l] = static_cast<int32_t>(hw);
         g->lvl_w[l] = h->w[l];
+        g->lvl_w_magic[l] = h->w[l] == 1 ? 0xffffffffu : static_cast<uint32_t>(((1ull << 32) + h->w[l] - 1) / h->w[l]);  // ceil(2^32 / W)
         g->lvl_aoff[l] = static_cast<int32_t>(a);
         g->lvl_stride[l] = h->stride[l];
         g->lvl_ptr[l] = h->data[l];
@@ -270,7 +272,8 @@ static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandSto
             const cuuint32_t box[3] = {kTileA, static_cast<cuuint32_t>(nch), 1};
             const cuuint32_t estr[3] = {1, 1, 1};
             const CUresult r = enc(&p.maps[l], g.is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(g.lvl_ptr[l]), dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   static_cast<CUtensorMapL2promotion>(env_int("SARPOST_K1_L2PROMO", CU_TENSOR_MAP_L2_PROMOTION_L2_256B)),
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(SARPOST_ECUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, static_cast<int>(r));
         }
