@@ -73,6 +73,11 @@ typedef struct sarpost_nms_params {
     float max_wh;          /* ops.py:289,295 class offset = cls * max_wh */
     const int32_t *classes;/* HOST pointer to the `classes` filter (ops.py:278-279) or NULL */
     int32_t n_classes;
+    const float *labels;   /* sarpost_nms_decoded only: DEVICE pointer (B, max_labels, 5) rows cls,x,y,w,h — the apriori labels of
+                              `save_hybrid` (ops.py:256-261): appended to every image's candidates with probability 1.0 for
+                              their class and zero extras; NULL = none */
+    const int32_t *label_counts; /* DEVICE (B): valid label rows per image */
+    int32_t max_labels;
     const float *rescale;  /* DEVICE pointer (B, 5) = pad_x, pad_y, gain, w0, h0 per image, or NULL.  When set the gather
                               kernel applies ops.scale_boxes + clip_boxes (utils/ops.py:92-127, :319-338) to the output
                               boxes: x = clamp((x - pad_x) / gain, 0, w0), y likewise with pad_y, h0 — the per-image
@@ -111,6 +116,8 @@ int32_t sarpost_decode(const sarpost_head_t *head, void *y, void *stream);
 /*
  * Replaces ops.non_max_suppression (utils/ops.py:167-316, non-rotated branch) on an already
  * decoded prediction (B, C, A), C = 4 + nc + nm, rows cx,cy,w,h | nc probabilities | nm extras.
+ * With apriori labels (params->labels) size the workspace for `anchors + max_labels` anchors; kept_index of a
+ * label row is (anchors + label_row)*nc + class.
  *   out        device (B, max_det, 6 + nm): x1,y1,x2,y2,conf,cls,extras — rows [0, counts[b]) valid,
  *              in descending confidence; rows beyond are left untouched
  *   counts     device (B) int32

@@ -32,7 +32,8 @@ class NmsParams(C.Structure):
     _fields_ = [
         ("conf_thres", C.c_float), ("iou_thres", C.c_double), ("agnostic", C.c_int32), ("multi_label", C.c_int32),
         ("max_det", C.c_int32), ("max_nms", C.c_int32), ("max_wh", C.c_float),
-        ("classes", C.POINTER(C.c_int32)), ("n_classes", C.c_int32), ("rescale", C.c_void_p),
+        ("classes", C.POINTER(C.c_int32)), ("n_classes", C.c_int32), ("labels", C.c_void_p),
+        ("label_counts", C.c_void_p), ("max_labels", C.c_int32), ("rescale", C.c_void_p),
         ("workspace_clean", C.c_int32),
     ]
 

@@ -331,6 +331,37 @@ __global__ void __launch_bounds__(kTileA) k1_decoded(const __grid_constant__ K1D
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1 (labels): apriori labels of `save_hybrid` (ops.py:256-261): v[:, :4] = xywh2xyxy(lb[:, 1:5]),
+// v[i, 4 + cls] = 1.0, extras 0, concatenated AFTER the image's own rows — here the tiles that follow the
+// anchor tiles.  A label row yields one candidate (score 1.0, its class) in both best-class and multi-label
+// mode, subject to `score > conf` and the `classes` filter.  grid = (label tiles, B), blockDim = kTileA.
+// ---------------------------------------------------------------------------------------------
+struct K1LabelParams {
+    const float *labels;          // [B, max_labels, 5]
+    const int32_t *label_counts;  // [B]
+    int32_t max_labels, nc;
+    int32_t first_tile;           // index of the first label tile inside an image
+    uint32_t first_anchor;        // = A: label row i is reported as anchor A + i
+    CandFilter f;
+    CandStore st;
+};
+
+__global__ void __launch_bounds__(kTileA) k1_labels(const __grid_constant__ K1LabelParams p) {
+    __shared__ int scratch[8];
+    const int lt = blockIdx.x, b = blockIdx.y;
+    const int i = lt * kTileA + threadIdx.x;
+    int n = p.label_counts[b];
+    n = n < 0 ? 0 : (n > p.max_labels ? p.max_labels : n);
+    const bool valid = i < n;
+    const float *row = p.labels + (static_cast<int64_t>(b) * p.max_labels + (valid ? i : 0)) * 5;
+    const int cls = valid ? static_cast<int>(row[0]) : -1;  // lb[:, 0].long()
+    const float4 xyxy = xywh2xyxy_rn(make_float4(row[1], row[2], row[3], row[4]));
+    auto score = [&](int j) { return j == cls ? 1.0f : 0.0f; };
+    emit_candidates(valid && cls >= 0 && cls < p.nc, xyxy, p.first_anchor + static_cast<uint32_t>(i), p.nc, p.f, score, p.st, b,
+                    p.first_tile + lt, scratch);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1 (merge): candidates for the cross-tile merge — one block per SAHI tile; rows are already
 // filtered detections (x1,y1,x2,y2,conf,cls,...) which are shifted by the tile origin.
 // grid = (tiles_per_frame, n_frames), blockDim = 128.

@@ -656,7 +656,9 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
         o[5] = static_cast<float>(cls);
         if (p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
     }
-    if (p.ex.nm > 0) {
+    if (p.ex.nm > 0 && p.ex.mode == 0 && anchor >= static_cast<uint32_t>(p.ex.anchors)) {
+        for (int c = lane; c < p.ex.nm; c += 32) o[6 + c] = 0.0f;  // apriori label row: no extras (ops.py:258)
+    } else if (p.ex.nm > 0) {
         int64_t stride;
         const void *base;
         const int64_t at = extras_base(p.ex, b, anchor, &stride, &base);

@@ -434,7 +434,12 @@ int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t chan
     CandFilter f;
     make_filter(params, nc, &f);
     const int64_t nc_eff = f.multi_label ? nc : 1;
-    const int64_t tpi = (anchors + kTileA - 1) / kTileA;
+    const bool with_labels = params->labels != nullptr && params->max_labels > 0;
+    if (with_labels && !params->label_counts) return fail(SARPOST_EINVAL, "labels given without label_counts");
+    const int64_t tpi_anchor = (anchors + kTileA - 1) / kTileA;
+    const int64_t tpi_label = with_labels ? (params->max_labels + kTileA - 1) / kTileA : 0;
+    const int64_t tpi = tpi_anchor + tpi_label;
+    if ((anchors + (with_labels ? params->max_labels : 0)) * nc >= (1ll << 32)) return fail(SARPOST_EUNSUPPORTED, "(anchors+labels)*nc does not fit 32 bits");
     const int64_t region = kTileA * nc_eff;
     Pipeline P;
     if (int rc = bind_workspace(workspace, workspace_bytes, batch, tpi * region, tpi, region, params->max_det, false, &P)) return rc;
@@ -448,9 +453,23 @@ int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t chan
     kp.anchors = anchors;
     kp.f = f;
     kp.st = P.st;
-    k1_decoded<<<dim3(static_cast<unsigned>(tpi), batch), kTileA, 0, s>>>(kp);
+    k1_decoded<<<dim3(static_cast<unsigned>(tpi_anchor), batch), kTileA, 0, s>>>(kp);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
+    if (with_labels) {
+        K1LabelParams lp;
+        lp.labels = params->labels;
+        lp.label_counts = params->label_counts;
+        lp.max_labels = params->max_labels;
+        lp.nc = nc;
+        lp.first_tile = static_cast<int32_t>(tpi_anchor);
+        lp.first_anchor = static_cast<uint32_t>(anchors);
+        lp.f = f;
+        lp.st = P.st;
+        k1_labels<<<dim3(static_cast<unsigned>(tpi_label), batch), kTileA, 0, s>>>(lp);
+        ++g_launches;
+        CUDA_TRY(cudaGetLastError());
+    }
     stage_mark(2, s);
 
     ExtrasSrc ex;

@@ -200,7 +200,8 @@ def non_max_suppression(
     (SURVEY.md Appendix B.10): the input is never modified (`in_place` is accepted and ignored), the
     wall-clock limit `max_time_img` is accepted and ignored (nothing here can time out), score ties at
     the `max_nms` cut resolve to the lower anchor index (the reference's order there is torch-version
-    defined).  `rotated=True` and non-empty `labels` raise NotImplementedError.
+    defined).  `rotated=True` raises NotImplementedError.  Apriori `labels` (save_hybrid) are supported; with
+    `return_index` a label row reports anchor index `A + label_row`.
     `return_index=True` (extension) also returns per image the int32 `anchor*nc + class` of each row.
     """
     # Checks (ops.py:217-220)
@@ -211,8 +212,7 @@ def non_max_suppression(
     _require_cuda(prediction, "prediction")
     if rotated:
         raise NotImplementedError("sarpost: rotated=True (OBB probiou NMS, ops.py:146-164) is outside the accelerated path")
-    if labels and any(len(lb) for lb in labels):
-        raise NotImplementedError("sarpost: apriori `labels` (save_hybrid, ops.py:256-261) are not supported")
+    has_labels = bool(labels) and any(len(lb) for lb in labels)
 
     if prediction.shape[-1] == 6:  # end-to-end model (BNC, i.e. 1,300,6): no NMS at all (ops.py:224-228)
         output = [pred[pred[:, 4] > conf_thres][:max_det] for pred in prediction]
@@ -233,8 +233,20 @@ def non_max_suppression(
         return (empty, [torch.zeros((0,), dtype=torch.int32, device=dev)] * bs) if return_index else empty
 
     params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+    n_lab = 0
+    if has_labels:  # apriori labels for autolabelling (ops.py:256-261): padded (B, L, 5) cls,x,y,w,h + counts
+        if len(labels) != bs:
+            raise ValueError(f"sarpost: {len(labels)} label tensors for a batch of {bs}")
+        lbs = [torch.as_tensor(lb, dtype=torch.float32).reshape(-1, 5) for lb in labels]
+        n_lab = max(int(lb.shape[0]) for lb in lbs)
+        lab = torch.zeros((bs, n_lab, 5), dtype=torch.float32)
+        for i, lb in enumerate(lbs):
+            lab[i, : lb.shape[0]] = lb.detach().cpu()
+        lab = lab.to(dev)
+        lab_cnt = torch.tensor([int(lb.shape[0]) for lb in lbs], dtype=torch.int32).to(dev)
+        params.labels, params.label_counts, params.max_labels = lab.data_ptr(), lab_cnt.data_ptr(), n_lab
     with torch.cuda.device(dev):
-        ws_bytes = lib.sarpost_workspace_bytes(bs, na, nc, int(bool(multi_label)), int(max_det))
+        ws_bytes = lib.sarpost_workspace_bytes(bs, na + n_lab, nc, int(bool(multi_label)), int(max_det))
         if ws_bytes < 0:
             _lib.check(int(ws_bytes))
         ws = _Workspace(ws_bytes, bs, dev)

@@ -4,7 +4,7 @@ Every reference call site resolves `ops.non_max_suppression` through the module 
 time (models/yolo/jde/predict.py:31, jde/val.py:648, detect/predict.py:25, detect/val.py:94, ...) and
 the heads call `self._inference(x)` (nn/modules/head.py:73, :211), so replacing those three attributes
 is enough for `model.predict()` / `model.val()`.  Calls this package does not
-accelerate (CPU tensors, rotated boxes, apriori labels, export mode) are forwarded to the ORIGINAL
+accelerate (CPU tensors, rotated boxes, export mode) are forwarded to the ORIGINAL
 reference function that was saved at patch time — never to a re-implementation of ours.
 """
 from __future__ import annotations
@@ -21,10 +21,8 @@ _SAVED = {}
 def _nms_dispatch(prediction, *args, **kwargs):
     orig = _SAVED["nms"]
     pred = prediction[0] if isinstance(prediction, (list, tuple)) else prediction
-    labels = kwargs.get("labels", args[5] if len(args) > 5 else ())
     rotated = kwargs.get("rotated", args[12] if len(args) > 12 else False)
-    has_labels = bool(labels) and any(len(lb) for lb in labels)
-    if (not getattr(pred, "is_cuda", False)) or rotated or has_labels:
+    if (not getattr(pred, "is_cuda", False)) or rotated:
         return orig(prediction, *args, **kwargs)  # the reference's own code path, untouched
     return _ops.non_max_suppression(prediction, *args, **kwargs)
 

@@ -43,3 +43,23 @@ def canon(rows: torch.Tensor) -> torch.Tensor:
         return rows.detach().cpu()
     keys = [r[:, c] for c in range(r.shape[1] - 1, -1, -1) if c != 4] + [-r[:, 4]]
     return torch.from_numpy(r[np.lexsort(keys)])
+
+
+def synth_labels(seed, nc, counts=(5, 0, 150)):
+    """Same generator as tests/golden/make_golden.py::synth_labels."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for n in counts:
+        cls = torch.randint(0, nc, (n, 1), generator=g).float()
+        xy = torch.rand(n, 2, generator=g) * 600
+        wh = 10 + torch.rand(n, 2, generator=g) * 80
+        out.append(torch.cat((cls, xy, wh), 1))
+    return out
+
+
+def nms_case_inputs(sarpost, meta):
+    y = sarpost.synth.decoded_prediction(**meta["gen"])
+    kw = dict(meta["kw"])
+    if "labels_seed" in meta:
+        kw["labels"] = synth_labels(meta["labels_seed"], meta["gen"]["nc"])
+    return y, kw

@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from golden_util import canon, head_inputs, load, names
+from golden_util import canon, head_inputs, load, names, nms_case_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -10,8 +10,10 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("name", names("nms_"))
 def test_cuda_nms_equals_reference_golden(sarpost, cuda, name):
     g = load(name)
-    y = sarpost.synth.decoded_prediction(**g["meta"]["gen"]).to(cuda)
-    rows = sarpost.non_max_suppression(y, **g["meta"]["kw"])
+    y, kw = nms_case_inputs(sarpost, g["meta"])
+    if "labels" in kw:
+        kw["labels"] = [lb.to(cuda) for lb in kw["labels"]]
+    rows = sarpost.non_max_suppression(y.to(cuda), **kw)
     assert [r.shape[0] for r in rows] == g["counts"]
     for a, b in zip(rows, g["rows"]):
         # bit-exact kept rows, classes and extras; canon() only re-orders rows with exactly equal scores

@@ -385,3 +385,27 @@ def test_fp16_level_tensors(sarpost, cuda, imgsz, strides, nc, ed, sc):
     st = torch.cat([torch.full((h * w,), float(s)) for (h, w), s in zip(shapes, strides)])
     err = (y32.cpu()[:, :4] - y_ref[:, :4]).abs()
     assert bool((err <= 1e-5 * y_ref[:, :4].abs() + 1e-5 * st).all())
+
+
+@pytest.mark.parametrize("multi_label", [False, True])
+def test_apriori_labels_save_hybrid(sarpost, cuda, multi_label):
+    """ops.py:256-261: apriori labels are appended to each image's rows (prob 1.0, zero extras) before NMS."""
+    g = torch.Generator().manual_seed(9)
+    bs, na, nc, nm = 3, 3000, 4, 3
+    y = sarpost.synth.decoded_prediction(bs, na, nc, nm, seed=77)
+    labels = []
+    for n in (5, 0, 150):
+        cls = torch.randint(0, nc, (n, 1), generator=g).float()
+        xy = torch.rand(n, 2, generator=g) * 600
+        wh = 10 + torch.rand(n, 2, generator=g) * 80
+        labels.append(torch.cat((cls, xy, wh), 1))
+    kw = dict(conf_thres=0.3, iou_thres=0.6, nc=nc, multi_label=multi_label, classes=[0, 1, 3], max_det=400)
+    rows, idx = sarpost.non_max_suppression(y.to(cuda), labels=[lb.to(cuda) for lb in labels], return_index=True, **kw)
+    ref_rows, ref_idx = R.non_max_suppression_ref(y, labels=labels, return_index=True, **kw)
+    for b in range(bs):
+        assert torch.equal(rows[b].cpu(), ref_rows[b])
+        a = idx[b].cpu().long() // nc
+        src = ref_idx[b][:, 0]
+        exp = torch.where(src >= 0, src, na + (-1 - src))  # oracle marks label row k as -1-k
+        assert torch.equal(a, exp)
+    assert any((r[:, 4] == 1.0).any() for r in rows)

@@ -71,7 +71,7 @@ def test_plugin_patch_and_unpatch_forward_unaccelerated_calls(sarpost):
     try:
         assert sarpost.plugin.is_patched()
         assert ops_mod.non_max_suppression is not ref_nms
-        # CPU tensors, rotated boxes and apriori labels go to the reference's own function
+        # CPU tensors and rotated boxes go to the reference's own function
         y = torch.zeros(1, 6, 10)
         assert ops_mod.non_max_suppression(y) == ["ref"]
         assert ops_mod.non_max_suppression((y, None), 0.25, 0.45, None, False, False, (), 300, 0, 0.05, 30000, 7680, True, True) == ["ref"]

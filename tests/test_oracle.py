@@ -5,21 +5,21 @@ import os
 import pytest
 import torch
 
-from golden_util import GOLDEN_DIR, canon, head_inputs, load, names
+from golden_util import GOLDEN_DIR, canon, head_inputs, load, names, nms_case_inputs
 from oracle import postprocess_ref as R
 
 
 @pytest.mark.parametrize("name", names("nms_"))
 def test_oracle_nms_equals_reference_golden(sarpost, name):
     g = load(name)
-    y = sarpost.synth.decoded_prediction(**g["meta"]["gen"])
+    y, kw = nms_case_inputs(sarpost, g["meta"])
     # literal restatement (the reference's unstable argsort at the max_nms cut): bit-equal incl. row order
-    rows = R.non_max_suppression_ref(y, stable_topk=False, **g["meta"]["kw"])
+    rows = R.non_max_suppression_ref(y, stable_topk=False, **kw)
     assert [r.shape[0] for r in rows] == g["counts"]
     for a, b in zip(rows, g["rows"]):
         assert torch.equal(a, b)
     # stable tie rule (what the CUDA path implements): same kept set, equal-score rows may be permuted
-    rows = R.non_max_suppression_ref(y, stable_topk=True, **g["meta"]["kw"])
+    rows = R.non_max_suppression_ref(y, stable_topk=True, **kw)
     for a, b in zip(rows, g["rows"]):
         assert torch.equal(canon(a), canon(b))
 
