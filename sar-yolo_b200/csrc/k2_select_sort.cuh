@@ -39,15 +39,16 @@ constexpr int kTileListCap = 2048;
 template <class Fn>
 __device__ __forceinline__ void for_each_candidate_in(const CandStore &st, const int32_t *tcount, const uint32_t *tmax,
                                                       const float *score, uint32_t lo_bits, uint32_t hi_bits,
+                                                      int tile_lo, int tile_hi /* this CTA's share of the image's tiles */,
                                                       uint32_t *tile_list /*[kTileListCap] smem*/, int *list_n /*smem*/,
                                                       const Fn &fn) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const uint32_t span = hi_bits - lo_bits;  // in range  <=>  (bits - lo_bits) <= span  (unsigned)
-    for (int t0 = 0; t0 < st.tpi; t0 += kTileListCap) {
+    for (int t0 = tile_lo; t0 < tile_hi; t0 += kTileListCap) {
         __syncthreads();
         if (tid == 0) *list_n = 0;
         __syncthreads();
-        const int t1 = min(st.tpi, t0 + kTileListCap);
+        const int t1 = min(tile_hi, t0 + kTileListCap);
         for (int tb = t0 + warp * 32; tb < t1; tb += nwarps * 32) {
             const int t = tb + lane;
             const int c = (t < t1 && tmax[t] >= lo_bits) ? tcount[t] : 0;

@@ -17,7 +17,12 @@
 //             bitmask, all threads);
 //   sweep     one warp resolves the sub-chunk on the bitmask, 32 candidates per step when no two live
 //             candidates of the group overlap, else one step per KEPT box; appends to the kept list.
+// Small batches (B*CL <= #SMs) run a thread-block CLUSTER of CL CTAs per image: the selection scan, phase 1
+// and the bitmask are split across the CTAs, the sort/compaction are replicated (same data, same result),
+// the sweep stays on the master CTA; candidates, survivors' flags, mask rows and new kept boxes travel through
+// distributed shared memory, with 3 cluster barriers per sub-chunk.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -243,10 +248,21 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *key, int l
     }
 }
 
-// dynamic shared memory: kept_box[max_det] float4 | kept_area[max_det] | kept_slot[max_det]
-__host__ __device__ inline size_t nms_smem_bytes(int max_det) { return static_cast<size_t>(max_det) * 24; }
+// dynamic shared memory: kept_box[max_det] float4 | kept_area[max_det] | kept_slot[max_det] | (pad to 16) |
+// plist[kSortCap] u64 (this CTA's share of a collected chunk, cluster variant)
+__host__ __device__ inline size_t nms_kept_bytes(int max_det) { return (static_cast<size_t>(max_det) * 24 + 15) / 16 * 16; }
+__host__ __device__ inline size_t nms_smem_bytes(int max_det) { return nms_kept_bytes(max_det) + kSortCap * 8; }
 
+constexpr int kMaxNmsCluster = 4;
+
+template <int CL>
 __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__ NmsParams p) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = CL > 1 ? static_cast<int>(cluster.block_rank()) : 0;
+    auto cluster_sync = [&]() {
+        if constexpr (CL > 1) cluster.sync(); else __syncthreads();
+    };
     // All shared arrays are referenced through their symbols (never through pointers kept in
     // structs) so every access compiles to LDS/STS rather than a generic LD/ST.
     extern __shared__ float4 dyn_kept[];
@@ -254,7 +270,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     __shared__ uint32_t s_mask[kSub * kSubWords];
     __shared__ float s_a_area[kSub], s_c_area[kSub];
     __shared__ uint32_t s_a_slot[kSub], s_c_slot[kSub];
-    __shared__ int32_t s_a_alive[kSub];
+    __shared__ int32_t s_dead[kSub];  // phase-1 verdicts; written by every CTA of the cluster, cleared by its owner
     __shared__ int32_t s_misc[32];
     // union region: skey[kSortCap] u64 | a_box[kSub] | c_box[kSub]; the fallback radix sort aliases all of it
     __shared__ __align__(16) unsigned char s_uni[256 * (kNmsWarps + 1) * 4];
@@ -266,9 +282,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #define A_BOX (reinterpret_cast<float4 *>(s_uni + kSortCap * 8))
 #define C_BOX (reinterpret_cast<float4 *>(s_uni + kSortCap * 8 + kSub * 16))
 #define TILE_LIST (reinterpret_cast<uint32_t *>(s_uni + kSortCap * 8))  /* aliases A_BOX|C_BOX, idle while collecting */
+#define PLIST (reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(dyn_kept) + nms_kept_bytes(p.max_det)))
     static_assert(kTileListCap * 4 <= 2 * kSub * 16, "tile list must fit the a_box|c_box region");
 
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
     const int32_t *tcount = p.st.tile_count + static_cast<int64_t>(b) * p.st.tpi;
     const uint32_t *tmaxv = p.st.tile_max + static_cast<int64_t>(b) * p.st.tpi;
@@ -277,6 +294,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #ifdef SARPOST_PHASE_PROF
     long long prof_t = clock64();
 #endif
+    if (tid < kSub) s_dead[tid] = 0;
 
     // ---- descending exclusive scan of the sampled score histogram: s_bstart[d] ~ estimated rank of the first
     //      candidate of bucket 4095-d in the sorted order (x kHistSample).  Estimates only steer how many
@@ -288,7 +306,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
             loc[i] = hist[kBuckets - 1 - (tid * kPer + i)] * kHistSample;
-            hist[kBuckets - 1 - (tid * kPer + i)] = 0;  // leave the histogram zeroed for the next call (workspace_clean)
+            if constexpr (CL == 1) hist[kBuckets - 1 - (tid * kPer + i)] = 0;  // leave it zeroed for the next call (workspace_clean)
             sum += loc[i];
         }
         int tot = 0;
@@ -318,6 +336,11 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         if (tid == 0) s_misc[19] = tot;
     }
     __syncthreads();
+    if constexpr (CL > 1) {  // every CTA of the cluster has read the histogram: the master zeroes it
+        cluster.sync();
+        if (crank == 0)
+            for (int i = tid; i < kBuckets; i += kNmsThreads) p.st.hist[static_cast<int64_t>(b) * kBuckets + i] = 0;
+    }
     PROF_MARK(0);
     const int n_all = s_misc[19];
     const int n_limit = min(n_all, p.max_nms);  // ops.py:285-286: only the top max_nms ranks are eligible
@@ -341,16 +364,17 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 A_BOX[tid] = ob;
                 s_a_area[tid] = box_area_rn(ob);
                 s_a_slot[tid] = slot;
-                s_a_alive[tid] = 1;
             }
             __syncthreads();
             PROF_MARK(3);
             // ---- phase 1: candidates x kept list, kNmsThreads/sub_p2 threads per candidate ----
             if (kept > 0) {
+                // this CTA's share of the candidates (the whole sub-chunk when CL == 1)
+                const int per = (sub + CL - 1) / CL, c_lo = crank * per, c_n = max(0, min(sub, c_lo + per) - c_lo);
                 int sub_p2 = 64;
-                while (sub_p2 < sub) sub_p2 <<= 1;
-                const int cand = tid & (sub_p2 - 1), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
-                if (cand < sub) {
+                while (sub_p2 < c_n) sub_p2 <<= 1;
+                const int cand = c_lo + (tid & (sub_p2 - 1)), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
+                if (cand < c_lo + c_n) {
                     const float4 ob = A_BOX[cand];
                     const float oa = s_a_area[cand];
                     bool dead = false, any_border = false;
@@ -362,16 +386,23 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                     }
                     if (any_border && !dead)  // rare: a quotient within a few ulp of the threshold
                         for (int k = part; k < kept; k += nparts) dead |= iou_gt(KEPT_BOX[k], KEPT_AREA[k], ob, oa, p.thr);
-                    if (dead) s_a_alive[cand] = 0;
+                    if (dead) {
+                        s_dead[cand] = 1;
+                        if constexpr (CL > 1)
+                            for (int r2 = 0; r2 < CL; ++r2)
+                                if (r2 != crank) *cluster.map_shared_rank(&s_dead[cand], r2) = 1;
+                    }
                 }
-                __syncthreads();
+                cluster_sync();
             }
             PROF_MARK(4);
             // ---- ordered compaction of survivors (first kSub threads = 8 warps) ----
             bool alive = false;
             uint32_t bal = 0;
             if (tid < kSub) {
-                alive = tid < sub && s_a_alive[tid];
+                alive = tid < sub && !s_dead[tid];
+                // cleared by its owner here: peers write it again only after the two cluster barriers that follow
+                s_dead[tid] = 0;
                 bal = __ballot_sync(0xffffffffu, alive);
                 if (lane == 0) s_misc[warp] = __popc(bal);
             }
@@ -392,7 +423,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             // ---- phase 2: suppression bitmask among the m survivors (row r, bits j > r) ----
             // warp per row r, lane j tests the pair (r, 32w + j) for every word w >= r/32; a ballot packs the word
             const int words = (m + 31) >> 5;
-            for (int r = warp; r < m; r += kNmsWarps) {
+            uint32_t *mask_out = s_mask;  // the master's bitmask (it runs the sweep)
+            if constexpr (CL > 1) mask_out = cluster.map_shared_rank(s_mask, 0);
+            for (int r = warp * CL + crank; r < m; r += kNmsWarps * CL) {
                 const float4 rb = C_BOX[r];
                 const float ra = s_c_area[r];
                 for (int w = r >> 5; w < words; w += 2) {
@@ -407,8 +440,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                     const bool ov1 = v1 && fminf(rb.z, cb1.z) > fmaxf(rb.x, cb1.x) && fminf(rb.w, cb1.w) > fmaxf(rb.y, cb1.y);
                     if (!__any_sync(0xffffffffu, ov0 || ov1)) {
                         if (lane == 0) {
-                            s_mask[r * kSubWords + w] = 0u;
-                            if (w + 1 < words) s_mask[r * kSubWords + w + 1] = 0u;
+                            mask_out[r * kSubWords + w] = 0u;
+                            if (w + 1 < words) mask_out[r * kSubWords + w + 1] = 0u;
                         }
                         continue;
                     }
@@ -421,15 +454,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                     const uint32_t bits0 = __ballot_sync(0xffffffffu, g0 && v0);
                     const uint32_t bits1 = __ballot_sync(0xffffffffu, g1 && v1);
                     if (lane == 0) {
-                        s_mask[r * kSubWords + w] = bits0;
-                        if (w + 1 < words) s_mask[r * kSubWords + w + 1] = bits1;
+                        mask_out[r * kSubWords + w] = bits0;
+                        if (w + 1 < words) mask_out[r * kSubWords + w + 1] = bits1;
                     }
                 }
             }
-            __syncthreads();
+            cluster_sync();
             PROF_MARK(6);
-            // ---- sweep (warp 0) ----
-            if (warp == 0) {
+            // ---- sweep (warp 0 of the master CTA) ----
+            if (warp == 0 && crank == 0) {
                 uint32_t km[kSubWords];  // kept bits of the groups resolved so far (warp-uniform)
 #pragma unroll
                 for (int g = 0; g < kSubWords; ++g) km[g] = 0u;
@@ -481,7 +514,22 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 }
                 if (lane == 0) s_misc[16] = kl;
             }
-            __syncthreads();
+            if constexpr (CL > 1) {
+                if (crank == 0) {  // replicate the new kept boxes and the new count in the other CTAs of the cluster
+                    __syncthreads();
+                    const int kl = s_misc[16];
+                    for (int i = kept + tid; i < kl; i += kNmsThreads)
+                        for (int r2 = 1; r2 < CL; ++r2) {
+                            *cluster.map_shared_rank(&KEPT_BOX[i], r2) = KEPT_BOX[i];
+                            *cluster.map_shared_rank(&KEPT_AREA[i], r2) = KEPT_AREA[i];
+                        }
+                    if (tid == 0)
+                        for (int r2 = 1; r2 < CL; ++r2) *cluster.map_shared_rank(&s_misc[16], r2) = kl;
+                }
+                cluster.sync();
+            } else {
+                __syncthreads();
+            }
             kept = s_misc[16];
             pdone += sub;
             __syncthreads();
@@ -489,14 +537,19 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         }
     };
 
-    // members of score buckets [b_lo, b_hi] -> SKEY (first kSortCap of them), exact count -> s_misc[18]
-    auto collect_smem = [&](int b_lo, int b_hi) {
+    // this CTA's share of the image's tiles (everything when CL == 1)
+    const int tiles_per_cta = (p.st.tpi + CL - 1) / CL;
+    const int tile_lo = min(p.st.tpi, crank * tiles_per_cta), tile_hi = min(p.st.tpi, tile_lo + tiles_per_cta);
+    // members of score buckets [b_lo, b_hi] among this CTA's tiles -> `list` (first kSortCap of them), exact
+    // count -> s_misc[18]
+    auto collect_smem = [&](int b_lo, int b_hi, unsigned long long *list) {
         const uint32_t lo_bits = bucket_floor_bits(b_lo);
         const uint32_t hi_bits = b_hi >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_hi + 1) - 1u;
-        for_each_candidate_in(p.st, tcount, tmaxv, score, lo_bits, hi_bits, TILE_LIST, &s_misc[20], [&](uint32_t slot, uint32_t bits) {
-            const int at = atomicAdd(&s_misc[18], 1);  // members are rare (a few hundred per image)
-            if (at < kSortCap) SKEY[at] = (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - slot);
-        });
+        for_each_candidate_in(p.st, tcount, tmaxv, score, lo_bits, hi_bits, tile_lo, tile_hi, TILE_LIST, &s_misc[20],
+                              [&](uint32_t slot, uint32_t bits) {
+                                  const int at = atomicAdd(&s_misc[18], 1);  // members are rare (a few hundred per image)
+                                  if (at < kSortCap) list[at] = (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - slot);
+                              });
     };
 
     while (d < kBuckets && pos < n_limit && kept < p.max_det) {
@@ -519,15 +572,42 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         __syncthreads();
         int d1 = s_misc[17];
         int m = 0;
+        int my_off = 0, my_cnt = 0;
         for (;;) {  // collect; if the real population overflows shared memory, halve the bucket run and retry
             __syncthreads();
             if (tid == 0) s_misc[18] = 0;
             __syncthreads();
-            collect_smem(kBuckets - d1, kBuckets - 1 - d);
-            __syncthreads();
-            m = s_misc[18];
+            if constexpr (CL == 1) {
+                collect_smem(kBuckets - d1, kBuckets - 1 - d, SKEY);
+                __syncthreads();
+                m = s_misc[18];
+            } else {
+                collect_smem(kBuckets - d1, kBuckets - 1 - d, PLIST);
+                __syncthreads();
+                my_cnt = s_misc[18];
+                if (tid < CL) *cluster.map_shared_rank(&s_misc[24 + crank], tid) = my_cnt;  // my count -> every CTA
+                cluster.sync();
+                m = 0;
+                my_off = 0;
+#pragma unroll
+                for (int r2 = 0; r2 < CL; ++r2) {
+                    my_off += r2 < crank ? s_misc[24 + r2] : 0;
+                    m += s_misc[24 + r2];
+                }
+                cluster.sync();  // everyone has read the counts before a retry may overwrite them
+            }
             if (m <= kSortCap || d1 - d == 1) break;
             d1 = d + (d1 - d) / 2;
+        }
+        if constexpr (CL > 1) {
+            if (m <= kSortCap) {  // all-gather the shares: every CTA ends up with the same chunk in SKEY
+                for (int i = tid; i < my_cnt; i += kNmsThreads) {
+                    const unsigned long long v = PLIST[i];
+#pragma unroll
+                    for (int r2 = 0; r2 < CL; ++r2) *cluster.map_shared_rank(&SKEY[my_off + i], r2) = v;
+                }
+            }
+            cluster.sync();
         }
         PROF_MARK(1);
         if (m <= kSortCap) {
@@ -543,37 +623,44 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             }
         } else {
             // ---- a single bucket larger than shared memory: collect to global scratch, stable LSD radix sort
-            //      on (score bits desc, slot asc), then stream it through the suppression phases ----
+            //      on (score bits desc, slot asc), then stream it through the suppression phases.  With a
+            //      cluster the master CTA does this alone (rare path); the others wait and read the result. ----
             uint32_t *ka = p.tmp_key_a + seg, *va = p.tmp_val_a + seg, *kb = p.tmp_key_b + seg, *vb = p.tmp_val_b + seg;
             const int b_one = kBuckets - 1 - d;
-            __syncthreads();
-            if (tid == 0) s_misc[18] = 0;
-            __syncthreads();
-            for_each_candidate_in(p.st, tcount, tmaxv, score, bucket_floor_bits(b_one),
-                                  b_one >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_one + 1) - 1u, TILE_LIST, &s_misc[20],
-                                  [&](uint32_t slot, uint32_t bits) {
-                                      const int at = atomicAdd(&s_misc[18], 1);
-                                      ka[at] = bits;
-                                      va[at] = slot;
-                                  });
-            __syncthreads();
-            int *cnt = reinterpret_cast<int *>(s_uni);
-            int *wt = s_misc;
             const uint32_t *ik = ka, *iv = va;
             uint32_t *ok = kb, *ov = vb;
             int slot_bits = 1;
             while ((static_cast<int64_t>(1) << slot_bits) < p.st.cap) ++slot_bits;
             const int passes_slot = (slot_bits + 7) / 8;
-            for (int ps = 0; ps < passes_slot + 4; ++ps) {
-                const int sh = ps < passes_slot ? ps * 8 : (ps - passes_slot) * 8;
-                if (ps < passes_slot)
-                    radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t, uint32_t v) { return (v >> sh) & 255u; }, cnt, wt);
-                else
-                    radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t k, uint32_t) { return ((~k) >> sh) & 255u; }, cnt, wt);
-                const uint32_t *tk = ik, *tv = iv;
-                ik = ok; iv = ov;
-                ok = const_cast<uint32_t *>(tk); ov = const_cast<uint32_t *>(tv);
+            if (crank == 0) {
+                __syncthreads();
+                if (tid == 0) s_misc[18] = 0;
+                __syncthreads();
+                for_each_candidate_in(p.st, tcount, tmaxv, score, bucket_floor_bits(b_one),
+                                      b_one >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_one + 1) - 1u, 0, p.st.tpi,
+                                      TILE_LIST, &s_misc[20], [&](uint32_t slot, uint32_t bits) {
+                                          const int at = atomicAdd(&s_misc[18], 1);
+                                          ka[at] = bits;
+                                          va[at] = slot;
+                                      });
+                __syncthreads();
+                int *cnt = reinterpret_cast<int *>(s_uni);
+                int *wt = s_misc;
+                for (int ps = 0; ps < passes_slot + 4; ++ps) {
+                    const int sh = ps < passes_slot ? ps * 8 : (ps - passes_slot) * 8;
+                    if (ps < passes_slot)
+                        radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t, uint32_t v) { return (v >> sh) & 255u; }, cnt, wt);
+                    else
+                        radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t k, uint32_t) { return ((~k) >> sh) & 255u; }, cnt, wt);
+                    const uint32_t *tk = ik, *tv = iv;
+                    ik = ok; iv = ov;
+                    ok = const_cast<uint32_t *>(tk); ov = const_cast<uint32_t *>(tv);
+                }
+                __threadfence();
+            } else if ((passes_slot + 4) & 1) {  // same ping-pong parity as the master: where the sorted values end up
+                iv = vb;
             }
+            if constexpr (CL > 1) cluster.sync();
             const uint32_t *sorted = iv;
             const int lim = min(m, n_limit - pos);
             for (int piece = 0; piece < lim && kept < p.max_det; piece += kSortCap) {
@@ -583,10 +670,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         pos += m;
         d = d1;
     }
-    // ---- publish ----
+    // ---- publish (master CTA) ----
     __syncthreads();
-    for (int k = tid; k < kept; k += kNmsThreads) p.kept_slot[static_cast<int64_t>(b) * p.max_det + k] = KEPT_SLOT[k];
-    if (tid == 0) p.counts[b] = kept;
+    if (crank == 0) {
+        for (int k = tid; k < kept; k += kNmsThreads) p.kept_slot[static_cast<int64_t>(b) * p.max_det + k] = KEPT_SLOT[k];
+        if (tid == 0) p.counts[b] = kept;
+    }
+    if constexpr (CL > 1) cluster.sync();  // no CTA may exit while a peer can still address its shared memory
     PROF_MARK(8);
 #undef KEPT_BOX
 #undef KEPT_AREA
@@ -595,6 +685,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #undef A_BOX
 #undef C_BOX
 #undef TILE_LIST
+#undef PLIST
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -319,8 +319,36 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     np.max_wh = prm->agnostic ? 0.0f : prm->max_wh;
     np.thr = iou_thr_float(prm->iou_thres);
     const int nms_smem = static_cast<int>(nms_smem_bytes(prm->max_det));
-    CUDA_TRY(cudaFuncSetAttribute(k4_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(nms_smem_bytes(4096))));
-    k4_nms<<<batch, kNmsThreads, nms_smem, s>>>(np);
+    // one CTA per image; when the batch leaves SMs idle, a cluster of 2 or 4 CTAs per image shares the work
+    int sms = 0, smem_optin = 0;
+    if (int rc = device_sm_count(&sms, &smem_optin)) return rc;
+    int cl = batch * 4 <= sms ? 4 : (batch * 2 <= sms ? 2 : 1);
+    const int forced_cl = env_int("SARPOST_NMS_CLUSTER", 0);
+    if (forced_cl == 1 || forced_cl == 2 || forced_cl == 4) cl = forced_cl;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(batch * cl);
+    cfg.blockDim = dim3(kNmsThreads);
+    cfg.dynamicSmemBytes = nms_smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = cl;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    const int max_smem = static_cast<int>(nms_smem_bytes(4096));
+    if (cl == 4) {
+        CUDA_TRY(cudaFuncSetAttribute(k4_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k4_nms<4>, np));
+    } else if (cl == 2) {
+        CUDA_TRY(cudaFuncSetAttribute(k4_nms<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k4_nms<2>, np));
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k4_nms<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k4_nms<1>, np));
+    }
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     stage_mark(3, s);
