@@ -1,6 +1,9 @@
 """hot.py <ncu-rep> <kernel-regex> [topn] — per-source-line stall samples by joining ncu SASS rows with nvdisasm -g line info."""
 import csv,sys,subprocess,re,collections,os,glob
 rep=sys.argv[1]; kern=sys.argv[2]; topn=int(sys.argv[3]) if len(sys.argv)>3 else 25
+# kern is matched against the MANGLED section name in the cubin (e.g. k4_nmsILi4E for k4_nms<4>); the ncu filter
+# uses the plain function name in front of the template suffix
+ncu_kern=re.split(r"I[A-Z0-9]", kern)[0] if re.search(r"I(Li\d+|f|6__half)E", kern) else kern
 so="/root/repo/sar-yolo_b200/libsarpost.so"
 wd="/tmp/probe/cubin"; os.makedirs(wd,exist_ok=True)
 for f in glob.glob(wd+"/*.cubin"): os.remove(f)
@@ -19,7 +22,7 @@ for l in dis[start+1:]:
     if m: cur=(os.path.basename(m.group(1)),int(m.group(2))); continue
     m=re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(.*?);',l)
     if m: lines.append((int(m.group(1),16),cur,m.group(2)))
-out=subprocess.run(["ncu","-i",rep,"--page","source","--csv","--kernel-name","regex:"+kern],capture_output=True,text=True).stdout
+out=subprocess.run(["ncu","-i",rep,"--page","source","--csv","--kernel-name","regex:"+ncu_kern],capture_output=True,text=True).stdout
 rows=list(csv.reader(out.splitlines()))
 # may contain multiple kernel instances; take the first
 hdr=None; inst=[]; ninst=0
