@@ -409,3 +409,33 @@ def test_apriori_labels_save_hybrid(sarpost, cuda, multi_label):
         exp = torch.where(src >= 0, src, na + (-1 - src))  # oracle marks label row k as -1-k
         assert torch.equal(a, exp)
     assert any((r[:, 4] == 1.0).any() for r in rows)
+
+
+def test_cuda_graph_capture_and_replay(sarpost, cuda):
+    """The whole pipeline is stream-ordered (no host sync, no allocation inside the library), so a call can be
+    captured into a CUDA graph and replayed on new data written into the same input buffers."""
+    strides = (8, 16, 32)
+    shapes = sarpost.synth.level_shapes(320, strides)
+    spec = sarpost.HeadSpec(nc=2, strides=strides, embed_dim=16, state_classes=6)
+    a = [x.to(cuda) for x in sarpost.synth.head_outputs(4, shapes, 2, 16, 6, seed=1)]
+    b = [x.to(cuda) for x in sarpost.synth.head_outputs(4, shapes, 2, 16, 6, seed=2)]
+    kw = dict(conf_thres=0.25, iou_thres=0.7, max_det=100)
+    ref_a = sarpost.postprocess_fused(a, spec, return_padded=True, **kw)
+    ref_b = sarpost.postprocess_fused(b, spec, return_padded=True, **kw)
+    static_in = [x.clone() for x in a]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # warm-up on the capture stream (workspace allocation + prepare)
+        sarpost.postprocess_fused(static_in, spec, return_padded=True, **kw)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out, counts = sarpost.postprocess_fused(static_in, spec, return_padded=True, **kw)
+    for src, ref in ((a, ref_a), (b, ref_b), (a, ref_a)):
+        for dst, s in zip(static_in, src):
+            dst.copy_(s)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(counts, ref[1])
+        for i, n in enumerate(counts.tolist()):
+            assert torch.equal(out[i, :n], ref[0][i, :n])
