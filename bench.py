@@ -234,10 +234,25 @@ def main():
         g_cnt = torch.zeros((n_frames * tpf,), dtype=torch.int32, device=dev)
         origins = origins1.repeat(n_frames, 1)
         lo = rank * bs
+        peer = None
+        if world > 1 and not os.environ.get("SARPOST_BENCH_NCCL_GATHER"):
+            # fused gather + exchange: K5 stores this rank's rows/counts into every rank's buffer over NVLink
+            peer = sarpost.dist.PeerGatherBuffer(bs, kw["max_det"], 6, dev)
 
         def step():
             # boxes only: the extras of the few rows that survive the merge are fetched afterwards from the rank
             # that owns the tile (sarpost.gather_extras), not for 300 rows of every tile
+            if peer is not None:
+                rows_all, cnt_all = sarpost.postprocess_fused(levels, spec, with_extras=False, peer_out=peer.next(), **kw)
+                peer.barrier()
+                if f_hi > f_lo:
+                    t0, t1 = f_lo * tpf, min(f_hi * tpf, total_tiles)
+                    g_rows[t0:t1].copy_(rows_all[t0:t1])  # pad the last frame with empty tiles (g_cnt stays 0 there)
+                    g_cnt[t0:t1].copy_(cnt_all[t0:t1])
+                    return sarpost.merge_tiles(g_rows[f_lo * tpf:f_hi * tpf], g_cnt[f_lo * tpf:f_hi * tpf],
+                                               origins[f_lo * tpf:f_hi * tpf], tpf, iou_thres=kw["iou_thres"],
+                                               max_det=kw["max_det"], return_padded=True)
+                return rows_all, cnt_all
             out, counts = sarpost.postprocess_fused(levels, spec, return_padded=True, with_extras=False, **kw)
             g_rows[lo:lo + bs].copy_(out)
             g_cnt[lo:lo + bs].copy_(counts)
@@ -367,7 +382,10 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "images_per_gpu": bs, "global_batch": bs * n_gpus,
-                       "anchors": anchors, "channels": spec.no, "parallelism": (f"tiles sharded x{n_gpus}, NCCL all-gather of counts+boxes, frames merged by their owner rank" if sahi
+                       "anchors": anchors, "channels": spec.no, "parallelism": ((f"tiles sharded x{n_gpus}, gather kernel stores counts+boxes into every rank over NVLink peer memory "
+                                        f"(fused gather+exchange, no NCCL collective), frames merged by their owner rank"
+                                        if (n_gpus > 1 and not os.environ.get("SARPOST_BENCH_NCCL_GATHER")) else
+                                        f"tiles sharded x{n_gpus}, NCCL all-gather of counts+boxes, frames merged by their owner rank") if sahi
                                        else f"batch-sharded x{n_gpus}, no data-path collective"),
                        "l2": "one batch of inputs (hot channels %.0f MB) exceeds the 126 MB L2; no flush" % (bs * anchors * (64 + nc) * 4 / 1e6),
                        "candidates_per_image": n_cand / bs, "detections_per_image": n_det / bs},

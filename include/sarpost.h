@@ -82,6 +82,14 @@ typedef struct sarpost_nms_params {
                               kernel applies ops.scale_boxes + clip_boxes (utils/ops.py:92-127, :319-338) to the output
                               boxes: x = clamp((x - pad_x) / gain, 0, w0), y likewise with pad_y, h0 — the per-image
                               loop of models/yolo/jde/predict.py:49 (ignored by sarpost_merge_tiles). */
+    /* Fused gather + exchange over NVLink peer memory (multi-GPU, one process per GPU): when n_peers > 0 the gather
+     * kernel stores every output row — and every image's count — into the buffers of ALL n_peers ranks (P2P-mapped
+     * device pointers, e.g. torch symmetric memory), at image slot peer_slot_offset + b, instead of `out`/`counts`:
+     * the all-gather of SURVEY §8e happens inside K5.  The caller runs a cross-rank barrier afterwards. */
+    float *peer_out[8];      /* each (total_images, max_det, 6 + nm) */
+    int32_t *peer_counts[8]; /* each (total_images) */
+    int32_t n_peers;
+    int32_t peer_slot_offset;
     int32_t workspace_clean;/* 0: the call zeroes the score-histogram head of the workspace itself (one memset node).
                               1: the caller guarantees the first sarpost_workspace_clean_bytes(batch) bytes are zero —
                               true after sarpost_workspace_prepare and after every successful call that used the

@@ -34,7 +34,8 @@ class NmsParams(C.Structure):
         ("max_det", C.c_int32), ("max_nms", C.c_int32), ("max_wh", C.c_float),
         ("classes", C.POINTER(C.c_int32)), ("n_classes", C.c_int32), ("labels", C.c_void_p),
         ("label_counts", C.c_void_p), ("max_labels", C.c_int32), ("rescale", C.c_void_p),
-        ("workspace_clean", C.c_int32),
+        ("peer_out", C.c_void_p * 8), ("peer_counts", C.c_void_p * 8), ("n_peers", C.c_int32),
+        ("peer_slot_offset", C.c_int32), ("workspace_clean", C.c_int32),
     ]
 
 

@@ -702,6 +702,10 @@ struct GatherParams {
     int32_t *kept_index;        // [B*max_det] or nullptr
     const float *rescale;       // [B,5] pad_x, pad_y, gain, w0, h0 or nullptr (ops.scale_boxes + clip_boxes)
     int32_t max_det;
+    // fused gather + exchange: rows/counts are stored into every rank's buffer (P2P-mapped pointers over NVLink)
+    float *peer_out[8];
+    int32_t *peer_counts[8];
+    int32_t n_peers, peer_slot_offset;
 };
 
 // ops.scale_boxes (utils/ops.py:92-127, padding=True, xyxy) followed by clip_boxes (:319-338), in torch's fp32
@@ -721,17 +725,24 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
     const int b = blockIdx.y;
     const int r = blockIdx.x * kGatherWarps + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (r >= p.counts[b]) return;
+    const int n_rows = p.counts[b];
+    const int row_len = 6 + p.ex.nm;
+    // destinations of this row: the local output, or the same slot in every rank's buffer (peer stores)
+    const int n_dst = p.n_peers > 0 ? p.n_peers : 1;
+    const int64_t img = p.n_peers > 0 ? p.peer_slot_offset + b : b;
+    if (p.n_peers > 0 && r == 0 && lane < p.n_peers) p.peer_counts[lane][img] = n_rows;  // the counts travel with the rows
+    if (r >= n_rows) return;
+    auto dst = [&](int q) { return (p.n_peers > 0 ? p.peer_out[q] : p.out) + (img * p.max_det + r) * row_len; };
     const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
     const uint32_t slot = p.kept_slot[static_cast<int64_t>(b) * p.max_det + r];
     const uint32_t key = p.st.key[seg + slot];
-    const int row_len = 6 + p.ex.nm;
-    float *o = p.out + (static_cast<int64_t>(b) * p.max_det + r) * row_len;
     if (p.ex.mode == 2) {
         const float *src = p.ex.dets + (static_cast<int64_t>(b) * p.st.tpi * p.ex.dets_per_tile + key) * p.ex.row_len;
         const float4 bx = p.st.box[seg + slot];
-        for (int c = lane; c < row_len; c += 32)
-            o[c] = c == 0 ? bx.x : c == 1 ? bx.y : c == 2 ? bx.z : c == 3 ? bx.w : src[c];
+        for (int c = lane; c < row_len; c += 32) {
+            const float v = c == 0 ? bx.x : c == 1 ? bx.y : c == 2 ? bx.z : c == 3 ? bx.w : src[c];
+            for (int q = 0; q < n_dst; ++q) dst(q)[c] = v;
+        }
         if (lane == 0 && p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
         return;
     }
@@ -739,16 +750,21 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
     if (lane == 0) {
         float4 bx = p.st.box[seg + slot];
         if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
-        o[0] = bx.x;
-        o[1] = bx.y;
-        o[2] = bx.z;
-        o[3] = bx.w;
-        o[4] = p.st.score[seg + slot];
-        o[5] = static_cast<float>(cls);
+        const float sc = p.st.score[seg + slot];
+        for (int q = 0; q < n_dst; ++q) {
+            float *o = dst(q);
+            o[0] = bx.x;
+            o[1] = bx.y;
+            o[2] = bx.z;
+            o[3] = bx.w;
+            o[4] = sc;
+            o[5] = static_cast<float>(cls);
+        }
         if (p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
     }
     if (p.ex.nm > 0 && p.ex.mode == 0 && anchor >= static_cast<uint32_t>(p.ex.anchors)) {
-        for (int c = lane; c < p.ex.nm; c += 32) o[6 + c] = 0.0f;  // apriori label row: no extras (ops.py:258)
+        for (int c = lane; c < p.ex.nm; c += 32)
+            for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = 0.0f;  // apriori label row: no extras (ops.py:258)
     } else if (p.ex.nm > 0) {
         int64_t stride;
         const void *base;
@@ -756,8 +772,9 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
         const bool hf = p.ex.mode == 1 && p.ex.is_half;
         const int n_raw = p.ex.mode == 0 ? p.ex.nm : p.ex.n_extra_raw;  // a decoded prediction is copied verbatim
         for (int c = lane; c < p.ex.nm; c += 32) {
-            const float v = load_elem(base, at + c * stride, hf);
-            o[6 + c] = c < n_raw ? v : sigmoid_rn(v);
+            float v = load_elem(base, at + c * stride, hf);
+            v = c < n_raw ? v : sigmoid_rn(v);
+            for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = v;
         }
     }
 }

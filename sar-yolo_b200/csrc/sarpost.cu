@@ -129,6 +129,9 @@ static int check_params(const sarpost_nms_params_t *p, int nc) {
     if (p->max_nms < 1) return fail(SARPOST_EINVAL, "max_nms %d < 1", p->max_nms);
     if (nc < 1 || nc > SARPOST_MAX_CLASSES) return fail(SARPOST_EUNSUPPORTED, "nc %d outside [1, %d]", nc, SARPOST_MAX_CLASSES);
     if (p->n_classes < 0 || (p->n_classes > 0 && !p->classes)) return fail(SARPOST_EINVAL, "classes pointer/count mismatch");
+    if (p->n_peers < 0 || p->n_peers > 8) return fail(SARPOST_EINVAL, "n_peers %d outside [0, 8]", p->n_peers);
+    for (int q = 0; q < p->n_peers; ++q)
+        if (!p->peer_out[q] || !p->peer_counts[q]) return fail(SARPOST_EINVAL, "peer buffer %d is NULL", q);
     return SARPOST_OK;
 }
 
@@ -362,6 +365,12 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     gp.kept_index = kept_index;
     gp.rescale = ex.mode == 2 ? nullptr : prm->rescale;
     gp.max_det = prm->max_det;
+    gp.n_peers = prm->n_peers;
+    gp.peer_slot_offset = prm->peer_slot_offset;
+    for (int q = 0; q < 8; ++q) {
+        gp.peer_out[q] = q < prm->n_peers ? prm->peer_out[q] : nullptr;
+        gp.peer_counts[q] = q < prm->n_peers ? prm->peer_counts[q] : nullptr;
+    }
     k5_gather<<<dim3((prm->max_det + kGatherWarps - 1) / kGatherWarps, batch), kGatherWarps * 32, 0, s>>>(gp);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
@@ -519,7 +528,7 @@ int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *pa
     int64_t anchors = 0;
     if (int rc = fill_geom(head, &g, &anchors)) return rc;
     if (int rc = check_params(params, g.nc)) return rc;
-    if (!out || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
+    if ((!out && params->n_peers == 0) || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
     CandFilter f;
     make_filter(params, g.nc, &f);
     const int64_t nc_eff = f.multi_label ? g.nc : 1;

@@ -85,3 +85,55 @@ class GatherBuffer:
             dist.all_gather_into_tensor(self.out, self.local_out, group=self.group)
             dist.all_gather_into_tensor(self.counts, self.local_counts, group=self.group)
         return self.out, self.counts
+
+
+class PeerGatherBuffer:
+    """All-gather destination in NVLink peer memory (torch symmetric memory): every rank holds the full
+    `(W*per, max_det, row_len)` rows + `(W*per,)` counts, and every rank's gather kernel (K5) stores its rows
+    straight into ALL ranks' buffers (P2P stores over NVLink/NVSwitch) — the exchange is fused into the kernel that
+    produces the data; no NCCL collective, no staging copy.  `barrier()` (a device-side signal-pad barrier on the
+    current stream) orders those stores before any rank reads.  Two alternating buffers let step i+1 write while a
+    slow peer still reads step i (its barrier i+1 comes after its reads of step i in stream order).
+    """
+
+    def __init__(self, per_rank_batch: int, max_det: int, row_len: int, device, group=None, n_buffers: int = 2):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = group or dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.per, self.max_det, self.row_len = int(per_rank_batch), int(max_det), int(row_len)
+        total = self.world * self.per
+        self._bufs = []
+        for _ in range(n_buffers):
+            rows = symm_mem.empty((total, self.max_det, self.row_len), dtype=torch.float32, device=device)
+            cnts = symm_mem.empty((total,), dtype=torch.int32, device=device)
+            h_rows = symm_mem.rendezvous(rows, group)
+            h_cnts = symm_mem.rendezvous(cnts, group)
+            self._bufs.append((rows, cnts, h_rows, h_cnts))
+        self._i = 0
+
+    def next(self) -> "PeerGatherBuffer":
+        """Advance to the other buffer (call once per step, before the fused call)."""
+        self._i = (self._i + 1) % len(self._bufs)
+        return self
+
+    @property
+    def rows(self) -> torch.Tensor:
+        return self._bufs[self._i][0]
+
+    @property
+    def counts(self) -> torch.Tensor:
+        return self._bufs[self._i][1]
+
+    @property
+    def slot_offset(self) -> int:
+        return self.rank * self.per
+
+    def peer_ptrs(self):
+        _, _, h_rows, h_cnts = self._bufs[self._i]
+        return list(h_rows.buffer_ptrs), list(h_cnts.buffer_ptrs)
+
+    def barrier(self) -> None:
+        """All ranks' peer stores issued before this point (on their current streams) are visible after it."""
+        self._bufs[self._i][2].barrier(channel=0)

@@ -282,7 +282,7 @@ def decode(levels: Sequence[torch.Tensor], spec: HeadSpec) -> torch.Tensor:
 
 def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres=0.25, iou_thres=0.45, classes=None,
                       agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=7680,
-                      return_index=False, return_padded=False, with_extras=True, scale_to=None):
+                      return_index=False, return_padded=False, with_extras=True, scale_to=None, peer_out=None):
     """decode + non_max_suppression in one pass (never materialises y; the extras channels are read only
     for the kept rows).  Result as `non_max_suppression`; `return_padded=True` returns the raw
     `(out (B, max_det, 6+nm), counts (B,) int32[, kept_index])` device tensors without any host sync.
@@ -290,7 +290,10 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
     survive a subsequent stage such as the cross-tile merge).
     `scale_to=(img1_shape, [img0_shape, ...])` additionally applies `ops.scale_boxes` + `clip_boxes` per image
     (the loop of models/yolo/jde/predict.py:48-49) inside the gather kernel: `img1_shape` = (h, w) of the network
-    input, one (h, w[, c]) per original image."""
+    input, one (h, w[, c]) per original image.
+    `peer_out=dist.PeerGatherBuffer` (multi-GPU): the gather kernel stores this rank's rows and counts into every
+    rank's buffer over NVLink peer memory — the all-gather is fused into the kernel; returns `(rows, counts)` views
+    of the full buffers, valid after `peer_out.barrier()`."""
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     levels = _prep_levels(levels)
@@ -306,18 +309,30 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
             raise ValueError(f"sarpost: scale_to has {len(img0_shapes)} original shapes for a batch of {bs}")
         rescale = scale_params(img1_shape, img0_shapes, dev)
     params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, rescale)
+    if peer_out is not None:
+        if (peer_out.per, peer_out.max_det, peer_out.row_len) != (bs, int(max_det), 6 + nm):
+            raise ValueError("sarpost: peer_out buffer geometry does not match this call")
+        rp, cp = peer_out.peer_ptrs()
+        params.n_peers = len(rp)
+        params.peer_slot_offset = peer_out.slot_offset
+        for q in range(len(rp)):
+            params.peer_out[q] = rp[q]
+            params.peer_counts[q] = cp[q]
     with torch.cuda.device(dev):
         ws_bytes = lib.sarpost_workspace_bytes(bs, anchors, spec.nc, int(bool(multi_label)), int(max_det))
         if ws_bytes < 0:
             _lib.check(int(ws_bytes))
         ws = _Workspace(ws_bytes, bs, dev)
-        out = torch.empty((bs, int(max_det), 6 + nm), dtype=torch.float32, device=dev)
+        out = torch.empty((bs, int(max_det), 6 + nm), dtype=torch.float32, device=dev) if peer_out is None else None
         counts = torch.empty((bs,), dtype=torch.int32, device=dev)
         want_idx = return_index
         kidx = torch.empty((bs, int(max_det)), dtype=torch.int32, device=dev) if want_idx else None
-        _lib.check(lib.sarpost_fused(C.byref(head), C.byref(params), out.data_ptr(), counts.data_ptr(),
-                                     kidx.data_ptr() if want_idx else None, ws.ptr(), ws_bytes, _stream_ptr(dev)))
+        _lib.check(lib.sarpost_fused(C.byref(head), C.byref(params), out.data_ptr() if out is not None else None,
+                                     counts.data_ptr(), kidx.data_ptr() if want_idx else None, ws.ptr(), ws_bytes,
+                                     _stream_ptr(dev)))
         ws.release()
+    if peer_out is not None:
+        return (peer_out.rows, peer_out.counts, kidx) if want_idx else (peer_out.rows, peer_out.counts)
     if return_padded:
         return (out, counts, kidx) if want_idx else (out, counts)
     rows = _split(out, counts)

@@ -439,3 +439,17 @@ def test_cuda_graph_capture_and_replay(sarpost, cuda):
         assert torch.equal(counts, ref[1])
         for i, n in enumerate(counts.tolist()):
             assert torch.equal(out[i, :n], ref[0][i, :n])
+
+
+def test_fused_gather_exchange_over_peer_memory(sarpost, cuda):
+    """Multi-GPU: K5's peer stores (NVLink symmetric memory) must reproduce the NCCL all-gather bit for bit.
+    Needs >= 2 GPUs (the 1-GPU box skips; `gpurun --gpus 2` runs it)."""
+    import os, subprocess, sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}", "--master-addr",
+           "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "test_peer_gather.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "peer gather == nccl all-gather: True" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
