@@ -453,3 +453,26 @@ def test_fused_gather_exchange_over_peer_memory(sarpost, cuda):
            "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "test_peer_gather.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "peer gather == nccl all-gather: True" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("imgsz,strides,nc,bs,kw", [
+    (320, (8, 16, 32), 80, 2, dict(conf_thres=0.001, iou_thres=0.7, multi_label=True)),       # COCO-like multi-label, 80 classes
+    (160, (8, 16, 32), 200, 2, dict(conf_thres=0.05, iou_thres=0.6)),                         # 64+nc > 256 box rows -> LDG path
+    (320, (8, 16, 32), 3, 2, dict(conf_thres=0.0, iou_thres=0.5, max_det=1)),                 # conf 0 (every anchor), max_det 1
+    (160, (8, 16, 32), 2, 37, dict(conf_thres=0.25, iou_thres=0.7)),                          # 37 images: cluster of 4 CTAs
+    (160, (8, 16, 32), 2, 75, dict(conf_thres=0.25, iou_thres=0.7)),                          # 75 images: cluster of 1
+    (160, (8, 16, 32), 1, 160, dict(conf_thres=0.1, iou_thres=0.7, max_det=20)),              # more images than SMs
+    (320, (8, 16, 32), 4, 2, dict(conf_thres=0.3, iou_thres=0.7, classes=[])),                # empty class filter keeps nothing
+    (320, (8, 16, 32), 4, 2, dict(conf_thres=0.2, iou_thres=0.0)),                            # iou 0: any overlap suppresses
+    (320, (8, 16, 32), 4, 2, dict(conf_thres=0.2, iou_thres=1.0)),                            # iou 1: nothing suppresses
+    (320, (8, 16, 32), 4, 2, dict(conf_thres=0.2, iou_thres=0.7, max_wh=0.0)),                # offset 0 == agnostic
+    (320, (8, 16, 32), 4, 2, dict(conf_thres=0.01, iou_thres=0.7, max_nms=7, max_det=300)),   # tiny max_nms
+])
+def test_fused_configuration_sweep(sarpost, cuda, imgsz, strides, nc, bs, kw):
+    shapes = sarpost.synth.level_shapes(imgsz, strides)
+    levels = [x.to(cuda) for x in sarpost.synth.head_outputs(bs, shapes, nc, 0, 0, seed=61, blobs=4)]
+    spec = sarpost.HeadSpec(nc=nc, strides=strides)
+    rows, idx = sarpost.postprocess_fused(levels, spec, return_index=True, **kw)
+    y = sarpost.decode(levels, spec).cpu()
+    ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=nc, return_index=True, **kw)
+    _assert_same(rows, idx, ref_rows, ref_idx, nc)
