@@ -170,6 +170,26 @@ int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const 
                             int64_t workspace_bytes, void *stream);
 
 /*
+ * Validator matching on the GPU: replaces, for a whole batch at once and without the per-image
+ * device->host copy, utils/metrics.py:55-75 (box_iou, eps 1e-7) and BaseValidator.match_predictions
+ * (engine/validator.py:222-262, use_scipy=False; JDE variant models/yolo/jde/val.py:683-736):
+ *   iou[l][d] = box_iou(gt_l, det_d) zeroed where the classes differ; for every threshold t: the pairs with
+ *   iou >= t are ordered by descending iou, each detection keeps its best label, each label then keeps the
+ *   lowest-index detection among those that chose it; correct[d][t] = 1 for the surviving pairs.
+ * (Equal IoUs: the reference's order is numpy's unstable argsort; here the lower label index wins.)
+ *   dets        device (B, max_det, row_len) rows x1,y1,x2,y2,conf,cls,...;  det_counts device (B)
+ *   gt_boxes    device (B, max_gt, 4) xyxy;  gt_cls device (B, max_gt) fp32;  gt_counts device (B)
+ *   iouv        HOST (n_thr <= 16) thresholds, e.g. linspace(0.5, 0.95, 10)
+ *   correct     device (B, max_det, n_thr) uint8
+ *   matched_gt  device (B, max_det) int32 or NULL: label index matched at threshold index `tag_thr` or -1
+ *               (the JDE validator reads true_tags[matched_gt], jde/val.py:731-735)
+ */
+int32_t sarpost_match_predictions(const float *dets, const int32_t *det_counts, int32_t batch, int32_t max_det,
+                                  int32_t row_len, const float *gt_boxes, const float *gt_cls, const int32_t *gt_counts,
+                                  int32_t max_gt, const float *iouv, int32_t n_thr, uint8_t *correct,
+                                  int32_t *matched_gt, int32_t tag_thr, void *stream);
+
+/*
  * End-to-end entry with HOST buffers (what a caller holding CPU tensors uses; timed as `e2e` by
  * bench.py).  A context owns pinned staging, device buffers and streams for one head geometry.
  * sarpost_fused_host copies only the channels the path reads (box + cls) host->device, runs the

@@ -211,3 +211,34 @@ def scale_boxes_ref(img1_shape, boxes: torch.Tensor, img0_shape) -> torch.Tensor
     boxes[..., 2] = boxes[..., 2].clamp(0, img0_shape[1])
     boxes[..., 3] = boxes[..., 3].clamp(0, img0_shape[0])
     return boxes
+
+
+def box_iou_ref(box1: torch.Tensor, box2: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
+    """utils/metrics.py:55-75."""
+    (a1, a2), (b1, b2) = box1.float().unsqueeze(1).chunk(2, 2), box2.float().unsqueeze(0).chunk(2, 2)
+    inter = (torch.min(a2, b2) - torch.max(a1, b1)).clamp_(0).prod(2)
+    return inter / ((a2 - a1).prod(2) + (b2 - b1).prod(2) - inter + eps)
+
+
+def match_predictions_ref(pred_classes: torch.Tensor, true_classes: torch.Tensor, iou: torch.Tensor, iouv: torch.Tensor,
+                          tag_thr: Optional[float] = None):
+    """engine/validator.py:222-262 (use_scipy=False), numpy like the reference; with `tag_thr` also returns the label
+    index matched at that threshold per detection or -1 (the pairs jde/val.py:731-735 iterates over)."""
+    correct = np.zeros((pred_classes.shape[0], iouv.shape[0])).astype(bool)
+    matched = np.full((pred_classes.shape[0],), -1, dtype=np.int32)
+    correct_class = true_classes[:, None] == pred_classes
+    iou = (iou * correct_class).cpu().numpy()
+    for i, threshold in enumerate(iouv.cpu().tolist()):
+        matches = np.nonzero(iou >= threshold)
+        matches = np.array(matches).T
+        if matches.shape[0]:
+            if matches.shape[0] > 1:
+                matches = matches[iou[matches[:, 0], matches[:, 1]].argsort()[::-1]]
+                matches = matches[np.unique(matches[:, 1], return_index=True)[1]]
+                matches = matches[np.unique(matches[:, 0], return_index=True)[1]]
+            correct[matches[:, 1].astype(int), i] = True
+            if tag_thr is not None and threshold == tag_thr:
+                for gt_idx, pred_idx in matches:
+                    matched[pred_idx] = gt_idx
+    c = torch.tensor(correct, dtype=torch.bool)
+    return (c, torch.from_numpy(matched)) if tag_thr is not None else c

@@ -62,6 +62,9 @@ SYMBOLS = {
     "sarpost_merge_tiles": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_void_p]),
+    "sarpost_match_predictions": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.c_void_p, C.c_void_p,
+                                              C.c_int32, C.c_void_p]),
     "sarpost_host_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
     "sarpost_host_ctx_destroy": (None, [C.c_void_p]),
     "sarpost_fused_host": (C.c_int32, [C.c_void_p, C.POINTER(Head), C.POINTER(NmsParams), C.c_void_p, C.c_void_p,

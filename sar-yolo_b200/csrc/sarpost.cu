@@ -17,6 +17,7 @@
 #include "k1_candidates.cuh"
 #include "k2_select_sort.cuh"
 #include "k4_nms.cuh"
+#include "k6_match.cuh"
 
 namespace sarpost {
 
@@ -625,6 +626,39 @@ int32_t sarpost_gather_extras(const sarpost_head_t *head, const int32_t *image_i
     }
     p.is_half = g.is_half;
     k_gather_extras<<<(n + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return SARPOST_OK;
+}
+
+int32_t sarpost_match_predictions(const float *dets, const int32_t *det_counts, int32_t batch, int32_t max_det,
+                                  int32_t row_len, const float *gt_boxes, const float *gt_cls, const int32_t *gt_counts,
+                                  int32_t max_gt, const float *iouv, int32_t n_thr, uint8_t *correct,
+                                  int32_t *matched_gt, int32_t tag_thr, void *stream) {
+    g_launches = 0;
+    if (!dets || !det_counts || !gt_boxes || !gt_cls || !gt_counts || !iouv || !correct) return fail(SARPOST_EINVAL, "NULL pointer");
+    if (batch < 1 || max_det < 1 || max_gt < 1 || row_len < 6) return fail(SARPOST_EINVAL, "bad match geometry");
+    if (n_thr < 1 || n_thr > kMaxThr) return fail(SARPOST_EINVAL, "n_thr %d outside [1, %d]", n_thr, kMaxThr);
+    if (reinterpret_cast<uintptr_t>(gt_boxes) % 16) return fail(SARPOST_EINVAL, "gt_boxes must be 16-byte aligned");
+    MatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.dets = dets;
+    p.det_counts = det_counts;
+    p.max_det = max_det;
+    p.row_len = row_len;
+    p.gt_boxes = gt_boxes;
+    p.gt_cls = gt_cls;
+    p.gt_counts = gt_counts;
+    p.max_gt = max_gt;
+    for (int i = 0; i < n_thr; ++i) p.iouv[i] = iouv[i];
+    p.n_thr = n_thr;
+    p.correct = correct;
+    p.matched_gt = matched_gt;
+    p.tag_thr = tag_thr;
+    const size_t smem = static_cast<size_t>(max_det) * 8 + static_cast<size_t>(max_gt) * 4;
+    if (smem > 200 * 1024) return fail(SARPOST_EUNSUPPORTED, "max_det/max_gt too large for one CTA");
+    CUDA_TRY(cudaFuncSetAttribute(k6_match, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k6_match<<<batch, kMatchThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return SARPOST_OK;

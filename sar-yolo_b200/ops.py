@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import Head, NmsParams, lib
 
-__all__ = ["HeadSpec", "non_max_suppression", "decode", "postprocess_fused", "merge_tiles", "gather_extras", "postprocess_host",
+__all__ = ["HeadSpec", "non_max_suppression", "decode", "postprocess_fused", "merge_tiles", "gather_extras", "match_predictions", "postprocess_host",
            "HostContext", "last_launch_count", "stage_timing", "stage_times"]
 
 
@@ -397,6 +397,40 @@ def merge_tiles(dets: torch.Tensor, det_counts: torch.Tensor, origins: torch.Ten
         n = [r.shape[0] for r in rows]
         return rows, [kidx[b, : n[b]] for b in range(nf)]
     return rows
+
+
+def match_predictions(dets: torch.Tensor, det_counts: torch.Tensor, gt_boxes: torch.Tensor, gt_cls: torch.Tensor,
+                      gt_counts: torch.Tensor, iouv: Sequence[float] = tuple(0.5 + 0.05 * i for i in range(10)),
+                      tag_threshold_index: Optional[int] = None):
+    """Batched validator matching on the GPU: `box_iou` (utils/metrics.py:55-75) + `match_predictions`
+    (engine/validator.py:222-262, `use_scipy=False`) for every image of the batch in one launch, no host copies.
+      dets (B, max_det, row_len>=6) padded detections, det_counts (B,), gt_boxes (B, max_gt, 4) xyxy,
+      gt_cls (B, max_gt), gt_counts (B,)
+    Returns `correct (B, max_det, len(iouv))` bool; with `tag_threshold_index` also `matched_gt (B, max_det)` int32 —
+    the label index each detection matched at that threshold or -1 (JDE: `true_tags[matched_gt]`, jde/val.py:731-735)."""
+    _require_cuda(dets, "dets")
+    dev = dets.device
+    dets = dets.float().contiguous()
+    bsz, max_det, row_len = (int(v) for v in dets.shape)
+    gt_boxes = gt_boxes.to(device=dev, dtype=torch.float32).contiguous()
+    max_gt = int(gt_boxes.shape[1])
+    if max_gt == 0:
+        correct = torch.zeros((bsz, max_det, len(iouv)), dtype=torch.bool, device=dev)
+        return (correct, torch.full((bsz, max_det), -1, dtype=torch.int32, device=dev)) if tag_threshold_index is not None else correct
+    gt_cls = gt_cls.to(device=dev, dtype=torch.float32).contiguous()
+    det_counts = det_counts.to(device=dev, dtype=torch.int32).contiguous()
+    gt_counts = gt_counts.to(device=dev, dtype=torch.int32).contiguous()
+    thr = (C.c_float * len(iouv))(*[float(v) for v in iouv])
+    correct = torch.empty((bsz, max_det, len(iouv)), dtype=torch.uint8, device=dev)
+    matched = torch.empty((bsz, max_det), dtype=torch.int32, device=dev) if tag_threshold_index is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.sarpost_match_predictions(dets.data_ptr(), det_counts.data_ptr(), bsz, max_det, row_len,
+                                                 gt_boxes.data_ptr(), gt_cls.data_ptr(), gt_counts.data_ptr(), max_gt, thr,
+                                                 len(iouv), correct.data_ptr(), matched.data_ptr() if matched is not None else None,
+                                                 int(tag_threshold_index) if tag_threshold_index is not None else -1,
+                                                 _stream_ptr(dev)))
+    correct = correct.bool()
+    return (correct, matched) if matched is not None else correct
 
 
 class HostContext:

@@ -476,3 +476,34 @@ def test_fused_configuration_sweep(sarpost, cuda, imgsz, strides, nc, bs, kw):
     y = sarpost.decode(levels, spec).cpu()
     ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=nc, return_index=True, **kw)
     _assert_same(rows, idx, ref_rows, ref_idx, nc)
+
+
+def test_match_predictions_gpu(sarpost, cuda):
+    """§8f row 3: batched box_iou + match_predictions on the GPU vs the numpy restatement (tie-free inputs)."""
+    from test_oracle import _match_case
+    iouv = torch.linspace(0.5, 0.95, 10)
+    cases = [_match_case(s, n_det=n, n_gt=m) for s, n, m in ((0, 120, 40), (1, 300, 7), (2, 5, 60), (3, 0, 10), (4, 50, 0))]
+    max_det, max_gt = 300, 64
+    dets = torch.zeros(len(cases), max_det, 8)
+    gtb = torch.zeros(len(cases), max_gt, 4)
+    gtc = torch.zeros(len(cases), max_gt)
+    dn, gn = [], []
+    for i, (d, g, c) in enumerate(cases):
+        dets[i, : d.shape[0], :6] = d
+        gtb[i, : g.shape[0]] = g
+        gtc[i, : g.shape[0]] = c
+        dn.append(d.shape[0]); gn.append(g.shape[0])
+    correct, matched = sarpost.match_predictions(dets.to(cuda), torch.tensor(dn), gtb.to(cuda), gtc.to(cuda), torch.tensor(gn),
+                                                 iouv.tolist(), tag_threshold_index=0)
+    assert correct.shape == (len(cases), max_det, 10) and correct.dtype == torch.bool
+    for i, (d, g, c) in enumerate(cases):
+        n = d.shape[0]
+        if n == 0 or g.shape[0] == 0:
+            assert not bool(correct[i].any())
+            continue
+        iou = R.box_iou_ref(g, d[:, :4])
+        ref, ref_m = R.match_predictions_ref(d[:, 5], c, iou, iouv, tag_thr=iouv[0].item())
+        assert torch.equal(correct[i, :n].cpu(), ref), f"case {i}"
+        assert not bool(correct[i, n:].any())
+        assert torch.equal(matched[i, :n].cpu(), ref_m)
+        assert ref.any()

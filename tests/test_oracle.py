@@ -118,3 +118,39 @@ def test_scale_boxes_ref_matches_live_reference():
     b = torch.rand(500, 4, generator=g) * 700 - 30
     for img1, img0 in [((384, 640), (1080, 1920, 3)), ((640, 640), (3000, 4000, 3)), ((1280, 1280), (480, 640))]:
         assert torch.equal(R.scale_boxes_ref(img1, b, img0), ops.scale_boxes(img1, b.clone(), img0))
+
+
+def _match_case(seed, n_det=120, n_gt=40, nc=3):
+    g = torch.Generator().manual_seed(seed)
+    gxy = torch.rand(n_gt, 2, generator=g) * 500
+    gwh = 20 + torch.rand(n_gt, 2, generator=g) * 100
+    gt = torch.cat((gxy, gxy + gwh), 1)
+    gcls = torch.randint(0, nc, (n_gt,), generator=g).float()
+    if n_gt == 0:
+        xy = torch.rand(n_det, 2, generator=g) * 500
+        det = torch.cat((xy, xy + 50), 1)
+        dcls = torch.randint(0, nc, (n_det,), generator=g).float()
+    else:
+        src = torch.randint(0, n_gt, (n_det,), generator=g)
+        det = gt[src] + torch.randn(n_det, 4, generator=g) * 8   # jittered copies of labels: many competing matches
+        dcls = torch.where(torch.rand(n_det, generator=g) < 0.8, gcls[src], torch.randint(0, nc, (n_det,), generator=g).float())
+    conf = torch.rand(n_det, generator=g).sort(descending=True).values
+    dets = torch.cat((det, conf[:, None], dcls[:, None]), 1)
+    return dets, gt, gcls
+
+
+def test_match_predictions_ref_matches_live_reference():
+    import types
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ref_shim.load()
+    import ultralytics.engine.validator as V
+    import ultralytics.utils.metrics as M
+    iouv = torch.linspace(0.5, 0.95, 10)
+    for seed in range(4):
+        dets, gt, gcls = _match_case(seed)
+        iou = M.box_iou(gt, dets[:, :4])
+        assert torch.equal(iou, R.box_iou_ref(gt, dets[:, :4]))
+        ref = V.BaseValidator.match_predictions(types.SimpleNamespace(iouv=iouv), dets[:, 5], gcls, iou)
+        assert torch.equal(ref, R.match_predictions_ref(dets[:, 5], gcls, iou, iouv))
