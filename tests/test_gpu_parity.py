@@ -507,3 +507,38 @@ def test_match_predictions_gpu(sarpost, cuda):
         assert not bool(correct[i, n:].any())
         assert torch.equal(matched[i, :n].cpu(), ref_m)
         assert ref.any()
+
+
+def test_reentrant_from_two_threads_and_streams(sarpost, cuda):
+    """SURVEY §8b threading: different predictor objects may run on different Python threads / streams.
+    No global mutable state: concurrent calls must give exactly the single-threaded results."""
+    import threading
+    strides = (8, 16, 32)
+    shapes = sarpost.synth.level_shapes(320, strides)
+    spec = sarpost.HeadSpec(nc=2, strides=strides, embed_dim=8, state_classes=0)
+    inputs = [[x.to(cuda) for x in sarpost.synth.head_outputs(3, shapes, 2, 8, 0, seed=70 + i)] for i in range(2)]
+    kws = [dict(conf_thres=0.25, iou_thres=0.7), dict(conf_thres=0.01, iou_thres=0.5, multi_label=True, max_det=150)]
+    expect = [sarpost.postprocess_fused(inputs[i], spec, **kws[i]) for i in range(2)]
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(25):
+                    rows = sarpost.postprocess_fused(inputs[i], spec, **kws[i])
+                    for a, b in zip(rows, expect[i]):
+                        if not torch.equal(a, b):
+                            errors.append(f"thread {i}: mismatch")
+                            return
+            s.synchronize()
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"thread {i}: {e!r}")
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
