@@ -208,7 +208,7 @@ int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, co
         CUDA_TRY(cudaEventSynchronize(c->ev_done[k]));
         if (nm == 0) continue;
         const int64_t n_rows = static_cast<int64_t>(nb) * max_det;
-#pragma omp parallel for schedule(static) num_threads(8)
+#pragma omp parallel for schedule(static) num_threads(8) if (n_rows >= 64)
         for (int64_t q = 0; q < n_rows; ++q) {
             const int b = b0 + static_cast<int>(q / max_det), r = static_cast<int>(q % max_det);
             if (r >= hc[b]) continue;
