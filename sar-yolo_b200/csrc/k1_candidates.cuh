@@ -114,9 +114,32 @@ __device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, u
     int cnt = 0;
     float best = 0.0f;
     int bj = 0;
+    // multi-label with few classes (the SAR posture heads have nc = 6): every probability is evaluated once and
+    // kept in registers across the block scan; larger heads re-evaluate in the write loop
+    constexpr int kClsCache = 8;
+    float pc[kClsCache];
+    uint32_t pass = 0u;
+    const bool cached = f.multi_label && nc <= kClsCache;
+    float tmax = 0.0f;  // largest candidate score of the tile (lets the selection scan skip whole tiles)
     if (valid) {
-        if (f.multi_label) {
-            for (int j = 0; j < nc; ++j) cnt += (score(j) > f.conf) && cls_allowed(f, j);
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < kClsCache; ++j) {
+                pc[j] = j < nc ? score(j) : 0.0f;
+                if (j < nc && (pc[j] > f.conf) && cls_allowed(f, j)) {
+                    pass |= 1u << j;
+                    tmax = fmaxf(tmax, pc[j]);
+                }
+            }
+            cnt = __popc(pass);
+        } else if (f.multi_label) {
+            for (int j = 0; j < nc; ++j) {
+                const float p = score(j);
+                if ((p > f.conf) && cls_allowed(f, j)) {
+                    ++cnt;
+                    tmax = fmaxf(tmax, p);
+                }
+            }
         } else {
             best = score(0);
             for (int j = 1; j < nc; ++j) {
@@ -124,18 +147,7 @@ __device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, u
                 if (p > best) { best = p; bj = j; }  // strict >: first max wins (ops.py:274)
             }
             cnt = (best > f.conf) && cls_allowed(f, bj);
-        }
-    }
-    // largest candidate score of the tile (lets the selection scan skip whole tiles)
-    float tmax = 0.0f;
-    if (cnt) {
-        if (f.multi_label) {
-            for (int j = 0; j < nc; ++j) {
-                const float p = score(j);
-                if ((p > f.conf) && cls_allowed(f, j)) tmax = fmaxf(tmax, p);
-            }
-        } else {
-            tmax = best;
+            tmax = cnt ? best : 0.0f;
         }
     }
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(tmax, 0.0f)));
@@ -166,7 +178,18 @@ __device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, u
     int32_t *hist = st.hist + static_cast<int64_t>(b) * kBuckets;
     const bool sampled = (anchor % kHistSample) == 0;  // 1-in-8 sample keeps the RED traffic negligible
     if (cnt) {
-        if (f.multi_label) {
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < kClsCache; ++j) {
+                if ((pass >> j) & 1u) {
+                    st.box[pos] = xyxy;
+                    st.score[pos] = pc[j];
+                    st.key[pos] = anchor * static_cast<uint32_t>(nc) + static_cast<uint32_t>(j);
+                    if (sampled) atomicAdd(hist + score_bucket(__float_as_uint(pc[j])), 1);
+                    ++pos;
+                }
+            }
+        } else if (f.multi_label) {
             for (int j = 0; j < nc; ++j) {
                 const float p = score(j);
                 if ((p > f.conf) && cls_allowed(f, j)) {
