@@ -6,10 +6,11 @@
 //
 // Greedy NMS compares a candidate only with boxes KEPT before it, and stops at max_det keeps — so at
 // most n*max_det pair tests are needed, not n^2/2, and usually only the head of the sorted order is
-// ever looked at.  One CTA per image (selection scheme: k2_select_sort.cuh):
-//   select    the per-image score histogram written by K1 is scanned from the top; the next run of
-//             whole score buckets that fits shared memory is collected by streaming the image's
-//             candidate scores once, and sorted there (bitonic network on the 64-bit composite
+// ever looked at.  One CTA (or one cluster of CTAs, below) per image; selection scheme in k2_select_sort.cuh:
+//   select    the per-image SAMPLED score histogram written by K1 is scanned from the top to size the next
+//             run of whole score buckets (estimates only steer the size; membership is exact); the run is
+//             collected by streaming the image's candidate scores once (tiles whose best score is below
+//             the run are skipped), and sorted in shared memory (bitonic network on the 64-bit composite
 //             score|~slot = descending score, source order on ties); a single bucket larger than that
 //             falls back to a stable LSD radix sort in global memory;
 //   phase 1   a sub-chunk of <= 256 sorted candidates is tested against the kept list (smem);
@@ -50,7 +51,7 @@ constexpr int kSortCap = 1024;   // candidates sorted in shared memory at once
 constexpr int kSub = 256;        // candidates per NMS sub-chunk
 constexpr int kSubWords = kSub / 32;
 
-// Where the extras columns of an output row live (K5 gathers them; K4 prefetches them into L2).
+// Where the extras columns of an output row live (gathered by K5 for the kept rows only).
 struct ExtrasSrc {
     int32_t mode;               // 0 decoded prediction, 1 raw level tensors, 2 source detection rows (merge)
     int32_t nm, nc;

@@ -4,6 +4,8 @@
 //   K2/K3/K4        k4_nms: histogram scan, lazy top-k selection + sort, NMS  (k2_select_sort.cuh, k4_nms.cuh)
 //   K5 gather       k5_gather                                                (k4_nms.cuh)
 //
+//   K6 matching     k6_match: batched box_iou + match_predictions (validator)  (k6_match.cuh)
+//
 // No torch types, no exceptions across the ABI, no global mutable state (thread-local error string and
 // instrumentation only).
 #include <cmath>
