@@ -214,7 +214,8 @@ int32_t sarpost_host_ctx_last_traffic(const sarpost_host_ctx_t *ctx, int64_t *h2
  * milliseconds for {K1 candidates (incl. histogram memset), K2-K4 select+sort+NMS, K5 gather, whole call}.
  */
 int32_t sarpost_last_launch_count(void);
-int32_t sarpost_set_stage_timing(int32_t enabled);
+int32_t sarpost_set_stage_timing(int32_t enabled); /* 0 off, 1 time the last call, 2 accumulate: sarpost_stage_times
+                                                      then returns the MEAN over all calls since it was enabled / last read */
 int32_t sarpost_stage_times(float *ms4);
 
 #ifdef __cplusplus

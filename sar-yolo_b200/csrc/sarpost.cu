@@ -28,8 +28,9 @@ namespace sarpost {
 // ------------------------------------------------------------------------------------------------
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
-thread_local int g_timing = 0;
-thread_local cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+thread_local int g_timing = 0;  // 0 off, 1 time the last call, 2 accumulate every call until read
+thread_local std::vector<cudaEvent_t> g_ev;  // 5 events per timed call: start, hist ready, K1, NMS, gather
+thread_local int g_ev_calls = 0;             // complete event sets recorded (mode 1 keeps only the last)
 thread_local int g_ev_valid = 0;
 
 static int fail(int code, const char *fmt, ...) {
@@ -49,10 +50,16 @@ static int fail(int code, const char *fmt, ...) {
 
 static void stage_mark(int i, cudaStream_t s) {
     if (!g_timing) return;
-    if (!g_ev[0])
-        for (auto &e : g_ev) cudaEventCreate(&e);
-    cudaEventRecord(g_ev[i], s);
+    if (i == 0 && g_timing == 1) g_ev_calls = 0;  // mode 1: overwrite the single set
+    const size_t at = static_cast<size_t>(g_ev_calls) * 5 + i;
+    while (g_ev.size() <= at) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        g_ev.push_back(e);
+    }
+    cudaEventRecord(g_ev[at], s);
     g_ev_valid = i;
+    if (i == 4) ++g_ev_calls;
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -405,17 +412,30 @@ int32_t sarpost_version(void) { return SARPOST_VERSION; }
 int32_t sarpost_last_launch_count(void) { return g_launches; }
 
 int32_t sarpost_set_stage_timing(int32_t enabled) {
-    g_timing = enabled ? 1 : 0;
+    g_timing = enabled == 2 ? 2 : (enabled ? 1 : 0);
     g_ev_valid = 0;
+    g_ev_calls = 0;
     return SARPOST_OK;
 }
 
 int32_t sarpost_stage_times(float *ms4) {
     if (!ms4) return fail(SARPOST_EINVAL, "ms4 is NULL");
-    if (!g_timing || g_ev_valid != 4) return fail(SARPOST_EINVAL, "no timed call recorded on this thread");
-    CUDA_TRY(cudaEventSynchronize(g_ev[4]));
-    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventElapsedTime(&ms4[i], g_ev[i + 1], g_ev[i + 2]));
-    CUDA_TRY(cudaEventElapsedTime(&ms4[3], g_ev[0], g_ev[4]));
+    if (!g_timing || g_ev_calls < 1) return fail(SARPOST_EINVAL, "no timed call recorded on this thread");
+    // mode 1: the last call; mode 2: the MEAN over every call since timing was enabled / last read
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    CUDA_TRY(cudaEventSynchronize(g_ev[static_cast<size_t>(g_ev_calls - 1) * 5 + 4]));
+    for (int c = 0; c < g_ev_calls; ++c) {
+        const cudaEvent_t *e = &g_ev[static_cast<size_t>(c) * 5];
+        float v;
+        for (int i = 0; i < 3; ++i) {
+            CUDA_TRY(cudaEventElapsedTime(&v, e[i + 1], e[i + 2]));
+            acc[i] += v;
+        }
+        CUDA_TRY(cudaEventElapsedTime(&v, e[0], e[4]));
+        acc[3] += v;
+    }
+    for (int i = 0; i < 4; ++i) ms4[i] = acc[i] / static_cast<float>(g_ev_calls);
+    g_ev_calls = 0;
     return SARPOST_OK;
 }
 

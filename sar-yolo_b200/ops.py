@@ -495,8 +495,10 @@ def last_launch_count() -> int:
     return int(lib.sarpost_last_launch_count())
 
 
-def stage_timing(enabled: bool) -> None:
-    _lib.check(lib.sarpost_set_stage_timing(int(bool(enabled))))
+def stage_timing(enabled, accumulate: bool = False) -> None:
+    """Per-stage CUDA events inside the library.  `accumulate=True`: `stage_times()` returns the mean over every
+    call since (no host sync per call) — used by bench.py to time K1 inside the timed region itself."""
+    _lib.check(lib.sarpost_set_stage_timing(2 if (enabled and accumulate) else int(bool(enabled))))
 
 
 def stage_times() -> Tuple[float, float, float, float]:
