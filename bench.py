@@ -54,8 +54,9 @@ def parse_args():
     ap.add_argument("--impl", default="sarpost", choices=["sarpost", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
-    ap.add_argument("--streams", type=int, default=2,
-                    help="CUDA streams the timed steps are issued on round-robin: 2 (default) = two independent batches "
+    ap.add_argument("--streams", type=int, default=0,
+                    help="CUDA streams the timed steps are issued on round-robin: 0 (default) = 2 for batches of >= 8 images, "
+                         "else 1 (tiny batches are launch-bound and gain nothing); 2 = two independent batches "
                          "in flight, each with its own input buffers (the NMS kernel of one batch overlaps the fused "
                          "decode of the next); 1 = strictly one batch in flight.  The single-stream figure is always "
                          "measured too and reported as `single_stream`.")
@@ -221,6 +222,8 @@ def main():
 
     imgsz, strides, nc, ed, sc, bs, kw, cls_mean, desc = WORKLOADS[args.workload]
     bs = args.batch or bs
+    if args.streams <= 0:
+        args.streams = 2 if bs >= 8 else 1
     sahi = args.workload == "cfg4"
     scaling = "weak"
     if sahi:  # strong scaling: a fixed total of tiles is sharded over the ranks
