@@ -3,7 +3,7 @@ import csv,sys,subprocess,re,collections,os,glob
 rep=sys.argv[1]; kern=sys.argv[2]; topn=int(sys.argv[3]) if len(sys.argv)>3 else 25
 # kern is matched against the MANGLED section name in the cubin (e.g. k4_nmsILi4E for k4_nms<4>); the ncu filter
 # uses the plain function name in front of the template suffix
-ncu_kern=re.split(r"I[A-Z0-9]", kern)[0] if re.search(r"I(Li\d+|f|6__half)E", kern) else kern
+ncu_kern=re.sub(r"I(Li\d+|f|6__half)E.*$", "", kern)
 so="/root/repo/sar-yolo_b200/libsarpost.so"
 wd="/tmp/probe/cubin"; os.makedirs(wd,exist_ok=True)
 for f in glob.glob(wd+"/*.cubin"): os.remove(f)
