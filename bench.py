@@ -25,6 +25,23 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+def ensure_built():
+    """libsarpost.so normally exists (the driver runs __graft_entry__.build()); build it if a fresh checkout lacks it.
+    Under torchrun only local rank 0 compiles, the others wait for the file."""
+    lib = os.path.join(ROOT, "sar-yolo_b200", "libsarpost.so")
+    if os.path.exists(lib):
+        return
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        import __graft_entry__ as g
+
+        g.build()
+    else:
+        t0 = time.time()
+        while not os.path.exists(lib) and time.time() - t0 < 600:
+            time.sleep(1.0)
+        time.sleep(2.0)
+
 WORKLOADS = {
     # name: (imgsz, strides, nc, embed_dim, state_classes, per-GPU batch, nms kwargs, cls_mean, description)
     "cfg3": (1280, (4, 8, 16, 32), 1, 256, 6, 16,
@@ -191,6 +208,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    ensure_built()
     if args.impl == "reference":
         return run_reference_arm(args)
     if args.quick:
