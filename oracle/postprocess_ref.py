@@ -8,8 +8,7 @@ tests/test_oracle.py against golden vectors written by the live reference).
 from __future__ import annotations
 
 import ctypes
-import os
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch

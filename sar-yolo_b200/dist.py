@@ -10,7 +10,7 @@ Works with backend "nccl" (GPU) and "gloo" (CPU tensors, used by the host-logic 
 """
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import Tuple
 
 import torch
 import torch.distributed as dist

@@ -10,7 +10,6 @@ reference function that was saved at patch time — never to a re-implementation
 from __future__ import annotations
 
 import importlib
-from typing import Optional
 
 from . import head as _head
 from . import ops as _ops
