@@ -137,3 +137,31 @@ def test_allgather_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_patch_on_live_reference_modules(sarpost):
+    """With the real reference modules (build container only): patch() swaps the three attributes the call sites
+    resolve at call time, CPU calls still reach the reference's own code (identical results), unpatch() restores."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ops, _, head = ref_shim.load()
+    orig_nms, orig_det, orig_jde = ops.non_max_suppression, head.Detect._inference, head.JDE._inference
+    y = sarpost.synth.decoded_prediction(2, 500, 3, 2, seed=4)
+    want = orig_nms(y.clone(), 0.25, 0.6, nc=3)
+    shapes = sarpost.synth.level_shapes(64, (8, 16, 32))
+    levels = sarpost.synth.head_outputs(1, shapes, 1, 16, 6, seed=5)
+    m = head.JDE(nc=1, embed_dim=16, state_classes=6, ch=(64, 64, 64))
+    m.stride = torch.tensor([8.0, 16.0, 32.0])
+    m.eval()
+    want_y = m._inference([x.clone() for x in levels])
+    sarpost.patch()
+    try:
+        assert ops.non_max_suppression is not orig_nms and head.JDE._inference is not orig_jde
+        got = ops.non_max_suppression(y.clone(), 0.25, 0.6, nc=3)          # CPU tensor -> reference code path
+        assert all(torch.equal(a, b) for a, b in zip(got, want))
+        m.shape = None
+        assert torch.equal(m._inference([x.clone() for x in levels]), want_y)  # CPU levels -> reference decode
+    finally:
+        sarpost.unpatch()
+    assert ops.non_max_suppression is orig_nms and head.Detect._inference is orig_det and head.JDE._inference is orig_jde
