@@ -90,6 +90,8 @@ typedef struct sarpost_nms_params {
     int32_t *peer_counts[8]; /* each (total_images) */
     int32_t n_peers;
     int32_t peer_slot_offset;
+    int32_t prediction_dtype;/* sarpost_nms_decoded only: element type of `prediction`, SARPOST_F32 or SARPOST_F16 (the `y` of a
+                              `half=True` model); fp16 values are upcast exactly, arithmetic and output rows stay fp32 */
     int32_t workspace_clean;/* 0: the call zeroes the score-histogram head of the workspace itself (one memset node).
                               1: the caller guarantees the first sarpost_workspace_clean_bytes(batch) bytes are zero —
                               true after sarpost_workspace_prepare and after every successful call that used the
@@ -132,7 +134,7 @@ int32_t sarpost_decode(const sarpost_head_t *head, void *y, void *stream);
  *   kept_index device (B, max_det) int32 or NULL: anchor*nc + class of every output row
  * The input is not modified (the reference rewrites prediction[..., :4] in place, ops.py:243-244).
  */
-int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t channels, int64_t anchors,
+int32_t sarpost_nms_decoded(const void *prediction, int32_t batch, int32_t channels, int64_t anchors,
                             int32_t nc, const sarpost_nms_params_t *params, float *out, int32_t *counts,
                             int32_t *kept_index, void *workspace, int64_t workspace_bytes, void *stream);
 

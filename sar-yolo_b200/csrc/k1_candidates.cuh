@@ -332,24 +332,25 @@ __global__ void __launch_bounds__(kTileA) k1_fused_ldg(const __grid_constant__ K
 // ops.non_max_suppression receives (ops.py:167).  grid = (ceil(A/kTileA), B).
 // ---------------------------------------------------------------------------------------------
 struct K1DecodedParams {
-    const float *pred;
+    const void *pred;  // float or __half (kernel template parameter)
     int32_t channels, nc;
     int64_t anchors;
     CandFilter f;
     CandStore st;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(kTileA) k1_decoded(const __grid_constant__ K1DecodedParams p) {
     __shared__ int scratch[8];
     const int r = blockIdx.x, b = blockIdx.y;
     const int64_t a = static_cast<int64_t>(r) * kTileA + threadIdx.x;
     const bool valid = a < p.anchors;
     const int64_t ac = valid ? a : p.anchors - 1;
-    const float *base = p.pred + static_cast<int64_t>(b) * p.channels * p.anchors + ac;
-    const float4 xywh = make_float4(__ldg(base), __ldg(base + p.anchors), __ldg(base + 2 * p.anchors),
-                                    __ldg(base + 3 * p.anchors));
+    const T *base = static_cast<const T *>(p.pred) + static_cast<int64_t>(b) * p.channels * p.anchors + ac;
+    const float4 xywh = make_float4(to_f32(__ldg(base)), to_f32(__ldg(base + p.anchors)), to_f32(__ldg(base + 2 * p.anchors)),
+                                    to_f32(__ldg(base + 3 * p.anchors)));
     const float4 xyxy = xywh2xyxy_rn(xywh);
-    auto score = [&](int j) { return __ldg(base + static_cast<int64_t>(4 + j) * p.anchors); };
+    auto score = [&](int j) { return to_f32(__ldg(base + static_cast<int64_t>(4 + j) * p.anchors)); };
     emit_candidates(valid, xyxy, static_cast<uint32_t>(ac), p.nc, p.f, score, p.st, b, r, scratch);
 }
 

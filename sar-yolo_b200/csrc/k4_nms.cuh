@@ -56,7 +56,7 @@ struct ExtrasSrc {
     int32_t mode;               // 0 decoded prediction, 1 raw level tensors, 2 source detection rows (merge)
     int32_t nm, nc;
     // mode 0
-    const float *pred;
+    const void *pred;
     int32_t channels;
     int64_t anchors;
     // mode 1
@@ -64,7 +64,7 @@ struct ExtrasSrc {
     int32_t lvl_aoff[kMaxLevels + 1];
     int32_t lvl_hw[kMaxLevels];
     const void *lvl_ptr[kMaxLevels];
-    int32_t is_half;            // element type of the level tensors (mode 1)
+    int32_t is_half;            // element type of the level tensors (mode 1) / of the prediction (mode 0)
     // mode 2
     const float *dets;
     int32_t dets_per_tile, row_len;
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
         int64_t stride;
         const void *base;
         const int64_t at = extras_base(p.ex, b, anchor, &stride, &base);
-        const bool hf = p.ex.mode == 1 && p.ex.is_half;
+        const bool hf = p.ex.is_half != 0;
         const int n_raw = p.ex.mode == 0 ? p.ex.nm : p.ex.n_extra_raw;  // a decoded prediction is copied verbatim
         for (int c = lane; c < p.ex.nm; c += 32) {
             float v = load_elem(base, at + c * stride, hf);

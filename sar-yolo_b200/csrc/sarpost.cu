@@ -481,7 +481,7 @@ int32_t sarpost_decode(const sarpost_head_t *head, void *y, void *stream) {
     return SARPOST_OK;
 }
 
-int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t channels, int64_t anchors, int32_t nc,
+int32_t sarpost_nms_decoded(const void *prediction, int32_t batch, int32_t channels, int64_t anchors, int32_t nc,
                             const sarpost_nms_params_t *params, float *out, int32_t *counts, int32_t *kept_index,
                             void *workspace, int64_t workspace_bytes, void *stream) {
     g_launches = 0;
@@ -513,7 +513,10 @@ int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t chan
     kp.anchors = anchors;
     kp.f = f;
     kp.st = P.st;
-    k1_decoded<<<dim3(static_cast<unsigned>(tpi_anchor), batch), kTileA, 0, s>>>(kp);
+    const bool pred_half = params->prediction_dtype == SARPOST_F16;
+    if (params->prediction_dtype != SARPOST_F32 && !pred_half) return fail(SARPOST_EUNSUPPORTED, "prediction_dtype %d unsupported", params->prediction_dtype);
+    if (pred_half) k1_decoded<__half><<<dim3(static_cast<unsigned>(tpi_anchor), batch), kTileA, 0, s>>>(kp);
+    else k1_decoded<float><<<dim3(static_cast<unsigned>(tpi_anchor), batch), kTileA, 0, s>>>(kp);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     if (with_labels) {
@@ -540,6 +543,7 @@ int32_t sarpost_nms_decoded(const float *prediction, int32_t batch, int32_t chan
     ex.pred = prediction;
     ex.channels = channels;
     ex.anchors = anchors;
+    ex.is_half = pred_half ? 1 : 0;
     return run_tail(P, batch, params, nc, ex, out, counts, kept_index, s);
 }
 

@@ -222,7 +222,8 @@ def non_max_suppression(
         return output
 
     in_dtype = prediction.dtype
-    pred = prediction if in_dtype == torch.float32 else prediction.float()
+    # fp32 and fp16 (`half=True` models) are read as they are; anything else is upcast first
+    pred = prediction if in_dtype in (torch.float32, torch.float16) else prediction.float()
     pred = pred.contiguous()
     bs, ch, na = (int(s) for s in pred.shape)
     nc = int(nc) or (ch - 4)  # number of classes (ops.py:231)
@@ -233,6 +234,7 @@ def non_max_suppression(
         return (empty, [torch.zeros((0,), dtype=torch.int32, device=dev)] * bs) if return_index else empty
 
     params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+    params.prediction_dtype = 1 if pred.dtype == torch.float16 else 0
     n_lab = 0
     if has_labels:  # apriori labels for autolabelling (ops.py:256-261): padded (B, L, 5) cls,x,y,w,h + counts
         if len(labels) != bs:

@@ -542,3 +542,18 @@ def test_reentrant_from_two_threads_and_streams(sarpost, cuda):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_nms_decoded_fp16_prediction(sarpost, cuda):
+    """`half=True` drop-in: a fp16 `y` is read directly (no fp32 copy of the whole tensor); results equal the
+    fp32 path on the exactly upcast tensor, rows come back in the prediction's dtype like the reference."""
+    y32 = sarpost.synth.decoded_prediction(2, 8400, 3, 5, seed=91)
+    y16 = y32.half().to(cuda)
+    kw = dict(conf_thres=0.25, iou_thres=0.7, nc=3)
+    a, ia = sarpost.non_max_suppression(y16, return_index=True, **kw)
+    b, ib = sarpost.non_max_suppression(y16.float(), return_index=True, **kw)
+    for x, y, i, j in zip(a, b, ia, ib):
+        assert x.dtype == torch.float16 and torch.equal(x, y.half()) and torch.equal(i, j)
+    ref = R.non_max_suppression_ref(y16.float().cpu(), **kw)
+    for x, r in zip(b, ref):
+        assert torch.equal(x.cpu(), r)
