@@ -15,6 +15,8 @@
 #include <cstring>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in Nsight tools, no-ops otherwise
+
 #include "common.cuh"
 #include "k1_candidates.cuh"
 #include "k2_select_sort.cuh"
@@ -63,6 +65,12 @@ static void stage_mark(int i, cudaStream_t s) {
 }
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// NVTX range for the host-side span of one entry point / stage (per-stage tracing)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------------------------------------
 // workspace layout
@@ -248,6 +256,7 @@ static int env_int(const char *name, int dflt) {
 // stages
 // ------------------------------------------------------------------------------------------------
 static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandStore &st, cudaStream_t s) {
+    NvtxRange nvtx("sarpost:K1 decode+score+compact");
     const int nch = 4 * kRegMax + g.nc;
     const int esz = g.is_half ? 2 : 4;
     const int64_t stage_bytes = static_cast<int64_t>(nch) * kTileA * esz;
@@ -317,6 +326,7 @@ static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandSto
 // K2 + K4 + K5 on a filled candidate store.
 static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, int nc, const ExtrasSrc &ex, float *out,
                     int32_t *counts, int32_t *kept_index, cudaStream_t s) {
+    NvtxRange nvtx("sarpost:K2-K5 select+sort+nms+gather");
     NmsParams np;
     np.st = P.st;
     np.tmp_key_a = P.key_a;
@@ -549,6 +559,7 @@ int32_t sarpost_nms_decoded(const void *prediction, int32_t batch, int32_t chann
 
 int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *params, float *out, int32_t *counts,
                       int32_t *kept_index, void *workspace, int64_t workspace_bytes, void *stream) {
+    NvtxRange nvtx("sarpost_fused");
     g_launches = 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     HeadGeom g;

@@ -76,3 +76,21 @@ def test_argument_errors_do_not_need_a_gpu(sarpost):
     h.reg_max, h.no = 16, 69  # fewer channels than 4*reg_max + nc
     assert lib.sarpost_decode(C.byref(h), ptr, None) == L.EINVAL and "no 69" in L.last_error()
     assert lib.sarpost_stage_times(None) == L.EINVAL
+
+
+def test_cpp_example_builds_and_links(sarpost, tmp_path):
+    """examples/cpp_host_postprocess.cpp: the C ABI is usable from plain C++ (header compiles as C++, symbols link).
+    Without a GPU the program reports the missing device through the error channel and exits 2."""
+    import subprocess
+    exe = tmp_path / "cpp_host_postprocess"
+    libdir = os.path.dirname(sarpost._lib.LIB_PATH)
+    cmd = ["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "cpp_host_postprocess.cpp"),
+           "-L" + libdir, "-lsarpost", "-Wl,-rpath," + libdir, "-o", str(exe)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe), "1"], capture_output=True, text=True, timeout=120)
+    import torch
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and "detections" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode == 2 and "no usable CUDA device" in run.stderr
