@@ -37,22 +37,28 @@ def _make_inference(kind: str):
     return _inference
 
 
-def patch(ultralytics_ops=None, ultralytics_head=None, decode: bool = True) -> None:
-    """Monkey-patch the reference.  Modules default to the importable `ultralytics` package."""
+def patch(ultralytics_ops=None, ultralytics_head=None, decode: bool = True, fused: bool = False) -> None:
+    """Monkey-patch the reference.  Modules default to the importable `ultralytics` package.
+
+    `fused=False`: API-exact — `_inference` returns the real `y` (decode kernel), `non_max_suppression` runs the
+    decoded-input kernels.  `fused=True`: `_inference` returns a `LazyPrediction` handle and `non_max_suppression`
+    runs the single-pass fused kernels from the raw logits (the unmodified predictor / validator get the fused
+    speed); `y` is materialised only if something else touches it."""
     if _SAVED:
         return
     ops_mod = ultralytics_ops or importlib.import_module("ultralytics.utils.ops")
     _SAVED["ops_mod"] = ops_mod
     _SAVED["nms"] = ops_mod.non_max_suppression
-    ops_mod.non_max_suppression = _nms_dispatch
-    if decode:
+    ops_mod.non_max_suppression = _nms_dispatch_fused if fused else _nms_dispatch
+    if decode or fused:
+        make = _make_lazy_inference if fused else _make_inference
         head_mod = ultralytics_head or importlib.import_module("ultralytics.nn.modules.head")
         _SAVED["head_mod"] = head_mod
         _SAVED["detect"] = head_mod.Detect._inference
-        head_mod.Detect._inference = _make_inference("detect")
+        head_mod.Detect._inference = make("detect")
         if hasattr(head_mod, "JDE"):
             _SAVED["jde"] = head_mod.JDE._inference
-            head_mod.JDE._inference = _make_inference("jde")
+            head_mod.JDE._inference = make("jde")
 
 
 def unpatch() -> None:
@@ -83,3 +89,76 @@ def fused_postprocess(preds, head_module, img_shape=None, orig_shapes=None, **nm
     if img_shape is not None and orig_shapes is not None:  # fold predict.py:49 (scale_boxes + clip) into the gather
         nms_kwargs["scale_to"] = (tuple(img_shape), [tuple(s) for s in orig_shapes])
     return _ops.postprocess_fused(levels, spec, **nms_kwargs)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused drop-in: patch(fused=True)
+# ---------------------------------------------------------------------------------------------------------------
+import torch  # noqa: E402
+
+
+class LazyPrediction(torch.Tensor):
+    """What the patched `_inference` returns under `patch(fused=True)`: a tensor-shaped handle on the raw level
+    logits.  The patched `ops.non_max_suppression` recognises it and runs the fused kernels straight from the
+    logits, so the `(B, 4+nc+nm, A)` tensor `y` (2.3 GB at 1280² P2, batch 16) is never written or read.  Any other
+    use (a torch op, indexing, `.cpu()`, printing) transparently materialises `y` with the decode kernel first
+    (`__torch_dispatch__`), so code that really needs `y` keeps working — it just pays for it."""
+
+    @staticmethod
+    def __new__(cls, levels, spec):
+        b = int(levels[0].shape[0])
+        a = sum(int(x.shape[2]) * int(x.shape[3]) for x in levels)
+        r = torch.Tensor._make_wrapper_subclass(cls, (b, 4 + spec.nc + spec.nm, a), dtype=levels[0].dtype,
+                                                device=levels[0].device, requires_grad=False)
+        r._levels, r._spec, r._y = list(levels), spec, None
+        return r
+
+    def materialize(self) -> torch.Tensor:
+        if self._y is None:
+            self._y = _ops.decode(self._levels, self._spec)
+        return self._y
+
+    def __repr__(self):  # noqa: D105
+        return f"LazyPrediction(shape={tuple(self.shape)}, device={self.device}, materialized={self._y is not None})"
+
+    @classmethod
+    def __torch_dispatch__(cls, func, types, args=(), kwargs=None):
+        def unwrap(v):
+            if isinstance(v, LazyPrediction):
+                return v.materialize()
+            if isinstance(v, (list, tuple)):
+                return type(v)(unwrap(u) for u in v)
+            return v
+
+        return func(*unwrap(args), **{k: unwrap(v) for k, v in (kwargs or {}).items()})
+
+
+def _make_lazy_inference(kind: str):
+    def _inference(self, x):
+        if getattr(self, "export", False) or not x[0].is_cuda or getattr(self, "reg_max", 16) != 16:
+            return _SAVED[kind](self, x)
+        self.shape = x[0].shape
+        return LazyPrediction([xi if xi.dtype in (torch.float32, torch.float16) else xi.float() for xi in x],
+                              _ops.HeadSpec.from_module(self))
+
+    return _inference
+
+
+def _nms_dispatch_fused(prediction, *args, **kwargs):
+    pred = prediction[0] if isinstance(prediction, (list, tuple)) else prediction
+    if isinstance(pred, LazyPrediction):
+        names = ("conf_thres", "iou_thres", "classes", "agnostic", "multi_label", "labels", "max_det", "nc", "max_time_img",
+                 "max_nms", "max_wh", "in_place", "rotated")
+        kw = dict(zip(names, args))
+        kw.update(kwargs)
+        has_labels = bool(kw.get("labels")) and any(len(lb) for lb in kw["labels"])
+        nc = int(kw.get("nc") or 0)
+        if not kw.get("rotated") and not has_labels and nc in (0, pred._spec.nc) and pred._y is None:
+            fused_kw = {k: kw[k] for k in ("conf_thres", "iou_thres", "classes", "agnostic", "multi_label", "max_det",
+                                           "max_nms", "max_wh") if k in kw}
+            rows = _ops.postprocess_fused(pred._levels, pred._spec, **fused_kw)
+            if pred.dtype != torch.float32:
+                rows = [r.to(pred.dtype) for r in rows]  # the reference returns rows in the prediction's dtype
+            return rows
+        prediction = pred.materialize()
+    return _nms_dispatch(prediction, *args, **kwargs)

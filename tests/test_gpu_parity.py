@@ -557,3 +557,51 @@ def test_nms_decoded_fp16_prediction(sarpost, cuda):
     ref = R.non_max_suppression_ref(y16.float().cpu(), **kw)
     for x, r in zip(b, ref):
         assert torch.equal(x.cpu(), r)
+
+
+def test_patch_fused_lazy_prediction(sarpost, cuda):
+    """patch(fused=True): the unmodified call sequence `y = head._inference(x); ops.non_max_suppression(y, ...)`
+    runs the fused kernels; touching `y` in any other way materialises it with the decode kernel."""
+    import types
+
+    class Detect:
+        export = False
+        reg_max = 16
+
+        def __init__(self, nc, stride, embed_dim=0, state_classes=None):
+            self.nc, self.stride, self.embed_dim, self.state_classes = nc, torch.tensor(stride), embed_dim, state_classes
+
+        def _inference(self, x):
+            raise AssertionError("reference decode must not run for CUDA inputs")
+
+    class JDE(Detect):
+        pass
+
+    def ref_nms(*a, **k):
+        raise AssertionError("reference NMS must not run for CUDA inputs")
+
+    ops_mod = types.SimpleNamespace(non_max_suppression=ref_nms)
+    head_mod = types.SimpleNamespace(Detect=Detect, JDE=JDE)
+    strides = (8.0, 16.0, 32.0)
+    shapes = sarpost.synth.level_shapes(320, (8, 16, 32))
+    levels = [x.to(cuda) for x in sarpost.synth.head_outputs(2, shapes, 1, 16, 6, seed=12)]
+    spec = sarpost.HeadSpec(nc=1, strides=strides, embed_dim=16, state_classes=6)
+    want = sarpost.postprocess_fused(levels, spec, conf_thres=0.25, iou_thres=0.7, max_det=100)
+    want_y = sarpost.decode(levels, spec)
+    sarpost.patch(ops_mod, head_mod, fused=True)
+    try:
+        head = JDE(1, strides, 16, 6)
+        y = head._inference(levels)
+        assert isinstance(y, sarpost.plugin.LazyPrediction) and tuple(y.shape) == tuple(want_y.shape) and y.is_cuda
+        # the predictor's call (models/yolo/jde/predict.py:31-39): positional conf/iou, keyword rest, tuple input
+        rows = ops_mod.non_max_suppression((y, levels), 0.25, 0.7, agnostic=False, max_det=100, nc=1, classes=None)
+        assert y._y is None, "y must not have been materialised"
+        for a, b in zip(rows, want):
+            assert torch.equal(a, b)
+        # any other use materialises y transparently
+        assert torch.equal(y[:, :4], want_y[:, :4]) and torch.equal(y + 0, want_y) and y._y is not None
+        rows2 = ops_mod.non_max_suppression(y, 0.25, 0.7, max_det=100, nc=1)  # now the decoded-input kernels
+        for a, b in zip(rows2, want):
+            assert torch.equal(a, b)
+    finally:
+        sarpost.unpatch()

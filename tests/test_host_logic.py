@@ -155,13 +155,14 @@ def test_patch_on_live_reference_modules(sarpost):
     m.stride = torch.tensor([8.0, 16.0, 32.0])
     m.eval()
     want_y = m._inference([x.clone() for x in levels])
-    sarpost.patch()
-    try:
-        assert ops.non_max_suppression is not orig_nms and head.JDE._inference is not orig_jde
-        got = ops.non_max_suppression(y.clone(), 0.25, 0.6, nc=3)          # CPU tensor -> reference code path
-        assert all(torch.equal(a, b) for a, b in zip(got, want))
-        m.shape = None
-        assert torch.equal(m._inference([x.clone() for x in levels]), want_y)  # CPU levels -> reference decode
-    finally:
-        sarpost.unpatch()
+    for fused in (False, True):
+        sarpost.patch(fused=fused)
+        try:
+            assert ops.non_max_suppression is not orig_nms and head.JDE._inference is not orig_jde
+            got = ops.non_max_suppression(y.clone(), 0.25, 0.6, nc=3)          # CPU tensor -> reference code path
+            assert all(torch.equal(a, b) for a, b in zip(got, want))
+            m.shape = None
+            assert torch.equal(m._inference([x.clone() for x in levels]), want_y)  # CPU levels -> reference decode
+        finally:
+            sarpost.unpatch()
     assert ops.non_max_suppression is orig_nms and head.Detect._inference is orig_det and head.JDE._inference is orig_jde
