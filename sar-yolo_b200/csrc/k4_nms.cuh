@@ -378,11 +378,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 if (cand < c_lo + c_n) {
                     const float4 ob = A_BOX[cand];
                     const float oa = s_a_area[cand];
+                    // `dead` counts only verdicts the approximate quotient can be trusted with (not within the
+                    // band around the threshold); if none of those fired and some pair was borderline, every pair
+                    // is re-evaluated with the correctly rounded division
                     bool dead = false, any_border = false;
 #pragma unroll 4
                     for (int k = part; k < kept; k += nparts) {
                         bool bd;
-                        dead |= iou_gt_approx(KEPT_BOX[k], KEPT_AREA[k], ob, oa, p.thr, band, bd);
+                        const bool gt = iou_gt_approx(KEPT_BOX[k], KEPT_AREA[k], ob, oa, p.thr, band, bd);
+                        dead |= gt && !bd;
                         any_border |= bd;
                     }
                     if (any_border && !dead)  // rare: a quotient within a few ulp of the threshold

@@ -605,3 +605,29 @@ def test_patch_fused_lazy_prediction(sarpost, cuda):
             assert torch.equal(a, b)
     finally:
         sarpost.unpatch()
+
+
+def test_borderline_iou_both_directions(sarpost, cuda):
+    """Regression (found by tools/fuzz_parity.py): pairs whose IoU is within the approximate-quotient band of the
+    threshold must be decided by the exact division in BOTH directions — e.g. identical boxes at iou_thres = 1.0
+    (IoU == 1.0 is not > 1.0: nothing is suppressed), also when they meet in phase 1 (candidate vs kept list)."""
+    n = 700  # > one sub-chunk, so later duplicates are tested against the kept list
+    y = torch.zeros(1, 5, n)
+    y[0, :4] = torch.tensor([100.0, 80.0, 37.3, 55.1])[:, None]
+    y[0, 4] = torch.linspace(0.9, 0.3, n)
+    for thr, expect in ((1.0, 300), (0.999999, 1)):
+        kw = dict(conf_thres=0.25, iou_thres=thr)
+        rows, idx, ref_rows, ref_idx = _nms_both(sarpost, y, cuda, **kw)
+        _assert_same(rows, idx, ref_rows, ref_idx, 1)
+        assert rows[0].shape[0] == expect
+
+
+def test_seeded_fuzz(sarpost, cuda):
+    """150 random configurations (decoded / fused, fp32 / fp16, ties, clustered boxes, odd shapes, extreme
+    thresholds) against the oracle; `python tools/fuzz_parity.py 2000 <seed>` runs more."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                               "tools", "fuzz_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(150, 7) == 0
