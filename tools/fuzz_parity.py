@@ -12,8 +12,9 @@ def run(n_cases: int, seed: int) -> int:
   rng = random.Random(seed)
   dev = torch.device("cuda:0")
   bad = 0
+  stats = {}
   for case in range(n_cases):
-      mode = rng.choice(["decoded", "decoded", "fused"])
+      mode = rng.choice(["decoded", "decoded", "fused", "fused", "merge", "labels", "host"])
       nc = rng.choice([1, 1, 2, 3, 6, 9, 17])
       kw = dict(conf_thres=rng.choice([0.0, 0.001, 0.05, 0.25, 0.5, 0.9]), iou_thres=rng.choice([0.0, 0.3, 0.45, 0.6, 0.7, 0.95, 1.0]),
                 agnostic=rng.random() < 0.3, multi_label=rng.random() < 0.4, max_det=rng.choice([1, 7, 100, 300, 1000]),
@@ -22,7 +23,65 @@ def run(n_cases: int, seed: int) -> int:
           kw["classes"] = rng.sample(range(nc), k=rng.randint(0, nc))
       cs = rng.randint(0, 10 ** 6)
       try:
-          if mode == "decoded":
+          if mode == "merge":
+              tpf, d, nf, rl = rng.choice([1, 3, 12, 48]), rng.choice([1, 20, 300]), rng.choice([1, 2, 5]), rng.choice([6, 9])
+              g = torch.Generator().manual_seed(cs)
+              dets = torch.zeros(nf * tpf, d, rl)
+              cnt = torch.randint(0, d + 1, (nf * tpf,), generator=g, dtype=torch.int32)
+              xy = torch.rand(nf * tpf, d, 2, generator=g) * 300
+              dets[..., 0:2] = xy
+              dets[..., 2:4] = xy + 10 + torch.rand(nf * tpf, d, 2, generator=g) * 100
+              sc_ = torch.rand(nf * tpf, d, generator=g)
+              if rng.random() < 0.3:
+                  sc_ = (sc_ * 8).floor() / 8 + 0.05
+              dets[..., 4] = sc_
+              dets[..., 5] = torch.randint(0, nc, (nf * tpf, d), generator=g).float()
+              if rl > 6:
+                  dets[..., 6:] = torch.randn(nf * tpf, d, rl - 6, generator=g)
+              org = (torch.rand(tpf, 2, generator=g) * 400).floor().repeat(nf, 1)
+              mk = dict(iou_thres=kw["iou_thres"], agnostic=kw["agnostic"], max_det=kw["max_det"], max_nms=kw["max_nms"], max_wh=kw["max_wh"])
+              rows, idx = sarpost.merge_tiles(dets.to(dev), cnt.to(dev), org.to(dev), tpf, return_index=True, **mk)
+              ref_rows, ref_idx = [], []
+              for f in range(nf):
+                  cand, src = [], []
+                  for t in range(tpf):
+                      k = f * tpf + t
+                      n_ = int(cnt[k])
+                      r_ = dets[k, :n_].clone()
+                      r_[:, 0] += org[k, 0]; r_[:, 2] += org[k, 0]; r_[:, 1] += org[k, 1]; r_[:, 3] += org[k, 1]
+                      cand.append(r_); src.append(torch.arange(n_) + t * d)
+                  x = torch.cat(cand); srcc = torch.cat(src)
+                  if x.shape[0] > mk["max_nms"]:
+                      o = x[:, 4].argsort(descending=True, stable=True)[: mk["max_nms"]]
+                      x, srcc = x[o], srcc[o]
+                  c_ = x[:, 5:6] * (0 if mk["agnostic"] else mk["max_wh"])
+                  keep = R.nms_ref(x[:, :4] + c_, x[:, 4], mk["iou_thres"])[: mk["max_det"]]
+                  ref_rows.append(x[keep]); ref_idx.append(torch.stack((srcc[keep], torch.zeros_like(srcc[keep])), 1))
+              nc = 1  # kept_index of the merge is tile*dets_per_tile + row
+          elif mode == "labels":
+              bs, na, nm = rng.choice([1, 3]), rng.choice([129, 1000, 4000]), rng.choice([0, 3])
+              y = sarpost.synth.decoded_prediction(bs, na, nc, nm, seed=cs, clustered=rng.random() < 0.5)
+              g = torch.Generator().manual_seed(cs + 1)
+              labels = []
+              for _ in range(bs):
+                  n_ = rng.choice([0, 1, 40, 200])
+                  labels.append(torch.cat((torch.randint(0, nc, (n_, 1), generator=g).float(), torch.rand(n_, 2, generator=g) * 600,
+                                           5 + torch.rand(n_, 2, generator=g) * 90), 1))
+              rows, idx = sarpost.non_max_suppression(y.to(dev), nc=nc, labels=[lb.to(dev) for lb in labels], return_index=True, **kw)
+              ref_rows, ri_ = R.non_max_suppression_ref(y, nc=nc, labels=labels, return_index=True, **kw)
+              ref_idx = [torch.stack((torch.where(r[:, 0] >= 0, r[:, 0], na + (-1 - r[:, 0])), r[:, 1]), 1) for r in ri_]
+          elif mode == "host":
+              strides = rng.choice([(8, 16, 32), (16,)])
+              imgsz = rng.choice([64, 160])
+              bs, ed, sc = rng.choice([1, 5]), rng.choice([0, 4]), rng.choice([0, 6])
+              shapes = sarpost.synth.level_shapes(imgsz, strides)
+              lv = sarpost.synth.head_outputs(bs, shapes, nc, ed, sc, seed=cs, cls_mean=rng.choice([-4.0, 1.0]))
+              spec = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=sc)
+              lvd = lv
+              rows, idx = sarpost.postprocess_host(lv, spec, return_index=True, **kw)
+              y = sarpost.decode([x.to(dev) for x in lv], spec).cpu()
+              ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=nc, return_index=True, **kw)
+          elif mode == "decoded":
               bs, na, nm = rng.choice([1, 2, 5, 40]), rng.choice([1, 31, 128, 129, 1000, 5000, 20000]), rng.choice([0, 0, 3, 40])
               y = sarpost.synth.decoded_prediction(bs, na, nc, nm, seed=cs, clustered=rng.random() < 0.5, score_pow=rng.choice([1.0, 2.0, 4.0]))
               if rng.random() < 0.3:  # quantised scores: heavy ties
@@ -44,6 +103,9 @@ def run(n_cases: int, seed: int) -> int:
               y = sarpost.decode([x.float() for x in lvd], spec).cpu()
               ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=nc, return_index=True, **kw)
           ok = len(rows) == len(ref_rows)
+          st = stats.setdefault(mode, [0, 0])
+          st[0] += 1
+          st[1] += sum(int(r.shape[0]) for r in ref_rows)
           for r, i, rr, ri in zip(rows, idx, ref_rows, ref_idx):
               ok = ok and tuple(r.shape) == tuple(rr.shape) and torch.equal(r.cpu(), rr) and torch.equal(i.cpu().long() // nc, ri[:, 0]) \
                    and torch.equal(i.cpu().long() % nc, ri[:, 1])
@@ -52,8 +114,11 @@ def run(n_cases: int, seed: int) -> int:
           print("EXC", repr(e))
       if not ok:
           bad += 1
-          extra = dict(bs=bs, na=na, nm=nm) if mode == "decoded" else dict(strides=strides, imgsz=imgsz, bs=bs, ed=ed, sc=sc,
-                                                                            half=lvd[0].dtype == torch.float16)
+          extra = {}
+          if mode in ("decoded", "labels"):
+              extra = dict(bs=bs, na=na, nm=nm)
+          elif mode in ("fused", "host"):
+              extra = dict(strides=strides, imgsz=imgsz, bs=bs, ed=ed, sc=sc, half=lvd[0].dtype == torch.float16)
           print("MISMATCH case", case, mode, "nc", nc, kw, "seed", cs, extra)
           try:
               for b_, (r, rr, i, ri) in enumerate(zip(rows, ref_rows, idx, ref_idx)):
@@ -66,6 +131,7 @@ def run(n_cases: int, seed: int) -> int:
                       print("  image", b_, "first differing row", k, "ours", r[k, :6].tolist(), int(i[k]), "ref", rr[k, :6].tolist(), ri[k].tolist())
           except Exception as e2:  # noqa: BLE001
               print("  (detail failed)", repr(e2))
+  print("cases / oracle rows compared per mode:", {k: tuple(v) for k, v in sorted(stats.items())})
   return bad
 
 
