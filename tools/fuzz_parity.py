@@ -14,7 +14,7 @@ def run(n_cases: int, seed: int) -> int:
   bad = 0
   stats = {}
   for case in range(n_cases):
-      mode = rng.choice(["decoded", "decoded", "fused", "fused", "merge", "labels", "host"])
+      mode = rng.choice(["decoded", "decoded", "fused", "fused", "merge", "labels", "host", "match"])
       nc = rng.choice([1, 1, 2, 3, 6, 9, 17])
       kw = dict(conf_thres=rng.choice([0.0, 0.001, 0.05, 0.25, 0.5, 0.9]), iou_thres=rng.choice([0.0, 0.3, 0.45, 0.6, 0.7, 0.95, 1.0]),
                 agnostic=rng.random() < 0.3, multi_label=rng.random() < 0.4, max_det=rng.choice([1, 7, 100, 300, 1000]),
@@ -23,7 +23,34 @@ def run(n_cases: int, seed: int) -> int:
           kw["classes"] = rng.sample(range(nc), k=rng.randint(0, nc))
       cs = rng.randint(0, 10 ** 6)
       try:
-          if mode == "merge":
+          if mode == "match":
+              sys.path.insert(0, "tests")
+              from test_oracle import _match_case
+              nb = rng.choice([1, 4])
+              md, mg = rng.choice([10, 300]), rng.choice([1, 64, 200])
+              iouv = torch.linspace(0.5, 0.95, 10)
+              cases = [_match_case(cs + j, n_det=rng.randint(0, md), n_gt=rng.randint(0, mg), nc=nc) for j in range(nb)]
+              dets = torch.zeros(nb, md, 7); gtb = torch.zeros(nb, mg, 4); gtc = torch.zeros(nb, mg)
+              for j, (d_, g_, c_) in enumerate(cases):
+                  dets[j, : d_.shape[0], :6] = d_; gtb[j, : g_.shape[0]] = g_; gtc[j, : g_.shape[0]] = c_
+              ti = rng.choice([0, 5])
+              correct, matched = sarpost.match_predictions(dets.to(dev), torch.tensor([c[0].shape[0] for c in cases]), gtb.to(dev), gtc.to(dev),
+                                                           torch.tensor([c[1].shape[0] for c in cases]), iouv.tolist(), tag_threshold_index=ti)
+              rows, idx, ref_rows, ref_idx = [], [], [], []
+              for j, (d_, g_, c_) in enumerate(cases):
+                  n_ = d_.shape[0]
+                  if n_ == 0 or g_.shape[0] == 0:
+                      rc_, rm_ = torch.zeros(n_, 10), torch.full((n_,), -1)
+                  else:
+                      rc_, rm_ = R.match_predictions_ref(d_[:, 5], c_, R.box_iou_ref(g_, d_[:, :4]), iouv, tag_thr=iouv[ti].item())
+                      rc_, rm_ = rc_.float(), rm_.long()
+                  rows.append(correct[j, :n_].float()); idx.append(matched[j, :n_].long() + 1)
+                  ref_rows.append(rc_); ref_idx.append(torch.stack((rm_ + 1, torch.zeros_like(rm_)), 1))
+                  ok_pad = not bool(correct[j, n_:].any())
+                  if not ok_pad:
+                      raise RuntimeError("padding rows marked correct")
+              nc = 1
+          elif mode == "merge":
               tpf, d, nf, rl = rng.choice([1, 3, 12, 48]), rng.choice([1, 20, 300]), rng.choice([1, 2, 5]), rng.choice([6, 9])
               g = torch.Generator().manual_seed(cs)
               dets = torch.zeros(nf * tpf, d, rl)
@@ -99,9 +126,16 @@ def run(n_cases: int, seed: int) -> int:
               lvd = [x.to(dev) for x in lv]
               if rng.random() < 0.3:
                   lvd = [x.half() for x in lvd]
-              rows, idx = sarpost.postprocess_fused(lvd, spec, return_index=True, **kw)
+              scale_to = None
+              if rng.random() < 0.3:
+                  ih, iw = (imgsz, imgsz) if isinstance(imgsz, int) else imgsz
+                  scale_to = ((ih, iw), [(rng.randint(20, 900), rng.randint(20, 900), 3) for _ in range(bs)])
+              rows, idx = sarpost.postprocess_fused(lvd, spec, return_index=True, scale_to=scale_to, **kw)
               y = sarpost.decode([x.float() for x in lvd], spec).cpu()
               ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=nc, return_index=True, **kw)
+              if scale_to is not None:
+                  for r_, o_ in zip(ref_rows, scale_to[1]):
+                      r_[:, :4] = R.scale_boxes_ref(scale_to[0], r_[:, :4], o_)
           ok = len(rows) == len(ref_rows)
           st = stats.setdefault(mode, [0, 0])
           st[0] += 1
