@@ -96,6 +96,8 @@ typedef struct sarpost_nms_params {
                               1: the caller guarantees the first sarpost_workspace_clean_bytes(batch) bytes are zero —
                               true after sarpost_workspace_prepare and after every successful call that used the
                               workspace with the SAME batch (each call leaves that region zeroed again). */
+    int32_t out_tail_cols;  /* columns reserved at the END of every output row: rows are (6 + nm + out_tail_cols) floats
+                              wide and the call leaves the tail untouched (sarpost_state_head fills it).  0 = none. */
 } sarpost_nms_params_t;
 
 /* Last error message of the calling thread ("" if none). */
@@ -190,6 +192,24 @@ int32_t sarpost_match_predictions(const float *dets, const int32_t *det_counts, 
                                   int32_t row_len, const float *gt_boxes, const float *gt_cls, const int32_t *gt_counts,
                                   int32_t max_gt, const float *iouv, int32_t n_thr, uint8_t *correct,
                                   int32_t *matched_gt, int32_t tag_thr, void *stream);
+
+/*
+ * Deferred JDE state head.  Replaces the per-anchor evaluation of JDE.state_predictor inside
+ * JDE.forward (nn/modules/head.py:189-190 = Linear(E, E/2), ReLU, Dropout (identity in eval), Linear(E/2, S);
+ * applied at :198-204, sigmoid at :247) by one evaluation per KEPT row after the gather: for every image b and row
+ * r < counts[b]
+ *     rows[b][r][state_col .. +n_state) = sigmoid(W2 · relu(W1 · rows[b][r][emb_col .. +embed_dim) + b1) + b2)
+ * in place, fp32 FMA accumulation (results within 1e-5 of the reference's per-anchor matmul; the embedding columns
+ * are bit-identical, so the only difference is summation order).  Run sarpost_fused on levels WITHOUT the state
+ * channels (head.n_extra_sigmoid = 0) with params.out_tail_cols = n_state, then this call with emb_col = 6,
+ * state_col = 6 + embed_dim: the output rows equal the reference's [xyxy, conf, cls, emb, state].
+ *   rows   device (B, max_det, row_len);  counts device (B)
+ *   w1     device (hidden, embed_dim) row-major (nn.Linear.weight), b1 (hidden);  w2 (n_state, hidden), b2 (n_state)
+ *   embed_dim, hidden <= 1024, n_state <= 64
+ */
+int32_t sarpost_state_head(float *rows, const int32_t *counts, int32_t batch, int32_t max_det, int32_t row_len,
+                           int32_t emb_col, int32_t embed_dim, int32_t state_col, int32_t n_state, int32_t hidden,
+                           const float *w1, const float *b1, const float *w2, const float *b2, void *stream);
 
 /*
  * End-to-end entry with HOST buffers (what a caller holding CPU tensors uses; timed as `e2e` by

@@ -241,3 +241,10 @@ def match_predictions_ref(pred_classes: torch.Tensor, true_classes: torch.Tensor
                     matched[pred_idx] = gt_idx
     c = torch.tensor(correct, dtype=torch.bool)
     return (c, torch.from_numpy(matched)) if tag_thr is not None else c
+
+
+def state_head_ref(emb: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor) -> torch.Tensor:
+    """nn/modules/head.py:189-190 (`state_predictor` = Linear, ReLU, Dropout — identity in eval —, Linear), applied per
+    anchor at :198-204, sigmoid at :247.  `emb (..., E)` -> `(..., S)` probabilities, fp32 on the CPU."""
+    h = torch.relu(torch.nn.functional.linear(emb.float(), w1.float(), b1.float()))
+    return torch.nn.functional.linear(h, w2.float(), b2.float()).sigmoid()

@@ -101,6 +101,24 @@ def ref_decode(levels, strides, nc, embed_dim=0, state_classes=0):
         return m._inference([x.clone() for x in levels])
 
 
+def ref_jde_forward(feats, strides, nc, embed_dim, state_classes, seed=0):
+    """Run the reference's whole JDE head (head.py:174-249: cv2/cv3/cv4 convolutions, state_predictor on every
+    anchor, _inference) in eval mode on backbone features `feats`, with seeded random weights.
+    Returns (y, x_levels, module) — x_levels are the raw per-level head outputs the module returns next to y."""
+    import torch
+
+    _, _, head = load()
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        m = head.JDE(nc=nc, embed_dim=embed_dim, state_classes=state_classes, ch=tuple(int(f.shape[1]) for f in feats))
+        for prm in m.state_predictor.parameters():  # default init is tiny; spread the logits so the sigmoid is exercised
+            prm.mul_(4.0)
+        m.stride = torch.tensor([float(s) for s in strides])
+        m.eval()
+        y, x = m([f.clone() for f in feats])
+    return y, x, m
+
+
 def ref_nms(prediction, **kw):
     """Run the reference's own ops.non_max_suppression (utils/ops.py:167-316) on a clone of `prediction`."""
     ops, _, _ = load()

@@ -35,7 +35,7 @@ class NmsParams(C.Structure):
         ("classes", C.POINTER(C.c_int32)), ("n_classes", C.c_int32), ("labels", C.c_void_p),
         ("label_counts", C.c_void_p), ("max_labels", C.c_int32), ("rescale", C.c_void_p),
         ("peer_out", C.c_void_p * 8), ("peer_counts", C.c_void_p * 8), ("n_peers", C.c_int32),
-        ("peer_slot_offset", C.c_int32), ("prediction_dtype", C.c_int32), ("workspace_clean", C.c_int32),
+        ("peer_slot_offset", C.c_int32), ("prediction_dtype", C.c_int32), ("workspace_clean", C.c_int32), ("out_tail_cols", C.c_int32),
     ]
 
 
@@ -65,6 +65,7 @@ SYMBOLS = {
     "sarpost_match_predictions": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.c_void_p, C.c_void_p,
                                               C.c_int32, C.c_void_p]),
+    "sarpost_state_head": (C.c_int32, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p] * 5),
     "sarpost_host_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
     "sarpost_host_ctx_destroy": (None, [C.c_void_p]),
     "sarpost_fused_host": (C.c_int32, [C.c_void_p, C.POINTER(Head), C.POINTER(NmsParams), C.c_void_p, C.c_void_p,

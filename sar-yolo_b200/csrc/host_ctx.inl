@@ -164,6 +164,7 @@ int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, co
     int32_t *hc = static_cast<int32_t *>(c->h_counts.p), *hk = static_cast<int32_t *>(c->h_kidx.p);
 
     sarpost_nms_params_t prm = *params;
+    prm.out_tail_cols = 0;  // the host entry packs its own rows (6 + nm wide)
     prm.workspace_clean = 0;  // chunks of different sizes share the context's workspace: let each call zero its histogram
     // ---- enqueue copy + compute of every chunk ----
     for (int k = 0; k < n_chunks; ++k) {

@@ -707,6 +707,7 @@ struct GatherParams {
     int32_t *kept_index;        // [B*max_det] or nullptr
     const float *rescale;       // [B,5] pad_x, pad_y, gain, w0, h0 or nullptr (ops.scale_boxes + clip_boxes)
     int32_t max_det;
+    int32_t tail_cols;          // columns reserved (unwritten) at the end of every output row
     // fused gather + exchange: rows/counts are stored into every rank's buffer (P2P-mapped pointers over NVLink)
     float *peer_out[8];
     int32_t *peer_counts[8];
@@ -731,7 +732,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
     const int r = blockIdx.x * kGatherWarps + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int n_rows = p.counts[b];
-    const int row_len = 6 + p.ex.nm;
+    const int row_len = 6 + p.ex.nm + p.tail_cols;
     // destinations of this row: the local output, or the same slot in every rank's buffer (peer stores)
     const int n_dst = p.n_peers > 0 ? p.n_peers : 1;
     const int64_t img = p.n_peers > 0 ? p.peer_slot_offset + b : b;
@@ -744,7 +745,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
     if (p.ex.mode == 2) {
         const float *src = p.ex.dets + (static_cast<int64_t>(b) * p.st.tpi * p.ex.dets_per_tile + key) * p.ex.row_len;
         const float4 bx = p.st.box[seg + slot];
-        for (int c = lane; c < row_len; c += 32) {
+        for (int c = lane; c < 6 + p.ex.nm; c += 32) {
             const float v = c == 0 ? bx.x : c == 1 ? bx.y : c == 2 ? bx.z : c == 3 ? bx.w : src[c];
             for (int q = 0; q < n_dst; ++q) dst(q)[c] = v;
         }

@@ -1,0 +1,149 @@
+// K7: deferred JDE state head.
+//
+// The reference evaluates `state_predictor` = Linear(E, E/2) -> ReLU -> Dropout (identity in eval) -> Linear(E/2, S)
+// on the embedding of EVERY anchor inside JDE.forward (nn/modules/head.py:189-190, 198-204) and applies the sigmoid in
+// `_inference` (head.py:247); only the <= max_det rows that survive NMS are ever read.  The MLP is per-anchor, so the
+// same numbers come out when it runs on the survivors' embeddings after the gather: B*max_det rows instead of B*A.
+//
+// One CTA (128 threads) = kStateRows output rows of one image.  Embeddings are staged in shared memory; W1 streams
+// through a double-buffered 32-column shared tile (128-bit global loads prefetched into registers while the previous
+// tile is consumed; `[j][36]` layout = conflict-free 128-bit shared loads).  Every thread owns a JT x 4 register tile
+// (JT hidden units x 4 rows): per 4 columns JT + 4 shared loads feed 16*JT FMAs (fp32, k ascending).  The lanes of a
+// warp share their rows, so embedding reads are broadcasts.  Layer 2 is a handful of dot products per row.
+#pragma once
+#include "common.cuh"
+
+namespace sarpost {
+
+constexpr int kStateRows = 16;     // rows per CTA (300 kept rows x 16 images = 304 CTAs: one wave at 2-3 CTAs per SM)
+constexpr int kStateThreads = 128;
+constexpr int kStateRT = 4;        // rows per thread (kStateRows = 4 warps x kStateRT)
+constexpr int kStateKC = 32;       // W1 columns per shared tile
+constexpr int kStateWS = kStateKC + 4;  // shared row stride of the W1 tile (floats)
+
+struct StateHeadParams {
+    float *rows;            // [B, max_det, row_len], updated in place
+    const int32_t *counts;  // [B]
+    int32_t max_det, row_len, emb_col, embed_dim, state_col, n_state, hidden;
+    int32_t w1_vec;         // W1 rows are 16-byte aligned (embed_dim % 4 == 0, aligned base): 128-bit loads
+    const float *w1, *b1;   // nn.Linear(E, H): weight (H, E) row-major, bias (H)
+    const float *w2, *b2;   // nn.Linear(H, S): weight (S, H) row-major, bias (S)
+};
+
+__host__ __device__ inline int state_head_smem_floats(int embed_dim, int hidden, int jt) {
+    const int jl = 32 * jt, hpad = ((hidden + jl - 1) / jl) * jl, epad = ((embed_dim + kStateKC - 1) / kStateKC) * kStateKC;
+    return kStateRows * epad + 2 * jl * kStateWS + kStateRows * (hpad + 1);
+}
+
+// JT = hidden units per thread; one pass covers JL = 32*JT hidden units.
+template <int JT>
+__global__ void __launch_bounds__(kStateThreads) k7_state_head(const __grid_constant__ StateHeadParams p) {
+    constexpr int JL = 32 * JT;
+    constexpr int kVPer = JL * (kStateKC / 4) / kStateThreads;  // float4 of a W1 tile per thread (2 * JT)
+    constexpr int kTileF = JL * kStateWS;
+    extern __shared__ __align__(16) float sh_state[];
+    const int b = blockIdx.y, row0 = blockIdx.x * kStateRows, tid = threadIdx.x;
+    const int n_rows = min(p.counts[b], p.max_det) - row0;
+    if (n_rows <= 0) return;
+    const int E = p.embed_dim, H = p.hidden, S = p.n_state;
+    const int hpad = ((H + JL - 1) / JL) * JL, epad = ((E + kStateKC - 1) / kStateKC) * kStateKC;
+    float *EMB = sh_state;                 // [kStateRows][epad], zero padded
+    float *WT = EMB + kStateRows * epad;   // 2 x [JL][kStateWS]
+    float *HID = WT + 2 * kTileF;          // [kStateRows][hpad + 1]
+    float *img_rows = p.rows + (static_cast<int64_t>(b) * p.max_det + row0) * p.row_len;
+
+    const int n_kt = epad / kStateKC, n_tiles = (hpad / JL) * n_kt;
+    float4 wreg[kVPer];
+    auto load_tile = [&](int j0, int k0) {  // global -> registers; 8 consecutive threads read one 128-byte run of a W1 row
+#pragma unroll
+        for (int i = 0; i < kVPer; ++i) {
+            const int idx = tid + i * kStateThreads, j = j0 + (idx >> 3), k = k0 + (idx & 7) * 4;
+            const float *src = p.w1 + static_cast<int64_t>(j) * E + k;
+            if (p.w1_vec) {
+                wreg[i] = (j < H && k < E) ? __ldg(reinterpret_cast<const float4 *>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                wreg[i].x = (j < H && k + 0 < E) ? __ldg(src + 0) : 0.0f;
+                wreg[i].y = (j < H && k + 1 < E) ? __ldg(src + 1) : 0.0f;
+                wreg[i].z = (j < H && k + 2 < E) ? __ldg(src + 2) : 0.0f;
+                wreg[i].w = (j < H && k + 3 < E) ? __ldg(src + 3) : 0.0f;
+            }
+        }
+    };
+    auto store_tile = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < kVPer; ++i) {
+            const int idx = tid + i * kStateThreads;
+            *reinterpret_cast<float4 *>(WT + buf * kTileF + (idx >> 3) * kStateWS + (idx & 7) * 4) = wreg[i];
+        }
+    };
+    load_tile(0, 0);
+    for (int r = 0; r < kStateRows; ++r) {
+        const float *src = img_rows + static_cast<int64_t>(r) * p.row_len + p.emb_col;
+        for (int k = tid; k < epad; k += kStateThreads) EMB[r * epad + k] = (r < n_rows && k < E) ? src[k] : 0.0f;
+    }
+    store_tile(0);
+    __syncthreads();
+
+    const int lane = tid & 31, grp = tid >> 5;
+    const float *my_emb = EMB + grp * kStateRT * epad;
+    float acc[JT][kStateRT];
+    int j0 = 0, kt = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+        if (kt == 0) {
+#pragma unroll
+            for (int i = 0; i < JT; ++i)
+#pragma unroll
+                for (int r = 0; r < kStateRT; ++r) acc[i][r] = 0.0f;
+        }
+        const int k0 = kt * kStateKC;
+        const bool last_k = kt == n_kt - 1, more = t + 1 < n_tiles;
+        if (more) load_tile(last_k ? j0 + JL : j0, last_k ? 0 : k0 + kStateKC);  // in flight while this tile is consumed
+        const float *wbase = WT + (t & 1) * kTileF + lane * kStateWS;
+        const float *ebase = my_emb + k0;
+#pragma unroll
+        for (int k = 0; k < kStateKC; k += 4) {
+            float4 w[JT];
+#pragma unroll
+            for (int i = 0; i < JT; ++i) w[i] = *reinterpret_cast<const float4 *>(wbase + i * 32 * kStateWS + k);
+#pragma unroll
+            for (int r = 0; r < kStateRT; ++r) {
+                const float4 e = *reinterpret_cast<const float4 *>(ebase + r * epad + k);
+#pragma unroll
+                for (int i = 0; i < JT; ++i) {
+                    acc[i][r] = fmaf(w[i].x, e.x, acc[i][r]);
+                    acc[i][r] = fmaf(w[i].y, e.y, acc[i][r]);
+                    acc[i][r] = fmaf(w[i].z, e.z, acc[i][r]);
+                    acc[i][r] = fmaf(w[i].w, e.w, acc[i][r]);
+                }
+            }
+        }
+        if (last_k) {
+#pragma unroll
+            for (int i = 0; i < JT; ++i) {
+                const int j = j0 + lane + 32 * i;
+                const float bias = j < H ? p.b1[j] : 0.0f;
+#pragma unroll
+                for (int r = 0; r < kStateRT; ++r) HID[(grp * kStateRT + r) * (hpad + 1) + j] = j < H ? fmaxf(acc[i][r] + bias, 0.0f) : 0.0f;
+            }
+        }
+        if (more) store_tile((t + 1) & 1);  // the other buffer: last read before the previous barrier
+        __syncthreads();
+        if (last_k) {
+            kt = 0;
+            j0 += JL;
+        } else {
+            ++kt;
+        }
+    }
+    for (int o = tid; o < kStateRows * S; o += kStateThreads) {
+        const int r = o / S, s = o - r * S;
+        if (r >= n_rows) continue;
+        const float *h = HID + r * (hpad + 1);
+        const float *w = p.w2 + static_cast<int64_t>(s) * H;
+        float a = 0.0f;
+        for (int j = 0; j < H; ++j) a = fmaf(__ldg(w + j), h[j], a);
+        img_rows[static_cast<int64_t>(r) * p.row_len + p.state_col + s] = sigmoid_rn(a + p.b2[s]);  // head.py:247
+    }
+}
+
+}  // namespace sarpost

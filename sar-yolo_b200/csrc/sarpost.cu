@@ -22,6 +22,7 @@
 #include "k2_select_sort.cuh"
 #include "k4_nms.cuh"
 #include "k6_match.cuh"
+#include "k7_state_head.cuh"
 
 namespace sarpost {
 
@@ -150,6 +151,7 @@ static int check_params(const sarpost_nms_params_t *p, int nc) {
     if (p->n_peers < 0 || p->n_peers > 8) return fail(SARPOST_EINVAL, "n_peers %d outside [0, 8]", p->n_peers);
     for (int q = 0; q < p->n_peers; ++q)
         if (!p->peer_out[q] || !p->peer_counts[q]) return fail(SARPOST_EINVAL, "peer buffer %d is NULL", q);
+    if (p->out_tail_cols < 0 || p->out_tail_cols > 4096) return fail(SARPOST_EINVAL, "out_tail_cols %d outside [0, 4096]", p->out_tail_cols);
     return SARPOST_OK;
 }
 
@@ -385,6 +387,7 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     gp.kept_index = kept_index;
     gp.rescale = ex.mode == 2 ? nullptr : prm->rescale;
     gp.max_det = prm->max_det;
+    gp.tail_cols = prm->out_tail_cols;
     gp.n_peers = prm->n_peers;
     gp.peer_slot_offset = prm->peer_slot_offset;
     for (int q = 0; q < 8; ++q) {
@@ -696,6 +699,53 @@ int32_t sarpost_match_predictions(const float *dets, const int32_t *det_counts, 
     if (smem > 200 * 1024) return fail(SARPOST_EUNSUPPORTED, "max_det/max_gt too large for one CTA");
     CUDA_TRY(cudaFuncSetAttribute(k6_match, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     k6_match<<<batch, kMatchThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return SARPOST_OK;
+}
+
+int32_t sarpost_state_head(float *rows, const int32_t *counts, int32_t batch, int32_t max_det, int32_t row_len,
+                           int32_t emb_col, int32_t embed_dim, int32_t state_col, int32_t n_state, int32_t hidden,
+                           const float *w1, const float *b1, const float *w2, const float *b2, void *stream) {
+    g_launches = 0;
+    if (!rows || !counts || !w1 || !b1 || !w2 || !b2) return fail(SARPOST_EINVAL, "NULL pointer");
+    if (batch < 1 || max_det < 1) return fail(SARPOST_EINVAL, "bad state-head geometry");
+    if (embed_dim < 1 || embed_dim > 1024 || hidden < 1 || hidden > 1024 || n_state < 1 || n_state > 64)
+        return fail(SARPOST_EUNSUPPORTED, "state head %d -> %d -> %d outside (<=1024, <=1024, <=64)", embed_dim, hidden, n_state);
+    if (emb_col < 0 || state_col < 0 || emb_col + embed_dim > row_len || state_col + n_state > row_len)
+        return fail(SARPOST_EINVAL, "embedding / state columns outside the row (row_len %d)", row_len);
+    if (state_col < emb_col + embed_dim && emb_col < state_col + n_state)
+        return fail(SARPOST_EINVAL, "embedding and state columns overlap");
+    StateHeadParams p;
+    p.rows = rows;
+    p.counts = counts;
+    p.max_det = max_det;
+    p.row_len = row_len;
+    p.emb_col = emb_col;
+    p.embed_dim = embed_dim;
+    p.state_col = state_col;
+    p.n_state = n_state;
+    p.hidden = hidden;
+    p.w1 = w1;
+    p.b1 = b1;
+    p.w2 = w2;
+    p.b2 = b2;
+    p.w1_vec = (embed_dim % 4 == 0 && reinterpret_cast<uintptr_t>(w1) % 16 == 0) ? 1 : 0;
+    const int jt = hidden > 64 ? 4 : hidden > 32 ? 2 : 1;
+    const size_t smem = static_cast<size_t>(state_head_smem_floats(embed_dim, hidden, jt)) * 4;
+    if (smem > 220 * 1024) return fail(SARPOST_EUNSUPPORTED, "state head too large for one CTA's shared memory");
+    const dim3 grid((max_det + kStateRows - 1) / kStateRows, batch);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (jt == 4) {
+        CUDA_TRY(cudaFuncSetAttribute(k7_state_head<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        k7_state_head<4><<<grid, kStateThreads, smem, s>>>(p);
+    } else if (jt == 2) {
+        CUDA_TRY(cudaFuncSetAttribute(k7_state_head<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        k7_state_head<2><<<grid, kStateThreads, smem, s>>>(p);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k7_state_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        k7_state_head<1><<<grid, kStateThreads, smem, s>>>(p);
+    }
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return SARPOST_OK;

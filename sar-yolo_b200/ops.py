@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import Head, NmsParams, lib
 
-__all__ = ["HeadSpec", "non_max_suppression", "decode", "postprocess_fused", "merge_tiles", "gather_extras", "match_predictions", "postprocess_host",
+__all__ = ["HeadSpec", "StateMLP", "state_head", "non_max_suppression", "decode", "postprocess_fused", "merge_tiles", "gather_extras", "match_predictions", "postprocess_host",
            "HostContext", "last_launch_count", "stage_timing", "stage_times"]
 
 
@@ -48,6 +48,75 @@ class HeadSpec:
         return HeadSpec(nc=int(m.nc), strides=tuple(float(s) for s in m.stride), reg_max=int(m.reg_max),
                         embed_dim=int(getattr(m, "embed_dim", 0) or 0),
                         state_classes=int(getattr(m, "state_classes", 0) or 0))
+
+
+@dataclass(frozen=True)
+class StateMLP:
+    """Weights of `JDE.state_predictor` (head.py:189-190): Linear(E, H) -> ReLU -> Dropout (identity in eval) ->
+    Linear(H, S), as contiguous fp32 CUDA tensors in `nn.Linear` layout: w1 (H, E), b1 (H), w2 (S, H), b2 (S)."""
+    w1: torch.Tensor
+    b1: torch.Tensor
+    w2: torch.Tensor
+    b2: torch.Tensor
+
+    def __post_init__(self):
+        h, e = self.w1.shape
+        s, h2 = self.w2.shape
+        if h2 != h or tuple(self.b1.shape) != (h,) or tuple(self.b2.shape) != (s,):
+            raise ValueError(f"sarpost: state MLP shapes {tuple(self.w1.shape)}, {tuple(self.b1.shape)}, "
+                             f"{tuple(self.w2.shape)}, {tuple(self.b2.shape)} are not Linear(E,H) -> Linear(H,S)")
+        for t in (self.w1, self.b1, self.w2, self.b2):
+            _require_cuda(t, "state MLP weight")
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("sarpost: state MLP weights must be contiguous float32")
+
+    @property
+    def embed_dim(self) -> int:
+        return int(self.w1.shape[1])
+
+    @property
+    def hidden(self) -> int:
+        return int(self.w1.shape[0])
+
+    @property
+    def n_state(self) -> int:
+        return int(self.w2.shape[0])
+
+    @staticmethod
+    def from_tensors(w1, b1, w2, b2, device=None) -> "StateMLP":
+        dev = device if device is not None else w1.device
+        return StateMLP(*(t.detach().to(device=dev, dtype=torch.float32).contiguous() for t in (w1, b1, w2, b2)))
+
+    @staticmethod
+    def from_module(m, device=None) -> "StateMLP":
+        """From a reference JDE module (or its `state_predictor`): the two `nn.Linear` layers of the Sequential."""
+        seq = getattr(m, "state_predictor", m)
+        lin = [layer for layer in seq if isinstance(layer, torch.nn.Linear)]
+        if len(lin) != 2:
+            raise ValueError(f"sarpost: expected 2 Linear layers in state_predictor, found {len(lin)}")
+        return StateMLP.from_tensors(lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, device)
+
+
+def state_head(rows: torch.Tensor, counts: torch.Tensor, mlp: StateMLP, emb_col: int = 6, state_col: Optional[int] = None) -> torch.Tensor:
+    """Deferred JDE state head (head.py:189-190,198-204,247) on padded rows, IN PLACE:
+    `rows[b, r, state_col:state_col+S] = sigmoid(state_predictor(rows[b, r, emb_col:emb_col+E]))` for `r < counts[b]`.
+    `rows (B, max_det, row_len)` fp32 contiguous CUDA, `counts (B,)` int32.  Returns `rows`."""
+    _require_cuda(rows, "rows")
+    if rows.dtype != torch.float32 or not rows.is_contiguous() or rows.dim() != 3:
+        raise ValueError("sarpost: rows must be a contiguous float32 (B, max_det, row_len) tensor")
+    dev = rows.device
+    counts = counts.to(device=dev, dtype=torch.int32).contiguous()
+    bsz, max_det, row_len = (int(v) for v in rows.shape)
+    if counts.shape != (bsz,):
+        raise ValueError("sarpost: counts must have one entry per image")
+    if mlp.w1.device != dev:
+        raise RuntimeError(f"sarpost: state MLP weights are on {mlp.w1.device}, rows on {dev}")
+    sc = emb_col + mlp.embed_dim if state_col is None else int(state_col)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sarpost_state_head(rows.data_ptr(), counts.data_ptr(), bsz, max_det, row_len, int(emb_col), mlp.embed_dim,
+                                          sc, mlp.n_state, mlp.hidden, mlp.w1.data_ptr(), mlp.b1.data_ptr(), mlp.w2.data_ptr(),
+                                          mlp.b2.data_ptr(), _stream_ptr(dev)))
+    return rows
 
 
 def _require_cuda(t: torch.Tensor, what: str) -> None:
@@ -284,7 +353,8 @@ def decode(levels: Sequence[torch.Tensor], spec: HeadSpec) -> torch.Tensor:
 
 def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres=0.25, iou_thres=0.45, classes=None,
                       agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=7680,
-                      return_index=False, return_padded=False, with_extras=True, scale_to=None, peer_out=None):
+                      return_index=False, return_padded=False, with_extras=True, scale_to=None, peer_out=None,
+                      state_mlp: Optional[StateMLP] = None):
     """decode + non_max_suppression in one pass (never materialises y; the extras channels are read only
     for the kept rows).  Result as `non_max_suppression`; `return_padded=True` returns the raw
     `(out (B, max_det, 6+nm), counts (B,) int32[, kept_index])` device tensors without any host sync.
@@ -295,10 +365,22 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
     input, one (h, w[, c]) per original image.
     `peer_out=dist.PeerGatherBuffer` (multi-GPU): the gather kernel stores this rank's rows and counts into every
     rank's buffer over NVLink peer memory — the all-gather is fused into the kernel; returns `(rows, counts)` views
-    of the full buffers, valid after `peer_out.barrier()`."""
+    of the full buffers, valid after `peer_out.barrier()`.
+    `state_mlp=StateMLP` (deferred JDE state head): `levels` come from a head that SKIPPED
+    `state_predictor` (channels = box, cls, embedding only; `spec.state_classes` still names S); the MLP + sigmoid
+    run on the kept rows' embeddings after the gather and fill the last S columns — same row layout as the reference."""
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     levels = _prep_levels(levels)
+    tail = 0
+    if state_mlp is not None:
+        if not with_extras or peer_out is not None:
+            raise ValueError("sarpost: state_mlp needs with_extras=True and does not combine with peer_out")
+        if (state_mlp.embed_dim, state_mlp.n_state) != (spec.embed_dim, spec.state_classes):
+            raise ValueError(f"sarpost: state MLP is {state_mlp.embed_dim}->{state_mlp.n_state}, head has embed_dim "
+                             f"{spec.embed_dim}, state_classes {spec.state_classes}")
+        tail = spec.state_classes
+        spec = HeadSpec(nc=spec.nc, strides=spec.strides, reg_max=spec.reg_max, embed_dim=spec.embed_dim, state_classes=0)
     head = _make_head(levels, spec, with_extras=with_extras)
     nm = spec.nm if with_extras else 0
     dev = levels[0].device
@@ -311,6 +393,7 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
             raise ValueError(f"sarpost: scale_to has {len(img0_shapes)} original shapes for a batch of {bs}")
         rescale = scale_params(img1_shape, img0_shapes, dev)
     params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, rescale)
+    params.out_tail_cols = tail
     if peer_out is not None:
         if (peer_out.per, peer_out.max_det, peer_out.row_len) != (bs, int(max_det), 6 + nm):
             raise ValueError("sarpost: peer_out buffer geometry does not match this call")
@@ -325,7 +408,7 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
         if ws_bytes < 0:
             _lib.check(int(ws_bytes))
         ws = _Workspace(ws_bytes, bs, dev)
-        out = torch.empty((bs, int(max_det), 6 + nm), dtype=torch.float32, device=dev) if peer_out is None else None
+        out = torch.empty((bs, int(max_det), 6 + nm + tail), dtype=torch.float32, device=dev) if peer_out is None else None
         counts = torch.empty((bs,), dtype=torch.int32, device=dev)
         want_idx = return_index
         kidx = torch.empty((bs, int(max_det)), dtype=torch.int32, device=dev) if want_idx else None
@@ -333,6 +416,8 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
                                      counts.data_ptr(), kidx.data_ptr() if want_idx else None, ws.ptr(), ws_bytes,
                                      _stream_ptr(dev)))
         ws.release()
+        if state_mlp is not None:
+            state_head(out, counts, state_mlp, emb_col=6, state_col=6 + nm)
     if peer_out is not None:
         return (peer_out.rows, peer_out.counts, kidx) if want_idx else (peer_out.rows, peer_out.counts)
     if return_padded:

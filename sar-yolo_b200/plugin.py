@@ -37,15 +37,22 @@ def _make_inference(kind: str):
     return _inference
 
 
-def patch(ultralytics_ops=None, ultralytics_head=None, decode: bool = True, fused: bool = False) -> None:
+def patch(ultralytics_ops=None, ultralytics_head=None, decode: bool = True, fused: bool = False,
+          defer_state: bool = False) -> None:
     """Monkey-patch the reference.  Modules default to the importable `ultralytics` package.
 
     `fused=False`: API-exact — `_inference` returns the real `y` (decode kernel), `non_max_suppression` runs the
     decoded-input kernels.  `fused=True`: `_inference` returns a `LazyPrediction` handle and `non_max_suppression`
     runs the single-pass fused kernels from the raw logits (the unmodified predictor / validator get the fused
-    speed); `y` is materialised only if something else touches it."""
+    speed); `y` is materialised only if something else touches it.
+    `defer_state=True` (with `fused=True`): `JDE.forward` in eval mode skips `state_predictor` on the
+    `(B, A, embed_dim)` embedding map (head.py:198-204) and the patched NMS evaluates that MLP only on the kept rows
+    (`sarpost_state_head`); the returned level list then has no state channels, so keep it off while a validator
+    computes a loss from `preds[1]`."""
     if _SAVED:
         return
+    if defer_state and not fused:
+        raise ValueError("sarpost: defer_state=True needs fused=True")
     ops_mod = ultralytics_ops or importlib.import_module("ultralytics.utils.ops")
     _SAVED["ops_mod"] = ops_mod
     _SAVED["nms"] = ops_mod.non_max_suppression
@@ -59,6 +66,9 @@ def patch(ultralytics_ops=None, ultralytics_head=None, decode: bool = True, fuse
         if hasattr(head_mod, "JDE"):
             _SAVED["jde"] = head_mod.JDE._inference
             head_mod.JDE._inference = make("jde")
+            if defer_state:
+                _SAVED["jde_forward"] = head_mod.JDE.forward
+                head_mod.JDE.forward = _jde_forward_deferred
 
 
 def unpatch() -> None:
@@ -70,6 +80,8 @@ def unpatch() -> None:
         head_mod.Detect._inference = _SAVED["detect"]
         if "jde" in _SAVED:
             head_mod.JDE._inference = _SAVED["jde"]
+        if "jde_forward" in _SAVED:
+            head_mod.JDE.forward = _SAVED["jde_forward"]
     _SAVED.clear()
 
 
@@ -105,17 +117,33 @@ class LazyPrediction(torch.Tensor):
     (`__torch_dispatch__`), so code that really needs `y` keeps working — it just pays for it."""
 
     @staticmethod
-    def __new__(cls, levels, spec):
+    def __new__(cls, levels, spec, state_module=None):
         b = int(levels[0].shape[0])
         a = sum(int(x.shape[2]) * int(x.shape[3]) for x in levels)
         r = torch.Tensor._make_wrapper_subclass(cls, (b, 4 + spec.nc + spec.nm, a), dtype=levels[0].dtype,
                                                 device=levels[0].device, requires_grad=False)
         r._levels, r._spec, r._y = list(levels), spec, None
+        # deferred state head: `levels` carry no state channels; `state_module` is the JDE head that owns state_predictor
+        r._state_module = state_module
         return r
+
+    def state_mlp(self):
+        return None if self._state_module is None else _ops.StateMLP.from_module(self._state_module, self.device)
 
     def materialize(self) -> torch.Tensor:
         if self._y is None:
-            self._y = _ops.decode(self._levels, self._spec)
+            levels = self._levels
+            if self._state_module is not None:  # somebody wants the whole y: run the module's own MLP on every anchor
+                e0 = 4 * self._spec.reg_max + self._spec.nc
+                full = []
+                with torch.no_grad():
+                    for x in levels:
+                        b, _, h, w = x.shape
+                        emb = x[:, e0: e0 + self._spec.embed_dim].flatten(2).permute(0, 2, 1)
+                        st = self._state_module.state_predictor(emb.to(next(self._state_module.state_predictor.parameters()).dtype))
+                        full.append(torch.cat((x, st.to(x.dtype).permute(0, 2, 1).reshape(b, -1, h, w)), 1))
+                levels = full
+            self._y = _ops.decode(levels, self._spec)
         return self._y
 
     def __repr__(self):  # noqa: D105
@@ -144,6 +172,19 @@ def _make_lazy_inference(kind: str):
     return _inference
 
 
+def _jde_forward_deferred(self, x):
+    """JDE.forward (head.py:193-212) in eval mode without the per-anchor state_predictor (:198-204): the three
+    convolution branches are concatenated as in the stateless branch (:206) and the state MLP is left to the NMS."""
+    if (self.training or getattr(self, "export", False) or getattr(self, "end2end", False) or self.state_classes is None
+            or not x[0].is_cuda or getattr(self, "reg_max", 16) != 16):
+        return _SAVED["jde_forward"](self, x)
+    for i in range(self.nl):
+        x[i] = torch.cat((self.cv2[i](x[i]), self.cv3[i](x[i]), self.cv4[i](x[i])), 1)
+    self.shape = x[0].shape
+    levels = [xi if xi.dtype in (torch.float32, torch.float16) else xi.float() for xi in x]
+    return LazyPrediction(levels, _ops.HeadSpec.from_module(self), state_module=self), x
+
+
 def _nms_dispatch_fused(prediction, *args, **kwargs):
     pred = prediction[0] if isinstance(prediction, (list, tuple)) else prediction
     if isinstance(pred, LazyPrediction):
@@ -156,7 +197,7 @@ def _nms_dispatch_fused(prediction, *args, **kwargs):
         if not kw.get("rotated") and not has_labels and nc in (0, pred._spec.nc) and pred._y is None:
             fused_kw = {k: kw[k] for k in ("conf_thres", "iou_thres", "classes", "agnostic", "multi_label", "max_det",
                                            "max_nms", "max_wh") if k in kw}
-            rows = _ops.postprocess_fused(pred._levels, pred._spec, **fused_kw)
+            rows = _ops.postprocess_fused(pred._levels, pred._spec, state_mlp=pred.state_mlp(), **fused_kw)
             if pred.dtype != torch.float32:
                 rows = [r.to(pred.dtype) for r in rows]  # the reference returns rows in the prediction's dtype
             return rows

@@ -63,3 +63,14 @@ def nms_case_inputs(sarpost, meta):
     if "labels_seed" in meta:
         kw["labels"] = synth_labels(meta["labels_seed"], meta["gen"]["nc"])
     return y, kw
+
+
+def load_state_case():
+    """tests/golden/state_jde_mlp.npz: the live reference's whole JDE head (state_predictor on every anchor)."""
+    z = np.load(os.path.join(GOLDEN_DIR, "state_jde_mlp.npz"))
+    meta = json.loads(str(z["meta"]))
+    t = {k: torch.from_numpy(z[k]) for k in ("w1", "b1", "w2", "b2", "y", "rows")}
+    t["levels"] = [torch.from_numpy(z[f"level{i}"]) for i in range(len(meta["strides"]))]
+    t["rows"] = list(torch.split(t["rows"], z["counts"].tolist()))
+    t["meta"] = meta
+    return t

@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from golden_util import canon, head_inputs, load, names, nms_case_inputs
+from golden_util import canon, head_inputs, load, load_state_case, names, nms_case_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -49,3 +49,22 @@ def test_cuda_decode_and_fused_vs_reference_golden(sarpost, cuda, name):
         ok = torch.isclose(canon(a), canon(b), rtol=1e-5, atol=1e-5 * max(m["strides"])).all(1)
         bad += int((~ok).sum())
     assert bad <= 1e-4 * total, f"{bad} of {total} detections differ from the reference"
+
+
+def test_cuda_deferred_state_head_vs_reference_golden(sarpost, cuda):
+    """§8f row 2: head WITHOUT the state channels + sarpost_state_head on the kept rows == the reference's rows, where
+    state_predictor ran on every anchor inside JDE.forward (head.py:198-204).  Tolerance: 1e-5 on the state
+    probabilities (fp32 summation order), the other columns as in the head goldens."""
+    g = load_state_case()
+    m = g["meta"]
+    nc, ed, sc = m["nc"], m["ed"], m["sc"]
+    spec = sarpost.HeadSpec(nc=nc, strides=tuple(m["strides"]), embed_dim=ed, state_classes=sc)
+    mlp = sarpost.StateMLP.from_tensors(g["w1"], g["b1"], g["w2"], g["b2"], device=cuda)
+    full = sarpost.postprocess_fused([x.to(cuda) for x in g["levels"]], spec, **m["kw"])
+    deferred = sarpost.postprocess_fused([x[:, : 64 + nc + ed].contiguous().to(cuda) for x in g["levels"]], spec, state_mlp=mlp, **m["kw"])
+    for a, d, b in zip(full, deferred, g["rows"]):
+        assert a.shape == d.shape == b.shape
+        assert torch.equal(a[:, : 6 + ed], d[:, : 6 + ed])                       # same kernels, same bits
+        assert torch.allclose(d[:, 6 + ed:], a[:, 6 + ed:], rtol=0, atol=1e-5)   # deferred vs per-anchor (our sigmoid of the ref logits)
+        assert torch.allclose(d.cpu()[:, : 6 + ed], b[:, : 6 + ed], rtol=1e-5, atol=1e-5 * max(m["strides"]))
+        assert torch.allclose(d.cpu()[:, 6 + ed:], b[:, 6 + ed:], rtol=0, atol=1e-5)

@@ -631,3 +631,108 @@ def test_seeded_fuzz(sarpost, cuda):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(150, 7) == 0
+
+
+@pytest.mark.parametrize("e,h,s,bsz,max_det", [(256, 128, 6, 16, 300), (128, 64, 6, 3, 100), (20, 10, 3, 2, 37), (64, 200, 17, 2, 50), (10, 5, 3, 2, 20), (36, 33, 64, 1, 17)])
+def test_state_head_kernel_vs_oracle(sarpost, cuda, e, h, s, bsz, max_det):
+    """§8f row 2: sarpost_state_head on padded rows vs the oracle MLP (head.py:189-190,247); fp32, atol 1e-5 on the
+    probabilities.  Rows beyond counts[b] and all other columns stay untouched."""
+    g = torch.Generator().manual_seed(e * 7 + h)
+    w1, b1 = torch.randn(h, e, generator=g) * (2.0 / e ** 0.5), torch.randn(h, generator=g)
+    w2, b2 = torch.randn(s, h, generator=g) * (2.0 / h ** 0.5), torch.randn(s, generator=g)
+    row_len = 6 + e + s
+    rows = torch.randn(bsz, max_det, row_len, generator=g)
+    counts = torch.randint(0, max_det + 1, (bsz,), generator=g, dtype=torch.int32)
+    counts[0] = max_det
+    if bsz > 1:
+        counts[1] = 0
+    mlp = sarpost.StateMLP.from_tensors(w1, b1, w2, b2, device=cuda)
+    out = sarpost.state_head(rows.to(cuda).clone(), counts.to(cuda), mlp).cpu()
+    ref = R.state_head_ref(rows[..., 6: 6 + e], w1, b1, w2, b2)
+    for b in range(bsz):
+        n = int(counts[b])
+        assert torch.allclose(out[b, :n, 6 + e:], ref[b, :n], rtol=0, atol=1e-5), float((out[b, :n, 6 + e:] - ref[b, :n]).abs().max())
+        assert torch.equal(out[b, n:], rows[b, n:])
+        assert torch.equal(out[b, :, : 6 + e], rows[b, :, : 6 + e])
+    assert sarpost.ops.last_launch_count() == 1
+
+
+def test_state_head_errors(sarpost, cuda):
+    mlp = sarpost.StateMLP.from_tensors(torch.zeros(4, 8), torch.zeros(4), torch.zeros(2, 4), torch.zeros(2), device=cuda)
+    rows = torch.zeros(1, 5, 6 + 8 + 2, device=cuda)
+    cnt = torch.ones(1, dtype=torch.int32, device=cuda)
+    with pytest.raises(sarpost.SarpostError, match="outside the row"):
+        sarpost.state_head(rows, cnt, mlp, emb_col=6, state_col=15)
+    with pytest.raises(sarpost.SarpostError, match="overlap"):
+        sarpost.state_head(rows, cnt, mlp, emb_col=6, state_col=10)
+    with pytest.raises(RuntimeError, match="only CUDA"):
+        sarpost.state_head(rows.cpu(), cnt, mlp)
+    with pytest.raises(ValueError, match="state MLP is"):
+        spec = sarpost.HeadSpec(nc=1, strides=(8,), embed_dim=16, state_classes=2)
+        sarpost.postprocess_fused([torch.zeros(1, 64 + 1 + 16, 4, 4, device=cuda)], spec, state_mlp=mlp)
+
+
+def test_patch_defer_state_runs_the_mlp_on_kept_rows_only(sarpost, cuda):
+    """patch(fused=True, defer_state=True): JDE.forward skips state_predictor on the anchor map and the patched NMS
+    fills the state columns from the kept rows' embeddings; rows equal the undeferred path (state within 1e-5)."""
+    import types
+
+    calls = {"mlp": 0}
+
+    class Counting(torch.nn.Sequential):
+        def forward(self, x):
+            calls["mlp"] += 1
+            return super().forward(x)
+
+    class JDE(torch.nn.Module):
+        export, reg_max, end2end = False, 16, False
+
+        def __init__(self, nc, stride, embed_dim, state_classes, ch):
+            super().__init__()
+            self.nc, self.stride, self.embed_dim, self.state_classes, self.nl = nc, torch.tensor(stride), embed_dim, state_classes, len(ch)
+            self.cv2 = torch.nn.ModuleList(torch.nn.Conv2d(c, 64, 1) for c in ch)
+            self.cv3 = torch.nn.ModuleList(torch.nn.Conv2d(c, nc, 1) for c in ch)
+            self.cv4 = torch.nn.ModuleList(torch.nn.Conv2d(c, embed_dim, 1) for c in ch)
+            self.state_predictor = Counting(torch.nn.Linear(embed_dim, embed_dim // 2), torch.nn.ReLU(), torch.nn.Dropout(0.1),
+                                            torch.nn.Linear(embed_dim // 2, state_classes))
+
+        def forward(self, x):  # the reference's structure (head.py:193-212)
+            for i in range(self.nl):
+                emb = self.cv4[i](x[i])
+                b, c, h, w = emb.shape
+                st = self.state_predictor(emb.view(b, c, -1).permute(0, 2, 1)).permute(0, 2, 1).view(b, self.state_classes, h, w)
+                x[i] = torch.cat((self.cv2[i](x[i]), self.cv3[i](x[i]), emb, st), 1)
+            return self._inference(x), x
+
+        def _inference(self, x):
+            raise AssertionError("reference decode must not run for CUDA inputs")
+
+    Detect = type("Detect", (), {"_inference": lambda self, x: None})
+    ops_mod = types.SimpleNamespace(non_max_suppression=lambda *a, **k: (_ for _ in ()).throw(AssertionError("reference NMS")))
+    head_mod = types.SimpleNamespace(Detect=Detect, JDE=JDE)
+    torch.manual_seed(3)
+    head = JDE(1, (8.0, 16.0), 32, 6, (8, 12)).to(cuda).eval()
+    feats = [torch.randn(2, 8, 20, 20, device=cuda), torch.randn(2, 12, 10, 10, device=cuda)]
+    with torch.no_grad():
+        sarpost.patch(ops_mod, head_mod, fused=True)
+        try:
+            y, _ = head([f.clone() for f in feats])
+            want = ops_mod.non_max_suppression(y, 0.3, 0.7, max_det=50, nc=1)
+            want_y = y + 0
+        finally:
+            sarpost.unpatch()
+        assert calls["mlp"] == 2
+        sarpost.patch(ops_mod, head_mod, fused=True, defer_state=True)
+        try:
+            y, x = head([f.clone() for f in feats])
+            assert calls["mlp"] == 2 and x[0].shape[1] == 64 + 1 + 32 and tuple(y.shape) == tuple(want_y.shape)
+            got = ops_mod.non_max_suppression(y, 0.3, 0.7, max_det=50, nc=1)
+            assert calls["mlp"] == 2 and y._y is None
+            assert sum(r.shape[0] for r in got) > 10
+            for a, b in zip(got, want):
+                assert a.shape == b.shape and torch.equal(a[:, :38], b[:, :38])
+                assert torch.allclose(a[:, 38:], b[:, 38:], rtol=0, atol=1e-5)
+            assert torch.allclose(y + 0, want_y, rtol=1e-5, atol=1e-5) and calls["mlp"] == 4   # materialising y runs the module's MLP
+        finally:
+            sarpost.unpatch()
+    assert JDE.forward is not sarpost.plugin._jde_forward_deferred

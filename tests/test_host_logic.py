@@ -166,3 +166,20 @@ def test_patch_on_live_reference_modules(sarpost):
         finally:
             sarpost.unpatch()
     assert ops.non_max_suppression is orig_nms and head.Detect._inference is orig_det and head.JDE._inference is orig_jde
+    # defer_state also swaps JDE.forward; CPU features still run the reference's own forward (state_predictor on every anchor)
+    orig_fwd = head.JDE.forward
+    feats = [torch.randn(1, 64, h, w, generator=torch.Generator().manual_seed(i)) for i, (h, w) in enumerate(shapes)]
+    with torch.no_grad():
+        m.shape = None
+        want_full, want_x = m([f.clone() for f in feats])
+        sarpost.patch(fused=True, defer_state=True)
+        try:
+            assert head.JDE.forward is not orig_fwd
+            m.shape = None
+            got_full, got_x = m([f.clone() for f in feats])
+            assert torch.equal(got_full, want_full) and all(torch.equal(a, b) for a, b in zip(got_x, want_x))
+        finally:
+            sarpost.unpatch()
+    assert head.JDE.forward is orig_fwd
+    with pytest.raises(ValueError):
+        sarpost.patch(defer_state=True)

@@ -154,3 +154,27 @@ def test_match_predictions_ref_matches_live_reference():
         assert torch.equal(iou, R.box_iou_ref(gt, dets[:, :4]))
         ref = V.BaseValidator.match_predictions(types.SimpleNamespace(iouv=iouv), dets[:, 5], gcls, iou)
         assert torch.equal(ref, R.match_predictions_ref(dets[:, 5], gcls, iou, iouv))
+
+
+def test_state_head_ref_equals_reference_golden():
+    """§8f row 2 pin: the per-anchor state_predictor of the live reference's JDE.forward (golden y) is reproduced by
+    the oracle MLP on the embedding channels of the head's raw level outputs — i.e. deferring it is value-preserving."""
+    from golden_util import load_state_case
+    g = load_state_case()
+    m = g["meta"]
+    nc, ed, sc = m["nc"], m["ed"], m["sc"]
+    emb = torch.cat([x.flatten(2) for x in g["levels"]], 2)[:, 64 + nc: 64 + nc + ed]      # (B, E, A)
+    state = R.state_head_ref(emb.permute(0, 2, 1), g["w1"], g["b1"], g["w2"], g["b2"]).permute(0, 2, 1)
+    ref = g["y"][:, 4 + nc + ed:]
+    assert ref.shape == state.shape and ref.shape[1] == sc
+    assert float(ref.max() - ref.min()) > 0.5          # the golden exercises the sigmoid, not a constant
+    assert torch.allclose(state, ref, rtol=0, atol=2e-6), float((state - ref).abs().max())
+    # and the whole deferred path in oracle form: NMS on the head WITHOUT state channels + MLP on the kept rows
+    levels_ns = [x[:, : 64 + nc + ed].contiguous() for x in g["levels"]]
+    y_ns = R.decode_ref(levels_ns, m["strides"], nc, embed_dim=ed)
+    rows = R.non_max_suppression_ref(y_ns, nc=nc, **m["kw"])
+    for a, b in zip(rows, g["rows"]):
+        assert a.shape[0] == b.shape[0] and b.shape[1] == 6 + ed + sc
+        assert torch.allclose(a, b[:, : 6 + ed], rtol=1e-5, atol=1e-4)
+        st = R.state_head_ref(a[:, 6:], g["w1"], g["b1"], g["w2"], g["b2"])
+        assert torch.allclose(st, b[:, 6 + ed:], rtol=0, atol=2e-6)
