@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import sys
@@ -203,6 +204,8 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+L2_BYTES = 126e6  # B200 L2
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -299,7 +302,20 @@ def main():
             return out, counts
     else:
         def step():
-            return sarpost.postprocess_fused(levels, spec, return_padded=True, **kw)
+            return sarpost.postprocess_fused(next_levels(), spec, return_padded=True, **kw)
+
+    # L2 rule: a batch whose hot channels do not clearly exceed the 126 MB L2 is rotated over enough identical copies
+    # of the inputs that a buffer has been evicted by the time it is read again (no flush kernel in the timed region)
+    hot_bytes = bs * anchors * (64 + nc) * 4
+    n_sets = 1 if (sahi or hot_bytes >= 2 * L2_BYTES) else min(int(math.ceil(2 * L2_BYTES / hot_bytes)), 128)
+    if not sahi:
+        n_sets = max(n_sets, args.streams)
+    level_sets = [levels] + [[x.clone() for x in levels] for _ in range(n_sets - 1)]
+    set_iter = [0]
+
+    def next_levels():
+        set_iter[0] += 1
+        return level_sets[set_iter[0] % n_sets]
 
     def barrier():
         if world > 1:
@@ -329,24 +345,22 @@ def main():
         # copy of the inputs and its own workspace; the NMS kernel of one batch (few SMs, latency-bound) overlaps
         # the fused decode of the next (HBM-bound).  Every step still does the whole path for one batch.
         streams = [torch.cuda.Stream() for _ in range(args.streams)]
-        copies = [levels] + [[x.clone() for x in levels] for _ in range(args.streams - 1)]
-        for s_, lv in zip(streams, copies):  # warm up each stream (workspace per stream)
+        for s_ in streams:  # warm up each stream (workspace per stream)
             with torch.cuda.stream(s_):
                 for _ in range(3):
-                    sarpost.postprocess_fused(lv, spec, return_padded=True, **kw)
+                    sarpost.postprocess_fused(next_levels(), spec, return_padded=True, **kw)
         barrier()
         ev0.record()
         for s_ in streams:
             s_.wait_event(ev0)
         for i in range(args.steps):
             with torch.cuda.stream(streams[i % args.streams]):
-                out, counts = sarpost.postprocess_fused(copies[i % args.streams], spec, return_padded=True, **kw)
+                out, counts = sarpost.postprocess_fused(next_levels(), spec, return_padded=True, **kw)  # n_sets >= streams
         for s_ in streams:
             torch.cuda.current_stream().wait_stream(s_)
         ev1.record()
         barrier()
         ms = ev0.elapsed_time(ev1)
-        del copies
     # second pass over the same K steps with CUDA events around every kernel (recorded by the library on the
     # launching stream, no host sync per step, mean read afterwards).  Kept out of the pass `value` comes from:
     # timing events between kernels cost ~8 % throughput by removing the overlap of consecutive launches.
@@ -459,7 +473,11 @@ def main():
                                         if (n_gpus > 1 and not os.environ.get("SARPOST_BENCH_NCCL_GATHER")) else
                                         f"tiles sharded x{n_gpus}, NCCL all-gather of counts+boxes, frames merged by their owner rank") if sahi
                                        else f"batch-sharded x{n_gpus}, no data-path collective"),
-                       "l2": "one batch of inputs (hot channels %.0f MB) exceeds the 126 MB L2; no flush" % (bs * anchors * (64 + nc) * 4 / 1e6),
+                       "l2": (("one batch of inputs (hot channels %.0f MB) exceeds the 126 MB L2; no flush" % (hot_bytes / 1e6))
+                              if hot_bytes >= 2 * L2_BYTES else
+                              ("hot channels %.1f MB per batch: steps rotate over %d identical input copies (%.0f MB in rotation > 2x the "
+                               "126 MB L2), so every step reads its inputs from HBM; no flush" % (hot_bytes / 1e6, n_sets, n_sets * hot_bytes / 1e6))),
+                       "input_sets": n_sets,
                        "candidates_per_image": n_cand / bs, "detections_per_image": n_det / bs},
             "single_stream": single, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step, "clocks": clocks.summary(),
