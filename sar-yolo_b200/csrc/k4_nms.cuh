@@ -472,19 +472,26 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #pragma unroll
                 for (int g = 0; g < kSubWords; ++g) km[g] = 0u;
                 int kl = kept;
+                // column g of the bitmask (word g of the rows g2*32+lane, g2 <= g) is loaded one group ahead, before
+                // the dependent chain of group g-1, so the sweep never waits on shared memory
+                uint32_t cur[kSubWords], nxt[kSubWords];
+                cur[0] = s_mask[lane * kSubWords];
 #pragma unroll
                 for (int g = 0; g < kSubWords; ++g) {
+                    if (g + 1 < kSubWords) {
+#pragma unroll
+                        for (int g2 = 0; g2 <= g + 1; ++g2) nxt[g2] = s_mask[((g2 << 5) + lane) * kSubWords + g + 1];
+                    }
                     if (g < words && kl < p.max_det) {
                         // removal word of group g = OR over the rows kept in earlier groups (lane = row)
                         uint32_t rem = 0u;
 #pragma unroll
-                        for (int g2 = 0; g2 < g; ++g2)
-                            if ((km[g2] >> lane) & 1u) rem |= s_mask[((g2 << 5) + lane) * kSubWords + g];
+                        for (int g2 = 0; g2 < g; ++g2) rem |= ((km[g2] >> lane) & 1u) ? cur[g2] : 0u;
                         rem = __reduce_or_sync(0xffffffffu, rem);
                         const int nvalid = min(32, m - (g << 5));
                         const uint32_t live = ~rem & (nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u));
                         const int r = (g << 5) + lane;
-                        const uint32_t diag = lane < nvalid ? s_mask[r * kSubWords + g] : 0u;
+                        const uint32_t diag = lane < nvalid ? cur[g] : 0u;
                         // rows that overlap a later live row of the group are the only ones whose fate matters to
                         // others: walk just those in order (usually none or a handful of the 32)
                         uint32_t pending = __ballot_sync(0xffffffffu, ((live >> lane) & 1u) && (diag & live));
@@ -515,6 +522,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                         }
                         kl += c;
                         km[g] = keptm;
+                    }
+                    if (g + 1 < kSubWords) {
+#pragma unroll
+                        for (int g2 = 0; g2 <= g + 1; ++g2) cur[g2] = nxt[g2];
                     }
                 }
                 if (lane == 0) s_misc[16] = kl;
