@@ -24,7 +24,7 @@ constexpr int kStateWS = kStateKC + 4;  // shared row stride of the W1 tile (flo
 struct StateHeadParams {
     float *rows;            // [B, max_det, row_len], updated in place
     const int32_t *counts;  // [B]
-    int32_t max_det, row_len, emb_col, embed_dim, state_col, n_state, hidden;
+    int32_t batch, max_det, row_len, emb_col, embed_dim, state_col, n_state, hidden;
     int32_t w1_vec;         // W1 rows are 16-byte aligned (embed_dim % 4 == 0, aligned base): 128-bit loads
     const float *w1, *b1;   // nn.Linear(E, H): weight (H, E) row-major, bias (H)
     const float *w2, *b2;   // nn.Linear(H, S): weight (S, H) row-major, bias (S)
@@ -143,6 +143,140 @@ __global__ void __launch_bounds__(kStateThreads) k7_state_head(const __grid_cons
         float a = 0.0f;
         for (int j = 0; j < H; ++j) a = fmaf(__ldg(w + j), h[j], a);
         img_rows[static_cast<int64_t>(r) * p.row_len + p.state_col + s] = sigmoid_rn(a + p.b2[s]);  // head.py:247
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Resident variant (the usual JDE sizes: E % 4 == 0, H <= 128, S <= 32, everything fits 220 KB of shared memory):
+// persistent CTAs copy W1 ONCE into shared memory with cp.async (no per-tile round trips to L2), then every warp
+// computes whole groups of kResRows kept rows with a JT x kResRows register tile: per 4 columns JT + kResRows 128-bit shared loads feed
+// 4*JT*kResRows FMAs.  Layer 2 runs out of registers: per state class 4 FMAs per lane and a butterfly reduction.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kResWarps = 12;
+constexpr int kResRows = 4;    // rows per warp pass (12 warps x 4 rows: three warps per scheduler hide the FMA and shared-memory latency)
+
+__host__ __device__ inline int state_head_resident_smem_floats(int embed_dim, int n_state, int jt) {
+    const int hp = 32 * jt;
+    return hp * (embed_dim + 4) + n_state * hp + hp + 32 + kResWarps * kResRows * embed_dim;
+}
+
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+template <int JT>
+__global__ void __launch_bounds__(kResWarps * 32, 1) k7_state_head_resident(const __grid_constant__ StateHeadParams p) {
+    constexpr int HP = 32 * JT;
+    extern __shared__ __align__(16) float sh_state[];
+    const int E = p.embed_dim, H = p.hidden, S = p.n_state, ws = E + 4, e4 = E >> 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float *WS = sh_state;                 // [HP][E + 4]: conflict-free 128-bit loads for lane-major rows
+    float *W2S = WS + HP * ws;            // [S][HP]
+    float *B1S = W2S + S * HP;            // [HP]
+    float *B2S = B1S + HP;                // [32]
+    float *slab = B2S + 32 + warp * (kResRows * E);  // this warp's 8 embedding rows
+
+    for (int j = warp; j < H; j += kResWarps)  // a warp copies whole rows of W1: 512-byte runs, no index division
+        for (int kq = lane; kq < e4; kq += 32) cp_async_16(WS + j * ws + kq * 4, p.w1 + static_cast<int64_t>(j) * E + kq * 4);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int idx = H * ws + tid; idx < HP * ws; idx += kResWarps * 32) WS[idx] = 0.0f;  // padding rows (H < 32*JT)
+    for (int s = warp; s < S; s += kResWarps)
+        for (int j = lane; j < HP; j += 32) W2S[s * HP + j] = j < H ? __ldg(p.w2 + s * H + j) : 0.0f;
+    for (int j = tid; j < HP; j += kResWarps * 32) B1S[j] = j < H ? __ldg(p.b1 + j) : 0.0f;
+    if (tid < 32) B2S[tid] = tid < S ? __ldg(p.b2 + tid) : 0.0f;
+
+    const int opi = (p.max_det + kResRows - 1) / kResRows;  // octs per image
+    const int n_octs = p.batch * opi;
+    const int stride = kResWarps * gridDim.x;
+    bool ready = false;  // W1 landed and visible
+    for (int o = warp * gridDim.x + blockIdx.x;; o += stride) {
+        int n_valid = 0, b = 0, row0 = 0;
+        if (o < n_octs) {
+            b = o / opi;
+            row0 = (o - b * opi) * kResRows;
+            n_valid = min(kResRows, min(p.counts[b], p.max_det) - row0);
+        }
+        float *img_rows = p.rows + (static_cast<int64_t>(b) * p.max_det + row0) * p.row_len;
+        if (n_valid > 0) {
+            __syncwarp();
+            // the embedding columns are only read in this kernel (the state columns it writes are disjoint): read-only
+            // loads, eight in flight per lane before the first store
+            for (int k0 = 0; k0 < E; k0 += 32) {
+                float v[kResRows];
+                const int k = k0 + lane;
+#pragma unroll
+                for (int r = 0; r < kResRows; ++r)
+                    v[r] = (r < n_valid && k < E) ? __ldg(img_rows + static_cast<int64_t>(r) * p.row_len + p.emb_col + k) : 0.0f;
+                if (k < E) {
+#pragma unroll
+                    for (int r = 0; r < kResRows; ++r) slab[r * E + k] = v[r];
+                }
+            }
+            __syncwarp();
+        }
+        if (!ready) {  // first pass of every warp, with or without work: one block barrier
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+            ready = true;
+        }
+        if (o >= n_octs) break;
+        if (n_valid <= 0) continue;
+
+        float acc[JT][kResRows];
+#pragma unroll
+        for (int i = 0; i < JT; ++i)
+#pragma unroll
+            for (int r = 0; r < kResRows; ++r) acc[i][r] = 0.0f;
+        const float *wb = WS + lane * ws;
+#pragma unroll 2
+        for (int k = 0; k < E; k += 4) {
+            float4 w[JT];
+#pragma unroll
+            for (int i = 0; i < JT; ++i) w[i] = *reinterpret_cast<const float4 *>(wb + i * 32 * ws + k);
+#pragma unroll
+            for (int r = 0; r < kResRows; ++r) {
+                const float4 e = *reinterpret_cast<const float4 *>(slab + r * E + k);
+#pragma unroll
+                for (int i = 0; i < JT; ++i) {
+                    acc[i][r] = fmaf(w[i].x, e.x, acc[i][r]);
+                    acc[i][r] = fmaf(w[i].y, e.y, acc[i][r]);
+                    acc[i][r] = fmaf(w[i].z, e.z, acc[i][r]);
+                    acc[i][r] = fmaf(w[i].w, e.w, acc[i][r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < JT; ++i) {
+            const float bias = B1S[lane + 32 * i];
+#pragma unroll
+            for (int r = 0; r < kResRows; ++r) acc[i][r] = fmaxf(acc[i][r] + bias, 0.0f);  // ReLU; padding units stay 0
+        }
+        float res[kResRows];
+#pragma unroll
+        for (int r = 0; r < kResRows; ++r) res[r] = 0.0f;
+        for (int s = 0; s < S; ++s) {
+            float part[kResRows];
+#pragma unroll
+            for (int r = 0; r < kResRows; ++r) part[r] = 0.0f;
+#pragma unroll
+            for (int i = 0; i < JT; ++i) {
+                const float w2 = W2S[s * HP + lane + 32 * i];
+#pragma unroll
+                for (int r = 0; r < kResRows; ++r) part[r] = fmaf(w2, acc[i][r], part[r]);
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+                for (int r = 0; r < kResRows; ++r) part[r] += __shfl_xor_sync(0xffffffffu, part[r], off);
+#pragma unroll
+            for (int r = 0; r < kResRows; ++r) res[r] = lane == s ? part[r] : res[r];
+        }
+        if (lane < S) {
+            const float b2 = B2S[lane];
+#pragma unroll
+            for (int r = 0; r < kResRows; ++r)
+                if (r < n_valid) img_rows[static_cast<int64_t>(r) * p.row_len + p.state_col + lane] = sigmoid_rn(res[r] + b2);  // head.py:247
+        }
     }
 }
 

@@ -719,6 +719,7 @@ int32_t sarpost_state_head(float *rows, const int32_t *counts, int32_t batch, in
     StateHeadParams p;
     p.rows = rows;
     p.counts = counts;
+    p.batch = batch;
     p.max_det = max_det;
     p.row_len = row_len;
     p.emb_col = emb_col;
@@ -732,10 +733,24 @@ int32_t sarpost_state_head(float *rows, const int32_t *counts, int32_t batch, in
     p.b2 = b2;
     p.w1_vec = (embed_dim % 4 == 0 && reinterpret_cast<uintptr_t>(w1) % 16 == 0) ? 1 : 0;
     const int jt = hidden > 64 ? 4 : hidden > 32 ? 2 : 1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t res_smem = static_cast<size_t>(state_head_resident_smem_floats(embed_dim, n_state, jt)) * 4;
+    if (p.w1_vec && hidden <= 128 && n_state <= 32 && res_smem <= 220 * 1024 && !getenv("SARPOST_STATE_TILED")) {
+        // resident variant: W1 copied once per persistent CTA, warps own whole groups of 8 kept rows
+        int sms = 0, smem_optin = 0;
+        if (int rc = device_sm_count(&sms, &smem_optin)) return rc;
+        const int n_octs = batch * ((max_det + kResRows - 1) / kResRows);
+        const int ctas = n_octs < sms ? n_octs : sms;  // persistent: warp w of CTA c takes octs w*ctas + c, + 6*ctas, ...
+        void (*kern)(const StateHeadParams) = jt == 4 ? k7_state_head_resident<4> : jt == 2 ? k7_state_head_resident<2> : k7_state_head_resident<1>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        kern<<<ctas, kResWarps * 32, res_smem, s>>>(p);
+        ++g_launches;
+        CUDA_TRY(cudaGetLastError());
+        return SARPOST_OK;
+    }
     const size_t smem = static_cast<size_t>(state_head_smem_floats(embed_dim, hidden, jt)) * 4;
     if (smem > 220 * 1024) return fail(SARPOST_EUNSUPPORTED, "state head too large for one CTA's shared memory");
     const dim3 grid((max_det + kStateRows - 1) / kStateRows, batch);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (jt == 4) {
         CUDA_TRY(cudaFuncSetAttribute(k7_state_head<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         k7_state_head<4><<<grid, kStateThreads, smem, s>>>(p);

@@ -634,9 +634,12 @@ def test_seeded_fuzz(sarpost, cuda):
 
 
 @pytest.mark.parametrize("e,h,s,bsz,max_det", [(256, 128, 6, 16, 300), (128, 64, 6, 3, 100), (20, 10, 3, 2, 37), (64, 200, 17, 2, 50), (10, 5, 3, 2, 20), (36, 33, 64, 1, 17)])
-def test_state_head_kernel_vs_oracle(sarpost, cuda, e, h, s, bsz, max_det):
+@pytest.mark.parametrize("tiled", [False, True])
+def test_state_head_kernel_vs_oracle(sarpost, cuda, monkeypatch, e, h, s, bsz, max_det, tiled):
     """§8f row 2: sarpost_state_head on padded rows vs the oracle MLP (head.py:189-190,247); fp32, atol 1e-5 on the
     probabilities.  Rows beyond counts[b] and all other columns stay untouched."""
+    if tiled:  # the streaming kernel (any size); otherwise the resident kernel where it applies
+        monkeypatch.setenv("SARPOST_STATE_TILED", "1")
     g = torch.Generator().manual_seed(e * 7 + h)
     w1, b1 = torch.randn(h, e, generator=g) * (2.0 / e ** 0.5), torch.randn(h, generator=g)
     w2, b2 = torch.randn(s, h, generator=g) * (2.0 / h ** 0.5), torch.randn(s, generator=g)
