@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsarpost.so")
 SOURCES = ["sarpost.cu"]
-DEPS = ["sarpost.cu", "common.cuh", "k1_candidates.cuh", "k2_select_sort.cuh", "k4_nms.cuh", "k6_match.cuh", "host_ctx.inl",
+DEPS = ["sarpost.cu", "common.cuh", "k1_candidates.cuh", "k2_select_sort.cuh", "k4_nms.cuh", "k6_match.cuh", "k7_state_head.cuh", "host_ctx.inl",
         os.path.join("..", "..", "include", "sarpost.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fopenmp", "-shared", "-cudart", "static", "-lgomp"]
