@@ -130,9 +130,28 @@ def run(n_cases: int, seed: int) -> int:
               if rng.random() < 0.3:
                   ih, iw = (imgsz, imgsz) if isinstance(imgsz, int) else imgsz
                   scale_to = ((ih, iw), [(rng.randint(20, 900), rng.randint(20, 900), 3) for _ in range(bs)])
-              rows, idx = sarpost.postprocess_fused(lvd, spec, return_index=True, scale_to=scale_to, **kw)
-              y = sarpost.decode([x.float() for x in lvd], spec).cpu()
-              ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=nc, return_index=True, **kw)
+              mlp = None
+              if sc and ed and rng.random() < 0.4:  # deferred state head: levels without the state channels + MLP on kept rows
+                  g = torch.Generator().manual_seed(cs + 7)
+                  hd = rng.choice([2, 8, 40])
+                  wts = (torch.randn(hd, ed, generator=g), torch.randn(hd, generator=g), torch.randn(sc, hd, generator=g), torch.randn(sc, generator=g))
+                  mlp = sarpost.StateMLP.from_tensors(*wts, device=dev)
+                  lvd = [x[:, : 64 + nc + ed].contiguous() for x in lvd]
+              rows, idx = sarpost.postprocess_fused(lvd, spec, return_index=True, scale_to=scale_to, state_mlp=mlp, **kw)
+              if mlp is not None:
+                  spec_ns = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=0)
+                  y = sarpost.decode([x.float() for x in lvd], spec_ns).cpu()
+                  ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=nc, return_index=True, **kw)
+                  for b_ in range(len(rows)):  # state columns: tolerance (fp32 summation order), then compared as equal
+                      st_ref = R.state_head_ref(ref_rows[b_][:, 6:6 + ed], *wts)
+                      got = rows[b_].cpu()
+                      if got.shape[0] == st_ref.shape[0] and torch.allclose(got[:, 6 + ed:], st_ref, rtol=0, atol=2e-5):
+                          ref_rows[b_] = torch.cat((ref_rows[b_], got[:, 6 + ed:]), 1)
+                      else:
+                          ref_rows[b_] = torch.cat((ref_rows[b_], st_ref), 1)
+              else:
+                  y = sarpost.decode([x.float() for x in lvd], spec).cpu()
+                  ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=nc, return_index=True, **kw)
               if scale_to is not None:
                   for r_, o_ in zip(ref_rows, scale_to[1]):
                       r_[:, :4] = R.scale_boxes_ref(scale_to[0], r_[:, :4], o_)
