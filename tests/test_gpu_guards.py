@@ -106,3 +106,70 @@ def test_decoded_and_merge_writes_stay_inside_their_buffers(sarpost, cuda):
     counts = cnt.view(torch.int32, (nf,)).tolist()
     for f in range(nf):
         assert torch.equal(out.view(torch.float32, (nf, md, rl))[f, :counts[f]], want[f])
+
+
+def test_decode_extras_match_state_writes_stay_inside_their_buffers(sarpost, cuda):
+    ops, lib = sarpost.ops, sarpost._lib.lib
+    stream = torch.cuda.current_stream().cuda_stream
+    strides, nc, ed, sc, bs = (8, 16, 32), 2, 8, 6, 3
+    spec = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=sc)
+    shapes = sarpost.synth.level_shapes((88, 120), strides)
+    anchors = sum(h * w for h, w in shapes)
+    for half in (False, True):  # API-exact decode, y in the input dtype
+        levels = [x.to(cuda) for x in sarpost.synth.head_outputs(bs, shapes, nc, ed, sc, seed=2)]
+        if half:
+            levels = [x.half() for x in levels]
+        want = sarpost.decode(levels, spec)
+        head = ops._make_head(levels, spec)
+        esz = 2 if half else 4
+        y = Guarded(bs * (4 + nc + ed + sc) * anchors * esz, cuda)
+        assert lib.sarpost_decode(C.byref(head), y.ptr, stream) == 0
+        torch.cuda.synchronize()
+        assert y.intact() and torch.equal(y.view(want.dtype, tuple(want.shape)), want)
+    # extras of explicit (image, anchor) pairs, including out-of-range ones (zero rows)
+    ii = torch.tensor([0, 2, 1, 5, -1, 0], dtype=torch.int32, device=cuda)
+    ai = torch.tensor([0, anchors - 1, 17, 3, 4, anchors], dtype=torch.int32, device=cuda)
+    levels = [x.to(cuda) for x in sarpost.synth.head_outputs(bs, shapes, nc, ed, sc, seed=2)]
+    want = sarpost.gather_extras(levels, spec, ii, ai)
+    head = ops._make_head(levels, spec)
+    ex = Guarded(6 * (ed + sc) * 4, cuda)
+    assert lib.sarpost_gather_extras(C.byref(head), ii.data_ptr(), ai.data_ptr(), 6, ex.ptr, stream) == 0
+    torch.cuda.synchronize()
+    assert ex.intact() and torch.equal(ex.view(torch.float32, (6, ed + sc)), want)
+    # validator matching
+    from test_oracle import _match_case
+    md, mg, nt = 40, 16, 10
+    dets = torch.zeros(2, md, 7); gtb = torch.zeros(2, mg, 4); gtc = torch.zeros(2, mg)
+    dn, gn = [], []
+    for j in range(2):
+        d_, g_, c_ = _match_case(20 + j, n_det=35 + j, n_gt=12 + j)
+        dets[j, : d_.shape[0], :6] = d_; gtb[j, : g_.shape[0]] = g_; gtc[j, : g_.shape[0]] = c_
+        dn.append(d_.shape[0]); gn.append(g_.shape[0])
+    iouv = [0.5 + 0.05 * i for i in range(nt)]
+    want_c, want_m = sarpost.match_predictions(dets.to(cuda), torch.tensor(dn), gtb.to(cuda), gtc.to(cuda), torch.tensor(gn), iouv, tag_threshold_index=0)
+    cor, mat = Guarded(2 * md * nt, cuda), Guarded(2 * md * 4, cuda)
+    dd, gb, gc = dets.to(cuda), gtb.to(cuda), gtc.to(cuda)
+    dnt, gnt = torch.tensor(dn, dtype=torch.int32, device=cuda), torch.tensor(gn, dtype=torch.int32, device=cuda)
+    thr = (C.c_float * nt)(*iouv)
+    assert lib.sarpost_match_predictions(dd.data_ptr(), dnt.data_ptr(), 2, md, 7, gb.data_ptr(), gc.data_ptr(), gnt.data_ptr(), mg, thr, nt,
+                                         cor.ptr, mat.ptr, 0, stream) == 0
+    torch.cuda.synchronize()
+    assert cor.intact() and mat.intact()
+    assert torch.equal(cor.view(torch.uint8, (2, md, nt)).bool(), want_c) and torch.equal(mat.view(torch.int32, (2, md)), want_m)
+    # deferred state head, both kernels: only the state columns of rows < counts[b] may change
+    import os
+    for e, h, s in ((32, 16, 6), (10, 5, 3)):
+        g = torch.Generator().manual_seed(e)
+        mlp = sarpost.StateMLP.from_tensors(torch.randn(h, e, generator=g), torch.randn(h, generator=g), torch.randn(s, h, generator=g),
+                                            torch.randn(s, generator=g), device=cuda)
+        md, rl = 21, 6 + e + s
+        src = torch.randn(2, md, rl, generator=g).to(cuda)
+        cnts = torch.tensor([md, 5], dtype=torch.int32, device=cuda)
+        rows = Guarded(2 * md * rl * 4, cuda)
+        rows.view(torch.float32, (2, md, rl)).copy_(src)
+        assert lib.sarpost_state_head(rows.ptr, cnts.data_ptr(), 2, md, rl, 6, e, 6 + e, s, h, mlp.w1.data_ptr(), mlp.b1.data_ptr(),
+                                      mlp.w2.data_ptr(), mlp.b2.data_ptr(), stream) == 0
+        torch.cuda.synchronize()
+        got = rows.view(torch.float32, (2, md, rl))
+        assert rows.intact() and torch.equal(got[..., : 6 + e], src[..., : 6 + e]) and torch.equal(got[1, 5:], src[1, 5:])
+        assert not torch.equal(got[0, :, 6 + e:], src[0, :, 6 + e:])
