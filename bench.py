@@ -238,6 +238,7 @@ def main():
     except Exception:
         pass
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
