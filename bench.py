@@ -152,7 +152,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -209,8 +209,29 @@ L2_BYTES = 126e6  # B200 L2
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: keep a private handle on the real stdout for it and point fd 1 at stderr,
+    so that anything a library prints there (NCCL prints its version on stdout) cannot end up in front of the line."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
+def emit(line: dict) -> None:
+    out = claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     ensure_built()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -238,7 +259,6 @@ def main():
     except Exception:
         pass
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
@@ -483,7 +503,7 @@ def main():
             "single_stream": single, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step, "clocks": clocks.summary(),
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
