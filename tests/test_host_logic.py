@@ -183,3 +183,56 @@ def test_patch_on_live_reference_modules(sarpost):
     assert head.JDE.forward is orig_fwd
     with pytest.raises(ValueError):
         sarpost.patch(defer_state=True)
+
+
+def test_scale_params_equal_reference_host_arithmetic(sarpost):
+    """ops.scale_params = the Python-float part of ops.scale_boxes (utils/ops.py:110-116): gain, rounded pads, clip bounds."""
+    from oracle import postprocess_ref as R
+    img1 = (640, 512)
+    shapes = [(1080, 1920, 3), (333, 777), (640, 512), (17, 4000, 3)]
+    prm = sarpost.ops.scale_params(img1, shapes, "cpu")
+    assert prm.shape == (4, 5) and prm.dtype == torch.float32
+    boxes = torch.tensor([[0.0, 0.0, 512.0, 640.0], [100.5, 200.25, 300.75, 400.125]])
+    for row, s0 in zip(prm.tolist(), shapes):
+        px, py, gain, w0, h0 = row
+        got = boxes.clone()
+        got[:, [0, 2]] = ((got[:, [0, 2]] - px) / gain).clamp(0, w0)   # what the gather kernel does, in torch fp32
+        got[:, [1, 3]] = ((got[:, [1, 3]] - py) / gain).clamp(0, h0)
+        assert torch.equal(got, R.scale_boxes_ref(img1, boxes, s0))
+
+
+def test_state_mlp_validation_and_error_types(sarpost):
+    w1, b1, w2, b2 = torch.zeros(4, 8), torch.zeros(4), torch.zeros(2, 4), torch.zeros(2)
+    with pytest.raises(RuntimeError, match="only CUDA"):        # no CPU fallback for the deferred state head either
+        sarpost.StateMLP.from_tensors(w1, b1, w2, b2)
+    with pytest.raises(ValueError, match="2 Linear layers"):
+        sarpost.StateMLP.from_module(torch.nn.Sequential(torch.nn.Linear(8, 4), torch.nn.ReLU()))
+    with pytest.raises(RuntimeError, match="only CUDA"):
+        sarpost.state_head(torch.zeros(1, 3, 16), torch.zeros(1, dtype=torch.int32), None)
+    assert issubclass(sarpost.SarpostError, RuntimeError)
+
+
+def test_fused_dispatch_argument_mapping_on_cpu(sarpost):
+    """The patched NMS takes the reference's positional order (ops.py:167-182): a CPU prediction with positional
+    arguments must reach the ORIGINAL function unchanged, under both patch modes."""
+    import types
+    seen = {}
+
+    def ref_nms(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False, labels=(),
+                max_det=300, nc=0, max_time_img=0.05, max_nms=30000, max_wh=7680, in_place=True, rotated=False):
+        seen.update(conf_thres=conf_thres, iou_thres=iou_thres, classes=classes, agnostic=agnostic, max_det=max_det, nc=nc, rotated=rotated)
+        return "ref"
+
+    Detect = type("Detect", (), {"_inference": lambda self, x: "ref-decode"})
+    for fused in (False, True):
+        ops_mod = types.SimpleNamespace(non_max_suppression=ref_nms)
+        head_mod = types.SimpleNamespace(Detect=Detect)
+        sarpost.patch(ops_mod, head_mod, fused=fused)
+        try:
+            y = torch.zeros(1, 6, 10)
+            assert ops_mod.non_max_suppression((y, None), 0.3, 0.6, [0], True, max_det=5, nc=2) == "ref"
+            assert seen == dict(conf_thres=0.3, iou_thres=0.6, classes=[0], agnostic=True, max_det=5, nc=2, rotated=False)
+            assert Detect()._inference([torch.zeros(1, 66, 2, 2)]) == "ref-decode"
+        finally:
+            sarpost.unpatch()
+        assert ops_mod.non_max_suppression is ref_nms
