@@ -236,3 +236,27 @@ def test_fused_dispatch_argument_mapping_on_cpu(sarpost):
         finally:
             sarpost.unpatch()
         assert ops_mod.non_max_suppression is ref_nms
+
+
+def test_product_code_never_touches_the_oracle_or_a_cpu_fallback():
+    """The oracle is test infrastructure: nothing under the package (Python or CUDA) may import, link or call it, nor
+    torchvision's NMS, Triton or torch.compile; bench.py may use it only in its CPU legs."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "sar-yolo_b200")
+    banned = re.compile(r"\b(import\s+oracle|from\s+oracle|oracle\.|torchvision|import\s+triton|torch\.compile)\b")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
+                src = open(os.path.join(dirpath, fn), encoding="utf-8").read()
+                hit = [ln for ln in src.splitlines() if banned.search(ln) and not ln.lstrip().startswith(("#", "//", "*"))
+                       and "no `torchvision" not in ln and "torchvision's" not in ln and "torchvision." not in ln.split("#")[-1]]
+                hit = [ln for ln in hit if re.search(r"^\s*(import|from)\s+(oracle|torchvision|triton)|torch\.compile\(|oracle\.", ln)]
+                assert not hit, f"{fn}: {hit[:2]}"
+    bench = open(os.path.join(root, "bench.py"), encoding="utf-8").read()
+    uses = [m.start() for m in re.finditer(r"from oracle|import oracle", bench)]
+    assert uses, "bench.py's CPU legs use the oracle port"
+    for at in uses:  # every use sits inside a CPU-leg function
+        fn = re.findall(r"\ndef (\w+)\(", bench[:at])[-1]
+        assert fn in ("cpu_reference_step", "time_cpu_baseline", "run_reference_arm"), fn
