@@ -372,6 +372,12 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     levels = _prep_levels(levels)
+    if int(levels[0].shape[0]) == 0 and peer_out is None:  # empty batch: the reference returns an empty list (ops.py:250)
+        dev0, cols = levels[0].device, 6 + (spec.nm if with_extras else 0)
+        if return_padded:
+            e = (torch.zeros((0, int(max_det), cols), device=dev0), torch.zeros((0,), dtype=torch.int32, device=dev0))
+            return e + (torch.zeros((0, int(max_det)), dtype=torch.int32, device=dev0),) if return_index else e
+        return ([], []) if return_index else []
     tail = 0
     if state_mlp is not None:
         if not with_extras or peer_out is not None:

@@ -739,3 +739,13 @@ def test_patch_defer_state_runs_the_mlp_on_kept_rows_only(sarpost, cuda):
         finally:
             sarpost.unpatch()
     assert JDE.forward is not sarpost.plugin._jde_forward_deferred
+
+
+def test_empty_batch_returns_empty_list(sarpost, cuda):
+    """B = 0: the reference's per-image loop simply produces no outputs (ops.py:250)."""
+    spec = sarpost.HeadSpec(nc=1, strides=(8, 16, 32), embed_dim=4, state_classes=0)
+    levels = [torch.zeros(0, 69, h, w, device=cuda) for h, w in sarpost.synth.level_shapes(64, (8, 16, 32))]
+    assert sarpost.postprocess_fused(levels, spec) == []
+    out, counts = sarpost.postprocess_fused(levels, spec, return_padded=True, max_det=10)
+    assert tuple(out.shape) == (0, 10, 10) and tuple(counts.shape) == (0,)
+    assert sarpost.non_max_suppression(torch.zeros(0, 9, 50, device=cuda), nc=1) == []
