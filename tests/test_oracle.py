@@ -178,3 +178,70 @@ def test_state_head_ref_equals_reference_golden():
         assert torch.allclose(a, b[:, : 6 + ed], rtol=1e-5, atol=1e-4)
         st = R.state_head_ref(a[:, 6:], g["w1"], g["b1"], g["w2"], g["b2"])
         assert torch.allclose(st, b[:, 6 + ed:], rtol=0, atol=2e-6)
+
+
+def test_oracle_fuzz_against_live_reference(sarpost):
+    """Beyond the committed goldens: 60 seeded random configurations run through the LIVE reference's
+    ops.non_max_suppression (build container only; /root/reference is absent on the GPU box) and through the
+    oracle's literal restatement — bit-equal rows in the same order."""
+    import random
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ref_shim.load()
+    rng = random.Random(2024)
+    checked = rows_total = 0
+    for case in range(60):
+        nc = rng.choice([1, 2, 6, 11])
+        nm = rng.choice([0, 0, 3, 32])
+        bs, na = rng.choice([1, 2, 3]), rng.choice([1, 77, 600, 2500])
+        kw = dict(conf_thres=rng.choice([0.0, 0.001, 0.1, 0.25, 0.6]), iou_thres=rng.choice([0.0, 0.3, 0.45, 0.7, 1.0]),
+                  agnostic=rng.random() < 0.3, multi_label=rng.random() < 0.4, max_det=rng.choice([1, 10, 300]),
+                  max_nms=rng.choice([7, 500, 30000]), max_wh=rng.choice([7680, 0, 123.5]), nc=nc)
+        if rng.random() < 0.3:
+            kw["classes"] = rng.sample(range(nc), k=rng.randint(1, nc))
+        y = sarpost.synth.decoded_prediction(bs, na, nc, nm, seed=1000 + case, clustered=rng.random() < 0.5,
+                                             score_pow=rng.choice([1.0, 4.0]))
+        if rng.random() < 0.25:  # exact score ties
+            y[:, 4:4 + nc] = (y[:, 4:4 + nc] * 8).floor() / 8 + 0.01
+        labels = ()
+        if rng.random() < 0.2:
+            g = torch.Generator().manual_seed(case)
+            labels = [torch.cat((torch.randint(0, nc, (n, 1), generator=g).float(), torch.rand(n, 2, generator=g) * 500,
+                                 5 + torch.rand(n, 2, generator=g) * 60), 1) for n in [rng.choice([0, 3, 40]) for _ in range(bs)]]
+        want = ref_shim.ref_nms(y, labels=labels, **kw)
+        got = R.non_max_suppression_ref(y, labels=labels, stable_topk=False, **kw)
+        assert len(want) == len(got) == bs
+        for a, b in zip(got, want):
+            assert a.shape == b.shape, (case, kw, a.shape, b.shape)
+            # ties at the max_nms cut: the reference's unstable argsort and the literal restatement are the same call
+            assert torch.equal(a, b), (case, kw)
+            rows_total += a.shape[0]
+        checked += 1
+    assert checked == 60 and rows_total > 2000
+
+
+def test_oracle_decode_fuzz_against_live_reference(sarpost):
+    """Random head geometries through the live reference's Detect/JDE._inference (head.py:100-131, :214-249) and through
+    oracle.decode_ref: same torch CPU ops in the same order, so equal to the last bit under the same thread count
+    (tolerance 2e-6 relative kept for hosts whose vector ISA rounds softmax differently)."""
+    import random
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ref_shim.load()
+    rng = random.Random(7)
+    for case in range(12):
+        strides = rng.choice([(8, 16, 32), (4, 8, 16, 32), (16,), (8, 32)])
+        imgsz = rng.choice([64, 96, (88, 120), (32, 160), 224])
+        nc = rng.choice([1, 2, 6, 15])
+        ed, sc = rng.choice([(0, 0), (16, 0), (8, 6), (128, 6)])
+        bs = rng.choice([1, 2, 3])
+        shapes = sarpost.synth.level_shapes(imgsz, strides)
+        levels = sarpost.synth.head_outputs(bs, shapes, nc, ed, sc, seed=400 + case, box_std=rng.choice([0.5, 2.0, 6.0]))
+        want = ref_shim.ref_decode(levels, strides, nc, ed, sc)
+        got = R.decode_ref(levels, strides, nc, 16, ed, sc)
+        assert got.shape == want.shape
+        st = torch.cat([torch.full((h * w,), float(s)) for (h, w), s in zip(shapes, strides)])
+        assert bool(((got[:, :4] - want[:, :4]).abs() <= 2e-6 * want[:, :4].abs() + 2e-6 * st).all()), case
+        assert torch.allclose(got[:, 4:], want[:, 4:], rtol=2e-6, atol=1e-9), case
