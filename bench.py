@@ -121,6 +121,17 @@ def time_cpu_baseline(levels_cpu, strides, nc, ed, sc, kw, repeats=1):
     return n_img / best, best
 
 
+def load_synth_standalone():
+    """The synthetic-input generator (pure torch) loaded by file path, so the CPU reference arm does not import the
+    `sarpost` package and therefore never maps libsarpost.so into its process."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_sarpost_synth", os.path.join(ROOT, "sar-yolo_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def run_reference_arm(args):
     import torch
 
@@ -128,8 +139,7 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     imgsz, strides, nc, ed, sc, bs, kw, cls_mean, desc = WORKLOADS[args.workload]
-    import sarpost
-    from sarpost import synth
+    synth = load_synth_standalone()  # the product package (and libsarpost.so) is never imported by this arm
 
     shapes = synth.level_shapes(imgsz, strides)
     per_step = args.cpu_images or (1 if args.workload == "cfg3" else min(bs, 8))
@@ -232,9 +242,9 @@ def emit(line: dict) -> None:
 def main():
     args = parse_args()
     claim_stdout()
-    ensure_built()
-    if args.impl == "reference":
+    if args.impl == "reference":  # CPU arm: oracle port + torchvision only — libsarpost.so is neither built nor loaded here
         return run_reference_arm(args)
+    ensure_built()
     if args.quick:
         args.no_e2e = args.no_cpu_baseline = True
 

@@ -20,9 +20,13 @@ __global__ void __launch_bounds__(256) k_extras_finish(const __grid_constant__ E
     const int b = blockIdx.y;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (r >= p.max_det || r >= p.counts[b]) return;
+    if (r >= p.max_det) return;
     const int64_t row = static_cast<int64_t>(b) * p.max_det + r;
     float *o = p.out + row * (6 + p.nm);
+    if (r >= p.counts[b]) {  // the whole buffer travels to the caller: rows beyond the count are defined (zero), never stale
+        for (int c = lane; c < 6 + p.nm; c += 32) o[c] = 0.0f;
+        return;
+    }
     if (lane < 6) o[lane] = p.rows6[row * 6 + lane];
     for (int c = lane; c < p.nm; c += 32) {
         const float v = p.extras[row * p.nm + c];
@@ -58,6 +62,7 @@ struct Buf {
 
 struct sarpost_host_ctx {
     int device = 0;
+    int pack_threads = 1;  // host threads packing the extras of the kept rows (see sarpost_host_ctx_create)
     cudaStream_t s_copy = nullptr, s_main = nullptr, s_fin = nullptr;
     std::vector<cudaEvent_t> ev_copied, ev_done;
     sarpost::Buf d_levels, d_ws, d_rows6, d_counts, d_kidx, d_extras, d_out;
@@ -73,6 +78,18 @@ int32_t sarpost_host_ctx_create(int32_t device, sarpost_host_ctx_t **ctx) {
     sarpost_host_ctx *c = new sarpost_host_ctx();
     c->device = device;
     c->h_rows6.host = c->h_counts.host = c->h_kidx.host = c->h_extras.host = true;
+    {
+        // Packing threads: one process per GPU shares the host's cores with its LOCAL_WORLD_SIZE - 1 siblings (torchrun
+        // exports it), so the share of this process is cpus / local_world, capped at 8 (more does not help a gather of
+        // <= max_det rows per image) — 8 ranks x 8 threads on a 32-vCPU host was measurable oversubscription.
+        // SARPOST_HOST_THREADS overrides.
+        const int cpus = omp_get_num_procs();
+        const int lws = env_int("LOCAL_WORLD_SIZE", 1);
+        int t = cpus / (lws > 0 ? lws : 1);
+        t = t < 1 ? 1 : (t > 8 ? 8 : t);
+        const int forced = env_int("SARPOST_HOST_THREADS", 0);
+        c->pack_threads = forced > 0 ? forced : t;
+    }
     for (cudaStream_t *st : {&c->s_copy, &c->s_main, &c->s_fin}) {
         cudaError_t e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
@@ -112,9 +129,25 @@ int32_t sarpost_host_ctx_last_traffic(const sarpost_host_ctx_t *c, int64_t *h2d_
 //   s_fin   H2D of the packed extras of the chunk's kept rows, finish kernel, D2H of the final rows
 // While the copy engine streams chunk k+1, the GPU post-processes chunk k and the host packs the extras of
 // chunk k-1 (OpenMP), so the call costs about the PCIe time of the inputs.
+static int32_t fused_host_impl(sarpost_host_ctx_t *c, const sarpost_head_t *head, const sarpost_nms_params_t *params,
+                               float *out, int32_t *counts, int32_t *kept_index);
+
 int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, const sarpost_nms_params_t *params,
                            float *out, int32_t *counts, int32_t *kept_index) {
     if (!c) return fail(SARPOST_EINVAL, "ctx is NULL");
+    const int32_t rc = fused_host_impl(c, head, params, out, counts, kept_index);
+    if (rc != SARPOST_OK) {
+        // a failed call may have left copies / kernels in flight that reference the context's buffers (which the next
+        // call may reallocate) and the caller's host pointers: drain the three streams before handing control back
+        for (cudaStream_t st : {c->s_copy, c->s_main, c->s_fin})
+            if (st) cudaStreamSynchronize(st);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+static int32_t fused_host_impl(sarpost_host_ctx_t *c, const sarpost_head_t *head, const sarpost_nms_params_t *params,
+                               float *out, int32_t *counts, int32_t *kept_index) {
     HeadGeom g;
     int64_t anchors = 0;
     if (int rc = fill_geom(head, &g, &anchors)) return rc;
@@ -186,6 +219,8 @@ int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, co
         }
         CUDA_TRY(cudaEventRecord(c->ev_copied[k], c->s_copy));
         CUDA_TRY(cudaStreamWaitEvent(c->s_main, c->ev_copied[k], 0));
+        if (nm == 0)  // these rows go to the caller as they are: rows beyond counts[b] must not carry an earlier call's data
+            CUDA_TRY(cudaMemsetAsync(d_rows6 + static_cast<int64_t>(b0) * max_det * 6, 0, static_cast<size_t>(nb) * max_det * 24, c->s_main));
         if (int rc = sarpost_fused(&hd, &prm, d_rows6 + static_cast<int64_t>(b0) * max_det * 6, d_counts + b0,
                                    d_kidx + static_cast<int64_t>(b0) * max_det, c->d_ws.p, c->d_ws.bytes, c->s_main))
             return rc;
@@ -209,7 +244,7 @@ int32_t sarpost_fused_host(sarpost_host_ctx_t *c, const sarpost_head_t *head, co
         CUDA_TRY(cudaEventSynchronize(c->ev_done[k]));
         if (nm == 0) continue;
         const int64_t n_rows = static_cast<int64_t>(nb) * max_det;
-#pragma omp parallel for schedule(static) num_threads(8) if (n_rows >= 64)
+#pragma omp parallel for schedule(static) num_threads(c->pack_threads) if (n_rows >= 64 && c->pack_threads > 1)
         for (int64_t q = 0; q < n_rows; ++q) {
             const int b = b0 + static_cast<int>(q / max_det), r = static_cast<int>(q % max_det);
             if (r >= hc[b]) continue;

@@ -15,6 +15,8 @@
 #include <cstring>
 #include <vector>
 
+#include <omp.h>
+
 #include <nvtx3/nvToolsExt.h>  // header-only; ranges show up in Nsight tools, no-ops otherwise
 
 #include "common.cuh"

@@ -253,7 +253,7 @@ def non_max_suppression(
     multi_label=False,
     labels=(),
     max_det=300,
-    nc=0,  # number of classes (optional)
+    nc=0,
     max_time_img=0.05,
     max_nms=30000,
     max_wh=7680,
@@ -273,30 +273,35 @@ def non_max_suppression(
     `return_index` a label row reports anchor index `A + label_row`.
     `return_index=True` (extension) also returns per image the int32 `anchor*nc + class` of each row.
     """
-    # Checks (ops.py:217-220)
+    # the drop-in keeps the reference's assertion texts (ops.py:217-218): callers and tests match on them
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
-    if isinstance(prediction, (list, tuple)):  # YOLOv8 model in validation model, output = (inference_out, loss_out)
-        prediction = prediction[0]  # select only inference output
+    if isinstance(prediction, (list, tuple)):
+        prediction = prediction[0]  # a validator hands over (y, raw_levels); only y is post-processed (ops.py:219-220)
     _require_cuda(prediction, "prediction")
     if rotated:
         raise NotImplementedError("sarpost: rotated=True (OBB probiou NMS, ops.py:146-164) is outside the accelerated path")
     has_labels = bool(labels) and any(len(lb) for lb in labels)
 
-    if prediction.shape[-1] == 6:  # end-to-end model (BNC, i.e. 1,300,6): no NMS at all (ops.py:224-228)
-        output = [pred[pred[:, 4] > conf_thres][:max_det] for pred in prediction]
-        if classes is not None:
-            cls_t = torch.tensor(classes, device=prediction.device)
-            output = [pred[(pred[:, 5:6] == cls_t).any(1)] for pred in output]
-        return output
+    if prediction.shape[-1] == 6:
+        # NMS-free heads (v10-style) already emit (B, N, 6) rows x1,y1,x2,y2,conf,cls: the reference only thresholds,
+        # truncates and applies the class filter (ops.py:224-228).  No kernel involved: a handful of tiny torch ops.
+        allow = None if classes is None else torch.as_tensor(classes, device=prediction.device)
+        picked = []
+        for rows in prediction:
+            rows = rows[rows[:, 4] > conf_thres][:max_det]
+            if allow is not None:
+                rows = rows[(rows[:, 5:6] == allow).any(1)]
+            picked.append(rows)
+        return picked
 
     in_dtype = prediction.dtype
     # fp32 and fp16 (`half=True` models) are read as they are; anything else is upcast first
     pred = prediction if in_dtype in (torch.float32, torch.float16) else prediction.float()
     pred = pred.contiguous()
     bs, ch, na = (int(s) for s in pred.shape)
-    nc = int(nc) or (ch - 4)  # number of classes (ops.py:231)
-    nm = ch - nc - 4  # number of masks / extras
+    nc = int(nc) or (ch - 4)  # nc=0 means "every channel after the box is a class" (ops.py:231)
+    nm = ch - nc - 4  # trailing per-anchor payload carried through NMS (mask coefficients, JDE embedding + state)
     dev = pred.device
     if bs == 0 or na == 0:
         empty = [torch.zeros((0, 6 + nm), device=dev)] * bs

@@ -2,37 +2,92 @@
 
 Every reference call site resolves `ops.non_max_suppression` through the module attribute at call
 time (models/yolo/jde/predict.py:31, jde/val.py:648, detect/predict.py:25, detect/val.py:94, ...) and
-the heads call `self._inference(x)` (nn/modules/head.py:73, :211), so replacing those three attributes
+the heads call `self._inference(x)` (nn/modules/head.py:73, :211), so replacing those attributes
 is enough for `model.predict()` / `model.val()`.  Calls this package does not
-accelerate (CPU tensors, rotated boxes, export mode) are forwarded to the ORIGINAL
-reference function that was saved at patch time — never to a re-implementation of ours.
+accelerate are forwarded to the ORIGINAL reference function that was saved at patch time — never to a
+re-implementation of ours: CPU tensors, rotated boxes, export mode, head subclasses with their own box
+decode (OBB `dist2rbox`, end2end/v10 heads that expect xyxy, Pose/Segment which read the anchor cache the
+reference `_inference` fills), and argument ranges the library rejects (`max_det > 4096`, `nc > 2048`, ...).
 """
 from __future__ import annotations
 
 import importlib
 
-from . import head as _head
+import torch
+
+from . import _lib
 from . import ops as _ops
 
 _SAVED = {}
 
+_NMS_ARG_NAMES = ("conf_thres", "iou_thres", "classes", "agnostic", "multi_label", "labels", "max_det", "nc", "max_time_img",
+                  "max_nms", "max_wh", "in_place", "rotated")
+
+
+def _nms_kwargs(args, kwargs) -> dict:
+    """Positional + keyword arguments of `ops.non_max_suppression` (utils/ops.py:167-182) by name."""
+    kw = dict(zip(_NMS_ARG_NAMES, args))
+    kw.update(kwargs)
+    return kw
+
+
+def _nms_supported_fields(is_cuda: bool, ndim: int, dtype, shape, kw) -> bool:
+    if not is_cuda or kw.get("rotated", False) or ndim != 3 or not dtype.is_floating_point:
+        return False
+    if shape[-1] == 6:  # end-to-end layout: plain thresholding, handled by ops.non_max_suppression in torch
+        return True
+    try:
+        max_det, max_nms = int(kw.get("max_det", 300)), int(kw.get("max_nms", 30000))
+        nc = int(kw.get("nc", 0) or 0) or int(shape[1]) - 4
+    except (TypeError, ValueError):
+        return False
+    return 1 <= max_det <= 4096 and max_nms >= 1 and 1 <= nc <= _lib.MAX_CLASSES and int(shape[1]) >= 4 + nc
+
+
+def _nms_supported(pred, kw) -> bool:
+    """True when libsarpost covers this call; everything else runs the reference's own function."""
+    if not isinstance(pred, torch.Tensor):
+        return False
+    return _nms_supported_fields(pred.is_cuda, pred.dim(), pred.dtype, tuple(pred.shape), kw)
+
 
 def _nms_dispatch(prediction, *args, **kwargs):
-    orig = _SAVED["nms"]
     pred = prediction[0] if isinstance(prediction, (list, tuple)) else prediction
-    rotated = kwargs.get("rotated", args[12] if len(args) > 12 else False)
-    if (not getattr(pred, "is_cuda", False)) or rotated:
-        return orig(prediction, *args, **kwargs)  # the reference's own code path, untouched
+    if not _nms_supported(pred, _nms_kwargs(args, kwargs)):
+        return _SAVED["nms"](prediction, *args, **kwargs)  # the reference's own code path, untouched
     return _ops.non_max_suppression(prediction, *args, **kwargs)
 
 
+def _plain_head(self, kind: str) -> bool:
+    """Only the exact `Detect` / `JDE` classes with the stock xywh `decode_bboxes` take the accelerated decode.
+    Subclasses (OBB, Pose, Segment, v10Detect, ...) override the decode or read `self.anchors/self.strides`, which
+    only the reference `_inference` maintains (head.py:105-107, :303, :354)."""
+    head_mod = _SAVED.get("head_mod")
+    base = getattr(head_mod, "Detect", None)
+    want = getattr(head_mod, "JDE", None) if kind == "jde" else base
+    if want is None or type(self) is not want:
+        return False
+    if getattr(self, "end2end", False) or getattr(self, "export", False) or getattr(self, "reg_max", 16) != 16:
+        return False
+    dec, base_dec = getattr(type(self), "decode_bboxes", None), getattr(base, "decode_bboxes", None)
+    return dec is base_dec
+
+
+def _levels_ok(self, x) -> bool:
+    return (len(x) > 0 and all(isinstance(xi, torch.Tensor) and xi.is_cuda and xi.dim() == 4 for xi in x)
+            and all(int(xi.shape[1]) == int(getattr(self, "no", xi.shape[1])) for xi in x))
+
+
 def _make_inference(kind: str):
-    fast = _head.jde_inference if kind == "jde" else _head.detect_inference
+    """`Detect._inference(self, x)` (head.py:100-131) / `JDE._inference` (:214-249) replacement returning the real
+    `y = cat(dbox, cls.sigmoid()[, emb, state.sigmoid()])` from the decode kernel.  The reference's anchor cache
+    (`self.shape/anchors/strides`, head.py:105-107) is left untouched so a later call of the ORIGINAL method (after
+    `unpatch()`, or for a CPU input) recomputes it as usual."""
 
     def _inference(self, x):
-        if getattr(self, "export", False) or not x[0].is_cuda or getattr(self, "reg_max", 16) != 16:
+        if not _plain_head(self, kind) or not _levels_ok(self, x):
             return _SAVED[kind](self, x)
-        return fast(self, x)
+        return _ops.decode(x, _ops.HeadSpec.from_module(self))
 
     return _inference
 
@@ -106,9 +161,6 @@ def fused_postprocess(preds, head_module, img_shape=None, orig_shapes=None, **nm
 # ---------------------------------------------------------------------------------------------------------------
 # fused drop-in: patch(fused=True)
 # ---------------------------------------------------------------------------------------------------------------
-import torch  # noqa: E402
-
-
 class LazyPrediction(torch.Tensor):
     """What the patched `_inference` returns under `patch(fused=True)`: a tensor-shaped handle on the raw level
     logits.  The patched `ops.non_max_suppression` recognises it and runs the fused kernels straight from the
@@ -163,9 +215,8 @@ class LazyPrediction(torch.Tensor):
 
 def _make_lazy_inference(kind: str):
     def _inference(self, x):
-        if getattr(self, "export", False) or not x[0].is_cuda or getattr(self, "reg_max", 16) != 16:
+        if not _plain_head(self, kind) or not _levels_ok(self, x):
             return _SAVED[kind](self, x)
-        self.shape = x[0].shape
         return LazyPrediction([xi if xi.dtype in (torch.float32, torch.float16) else xi.float() for xi in x],
                               _ops.HeadSpec.from_module(self))
 
@@ -175,12 +226,11 @@ def _make_lazy_inference(kind: str):
 def _jde_forward_deferred(self, x):
     """JDE.forward (head.py:193-212) in eval mode without the per-anchor state_predictor (:198-204): the three
     convolution branches are concatenated as in the stateless branch (:206) and the state MLP is left to the NMS."""
-    if (self.training or getattr(self, "export", False) or getattr(self, "end2end", False) or self.state_classes is None
-            or not x[0].is_cuda or getattr(self, "reg_max", 16) != 16):
+    if (self.training or self.state_classes is None or not _plain_head(self, "jde")
+            or not all(isinstance(xi, torch.Tensor) and xi.is_cuda for xi in x)):
         return _SAVED["jde_forward"](self, x)
     for i in range(self.nl):
         x[i] = torch.cat((self.cv2[i](x[i]), self.cv3[i](x[i]), self.cv4[i](x[i])), 1)
-    self.shape = x[0].shape
     levels = [xi if xi.dtype in (torch.float32, torch.float16) else xi.float() for xi in x]
     return LazyPrediction(levels, _ops.HeadSpec.from_module(self), state_module=self), x
 
@@ -188,13 +238,11 @@ def _jde_forward_deferred(self, x):
 def _nms_dispatch_fused(prediction, *args, **kwargs):
     pred = prediction[0] if isinstance(prediction, (list, tuple)) else prediction
     if isinstance(pred, LazyPrediction):
-        names = ("conf_thres", "iou_thres", "classes", "agnostic", "multi_label", "labels", "max_det", "nc", "max_time_img",
-                 "max_nms", "max_wh", "in_place", "rotated")
-        kw = dict(zip(names, args))
-        kw.update(kwargs)
+        kw = _nms_kwargs(args, kwargs)
         has_labels = bool(kw.get("labels")) and any(len(lb) for lb in kw["labels"])
         nc = int(kw.get("nc") or 0)
-        if not kw.get("rotated") and not has_labels and nc in (0, pred._spec.nc) and pred._y is None:
+        if (not kw.get("rotated") and not has_labels and nc in (0, pred._spec.nc) and pred._y is None
+                and 1 <= int(kw.get("max_det", 300)) <= 4096 and int(kw.get("max_nms", 30000)) >= 1):
             fused_kw = {k: kw[k] for k in ("conf_thres", "iou_thres", "classes", "agnostic", "multi_label", "max_det",
                                            "max_nms", "max_wh") if k in kw}
             rows = _ops.postprocess_fused(pred._levels, pred._spec, state_mlp=pred.state_mlp(), **fused_kw)

@@ -450,7 +450,7 @@ def test_fused_gather_exchange_over_peer_memory(sarpost, cuda):
         pytest.skip("needs >= 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}", "--master-addr",
-           "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "test_peer_gather.py")]
+           "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "peer_gather_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "peer gather == nccl all-gather: True" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
@@ -749,3 +749,69 @@ def test_empty_batch_returns_empty_list(sarpost, cuda):
     out, counts = sarpost.postprocess_fused(levels, spec, return_padded=True, max_det=10)
     assert tuple(out.shape) == (0, 10, 10) and tuple(counts.shape) == (0,)
     assert sarpost.non_max_suppression(torch.zeros(0, 9, 50, device=cuda), nc=1) == []
+
+
+def test_bench_batch_cfg3_against_oracle(sarpost, cuda):
+    """The bench's own input (bench.py default workload: cfg3, JDE no=327, 16 images generated ON THE DEVICE with seed 3000,
+    cls_mean -4) at full size: the 262-channel extras gather at 136 000 anchors and the deep max_nms cut are compared with
+    the oracle — rows / indices / extras bit-exact on our decoded y for the first two images, and the raw-logit path inside
+    the 1e-4 mismatch budget for the first image."""
+    strides = (4, 8, 16, 32)
+    shapes = sarpost.synth.level_shapes(1280, strides)
+    spec = sarpost.HeadSpec(nc=1, strides=strides, embed_dim=256, state_classes=6)
+    levels = sarpost.synth.head_outputs(16, shapes, 1, 256, 6, cls_mean=-4.0, seed=3000, device=cuda)  # as bench.py, rank 0
+    kw = dict(conf_thres=0.001, iou_thres=0.7, max_det=300, max_nms=30000, multi_label=False)
+    rows, idx = sarpost.postprocess_fused(levels, spec, return_index=True, **kw)
+    assert len(rows) == 16 and all(r.shape == (300, 268) for r in rows)
+    first = [x[:2].contiguous() for x in levels]
+    y = sarpost.decode(first, spec).cpu()
+    assert y.shape == (2, 267, 136000)
+    ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=1, return_index=True, **kw)
+    _assert_same(rows[:2], idx[:2], ref_rows, ref_idx, 1)
+    # raw logits -> oracle decode -> oracle NMS (image 0)
+    lv0 = [x[:1].cpu() for x in levels]
+    y_ref = R.decode_ref(lv0, strides, 1, 16, 256, 6)
+    e_rows, e_idx = R.non_max_suppression_ref(y_ref, nc=1, return_index=True, **kw)
+    ours = {int(k): r for k, r in zip(idx[0].cpu().tolist(), rows[0].cpu())}
+    ref = {int(a): r for (a, c), r in zip(e_idx[0].tolist(), e_rows[0])}
+    bad = sum(1 for k in set(ours) | set(ref)
+              if k not in ours or k not in ref or not torch.allclose(ours[k], ref[k], rtol=1e-5, atol=1e-5 * 32))
+    total = max(len(ours), len(ref))
+    assert total == 300 and bad <= 1e-4 * total, f"{bad} mismatching detections out of {total}"
+
+
+def _extreme_cases(S, sarpost):
+    s4, s3 = (4, 8, 16, 32), (8, 16, 32)
+    spec = sarpost.HeadSpec(nc=1, strides=s4, embed_dim=8, state_classes=0)
+    spec80 = sarpost.HeadSpec(nc=80, strides=s3)
+    return {
+        # 544 000 anchors: more tiles than one tile-list round holds
+        "p2_2560_544k_anchors": (lambda: S.head_outputs(2, S.level_shapes(2560, s4), 1, 8, 0, seed=1, cls_mean=-2.0), spec,
+                                 dict(conf_thres=0.001, iou_thres=0.7)),
+        "max_det_4096_max_nms_100000": (lambda: S.head_outputs(1, S.level_shapes(2560, s4), 1, 8, 0, seed=2, cls_mean=-2.0), spec,
+                                        dict(conf_thres=0.001, iou_thres=0.7, max_det=4096, max_nms=100000)),
+        "nc80_multi_label_672k_slots": (lambda: S.head_outputs(3, S.level_shapes(640, s3), 80, seed=3, cls_mean=-3.0), spec80,
+                                        dict(conf_thres=0.001, iou_thres=0.7, multi_label=True)),
+        "nc80_quantised_scores_ties": (lambda: [x.mul(2).round().div(2) for x in S.head_outputs(2, S.level_shapes(640, s3), 80, seed=4, cls_mean=-1.0)],
+                                       spec80, dict(conf_thres=0.05, iou_thres=0.6, agnostic=True)),
+        "batch_300_more_images_than_sms": (lambda: S.head_outputs(300, S.level_shapes(64, (16,)), 2, seed=5, cls_mean=0.0),
+                                           sarpost.HeadSpec(nc=2, strides=(16,)), dict(conf_thres=0.25, iou_thres=0.5)),
+        # every score equal: one giant score bucket -> the global radix-sort fallback
+        "all_scores_equal_radix_fallback": (lambda: [torch.zeros(1, 65, h, w) for h, w in S.level_shapes(640, s3)],
+                                            sarpost.HeadSpec(nc=1, strides=s3), dict(conf_thres=0.25, iou_thres=0.7)),
+    }
+
+
+@pytest.mark.parametrize("name", ["p2_2560_544k_anchors", "max_det_4096_max_nms_100000", "nc80_multi_label_672k_slots",
+                                  "nc80_quantised_scores_ties", "batch_300_more_images_than_sms", "all_scores_equal_radix_fallback"])
+def test_extreme_geometry(sarpost, cuda, name):
+    """Edges of the supported geometry (formerly tools/extreme_parity.py): fused and decoded entry points bit-exact vs the oracle."""
+    make, spec, kw = _extreme_cases(sarpost.synth, sarpost)[name]
+    levels = [x.to(cuda) for x in make()]
+    rows, idx = sarpost.postprocess_fused(levels, spec, return_index=True, **kw)
+    y = sarpost.decode(levels, spec)
+    ref_rows, ref_idx = R.non_max_suppression_ref(y.cpu(), nc=spec.nc, return_index=True, **kw)
+    _assert_same(rows, idx, ref_rows, ref_idx, spec.nc)
+    rows2 = sarpost.non_max_suppression(y, nc=spec.nc, **kw)
+    for a, b in zip(rows2, ref_rows):
+        assert torch.equal(a.cpu(), b)

@@ -40,7 +40,8 @@ def test_level_shapes_and_anchor_counts(sarpost):
     assert s == [(80, 80), (40, 40), (20, 20)] and sum(h * w for h, w in s) == 8400
     p2 = sarpost.synth.level_shapes(1280, (4, 8, 16, 32))
     assert sum(h * w for h, w in p2) == 136000
-    pts, st = sarpost.head.make_anchors([torch.zeros(1, 1, 2, 3), torch.zeros(1, 1, 1, 2)], [8, 16])
+    from oracle import postprocess_ref as R
+    pts, st = R.make_anchors_ref([(2, 3), (1, 2)], [8, 16])  # anchors are analytic inside the kernels; the oracle restates tal.py
     assert pts.tolist() == [[0.5, 0.5], [1.5, 0.5], [2.5, 0.5], [0.5, 1.5], [1.5, 1.5], [2.5, 1.5], [0.5, 0.5], [1.5, 0.5]]
     assert st.flatten().tolist() == [8.0] * 6 + [16.0] * 2
 
@@ -161,7 +162,6 @@ def test_patch_on_live_reference_modules(sarpost):
             assert ops.non_max_suppression is not orig_nms and head.JDE._inference is not orig_jde
             got = ops.non_max_suppression(y.clone(), 0.25, 0.6, nc=3)          # CPU tensor -> reference code path
             assert all(torch.equal(a, b) for a, b in zip(got, want))
-            m.shape = None
             assert torch.equal(m._inference([x.clone() for x in levels]), want_y)  # CPU levels -> reference decode
         finally:
             sarpost.unpatch()
@@ -170,12 +170,10 @@ def test_patch_on_live_reference_modules(sarpost):
     orig_fwd = head.JDE.forward
     feats = [torch.randn(1, 64, h, w, generator=torch.Generator().manual_seed(i)) for i, (h, w) in enumerate(shapes)]
     with torch.no_grad():
-        m.shape = None
         want_full, want_x = m([f.clone() for f in feats])
         sarpost.patch(fused=True, defer_state=True)
         try:
             assert head.JDE.forward is not orig_fwd
-            m.shape = None
             got_full, got_x = m([f.clone() for f in feats])
             assert torch.equal(got_full, want_full) and all(torch.equal(a, b) for a, b in zip(got_x, want_x))
         finally:
@@ -183,6 +181,93 @@ def test_patch_on_live_reference_modules(sarpost):
     assert head.JDE.forward is orig_fwd
     with pytest.raises(ValueError):
         sarpost.patch(defer_state=True)
+
+
+def test_only_plain_detect_and_jde_heads_take_the_fast_decode(sarpost):
+    """`patch()` replaces `Detect._inference` on the base class, so every subclass inherits it.  OBB decodes
+    with dist2rbox (head.py:303), end2end/v10 heads expect xyxy (head.py:147), Pose/Segment read the anchor cache only
+    the reference `_inference` fills (head.py:354): all of those must keep the reference's own method.  Checked on the
+    live reference classes (build container) — and, below, on stand-in classes so the rule is also covered on the GPU box."""
+    from oracle import ref_shim
+    P = sarpost.plugin
+    if ref_shim.available():
+        _, _, head = ref_shim.load()
+        sarpost.patch()
+        try:
+            ch = (16, 16, 16)
+            assert P._plain_head(head.Detect(nc=2, ch=ch), "detect")
+            assert P._plain_head(head.JDE(nc=1, embed_dim=16, state_classes=6, ch=ch), "jde")
+            assert P._plain_head(head.JDE(nc=1, embed_dim=16, ch=ch), "jde")
+            for sub in (head.OBB(nc=2, ne=1, ch=ch), head.Pose(nc=1, kpt_shape=(17, 3), ch=ch), head.Segment(nc=2, nm=8, npr=16, ch=ch),
+                        head.v10Detect(nc=2, ch=ch)):
+                assert not P._plain_head(sub, "detect"), type(sub).__name__
+                assert not P._plain_head(sub, "jde"), type(sub).__name__
+            d = head.Detect(nc=2, ch=ch)
+            d.export = True
+            assert not P._plain_head(d, "detect")
+            # patch -> (CPU call: reference decode, fills the anchor cache) -> unpatch -> reference call: same y, cache intact
+            m = head.Detect(nc=2, ch=ch)
+            m.stride = torch.tensor([8.0, 16.0, 32.0])
+            m.eval()
+            lv = [torch.randn(1, m.no, s, s) for s in (8, 4, 2)]
+            y_patched = m._inference([x.clone() for x in lv])
+        finally:
+            sarpost.unpatch()
+        assert m.anchors.shape[-1] == 8 * 8 + 4 * 4 + 2 * 2
+        assert torch.equal(m._inference([x.clone() for x in lv]), y_patched)
+
+    class Detect:
+        export, end2end, reg_max = False, False, 16
+
+        def decode_bboxes(self, b, a):
+            return b
+
+        def _inference(self, x):
+            return "ref"
+
+    class JDE(Detect):
+        pass
+
+    class OBB(Detect):
+        def decode_bboxes(self, b, a):
+            return "rotated"
+
+    class Pose(Detect):
+        pass
+
+    class V10(Detect):
+        end2end = True
+
+    sarpost.patch(types.SimpleNamespace(non_max_suppression=lambda *a, **k: None), types.SimpleNamespace(Detect=Detect, JDE=JDE))
+    try:
+        assert P._plain_head(Detect(), "detect") and P._plain_head(JDE(), "jde")
+        assert not P._plain_head(JDE(), "detect") and not P._plain_head(Detect(), "jde")
+        for sub in (OBB(), Pose(), V10()):
+            assert not P._plain_head(sub, "detect")
+            assert sub._inference([torch.zeros(1, 65, 2, 2)]) == "ref"
+    finally:
+        sarpost.unpatch()
+
+
+def test_nms_dispatch_forwards_what_the_library_rejects(sarpost):
+    """argument ranges libsarpost rejects (max_det > 4096, nc > 2048, max_nms < 1, odd dtypes/ranks) must run the
+    reference's function instead of raising inside an unmodified predictor.  `_nms_supported` is the gate (pure host logic;
+    a meta-device tensor stands in for a CUDA one)."""
+    P = sarpost.plugin
+    y = torch.empty(2, 10, 50, device="meta")
+
+    def sup(t, **kw):
+        return P._nms_supported_fields(True, t.dim(), t.dtype, tuple(t.shape), kw)
+
+    assert sup(y)
+    assert sup(y, max_det=4096) and not sup(y, max_det=4097) and not sup(y, max_det=0)
+    assert not sup(y, max_nms=0)
+    assert not sup(y, rotated=True)
+    assert not sup(torch.empty(2, 4000, 50, device="meta"))            # nc = 3996 > 2048
+    assert sup(torch.empty(2, 4000, 50, device="meta"), nc=80)
+    assert not sup(torch.empty(2, 10, 50, device="meta", dtype=torch.int32))
+    assert not sup(torch.empty(10, 50, device="meta"))
+    assert not P._nms_supported_fields(False, 3, torch.float32, (2, 10, 50), {})  # CPU tensor
 
 
 def test_scale_params_equal_reference_host_arithmetic(sarpost):

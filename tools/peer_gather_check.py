@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N tools/test_peer_gather.py — fused gather+exchange (K5 peer stores) vs NCCL all-gather."""
+"""torchrun --nproc-per-node N tools/peer_gather_check.py — fused gather+exchange (K5 peer stores) vs NCCL all-gather."""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import sarpost
