@@ -1,16 +1,31 @@
 #!/usr/bin/env python
-"""bench.py — post-processed images/sec (decode + NMS) on 1/2/4/8 B200, with roofline and CPU baseline.
+"""bench.py — post-processed images/sec (decode + NMS) on 1/2/4/8 B200, with roofline, the reference's own GPU and
+CPU paths timed beside it, a clustered (suppression-heavy) leg, the host-buffer e2e figure and — at N > 1 — the sliced
+inference (SAHI) exchange step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg5|cfg1] [--batch B]
-    python bench.py --impl reference ...        # the reference's CPU path (oracle port) on the host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg2|cfg5|cfg1|cfg4] [--batch B]
+    python bench.py --impl reference ...        # the reference's CPU path on the host cores (no GPU, no libsarpost.so)
 
-A step = one pass of the hot path (fused decode + candidate filter + top-k + NMS + gather) over one
-batch of synthetic raw head logits resident in HBM.  Default workload = BASELINE.json's headline
-configuration: 1280x1280 with the P2 stride-4 head (136 000 anchors), SAR posture JDE head (nc=1,
-256-d embedding + 6 state logits, no = 327), val-mode thresholds conf 0.001 / IoU 0.7 / max_nms 30000 /
-max_det 300, 16 images per GPU (cfg/default.yaml:15).  One batch of inputs is 2.85 GB (hot channels
-566 MB) — larger than the 126 MB L2, so no flush is needed between steps.
-Multi-GPU: images are independent -> weak scaling, batch sharded by rank, no data-path collective.
+A step = one pass of the hot path (fused decode + candidate filter + top-k + NMS + gather) over one batch of synthetic
+raw head logits resident in HBM.  Default workload = BASELINE.json's headline configuration: 1280x1280 with the P2
+stride-4 head (136 000 anchors), SAR posture JDE head (nc=1, 256-d embedding + 6 state logits, no = 327), val-mode
+thresholds conf 0.001 / IoU 0.7 / max_nms 30000 / max_det 300, 16 images per GPU (cfg/default.yaml:15).  One batch of
+inputs is 2.85 GB (hot channels 566 MB) — larger than the 126 MB L2, so no flush is needed between steps.
+Multi-GPU: images are independent -> weak scaling, batch sharded by rank, no data-path collective in the image step;
+the one real exchange of the path (sliced inference: tiles of a frame on different ranks) is measured in the `sahi` block.
+
+Keys of the JSON line beyond the contract:
+  single_stream   the same K steps strictly one batch in flight
+  roofline        K1 (fused decode) algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json
+  clustered       the same shapes/thresholds on inputs whose class logits carry 50 Gaussian blobs per image: neighbouring
+                  anchors fire together and overlap, so NMS has to suppress (the regime of a trained detector)
+  reference_gpu   the reference's own path as a `device=0` user runs it on this GPU: JDE._inference (torch CUDA ops) +
+                  ops.non_max_suppression (torch CUDA ops + torchvision.ops.nms CUDA) — the UNMODIFIED reference code from
+                  baseline/_ref when that install is present (kind "reference"), else the oracle's restatement of the same
+                  op sequence on CUDA tensors (kind "port")
+  cpu_baseline    the reference's CPU path on the host cores, bounded sample (N = 1 only)
+  e2e             HOST buffers through the C-ABI host entry, H2D + D2H inside the timed region (+ the measured H2D ceiling)
+  sahi            (N > 1) cfg4: 512 tiles of 640x640 sharded over the ranks, per-tile fused call -> exchange -> cross-tile merge
 """
 from __future__ import annotations
 
@@ -43,6 +58,7 @@ def ensure_built():
             time.sleep(1.0)
         time.sleep(2.0)
 
+
 WORKLOADS = {
     # name: (imgsz, strides, nc, embed_dim, state_classes, per-GPU batch, nms kwargs, cls_mean, description)
     "cfg3": (1280, (4, 8, 16, 32), 1, 256, 6, 16,
@@ -57,7 +73,7 @@ WORKLOADS = {
     "cfg4": (640, (8, 16, 32), 1, 256, 6, 512,
              dict(conf_thres=0.25, iou_thres=0.7, max_det=300, max_nms=30000, multi_label=False), -4.0,
              "SAHI-style 640 tiles of 4000x3000 frames (48 tiles/frame), 512 tiles in total sharded over the GPUs "
-             "(strong scaling), per-tile post-process + all-gather of counts/boxes + cross-tile merge per frame"),
+             "(strong scaling), per-tile post-process + exchange of counts/boxes + cross-tile merge per frame"),
     "cfg5": (640, (8, 16, 32), 6, 0, 0, 32,
              dict(conf_thres=0.001, iou_thres=0.7, max_det=300, max_nms=30000, multi_label=True), -4.0,
              "val-mode multi_label sweep at 640x640, Detect nc=6 no=70, conf 0.001, 32 images per GPU"),
@@ -78,47 +94,15 @@ def parse_args():
                          "in flight, each with its own input buffers (the NMS kernel of one batch overlaps the fused "
                          "decode of the next); 1 = strictly one batch in flight.  The single-stream figure is always "
                          "measured too and reported as `single_stream`.")
-    ap.add_argument("--quick", action="store_true", help="profiling run: no clock probe, no e2e, no CPU baseline")
+    ap.add_argument("--quick", action="store_true", help="profiling run: no clock probe, no extra legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
+    ap.add_argument("--no-clustered", action="store_true")
+    ap.add_argument("--no-sahi", action="store_true")
+    ap.add_argument("--blobs", type=int, default=0, help="profiling: make the MAIN workload the clustered variant (Gaussian blobs per image)")
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU baseline sample (default: ~10-30 s of work)")
     return ap.parse_args()
-
-
-# ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle port) on the host cores
-# ------------------------------------------------------------------------------------------------
-def cpu_threads():
-    # the reference's NUM_THREADS (ultralytics/utils/__init__.py:43), applied by select_device("cpu")
-    return min(8, max(1, (os.cpu_count() or 1) - 1))
-
-
-def cpu_reference_step(levels_cpu, strides, nc, ed, sc, kw):
-    """decode + non_max_suppression exactly as the reference runs them on CPU (oracle port; the
-    suppression call is torchvision.ops.nms like ops.py:296 when torchvision is importable)."""
-    from oracle import postprocess_ref as R
-
-    try:
-        import torchvision  # noqa: F401
-        nms_fn = R.nms_torchvision
-    except Exception:
-        nms_fn = R.nms_ref
-    y = R.decode_ref(levels_cpu, strides, nc, 16, ed, sc)
-    return R.non_max_suppression_ref(y, nc=nc, nms_fn=nms_fn, stable_topk=False, **kw)
-
-
-def time_cpu_baseline(levels_cpu, strides, nc, ed, sc, kw, repeats=1):
-    import torch
-
-    torch.set_num_threads(cpu_threads())
-    n_img = levels_cpu[0].shape[0]
-    best = None
-    for _ in range(repeats):
-        t = time.perf_counter()
-        cpu_reference_step(levels_cpu, strides, nc, ed, sc, kw)
-        dt = time.perf_counter() - t
-        best = dt if best is None else min(best, dt)
-    return n_img / best, best
 
 
 def load_synth_standalone():
@@ -130,6 +114,71 @@ def load_synth_standalone():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's own implementation of the path (CPU arm, cpu_baseline, reference_gpu)
+# ------------------------------------------------------------------------------------------------
+def cpu_threads():
+    # the reference's NUM_THREADS (ultralytics/utils/__init__.py:43), applied by select_device("cpu")
+    return min(8, max(1, (os.cpu_count() or 1) - 1))
+
+
+class ReferencePath:
+    """decode + non_max_suppression the way the reference runs them, on `device`.
+
+    kind "reference": the UNMODIFIED reference imported from baseline/_ref (or /root/reference in the build container):
+        head.JDE._inference / head.Detect._inference (nn/modules/head.py:100-131, :214-249) followed by
+        utils/ops.non_max_suppression (:167-316), which calls torchvision.ops.nms (:296) — CPU or CUDA build, whichever
+        device the tensors are on.  `max_time_img` is raised so the soft wall-clock limit (:312-314) never truncates a batch.
+    kind "port": no reference install on this machine — the oracle's restatement of the same op sequence
+        (oracle/postprocess_ref.py, pinned bit-equal to the live reference by tests/test_oracle.py) with torchvision.ops.nms.
+    """
+
+    def __init__(self, strides, nc, ed, sc, device):
+        import torch
+
+        self.strides, self.nc, self.ed, self.sc, self.device = strides, nc, ed, sc, torch.device(device)
+        self.kind, self.source, self.module = "port", "oracle/postprocess_ref.py", None
+        if not os.environ.get("SARPOST_BENCH_FORCE_PORT"):
+            try:
+                from oracle import ref_shim
+
+                if ref_shim.available():
+                    self.ops, _, head = ref_shim.load()
+                    ch = tuple(64 for _ in strides)
+                    with torch.no_grad():
+                        m = (head.JDE(nc=nc, embed_dim=ed, state_classes=(sc or None), ch=ch) if ed else head.Detect(nc=nc, ch=ch))
+                        m.stride = torch.tensor([float(s) for s in strides])
+                        m.eval()
+                        self.module = m.to(self.device)
+                    self.kind, self.source = "reference", ref_shim.source()
+            except Exception as e:  # noqa: BLE001  (a broken install must not take the bench down: fall back to the port)
+                print(f"[bench] reference import failed ({type(e).__name__}: {e}); using the oracle port", file=sys.stderr)
+                self.module = None
+                self.kind, self.source = "port", "oracle/postprocess_ref.py"
+
+    def describe(self):
+        import torch
+        import torchvision
+
+        what = ("unmodified reference code (" + self.source + "): head._inference + ops.non_max_suppression" if self.kind == "reference"
+                else "oracle port of head.py:214-249 + ops.py:167-316 (pinned bit-equal to the live reference)")
+        return f"{what}, torch {torch.__version__} ops on {self.device.type} + torchvision {torchvision.__version__} ops.nms ({self.device.type})"
+
+    def step(self, levels, kw):
+        import torch
+
+        with torch.no_grad():
+            if self.kind == "reference":
+                y = self.module._inference(list(levels))
+                return self.ops.non_max_suppression(y, nc=self.nc, max_time_img=1e9, **kw)
+            import torchvision
+
+            from oracle import postprocess_ref as R
+
+            y = R.decode_ref(levels, self.strides, self.nc, 16, self.ed, self.sc, device=self.device)
+            return R.non_max_suppression_ref(y, nc=self.nc, nms_fn=torchvision.ops.nms, stable_topk=False, device=self.device, **kw)
 
 
 def run_reference_arm(args):
@@ -145,20 +194,22 @@ def run_reference_arm(args):
     per_step = args.cpu_images or (1 if args.workload == "cfg3" else min(bs, 8))
     levels = synth.head_outputs(per_step, shapes, nc, ed, sc, cls_mean=cls_mean, seed=3000)
     torch.set_num_threads(cpu_threads())
+    ref = ReferencePath(strides, nc, ed, sc, "cpu")
     for _ in range(max(args.warmup, 1)):
-        cpu_reference_step(levels, strides, nc, ed, sc, kw)
+        ref.step(levels, kw)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_step(levels, strides, nc, ed, sc, kw)
+        ref.step(levels, kw)
     dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = f"{per_step} image(s) of {args.workload} per step, oracle port of head.py:214-249 + ops.py:167-316 with torchvision.ops.nms CPU"
+    sample = f"{per_step} image(s) of {args.workload} per step; {ref.describe()}; {cpu_threads()} torch threads, host has {os.cpu_count()} cpus"
     line = {
-        "impl": "reference", "metric": "post-processed images/sec (decode+NMS)", "value": value, "unit": "images/s",
+        "impl": "reference", "impl_detail": "reference-cpu" if ref.kind == "reference" else "reference-cpu-port",
+        "metric": "post-processed images/sec (decode+NMS)", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "images_per_step": per_step},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cpu_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cpu_threads(), "kind": ref.kind, "sample": sample},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -216,9 +267,6 @@ class ClockSampler:
 
 L2_BYTES = 126e6  # B200 L2
 
-# ------------------------------------------------------------------------------------------------
-# GPU arm
-# ------------------------------------------------------------------------------------------------
 _JSON_OUT = None
 
 
@@ -239,139 +287,425 @@ def emit(line: dict) -> None:
     out.flush()
 
 
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class Ctx:
+    """What every leg of the GPU arm needs."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        import sarpost
+
+        self.args, self.torch, self.dist, self.sarpost = args, torch, dist, sarpost
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        try:  # NUMA locality for the pinned host buffers of the e2e leg: run this rank on the CPUs next to its GPU
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(self.local))
+        except Exception:
+            pass
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+
+def rotating(level_sets):
+    it = [0]
+
+    def nxt():
+        it[0] += 1
+        return level_sets[it[0] % len(level_sets)]
+
+    return nxt
+
+
+def time_steps(cx, step, n, streams=None):
+    """K steps timed with CUDA events on the launching stream (round-robin over `streams` when given), barrier +
+    synchronize on both sides.  Returns this rank's milliseconds."""
+    torch = cx.torch
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cx.barrier()
+    ev0.record()
+    if not streams:
+        for _ in range(n):
+            step()
+    else:
+        for s_ in streams:
+            s_.wait_event(ev0)
+        for i in range(n):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                step()
+        for s_ in streams:
+            torch.cuda.current_stream().wait_stream(s_)
+    ev1.record()
+    cx.barrier()
+    return ev0.elapsed_time(ev1)
+
+
+def stage_means(cx, step, n):
+    """Per-kernel CUDA-event durations recorded by the library on the launching stream (mean over n steps)."""
+    ops = cx.sarpost.ops
+    ops.stage_timing(True, accumulate=True)
+    for _ in range(n):
+        step()
+    st = list(ops.stage_times())
+    ops.stage_timing(False)
+    return st
+
+
+def count_candidates(torch, levels, nc, kw):
+    n = 0
+    for x in levels:  # candidates = anchors whose best class probability passes conf (bookkeeping, untimed)
+        p = x[:, 64:64 + nc].sigmoid()
+        n += int(((p > kw["conf_thres"]).sum() if kw.get("multi_label") and nc > 1 else (p.amax(1) > kw["conf_thres"]).sum()).item())
+    return n
+
+
+def leg_clustered(cx, spec, shapes, nc, ed, sc, bs, kw, cls_mean, steps):
+    """Shapes / thresholds of the main workload on clustered inputs (synth.head_outputs(blobs=50)): the NMS kernel
+    has to walk deep into the sorted candidates because most of them are suppressed."""
+    torch, sarpost = cx.torch, cx.sarpost
+    levels = sarpost.synth.head_outputs(bs, shapes, nc, ed, sc, cls_mean=cls_mean, seed=3500 + cx.rank, device=cx.dev, blobs=50)
+    stats = torch.zeros((bs, 4), dtype=torch.int64, device=cx.dev)
+
+    def step():
+        return sarpost.postprocess_fused(levels, spec, return_padded=True, **kw)
+
+    for _ in range(3):
+        out, counts = step()
+    ms = time_steps(cx, step, steps)
+    st = stage_means(cx, step, min(steps, 50))
+    sarpost.postprocess_fused(levels, spec, return_padded=True, nms_stats=stats, **kw)
+    torch.cuda.synchronize()
+    (ms,) = cx.max_over_ranks(ms)
+    s = stats.double().mean(0).tolist()
+    return {"value": bs * cx.world * steps / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps,
+            "k1_ms": st[0], "k4_ms": st[1], "k5_ms": st[2],
+            "keeps_depth": s[0], "pair_tests": s[1], "sub_chunks": s[2], "collections": s[3],
+            "detections_per_image": float(counts.sum().item()) / bs,
+            "input": "synth.head_outputs(blobs=50): 50 Gaussian bumps (+6 logit) per image and level on the class logits, box logits of "
+                     "fired anchors pulled to a common shape so neighbours overlap; one batch in flight",
+            "note": "per image means on rank 0: keeps_depth = sorted candidates NMS consumed before it had max_det keeps (or ran out), "
+                    "pair_tests = IoU tests executed, sub_chunks / collections = passes of the NMS / selection loops"}
+
+
+def leg_reference_gpu(cx, levels, strides, nc, ed, sc, kw, n_img, reps, our_rows):
+    """The reference's own path on this GPU (see ReferencePath) on the first n_img images of the batch."""
+    torch = cx.torch
+    ref = ReferencePath(strides, nc, ed, sc, cx.dev)
+    sub = [x[:n_img].contiguous() for x in levels]
+    for _ in range(2):
+        rows = ref.step(sub, kw)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(cx.local)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(reps):
+        rows = ref.step(sub, kw)
+    ev1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    # kept-set agreement with our rows for the same images (ours are bit-equal to the CPU oracle on identical decoded
+    # input; torchvision's CUDA kernel may legitimately differ on 1-ulp IoU pairs and on score ties — SURVEY §7 hard part 1)
+    only_ours = only_ref = total = 0
+    for b in range(n_img):
+        a, r = our_rows[b][:, :6].float().cpu(), rows[b][:, :6].float().cpu()
+        total += max(a.shape[0], r.shape[0])
+        if a.shape[0] and r.shape[0]:
+            d = (a[:, None, :] - r[None, :, :]).abs()
+            tol = 1e-4 * r[None, :, :].abs() + 2e-3
+            hit = (d <= tol).all(-1)
+            only_ours += int((~hit.any(1)).sum())
+            only_ref += int((~hit.any(0)).sum())
+        else:
+            only_ours += a.shape[0]
+            only_ref += r.shape[0]
+    return {"value": n_img * reps / (ms / 1e3), "unit": "images/s", "ms_per_image": ms / (n_img * reps), "wall_ms_per_image": 1e3 * wall / (n_img * reps),
+            "kind": ref.kind, "images_per_step": n_img, "steps": reps, "what": ref.describe(),
+            "kept_set_diff_vs_sarpost": {"only_in_sarpost": only_ours, "only_in_reference_gpu": only_ref, "of": total},
+            "clocks": clocks.summary()}
+
+
+def leg_e2e(cx, levels, spec, bs, kw):
+    """HOST buffers through the C-ABI host entry (H2D + D2H inside the timed region), and the H2D ceiling of this rank
+    measured the same way (all ranks copying concurrently): the bare cudaMemcpyAsync of the same bytes, nothing else."""
+    torch, sarpost = cx.torch, cx.sarpost
+    host_levels = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x) for x in levels]
+    ctx = sarpost.HostContext(cx.local)
+    out_host = torch.empty((bs, kw["max_det"], 6 + spec.nm), dtype=torch.float32, pin_memory=True)
+    e2e_steps = max(3, min(cx.args.steps, 20))
+    for _ in range(2):
+        ctx.postprocess(host_levels, spec, out=out_host, **kw)
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.postprocess(host_levels, spec, out=out_host, **kw)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    (dt,) = cx.max_over_ranks(dt)
+    h2d, d2h = ctx.last_traffic()
+    ctx.close()
+    # H2D ceiling: the same hot channels (box + cls rows of every image and level), one contiguous copy per image and
+    # level exactly like the host entry issues them, all ranks at once
+    nch = 64 + spec.nc
+    dst = [torch.empty((bs, nch) + tuple(x.shape[2:]), dtype=x.dtype, device=cx.dev) for x in levels]
+    copy_stream = torch.cuda.Stream()
+
+    def copy_all():
+        with torch.cuda.stream(copy_stream):
+            for d, h in zip(dst, host_levels):
+                for b in range(bs):
+                    d[b].copy_(h[b, :nch], non_blocking=True)
+
+    copy_all()
+    copy_stream.synchronize()
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copy_all()
+    copy_stream.synchronize()
+    dt_c = time.perf_counter() - t0
+    (dt_c,) = cx.max_over_ranks(dt_c)
+    hot = sum(d.numel() * d.element_size() for d in dst)
+    value = bs * cx.world * e2e_steps / dt
+    ceiling = bs * cx.world * e2e_steps / dt_c
+    del host_levels, dst
+    return {"value": value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+            "api": "sarpost_fused_host (pinned host level tensors in, host rows out)",
+            "h2d_ceiling": {"value": ceiling, "unit": "images/s", "gbytes_per_s_per_gpu": hot * e2e_steps / dt_c / 1e9,
+                            "gbytes_per_s_aggregate": hot * cx.world * e2e_steps / dt_c / 1e9,
+                            "what": f"bare pinned->device cudaMemcpyAsync of the same {hot / 1e6:.0f} MB of box+cls channels per step, "
+                                    f"{cx.world} rank(s) concurrently, max over ranks"},
+            "frac_of_h2d_ceiling": value / ceiling}
+
+
+def leg_sahi(cx, steps):
+    """cfg4 (BASELINE configs[3]): 512 SAHI tiles (640x640, 48 per 4000x3000 frame) sharded over the ranks — strong
+    scaling.  Step = per-tile fused post-process -> exchange -> cross-tile merge per frame.  Two shardings:
+      tiles   equal tile ranges per rank; K5 stores rows+counts into every rank's buffer over NVLink peer memory, one
+              signal-pad barrier, every rank merges the frames it owns (frames straddle ranks);
+      frames  whole frames per rank (dist.shard_frames): the merge is rank-local, only the merged per-frame rows are
+              exchanged (again by peer stores, from the gather kernel of the merge).
+    Both are timed; `value` is the better one and says which."""
+    torch, sarpost, D = cx.torch, cx.sarpost, cx.sarpost.dist
+    imgsz, strides, nc, ed, sc, total_tiles, kw, cls_mean, desc = WORKLOADS["cfg4"]
+    world, rank, dev = cx.world, cx.rank, cx.dev
+    spec = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=sc)
+    shapes = sarpost.synth.level_shapes(imgsz, strides)
+    origins1 = D.sahi_grid(4000, 3000, 640, 0.2).to(dev)
+    tpf = origins1.shape[0]
+    n_frames = -(-total_tiles // tpf)
+    max_det = kw["max_det"]
+    res = {}
+    n_in_flight = 2 if world > 1 else 1
+
+    class Marks:
+        def __init__(self, on):
+            self.on, self.ev = on, []
+
+        def __call__(self):
+            if self.on:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                self.ev.append(e)
+
+    def run(name, step_factory, n_local, phase_names):
+        hot = n_local * sum(h * w for h, w in shapes) * (64 + nc) * 4
+        n_sets = max(n_in_flight, min(int(math.ceil(2 * L2_BYTES / max(hot, 1))), 16))
+        sets = [sarpost.synth.head_outputs(n_local, shapes, nc, ed, sc, cls_mean=cls_mean, seed=4000 + 17 * rank + 1000 * s_, device=dev)
+                for s_ in range(n_sets)]
+        nxt = rotating(sets)
+        pipes = [step_factory(i) for i in range(n_in_flight)]
+        streams = [torch.cuda.Stream() for _ in range(n_in_flight)]
+        for i, s_ in enumerate(streams):  # warm-up: workspaces are cached per stream
+            s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                for _ in range(3):
+                    pipes[i](nxt())
+        for _ in range(3):
+            pipes[0](nxt())
+        cx.barrier()
+        ms1 = time_steps(cx, lambda: pipes[0](nxt()), steps)
+        # steps alternate between the pipelines (own exchange buffers) on their own streams: the barrier + merge latency
+        # chain of one step overlaps the per-tile kernels of the next
+        k = [0]
+
+        def one():
+            k[0] += 1
+            pipes[(k[0] - 1) % n_in_flight](nxt())
+
+        ms2 = time_steps(cx, one, steps, streams) if n_in_flight > 1 else ms1
+        ms1, ms2 = cx.max_over_ranks(ms1, ms2)
+        # per-phase breakdown (one step in flight, events between the phases, mean over a few steps)
+        reps, acc = 20, None
+        for _ in range(reps):
+            ev = pipes[0](nxt(), phases=True)
+            torch.cuda.synchronize()
+            d = [ev[i].elapsed_time(ev[i + 1]) for i in range(len(ev) - 1)]
+            acc = d if acc is None else [a + b for a, b in zip(acc, d)]
+        acc = cx.max_over_ranks(*[a / reps for a in acc])
+        res[name] = {"tiles_per_s": total_tiles * steps / (ms2 / 1e3), "ms_per_step": ms2 / steps,
+                     "one_in_flight": {"tiles_per_s": total_tiles * steps / (ms1 / 1e3), "ms_per_step": ms1 / steps},
+                     "tiles_on_rank0": n_local, "input_sets": n_sets, "hot_mb_in_rotation": n_sets * hot / 1e6,
+                     "phase_ms_max_over_ranks": dict(zip(phase_names, acc))}
+        del sets, pipes
+        torch.cuda.empty_cache()
+
+    # ---- sharding by tiles: equal ranges, fused gather + exchange, frames merged by their owner ----
+    if total_tiles % world == 0:
+        per = total_tiles // world
+        lo = rank * per
+        f_lo, f_hi = D.shard_range(n_frames, rank, world)
+        origins = origins1.repeat(n_frames, 1)
+
+        def factory_tiles(i):
+            peer = None
+            if world > 1:
+                peer = D.PeerGatherBuffer(per, max_det, 6, dev, total_slots=n_frames * tpf, slot_offset=lo)
+                for r_, c_, _, _ in peer._bufs:  # slots beyond total_tiles (padding of the last frame) stay empty tiles
+                    c_.zero_()
+            g_rows = torch.zeros((n_frames * tpf, max_det, 6), dtype=torch.float32, device=dev) if world == 1 else None
+            g_cnt = torch.zeros((n_frames * tpf,), dtype=torch.int32, device=dev) if world == 1 else None
+
+            def step(levels, phases=False):
+                mark = Marks(phases)
+                mark()
+                if peer is not None:
+                    rows_all, cnt_all = sarpost.postprocess_fused(levels, spec, with_extras=False, peer_out=peer.next(), **kw)
+                    mark()
+                    peer.barrier()
+                else:
+                    rows_all, cnt_all = g_rows, g_cnt
+                    sarpost.postprocess_fused(levels, spec, with_extras=False, return_padded=True, out=(g_rows[:per], g_cnt[:per]), **kw)
+                    mark()
+                mark()
+                if f_hi > f_lo:
+                    sarpost.merge_tiles(rows_all[f_lo * tpf:f_hi * tpf], cnt_all[f_lo * tpf:f_hi * tpf], origins[f_lo * tpf:f_hi * tpf], tpf,
+                                        iou_thres=kw["iou_thres"], max_det=max_det, return_padded=True)
+                mark()
+                return mark.ev
+
+            return step
+
+        run("tiles", factory_tiles, per, ("per_tile_fused", "exchange_barrier", "merge"))
+
+    # ---- sharding by frames: merge is rank-local, merged frames exchanged by the merge's own gather kernel ----
+    spans = [D.shard_range(n_frames, r, world) for r in range(world)]
+    if world > 1 and all(hi > lo for lo, hi in spans):
+        f_lo, f_hi = spans[rank]
+        t_lo, t_hi = f_lo * tpf, min(f_hi * tpf, total_tiles)
+        nf, n_local = f_hi - f_lo, t_hi - t_lo
+        org = origins1.repeat(nf, 1)
+
+        def factory_frames(i):
+            peer = D.PeerGatherBuffer(nf, max_det, 6, dev, total_slots=n_frames, slot_offset=f_lo)
+            rows = torch.zeros((nf * tpf, max_det, 6), dtype=torch.float32, device=dev)
+            cnt = torch.zeros((nf * tpf,), dtype=torch.int32, device=dev)
+
+            def step(levels, phases=False):
+                mark = Marks(phases)
+                mark()
+                sarpost.postprocess_fused(levels, spec, with_extras=False, return_padded=True, out=(rows[:n_local], cnt[:n_local]), **kw)
+                mark()
+                sarpost.merge_tiles(rows, cnt, org, tpf, iou_thres=kw["iou_thres"], max_det=max_det, peer_out=peer.next())
+                mark()
+                peer.barrier()
+                mark()
+                return mark.ev
+
+            return step
+
+        run("frames", factory_frames, n_local, ("per_tile_fused", "merge_with_peer_stores", "barrier"))
+
+    best = max(res, key=lambda k_: res[k_]["tiles_per_s"])
+    return {"workload": "cfg4: " + desc, "value": res[best]["tiles_per_s"], "unit": "tiles/s", "ms_per_step": res[best]["ms_per_step"],
+            "sharding": best, "scaling": "strong", "total_tiles": total_tiles, "tiles_per_frame": tpf, "frames": n_frames, "steps": steps,
+            "exchange": ("gather kernel stores rows+counts into every rank's symmetric-memory buffer over NVLink (P2P stores) + one signal-pad "
+                         "barrier; no NCCL collective in the step") if world > 1 else "none (one rank)",
+            "in_flight": f"{n_in_flight} step(s) in flight, each on its own stream with its own exchange buffers (`one_in_flight` = strictly sequential steps)",
+            "by_sharding": res}
+
+
 def main():
     args = parse_args()
     claim_stdout()
-    if args.impl == "reference":  # CPU arm: oracle port + torchvision only — libsarpost.so is neither built nor loaded here
+    if args.impl == "reference":  # CPU arm: reference / oracle port + torchvision only — libsarpost.so is neither built nor loaded here
         return run_reference_arm(args)
     ensure_built()
     if args.quick:
-        args.no_e2e = args.no_cpu_baseline = True
+        args.no_e2e = args.no_cpu_baseline = args.no_reference_gpu = args.no_clustered = args.no_sahi = True
 
-    import torch
-    import torch.distributed as dist
-
-    import sarpost
-    from sarpost import synth
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    try:  # NUMA locality for the pinned host buffers of the e2e leg: run this rank on the CPUs next to its GPU
-        import pynvml
-
-        pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
-    except Exception:
-        pass
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    cx = Ctx(args)
+    torch, dist, sarpost = cx.torch, cx.dist, cx.sarpost
+    synth = sarpost.synth
+    world, rank, dev = cx.world, cx.rank, cx.dev
     n_gpus = world
 
     imgsz, strides, nc, ed, sc, bs, kw, cls_mean, desc = WORKLOADS[args.workload]
     bs = args.batch or bs
+    if args.workload == "cfg4":  # as a --workload the SAHI job is the whole line (strong scaling)
+        blk = leg_sahi(cx, args.steps)
+        if rank == 0:
+            emit({"metric": "post-processed tiles/sec (decode+NMS+merge)", "value": blk["value"], "unit": "tiles/s", "n_gpus": n_gpus,
+                  "steps": args.steps, "warmup": 3, "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                  "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": blk["workload"]}, "sahi": blk})
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     if args.streams <= 0:
         args.streams = 2 if bs >= 8 else 1
-    sahi = args.workload == "cfg4"
-    scaling = "weak"
-    if sahi:  # strong scaling: a fixed total of tiles is sharded over the ranks
-        scaling = "strong"
-        total_tiles = bs
-        if total_tiles % n_gpus:
-            raise SystemExit("cfg4 needs the tile count to divide by the number of GPUs")
-        bs = total_tiles // n_gpus
-        args.no_e2e = True
     spec = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=sc)
     shapes = synth.level_shapes(imgsz, strides)
     anchors = sum(h * w for h, w in shapes)
-    levels = synth.head_outputs(bs, shapes, nc, ed, sc, cls_mean=cls_mean, seed=1000 * 3 + rank, device=dev)
+    levels = synth.head_outputs(bs, shapes, nc, ed, sc, cls_mean=cls_mean, seed=1000 * 3 + rank, device=dev, blobs=args.blobs)
     torch.cuda.synchronize()
-
-    if sahi:
-        origins1 = sarpost.dist.sahi_grid(4000, 3000, 640, 0.2).to(dev)  # (48, 2)
-        tpf = origins1.shape[0]
-        n_frames = -(-total_tiles // tpf)
-        f_lo, f_hi = sarpost.dist.shard_range(n_frames, rank, world)
-        # gathered detections of ALL tiles (6 columns), padded with empty tiles up to whole frames
-        g_rows = torch.zeros((n_frames * tpf, kw["max_det"], 6), dtype=torch.float32, device=dev)
-        g_cnt = torch.zeros((n_frames * tpf,), dtype=torch.int32, device=dev)
-        origins = origins1.repeat(n_frames, 1)
-        lo = rank * bs
-        peer = None
-        if world > 1 and not os.environ.get("SARPOST_BENCH_NCCL_GATHER"):
-            # fused gather + exchange: K5 stores this rank's rows/counts into every rank's buffer over NVLink
-            peer = sarpost.dist.PeerGatherBuffer(bs, kw["max_det"], 6, dev)
-
-        def step():
-            # boxes only: the extras of the few rows that survive the merge are fetched afterwards from the rank
-            # that owns the tile (sarpost.gather_extras), not for 300 rows of every tile
-            if peer is not None:
-                rows_all, cnt_all = sarpost.postprocess_fused(levels, spec, with_extras=False, peer_out=peer.next(), **kw)
-                peer.barrier()
-                if f_hi > f_lo:
-                    t0, t1 = f_lo * tpf, min(f_hi * tpf, total_tiles)
-                    g_rows[t0:t1].copy_(rows_all[t0:t1])  # pad the last frame with empty tiles (g_cnt stays 0 there)
-                    g_cnt[t0:t1].copy_(cnt_all[t0:t1])
-                    return sarpost.merge_tiles(g_rows[f_lo * tpf:f_hi * tpf], g_cnt[f_lo * tpf:f_hi * tpf],
-                                               origins[f_lo * tpf:f_hi * tpf], tpf, iou_thres=kw["iou_thres"],
-                                               max_det=kw["max_det"], return_padded=True)
-                return rows_all, cnt_all
-            out, counts = sarpost.postprocess_fused(levels, spec, return_padded=True, with_extras=False, **kw)
-            g_rows[lo:lo + bs].copy_(out)
-            g_cnt[lo:lo + bs].copy_(counts)
-            if world > 1:
-                dist.all_gather_into_tensor(g_rows[:total_tiles], g_rows[lo:lo + bs])
-                dist.all_gather_into_tensor(g_cnt[:total_tiles], g_cnt[lo:lo + bs])
-            if f_hi > f_lo:
-                return sarpost.merge_tiles(g_rows[f_lo * tpf:f_hi * tpf], g_cnt[f_lo * tpf:f_hi * tpf],
-                                           origins[f_lo * tpf:f_hi * tpf], tpf, iou_thres=kw["iou_thres"],
-                                           max_det=kw["max_det"], return_padded=True)
-            return out, counts
-    else:
-        def step():
-            return sarpost.postprocess_fused(next_levels(), spec, return_padded=True, **kw)
 
     # L2 rule: a batch whose hot channels do not clearly exceed the 126 MB L2 is rotated over enough identical copies
     # of the inputs that a buffer has been evicted by the time it is read again (no flush kernel in the timed region)
     hot_bytes = bs * anchors * (64 + nc) * 4
-    n_sets = 1 if (sahi or hot_bytes >= 2 * L2_BYTES) else min(int(math.ceil(2 * L2_BYTES / hot_bytes)), 128)
-    if not sahi:
-        n_sets = max(n_sets, args.streams)
-    level_sets = [levels] + [[x.clone() for x in levels] for _ in range(n_sets - 1)]
-    set_iter = [0]
+    n_sets = 1 if hot_bytes >= 2 * L2_BYTES else min(int(math.ceil(2 * L2_BYTES / hot_bytes)), 128)
+    n_sets = max(n_sets, args.streams)
+    next_levels = rotating([levels] + [[x.clone() for x in levels] for _ in range(n_sets - 1)])
 
-    def next_levels():
-        set_iter[0] += 1
-        return level_sets[set_iter[0] % n_sets]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def step():
+        return sarpost.postprocess_fused(next_levels(), spec, return_padded=True, **kw)
 
     for _ in range(max(args.warmup, 3)):
         out, counts = step()
-    barrier()
-    launches_per_step = sarpost.ops.last_launch_count() + (3 if sahi else 0)  # cfg4: fused (3) + merge (3)
+    cx.barrier()
+    launches_per_step = sarpost.ops.last_launch_count()
 
     # ---- timed region: K steps, CUDA events on the launching (current) stream ----
-    clocks = ClockSampler(local)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(cx.local)
     clocks.start()
-    barrier()
     # (a) strictly one batch in flight: K steps back to back on the current stream
-    ev0.record()
-    for _ in range(args.steps):
-        out, counts = step()
-    ev1.record()
-    barrier()
-    ms_single = ev0.elapsed_time(ev1)
+    ms_single = time_steps(cx, step, args.steps)
     ms = ms_single
-    if args.streams > 1 and not sahi:
+    if args.streams > 1:
         # (b) the same K steps issued round-robin on several streams: independent batches, each stream with its own
         # copy of the inputs and its own workspace; the NMS kernel of one batch (few SMs, latency-bound) overlaps
         # the fused decode of the next (HBM-bound).  Every step still does the whole path for one batch.
@@ -379,29 +713,12 @@ def main():
         for s_ in streams:  # warm up each stream (workspace per stream)
             with torch.cuda.stream(s_):
                 for _ in range(3):
-                    sarpost.postprocess_fused(next_levels(), spec, return_padded=True, **kw)
-        barrier()
-        ev0.record()
-        for s_ in streams:
-            s_.wait_event(ev0)
-        for i in range(args.steps):
-            with torch.cuda.stream(streams[i % args.streams]):
-                out, counts = sarpost.postprocess_fused(next_levels(), spec, return_padded=True, **kw)  # n_sets >= streams
-        for s_ in streams:
-            torch.cuda.current_stream().wait_stream(s_)
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
+                    step()
+        ms = time_steps(cx, step, args.steps, streams)
     # second pass over the same K steps with CUDA events around every kernel (recorded by the library on the
     # launching stream, no host sync per step, mean read afterwards).  Kept out of the pass `value` comes from:
     # timing events between kernels cost ~8 % throughput by removing the overlap of consecutive launches.
-    stage = None
-    if not sahi:
-        sarpost.ops.stage_timing(True, accumulate=True)
-        for _ in range(3 if args.quick else args.steps):
-            step()
-        stage = list(sarpost.ops.stage_times())
-        sarpost.ops.stage_timing(False)
+    stage = stage_means(cx, step, 3 if args.quick else args.steps)
     if len(clocks.samples) < 20 and not args.quick:  # short region: keep sampling over the same step to have clocks under load
         t_end = time.perf_counter() + 1.0
         while time.perf_counter() < t_end:
@@ -409,29 +726,14 @@ def main():
                 step()
             torch.cuda.synchronize()
     clocks.stop()
-    t_ms = torch.tensor([ms, ms_single], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms, ms_single = float(t_ms[0].item()), float(t_ms[1].item())
+    ms, ms_single = cx.max_over_ranks(ms, ms_single)
     value = bs * n_gpus * args.steps / (ms / 1e3)
     single = {"value": bs * n_gpus * args.steps / (ms_single / 1e3), "unit": "images/s", "ms_per_step": ms_single / args.steps,
               "note": "strictly one batch in flight (all K steps on one stream)"}
     n_det = int(counts.sum().item())
-    if sahi:
-        def step():  # stage timing / roofline below look at the per-tile fused call only
-            return sarpost.postprocess_fused(levels, spec, return_padded=True, with_extras=False, **kw)
 
-    # ---- per-stage durations (from the evented pass above); K1 roofline ----
-    if stage is None:  # cfg4: time the per-tile fused call on its own
-        sarpost.ops.stage_timing(True, accumulate=True)
-        for _ in range(2 if args.quick else min(max(args.steps, 5), 50)):
-            step()
-        stage = list(sarpost.ops.stage_times())
-        sarpost.ops.stage_timing(False)
-    n_cand = 0
-    for x in levels:  # candidates = anchors whose best class probability passes conf (bookkeeping, untimed)
-        p = x[:, 64:64 + nc].sigmoid()
-        n_cand += int(((p > kw["conf_thres"]).sum() if kw.get("multi_label") and nc > 1 else (p.amax(1) > kw["conf_thres"]).sum()).item())
+    # ---- K1 roofline from the evented pass ----
+    n_cand = count_candidates(torch, levels, nc, kw)
     k1_bytes = bs * anchors * (64 + nc) * 4 + n_cand * 24
     peaks = {}
     try:
@@ -452,30 +754,21 @@ def main():
         except Exception:
             pass
 
+    # ---- clustered leg (same shapes / thresholds, suppression-heavy inputs) ----
+    clustered = None
+    if not args.no_clustered and not args.blobs:
+        clustered = leg_clustered(cx, spec, shapes, nc, ed, sc, bs, kw, cls_mean, max(10, min(args.steps, 100)))
+
+    # ---- the reference's own GPU path on the same box (rank 0, N = 1 only) ----
+    ref_gpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_reference_gpu:
+        n_img = min(bs, 4)
+        ours = sarpost.postprocess_fused([x[:n_img].contiguous() for x in levels], spec, **kw)
+        ref_gpu = leg_reference_gpu(cx, levels, strides, nc, ed, sc, kw, n_img, 5, ours)
+        ref_gpu["sarpost_over_reference_gpu"] = {"device_value": value / ref_gpu["value"], "single_stream": single["value"] / ref_gpu["value"]}
+
     # ---- e2e: HOST buffers through the C-ABI host entry (H2D + D2H inside the timed region) ----
-    e2e = None
-    if not args.no_e2e:
-        host_levels = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x) for x in levels]
-        ctx = sarpost.HostContext(local)
-        out_host = torch.empty((bs, kw["max_det"], 6 + spec.nm), dtype=torch.float32, pin_memory=True)
-        e2e_steps = max(3, min(args.steps, 20))
-        for _ in range(2):
-            ctx.postprocess(host_levels, spec, out=out_host, **kw)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            ctx.postprocess(host_levels, spec, out=out_host, **kw)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t_e = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        h2d, d2h = ctx.last_traffic()
-        e2e = {"value": bs * n_gpus * e2e_steps / float(t_e.item()), "unit": "images/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-               "api": "sarpost_fused_host (pinned host level tensors in, host rows out)"}
-        ctx.close()
-        del host_levels
+    e2e = None if args.no_e2e else leg_e2e(cx, levels, spec, bs, kw)
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----
     cpu = None
@@ -483,35 +776,42 @@ def main():
         n_img = args.cpu_images or (4 if args.workload == "cfg3" else min(bs, 16))
         n_img = min(n_img, bs)
         levels_cpu = [x[:n_img].cpu() for x in levels]
-        cpu_reference_step([x[:1] for x in levels_cpu], strides, nc, ed, sc, kw)  # warm-up (lazy torchvision import)
-        v, secs = time_cpu_baseline(levels_cpu, strides, nc, ed, sc, kw)
-        cpu = {"value": v, "unit": "images/s", "cores": cpu_threads(), "kind": "port",
-               "sample": f"first {n_img} images of the GPU batch, {secs:.1f} s; oracle port of head.py:214-249 + ops.py:167-316 "
-                         f"(torch CPU ops + torchvision.ops.nms CPU, {cpu_threads()} torch threads, host has {os.cpu_count()} cpus)"}
+        torch.set_num_threads(cpu_threads())
+        ref = ReferencePath(strides, nc, ed, sc, "cpu")
+        ref.step([x[:1] for x in levels_cpu], kw)  # warm-up (lazy torchvision import)
+        t0 = time.perf_counter()
+        ref.step(levels_cpu, kw)
+        secs = time.perf_counter() - t0
+        cpu = {"value": n_img / secs, "unit": "images/s", "cores": cpu_threads(), "kind": ref.kind,
+               "sample": f"first {n_img} images of the GPU batch, {secs:.1f} s; {ref.describe()}; {cpu_threads()} torch threads, host has {os.cpu_count()} cpus"}
+        del levels_cpu
+
+    # ---- sliced inference (cfg4): the one exchange step of the path, measured whenever there is more than one rank ----
+    sahi = None
+    if world > 1 and not args.no_sahi:
+        del next_levels, levels
+        torch.cuda.empty_cache()
+        sahi = leg_sahi(cx, max(10, min(args.steps, 100)))
 
     if rank == 0:
         line = {
             "metric": "post-processed images/sec (decode+NMS)", "value": value, "unit": "images/s", "n_gpus": n_gpus,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "images_per_gpu": bs, "global_batch": bs * n_gpus,
-                       "anchors": anchors, "channels": spec.no,
-                       "streams": (1 if sahi else args.streams),
-                       "in_flight": ("one batch" if (sahi or args.streams == 1) else
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}" + (f" [clustered inputs, blobs={args.blobs}]" if args.blobs else ""),
+                       "images_per_gpu": bs, "global_batch": bs * n_gpus, "anchors": anchors, "channels": spec.no, "streams": args.streams,
+                       "in_flight": ("one batch" if args.streams == 1 else
                                      f"{args.streams} independent batches, steps issued round-robin on {args.streams} CUDA streams, "
-                                     "each with its own input buffers; `single_stream` holds the one-batch-in-flight figure"), "parallelism": ((f"tiles sharded x{n_gpus}, gather kernel stores counts+boxes into every rank over NVLink peer memory "
-                                        f"(fused gather+exchange, no NCCL collective), frames merged by their owner rank"
-                                        if (n_gpus > 1 and not os.environ.get("SARPOST_BENCH_NCCL_GATHER")) else
-                                        f"tiles sharded x{n_gpus}, NCCL all-gather of counts+boxes, frames merged by their owner rank") if sahi
-                                       else f"batch-sharded x{n_gpus}, no data-path collective"),
+                                     "each with its own input buffers; `single_stream` holds the one-batch-in-flight figure"),
+                       "parallelism": f"batch-sharded x{n_gpus}, no data-path collective",
                        "l2": (("one batch of inputs (hot channels %.0f MB) exceeds the 126 MB L2; no flush" % (hot_bytes / 1e6))
                               if hot_bytes >= 2 * L2_BYTES else
                               ("hot channels %.1f MB per batch: steps rotate over %d identical input copies (%.0f MB in rotation > 2x the "
                                "126 MB L2), so every step reads its inputs from HBM; no flush" % (hot_bytes / 1e6, n_sets, n_sets * hot_bytes / 1e6))),
                        "input_sets": n_sets,
                        "candidates_per_image": n_cand / bs, "detections_per_image": n_det / bs},
-            "single_stream": single, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "launches_per_step": launches_per_step, "clocks": clocks.summary(),
+            "single_stream": single, "roofline": roofline, "clustered": clustered, "reference_gpu": ref_gpu, "cpu_baseline": cpu, "e2e": e2e,
+            "sahi": sahi, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "clocks": clocks.summary(),
         }
         emit(line)
     if world > 1:

@@ -98,6 +98,9 @@ typedef struct sarpost_nms_params {
                               workspace with the SAME batch (each call leaves that region zeroed again). */
     int32_t out_tail_cols;  /* columns reserved at the END of every output row: rows are (6 + nm + out_tail_cols) floats
                               wide and the call leaves the tail untouched (sarpost_state_head fills it).  0 = none. */
+    int64_t *stats;         /* instrumentation, DEVICE (B, 4) int64 or NULL: per image, what the NMS kernel did — sorted
+                              candidates consumed before max_det keeps were found (or the candidates ran out), IoU pair
+                              tests executed, NMS sub-chunks, selection passes.  bench.py's `clustered` leg reports them. */
 } sarpost_nms_params_t;
 
 /* Last error message of the calling thread ("" if none). */

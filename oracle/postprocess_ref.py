@@ -55,15 +55,15 @@ def nms_torchvision(boxes: torch.Tensor, scores: torch.Tensor, iou_thres: float)
 # ----------------------------------------------------------------------------------------------
 # decode
 # ----------------------------------------------------------------------------------------------
-def make_anchors_ref(shapes: Sequence[Tuple[int, int]], strides: Sequence[float], offset: float = 0.5):
+def make_anchors_ref(shapes: Sequence[Tuple[int, int]], strides: Sequence[float], offset: float = 0.5, device="cpu"):
     """utils/tal.py:366-378 — anchor centres (A,2) as (x,y) and stride column (A,1), levels concatenated."""
     pts, st = [], []
     for (h, w), s in zip(shapes, strides):
-        sx = torch.arange(end=w, dtype=torch.float32) + offset
-        sy = torch.arange(end=h, dtype=torch.float32) + offset
+        sx = torch.arange(end=w, dtype=torch.float32, device=device) + offset
+        sy = torch.arange(end=h, dtype=torch.float32, device=device) + offset
         sy, sx = torch.meshgrid(sy, sx, indexing="ij")
         pts.append(torch.stack((sx, sy), -1).view(-1, 2))
-        st.append(torch.full((h * w, 1), float(s), dtype=torch.float32))
+        st.append(torch.full((h * w, 1), float(s), dtype=torch.float32, device=device))
     return torch.cat(pts), torch.cat(st)
 
 
@@ -72,7 +72,7 @@ def dfl_ref(box: torch.Tensor, reg_max: int = 16) -> torch.Tensor:
     then the fixed 1x1 conv with weights arange(reg_max) (block.py:72-74) = expectation."""
     b, _, a = box.shape
     p = box.view(b, 4, reg_max, a).transpose(2, 1).softmax(1)  # (B, reg_max, 4, A)
-    w = torch.arange(reg_max, dtype=torch.float32).view(1, reg_max, 1, 1)
+    w = torch.arange(reg_max, dtype=torch.float32, device=box.device).view(1, reg_max, 1, 1)
     return torch.nn.functional.conv2d(p, w).view(b, 4, a)
 
 
@@ -87,16 +87,17 @@ def dist2bbox_ref(distance: torch.Tensor, anchor_points: torch.Tensor) -> torch.
 
 
 def decode_ref(levels: Sequence[torch.Tensor], strides: Sequence[float], nc: int, reg_max: int = 16,
-               embed_dim: int = 0, state_classes: int = 0) -> torch.Tensor:
+               embed_dim: int = 0, state_classes: int = 0, device="cpu") -> torch.Tensor:
     """nn/modules/head.py:100-131 (Detect._inference, embed_dim=state_classes=0) and
     :214-249 (JDE._inference).  levels[l]: (B, no, H_l, W_l) fp32, no = 4*reg_max+nc+embed_dim+state_classes.
-    Returns y (B, 4+nc+embed_dim+state_classes, A)."""
-    levels = [x.detach().cpu().float() for x in levels]
+    Returns y (B, 4+nc+embed_dim+state_classes, A).  `device`: where the torch ops run — "cpu" for every parity check;
+    bench.py's `reference_gpu` leg passes a CUDA device to time the same op sequence as a `device=0` user runs it."""
+    levels = [x.detach().to(device).float() for x in levels]
     bsz = levels[0].shape[0]
     no = 4 * reg_max + nc + embed_dim + state_classes
     x_cat = torch.cat([xi.reshape(bsz, no, -1) for xi in levels], 2)  # head.py:104 / :218
     anchors, stride_t = (t.transpose(0, 1) for t in
-                         make_anchors_ref([tuple(x.shape[2:]) for x in levels], strides))  # head.py:106 / :220
+                         make_anchors_ref([tuple(x.shape[2:]) for x in levels], strides, device=device))  # head.py:106 / :220
     parts = x_cat.split([4 * reg_max, nc] + ([embed_dim] if embed_dim else []) + ([state_classes] if state_classes else []), 1)
     box, cls = parts[0], parts[1]
     dbox = dist2bbox_ref(dfl_ref(box, reg_max), anchors.unsqueeze(0)) * stride_t  # head.py:129 / :245
@@ -125,7 +126,7 @@ def non_max_suppression_ref(prediction: torch.Tensor, conf_thres: float = 0.25, 
                             classes: Optional[Sequence[int]] = None, agnostic: bool = False,
                             multi_label: bool = False, labels=(), max_det: int = 300, nc: int = 0,
                             max_nms: int = 30000, max_wh=7680, nms_fn=None, stable_topk: bool = True,
-                            return_index: bool = False):
+                            return_index: bool = False, device="cpu"):
     """utils/ops.py:167-316 (non-rotated, non end-to-end branch).
 
     Deviations, all deliberate and documented in SURVEY.md Appendix B:
@@ -135,14 +136,17 @@ def non_max_suppression_ref(prediction: torch.Tensor, conf_thres: float = 0.25, 
         tie order is torch-version defined, SURVEY §7 hard part 2) — pass False to use the literal call.
     `return_index=True` additionally returns, per image, an int64 (n_i, 2) tensor of (anchor, class)
     identifying each output row in the input — the "kept-index set" the GPU path is checked against.
+    `device`: where the torch ops run ("cpu" for every parity check; a CUDA device + a CUDA `nms_fn` only in bench.py's
+    `reference_gpu` leg, which times this op sequence the way a `device=0` user of the reference runs it).
     """
     if nms_fn is None:  # early stop after max_det keeps == truncating the full result (ops.py:297)
         nms_fn = lambda b_, s_, t_: nms_ref(b_, s_, t_, max_keep=max_det)
     assert 0 <= conf_thres <= 1 and 0 <= iou_thres <= 1  # ops.py:217-218
     if isinstance(prediction, (list, tuple)):
         prediction = prediction[0]  # ops.py:219-220
-    prediction = prediction.detach().cpu().float()
-    cls_t = torch.tensor(list(classes)) if classes is not None else None
+    prediction = prediction.detach().to(device).float()
+    dev = prediction.device
+    cls_t = torch.tensor(list(classes), device=dev) if classes is not None else None
     bs = prediction.shape[0]
     nc = nc or (prediction.shape[1] - 4)  # ops.py:231
     nm = prediction.shape[1] - nc - 4
@@ -151,19 +155,19 @@ def non_max_suppression_ref(prediction: torch.Tensor, conf_thres: float = 0.25, 
     multi_label = multi_label and nc > 1  # ops.py:239
     prediction = prediction.transpose(-1, -2)  # (B, A, C)
     prediction = torch.cat((xywh2xyxy_ref(prediction[..., :4]), prediction[..., 4:]), dim=-1)  # ops.py:246
-    output = [torch.zeros((0, 6 + nm))] * bs
-    index = [torch.zeros((0, 2), dtype=torch.int64)] * bs
+    output = [torch.zeros((0, 6 + nm), device=dev)] * bs
+    index = [torch.zeros((0, 2), dtype=torch.int64, device=dev)] * bs
     for xi, x in enumerate(prediction):
         sel = xc[xi].nonzero().squeeze(1)
         x = x[sel]  # ops.py:253
         src_a = sel
         if labels and len(labels[xi]):  # ops.py:256-261 (save_hybrid)
-            lb = labels[xi]
-            v = torch.zeros((len(lb), nc + nm + 4))
+            lb = labels[xi].to(dev)
+            v = torch.zeros((len(lb), nc + nm + 4), device=dev)
             v[:, :4] = xywh2xyxy_ref(lb[:, 1:5])
             v[range(len(lb)), lb[:, 0].long() + 4] = 1.0
             x = torch.cat((x, v), 0)
-            src_a = torch.cat((src_a, -1 - torch.arange(len(lb))))
+            src_a = torch.cat((src_a, -1 - torch.arange(len(lb), device=dev)))
         if not x.shape[0]:
             continue
         box, cls, mask = x.split((4, nc, nm), 1)  # ops.py:268

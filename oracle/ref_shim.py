@@ -1,10 +1,16 @@
-"""Import the LIVE reference (read-only /root/reference) for golden generation (TEST INFRASTRUCTURE).
+"""Import the LIVE, UNMODIFIED reference for golden generation, parity checks and the baseline legs of bench.py
+(TEST / BASELINE INFRASTRUCTURE — never imported by the product package).
 
-Only usable in the build container: /root/reference does not exist on the GPU box, so nothing
-under tests -m gpu / smoke() / bench.py may call this.  Recipe = SURVEY.md Appendix A: stub the
-three missing third-party imports, pre-seed bare `ultralytics` / `ultralytics.nn` namespace
-modules so the heavy package __init__ files are skipped, then import the hot-path modules.
-Nothing under /root/reference is modified or copied.
+Where the reference comes from, first hit wins:
+  1. $SARPOST_REFERENCE
+  2. /root/reference            (read-only source tree; exists in the build container only)
+  3. <repo>/baseline/_ref       (the reference pip-installed with
+         python -m pip install --no-index --no-build-isolation --no-deps --target baseline/_ref <copy of /root/reference>
+     — git-ignored, but it travels to the GPU box with the gpurun snapshot, so the `-m gpu` tests and bench.py can run
+     the reference's own code there.  Nothing reads /root/reference at run time on the GPU box.)
+Recipe = SURVEY.md Appendix A: stub the three missing third-party imports, pre-seed bare `ultralytics` /
+`ultralytics.nn` namespace modules so the heavy package __init__ files are skipped, then import the hot-path modules.
+Nothing under the reference tree is modified or copied.
 """
 import contextlib
 import os
@@ -12,11 +18,26 @@ import sys
 import tempfile
 import types
 
-REF_ROOT = os.environ.get("SARPOST_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    for cand in (os.environ.get("SARPOST_REFERENCE"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "ultralytics")):
+            return cand
+    return os.environ.get("SARPOST_REFERENCE") or "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "ultralytics"))
+
+
+def source() -> str:
+    """Which copy of the reference is in use: 'tree' (/root/reference or $SARPOST_REFERENCE) or 'baseline/_ref'."""
+    return "baseline/_ref" if os.path.abspath(REF_ROOT) == os.path.join(_REPO, "baseline", "_ref") else "tree"
 
 
 def _stub_third_party():

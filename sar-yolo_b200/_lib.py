@@ -36,6 +36,7 @@ class NmsParams(C.Structure):
         ("label_counts", C.c_void_p), ("max_labels", C.c_int32), ("rescale", C.c_void_p),
         ("peer_out", C.c_void_p * 8), ("peer_counts", C.c_void_p * 8), ("n_peers", C.c_int32),
         ("peer_slot_offset", C.c_int32), ("prediction_dtype", C.c_int32), ("workspace_clean", C.c_int32), ("out_tail_cols", C.c_int32),
+        ("stats", C.c_void_p),
     ]
 
 

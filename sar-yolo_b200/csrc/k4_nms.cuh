@@ -102,6 +102,7 @@ struct NmsParams {
     const float *cls_override;       // merge path: class id per slot (float) or nullptr
     float max_wh;                    // 0 when agnostic
     float thr;                       // largest float <= iou_thres
+    long long *stats;                // [B*4] or nullptr: candidates consumed, pair tests, sub-chunks, collections (instrumentation)
 };
 
 // IoU(a,b) > thr, bit-exact to the fp32 division of the reference but without paying for it on every
@@ -347,6 +348,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     const int n_limit = min(n_all, p.max_nms);  // ops.py:285-286: only the top max_nms ranks are eligible
     int kept = 0;
     int pos = 0, d = 0;  // pos = exact number of candidates consumed (all buckets above descending index d)
+    long long st_walk = 0, st_pairs = 0;  // instrumentation (NmsParams::stats), uniform across threads
+    int st_sub = 0, st_coll = 0;
 
     // Walks `cnt` sorted candidates whose slots are produced by slot_at(i), i in [0,cnt).
     auto process_sorted = [&](auto slot_at, int cnt) {
@@ -546,6 +549,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             } else {
                 __syncthreads();
             }
+            st_pairs += static_cast<long long>(sub) * kept + static_cast<long long>(m) * (m - 1) / 2;
+            ++st_sub;
+            st_walk += sub;
             kept = s_misc[16];
             pdone += sub;
             __syncthreads();
@@ -589,6 +595,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         int d1 = s_misc[17];
         int m = 0;
         int my_off = 0, my_cnt = 0;
+        ++st_coll;
         for (;;) {  // collect; if the real population overflows shared memory, halve the bucket run and retry
             __syncthreads();
             if (tid == 0) s_misc[18] = 0;
@@ -691,6 +698,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     if (crank == 0) {
         for (int k = tid; k < kept; k += kNmsThreads) p.kept_slot[static_cast<int64_t>(b) * p.max_det + k] = KEPT_SLOT[k];
         if (tid == 0) p.counts[b] = kept;
+        if (tid == 0 && p.stats) {
+            long long *o = p.stats + static_cast<int64_t>(b) * 4;
+            o[0] = st_walk;
+            o[1] = st_pairs;
+            o[2] = st_sub;
+            o[3] = st_coll;
+        }
     }
     if constexpr (CL > 1) cluster.sync();  // no CTA may exit while a peer can still address its shared memory
     PROF_MARK(8);

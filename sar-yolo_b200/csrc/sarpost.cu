@@ -345,6 +345,7 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     np.cls_override = P.cls;
     np.max_wh = prm->agnostic ? 0.0f : prm->max_wh;
     np.thr = iou_thr_float(prm->iou_thres);
+    np.stats = reinterpret_cast<long long *>(prm->stats);
     const int nms_smem = static_cast<int>(nms_smem_bytes(prm->max_det));
     // one CTA per image; when the batch leaves SMs idle, a cluster of 2 or 4 CTAs per image shares the work
     int sms = 0, smem_optin = 0;
@@ -608,7 +609,7 @@ int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const 
     g_launches = 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (int rc = check_params(params, 1)) return rc;
-    if (!dets || !det_counts || !origins || !out || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
+    if (!dets || !det_counts || !origins || (!out && params->n_peers == 0) || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
     if (n_frames < 1 || tiles_per_frame < 1 || dets_per_tile < 1 || row_len < 6) return fail(SARPOST_EINVAL, "bad merge geometry");
     Pipeline P;
     const int64_t cap = static_cast<int64_t>(tiles_per_frame) * dets_per_tile;

@@ -96,14 +96,20 @@ class PeerGatherBuffer:
     slow peer still reads step i (its barrier i+1 comes after its reads of step i in stream order).
     """
 
-    def __init__(self, per_rank_batch: int, max_det: int, row_len: int, device, group=None, n_buffers: int = 2):
+    def __init__(self, per_rank_batch: int, max_det: int, row_len: int, device, group=None, n_buffers: int = 2,
+                 total_slots: int = None, slot_offset: int = None):
+        """Default layout: every rank contributes `per_rank_batch` image slots, rank r at slot r*per.  Uneven shards
+        (whole frames per rank, `shard_frames`) pass `total_slots` and this rank's `slot_offset` explicitly."""
         import torch.distributed._symmetric_memory as symm_mem
 
         group = group or dist.group.WORLD
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.per, self.max_det, self.row_len = int(per_rank_batch), int(max_det), int(row_len)
-        total = self.world * self.per
+        total = self.world * self.per if total_slots is None else int(total_slots)
+        self._slot_offset = self.rank * self.per if slot_offset is None else int(slot_offset)
+        if self._slot_offset + self.per > total:
+            raise ValueError("sarpost: this rank's slots exceed the gather buffer")
         self._bufs = []
         for _ in range(n_buffers):
             rows = symm_mem.empty((total, self.max_det, self.row_len), dtype=torch.float32, device=device)
@@ -128,7 +134,7 @@ class PeerGatherBuffer:
 
     @property
     def slot_offset(self) -> int:
-        return self.rank * self.per
+        return self._slot_offset
 
     def peer_ptrs(self):
         _, _, h_rows, h_cnts = self._bufs[self._i]

@@ -359,7 +359,7 @@ def decode(levels: Sequence[torch.Tensor], spec: HeadSpec) -> torch.Tensor:
 def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres=0.25, iou_thres=0.45, classes=None,
                       agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=7680,
                       return_index=False, return_padded=False, with_extras=True, scale_to=None, peer_out=None,
-                      state_mlp: Optional[StateMLP] = None):
+                      state_mlp: Optional[StateMLP] = None, out=None, nms_stats: Optional[torch.Tensor] = None):
     """decode + non_max_suppression in one pass (never materialises y; the extras channels are read only
     for the kept rows).  Result as `non_max_suppression`; `return_padded=True` returns the raw
     `(out (B, max_det, 6+nm), counts (B,) int32[, kept_index])` device tensors without any host sync.
@@ -373,7 +373,11 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
     of the full buffers, valid after `peer_out.barrier()`.
     `state_mlp=StateMLP` (deferred JDE state head): `levels` come from a head that SKIPPED
     `state_predictor` (channels = box, cls, embedding only; `spec.state_classes` still names S); the MLP + sigmoid
-    run on the kept rows' embeddings after the gather and fill the last S columns — same row layout as the reference."""
+    run on the kept rows' embeddings after the gather and fill the last S columns — same row layout as the reference.
+    `out=(rows, counts)`: write into caller-owned contiguous `(B, max_det, row_len)` fp32 / `(B,)` int32 CUDA tensors (e.g. a
+    slice of a larger gather buffer) instead of allocating; implies the padded return form.
+    `nms_stats`: optional `(B, 4)` int64 CUDA tensor receiving the NMS kernel's instrumentation counters
+    (`sarpost_nms_params_t.stats`)."""
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     levels = _prep_levels(levels)
@@ -405,22 +409,28 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
         rescale = scale_params(img1_shape, img0_shapes, dev)
     params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, rescale)
     params.out_tail_cols = tail
+    if nms_stats is not None:
+        if nms_stats.dtype != torch.int64 or tuple(nms_stats.shape) != (bs, 4) or not nms_stats.is_contiguous() or nms_stats.device != dev:
+            raise ValueError("sarpost: nms_stats must be a contiguous (B, 4) int64 tensor on the levels' device")
+        params.stats = nms_stats.data_ptr()
     if peer_out is not None:
-        if (peer_out.per, peer_out.max_det, peer_out.row_len) != (bs, int(max_det), 6 + nm):
-            raise ValueError("sarpost: peer_out buffer geometry does not match this call")
-        rp, cp = peer_out.peer_ptrs()
-        params.n_peers = len(rp)
-        params.peer_slot_offset = peer_out.slot_offset
-        for q in range(len(rp)):
-            params.peer_out[q] = rp[q]
-            params.peer_counts[q] = cp[q]
+        _bind_peer(params, peer_out, bs, max_det, 6 + nm)
     with torch.cuda.device(dev):
         ws_bytes = lib.sarpost_workspace_bytes(bs, anchors, spec.nc, int(bool(multi_label)), int(max_det))
         if ws_bytes < 0:
             _lib.check(int(ws_bytes))
         ws = _Workspace(ws_bytes, bs, dev)
-        out = torch.empty((bs, int(max_det), 6 + nm + tail), dtype=torch.float32, device=dev) if peer_out is None else None
-        counts = torch.empty((bs,), dtype=torch.int32, device=dev)
+        if out is not None:
+            out, counts = out
+            if peer_out is not None:
+                raise ValueError("sarpost: out= and peer_out= are exclusive")
+            for t, shp, dt in ((out, (bs, int(max_det), 6 + nm + tail), torch.float32), (counts, (bs,), torch.int32)):
+                if tuple(t.shape) != shp or t.dtype != dt or not t.is_contiguous() or t.device != dev:
+                    raise ValueError(f"sarpost: out= tensors must be contiguous {shp} {dt} on {dev}")
+            return_padded = True
+        else:
+            out = torch.empty((bs, int(max_det), 6 + nm + tail), dtype=torch.float32, device=dev) if peer_out is None else None
+            counts = torch.empty((bs,), dtype=torch.int32, device=dev)
         want_idx = return_index
         kidx = torch.empty((bs, int(max_det)), dtype=torch.int32, device=dev) if want_idx else None
         _lib.check(lib.sarpost_fused(C.byref(head), C.byref(params), out.data_ptr() if out is not None else None,
@@ -457,14 +467,28 @@ def gather_extras(levels: Sequence[torch.Tensor], spec: HeadSpec, image_index: t
     return out
 
 
+def _bind_peer(params, peer_out, bs: int, max_det: int, row_len: int) -> None:
+    """Point the gather kernel's output at every rank's `dist.PeerGatherBuffer` (fused gather + exchange)."""
+    if (peer_out.per, peer_out.max_det, peer_out.row_len) != (bs, int(max_det), row_len):
+        raise ValueError("sarpost: peer_out buffer geometry does not match this call")
+    rp, cp = peer_out.peer_ptrs()
+    params.n_peers = len(rp)
+    params.peer_slot_offset = peer_out.slot_offset
+    for q in range(len(rp)):
+        params.peer_out[q] = rp[q]
+        params.peer_counts[q] = cp[q]
+
+
 def merge_tiles(dets: torch.Tensor, det_counts: torch.Tensor, origins: torch.Tensor, tiles_per_frame: int,
                 iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000, max_wh=7680, return_index=False,
-                return_padded=False):
+                return_padded=False, peer_out=None):
     """Cross-tile merge of sliced inference: `dets (T, D, row_len)` padded per-tile detections
     (x1,y1,x2,y2,conf,cls,extras...), `det_counts (T,)` int32, `origins (T, 2)` tile offsets in frame
     pixels; T = n_frames * tiles_per_frame with the tiles of a frame contiguous.  Per frame: shift by
     the tile origin, then the same class-offset NMS as ops.py:289-297.  Returns a list of per-frame
-    `(n_f, row_len)` tensors."""
+    `(n_f, row_len)` tensors.  `peer_out=dist.PeerGatherBuffer` (frames sharded over ranks): the merged rows and counts of
+    this rank's frames are stored into every rank's buffer by the gather kernel; returns the full `(rows, counts)` buffers,
+    valid after `peer_out.barrier()`."""
     _require_cuda(dets, "dets")
     dets = dets.float().contiguous()
     det_counts = det_counts.to(device=dets.device, dtype=torch.int32).contiguous()
@@ -475,19 +499,23 @@ def merge_tiles(dets: torch.Tensor, det_counts: torch.Tensor, origins: torch.Ten
     nf = t // tiles_per_frame
     dev = dets.device
     params, _keep = _make_params(0.0, iou_thres, None, agnostic, False, max_det, max_nms, max_wh)
+    if peer_out is not None:
+        _bind_peer(params, peer_out, nf, max_det, row_len)
     with torch.cuda.device(dev):
         ws_bytes = lib.sarpost_merge_workspace_bytes(nf, tiles_per_frame, d, int(max_det))
         if ws_bytes < 0:
             _lib.check(int(ws_bytes))
         ws = _Workspace(ws_bytes, nf, dev)
-        out = torch.empty((nf, int(max_det), row_len), dtype=torch.float32, device=dev)
+        out = torch.empty((nf, int(max_det), row_len), dtype=torch.float32, device=dev) if peer_out is None else None
         counts = torch.empty((nf,), dtype=torch.int32, device=dev)
         kidx = torch.empty((nf, int(max_det)), dtype=torch.int32, device=dev) if return_index else None
         _lib.check(lib.sarpost_merge_tiles(dets.data_ptr(), det_counts.data_ptr(), origins.data_ptr(), nf,
-                                           tiles_per_frame, d, row_len, C.byref(params), out.data_ptr(),
+                                           tiles_per_frame, d, row_len, C.byref(params), out.data_ptr() if out is not None else None,
                                            counts.data_ptr(), kidx.data_ptr() if return_index else None,
                                            ws.ptr(), ws_bytes, _stream_ptr(dev)))
         ws.release()
+    if peer_out is not None:
+        return (peer_out.rows, peer_out.counts, kidx) if return_index else (peer_out.rows, peer_out.counts)
     if return_padded:
         return (out, counts, kidx) if return_index else (out, counts)
     rows = _split(out, counts)

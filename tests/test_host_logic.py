@@ -342,6 +342,10 @@ def test_product_code_never_touches_the_oracle_or_a_cpu_fallback():
     bench = open(os.path.join(root, "bench.py"), encoding="utf-8").read()
     uses = [m.start() for m in re.finditer(r"from oracle|import oracle", bench)]
     assert uses, "bench.py's CPU legs use the oracle port"
-    for at in uses:  # every use sits inside a CPU-leg function
-        fn = re.findall(r"\ndef (\w+)\(", bench[:at])[-1]
-        assert fn in ("cpu_reference_step", "time_cpu_baseline", "run_reference_arm"), fn
+    for at in uses:  # every use sits inside the baseline class both CPU legs and the reference_gpu leg go through
+        owner = re.findall(r"\n(?:class|def) (\w+)[(:]", bench[:at])[-1]
+        assert owner == "ReferencePath", owner
+    # ... and the GPU arm's own step never goes near it: `ReferencePath` is only constructed in the three baseline legs
+    for m in re.finditer(r"ReferencePath\(", bench):
+        fn = re.findall(r"\ndef (\w+)\(", bench[:m.start()])[-1]
+        assert fn in ("run_reference_arm", "leg_reference_gpu", "main"), fn
