@@ -39,19 +39,22 @@ constexpr int kTileListCap = 2048;
 template <class Fn>
 __device__ __forceinline__ void for_each_candidate_in(const CandStore &st, const int32_t *tcount, const uint32_t *tmax,
                                                       const float *score, uint32_t lo_bits, uint32_t hi_bits,
-                                                      int tile_lo, int tile_hi /* this CTA's share of the image's tiles */,
+                                                      int tile_first, int tile_step, int n_share /* this CTA's share of the image's
+                                                      tiles: tile_first + i*tile_step, i in [0, n_share) — interleaved across the
+                                                      CTAs of a cluster so that dense regions of the image spread over all of them */,
                                                       uint32_t *tile_list /*[kTileListCap] smem*/, int *list_n /*smem*/,
                                                       const Fn &fn) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const uint32_t span = hi_bits - lo_bits;  // in range  <=>  (bits - lo_bits) <= span  (unsigned)
-    for (int t0 = tile_lo; t0 < tile_hi; t0 += kTileListCap) {
+    for (int t0 = 0; t0 < n_share; t0 += kTileListCap) {
         __syncthreads();
         if (tid == 0) *list_n = 0;
         __syncthreads();
-        const int t1 = min(tile_hi, t0 + kTileListCap);
+        const int t1 = min(n_share, t0 + kTileListCap);
         for (int tb = t0 + warp * 32; tb < t1; tb += nwarps * 32) {
-            const int t = tb + lane;
-            const int c = (t < t1 && tmax[t] >= lo_bits) ? tcount[t] : 0;
+            const int v = tb + lane;
+            const int t = tile_first + v * tile_step;
+            const int c = (v < t1 && tmax[t] >= lo_bits) ? tcount[t] : 0;
             const uint32_t bal = __ballot_sync(0xffffffffu, c > 0);
             if (bal) {
                 int base = 0;

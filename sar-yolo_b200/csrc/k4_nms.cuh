@@ -10,18 +10,20 @@
 //   select    the per-image SAMPLED score histogram written by K1 is scanned from the top to size the next
 //             run of whole score buckets (estimates only steer the size; membership is exact); the run is
 //             collected by streaming the image's candidate scores once (tiles whose best score is below
-//             the run are skipped), and sorted in shared memory (bitonic network on the 64-bit composite
-//             score|~slot = descending score, source order on ties); a single bucket larger than that
-//             falls back to a stable LSD radix sort in global memory;
-//   phase 1   a sub-chunk of <= 256 sorted candidates is tested against the kept list (smem);
-//   phase 2   an upper-triangular suppression bitmask is built among the survivors (tiled IoU
-//             bitmask, all threads);
+//             the run are skipped);
+//   phase 1   the collected candidates are tested against the kept list as it stood when the chunk began — this
+//             needs no order, so it happens BEFORE sorting, and in the suppression-heavy regime (clustered
+//             detections) a chunk spans thousands of candidates of which a handful survive;
+//   sort      the survivors are sorted in shared memory (bitonic network on the 64-bit composite score|~slot =
+//             descending score, source order on ties); a single bucket larger than that falls back to a stable
+//             LSD radix sort in global memory;
+//   phase 2   sub-chunks of <= 256 sorted survivors: test against boxes kept since the chunk began, ordered
+//             compaction, upper-triangular suppression bitmask (warp per row, ballot per word);
 //   sweep     one warp resolves the sub-chunk on the bitmask, 32 candidates per step when no two live
 //             candidates of the group overlap, else one step per KEPT box; appends to the kept list.
-// Small batches (B*CL <= #SMs) run a thread-block CLUSTER of CL CTAs per image: the selection scan, phase 1
-// and the bitmask are split across the CTAs, the sort/compaction are replicated (same data, same result),
-// the sweep stays on the master CTA; candidates, survivors' flags, mask rows and new kept boxes travel through
-// distributed shared memory, with 3 cluster barriers per sub-chunk.
+// Small batches (B*CL <= #SMs) run a thread-block CLUSTER of CL CTAs per image: collection and phase 1 are split
+// across the CTAs (interleaved tiles), survivors travel to the master CTA through distributed shared memory, the
+// master sorts / sweeps and replicates the new kept boxes: 2 cluster barriers per chunk.
 #pragma once
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
@@ -250,13 +252,63 @@ __device__ __forceinline__ void bitonic_sort_desc(unsigned long long *key, int l
     }
 }
 
-// dynamic shared memory: kept_box[max_det] float4 | kept_area[max_det] | kept_slot[max_det] | (pad to 16) |
-// plist[kSortCap] u64 (this CTA's share of a collected chunk, cluster variant)
-__host__ __device__ inline size_t nms_kept_bytes(int max_det) { return (static_cast<size_t>(max_det) * 24 + 15) / 16 * 16; }
-__host__ __device__ inline size_t nms_smem_bytes(int max_det) { return nms_kept_bytes(max_det) + kSortCap * 8; }
+// ---------------------------------------------------------------------------------------------
+// Shared memory of the NMS kernel: one dynamic allocation, fixed-size arrays first (compile-time offsets), the
+// kept list (max_det entries) last.
+// ---------------------------------------------------------------------------------------------
+constexpr int kShareCap = 1024;  // members one CTA collects (and phase-1 tests) per chunk
+constexpr int kMaxNmsCluster = 8;
 
-constexpr int kMaxNmsCluster = 4;
+struct NmsSmemLayout {
+    static constexpr int plist = 0;                                  // u64[kShareCap]  this CTA's members of the chunk
+    static constexpr int surv = plist + kShareCap * 8;               // u64[kShareCap]  its phase-1 survivors
+    static constexpr int skey = surv + kShareCap * 8;                // u64[kSortCap]   master: every CTA's survivors, sorted
+    static constexpr int radix_end = skey + kSortCap * 8;            // (the radix fallback aliases plist|surv|skey)
+    static constexpr int bstart = radix_end;                         // i32[kBuckets + 4]
+    static constexpr int mask = bstart + (kBuckets + 4) * 4;         // u32[kSub * kSubWords]
+    static constexpr int a_box = mask + kSub * kSubWords * 4;        // float4[kSub]  (a_box|c_box double as the tile list)
+    static constexpr int c_box = a_box + kSub * 16;                  // float4[kSub]
+    static constexpr int a_area = c_box + kSub * 16;                 // f32[kSub]
+    static constexpr int c_area = a_area + kSub * 4;
+    static constexpr int a_slot = c_area + kSub * 4;                 // u32[kSub]
+    static constexpr int c_slot = a_slot + kSub * 4;
+    static constexpr int dead = c_slot + kSub * 4;                   // i32[kSub]  master: verdicts of the incremental phase 1
+    static constexpr int deadw = dead + kSub * 4;                    // u32[kShareCap / 32]  share phase 1: dead bits
+    static constexpr int misc = deadw + kShareCap / 32 * 4;          // i32[64]
+    static constexpr int kept = misc + 64 * 4;                       // float4[max_det] | f32[max_det] | u32[max_det]
+};
+static_assert(NmsSmemLayout::radix_end >= 256 * (kNmsWarps + 1) * 4, "radix counters must fit the plist|surv|skey region");
+static_assert(kTileListCap * 4 <= 2 * kSub * 16, "tile list must fit the a_box|c_box region");
+static_assert(NmsSmemLayout::kept % 16 == 0, "kept boxes must be 16-byte aligned");
 
+__host__ __device__ inline size_t nms_smem_bytes(int max_det) { return NmsSmemLayout::kept + static_cast<size_t>(max_det) * 24; }
+
+// misc[] slots
+enum : int {
+    kMWarp = 0,      // [0, 16) per-warp partial sums
+    kMTot = 16,      // [16, 32) per-warp totals of the histogram prologue
+    kMNAll = 32,     // exact candidate count of the image
+    kMRunEnd = 33,   // chosen end of the bucket run
+    kMShareCnt = 34, // members collected by this CTA (exact, may exceed kShareCap)
+    kMSurvCnt = 35,  // phase-1 survivors of this CTA
+    kMOff = 36,      // offset of this CTA's survivors in the master's list
+    kMKept = 37,     // kept count after the sweep (master)
+    kMListN = 38,    // tile list length
+    kMCtl = 40,      // [40, 44) control block written by the master into every CTA: action, kept, members, survivors
+    kMCtr = 48,      // [48, 56) master only: two banks (chunk parity) of {members, survivors, overflow}
+};
+enum : int { kActOk = 0, kActHalve = 1, kActCareful = 2, kActRadix = 3 };
+
+// One CTA, or a thread-block cluster of CL CTAs, per image.
+//   every CTA   collects its share (interleaved tiles) of the next run of score buckets and tests those candidates
+//               against the kept list as of the start of the chunk (phase 1 needs no order, so it runs BEFORE any
+//               sorting, on up to CL*kShareCap candidates at once); only the survivors travel to the master
+//               (distributed shared memory, offsets from a remote atomic) — cluster barrier #1;
+//   the master  sorts the survivors (bitonic network on score|~slot), resolves them in order (sub-chunks of <= 256:
+//               incremental phase 1 against boxes kept since the chunk began, bitmask, one-warp sweep), replicates the
+//               new kept boxes and a control block into the peers — cluster barrier #2.
+// A chunk that would cross the max_nms rank cut, overflow the master's list or a CTA's share is redone (all members to
+// the master / half the bucket run / radix fallback): phase 1 is idempotent and nothing is committed before barrier #2.
 template <int CL>
 __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__ NmsParams p) {
     namespace cg = cooperative_groups;
@@ -265,27 +317,28 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     auto cluster_sync = [&]() {
         if constexpr (CL > 1) cluster.sync(); else __syncthreads();
     };
-    // All shared arrays are referenced through their symbols (never through pointers kept in
-    // structs) so every access compiles to LDS/STS rather than a generic LD/ST.
-    extern __shared__ float4 dyn_kept[];
-    __shared__ int32_t s_bstart[kBuckets + 4];
-    __shared__ uint32_t s_mask[kSub * kSubWords];
-    __shared__ float s_a_area[kSub], s_c_area[kSub];
-    __shared__ uint32_t s_a_slot[kSub], s_c_slot[kSub];
-    __shared__ int32_t s_dead[kSub];  // phase-1 verdicts; written by every CTA of the cluster, cleared by its owner
-    __shared__ int32_t s_misc[32];
-    // union region: skey[kSortCap] u64 | a_box[kSub] | c_box[kSub]; the fallback radix sort aliases all of it
-    __shared__ __align__(16) unsigned char s_uni[256 * (kNmsWarps + 1) * 4];
-    static_assert(sizeof(s_uni) >= kSortCap * 8 + 2 * kSub * 16, "union region too small");
-#define KEPT_BOX (dyn_kept)
-#define KEPT_AREA (reinterpret_cast<float *>(dyn_kept + p.max_det))
-#define KEPT_SLOT (reinterpret_cast<uint32_t *>(dyn_kept + p.max_det) + p.max_det)
-#define SKEY (reinterpret_cast<unsigned long long *>(s_uni))
-#define A_BOX (reinterpret_cast<float4 *>(s_uni + kSortCap * 8))
-#define C_BOX (reinterpret_cast<float4 *>(s_uni + kSortCap * 8 + kSub * 16))
-#define TILE_LIST (reinterpret_cast<uint32_t *>(s_uni + kSortCap * 8))  /* aliases A_BOX|C_BOX, idle while collecting */
-#define PLIST (reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(dyn_kept) + nms_kept_bytes(p.max_det)))
-    static_assert(kTileListCap * 4 <= 2 * kSub * 16, "tile list must fit the a_box|c_box region");
+    // Shared arrays are reached through offsets from the one dynamic symbol, so every local access compiles to
+    // LDS/STS; only the explicitly remote ones (map_shared_rank) are generic.
+    extern __shared__ __align__(16) unsigned char dyn[];
+    using L = NmsSmemLayout;
+#define PLIST (reinterpret_cast<unsigned long long *>(dyn + L::plist))
+#define SURV (reinterpret_cast<unsigned long long *>(dyn + L::surv))
+#define SKEY (reinterpret_cast<unsigned long long *>(dyn + L::skey))
+#define S_BSTART (reinterpret_cast<int32_t *>(dyn + L::bstart))
+#define S_MASK (reinterpret_cast<uint32_t *>(dyn + L::mask))
+#define A_BOX (reinterpret_cast<float4 *>(dyn + L::a_box))
+#define C_BOX (reinterpret_cast<float4 *>(dyn + L::c_box))
+#define TILE_LIST (reinterpret_cast<uint32_t *>(dyn + L::a_box)) /* aliases A_BOX|C_BOX, idle while collecting */
+#define S_A_AREA (reinterpret_cast<float *>(dyn + L::a_area))
+#define S_C_AREA (reinterpret_cast<float *>(dyn + L::c_area))
+#define S_A_SLOT (reinterpret_cast<uint32_t *>(dyn + L::a_slot))
+#define S_C_SLOT (reinterpret_cast<uint32_t *>(dyn + L::c_slot))
+#define S_DEAD (reinterpret_cast<int32_t *>(dyn + L::dead))
+#define S_DEADW (reinterpret_cast<uint32_t *>(dyn + L::deadw))
+#define S_MISC (reinterpret_cast<int32_t *>(dyn + L::misc))
+#define KEPT_BOX (reinterpret_cast<float4 *>(dyn + L::kept))
+#define KEPT_AREA (reinterpret_cast<float *>(dyn + L::kept + static_cast<size_t>(p.max_det) * 16))
+#define KEPT_SLOT (reinterpret_cast<uint32_t *>(dyn + L::kept + static_cast<size_t>(p.max_det) * 20))
 
     const int b = blockIdx.x / CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
@@ -293,12 +346,40 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     const uint32_t *tmaxv = p.st.tile_max + static_cast<int64_t>(b) * p.st.tpi;
     const float *score = p.st.score + seg;
     const float band = fmaxf(p.thr * 2e-6f, 1e-37f);
+    const bool need_cls = p.max_wh != 0.0f && (p.cls_override != nullptr || p.nc > 1);
 #ifdef SARPOST_PHASE_PROF
     long long prof_t = clock64();
 #endif
-    if (tid < kSub) s_dead[tid] = 0;
+    if (tid < kSub) S_DEAD[tid] = 0;
+    if (tid >= 32 && tid < 64) S_MISC[tid] = 0;  // control block, counters (both banks)
 
-    // ---- descending exclusive scan of the sampled score histogram: s_bstart[d] ~ estimated rank of the first
+    // class-offset box of a candidate slot (ops.py:289,295)
+    auto offset_box = [&](uint32_t slot) {
+        const float4 bx = p.st.box[seg + slot];
+        float cls = 0.0f;
+        if (need_cls)
+            cls = p.cls_override ? p.cls_override[seg + slot] : static_cast<float>(p.st.key[seg + slot] % static_cast<uint32_t>(p.nc));
+        const float off = __fmul_rn(cls, p.max_wh);
+        return make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
+    };
+    // does any kept box k in [k_lo, k_hi), k = k_lo + part, + nparts, ... suppress (ob, oa)?  `dead` counts only verdicts
+    // the approximate quotient can be trusted with (not within the band around the threshold); if none of those fired
+    // and some pair was borderline, every pair is re-evaluated with the correctly rounded division
+    auto killed_by_kept = [&](const float4 ob, const float oa, int k_lo, int k_hi, int part, int nparts) {
+        bool dead = false, any_border = false;
+#pragma unroll 4
+        for (int k = k_lo + part; k < k_hi; k += nparts) {
+            bool bd;
+            const bool gt = iou_gt_approx(KEPT_BOX[k], KEPT_AREA[k], ob, oa, p.thr, band, bd);
+            dead |= gt && !bd;
+            any_border |= bd;
+        }
+        if (any_border && !dead)  // rare: a quotient within a few ulp of the threshold
+            for (int k = k_lo + part; k < k_hi; k += nparts) dead |= iou_gt(KEPT_BOX[k], KEPT_AREA[k], ob, oa, p.thr);
+        return dead;
+    };
+
+    // ---- descending exclusive scan of the sampled score histogram: S_BSTART[d] ~ estimated rank of the first
     //      candidate of bucket 4095-d in the sorted order (x kHistSample).  Estimates only steer how many
     //      buckets a chunk spans; membership, ranks and results are exact.  n_all = exact candidate count. ----
     {
@@ -320,22 +401,22 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             if (lane >= dd) inc += v;
         }
         tot = __reduce_add_sync(0xffffffffu, tot);
-        if (lane == 31) s_misc[warp] = inc;
-        if (lane == 0) s_misc[16 + warp] = tot;
+        if (lane == 31) S_MISC[kMWarp + warp] = inc;
+        if (lane == 0) S_MISC[kMTot + warp] = tot;
         __syncthreads();
         int run = inc - sum;
-        for (int w = 0; w < warp; ++w) run += s_misc[w];
+        for (int w = 0; w < warp; ++w) run += S_MISC[kMWarp + w];
 #pragma unroll
         for (int i = 0; i < kPer; ++i) {
-            s_bstart[tid * kPer + i] = run;
+            S_BSTART[tid * kPer + i] = run;
             run += loc[i];
         }
-        if (tid == kNmsThreads - 1) s_bstart[kBuckets] = run;
+        if (tid == kNmsThreads - 1) S_BSTART[kBuckets] = run;
         tot = 0;
 #pragma unroll
-        for (int w = 0; w < kNmsWarps; ++w) tot += s_misc[16 + w];
+        for (int w = 0; w < kNmsWarps; ++w) tot += S_MISC[kMTot + w];
         __syncthreads();
-        if (tid == 0) s_misc[19] = tot;
+        if (tid == 0) S_MISC[kMNAll] = tot;
     }
     __syncthreads();
     if constexpr (CL > 1) {  // every CTA of the cluster has read the histogram: the master zeroes it
@@ -344,98 +425,69 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             for (int i = tid; i < kBuckets; i += kNmsThreads) p.st.hist[static_cast<int64_t>(b) * kBuckets + i] = 0;
     }
     PROF_MARK(0);
-    const int n_all = s_misc[19];
+    const int n_all = S_MISC[kMNAll];
     const int n_limit = min(n_all, p.max_nms);  // ops.py:285-286: only the top max_nms ranks are eligible
     int kept = 0;
     int pos = 0, d = 0;  // pos = exact number of candidates consumed (all buckets above descending index d)
-    long long st_walk = 0, st_pairs = 0;  // instrumentation (NmsParams::stats), uniform across threads
+    long long st_walk = 0, st_pairs = 0;  // instrumentation (NmsParams::stats); st_walk/st_sub/st_coll uniform, st_pairs per CTA
     int st_sub = 0, st_coll = 0;
 
-    // Walks `cnt` sorted candidates whose slots are produced by slot_at(i), i in [0,cnt).
-    auto process_sorted = [&](auto slot_at, int cnt) {
+    // MASTER ONLY (block-level barriers only).  Walks `cnt` sorted candidates whose slots are produced by slot_at(i);
+    // they have already been tested against kept[0, k_from).
+    auto process_sorted = [&](auto slot_at, int cnt, int k_from) {
         int pdone = 0;
         while (pdone < cnt && kept < p.max_det) {
             const int need = p.max_det - kept;
             const int sub = min(cnt - pdone, min(kSub, max(64, 2 * need)));
-            // ---- load sub-chunk: class-offset boxes (ops.py:289,295) ----
+            // ---- load sub-chunk ----
             if (tid < sub) {
                 const uint32_t slot = slot_at(pdone + tid);
-                const float4 bx = p.st.box[seg + slot];
-                const float cls = p.cls_override ? p.cls_override[seg + slot]
-                                                 : static_cast<float>(p.st.key[seg + slot] % static_cast<uint32_t>(p.nc));
-                const float off = __fmul_rn(cls, p.max_wh);
-                const float4 ob = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
+                const float4 ob = offset_box(slot);
                 A_BOX[tid] = ob;
-                s_a_area[tid] = box_area_rn(ob);
-                s_a_slot[tid] = slot;
+                S_A_AREA[tid] = box_area_rn(ob);
+                S_A_SLOT[tid] = slot;
             }
             __syncthreads();
             PROF_MARK(3);
-            // ---- phase 1: candidates x kept list, kNmsThreads/sub_p2 threads per candidate ----
-            if (kept > 0) {
-                // this CTA's share of the candidates (the whole sub-chunk when CL == 1)
-                const int per = (sub + CL - 1) / CL, c_lo = crank * per, c_n = max(0, min(sub, c_lo + per) - c_lo);
+            // ---- incremental phase 1: candidates x boxes kept since they were last tested ----
+            if (kept > k_from) {
                 int sub_p2 = 64;
-                while (sub_p2 < c_n) sub_p2 <<= 1;
-                const int cand = c_lo + (tid & (sub_p2 - 1)), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
-                if (cand < c_lo + c_n) {
-                    const float4 ob = A_BOX[cand];
-                    const float oa = s_a_area[cand];
-                    // `dead` counts only verdicts the approximate quotient can be trusted with (not within the
-                    // band around the threshold); if none of those fired and some pair was borderline, every pair
-                    // is re-evaluated with the correctly rounded division
-                    bool dead = false, any_border = false;
-#pragma unroll 4
-                    for (int k = part; k < kept; k += nparts) {
-                        bool bd;
-                        const bool gt = iou_gt_approx(KEPT_BOX[k], KEPT_AREA[k], ob, oa, p.thr, band, bd);
-                        dead |= gt && !bd;
-                        any_border |= bd;
-                    }
-                    if (any_border && !dead)  // rare: a quotient within a few ulp of the threshold
-                        for (int k = part; k < kept; k += nparts) dead |= iou_gt(KEPT_BOX[k], KEPT_AREA[k], ob, oa, p.thr);
-                    if (dead) {
-                        s_dead[cand] = 1;
-                        if constexpr (CL > 1)
-                            for (int r2 = 0; r2 < CL; ++r2)
-                                if (r2 != crank) *cluster.map_shared_rank(&s_dead[cand], r2) = 1;
-                    }
-                }
-                cluster_sync();
+                while (sub_p2 < sub) sub_p2 <<= 1;
+                const int cand = tid & (sub_p2 - 1), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
+                if (cand < sub && killed_by_kept(A_BOX[cand], S_A_AREA[cand], k_from, kept, part, nparts)) S_DEAD[cand] = 1;
+                st_pairs += static_cast<long long>(sub) * (kept - k_from);
+                __syncthreads();
             }
             PROF_MARK(4);
             // ---- ordered compaction of survivors (first kSub threads = 8 warps) ----
             bool alive = false;
             uint32_t bal = 0;
             if (tid < kSub) {
-                alive = tid < sub && !s_dead[tid];
-                // cleared by its owner here: peers write it again only after the two cluster barriers that follow
-                s_dead[tid] = 0;
+                alive = tid < sub && !S_DEAD[tid];
+                S_DEAD[tid] = 0;
                 bal = __ballot_sync(0xffffffffu, alive);
-                if (lane == 0) s_misc[warp] = __popc(bal);
+                if (lane == 0) S_MISC[kMWarp + warp] = __popc(bal);
             }
             __syncthreads();
             int m = 0;
 #pragma unroll
-            for (int w = 0; w < kSubWords; ++w) m += s_misc[w];
+            for (int w = 0; w < kSubWords; ++w) m += S_MISC[kMWarp + w];
             if (alive) {
                 int base = 0;
-                for (int w = 0; w < warp; ++w) base += s_misc[w];
+                for (int w = 0; w < warp; ++w) base += S_MISC[kMWarp + w];
                 const int at = base + __popc(bal & lanemask_lt());
                 C_BOX[at] = A_BOX[tid];
-                s_c_area[at] = s_a_area[tid];
-                s_c_slot[at] = s_a_slot[tid];
+                S_C_AREA[at] = S_A_AREA[tid];
+                S_C_SLOT[at] = S_A_SLOT[tid];
             }
             __syncthreads();
             PROF_MARK(5);
             // ---- phase 2: suppression bitmask among the m survivors (row r, bits j > r) ----
             // warp per row r, lane j tests the pair (r, 32w + j) for every word w >= r/32; a ballot packs the word
             const int words = (m + 31) >> 5;
-            uint32_t *mask_out = s_mask;  // the master's bitmask (it runs the sweep)
-            if constexpr (CL > 1) mask_out = cluster.map_shared_rank(s_mask, 0);
-            for (int r = warp * CL + crank; r < m; r += kNmsWarps * CL) {
+            for (int r = warp; r < m; r += kNmsWarps) {
                 const float4 rb = C_BOX[r];
-                const float ra = s_c_area[r];
+                const float ra = S_C_AREA[r];
                 for (int w = r >> 5; w < words; w += 2) {
                     const int j0 = (w << 5) + lane, j1 = j0 + 32;
                     const bool v0 = j0 > r && j0 < m, v1 = (w + 1 < words) && j1 < m;
@@ -448,29 +500,29 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                     const bool ov1 = v1 && fminf(rb.z, cb1.z) > fmaxf(rb.x, cb1.x) && fminf(rb.w, cb1.w) > fmaxf(rb.y, cb1.y);
                     if (!__any_sync(0xffffffffu, ov0 || ov1)) {
                         if (lane == 0) {
-                            mask_out[r * kSubWords + w] = 0u;
-                            if (w + 1 < words) mask_out[r * kSubWords + w + 1] = 0u;
+                            S_MASK[r * kSubWords + w] = 0u;
+                            if (w + 1 < words) S_MASK[r * kSubWords + w + 1] = 0u;
                         }
                         continue;
                     }
-                    bool g0 = iou_gt_approx(rb, ra, cb0, s_c_area[jc0], p.thr, band, bd0);
-                    bool g1 = iou_gt_approx(rb, ra, cb1, s_c_area[jc1], p.thr, band, bd1);
+                    bool g0 = iou_gt_approx(rb, ra, cb0, S_C_AREA[jc0], p.thr, band, bd0);
+                    bool g1 = iou_gt_approx(rb, ra, cb1, S_C_AREA[jc1], p.thr, band, bd1);
                     if (__any_sync(0xffffffffu, (bd0 && v0) || (bd1 && v1))) {  // rare: quotient within a few ulp of thr
-                        if (bd0) g0 = iou_gt(rb, ra, cb0, s_c_area[jc0], p.thr);
-                        if (bd1) g1 = iou_gt(rb, ra, cb1, s_c_area[jc1], p.thr);
+                        if (bd0) g0 = iou_gt(rb, ra, cb0, S_C_AREA[jc0], p.thr);
+                        if (bd1) g1 = iou_gt(rb, ra, cb1, S_C_AREA[jc1], p.thr);
                     }
                     const uint32_t bits0 = __ballot_sync(0xffffffffu, g0 && v0);
                     const uint32_t bits1 = __ballot_sync(0xffffffffu, g1 && v1);
                     if (lane == 0) {
-                        mask_out[r * kSubWords + w] = bits0;
-                        if (w + 1 < words) mask_out[r * kSubWords + w + 1] = bits1;
+                        S_MASK[r * kSubWords + w] = bits0;
+                        if (w + 1 < words) S_MASK[r * kSubWords + w + 1] = bits1;
                     }
                 }
             }
-            cluster_sync();
+            __syncthreads();
             PROF_MARK(6);
-            // ---- sweep (warp 0 of the master CTA) ----
-            if (warp == 0 && crank == 0) {
+            // ---- sweep (warp 0) ----
+            if (warp == 0) {
                 uint32_t km[kSubWords];  // kept bits of the groups resolved so far (warp-uniform)
 #pragma unroll
                 for (int g = 0; g < kSubWords; ++g) km[g] = 0u;
@@ -478,12 +530,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 // column g of the bitmask (word g of the rows g2*32+lane, g2 <= g) is loaded one group ahead, before
                 // the dependent chain of group g-1, so the sweep never waits on shared memory
                 uint32_t cur[kSubWords], nxt[kSubWords];
-                cur[0] = s_mask[lane * kSubWords];
+                cur[0] = S_MASK[lane * kSubWords];
 #pragma unroll
                 for (int g = 0; g < kSubWords; ++g) {
                     if (g + 1 < kSubWords) {
 #pragma unroll
-                        for (int g2 = 0; g2 <= g + 1; ++g2) nxt[g2] = s_mask[((g2 << 5) + lane) * kSubWords + g + 1];
+                        for (int g2 = 0; g2 <= g + 1; ++g2) nxt[g2] = S_MASK[((g2 << 5) + lane) * kSubWords + g + 1];
                     }
                     if (g < words && kl < p.max_det) {
                         // removal word of group g = OR over the rows kept in earlier groups (lane = row)
@@ -520,8 +572,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                         if ((keptm >> lane) & 1u) {
                             const int idx = kl + __popc(keptm & lanemask_lt());
                             KEPT_BOX[idx] = C_BOX[r];
-                            KEPT_AREA[idx] = s_c_area[r];
-                            KEPT_SLOT[idx] = s_c_slot[r];
+                            KEPT_AREA[idx] = S_C_AREA[r];
+                            KEPT_SLOT[idx] = S_C_SLOT[r];
                         }
                         kl += c;
                         km[g] = keptm;
@@ -531,165 +583,237 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                         for (int g2 = 0; g2 <= g + 1; ++g2) cur[g2] = nxt[g2];
                     }
                 }
-                if (lane == 0) s_misc[16] = kl;
+                if (lane == 0) S_MISC[kMKept] = kl;
             }
-            if constexpr (CL > 1) {
-                if (crank == 0) {  // replicate the new kept boxes and the new count in the other CTAs of the cluster
-                    __syncthreads();
-                    const int kl = s_misc[16];
-                    for (int i = kept + tid; i < kl; i += kNmsThreads)
-                        for (int r2 = 1; r2 < CL; ++r2) {
-                            *cluster.map_shared_rank(&KEPT_BOX[i], r2) = KEPT_BOX[i];
-                            *cluster.map_shared_rank(&KEPT_AREA[i], r2) = KEPT_AREA[i];
-                        }
-                    if (tid == 0)
-                        for (int r2 = 1; r2 < CL; ++r2) *cluster.map_shared_rank(&s_misc[16], r2) = kl;
-                }
-                cluster.sync();
-            } else {
-                __syncthreads();
-            }
-            st_pairs += static_cast<long long>(sub) * kept + static_cast<long long>(m) * (m - 1) / 2;
+            __syncthreads();
+            st_pairs += static_cast<long long>(m) * (m - 1) / 2;
             ++st_sub;
             st_walk += sub;
-            kept = s_misc[16];
+            kept = S_MISC[kMKept];
             pdone += sub;
             __syncthreads();
             PROF_MARK(7);
         }
     };
 
-    // this CTA's share of the image's tiles (everything when CL == 1)
-    const int tiles_per_cta = (p.st.tpi + CL - 1) / CL;
-    const int tile_lo = min(p.st.tpi, crank * tiles_per_cta), tile_hi = min(p.st.tpi, tile_lo + tiles_per_cta);
-    // members of score buckets [b_lo, b_hi] among this CTA's tiles -> `list` (first kSortCap of them), exact
-    // count -> s_misc[18]
-    auto collect_smem = [&](int b_lo, int b_hi, unsigned long long *list) {
-        const uint32_t lo_bits = bucket_floor_bits(b_lo);
-        const uint32_t hi_bits = b_hi >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_hi + 1) - 1u;
-        for_each_candidate_in(p.st, tcount, tmaxv, score, lo_bits, hi_bits, tile_lo, tile_hi, TILE_LIST, &s_misc[20],
-                              [&](uint32_t slot, uint32_t bits) {
-                                  const int at = atomicAdd(&s_misc[18], 1);  // members are rare (a few hundred per image)
-                                  if (at < kSortCap) list[at] = (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - slot);
-                              });
-    };
+    // this CTA's share of the image's tiles: crank, crank + CL, ... (everything when CL == 1)
+    const int n_share = crank < p.st.tpi ? (p.st.tpi - crank + CL - 1) / CL : 0;
+    int par = 0;          // chunk parity: which bank of the master's counters this round uses
+    bool careful = false; // redo of a chunk that crosses the max_nms cut: every member goes to the master (no phase 1 first)
+    int last_m = 1, last_s = 1;  // members / survivors of the last committed chunk (survival rate steers the chunk size)
 
     while (d < kBuckets && pos < n_limit && kept < p.max_det) {
         // ---- next chunk: a run of whole buckets [d, d1) whose ESTIMATED population fits the target ----
         if (tid == 0) {
-            // the first chunk is smaller: NMS usually finishes inside it and sorting cost grows with the chunk
-            const int target = pos == 0 ? min(kSortCap / 2, max(256, 2 * p.max_det)) : (kSortCap * 3) / 4;
-            const int base = s_bstart[d];
+            int target;
+            if (pos == 0) {
+                // the first chunk is smaller: NMS usually finishes inside it and sorting cost grows with the chunk
+                target = min(kSortCap / 2, max(256, 2 * p.max_det));
+            } else {
+                // only survivors of the kept-list test reach the master: when few survive (clustered detections) a chunk
+                // can span many more candidates than the master's list holds
+                const long long want = 640ll * last_m / max(last_s, 1);
+                target = static_cast<int>(min(static_cast<long long>(CL) * (kShareCap * 3 / 4), max(768ll, want)));
+            }
+            if (careful) target = min(target, (kSortCap * 3) / 4);
+            const int base = S_BSTART[d];
             int lo = d + 1, hi = kBuckets;
             if (n_all - pos <= kSortCap) {
                 lo = kBuckets;  // everything that is left fits shared memory: one chunk, no estimate needed
-            } else if (s_bstart[lo] - base <= target) {
+            } else if (S_BSTART[lo] - base <= target) {
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
-                    if (s_bstart[mid] - base <= target) lo = mid; else hi = mid - 1;
+                    if (S_BSTART[mid] - base <= target) lo = mid; else hi = mid - 1;
                 }
             }
-            s_misc[17] = lo;
+            S_MISC[kMRunEnd] = lo;
         }
         __syncthreads();
-        int d1 = s_misc[17];
-        int m = 0;
-        int my_off = 0, my_cnt = 0;
-        ++st_coll;
-        for (;;) {  // collect; if the real population overflows shared memory, halve the bucket run and retry
+        int d1 = S_MISC[kMRunEnd];
+        int action = kActOk, m = 0;
+        for (;;) {  // attempt; a failed attempt (overflow / rank cut) changes d1 or `careful` and comes back here
+            const int k0 = kept;
+            ++st_coll;
             __syncthreads();
-            if (tid == 0) s_misc[18] = 0;
+            if (tid == 0) { S_MISC[kMShareCnt] = 0; S_MISC[kMSurvCnt] = 0; }
+            if (tid < kShareCap / 32) S_DEADW[tid] = 0u;
             __syncthreads();
-            if constexpr (CL == 1) {
-                collect_smem(kBuckets - d1, kBuckets - 1 - d, SKEY);
-                __syncthreads();
-                m = s_misc[18];
-            } else {
-                collect_smem(kBuckets - d1, kBuckets - 1 - d, PLIST);
-                __syncthreads();
-                my_cnt = s_misc[18];
-                if (tid < CL) *cluster.map_shared_rank(&s_misc[24 + crank], tid) = my_cnt;  // my count -> every CTA
-                cluster.sync();
-                m = 0;
-                my_off = 0;
-#pragma unroll
-                for (int r2 = 0; r2 < CL; ++r2) {
-                    my_off += r2 < crank ? s_misc[24 + r2] : 0;
-                    m += s_misc[24 + r2];
-                }
-                cluster.sync();  // everyone has read the counts before a retry may overwrite them
-            }
-            if (m <= kSortCap || d1 - d == 1) break;
-            d1 = d + (d1 - d) / 2;
-        }
-        if constexpr (CL > 1) {
-            if (m <= kSortCap) {  // all-gather the shares: every CTA ends up with the same chunk in SKEY
-                for (int i = tid; i < my_cnt; i += kNmsThreads) {
-                    const unsigned long long v = PLIST[i];
-#pragma unroll
-                    for (int r2 = 0; r2 < CL; ++r2) *cluster.map_shared_rank(&SKEY[my_off + i], r2) = v;
-                }
-            }
-            cluster.sync();
-        }
-        PROF_MARK(1);
-        if (m <= kSortCap) {
-            if (m > 0) {
-                int lpw = 6;
-                while ((1 << lpw) < m) ++lpw;
-                const int pw = 1 << lpw;
-                for (int i = m + tid; i < pw; i += kNmsThreads) SKEY[i] = 0ull;
-                __syncthreads();
-                bitonic_sort_desc(SKEY, lpw);
-                PROF_MARK(2);
-                process_sorted([&](int i) { return 0xffffffffu - static_cast<uint32_t>(SKEY[i]); }, min(m, n_limit - pos));
-            }
-        } else {
-            // ---- a single bucket larger than shared memory: collect to global scratch, stable LSD radix sort
-            //      on (score bits desc, slot asc), then stream it through the suppression phases.  With a
-            //      cluster the master CTA does this alone (rare path); the others wait and read the result. ----
-            uint32_t *ka = p.tmp_key_a + seg, *va = p.tmp_val_a + seg, *kb = p.tmp_key_b + seg, *vb = p.tmp_val_b + seg;
-            const int b_one = kBuckets - 1 - d;
-            const uint32_t *ik = ka, *iv = va;
-            uint32_t *ok = kb, *ov = vb;
-            int slot_bits = 1;
-            while ((static_cast<int64_t>(1) << slot_bits) < p.st.cap) ++slot_bits;
-            const int passes_slot = (slot_bits + 7) / 8;
-            if (crank == 0) {
-                __syncthreads();
-                if (tid == 0) s_misc[18] = 0;
-                __syncthreads();
-                for_each_candidate_in(p.st, tcount, tmaxv, score, bucket_floor_bits(b_one),
-                                      b_one >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_one + 1) - 1u, 0, p.st.tpi,
-                                      TILE_LIST, &s_misc[20], [&](uint32_t slot, uint32_t bits) {
-                                          const int at = atomicAdd(&s_misc[18], 1);
-                                          ka[at] = bits;
-                                          va[at] = slot;
+            // ---- collect this CTA's members of score buckets [kBuckets - d1, kBuckets - 1 - d] ----
+            {
+                const int b_lo = kBuckets - d1, b_hi = kBuckets - 1 - d;
+                const uint32_t lo_bits = bucket_floor_bits(b_lo);
+                const uint32_t hi_bits = b_hi >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_hi + 1) - 1u;
+                for_each_candidate_in(p.st, tcount, tmaxv, score, lo_bits, hi_bits, crank, CL, n_share, TILE_LIST, &S_MISC[kMListN],
+                                      [&](uint32_t slot, uint32_t bits) {
+                                          const int at = atomicAdd(&S_MISC[kMShareCnt], 1);  // members are rare (a few hundred per image)
+                                          if (at < kShareCap) PLIST[at] = (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - slot);
                                       });
-                __syncthreads();
-                int *cnt = reinterpret_cast<int *>(s_uni);
-                int *wt = s_misc;
-                for (int ps = 0; ps < passes_slot + 4; ++ps) {
-                    const int sh = ps < passes_slot ? ps * 8 : (ps - passes_slot) * 8;
-                    if (ps < passes_slot)
-                        radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t, uint32_t v) { return (v >> sh) & 255u; }, cnt, wt);
-                    else
-                        radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t k, uint32_t) { return ((~k) >> sh) & 255u; }, cnt, wt);
-                    const uint32_t *tk = ik, *tv = iv;
-                    ik = ok; iv = ov;
-                    ok = const_cast<uint32_t *>(tk); ov = const_cast<uint32_t *>(tv);
+            }
+            __syncthreads();
+            PROF_MARK(1);
+            const int my_cnt = S_MISC[kMShareCnt];
+            const int my_n = min(my_cnt, kShareCap);
+            // ---- phase 1 on the share: members x kept[0, k0) ----
+            const bool do_p1 = k0 > 0 && !careful;
+            if (do_p1) {
+                for (int base = 0; base < my_n; base += kNmsThreads) {
+                    const int nb = min(kNmsThreads, my_n - base);
+                    int sub_p2 = 64;
+                    while (sub_p2 < nb) sub_p2 <<= 1;
+                    const int ci = tid & (sub_p2 - 1), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
+                    bool dead = false;
+                    if (ci < nb) {
+                        const uint32_t slot = 0xffffffffu - static_cast<uint32_t>(PLIST[base + ci]);
+                        const float4 ob = offset_box(slot);
+                        dead = killed_by_kept(ob, box_area_rn(ob), 0, k0, part, nparts);
+                    }
+                    const uint32_t bal = __ballot_sync(0xffffffffu, dead);  // a warp = 32 consecutive members, one part
+                    if (lane == 0 && bal) atomicOr(&S_DEADW[(base + ci) >> 5], bal);
                 }
-                __threadfence();
-            } else if ((passes_slot + 4) & 1) {  // same ping-pong parity as the master: where the sorted values end up
-                iv = vb;
+                st_pairs += static_cast<long long>(my_n) * k0;
+                __syncthreads();
+                for (int i0 = warp * 32; i0 < my_n; i0 += kNmsThreads) {  // unordered compaction (the survivors get sorted anyway)
+                    const int i = i0 + lane;
+                    const bool alive = i < my_n && !((S_DEADW[i >> 5] >> (i & 31)) & 1u);
+                    const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+                    int at = 0;
+                    if (lane == 0 && bal) at = atomicAdd(&S_MISC[kMSurvCnt], __popc(bal));
+                    at = __shfl_sync(0xffffffffu, at, 0);
+                    if (alive) SURV[at + __popc(bal & lanemask_lt())] = PLIST[i];
+                }
+                __syncthreads();
             }
-            if constexpr (CL > 1) cluster.sync();
-            const uint32_t *sorted = iv;
-            const int lim = min(m, n_limit - pos);
-            for (int piece = 0; piece < lim && kept < p.max_det; piece += kSortCap) {
-                process_sorted([&](int i) { return sorted[piece + i]; }, min(kSortCap, lim - piece));
+            PROF_MARK(2);
+            const unsigned long long *mine = do_p1 ? SURV : PLIST;
+            const int s_cnt = do_p1 ? S_MISC[kMSurvCnt] : my_n;
+            // ---- survivors -> master (offset from a remote atomic on the master's counters) ----
+            int32_t *ctr = &S_MISC[kMCtr + par * 4];
+            if constexpr (CL > 1) ctr = cluster.map_shared_rank(&S_MISC[kMCtr + par * 4], 0);
+            if (tid == 0) {
+                atomicAdd(ctr + 0, my_cnt);
+                S_MISC[kMOff] = atomicAdd(ctr + 1, s_cnt);
+                if (my_cnt > kShareCap) atomicOr(ctr + 2, 1);
             }
+            __syncthreads();
+            {
+                const int off = S_MISC[kMOff];
+                unsigned long long *dst = SKEY;
+                if constexpr (CL > 1) dst = cluster.map_shared_rank(SKEY, 0);
+                for (int i = tid; i < s_cnt; i += kNmsThreads)
+                    if (off + i < kSortCap) dst[off + i] = mine[i];
+            }
+            cluster_sync();  // barrier #1
+            PROF_MARK(3);
+            if (crank == 0) {
+                m = S_MISC[kMCtr + par * 4 + 0];
+                const int s_all = S_MISC[kMCtr + par * 4 + 1];
+                const bool share_ovf = S_MISC[kMCtr + par * 4 + 2] != 0;
+                if (share_ovf || s_all > kSortCap) action = (d1 - d == 1) ? kActRadix : kActHalve;
+                else if (!careful && k0 > 0 && pos + m > n_limit) action = kActCareful;  // crosses the rank cut: ranks need every member
+                else action = kActOk;
+                __syncthreads();
+                if (tid < 4) S_MISC[kMCtr + (par ^ 1) * 4 + tid] = 0;  // the other bank is idle until the next round
+                if (action == kActOk) {
+                    if (s_all > 0) {
+                        int lpw = 6;
+                        while ((1 << lpw) < s_all) ++lpw;
+                        for (int i = s_all + tid; i < (1 << lpw); i += kNmsThreads) SKEY[i] = 0ull;
+                        __syncthreads();
+                        bitonic_sort_desc(SKEY, lpw);
+                        PROF_MARK(4);
+                        // without a preceding phase 1 (first chunk, careful redo) the sorted list holds every member, so
+                        // the rank cut applies directly; after phase 1 the whole chunk is known to lie above the cut
+                        const int cnt = do_p1 ? s_all : min(s_all, n_limit - pos);
+                        process_sorted([&](int i) { return 0xffffffffu - static_cast<uint32_t>(SKEY[i]); }, cnt, do_p1 ? k0 : 0);
+                    }
+                } else if (action == kActRadix) {
+                    // ---- a single bucket larger than shared memory: collect to global scratch, stable LSD radix sort
+                    //      on (score bits desc, slot asc), then stream it through the suppression phases (rare path) ----
+                    uint32_t *ka = p.tmp_key_a + seg, *va = p.tmp_val_a + seg, *kb = p.tmp_key_b + seg, *vb = p.tmp_val_b + seg;
+                    const int b_one = kBuckets - 1 - d;
+                    const uint32_t *ik = ka, *iv = va;
+                    uint32_t *ok = kb, *ov = vb;
+                    int slot_bits = 1;
+                    while ((static_cast<int64_t>(1) << slot_bits) < p.st.cap) ++slot_bits;
+                    const int passes_slot = (slot_bits + 7) / 8;
+                    __syncthreads();
+                    if (tid == 0) S_MISC[kMShareCnt] = 0;
+                    __syncthreads();
+                    for_each_candidate_in(p.st, tcount, tmaxv, score, bucket_floor_bits(b_one),
+                                          b_one >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_one + 1) - 1u, 0, 1, p.st.tpi,
+                                          TILE_LIST, &S_MISC[kMListN], [&](uint32_t slot, uint32_t bits) {
+                                              const int at = atomicAdd(&S_MISC[kMShareCnt], 1);
+                                              ka[at] = bits;
+                                              va[at] = slot;
+                                          });
+                    __syncthreads();
+                    int *cnt = reinterpret_cast<int *>(dyn + L::plist);  // aliases plist|surv|skey
+                    int *wt = S_MISC + kMWarp;
+                    for (int ps = 0; ps < passes_slot + 4; ++ps) {
+                        const int sh = ps < passes_slot ? ps * 8 : (ps - passes_slot) * 8;
+                        if (ps < passes_slot)
+                            radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t, uint32_t v) { return (v >> sh) & 255u; }, cnt, wt);
+                        else
+                            radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t k, uint32_t) { return ((~k) >> sh) & 255u; }, cnt, wt);
+                        const uint32_t *tk = ik, *tv = iv;
+                        ik = ok; iv = ov;
+                        ok = const_cast<uint32_t *>(tk); ov = const_cast<uint32_t *>(tv);
+                    }
+                    const uint32_t *sorted = iv;
+                    const int lim = min(m, n_limit - pos);
+                    for (int piece = 0; piece < lim && kept < p.max_det; piece += kSortCap)
+                        process_sorted([&](int i) { return sorted[piece + i]; }, min(kSortCap, lim - piece), 0);
+                }
+                // ---- replicate the new kept boxes and the verdict into the peers ----
+                if constexpr (CL > 1) {
+                    __syncthreads();
+                    for (int i = k0 + tid; i < kept; i += kNmsThreads) {
+                        const float4 kb4 = KEPT_BOX[i];
+                        const float ka1 = KEPT_AREA[i];
+                        for (int r2 = 1; r2 < CL; ++r2) {
+                            *cluster.map_shared_rank(&KEPT_BOX[i], r2) = kb4;
+                            *cluster.map_shared_rank(&KEPT_AREA[i], r2) = ka1;
+                        }
+                    }
+                    if (tid < CL) {
+                        int32_t *ctl = cluster.map_shared_rank(&S_MISC[kMCtl], tid);
+                        ctl[0] = action;
+                        ctl[1] = kept;
+                        ctl[2] = m;
+                        ctl[3] = s_all;
+                    }
+                } else {
+                    if (tid == 0) {
+                        S_MISC[kMCtl + 0] = action;
+                        S_MISC[kMCtl + 1] = kept;
+                        S_MISC[kMCtl + 2] = m;
+                        S_MISC[kMCtl + 3] = s_all;
+                    }
+                }
+            }
+            cluster_sync();  // barrier #2
+            action = S_MISC[kMCtl + 0];
+            kept = S_MISC[kMCtl + 1];
+            m = S_MISC[kMCtl + 2];
+            const int s_all = S_MISC[kMCtl + 3];
+            par ^= 1;
+            PROF_MARK(5);
+            if (action == kActHalve) {
+                d1 = d + (d1 - d) / 2;
+                continue;
+            }
+            if (action == kActCareful) {
+                careful = true;
+                if (m > (kSortCap * 3) / 4 && d1 - d > 1) d1 = d + max(1, (d1 - d) * ((kSortCap * 3) / 4) / m);
+                continue;
+            }
+            if (action == kActOk && do_p1) {
+                last_m = max(m, 1);
+                last_s = max(s_all, 1);
+            }
+            break;
         }
+        careful = false;
         pos += m;
         d = d1;
     }
@@ -698,24 +822,36 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     if (crank == 0) {
         for (int k = tid; k < kept; k += kNmsThreads) p.kept_slot[static_cast<int64_t>(b) * p.max_det + k] = KEPT_SLOT[k];
         if (tid == 0) p.counts[b] = kept;
-        if (tid == 0 && p.stats) {
-            long long *o = p.stats + static_cast<int64_t>(b) * 4;
-            o[0] = st_walk;
-            o[1] = st_pairs;
-            o[2] = st_sub;
-            o[3] = st_coll;
+    }
+    if (p.stats && tid == 0) {  // accumulated with atomics (pair tests are counted per CTA): the caller zeroes the buffer
+        unsigned long long *o = reinterpret_cast<unsigned long long *>(p.stats) + static_cast<int64_t>(b) * 4;
+        if (crank == 0) {
+            atomicAdd(o + 0, static_cast<unsigned long long>(st_walk));
+            atomicAdd(o + 2, static_cast<unsigned long long>(st_sub));
+            atomicAdd(o + 3, static_cast<unsigned long long>(st_coll));
         }
+        atomicAdd(o + 1, static_cast<unsigned long long>(st_pairs));
     }
     if constexpr (CL > 1) cluster.sync();  // no CTA may exit while a peer can still address its shared memory
     PROF_MARK(8);
-#undef KEPT_BOX
-#undef KEPT_AREA
-#undef KEPT_SLOT
+#undef PLIST
+#undef SURV
 #undef SKEY
+#undef S_BSTART
+#undef S_MASK
 #undef A_BOX
 #undef C_BOX
 #undef TILE_LIST
-#undef PLIST
+#undef S_A_AREA
+#undef S_C_AREA
+#undef S_A_SLOT
+#undef S_C_SLOT
+#undef S_DEAD
+#undef S_DEADW
+#undef S_MISC
+#undef KEPT_BOX
+#undef KEPT_AREA
+#undef KEPT_SLOT
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -352,7 +352,7 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     if (int rc = device_sm_count(&sms, &smem_optin)) return rc;
     int cl = batch * 4 <= sms ? 4 : (batch * 2 <= sms ? 2 : 1);
     const int forced_cl = env_int("SARPOST_NMS_CLUSTER", 0);
-    if (forced_cl == 1 || forced_cl == 2 || forced_cl == 4) cl = forced_cl;
+    if (forced_cl == 1 || forced_cl == 2 || forced_cl == 4 || forced_cl == 8) cl = forced_cl;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(batch * cl);
@@ -367,16 +367,9 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     const int max_smem = static_cast<int>(nms_smem_bytes(4096));
-    if (cl == 4) {
-        CUDA_TRY(cudaFuncSetAttribute(k4_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, k4_nms<4>, np));
-    } else if (cl == 2) {
-        CUDA_TRY(cudaFuncSetAttribute(k4_nms<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, k4_nms<2>, np));
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute(k4_nms<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, k4_nms<1>, np));
-    }
+    void (*kern)(const NmsParams) = cl == 8 ? k4_nms<8> : cl == 4 ? k4_nms<4> : cl == 2 ? k4_nms<2> : k4_nms<1>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, np));
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     stage_mark(3, s);

@@ -412,6 +412,7 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
     if nms_stats is not None:
         if nms_stats.dtype != torch.int64 or tuple(nms_stats.shape) != (bs, 4) or not nms_stats.is_contiguous() or nms_stats.device != dev:
             raise ValueError("sarpost: nms_stats must be a contiguous (B, 4) int64 tensor on the levels' device")
+        nms_stats.zero_()  # the kernel accumulates into it
         params.stats = nms_stats.data_ptr()
     if peer_out is not None:
         _bind_peer(params, peer_out, bs, max_det, 6 + nm)

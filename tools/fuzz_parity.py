@@ -14,7 +14,7 @@ def run(n_cases: int, seed: int) -> int:
   bad = 0
   stats = {}
   for case in range(n_cases):
-      mode = rng.choice(["decoded", "decoded", "fused", "fused", "merge", "labels", "host", "match"])
+      mode = rng.choice(["decoded", "decoded", "fused", "fused", "merge", "labels", "host", "match", "deep"])
       nc = rng.choice([1, 1, 2, 3, 6, 9, 17])
       kw = dict(conf_thres=rng.choice([0.0, 0.001, 0.05, 0.25, 0.5, 0.9]), iou_thres=rng.choice([0.0, 0.3, 0.45, 0.6, 0.7, 0.95, 1.0]),
                 agnostic=rng.random() < 0.3, multi_label=rng.random() < 0.4, max_det=rng.choice([1, 7, 100, 300, 1000]),
@@ -108,6 +108,30 @@ def run(n_cases: int, seed: int) -> int:
               rows, idx = sarpost.postprocess_host(lv, spec, return_index=True, **kw)
               y = sarpost.decode([x.to(dev) for x in lv], spec).cpu()
               ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=nc, return_index=True, **kw)
+          elif mode == "deep":
+              # suppression-heavy inputs that make the NMS kernel walk many chunks: few far-apart clusters of near-duplicate boxes
+              # (kept list saturates below max_det, everything else is suppressed), optionally crossing the max_nms rank cut
+              bs, na = rng.choice([1, 2, 3]), rng.choice([3000, 12000, 40000, 140000])
+              k = rng.choice([3, 40, 299, 1000])
+              g = torch.Generator().manual_seed(cs)
+              y = torch.zeros(bs, 4 + nc, na)
+              cx = (torch.arange(k) % 40) * 60.0 + 40
+              cy = (torch.arange(k) // 40) * 80.0 + 40
+              pick = torch.randint(0, k, (bs, na), generator=g)
+              jit = rng.choice([0.5, 4.0, 12.0])
+              y[:, 0] = cx[pick] + torch.randn(bs, na, generator=g) * jit
+              y[:, 1] = cy[pick] + torch.randn(bs, na, generator=g) * jit
+              y[:, 2:4] = 30.0
+              y[:, 4:4 + nc] = torch.rand(bs, nc, na, generator=g) * 0.9 + 0.05
+              if rng.random() < 0.3:
+                  y[:, 4:4 + nc] = (y[:, 4:4 + nc] * 64).floor() / 64 + 1 / 128
+              kw["conf_thres"] = rng.choice([0.001, 0.3])
+              kw["iou_thres"] = rng.choice([0.3, 0.5, 0.7])
+              kw["max_nms"] = rng.choice([300, 2000, 30000, 30000])
+              kw["max_det"] = rng.choice([7, 100, 300, 300, 1000])
+              kw.pop("classes", None)
+              rows, idx = sarpost.non_max_suppression(y.to(dev), nc=nc, return_index=True, **kw)
+              ref_rows, ref_idx = R.non_max_suppression_ref(y, nc=nc, return_index=True, **kw)
           elif mode == "decoded":
               bs, na, nm = rng.choice([1, 2, 5, 40]), rng.choice([1, 31, 128, 129, 1000, 5000, 20000]), rng.choice([0, 0, 3, 40])
               y = sarpost.synth.decoded_prediction(bs, na, nc, nm, seed=cs, clustered=rng.random() < 0.5, score_pow=rng.choice([1.0, 2.0, 4.0]))
@@ -170,6 +194,8 @@ def run(n_cases: int, seed: int) -> int:
           extra = {}
           if mode in ("decoded", "labels"):
               extra = dict(bs=bs, na=na, nm=nm)
+          elif mode == "deep":
+              extra = dict(bs=bs, na=na, k=k, jit=jit)
           elif mode in ("fused", "host"):
               extra = dict(strides=strides, imgsz=imgsz, bs=bs, ed=ed, sc=sc, half=lvd[0].dtype == torch.float16)
           print("MISMATCH case", case, mode, "nc", nc, kw, "seed", cs, extra)
