@@ -17,6 +17,8 @@ the one real exchange of the path (sliced inference: tiles of a frame on differe
 Keys of the JSON line beyond the contract:
   single_stream   the same K steps strictly one batch in flight
   roofline        K1 (fused decode) algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json
+  split_layout    the same batches handed over as separate branch tensors (no torch.cat in front of the decode kernel,
+                  channels_last embedding): what `patch(fused=True, split=True)` feeds the kernels
   clustered       the same shapes/thresholds on inputs whose class logits carry 50 Gaussian blobs per image: neighbouring
                   anchors fire together and overlap, so NMS has to suppress (the regime of a trained detector)
   reference_gpu   the reference's own path as a `device=0` user runs it on this GPU: JDE._inference (torch CUDA ops) +
@@ -100,6 +102,7 @@ def parse_args():
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--no-clustered", action="store_true")
     ap.add_argument("--no-sahi", action="store_true")
+    ap.add_argument("--no-split", action="store_true")
     ap.add_argument("--blobs", type=int, default=0, help="profiling: make the MAIN workload the clustered variant (Gaussian blobs per image)")
     ap.add_argument("--cpu-images", type=int, default=0, help="images in the CPU baseline sample (default: ~10-30 s of work)")
     return ap.parse_args()
@@ -409,6 +412,41 @@ def leg_clustered(cx, spec, shapes, nc, ed, sc, bs, kw, cls_mean, steps):
                     "pair_tests = IoU tests executed, sub_chunks / collections = passes of the NMS / selection loops"}
 
 
+def leg_split(cx, level_sets, spec, bs, kw, steps, streams_n):
+    """The same batches in the split layout (SARPOST_LAYOUT_SPLIT): box / class / embedding / state branch outputs as separate
+    tensors — what `patch(fused=True, split=True)` hands over instead of the per-level torch.cat of head.py:204-206 — with the
+    embedding channels_last.  Same values as the concatenated inputs (built from them), rows checked identical."""
+    torch, sarpost = cx.torch, cx.sarpost
+    split_sets = [sarpost.split_levels(lv, spec, emb_channels_last=True) for lv in level_sets]
+    nxt = rotating(split_sets)
+
+    def step():
+        return sarpost.postprocess_fused(nxt(), spec, return_padded=True, **kw)
+
+    for _ in range(3):
+        step()
+    o_s, c_s = sarpost.postprocess_fused(split_sets[0], spec, return_padded=True, **kw)
+    o_c, c_c = sarpost.postprocess_fused(level_sets[0], spec, return_padded=True, **kw)
+    same = bool(torch.equal(c_s, c_c)) and all(bool(torch.equal(o_s[b, :n], o_c[b, :n])) for b, n in enumerate(c_c.tolist()))
+    ms1 = time_steps(cx, step, steps)
+    ms = ms1
+    if streams_n > 1:
+        streams = [torch.cuda.Stream() for _ in range(streams_n)]
+        for s_ in streams:
+            with torch.cuda.stream(s_):
+                for _ in range(3):
+                    step()
+        ms = time_steps(cx, step, steps, streams)
+    st = stage_means(cx, step, min(steps, 100))
+    ms, ms1 = cx.max_over_ranks(ms, ms1)
+    return {"value": bs * cx.world * steps / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / steps,
+            "single_stream": {"value": bs * cx.world * steps / (ms1 / 1e3), "ms_per_step": ms1 / steps},
+            "stage_ms": {"k1_candidates": st[0], "k2_k4_select_sort_nms": st[1], "k5_gather": st[2], "whole_call": st[3]},
+            "rows_identical_to_concatenated_layout": same, "steps": steps,
+            "layout": "per level: box (B,64,H,W), cls (B,nc,H,W), emb (B,H,W,E) channels_last, state (B,S,H,W); same values as the "
+                      "concatenated (B,no,H,W) inputs of `value`"}
+
+
 def leg_reference_gpu(cx, levels, strides, nc, ed, sc, kw, n_img, reps, our_rows):
     """The reference's own path on this GPU (see ReferencePath) on the first n_img images of the batch."""
     torch = cx.torch
@@ -657,7 +695,7 @@ def main():
         return run_reference_arm(args)
     ensure_built()
     if args.quick:
-        args.no_e2e = args.no_cpu_baseline = args.no_reference_gpu = args.no_clustered = args.no_sahi = True
+        args.no_e2e = args.no_cpu_baseline = args.no_reference_gpu = args.no_clustered = args.no_sahi = args.no_split = True
 
     cx = Ctx(args)
     torch, dist, sarpost = cx.torch, cx.dist, cx.sarpost
@@ -689,7 +727,8 @@ def main():
     hot_bytes = bs * anchors * (64 + nc) * 4
     n_sets = 1 if hot_bytes >= 2 * L2_BYTES else min(int(math.ceil(2 * L2_BYTES / hot_bytes)), 128)
     n_sets = max(n_sets, args.streams)
-    next_levels = rotating([levels] + [[x.clone() for x in levels] for _ in range(n_sets - 1)])
+    level_sets = [levels] + [[x.clone() for x in levels] for _ in range(n_sets - 1)]
+    next_levels = rotating(level_sets)
 
     def step():
         return sarpost.postprocess_fused(next_levels(), spec, return_padded=True, **kw)
@@ -754,6 +793,11 @@ def main():
         except Exception:
             pass
 
+    # ---- split layout (no torch.cat in front of K1, channels_last embedding) ----
+    split = None
+    if not args.no_split and not args.blobs:
+        split = leg_split(cx, level_sets, spec, bs, kw, max(10, min(args.steps, 200)), args.streams)
+
     # ---- clustered leg (same shapes / thresholds, suppression-heavy inputs) ----
     clustered = None
     if not args.no_clustered and not args.blobs:
@@ -789,7 +833,7 @@ def main():
     # ---- sliced inference (cfg4): the one exchange step of the path, measured whenever there is more than one rank ----
     sahi = None
     if world > 1 and not args.no_sahi:
-        del next_levels, levels
+        del next_levels, levels, level_sets
         torch.cuda.empty_cache()
         sahi = leg_sahi(cx, max(10, min(args.steps, 100)))
 
@@ -810,7 +854,7 @@ def main():
                                "126 MB L2), so every step reads its inputs from HBM; no flush" % (hot_bytes / 1e6, n_sets, n_sets * hot_bytes / 1e6))),
                        "input_sets": n_sets,
                        "candidates_per_image": n_cand / bs, "detections_per_image": n_det / bs},
-            "single_stream": single, "roofline": roofline, "clustered": clustered, "reference_gpu": ref_gpu, "cpu_baseline": cpu, "e2e": e2e,
+            "single_stream": single, "roofline": roofline, "split_layout": split, "clustered": clustered, "reference_gpu": ref_gpu, "cpu_baseline": cpu, "e2e": e2e,
             "sahi": sahi, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "clocks": clocks.summary(),
         }
         emit(line)

@@ -31,6 +31,9 @@ extern "C" {
 #define SARPOST_F32 0
 #define SARPOST_F16 1
 
+#define SARPOST_LAYOUT_CAT 0   /* one (B, no, H, W) tensor per level: the branches concatenated (head.py:204-206) */
+#define SARPOST_LAYOUT_SPLIT 1 /* one tensor per branch and level: the convolution outputs as they are, no torch.cat */
+
 #define SARPOST_OK 0
 #define SARPOST_EINVAL (-1)    /* bad argument */
 #define SARPOST_ECUDA (-2)     /* CUDA runtime error (message holds cudaGetErrorString) */
@@ -59,7 +62,19 @@ typedef struct sarpost_head {
     int32_t h[SARPOST_MAX_LEVELS];
     int32_t w[SARPOST_MAX_LEVELS];
     float stride[SARPOST_MAX_LEVELS]; /* Detect.stride (head.py:41) */
-    const void *data[SARPOST_MAX_LEVELS]; /* device (or, for *_host calls, host) pointers */
+    const void *data[SARPOST_MAX_LEVELS]; /* device (or, for *_host calls, host) pointers.  SPLIT layout: the box branch,
+                                             (B, 4*reg_max, H_l, W_l) — the output of cv2[l] (head.py:204) */
+    /* ---- SARPOST_LAYOUT_SPLIT only (device entry points; ignored for layout CAT) ----
+     * JDE.forward concatenates cv2 | cv3 | cv4 [| state] per level (head.py:204-206) only so that _inference can split
+     * them again (:232-235); at 1280x1280 P2, batch 16, that cat writes 2.85 GB of which the path reads 0.57 GB.  With the
+     * split layout the caller hands over the branch outputs directly.  The embedding may be channels-last
+     * ((B, H, W, E) in memory, what a channels_last cv4 branch writes): the <= max_det kept rows are then read as one
+     * contiguous E*4-byte run each instead of E isolated 4-byte reads 128-byte DRAM lines apart. */
+    int32_t layout;            /* SARPOST_LAYOUT_CAT (0, default) or SARPOST_LAYOUT_SPLIT */
+    int32_t emb_channels_last; /* 1: emb[l] is (B, H_l, W_l, n_extra_raw) in memory; 0: (B, n_extra_raw, H_l, W_l) */
+    const void *cls[SARPOST_MAX_LEVELS];   /* (B, nc, H_l, W_l): output of cv3[l] */
+    const void *emb[SARPOST_MAX_LEVELS];   /* output of cv4[l] (n_extra_raw channels), NULL when n_extra_raw == 0 */
+    const void *state[SARPOST_MAX_LEVELS]; /* (B, n_extra_sigmoid, H_l, W_l) state logits, NULL when n_extra_sigmoid == 0 */
 } sarpost_head_t;
 
 /* Keyword arguments of ops.non_max_suppression (utils/ops.py:167-182). */
@@ -195,6 +210,19 @@ int32_t sarpost_match_predictions(const float *dets, const int32_t *det_counts, 
                                   int32_t row_len, const float *gt_boxes, const float *gt_cls, const int32_t *gt_counts,
                                   int32_t max_gt, const float *iouv, int32_t n_thr, uint8_t *correct,
                                   int32_t *matched_gt, int32_t tag_thr, void *stream);
+
+/*
+ * The same matching at the boundary of BaseValidator.match_predictions(pred_classes, true_classes, iou)
+ * (engine/validator.py:222-262; JDE variant with tags: models/yolo/jde/val.py:683-736) for one image: the caller has
+ * already built the IoU matrix (box_iou, mask IoU, OKS ...); the reference copies it to the host and loops in numpy.
+ *   iou        device (n_gt, n_det) fp32, rows `iou_row_stride` elements apart
+ *   pred_cls   device (n_det) fp32;  true_cls device (n_gt) fp32
+ *   iouv       HOST (n_thr <= 16);  correct device (n_det, n_thr) uint8
+ *   matched_gt device (n_det) int32 or NULL: label index matched at threshold index tag_thr, else -1
+ */
+int32_t sarpost_match_from_iou(const float *iou, int32_t n_gt, int32_t n_det, int64_t iou_row_stride, const float *pred_cls,
+                               const float *true_cls, const float *iouv, int32_t n_thr, uint8_t *correct, int32_t *matched_gt,
+                               int32_t tag_thr, void *stream);
 
 /*
  * Deferred JDE state head.  Replaces the per-anchor evaluation of JDE.state_predictor inside

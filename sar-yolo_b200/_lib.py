@@ -24,6 +24,8 @@ class Head(C.Structure):
         ("n_extra_raw", C.c_int32), ("n_extra_sigmoid", C.c_int32), ("dtype", C.c_int32),
         ("h", C.c_int32 * MAX_LEVELS), ("w", C.c_int32 * MAX_LEVELS), ("stride", C.c_float * MAX_LEVELS),
         ("data", C.c_void_p * MAX_LEVELS),
+        ("layout", C.c_int32), ("emb_channels_last", C.c_int32),
+        ("cls", C.c_void_p * MAX_LEVELS), ("emb", C.c_void_p * MAX_LEVELS), ("state", C.c_void_p * MAX_LEVELS),
     ]
 
 
@@ -66,6 +68,8 @@ SYMBOLS = {
     "sarpost_match_predictions": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.c_int32, C.c_void_p, C.c_void_p,
                                               C.c_int32, C.c_void_p]),
+    "sarpost_match_from_iou": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
+                                           C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "sarpost_state_head": (C.c_int32, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p] * 5),
     "sarpost_host_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
     "sarpost_host_ctx_destroy": (None, [C.c_void_p]),

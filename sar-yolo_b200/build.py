@@ -26,21 +26,26 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
+    """`out` / `defines`: side builds for experiments (e.g. the phase-profiling variant: out=libsarpost_prof.so,
+    defines=("SARPOST_PHASE_PROF",), loaded through SARPOST_LIB_PATH); the product library is always LIB."""
+    if out is None and not force and not is_stale():
         return LIB
-    extra = os.environ.get("SARPOST_EXTRA_NVCC_FLAGS", "").split()
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+    extra = os.environ.get("SARPOST_EXTRA_NVCC_FLAGS", "").split() + [f"-D{d}" for d in defines]
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out or LIB] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
     import sys
 
-    print(build(force=True, verbose="-v" in sys.argv))
+    if "--prof" in sys.argv:
+        print(build(out=os.path.join(HERE, "libsarpost_prof.so"), defines=("SARPOST_PHASE_PROF",)))
+    else:
+        print(build(force=True, verbose="-v" in sys.argv))

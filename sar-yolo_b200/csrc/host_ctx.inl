@@ -154,6 +154,7 @@ static int32_t fused_host_impl(sarpost_host_ctx_t *c, const sarpost_head_t *head
     if (int rc = check_params(params, g.nc)) return rc;
     if (!out || !counts) return fail(SARPOST_EINVAL, "NULL output pointer");
     if (g.is_half) return fail(SARPOST_EUNSUPPORTED, "sarpost_fused_host takes fp32 host tensors");
+    if (g.split) return fail(SARPOST_EUNSUPPORTED, "sarpost_fused_host takes the concatenated level tensors (layout 0)");
     CUDA_TRY(cudaSetDevice(c->device));
     const int B = g.batch, nch = 4 * kRegMax + g.nc, nm = g.n_extra_raw + g.n_extra_sig, max_det = params->max_det;
     c->last_h2d = c->last_d2h = 0;

@@ -22,10 +22,24 @@ struct HeadGeom {
     int32_t lvl_w[kMaxLevels];
     int32_t lvl_aoff[kMaxLevels + 1];      // first global anchor index of the level; [nl] = A
     float lvl_stride[kMaxLevels];
-    const void *lvl_ptr[kMaxLevels];  // elements of type float or __half (kernel template parameter)
+    const void *lvl_ptr[kMaxLevels];  // elements of type float or __half (kernel template parameter); split layout: box branch
     int32_t is_half;
     uint32_t lvl_w_magic[kMaxLevels];  // ceil(2^32 / W_l): y = pos / W_l without an integer division
+    // split layout (SARPOST_LAYOUT_SPLIT): one tensor per branch, see include/sarpost.h
+    int32_t split, emb_cl;
+    const void *lvl_cls[kMaxLevels];
+    const void *lvl_emb[kMaxLevels];
+    const void *lvl_state[kMaxLevels];
 };
+
+// Element pointer of (image b, logical channel c, position pos) of level l, c in [0, 4*reg_max + nc): box then class rows.
+template <typename T>
+__device__ __forceinline__ const T *hot_channel_ptr(const HeadGeom &g, int l, int b, int c, int pos) {
+    const int64_t hw = g.lvl_hw[l];
+    if (!g.split) return static_cast<const T *>(g.lvl_ptr[l]) + (static_cast<int64_t>(b) * g.no + c) * hw + pos;
+    if (c < 4 * kRegMax) return static_cast<const T *>(g.lvl_ptr[l]) + (static_cast<int64_t>(b) * (4 * kRegMax) + c) * hw + pos;
+    return static_cast<const T *>(g.lvl_cls[l]) + (static_cast<int64_t>(b) * g.nc + (c - 4 * kRegMax)) * hw + pos;
+}
 
 // floor(n / d) for n*d < 2^32-ish operands via a precomputed magic = ceil(2^32 / d) and one correction step
 __device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
@@ -224,7 +238,8 @@ __device__ __forceinline__ int tile_level(const HeadGeom &g, int r) {
 // reads column t -> conflict-free, and the extras channels are never fetched.
 // ---------------------------------------------------------------------------------------------
 struct K1TmaParams {
-    CUtensorMap maps[kMaxLevels];
+    CUtensorMap maps[kMaxLevels];      // cat layout: box + cls rows of the level tensor; split layout: the box branch
+    CUtensorMap maps_cls[kMaxLevels];  // split layout: the class branch
     HeadGeom g;
     CandFilter f;
     CandStore st;
@@ -247,7 +262,10 @@ __global__ void __launch_bounds__(kTileA, sizeof(T) == 2 ? 6 : 3) k1_fused_tma(c
     if (tid == 0) {
         for (int s = 0; s < p.stages; ++s) mbar_init(&full_bar[s], 1);
         fence_barrier_init();
-        for (int l = 0; l < p.g.nl; ++l) tma_prefetch_desc(&p.maps[l]);
+        for (int l = 0; l < p.g.nl; ++l) {
+            tma_prefetch_desc(&p.maps[l]);
+            if (p.g.split) tma_prefetch_desc(&p.maps_cls[l]);
+        }
     }
     __syncthreads();
 
@@ -265,7 +283,10 @@ __global__ void __launch_bounds__(kTileA, sizeof(T) == 2 ? 6 : 3) k1_fused_tma(c
         const int l = tile_level(p.g, r);
         const int a0 = (r - p.g.lvl_tile_begin[l]) * kTileA;
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_3d(dyn + static_cast<size_t>(s) * stage_bytes, &p.maps[l], a0, 0, b, &full_bar[s]);
+        unsigned char *dst = dyn + static_cast<size_t>(s) * stage_bytes;
+        tma_load_3d(dst, &p.maps[l], a0, 0, b, &full_bar[s]);
+        if (p.g.split)  // the class rows land right behind the 4*reg_max box rows: same smem[channel][anchor] tile as the cat layout
+            tma_load_3d(dst + static_cast<size_t>(4 * kRegMax) * kTileA * sizeof(T), &p.maps_cls[l], a0, 0, b, &full_bar[s]);
     };
     int ib = first / p.g.tpi, ir = first - ib * p.g.tpi;  // next tile to issue (thread 0)
     if (tid == 0)
@@ -318,12 +339,12 @@ __global__ void __launch_bounds__(kTileA) k1_fused_ldg(const __grid_constant__ K
     const int pos = (r - p.g.lvl_tile_begin[l]) * kTileA + threadIdx.x;
     const bool valid = pos < hw;
     const int pc = valid ? pos : hw - 1;
-    const T *base = static_cast<const T *>(p.g.lvl_ptr[l]) + static_cast<int64_t>(b) * p.g.no * hw + pc;
-    auto acc = [&](int c) { return to_f32(__ldg(base + static_cast<int64_t>(c) * hw)); };
+    const T *base_box = hot_channel_ptr<T>(p.g, l, b, 0, pc), *base_cls = hot_channel_ptr<T>(p.g, l, b, 4 * kRegMax, pc);
+    auto acc = [&](int c) { return to_f32(__ldg(base_box + static_cast<int64_t>(c) * hw)); };
     const int w = p.g.lvl_w[l];
     const int yy = fast_div(pc, w, p.g.lvl_w_magic[l]), xx = pc - yy * w;
     const float4 xyxy = xywh2xyxy_rn(decode_xywh(acc, xx, yy, p.g.lvl_stride[l]));
-    auto score = [&](int j) { return sigmoid_rn(acc(4 * kRegMax + j)); };
+    auto score = [&](int j) { return sigmoid_rn(to_f32(__ldg(base_cls + static_cast<int64_t>(j) * hw))); };
     emit_candidates(valid, xyxy, static_cast<uint32_t>(p.g.lvl_aoff[l] + pc), p.g.nc, p.f, score, p.st, b, r, scratch);
 }
 

@@ -34,7 +34,8 @@
 namespace sarpost {
 
 #ifdef SARPOST_PHASE_PROF
-__device__ unsigned long long g_phase[16];
+__device__ unsigned long long g_phase[16];  // cycles of block 0 per phase: 0 prologue, 1 collect, 2 share phase 1, 3 deliver + barrier 1,
+// 4 sort, 9 master tail + replicate + barrier 2, 8 publish; inside process_sorted: 10 load, 11 incremental phase 1, 12 compaction, 13 bitmask, 14 sweep
 #define PROF_MARK(i)                                                         \
     do {                                                                     \
         if (blockIdx.x == 0 && threadIdx.x == 0) {                           \
@@ -67,30 +68,52 @@ struct ExtrasSrc {
     int32_t lvl_hw[kMaxLevels];
     const void *lvl_ptr[kMaxLevels];
     int32_t is_half;            // element type of the level tensors (mode 1) / of the prediction (mode 0)
+    // mode 1, split layout (SARPOST_LAYOUT_SPLIT): the extras come from their own branch tensors
+    int32_t split, emb_cl;
+    const void *lvl_emb[kMaxLevels];    // (B, E, H, W), or channels-last (B, H, W, E) when emb_cl
+    const void *lvl_state[kMaxLevels];  // (B, S, H, W) logits
     // mode 2
     const float *dets;
     int32_t dets_per_tile, row_len;
 };
 
-// element index (from the start of its tensor) of extras channel 0 of (image b, anchor), the element stride
-// between channels, and the tensor base pointer
-__device__ __forceinline__ int64_t extras_base(const ExtrasSrc &e, int b, uint32_t anchor, int64_t *stride, const void **base) {
+__device__ __forceinline__ float load_elem(const void *base, int64_t idx, bool is_half) {
+    return is_half ? __half2float(__ldg(static_cast<const __half *>(base) + idx)) : __ldg(static_cast<const float *>(base) + idx);
+}
+
+// Extras of (image b, anchor) for modes 0 and 1: store(c, value) for c = lane, lane + 32, ... < nm.  Raw embedding
+// columns are copied, state columns pass through the sigmoid (head.py:247); a decoded prediction is copied verbatim.
+template <class Store>
+__device__ __forceinline__ void gather_extras_row(const ExtrasSrc &e, int b, uint32_t anchor, int lane, const Store &store) {
+    const bool hf = e.is_half != 0;
     if (e.mode == 0) {
-        *stride = e.anchors;
-        *base = e.pred;
-        return (static_cast<int64_t>(b) * e.channels + 4 + e.nc) * e.anchors + anchor;
+        const int64_t at = (static_cast<int64_t>(b) * e.channels + 4 + e.nc) * e.anchors + anchor;
+        for (int c = lane; c < e.nm; c += 32) store(c, load_elem(e.pred, at + c * e.anchors, hf));
+        return;
     }
     int l = 0;
 #pragma unroll
     for (int i = 1; i < kMaxLevels; ++i) l += (i < e.nl && anchor >= static_cast<uint32_t>(e.lvl_aoff[i])) ? 1 : 0;
-    const int hw = e.lvl_hw[l];
-    *stride = hw;
-    *base = e.lvl_ptr[l];
-    return (static_cast<int64_t>(b) * e.no + 4 * kRegMax + e.nc) * hw + (anchor - e.lvl_aoff[l]);
-}
-
-__device__ __forceinline__ float load_elem(const void *base, int64_t idx, bool is_half) {
-    return is_half ? __half2float(__ldg(static_cast<const __half *>(base) + idx)) : __ldg(static_cast<const float *>(base) + idx);
+    const int64_t hw = e.lvl_hw[l];
+    const int64_t pos = anchor - e.lvl_aoff[l];
+    if (!e.split) {
+        const int64_t at = (static_cast<int64_t>(b) * e.no + 4 * kRegMax + e.nc) * hw + pos;
+        for (int c = lane; c < e.nm; c += 32) {
+            const float v = load_elem(e.lvl_ptr[l], at + c * hw, hf);
+            store(c, c < e.n_extra_raw ? v : sigmoid_rn(v));
+        }
+        return;
+    }
+    const int n_raw = e.n_extra_raw, n_sig = e.nm - e.n_extra_raw;
+    if (e.emb_cl) {  // one contiguous run of n_raw elements per kept row
+        const int64_t at = (static_cast<int64_t>(b) * hw + pos) * n_raw;
+        for (int c = lane; c < n_raw; c += 32) store(c, load_elem(e.lvl_emb[l], at + c, hf));
+    } else {
+        const int64_t at = static_cast<int64_t>(b) * n_raw * hw + pos;
+        for (int c = lane; c < n_raw; c += 32) store(c, load_elem(e.lvl_emb[l], at + c * hw, hf));
+    }
+    const int64_t at_s = static_cast<int64_t>(b) * n_sig * hw + pos;
+    for (int c = lane; c < n_sig; c += 32) store(n_raw + c, sigmoid_rn(load_elem(e.lvl_state[l], at_s + c * hw, hf)));
 }
 
 struct NmsParams {
@@ -448,7 +471,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 S_A_SLOT[tid] = slot;
             }
             __syncthreads();
-            PROF_MARK(3);
+            PROF_MARK(10);
             // ---- incremental phase 1: candidates x boxes kept since they were last tested ----
             if (kept > k_from) {
                 int sub_p2 = 64;
@@ -458,7 +481,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 st_pairs += static_cast<long long>(sub) * (kept - k_from);
                 __syncthreads();
             }
-            PROF_MARK(4);
+            PROF_MARK(11);
             // ---- ordered compaction of survivors (first kSub threads = 8 warps) ----
             bool alive = false;
             uint32_t bal = 0;
@@ -481,7 +504,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 S_C_SLOT[at] = S_A_SLOT[tid];
             }
             __syncthreads();
-            PROF_MARK(5);
+            PROF_MARK(12);
             // ---- phase 2: suppression bitmask among the m survivors (row r, bits j > r) ----
             // warp per row r, lane j tests the pair (r, 32w + j) for every word w >= r/32; a ballot packs the word
             const int words = (m + 31) >> 5;
@@ -520,7 +543,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 }
             }
             __syncthreads();
-            PROF_MARK(6);
+            PROF_MARK(13);
             // ---- sweep (warp 0) ----
             if (warp == 0) {
                 uint32_t km[kSubWords];  // kept bits of the groups resolved so far (warp-uniform)
@@ -592,7 +615,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             kept = S_MISC[kMKept];
             pdone += sub;
             __syncthreads();
-            PROF_MARK(7);
+            PROF_MARK(14);
         }
     };
 
@@ -797,7 +820,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             m = S_MISC[kMCtl + 2];
             const int s_all = S_MISC[kMCtl + 3];
             par ^= 1;
-            PROF_MARK(5);
+            PROF_MARK(9);
             if (action == kActHalve) {
                 d1 = d + (d1 - d) / 2;
                 continue;
@@ -933,16 +956,9 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
         for (int c = lane; c < p.ex.nm; c += 32)
             for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = 0.0f;  // apriori label row: no extras (ops.py:258)
     } else if (p.ex.nm > 0) {
-        int64_t stride;
-        const void *base;
-        const int64_t at = extras_base(p.ex, b, anchor, &stride, &base);
-        const bool hf = p.ex.is_half != 0;
-        const int n_raw = p.ex.mode == 0 ? p.ex.nm : p.ex.n_extra_raw;  // a decoded prediction is copied verbatim
-        for (int c = lane; c < p.ex.nm; c += 32) {
-            float v = load_elem(base, at + c * stride, hf);
-            v = c < n_raw ? v : sigmoid_rn(v);
+        gather_extras_row(p.ex, b, anchor, lane, [&](int c, float v) {
             for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = v;
-        }
+        });
     }
 }
 
@@ -950,33 +966,21 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
 // the rows that need them are only known after a later stage (cross-tile merge).  One warp per pair.
 struct GatherExtrasParams {
     const int32_t *image_index, *anchor_index;
-    int32_t n;
+    int32_t n, batch;
     float *out;  // [n, nm]
-    int32_t nl, no, nc, batch, n_extra_raw, nm;
-    int32_t lvl_aoff[kMaxLevels + 1];
-    int32_t lvl_hw[kMaxLevels];
-    const void *lvl_ptr[kMaxLevels];
-    int32_t is_half;
+    ExtrasSrc ex;  // mode 1
 };
 
 __global__ void __launch_bounds__(kGatherWarps * 32) k_gather_extras(const __grid_constant__ GatherExtrasParams p) {
     const int q = blockIdx.x * kGatherWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (q >= p.n) return;
     const int b = p.image_index[q], a = p.anchor_index[q];
-    float *o = p.out + static_cast<int64_t>(q) * p.nm;
-    if (b < 0 || b >= p.batch || a < 0 || a >= p.lvl_aoff[p.nl]) {  // out-of-range pair: zero row
-        for (int c = lane; c < p.nm; c += 32) o[c] = 0.0f;
+    float *o = p.out + static_cast<int64_t>(q) * p.ex.nm;
+    if (b < 0 || b >= p.batch || a < 0 || a >= p.ex.lvl_aoff[p.ex.nl]) {  // out-of-range pair: zero row
+        for (int c = lane; c < p.ex.nm; c += 32) o[c] = 0.0f;
         return;
     }
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < kMaxLevels; ++i) l += (i < p.nl && a >= p.lvl_aoff[i]) ? 1 : 0;
-    const int hw = p.lvl_hw[l];
-    const int64_t at = (static_cast<int64_t>(b) * p.no + 4 * kRegMax + p.nc) * hw + (a - p.lvl_aoff[l]);
-    for (int c = lane; c < p.nm; c += 32) {
-        const float v = load_elem(p.lvl_ptr[l], at + static_cast<int64_t>(c) * hw, p.is_half != 0);
-        o[c] = c < p.n_extra_raw ? v : sigmoid_rn(v);
-    }
+    gather_extras_row(p.ex, b, static_cast<uint32_t>(a), lane, [&](int c, float v) { o[c] = v; });
 }
 
 }  // namespace sarpost

@@ -86,4 +86,56 @@ __global__ void __launch_bounds__(kMatchThreads) k6_match(const __grid_constant_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Same matching from a PRECOMPUTED IoU matrix — the boundary of BaseValidator.match_predictions(pred_classes,
+// true_classes, iou) (engine/validator.py:222; JDE: jde/val.py:683), whose callers build `iou (L, D)` themselves
+// (box_iou, mask IoU, OKS, probiou).  One image per launch, one CTA.
+// ---------------------------------------------------------------------------------------------
+struct MatchIouParams {
+    const float *iou;         // (n_gt, n_det), row stride `ld`
+    int64_t ld;
+    const float *pred_cls;    // (n_det)
+    const float *true_cls;    // (n_gt)
+    int32_t n_det, n_gt;
+    float iouv[kMaxThr];
+    int32_t n_thr;
+    uint8_t *correct;         // (n_det, n_thr)
+    int32_t *matched_gt;      // (n_det) or nullptr
+    int32_t tag_thr;
+};
+
+__global__ void __launch_bounds__(kMatchThreads) k6_match_iou(const __grid_constant__ MatchIouParams p) {
+    extern __shared__ __align__(16) unsigned char match_smem[];
+    float *best_iou = reinterpret_cast<float *>(match_smem);
+    int32_t *best_l = reinterpret_cast<int32_t *>(best_iou + p.n_det);
+    int32_t *dmin = best_l + p.n_det;
+    const int tid = threadIdx.x;
+    for (int d = tid; d < p.n_det; d += kMatchThreads) {  // consecutive threads read consecutive columns of a row: coalesced
+        const float dc = p.pred_cls[d];
+        float bi = 0.0f;
+        int bl = -1;
+        for (int l = 0; l < p.n_gt; ++l) {
+            const float v = p.true_cls[l] == dc ? p.iou[static_cast<int64_t>(l) * p.ld + d] : 0.0f;  // iou * correct_class
+            if (v > bi) { bi = v; bl = l; }
+        }
+        best_iou[d] = bi;
+        best_l[d] = bl;
+    }
+    __syncthreads();
+    for (int t = 0; t < p.n_thr; ++t) {
+        const float thr = p.iouv[t];
+        for (int l = tid; l < p.n_gt; l += kMatchThreads) dmin[l] = 0x7fffffff;
+        __syncthreads();
+        for (int d = tid; d < p.n_det; d += kMatchThreads)
+            if (best_l[d] >= 0 && best_iou[d] >= thr) atomicMin(&dmin[best_l[d]], d);
+        __syncthreads();
+        for (int d = tid; d < p.n_det; d += kMatchThreads) {
+            const bool ok = best_l[d] >= 0 && best_iou[d] >= thr && dmin[best_l[d]] == d;
+            p.correct[static_cast<int64_t>(d) * p.n_thr + t] = ok ? 1 : 0;
+            if (p.matched_gt && t == p.tag_thr) p.matched_gt[d] = ok ? best_l[d] : -1;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace sarpost

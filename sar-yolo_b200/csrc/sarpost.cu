@@ -182,7 +182,10 @@ static int fill_geom(const sarpost_head_t *h, HeadGeom *g, int64_t *anchors) {
     if (h->batch < 1) return fail(SARPOST_EINVAL, "batch %d < 1", h->batch);
     if (h->dtype != SARPOST_F32 && h->dtype != SARPOST_F16) return fail(SARPOST_EUNSUPPORTED, "dtype %d unsupported (0 = f32, 1 = f16)", h->dtype);
     if (h->nc < 1 || h->nc > SARPOST_MAX_CLASSES) return fail(SARPOST_EUNSUPPORTED, "nc %d outside [1, %d]", h->nc, SARPOST_MAX_CLASSES);
-    if (h->n_extra_raw < 0 || h->n_extra_sigmoid < 0 || h->no < 4 * kRegMax + h->nc + h->n_extra_raw + h->n_extra_sigmoid)
+    if (h->layout != SARPOST_LAYOUT_CAT && h->layout != SARPOST_LAYOUT_SPLIT) return fail(SARPOST_EINVAL, "layout %d unknown (0 = cat, 1 = split)", h->layout);
+    const bool split = h->layout == SARPOST_LAYOUT_SPLIT;
+    if (h->n_extra_raw < 0 || h->n_extra_sigmoid < 0) return fail(SARPOST_EINVAL, "negative extras count");
+    if (!split && h->no < 4 * kRegMax + h->nc + h->n_extra_raw + h->n_extra_sigmoid)
         return fail(SARPOST_EINVAL, "no %d < 4*reg_max + nc + extras (%d)", h->no, 4 * kRegMax + h->nc + h->n_extra_raw + h->n_extra_sigmoid);
     memset(g, 0, sizeof(*g));
     g->nl = h->nl;
@@ -192,11 +195,21 @@ static int fill_geom(const sarpost_head_t *h, HeadGeom *g, int64_t *anchors) {
     g->n_extra_raw = h->n_extra_raw;
     g->n_extra_sig = h->n_extra_sigmoid;
     g->is_half = h->dtype == SARPOST_F16;
+    g->split = split ? 1 : 0;
+    g->emb_cl = (split && h->emb_channels_last) ? 1 : 0;
     int64_t a = 0, t = 0;
     for (int l = 0; l < h->nl; ++l) {
         if (h->h[l] < 1 || h->w[l] < 1) return fail(SARPOST_EINVAL, "level %d has empty shape %dx%d", l, h->h[l], h->w[l]);
         if (static_cast<int64_t>(h->h[l]) * h->w[l] >= (1 << 24)) return fail(SARPOST_EUNSUPPORTED, "level %d has more than 2^24 anchors", l);
         if (!h->data[l]) return fail(SARPOST_EINVAL, "level %d data pointer is NULL", l);
+        if (split) {
+            if (!h->cls[l]) return fail(SARPOST_EINVAL, "level %d class-branch pointer is NULL (split layout)", l);
+            if (h->n_extra_raw > 0 && !h->emb[l]) return fail(SARPOST_EINVAL, "level %d embedding-branch pointer is NULL (split layout)", l);
+            if (h->n_extra_sigmoid > 0 && !h->state[l]) return fail(SARPOST_EINVAL, "level %d state-branch pointer is NULL (split layout)", l);
+            g->lvl_cls[l] = h->cls[l];
+            g->lvl_emb[l] = h->emb[l];
+            g->lvl_state[l] = h->state[l];
+        }
         const int64_t hw = static_cast<int64_t>(h->h[l]) * h->w[l];
         g->lvl_tile_begin[l] = static_cast<int32_t>(t);
         g->lvl_hw[l] = static_cast<int32_t>(hw);
@@ -239,6 +252,7 @@ static bool tma_eligible(const HeadGeom &g) {
     for (int l = 0; l < g.nl; ++l) {
         if ((static_cast<int64_t>(g.lvl_hw[l]) * (g.is_half ? 2 : 4)) % 16) return false;
         if (reinterpret_cast<uintptr_t>(g.lvl_ptr[l]) % 16) return false;
+        if (g.split && reinterpret_cast<uintptr_t>(g.lvl_cls[l]) % 16) return false;
     }
     return get_encode_fn() != nullptr;
 }
@@ -292,15 +306,20 @@ static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandSto
         p.stages = stages;
         p.n_tiles = g.batch * g.tpi;
         PFN_encodeTiled enc = get_encode_fn();
-        for (int l = 0; l < g.nl; ++l) {
-            const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.lvl_hw[l]), static_cast<cuuint64_t>(g.no), static_cast<cuuint64_t>(g.batch)};
-            const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lvl_hw[l]) * esz, static_cast<cuuint64_t>(g.lvl_hw[l]) * g.no * esz};
-            const cuuint32_t box[3] = {kTileA, static_cast<cuuint32_t>(nch), 1};
+        const CUtensorMapDataType dt = g.is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+        const CUtensorMapL2promotion promo = static_cast<CUtensorMapL2promotion>(env_int("SARPOST_K1_L2PROMO", CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+        // one 3-D map (anchors of the level, channels, images) per tensor the tile is assembled from; box = {kTileA, rows, 1}
+        auto encode = [&](CUtensorMap *m, const void *ptr, int l, int channels_in_tensor, int rows) -> CUresult {
+            const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.lvl_hw[l]), static_cast<cuuint64_t>(channels_in_tensor), static_cast<cuuint64_t>(g.batch)};
+            const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lvl_hw[l]) * esz, static_cast<cuuint64_t>(g.lvl_hw[l]) * channels_in_tensor * esz};
+            const cuuint32_t box[3] = {kTileA, static_cast<cuuint32_t>(rows), 1};
             const cuuint32_t estr[3] = {1, 1, 1};
-            const CUresult r = enc(&p.maps[l], g.is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(g.lvl_ptr[l]), dims, strides, box, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   static_cast<CUtensorMapL2promotion>(env_int("SARPOST_K1_L2PROMO", CU_TENSOR_MAP_L2_PROMOTION_L2_256B)),
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            return enc(m, dt, 3, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        };
+        for (int l = 0; l < g.nl; ++l) {
+            CUresult r = g.split ? encode(&p.maps[l], g.lvl_ptr[l], l, 4 * kRegMax, 4 * kRegMax) : encode(&p.maps[l], g.lvl_ptr[l], l, g.no, nch);
+            if (r == CUDA_SUCCESS && g.split) r = encode(&p.maps_cls[l], g.lvl_cls[l], l, g.nc, g.nc);
             if (r != CUDA_SUCCESS) return fail(SARPOST_ECUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, static_cast<int>(r));
         }
         const int smem = static_cast<int>(stages * stage_bytes + 128);
@@ -325,6 +344,27 @@ static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandSto
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return SARPOST_OK;
+}
+
+// where the gather kernel finds the extras of a kept row when the input is the raw level tensors (mode 1)
+static void fill_extras_src(const HeadGeom &g, ExtrasSrc *ex) {
+    memset(ex, 0, sizeof(*ex));
+    ex->mode = 1;
+    ex->nc = g.nc;
+    ex->nm = g.n_extra_raw + g.n_extra_sig;
+    ex->nl = g.nl;
+    ex->no = g.no;
+    ex->n_extra_raw = g.n_extra_raw;
+    for (int l = 0; l <= kMaxLevels; ++l) ex->lvl_aoff[l] = g.lvl_aoff[l];
+    for (int l = 0; l < kMaxLevels; ++l) {
+        ex->lvl_hw[l] = g.lvl_hw[l];
+        ex->lvl_ptr[l] = g.lvl_ptr[l];
+        ex->lvl_emb[l] = g.lvl_emb[l];
+        ex->lvl_state[l] = g.lvl_state[l];
+    }
+    ex->is_half = g.is_half;
+    ex->split = g.split;
+    ex->emb_cl = g.emb_cl;
 }
 
 // K2 + K4 + K5 on a filled candidate store.
@@ -479,6 +519,7 @@ int32_t sarpost_decode(const sarpost_head_t *head, void *y, void *stream) {
     int64_t anchors = 0;
     if (int rc = fill_geom(head, &g, &anchors)) return rc;
     if (!y) return fail(SARPOST_EINVAL, "y is NULL");
+    if (g.split) return fail(SARPOST_EUNSUPPORTED, "sarpost_decode reproduces JDE._inference, which takes the concatenated levels (layout 0)");
     DecodeYParams p;
     p.g = g;
     p.y = y;
@@ -579,19 +620,7 @@ int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *pa
     stage_mark(2, s);
 
     ExtrasSrc ex;
-    memset(&ex, 0, sizeof(ex));
-    ex.mode = 1;
-    ex.nc = g.nc;
-    ex.nm = g.n_extra_raw + g.n_extra_sig;
-    ex.nl = g.nl;
-    ex.no = g.no;
-    ex.n_extra_raw = g.n_extra_raw;
-    for (int l = 0; l <= kMaxLevels; ++l) ex.lvl_aoff[l] = g.lvl_aoff[l];
-    for (int l = 0; l < kMaxLevels; ++l) {
-        ex.lvl_hw[l] = g.lvl_hw[l];
-        ex.lvl_ptr[l] = g.lvl_ptr[l];
-    }
-    ex.is_half = g.is_half;
+    fill_extras_src(g, &ex);
     return run_tail(P, g.batch, params, g.nc, ex, out, counts, kept_index, s);
 }
 
@@ -648,19 +677,9 @@ int32_t sarpost_gather_extras(const sarpost_head_t *head, const int32_t *image_i
     p.image_index = image_index;
     p.anchor_index = anchor_index;
     p.n = n;
-    p.out = out;
-    p.nl = g.nl;
-    p.no = g.no;
-    p.nc = g.nc;
     p.batch = g.batch;
-    p.n_extra_raw = g.n_extra_raw;
-    p.nm = g.n_extra_raw + g.n_extra_sig;
-    for (int l = 0; l <= kMaxLevels; ++l) p.lvl_aoff[l] = g.lvl_aoff[l];
-    for (int l = 0; l < kMaxLevels; ++l) {
-        p.lvl_hw[l] = g.lvl_hw[l];
-        p.lvl_ptr[l] = g.lvl_ptr[l];
-    }
-    p.is_half = g.is_half;
+    p.out = out;
+    fill_extras_src(g, &p.ex);
     k_gather_extras<<<(n + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(p);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
@@ -695,6 +714,37 @@ int32_t sarpost_match_predictions(const float *dets, const int32_t *det_counts, 
     if (smem > 200 * 1024) return fail(SARPOST_EUNSUPPORTED, "max_det/max_gt too large for one CTA");
     CUDA_TRY(cudaFuncSetAttribute(k6_match, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     k6_match<<<batch, kMatchThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    return SARPOST_OK;
+}
+
+int32_t sarpost_match_from_iou(const float *iou, int32_t n_gt, int32_t n_det, int64_t iou_row_stride, const float *pred_cls,
+                               const float *true_cls, const float *iouv, int32_t n_thr, uint8_t *correct, int32_t *matched_gt,
+                               int32_t tag_thr, void *stream) {
+    g_launches = 0;
+    if (n_det < 0 || n_gt < 0) return fail(SARPOST_EINVAL, "negative matrix size");
+    if (n_det == 0) return SARPOST_OK;
+    if (!correct || !iouv || !pred_cls || (n_gt > 0 && (!iou || !true_cls))) return fail(SARPOST_EINVAL, "NULL pointer");
+    if (n_thr < 1 || n_thr > kMaxThr) return fail(SARPOST_EINVAL, "n_thr %d outside [1, %d]", n_thr, kMaxThr);
+    if (iou_row_stride < n_det) return fail(SARPOST_EINVAL, "iou_row_stride %lld < n_det %d", (long long)iou_row_stride, n_det);
+    MatchIouParams p;
+    memset(&p, 0, sizeof(p));
+    p.iou = iou;
+    p.ld = iou_row_stride;
+    p.pred_cls = pred_cls;
+    p.true_cls = true_cls;
+    p.n_det = n_det;
+    p.n_gt = n_gt;
+    for (int i = 0; i < n_thr; ++i) p.iouv[i] = iouv[i];
+    p.n_thr = n_thr;
+    p.correct = correct;
+    p.matched_gt = matched_gt;
+    p.tag_thr = tag_thr;
+    const size_t smem = static_cast<size_t>(n_det) * 8 + static_cast<size_t>(n_gt) * 4;
+    if (smem > 200 * 1024) return fail(SARPOST_EUNSUPPORTED, "n_det/n_gt too large for one CTA");
+    CUDA_TRY(cudaFuncSetAttribute(k6_match_iou, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    k6_match_iou<<<1, kMatchThreads, smem, static_cast<cudaStream_t>(stream)>>>(p);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return SARPOST_OK;

@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import Head, NmsParams, lib
 
-__all__ = ["HeadSpec", "StateMLP", "state_head", "non_max_suppression", "decode", "postprocess_fused", "merge_tiles", "gather_extras", "match_predictions", "postprocess_host",
+__all__ = ["HeadSpec", "StateMLP", "state_head", "non_max_suppression", "decode", "postprocess_fused", "split_levels", "cat_levels", "merge_tiles", "gather_extras", "match_predictions", "match_from_iou", "postprocess_host",
            "HostContext", "last_launch_count", "stage_timing", "stage_times"]
 
 
@@ -166,43 +166,129 @@ def _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det,
     return p, keep
 
 
-def _make_head(levels: Sequence[torch.Tensor], spec: HeadSpec, host: bool = False, with_extras: bool = True) -> Head:
+def _is_split(levels) -> bool:
+    """Split layout (SARPOST_LAYOUT_SPLIT): every level is a tuple `(box, cls[, emb[, state]])` of branch outputs."""
+    return len(levels) > 0 and isinstance(levels[0], (tuple, list))
+
+
+def _box_of(level) -> torch.Tensor:
+    return level[0] if isinstance(level, (tuple, list)) else level
+
+
+def _emb_channels_last(e: torch.Tensor) -> bool:
+    """`e (B, E, H, W)` stored as (B, H, W, E) — what a channels_last convolution writes — and not also plain NCHW."""
+    return (not e.is_contiguous()) and e.is_contiguous(memory_format=torch.channels_last)
+
+
+def _make_head(levels, spec: HeadSpec, host: bool = False, with_extras: bool = True) -> Head:
     if len(levels) != len(spec.strides):
         raise ValueError(f"sarpost: {len(levels)} level tensors but {len(spec.strides)} strides")
     if len(levels) > _lib.MAX_LEVELS:
         raise ValueError(f"sarpost: at most {_lib.MAX_LEVELS} levels")
+    split = _is_split(levels)
+    first = _box_of(levels[0])
     h = Head()
     h.nl = len(levels)
-    h.batch = int(levels[0].shape[0])
+    h.batch = int(first.shape[0])
     h.no = spec.no
     h.nc = spec.nc
     h.reg_max = spec.reg_max
     h.n_extra_raw = spec.embed_dim if with_extras else 0
     h.n_extra_sigmoid = spec.state_classes if with_extras else 0
-    h.dtype = 1 if levels[0].dtype == torch.float16 else 0
-    for i, x in enumerate(levels):
-        if x.dim() != 4 or x.shape[0] != h.batch or x.shape[1] != spec.no:
-            raise ValueError(f"sarpost: level {i} has shape {tuple(x.shape)}, expected (B={h.batch}, no={spec.no}, H, W)")
-        if x.dtype != levels[0].dtype or x.dtype not in (torch.float32, torch.float16) or not x.is_contiguous():
+    h.dtype = 1 if first.dtype == torch.float16 else 0
+    h.layout = 1 if split else 0
+
+    def check(x, i, channels, what, channels_last_ok=False):
+        if x.dim() != 4 or x.shape[0] != h.batch or x.shape[1] != channels:
+            raise ValueError(f"sarpost: level {i} {what} has shape {tuple(x.shape)}, expected (B={h.batch}, {channels}, H, W)")
+        ok_layout = x.is_contiguous() or (channels_last_ok and x.is_contiguous(memory_format=torch.channels_last))
+        if x.dtype != first.dtype or x.dtype not in (torch.float32, torch.float16) or not ok_layout:
             raise ValueError("sarpost: level tensors must be contiguous and all float32 or all float16")
         if host == x.is_cuda:
             raise RuntimeError(f"sarpost: level {i} is on {x.device}, expected {'host' if host else 'CUDA'} memory")
+
+    if split:
+        if host:
+            raise ValueError("sarpost: the host entry takes concatenated level tensors")
+        embs = [lv[2] for lv in levels if len(lv) > 2 and lv[2] is not None]
+        h.emb_channels_last = int(bool(h.n_extra_raw) and len(embs) == len(levels) and all(_emb_channels_last(e) for e in embs))
+    for i, lv in enumerate(levels):
+        x = _box_of(lv)
+        check(x, i, 4 * spec.reg_max if split else spec.no, "box branch" if split else "tensor")
         h.h[i] = int(x.shape[2])
         h.w[i] = int(x.shape[3])
         h.stride[i] = float(spec.strides[i])
         h.data[i] = x.data_ptr()
+        if split:
+            hw = tuple(x.shape[2:])
+            check(lv[1], i, spec.nc, "class branch")
+            h.cls[i] = lv[1].data_ptr()
+            if h.n_extra_raw:
+                if len(lv) < 3 or lv[2] is None:
+                    raise ValueError(f"sarpost: level {i} has no embedding branch but the head has embed_dim {spec.embed_dim}")
+                check(lv[2], i, spec.embed_dim, "embedding branch", channels_last_ok=True)
+                if bool(h.emb_channels_last) != _emb_channels_last(lv[2]):
+                    raise ValueError("sarpost: embedding branches must all be channels_last or all NCHW (see _prep_levels)")
+                h.emb[i] = lv[2].data_ptr()
+            if h.n_extra_sigmoid:
+                if len(lv) < 4 or lv[3] is None:
+                    raise ValueError(f"sarpost: level {i} has no state branch but the head has state_classes {spec.state_classes}")
+                check(lv[3], i, spec.state_classes, "state branch")
+                h.state[i] = lv[3].data_ptr()
+            for t in lv[1:]:
+                if t is not None and tuple(t.shape[2:]) != hw:
+                    raise ValueError(f"sarpost: level {i}: branch tensors disagree on H, W")
     return h
 
 
-def _prep_levels(levels: Sequence[torch.Tensor]) -> List[torch.Tensor]:
-    out = []
-    half = all(x.dtype == torch.float16 for x in levels)  # `half=True` pipelines: fp16 logits are read as they are
-    for x in levels:
+def _prep_levels(levels) -> list:
+    """Device / dtype / contiguity normalisation.  fp16 (`half=True` pipelines) is read as it is; anything else but fp32 is
+    upcast.  Split levels: every branch made NCHW-contiguous, except the embedding branch which may stay channels_last
+    (and is kept so only when every level's embedding is)."""
+    split = _is_split(levels)
+    flat = [t for lv in levels for t in (lv if split else (lv,)) if t is not None]
+    half = all(x.dtype == torch.float16 for x in flat)  # `half=True` pipelines: fp16 logits are read as they are
+
+    def norm(x, keep_cl=False):
         _require_cuda(x, "level tensor")
         if not half and x.dtype != torch.float32:
             x = x.float()
-        out.append(x.contiguous())
+        if keep_cl and _emb_channels_last(x):
+            return x
+        return x.contiguous()
+
+    if not split:
+        return [norm(x) for x in levels]
+    embs = [lv[2] for lv in levels if len(lv) > 2 and lv[2] is not None]
+    keep_cl = len(embs) == len(levels) and all(_emb_channels_last(e) for e in embs)
+    out = []
+    for lv in levels:
+        lv = tuple(lv)
+        out.append(tuple(None if t is None else norm(t, keep_cl=(j == 2 and keep_cl)) for j, t in enumerate(lv)))
     return out
+
+
+def split_levels(levels: Sequence[torch.Tensor], spec: HeadSpec, emb_channels_last: bool = True):
+    """Concatenated level tensors `(B, no, H, W)` -> the split layout `[(box, cls, emb, state), ...]` holding the same values
+    (what a head that skips `torch.cat` hands over; used by tests and bench.py to feed both layouts the same numbers)."""
+    out = []
+    c0, c1 = 4 * spec.reg_max, 4 * spec.reg_max + spec.nc
+    for x in levels:
+        emb = state = None
+        if spec.embed_dim:
+            emb = x[:, c1:c1 + spec.embed_dim]
+            emb = emb.contiguous(memory_format=torch.channels_last) if emb_channels_last else emb.contiguous()
+        if spec.state_classes:
+            state = x[:, c1 + spec.embed_dim:c1 + spec.embed_dim + spec.state_classes].contiguous()
+        out.append((x[:, :c0].contiguous(), x[:, c0:c1].contiguous(), emb, state))
+    return out
+
+
+def cat_levels(levels) -> list:
+    """Inverse of `split_levels`: the reference's concatenated layout (head.py:204-206)."""
+    if not _is_split(levels):
+        return list(levels)
+    return [torch.cat([t.contiguous() for t in lv if t is not None], 1) for lv in levels]
 
 
 def _split(out: torch.Tensor, counts: torch.Tensor) -> List[torch.Tensor]:
@@ -346,7 +432,7 @@ def decode(levels: Sequence[torch.Tensor], spec: HeadSpec) -> torch.Tensor:
     """`Detect._inference` / `JDE._inference` (head.py:100-131, :214-249): raw level logits ->
     `y (B, 4 + nc + embed_dim + state_classes, A)` with xywh boxes in pixels, class probabilities, raw
     embedding and sigmoid state."""
-    levels = _prep_levels(levels)
+    levels = _prep_levels(cat_levels(levels))  # y is defined on the concatenated layout (head.py:218)
     head = _make_head(levels, spec)
     dev = levels[0].device
     anchors = sum(int(x.shape[2]) * int(x.shape[3]) for x in levels)
@@ -361,7 +447,9 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
                       return_index=False, return_padded=False, with_extras=True, scale_to=None, peer_out=None,
                       state_mlp: Optional[StateMLP] = None, out=None, nms_stats: Optional[torch.Tensor] = None):
     """decode + non_max_suppression in one pass (never materialises y; the extras channels are read only
-    for the kept rows).  Result as `non_max_suppression`; `return_padded=True` returns the raw
+    for the kept rows).  `levels`: the reference's concatenated `(B, no, H_l, W_l)` tensors, or the split layout —
+    per level a tuple `(box, cls[, emb[, state]])` of the branch outputs before `torch.cat` (head.py:204-206), the
+    embedding optionally channels_last (see `split_levels`, include/sarpost.h SARPOST_LAYOUT_SPLIT).  Result as `non_max_suppression`; `return_padded=True` returns the raw
     `(out (B, max_det, 6+nm), counts (B,) int32[, kept_index])` device tensors without any host sync.
     `with_extras=False` returns 6-column rows even for a JDE head (use `gather_extras` later for the rows that
     survive a subsequent stage such as the cross-tile merge).
@@ -381,8 +469,8 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     levels = _prep_levels(levels)
-    if int(levels[0].shape[0]) == 0 and peer_out is None:  # empty batch: the reference returns an empty list (ops.py:250)
-        dev0, cols = levels[0].device, 6 + (spec.nm if with_extras else 0)
+    if int(_box_of(levels[0]).shape[0]) == 0 and peer_out is None:  # empty batch: the reference returns an empty list (ops.py:250)
+        dev0, cols = _box_of(levels[0]).device, 6 + (spec.nm if with_extras else 0)
         if return_padded:
             e = (torch.zeros((0, int(max_det), cols), device=dev0), torch.zeros((0,), dtype=torch.int32, device=dev0))
             return e + (torch.zeros((0, int(max_det)), dtype=torch.int32, device=dev0),) if return_index else e
@@ -398,8 +486,8 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
         spec = HeadSpec(nc=spec.nc, strides=spec.strides, reg_max=spec.reg_max, embed_dim=spec.embed_dim, state_classes=0)
     head = _make_head(levels, spec, with_extras=with_extras)
     nm = spec.nm if with_extras else 0
-    dev = levels[0].device
-    anchors = sum(int(x.shape[2]) * int(x.shape[3]) for x in levels)
+    dev = _box_of(levels[0]).device
+    anchors = sum(int(_box_of(x).shape[2]) * int(_box_of(x).shape[3]) for x in levels)
     bs = head.batch
     rescale = None
     if scale_to is not None:
@@ -456,7 +544,7 @@ def gather_extras(levels: Sequence[torch.Tensor], spec: HeadSpec, image_index: t
     """Extras (raw embedding + sigmoid state, head.py:247) of explicit `(image, anchor)` pairs -> `(n, nm)`."""
     levels = _prep_levels(levels)
     head = _make_head(levels, spec)
-    dev = levels[0].device
+    dev = _box_of(levels[0]).device
     ii = image_index.to(device=dev, dtype=torch.int32).contiguous()
     ai = anchor_index.to(device=dev, dtype=torch.int32).contiguous()
     if ii.shape != ai.shape or ii.dim() != 1:
@@ -556,6 +644,36 @@ def match_predictions(dets: torch.Tensor, det_counts: torch.Tensor, gt_boxes: to
                                                  len(iouv), correct.data_ptr(), matched.data_ptr() if matched is not None else None,
                                                  int(tag_threshold_index) if tag_threshold_index is not None else -1,
                                                  _stream_ptr(dev)))
+    correct = correct.bool()
+    return (correct, matched) if matched is not None else correct
+
+
+def match_from_iou(pred_classes: torch.Tensor, true_classes: torch.Tensor, iou: torch.Tensor, iouv,
+                   tag_threshold_index: Optional[int] = None):
+    """`BaseValidator.match_predictions(pred_classes, true_classes, iou)` (engine/validator.py:222-262, `use_scipy=False`) on
+    the GPU for one image: `iou (n_gt, n_det)` as the validator computed it, `iouv` the thresholds (tensor or sequence).
+    Returns the `(n_det, len(iouv))` bool tensor on the device; with `tag_threshold_index` also `matched_gt (n_det,)` int32
+    (label index matched at that threshold, else -1 — JDE tags, jde/val.py:731-735)."""
+    _require_cuda(iou, "iou")
+    dev = iou.device
+    thr_list = [float(v) for v in (iouv.detach().cpu().tolist() if isinstance(iouv, torch.Tensor) else iouv)]
+    n_det = int(pred_classes.shape[0])
+    n_gt = int(true_classes.shape[0])
+    correct = torch.zeros((n_det, len(thr_list)), dtype=torch.uint8, device=dev)
+    matched = torch.full((n_det,), -1, dtype=torch.int32, device=dev) if tag_threshold_index is not None else None
+    if n_det and n_gt:
+        iou = iou.to(torch.float32)
+        if iou.dim() != 2 or tuple(iou.shape) != (n_gt, n_det):
+            raise ValueError(f"sarpost: iou has shape {tuple(iou.shape)}, expected ({n_gt}, {n_det})")
+        if iou.stride(1) != 1:
+            iou = iou.contiguous()
+        pc = pred_classes.to(device=dev, dtype=torch.float32).contiguous()
+        tc = true_classes.to(device=dev, dtype=torch.float32).contiguous()
+        thr = (C.c_float * len(thr_list))(*thr_list)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sarpost_match_from_iou(iou.data_ptr(), n_gt, n_det, int(iou.stride(0)), pc.data_ptr(), tc.data_ptr(), thr,
+                                                  len(thr_list), correct.data_ptr(), matched.data_ptr() if matched is not None else None,
+                                                  int(tag_threshold_index) if tag_threshold_index is not None else -1, _stream_ptr(dev)))
     correct = correct.bool()
     return (correct, matched) if matched is not None else correct
 

@@ -93,24 +93,34 @@ def _make_inference(kind: str):
 
 
 def patch(ultralytics_ops=None, ultralytics_head=None, decode: bool = True, fused: bool = False,
-          defer_state: bool = False) -> None:
+          defer_state: bool = False, split: bool = False, emb_channels_last: bool = True, match: bool = False,
+          ultralytics_validator=None) -> None:
     """Monkey-patch the reference.  Modules default to the importable `ultralytics` package.
 
     `fused=False`: API-exact — `_inference` returns the real `y` (decode kernel), `non_max_suppression` runs the
     decoded-input kernels.  `fused=True`: `_inference` returns a `LazyPrediction` handle and `non_max_suppression`
     runs the single-pass fused kernels from the raw logits (the unmodified predictor / validator get the fused
     speed); `y` is materialised only if something else touches it.
-    `defer_state=True` (with `fused=True`): `JDE.forward` in eval mode skips `state_predictor` on the
+    `split=True` (with `fused=True`): `Detect.forward` / `JDE.forward` in eval mode hand the convolution branch outputs
+    to the kernels as they are instead of concatenating them per level (head.py:204-206 writes all `no` channels only for
+    `_inference` to split them again, :232-235) — with `emb_channels_last` the JDE embedding branch (`cv4`) runs in
+    channels_last memory format, so the gather kernel reads one contiguous `embed_dim*4`-byte run per kept row.  The second
+    element of the head's return value then holds per-level `(box, cls[, emb[, state]])` tuples instead of `(B, no, H, W)`
+    tensors, so keep it off while a validator computes a loss from `preds[1]`.
+    `defer_state=True` (implies `split`): `JDE.forward` in eval mode also skips `state_predictor` on the
     `(B, A, embed_dim)` embedding map (head.py:198-204) and the patched NMS evaluates that MLP only on the kept rows
-    (`sarpost_state_head`); the returned level list then has no state channels, so keep it off while a validator
-    computes a loss from `preds[1]`."""
+    (`sarpost_state_head`).
+    `match=True`: `BaseValidator.match_predictions` (engine/validator.py:222-262) runs on the GPU
+    (`sarpost_match_predictions`) for CUDA inputs with `use_scipy=False`."""
     if _SAVED:
         return
-    if defer_state and not fused:
-        raise ValueError("sarpost: defer_state=True needs fused=True")
+    if (defer_state or split) and not fused:
+        raise ValueError("sarpost: split=True / defer_state=True need fused=True")
+    split = split or defer_state
     ops_mod = ultralytics_ops or importlib.import_module("ultralytics.utils.ops")
     _SAVED["ops_mod"] = ops_mod
     _SAVED["nms"] = ops_mod.non_max_suppression
+    _SAVED["opts"] = dict(defer_state=bool(defer_state), emb_channels_last=bool(emb_channels_last))
     ops_mod.non_max_suppression = _nms_dispatch_fused if fused else _nms_dispatch
     if decode or fused:
         make = _make_lazy_inference if fused else _make_inference
@@ -118,12 +128,30 @@ def patch(ultralytics_ops=None, ultralytics_head=None, decode: bool = True, fuse
         _SAVED["head_mod"] = head_mod
         _SAVED["detect"] = head_mod.Detect._inference
         head_mod.Detect._inference = make("detect")
+        if split:
+            _SAVED["detect_forward"] = head_mod.Detect.forward
+            head_mod.Detect.forward = _detect_forward_split
         if hasattr(head_mod, "JDE"):
             _SAVED["jde"] = head_mod.JDE._inference
             head_mod.JDE._inference = make("jde")
-            if defer_state:
+            if split:
                 _SAVED["jde_forward"] = head_mod.JDE.forward
-                head_mod.JDE.forward = _jde_forward_deferred
+                head_mod.JDE.forward = _jde_forward_split
+    if match:
+        val_mod = ultralytics_validator or importlib.import_module("ultralytics.engine.validator")
+        _SAVED["val_mod"] = val_mod
+        _SAVED["match"] = val_mod.BaseValidator.match_predictions
+        val_mod.BaseValidator.match_predictions = _match_predictions_dispatch
+        jde_val = getattr(val_mod, "JDEValidator", None)  # tests hand the class over on the same namespace
+        if jde_val is None and ultralytics_validator is None:
+            try:
+                jde_val = importlib.import_module("ultralytics.models.yolo.jde.val").JDEValidator
+            except Exception:  # noqa: BLE001  (light installs without the model zoo)
+                jde_val = None
+        if jde_val is not None and "match_predictions" in vars(jde_val):
+            _SAVED["jde_val"] = jde_val
+            _SAVED["jde_match"] = jde_val.match_predictions
+            jde_val.match_predictions = _jde_match_predictions_dispatch
 
 
 def unpatch() -> None:
@@ -133,15 +161,58 @@ def unpatch() -> None:
     head_mod = _SAVED.get("head_mod")
     if head_mod is not None:
         head_mod.Detect._inference = _SAVED["detect"]
+        if "detect_forward" in _SAVED:
+            head_mod.Detect.forward = _SAVED["detect_forward"]
         if "jde" in _SAVED:
             head_mod.JDE._inference = _SAVED["jde"]
         if "jde_forward" in _SAVED:
             head_mod.JDE.forward = _SAVED["jde_forward"]
+    if "match" in _SAVED:
+        _SAVED["val_mod"].BaseValidator.match_predictions = _SAVED["match"]
+    if "jde_match" in _SAVED:
+        _SAVED["jde_val"].match_predictions = _SAVED["jde_match"]
     _SAVED.clear()
 
 
 def is_patched() -> bool:
     return bool(_SAVED)
+
+
+def _match_predictions_dispatch(self, pred_classes, true_classes, iou, use_scipy=False):
+    """`BaseValidator.match_predictions(pred_classes, true_classes, iou)` (engine/validator.py:222-262) on the GPU: the
+    reference moves `iou` to the host and loops over the 10 thresholds in numpy (one D2H per image).  `iou (n_gt, n_det)`
+    arrives already computed by `box_iou`; the kernel redoes the class masking, the per-threshold greedy unique matching
+    and returns the `(n_det, n_thr)` bool tensor on `pred_classes.device`.  scipy matching and CPU inputs keep the
+    reference's own method."""
+    if use_scipy or not (isinstance(iou, torch.Tensor) and iou.is_cuda and pred_classes.is_cuda):
+        return _SAVED["match"](self, pred_classes, true_classes, iou, use_scipy)
+    return _ops.match_from_iou(pred_classes, true_classes, iou, _iouv_list(self))
+
+
+def _iouv_list(validator):
+    """`self.iouv` (a device tensor, engine/validator.py / detect/val.py:34) as Python floats, read back once per validator."""
+    cached = getattr(validator, "_sarpost_iouv", None)
+    if cached is None or cached[0] is not validator.iouv:
+        cached = (validator.iouv, [float(v) for v in validator.iouv.detach().cpu().tolist()])
+        validator._sarpost_iouv = cached
+    return cached[1]
+
+
+def _jde_match_predictions_dispatch(self, pred_classes, true_classes, true_tags, iou, use_scipy=False):
+    """`JDEValidator.match_predictions(pred_classes, true_classes, true_tags, iou)` (models/yolo/jde/val.py:683-736): the
+    same matching plus, for the pairs matched at `threshold == self.state_iou`, the label's tag per detection (0 where
+    unmatched — the reference's `[False] * n` turned into an int tensor)."""
+    if use_scipy or not (isinstance(iou, torch.Tensor) and iou.is_cuda and pred_classes.is_cuda):
+        return _SAVED["jde_match"](self, pred_classes, true_classes, true_tags, iou, use_scipy)
+    thr = _iouv_list(self)
+    tag_idx = next((i for i, t in enumerate(thr) if t == getattr(self, "state_iou", None)), None)
+    n = int(pred_classes.shape[0])
+    tags = torch.zeros((n,), dtype=torch.int, device=pred_classes.device)
+    if tag_idx is None or true_tags.dim() == 0 or true_tags.numel() == 0 or n == 0:
+        return _ops.match_from_iou(pred_classes, true_classes, iou, thr), tags
+    correct, matched = _ops.match_from_iou(pred_classes, true_classes, iou, thr, tag_threshold_index=tag_idx)
+    picked = true_tags.to(pred_classes.device)[matched.clamp(min=0).long()].to(torch.int)
+    return correct, torch.where(matched >= 0, picked, tags)
 
 
 def fused_postprocess(preds, head_module, img_shape=None, orig_shapes=None, **nms_kwargs):
@@ -170,10 +241,11 @@ class LazyPrediction(torch.Tensor):
 
     @staticmethod
     def __new__(cls, levels, spec, state_module=None):
-        b = int(levels[0].shape[0])
-        a = sum(int(x.shape[2]) * int(x.shape[3]) for x in levels)
-        r = torch.Tensor._make_wrapper_subclass(cls, (b, 4 + spec.nc + spec.nm, a), dtype=levels[0].dtype,
-                                                device=levels[0].device, requires_grad=False)
+        first = _ops._box_of(levels[0])  # `levels`: concatenated tensors, or split-layout tuples (box, cls[, emb[, state]])
+        b = int(first.shape[0])
+        a = sum(int(_ops._box_of(x).shape[2]) * int(_ops._box_of(x).shape[3]) for x in levels)
+        r = torch.Tensor._make_wrapper_subclass(cls, (b, 4 + spec.nc + spec.nm, a), dtype=first.dtype,
+                                                device=first.device, requires_grad=False)
         r._levels, r._spec, r._y = list(levels), spec, None
         # deferred state head: `levels` carry no state channels; `state_module` is the JDE head that owns state_predictor
         r._state_module = state_module
@@ -184,7 +256,7 @@ class LazyPrediction(torch.Tensor):
 
     def materialize(self) -> torch.Tensor:
         if self._y is None:
-            levels = self._levels
+            levels = _ops.cat_levels(self._levels)  # y is defined on the concatenated layout (head.py:218)
             if self._state_module is not None:  # somebody wants the whole y: run the module's own MLP on every anchor
                 e0 = 4 * self._spec.reg_max + self._spec.nc
                 full = []
@@ -217,22 +289,47 @@ def _make_lazy_inference(kind: str):
     def _inference(self, x):
         if not _plain_head(self, kind) or not _levels_ok(self, x):
             return _SAVED[kind](self, x)
-        return LazyPrediction([xi if xi.dtype in (torch.float32, torch.float16) else xi.float() for xi in x],
-                              _ops.HeadSpec.from_module(self))
+        return LazyPrediction([_as_float(xi) for xi in x], _ops.HeadSpec.from_module(self))
 
     return _inference
 
 
-def _jde_forward_deferred(self, x):
-    """JDE.forward (head.py:193-212) in eval mode without the per-anchor state_predictor (:198-204): the three
-    convolution branches are concatenated as in the stateless branch (:206) and the state MLP is left to the NMS."""
-    if (self.training or self.state_classes is None or not _plain_head(self, "jde")
-            or not all(isinstance(xi, torch.Tensor) and xi.is_cuda for xi in x)):
+def _as_float(t):
+    return t if t.dtype in (torch.float32, torch.float16) else t.float()
+
+
+def _detect_forward_split(self, x):
+    """Detect.forward (head.py:64-74) in eval mode without the per-level `torch.cat` (:70): the cv2 / cv3 outputs go to the
+    kernels as they are (split layout)."""
+    if (self.training or not _plain_head(self, "detect") or not all(isinstance(xi, torch.Tensor) and xi.is_cuda for xi in x)):
+        return _SAVED["detect_forward"](self, x)
+    levels = [(_as_float(self.cv2[i](x[i])), _as_float(self.cv3[i](x[i]))) for i in range(self.nl)]
+    return LazyPrediction(levels, _ops.HeadSpec.from_module(self)), levels
+
+
+def _jde_forward_split(self, x):
+    """JDE.forward (head.py:193-212) in eval mode without the per-level `torch.cat` (:204-206): box, class, embedding
+    [and state] branch outputs are handed over separately.  With `emb_channels_last` the cv4 branch runs in
+    channels_last memory format (its input feature map is converted once), so the embedding lands as (B, H, W, E).
+    With `defer_state` the per-anchor state_predictor (:198-204) is skipped and left to the NMS (kept rows only)."""
+    opts = _SAVED.get("opts", {})
+    if (self.training or not _plain_head(self, "jde") or not all(isinstance(xi, torch.Tensor) and xi.is_cuda for xi in x)):
         return _SAVED["jde_forward"](self, x)
+    defer = opts.get("defer_state", False) and self.state_classes is not None
+    levels = []
     for i in range(self.nl):
-        x[i] = torch.cat((self.cv2[i](x[i]), self.cv3[i](x[i]), self.cv4[i](x[i])), 1)
-    levels = [xi if xi.dtype in (torch.float32, torch.float16) else xi.float() for xi in x]
-    return LazyPrediction(levels, _ops.HeadSpec.from_module(self), state_module=self), x
+        box, cls = self.cv2[i](x[i]), self.cv3[i](x[i])
+        xin = x[i].contiguous(memory_format=torch.channels_last) if opts.get("emb_channels_last", True) else x[i]
+        emb = self.cv4[i](xin)
+        state = None
+        if self.state_classes is not None and not defer:
+            b, c, h, w = emb.shape
+            flat = emb.permute(0, 2, 3, 1).reshape(b, h * w, c)  # (B, H*W, E): a view when emb is channels_last
+            state = self.state_predictor(flat).permute(0, 2, 1).reshape(b, self.state_classes, h, w)
+        levels.append(tuple(None if t is None else _as_float(t) for t in (box, cls, emb, state)))
+    if defer:
+        levels = [lv[:3] for lv in levels]
+    return LazyPrediction(levels, _ops.HeadSpec.from_module(self), state_module=self if defer else None), levels
 
 
 def _nms_dispatch_fused(prediction, *args, **kwargs):

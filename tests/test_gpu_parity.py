@@ -815,3 +815,109 @@ def test_extreme_geometry(sarpost, cuda, name):
     rows2 = sarpost.non_max_suppression(y, nc=spec.nc, **kw)
     for a, b in zip(rows2, ref_rows):
         assert torch.equal(a.cpu(), b)
+
+
+@pytest.mark.parametrize("imgsz,strides,nc,ed,sc,bs", HEADS)
+@pytest.mark.parametrize("emb_cl", [False, True])
+def test_split_layout_equals_concatenated_layout(sarpost, cuda, imgsz, strides, nc, ed, sc, bs, emb_cl):
+    """SARPOST_LAYOUT_SPLIT: the branch outputs handed over separately (no torch.cat, head.py:204-206), embedding NCHW or
+    channels_last — rows, kept indices and extras must be bit-identical to the concatenated layout (TMA and LDG paths)."""
+    shapes = sarpost.synth.level_shapes(imgsz, strides)
+    cat = [x.to(cuda) for x in sarpost.synth.head_outputs(bs, shapes, nc, ed, sc, seed=13, blobs=3)]
+    spec = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=sc)
+    split = sarpost.split_levels(cat, spec, emb_channels_last=emb_cl)
+    back = sarpost.cat_levels(split)
+    assert all(torch.equal(a, b) for a, b in zip(back, cat))
+    for kw in (dict(conf_thres=0.25, iou_thres=0.7), dict(conf_thres=0.001, iou_thres=0.7, multi_label=True, max_det=50)):
+        a, ia = sarpost.postprocess_fused(cat, spec, return_index=True, **kw)
+        b, ib = sarpost.postprocess_fused(split, spec, return_index=True, **kw)
+        for x, y, i, j in zip(a, b, ia, ib):
+            assert torch.equal(x, y) and torch.equal(i, j)
+    if ed or sc:  # explicit extras gather from the split tensors
+        rows, idx = sarpost.postprocess_fused(cat, spec, return_index=True, conf_thres=0.25, iou_thres=0.7, max_det=40)
+        img = torch.cat([torch.full((i.shape[0],), b_, dtype=torch.int32, device=cuda) for b_, i in enumerate(idx)])
+        ex = sarpost.gather_extras(split, spec, img, torch.cat(idx) // nc)
+        assert torch.equal(ex, torch.cat([r[:, 6:] for r in rows]))
+        lean = sarpost.postprocess_fused(split, spec, with_extras=False, conf_thres=0.25, iou_thres=0.7, max_det=40)
+        assert all(torch.equal(l_, r[:, :6]) for l_, r in zip(lean, rows))
+    # fp16 branches
+    split16 = [tuple(None if t is None else t.half() for t in lv) for lv in split]
+    cat16 = [x.half() for x in cat]
+    a = sarpost.postprocess_fused(cat16, spec, conf_thres=0.25, iou_thres=0.7)
+    b = sarpost.postprocess_fused(split16, spec, conf_thres=0.25, iou_thres=0.7)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_split_layout_deferred_state_and_errors(sarpost, cuda):
+    strides = (8, 16, 32)
+    shapes = sarpost.synth.level_shapes(160, strides)
+    spec = sarpost.HeadSpec(nc=1, strides=strides, embed_dim=16, state_classes=6)
+    cat = [x.to(cuda) for x in sarpost.synth.head_outputs(2, shapes, 1, 16, 6, seed=5)]
+    g = torch.Generator().manual_seed(3)
+    mlp = sarpost.StateMLP.from_tensors(torch.randn(8, 16, generator=g), torch.randn(8, generator=g), torch.randn(6, 8, generator=g),
+                                        torch.randn(6, generator=g), device=cuda)
+    no_state_cat = [x[:, :64 + 1 + 16].contiguous() for x in cat]
+    no_state_split = [lv[:3] for lv in sarpost.split_levels(cat, spec)]
+    kw = dict(conf_thres=0.25, iou_thres=0.7)
+    a = sarpost.postprocess_fused(no_state_cat, spec, state_mlp=mlp, **kw)
+    b = sarpost.postprocess_fused(no_state_split, spec, state_mlp=mlp, **kw)
+    assert all(x.shape[1] == 6 + 16 + 6 and torch.equal(x, y) for x, y in zip(a, b))
+    with pytest.raises(ValueError, match="no state branch"):
+        sarpost.postprocess_fused(no_state_split, spec, **kw)
+    with pytest.raises(ValueError):
+        sarpost.postprocess_fused([lv[:1] + (lv[1][:, :, :-1],) + lv[2:] for lv in sarpost.split_levels(cat, spec)], spec, **kw)
+    # y is defined on the concatenated layout: decode() accepts split levels by concatenating them first
+    assert torch.equal(sarpost.decode(sarpost.split_levels(cat, spec), spec), sarpost.decode(cat, spec))
+
+
+def test_match_from_iou_equals_reference_method(sarpost, cuda):
+    """`patch(match=True)` boundary: BaseValidator.match_predictions(pred_classes, true_classes, iou) from a precomputed IoU
+    matrix (engine/validator.py:222-262) and the JDE variant's tags (jde/val.py:683-736) vs the numpy oracle."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_oracle import _match_case
+    iouv = torch.linspace(0.5, 0.95, 10)
+    for seed, (nd, ng, nc) in enumerate([(300, 40, 3), (17, 200, 1), (1, 1, 2), (120, 0, 2), (0, 5, 2), (299, 299, 6)]):
+        dets, gtb, gtc = _match_case(100 + seed, n_det=nd, n_gt=ng, nc=nc)
+        iou = R.box_iou_ref(gtb, dets[:, :4]) if nd and ng else torch.zeros(ng, nd)
+        got, matched = sarpost.match_from_iou(dets[:, 5].to(cuda), gtc.to(cuda), iou.to(cuda), iouv.to(cuda), tag_threshold_index=0)
+        if nd and ng:
+            ref, ref_m = R.match_predictions_ref(dets[:, 5], gtc, iou, iouv, tag_thr=iouv[0].item())
+        else:
+            ref, ref_m = torch.zeros(nd, 10, dtype=torch.bool), torch.full((nd,), -1, dtype=torch.int32)
+        assert got.dtype == torch.bool and torch.equal(got.cpu(), ref)
+        assert torch.equal(matched.cpu().long(), ref_m.long())
+    # through the patched methods on stand-in validator classes (the real ones are exercised by tools/dropin_predict_check.py)
+    import types
+
+    class BaseValidator:
+        def match_predictions(self, pred_classes, true_classes, iou, use_scipy=False):
+            return "ref"
+
+    class JDEValidator(BaseValidator):
+        def match_predictions(self, pred_classes, true_classes, true_tags, iou, use_scipy=False):
+            return "ref-jde"
+
+    vm = types.SimpleNamespace(BaseValidator=BaseValidator, JDEValidator=JDEValidator)
+    sarpost.patch(types.SimpleNamespace(non_max_suppression=lambda *a, **k: None), types.SimpleNamespace(Detect=type("Detect", (), {"_inference": None})),
+                  match=True, ultralytics_validator=vm)
+    try:
+        dets, gtb, gtc = _match_case(7, n_det=150, n_gt=30, nc=2)
+        iou = R.box_iou_ref(gtb, dets[:, :4])
+        v = BaseValidator()
+        v.iouv = iouv.to(cuda)
+        assert v.match_predictions(dets[:, 5], gtc, iou) == "ref"                                  # CPU tensors: the reference's own method
+        assert v.match_predictions(dets[:, 5].to(cuda), gtc.to(cuda), iou.to(cuda), use_scipy=True) == "ref"
+        got = v.match_predictions(dets[:, 5].to(cuda), gtc.to(cuda), iou.to(cuda))
+        ref, ref_m = R.match_predictions_ref(dets[:, 5], gtc, iou, iouv, tag_thr=iouv[0].item())
+        assert torch.equal(got.cpu(), ref)
+        j = JDEValidator()
+        j.iouv, j.state_iou = iouv.to(cuda), 0.5
+        tags = torch.arange(30).float() + 100
+        c, t = j.match_predictions(dets[:, 5].to(cuda), gtc.to(cuda), tags.to(cuda), iou.to(cuda))
+        assert torch.equal(c.cpu(), ref) and t.dtype == torch.int32
+        want = torch.where(ref_m >= 0, tags[ref_m.clamp(min=0).long()].int(), torch.zeros_like(ref_m, dtype=torch.int))
+        assert torch.equal(t.cpu(), want)
+    finally:
+        sarpost.unpatch()
+    assert BaseValidator().match_predictions(None, None, None) == "ref" and JDEValidator().match_predictions(None, None, None, None) == "ref-jde"

@@ -8,9 +8,12 @@ container).  What it does:
   * a forward pre-hook feeds the JDE head seeded N(0,1) feature maps (the untrained trunk kills the signal)
     and the class bias is shifted so scores spread over (0.05, 0.9); a forward hook captures the raw per-level logits the
     head returns next to `y`;
-  * runs `model.predict([ndarray, ...])` four times: reference as is (torch CUDA ops + torchvision CUDA NMS), then under
-    `patch()` (API-exact decode + NMS kernels), `patch(fused=True)` (LazyPrediction -> fused kernels) and
+  * runs `model.predict([ndarray, ...])` six times: reference as is (torch CUDA ops + torchvision CUDA NMS), then under
+    `patch()` (API-exact decode + NMS kernels), `patch(fused=True)` (LazyPrediction -> fused kernels),
+    `patch(fused=True, split=True)` with a channels_last and with an NCHW embedding branch (no torch.cat in the head) and
     `patch(fused=True, defer_state=True)` (state MLP on the kept rows only);
+  * runs `BaseValidator.match_predictions` / `JDEValidator.match_predictions` of the reference with and without
+    `patch(match=True)` on the same CUDA inputs;
   * checks every patched run against the CPU oracle evaluated on the logits captured IN THAT RUN (decode_ref + NMS +
     scale_boxes + state argmax + 7-column re-pack = models/yolo/jde/predict.py:29-78): rows matched in order, decode
     tolerance, mismatch budget 1e-4 of the detections; the deferred-state run is checked against the fused run;
@@ -73,7 +76,8 @@ def main():
 
     def grab(mod, inp, out):
         if isinstance(out, tuple) and isinstance(out[1], list):
-            captured["levels"] = [x.detach().float().cpu().clone() for x in out[1]]
+            captured["split"] = bool(out[1]) and isinstance(out[1][0], tuple)
+            captured["levels"] = [x.detach().float().cpu().clone() for x in sarpost.cat_levels(out[1])]
 
     head.register_forward_pre_hook(feed)
     head.register_forward_hook(grab)
@@ -129,14 +133,18 @@ def main():
     report["runs"]["reference_unpatched"] = {"detections": [int(x[0].shape[0]) for x in ref_res], "vs_cpu_oracle": {"mismatch": b, "of": t},
                                              "box_columns": int(ref_res[0][0].shape[1])}
     fused_res = None
-    for name, mode in (("patch", {}), ("patch_fused", dict(fused=True)), ("patch_fused_defer_state", dict(fused=True, defer_state=True))):
+    for name, mode in (("patch", {}), ("patch_fused", dict(fused=True)), ("patch_fused_split", dict(fused=True, split=True)),
+                       ("patch_fused_split_nchw_emb", dict(fused=True, split=True, emb_channels_last=False)),
+                       ("patch_fused_defer_state", dict(fused=True, defer_state=True))):
         sarpost.patch(**mode)
         try:
             res, levels = run()
+            was_split = captured.pop("split", False)
         finally:
             sarpost.unpatch()
         exp = expected(levels)
-        entry = {"detections": [int(x[0].shape[0]) for x in res], "box_columns": int(res[0][0].shape[1]) if res else None}
+        entry = {"detections": [int(x[0].shape[0]) for x in res], "box_columns": int(res[0][0].shape[1]) if res else None,
+                 "head_returned_split_levels": bool(was_split)}
         if exp is not None:
             b, t = diff(res, exp)
             entry["vs_cpu_oracle"] = {"mismatch": b, "of": t}
@@ -145,7 +153,8 @@ def main():
             b = tot = 0
             for (ba, ea), (bb, eb) in zip(res, fused_res):
                 tot += max(ba.shape[0], bb.shape[0])
-                same = ba.shape == bb.shape and torch.equal(ba[:, [0, 1, 2, 3, 5, 6]], bb[:, [0, 1, 2, 3, 5, 6]]) and torch.equal(ea, eb)
+                same = (ba.shape == bb.shape and torch.equal(ba[:, [0, 1, 2, 3, 5, 6]], bb[:, [0, 1, 2, 3, 5, 6]])
+                        and torch.allclose(ea, eb, rtol=1e-4, atol=1e-5))
                 b += 0 if same else max(ba.shape[0], bb.shape[0])
                 if same:
                     b += int((ba[:, 4] != bb[:, 4]).sum())
@@ -156,9 +165,45 @@ def main():
         entry["vs_reference_gpu_run"] = {"mismatch": b2, "of": t2}
         entry["ok"] = bool(good)
         ok = ok and good
-        if name == "patch_fused":
+        if name == "patch_fused_split":  # same forward (channels_last cv4 branch) as the deferred-state run, state head on every anchor
             fused_res = res
         report["runs"][name] = entry
+    # ---- validator side: BaseValidator.match_predictions / JDEValidator.match_predictions under patch(match=True) ----
+    try:
+        from ultralytics.engine.validator import BaseValidator
+        from ultralytics.models.yolo.jde.val import JDEValidator
+        from ultralytics.utils.metrics import box_iou
+
+        g = torch.Generator().manual_seed(5)
+        n_gt, n_det = 37, 300
+        gxy = torch.rand(n_gt, 2, generator=g) * 500
+        gt = torch.cat((gxy, gxy + 20 + torch.rand(n_gt, 2, generator=g) * 100), 1)
+        src = torch.randint(0, n_gt, (n_det,), generator=g)
+        det = gt[src] + torch.randn(n_det, 4, generator=g) * 8
+        gcls = torch.randint(0, 3, (n_gt,), generator=g).float()
+        dcls = torch.where(torch.rand(n_det, generator=g) < 0.8, gcls[src], torch.randint(0, 3, (n_det,), generator=g).float())
+        tags = torch.randint(1, 90, (n_gt,), generator=g).float()
+        d = torch.device(dev)
+        bv, jv = BaseValidator.__new__(BaseValidator), JDEValidator.__new__(JDEValidator)
+        bv.iouv = jv.iouv = torch.linspace(0.5, 0.95, 10).to(d)
+        jv.state_iou = 0.5
+        iou = box_iou(gt.to(d), det.to(d))
+        want = bv.match_predictions(dcls.to(d), gcls.to(d), iou)
+        want_j = jv.match_predictions(dcls.to(d), gcls.to(d), tags.to(d), iou)
+        sarpost.patch(match=True)
+        try:
+            got = bv.match_predictions(dcls.to(d), gcls.to(d), iou)
+            got_j = jv.match_predictions(dcls.to(d), gcls.to(d), tags.to(d), iou)
+            patched = BaseValidator.match_predictions is not sarpost.plugin._SAVED["match"] and "jde_match" in sarpost.plugin._SAVED
+        finally:
+            sarpost.unpatch()
+        vm_ok = (patched and torch.equal(got, want) and torch.equal(got_j[0], want_j[0]) and torch.equal(got_j[1].long(), want_j[1].long())
+                 and got.device == want.device)
+        report["validator_match"] = {"ok": bool(vm_ok), "true_positives_at_0.5": int(want[:, 0].sum()), "tags_assigned": int((want_j[1] != 0).sum())}
+        ok = ok and (vm_ok or dev == "cpu")
+    except Exception as e:  # noqa: BLE001
+        report["validator_match"] = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+        ok = False
     report["ok"] = bool(ok)
     print(json.dumps(report))
     return 0 if ok else 1
