@@ -116,6 +116,20 @@ typedef struct sarpost_nms_params {
     int64_t *stats;         /* instrumentation, DEVICE (B, 4) int64 or NULL: per image, what the NMS kernel did — sorted
                               candidates consumed before max_det keeps were found (or the candidates ran out), IoU pair
                               tests executed, NMS sub-chunks, selection passes.  bench.py's `clustered` leg reports them. */
+    /* Results layout (models/yolo/jde/predict.py:52-66, engine/results.py:1011-1014): when
+     * res_boxes != NULL the gather kernel writes, instead of the (6 + nm)-column rows of `out` (which may then be NULL),
+     * what JDEPredictor.postprocess builds per image with split / argmax / cat:
+     *   res_boxes   DEVICE (B, max_det, 7)  x1,y1,x2,y2, state_id, conf, cls — state_id = argmax over the
+     *               n_extra_sigmoid state probabilities (first maximum, like torch.argmax) as a float; -1 when the
+     *               head has no state channels or they are deferred (sarpost_state_ids fills the column then)
+     *   res_embeds  DEVICE (B, max_det, n_extra_raw) the raw embedding of every kept row, contiguous (NULL allowed
+     *               when n_extra_raw == 0)
+     * Rows beyond counts[b] are left untouched.  Device entry points sarpost_fused / sarpost_nms_decoded only (for
+     * a decoded prediction the first nm - res_state_cols extras columns are the embedding); not combinable with the
+     * peer_out exchange or out_tail_cols. */
+    float *res_boxes;
+    float *res_embeds;
+    int32_t res_state_cols; /* sarpost_nms_decoded only: how many of the trailing extras columns are state probabilities */
 } sarpost_nms_params_t;
 
 /* Last error message of the calling thread ("" if none). */
@@ -241,6 +255,20 @@ int32_t sarpost_match_from_iou(const float *iou, int32_t n_gt, int32_t n_det, in
 int32_t sarpost_state_head(float *rows, const int32_t *counts, int32_t batch, int32_t max_det, int32_t row_len,
                            int32_t emb_col, int32_t embed_dim, int32_t state_col, int32_t n_state, int32_t hidden,
                            const float *w1, const float *b1, const float *w2, const float *b2, void *stream);
+
+/*
+ * Deferred state head for the results layout (params.res_boxes / res_embeds of a sarpost_fused call on levels WITHOUT
+ * state channels): evaluates the same MLP on embeds (B, max_det, embed_dim) and writes only what
+ * JDEPredictor.postprocess keeps of it (models/yolo/jde/predict.py:61-64): boxes7[b][r][4] = argmax_s sigmoid(...)
+ * (first maximum) as a float, for r < counts[b].  boxes7 device (B, max_det, 7).
+ */
+int32_t sarpost_state_ids(const float *embeds, const int32_t *counts, float *boxes7, int32_t batch, int32_t max_det,
+                          int32_t embed_dim, int32_t n_state, int32_t hidden, const float *w1, const float *b1,
+                          const float *w2, const float *b2, void *stream);
+
+/* sizeof(sarpost_head_t) / sizeof(sarpost_nms_params_t) as this library was compiled: lets a binding written in
+ * another language (ctypes, cgo, JNI ...) verify its struct mirrors before the first call. */
+int32_t sarpost_abi_sizes(int32_t *head_bytes, int32_t *params_bytes);
 
 /*
  * End-to-end entry with HOST buffers (what a caller holding CPU tensors uses; timed as `e2e` by

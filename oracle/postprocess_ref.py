@@ -216,6 +216,22 @@ def scale_boxes_ref(img1_shape, boxes: torch.Tensor, img0_shape) -> torch.Tensor
     return boxes
 
 
+def jde_results_ref(rows: torch.Tensor, img1_shape, img0_shape, embed_dim: int, state_classes: int):
+    """The per-image tail of JDEPredictor.postprocess (models/yolo/jde/predict.py:48-77) on one image's NMS rows
+    `(n, 6 + embed_dim + state_classes)`: boxes scaled to the original image (:49), then — with a state head and at
+    least one row — `boxes (n, 7)` = x1,y1,x2,y2,state_id,conf,cls with state_id = argmax over the state columns
+    (:61-64); otherwise the plain 6 columns (:66-69, :73-75).  Returns `(boxes, embeds)` as `Results` receives them."""
+    pred = rows.clone()
+    pred[:, :4] = scale_boxes_ref(img1_shape, pred[:, :4], img0_shape)
+    if not state_classes:
+        return pred[:, :6], pred[:, 6:]
+    box6, emb, states = pred[:, :6], pred[:, 6:6 + embed_dim], pred[:, 6 + embed_dim:6 + embed_dim + state_classes]
+    if len(states) == 0:
+        return box6, emb
+    ids = states.argmax(dim=1).unsqueeze(1)
+    return torch.cat([box6[:, :4], ids, box6[:, 4:]], dim=1), emb
+
+
 def box_iou_ref(box1: torch.Tensor, box2: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
     """utils/metrics.py:55-75."""
     (a1, a2), (b1, b2) = box1.float().unsqueeze(1).chunk(2, 2), box2.float().unsqueeze(0).chunk(2, 2)

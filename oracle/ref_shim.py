@@ -145,3 +145,30 @@ def ref_nms(prediction, **kw):
     ops, _, _ = load()
     kw.setdefault("max_time_img", 1e9)  # never hit the soft time limit (ops.py:312-314)
     return ops.non_max_suppression(prediction.clone(), **kw)
+
+
+def ref_jde_predictor_postprocess(y, head_module, img_shape, orig_shapes, conf, iou, max_det=300, classes=None, agnostic=False,
+                                  names=None):
+    """Run the reference's own, unmodified `JDEPredictor.postprocess` (models/yolo/jde/predict.py:29-78) on a decoded
+    prediction `y`: NMS, `scale_boxes`, state argmax, 7-column re-pack, `Results`.  The method only reads
+    `self.args`, `self.model.names / person_states / model.model[-1]` and `self.batch[0]`, so a namespace stands in for
+    the predictor object.  `orig_shapes`: (h, w) per image (zero images of that size are handed over as `orig_imgs`).
+    Returns per image `(boxes.data, embeds.data)`."""
+    import types as _t
+
+    import numpy as np
+
+    load()
+    import ultralytics.models.yolo.jde.predict as P
+
+    names = names or {i: str(i) for i in range(int(head_module.nc))}
+    fake = _t.SimpleNamespace(
+        args=_t.SimpleNamespace(conf=conf, iou=iou, agnostic_nms=agnostic, max_det=max_det, classes=classes),
+        model=_t.SimpleNamespace(names=names, person_states={0: "s"}, model=_t.SimpleNamespace(model=[head_module])),
+        batch=[[f"img{i}.jpg" for i in range(len(orig_shapes))]])
+    import torch
+
+    img = torch.zeros((len(orig_shapes), 3, int(img_shape[0]), int(img_shape[1])))
+    orig = [np.zeros((int(h), int(w), 3), dtype=np.uint8) for h, w in orig_shapes]
+    res = P.JDEPredictor.postprocess(fake, [y.clone()], img, orig)
+    return [(r.boxes.data, r.embeds.data) for r in res]

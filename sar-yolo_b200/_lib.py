@@ -39,6 +39,7 @@ class NmsParams(C.Structure):
         ("peer_out", C.c_void_p * 8), ("peer_counts", C.c_void_p * 8), ("n_peers", C.c_int32),
         ("peer_slot_offset", C.c_int32), ("prediction_dtype", C.c_int32), ("workspace_clean", C.c_int32), ("out_tail_cols", C.c_int32),
         ("stats", C.c_void_p),
+        ("res_boxes", C.c_void_p), ("res_embeds", C.c_void_p), ("res_state_cols", C.c_int32),
     ]
 
 
@@ -71,6 +72,8 @@ SYMBOLS = {
     "sarpost_match_from_iou": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_float),
                                            C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "sarpost_state_head": (C.c_int32, [C.c_void_p, C.c_void_p] + [C.c_int32] * 8 + [C.c_void_p] * 5),
+    "sarpost_state_ids": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_void_p] * 5),
+    "sarpost_abi_sizes": (C.c_int32, [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "sarpost_host_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
     "sarpost_host_ctx_destroy": (None, [C.c_void_p]),
     "sarpost_fused_host": (C.c_int32, [C.c_void_p, C.POINTER(Head), C.POINTER(NmsParams), C.c_void_p, C.c_void_p,
@@ -96,6 +99,18 @@ def _load() -> C.CDLL:
 
 
 lib = _load()
+
+
+def _check_abi() -> None:
+    """The ctypes mirrors above must be the structs the library was compiled with (a stale .so would read garbage)."""
+    hb, pb = C.c_int32(), C.c_int32()
+    lib.sarpost_abi_sizes(C.byref(hb), C.byref(pb))
+    if (hb.value, pb.value) != (C.sizeof(Head), C.sizeof(NmsParams)):
+        raise ImportError(f"{LIB_PATH} was built from a different include/sarpost.h: sarpost_head_t {hb.value} B vs binding "
+                          f"{C.sizeof(Head)} B, sarpost_nms_params_t {pb.value} B vs binding {C.sizeof(NmsParams)} B — rebuild it")
+
+
+_check_abi()
 
 
 def last_error() -> str:

@@ -199,6 +199,7 @@ static int32_t fused_host_impl(sarpost_host_ctx_t *c, const sarpost_head_t *head
 
     sarpost_nms_params_t prm = *params;
     prm.out_tail_cols = 0;  // the host entry packs its own rows (6 + nm wide)
+    prm.res_boxes = prm.res_embeds = nullptr;  // results layout: device entry points only
     prm.workspace_clean = 0;  // chunks of different sizes share the context's workspace: let each call zero its histogram
     // ---- enqueue copy + compute of every chunk ----
     for (int k = 0; k < n_chunks; ++k) {

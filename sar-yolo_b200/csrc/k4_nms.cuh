@@ -34,6 +34,7 @@
 namespace sarpost {
 
 #ifdef SARPOST_PHASE_PROF
+__device__ unsigned long long g_phase_n[16], g_phase_max[16];  // visits / longest single visit per phase
 __device__ unsigned long long g_phase[16];  // cycles of block 0 per phase: 0 prologue, 1 collect, 2 share phase 1, 3 deliver + barrier 1,
 // 4 sort, 9 master tail + replicate + barrier 2, 8 publish; inside process_sorted: 10 load, 11 incremental phase 1, 12 compaction, 13 bitmask, 14 sweep
 #define PROF_MARK(i)                                                         \
@@ -41,6 +42,8 @@ __device__ unsigned long long g_phase[16];  // cycles of block 0 per phase: 0 pr
         if (blockIdx.x == 0 && threadIdx.x == 0) {                           \
             const long long _t = clock64();                                  \
             g_phase[i] += static_cast<unsigned long long>(_t - prof_t);      \
+            g_phase_n[i] += 1ull;                                            \
+            if (static_cast<unsigned long long>(_t - prof_t) > g_phase_max[i]) g_phase_max[i] = static_cast<unsigned long long>(_t - prof_t); \
             prof_t = _t;                                                     \
         }                                                                    \
     } while (0)
@@ -288,7 +291,7 @@ struct NmsSmemLayout {
     static constexpr int skey = surv + kShareCap * 8;                // u64[kSortCap]   master: every CTA's survivors, sorted
     static constexpr int radix_end = skey + kSortCap * 8;            // (the radix fallback aliases plist|surv|skey)
     static constexpr int bstart = radix_end;                         // i32[kBuckets + 4]
-    static constexpr int mask = bstart + (kBuckets + 4) * 4;         // u32[kSub * kSubWords]
+    static constexpr int mask = bstart + (kBuckets + 4) * 4;         // u32[kSubWords][kSub]  word-major bitmask
     static constexpr int a_box = mask + kSub * kSubWords * 4;        // float4[kSub]  (a_box|c_box double as the tile list)
     static constexpr int c_box = a_box + kSub * 16;                  // float4[kSub]
     static constexpr int a_area = c_box + kSub * 16;                 // f32[kSub]
@@ -401,6 +404,34 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             for (int k = k_lo + part; k < k_hi; k += nparts) dead |= iou_gt(KEPT_BOX[k], KEPT_AREA[k], ob, oa, p.thr);
         return dead;
     };
+    // The same verdict for the master's incremental phase 1, where boxes kept a moment ago rarely overlap the next
+    // candidates: four kept boxes per step, and the IoU arithmetic runs only when some lane of the warp sees its
+    // candidate intersect one of them.  Called by every thread of the block (`valid` = the thread owns a candidate);
+    // `part` / `nparts` must be warp-uniform.  Disjoint boxes have inter = 0 -> IoU 0 or NaN, never > thr >= 0.
+    auto killed_by_kept_sparse = [&](bool valid, const float4 ob, const float oa, int k_lo, int k_hi, int part, int nparts) {
+        bool dead = false;
+        for (int k = k_lo + part; k < k_hi; k += 4 * nparts) {
+            float4 kb[4];
+            bool ov[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ku = k + u * nparts;
+                kb[u] = KEPT_BOX[ku < k_hi ? ku : k];
+                ov[u] = valid && ku < k_hi && kb[u].z > ob.x && ob.z > kb[u].x && kb[u].w > ob.y && ob.w > kb[u].y;
+            }
+            if (!__any_sync(0xffffffffu, ov[0] || ov[1] || ov[2] || ov[3])) continue;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!ov[u]) continue;
+                const float ka = KEPT_AREA[k + u * nparts];
+                bool bd;
+                bool gt = iou_gt_approx(kb[u], ka, ob, oa, p.thr, band, bd);
+                if (bd) gt = iou_gt(kb[u], ka, ob, oa, p.thr);  // rare: a quotient within a few ulp of the threshold
+                dead |= gt;
+            }
+        }
+        return dead;
+    };
 
     // ---- descending exclusive scan of the sampled score histogram: S_BSTART[d] ~ estimated rank of the first
     //      candidate of bucket 4095-d in the sorted order (x kHistSample).  Estimates only steer how many
@@ -477,7 +508,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 int sub_p2 = 64;
                 while (sub_p2 < sub) sub_p2 <<= 1;
                 const int cand = tid & (sub_p2 - 1), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
-                if (cand < sub && killed_by_kept(A_BOX[cand], S_A_AREA[cand], k_from, kept, part, nparts)) S_DEAD[cand] = 1;
+                const int cc = cand < sub ? cand : 0;
+                if (killed_by_kept_sparse(cand < sub, A_BOX[cc], S_A_AREA[cc], k_from, kept, part, nparts)) S_DEAD[cand] = 1;
                 st_pairs += static_cast<long long>(sub) * (kept - k_from);
                 __syncthreads();
             }
@@ -505,41 +537,55 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             }
             __syncthreads();
             PROF_MARK(12);
-            // ---- phase 2: suppression bitmask among the m survivors (row r, bits j > r) ----
-            // warp per row r, lane j tests the pair (r, 32w + j) for every word w >= r/32; a ballot packs the word
+            // ---- phase 2: suppression bitmask among the m survivors (row r, bits j > r), stored word-major:
+            //      S_MASK[w * kSub + r] = word w (columns 32w .. 32w+31) of row r ----
+            // Work items = (word w, row r < min(m, 32(w+1))), flattened word-major and cut into equal slices, one per warp.
+            // A warp keeps the 32 column boxes of its current word in registers (lane = column) and streams rows past
+            // them, four at a time: one broadcast shared load and four compares per (row, word); the IoU arithmetic runs
+            // only for rows that intersect some column of the word (disjoint boxes: inter = 0 -> IoU 0 or NaN, never > thr).
             const int words = (m + 31) >> 5;
-            for (int r = warp; r < m; r += kNmsWarps) {
-                const float4 rb = C_BOX[r];
-                const float ra = S_C_AREA[r];
-                for (int w = r >> 5; w < words; w += 2) {
-                    const int j0 = (w << 5) + lane, j1 = j0 + 32;
-                    const bool v0 = j0 > r && j0 < m, v1 = (w + 1 < words) && j1 < m;
-                    bool bd0 = false, bd1 = false;
-                    const int jc0 = v0 ? j0 : r, jc1 = v1 ? j1 : r;
-                    const float4 cb0 = C_BOX[jc0], cb1 = C_BOX[jc1];
-                    // disjoint boxes have inter = 0 -> IoU 0 (or NaN), never > thr >= 0: skip the arithmetic when no
-                    // lane of the warp sees an overlap (the usual case for boxes spread over the image)
-                    const bool ov0 = v0 && fminf(rb.z, cb0.z) > fmaxf(rb.x, cb0.x) && fminf(rb.w, cb0.w) > fmaxf(rb.y, cb0.y);
-                    const bool ov1 = v1 && fminf(rb.z, cb1.z) > fmaxf(rb.x, cb1.x) && fminf(rb.w, cb1.w) > fmaxf(rb.y, cb1.y);
-                    if (!__any_sync(0xffffffffu, ov0 || ov1)) {
-                        if (lane == 0) {
-                            S_MASK[r * kSubWords + w] = 0u;
-                            if (w + 1 < words) S_MASK[r * kSubWords + w + 1] = 0u;
+            {
+                const int n_items = 16 * words * (words - 1) + m;  // full words contribute 32(w+1) rows each, the last one m
+                const int it_lo = static_cast<int>(static_cast<long long>(n_items) * warp / kNmsWarps);
+                const int it_hi = static_cast<int>(static_cast<long long>(n_items) * (warp + 1) / kNmsWarps);
+                int it = it_lo, w = 0;
+                while (w + 1 < words && 16 * (w + 1) * (w + 2) <= it) ++w;
+                while (it < it_hi) {
+                    const int r_begin = it - 16 * w * (w + 1);
+                    const int r_end = min(w == words - 1 ? m : 32 * (w + 1), r_begin + (it_hi - it));
+                    const int j = (w << 5) + lane;
+                    const bool jv = j < m;
+                    const float4 cb = C_BOX[jv ? j : 0];
+                    const float ca = S_C_AREA[jv ? j : 0];
+                    for (int r0 = r_begin; r0 < r_end; r0 += 4) {
+                        float4 rb[4];
+                        bool ov[4], any[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) rb[u] = C_BOX[min(r0 + u, r_end - 1)];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            ov[u] = jv && j > r0 + u && rb[u].z > cb.x && cb.z > rb[u].x && rb[u].w > cb.y && cb.w > rb[u].y;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) any[u] = __any_sync(0xffffffffu, ov[u]);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (r0 + u >= r_end) break;
+                            uint32_t bits = 0u;
+                            if (any[u]) {
+                                bool g = false;
+                                if (ov[u]) {
+                                    const float ra = S_C_AREA[r0 + u];
+                                    bool bd;
+                                    g = iou_gt_approx(rb[u], ra, cb, ca, p.thr, band, bd);
+                                    if (bd) g = iou_gt(rb[u], ra, cb, ca, p.thr);  // rare: quotient within a few ulp of thr
+                                }
+                                bits = __ballot_sync(0xffffffffu, g);
+                            }
+                            if (lane == 0) S_MASK[w * kSub + r0 + u] = bits;
                         }
-                        continue;
                     }
-                    bool g0 = iou_gt_approx(rb, ra, cb0, S_C_AREA[jc0], p.thr, band, bd0);
-                    bool g1 = iou_gt_approx(rb, ra, cb1, S_C_AREA[jc1], p.thr, band, bd1);
-                    if (__any_sync(0xffffffffu, (bd0 && v0) || (bd1 && v1))) {  // rare: quotient within a few ulp of thr
-                        if (bd0) g0 = iou_gt(rb, ra, cb0, S_C_AREA[jc0], p.thr);
-                        if (bd1) g1 = iou_gt(rb, ra, cb1, S_C_AREA[jc1], p.thr);
-                    }
-                    const uint32_t bits0 = __ballot_sync(0xffffffffu, g0 && v0);
-                    const uint32_t bits1 = __ballot_sync(0xffffffffu, g1 && v1);
-                    if (lane == 0) {
-                        S_MASK[r * kSubWords + w] = bits0;
-                        if (w + 1 < words) S_MASK[r * kSubWords + w + 1] = bits1;
-                    }
+                    it += r_end - r_begin;
+                    ++w;
                 }
             }
             __syncthreads();
@@ -550,15 +596,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #pragma unroll
                 for (int g = 0; g < kSubWords; ++g) km[g] = 0u;
                 int kl = kept;
-                // column g of the bitmask (word g of the rows g2*32+lane, g2 <= g) is loaded one group ahead, before
+                // column g of the bitmask (word g of the rows g2*32+lane, g2 <= g; word-major layout: conflict-free) is loaded one group ahead, before
                 // the dependent chain of group g-1, so the sweep never waits on shared memory
                 uint32_t cur[kSubWords], nxt[kSubWords];
-                cur[0] = S_MASK[lane * kSubWords];
+                cur[0] = S_MASK[lane];
 #pragma unroll
                 for (int g = 0; g < kSubWords; ++g) {
                     if (g + 1 < kSubWords) {
 #pragma unroll
-                        for (int g2 = 0; g2 <= g + 1; ++g2) nxt[g2] = S_MASK[((g2 << 5) + lane) * kSubWords + g + 1];
+                        for (int g2 = 0; g2 <= g + 1; ++g2) nxt[g2] = S_MASK[(g + 1) * kSub + (g2 << 5) + lane];
                     }
                     if (g < words && kl < p.max_det) {
                         // removal word of group g = OR over the rows kept in earlier groups (lane = row)
@@ -896,6 +942,10 @@ struct GatherParams {
     float *peer_out[8];
     int32_t *peer_counts[8];
     int32_t n_peers, peer_slot_offset;
+    // results layout (sarpost_nms_params_t.res_boxes): 7-column boxes with the state id + contiguous embeddings
+    float *res_boxes;    // [B, max_det, 7] x1,y1,x2,y2,state_id,conf,cls or nullptr
+    float *res_embeds;   // [B, max_det, res_n_raw]
+    int32_t res_n_raw;   // leading extras columns that are the embedding; the remaining nm - res_n_raw are state probabilities
 };
 
 // ops.scale_boxes (utils/ops.py:92-127, padding=True, xyxy) followed by clip_boxes (:319-338), in torch's fp32
@@ -937,6 +987,43 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
         return;
     }
     const uint32_t anchor = key / static_cast<uint32_t>(p.ex.nc), cls = key - anchor * static_cast<uint32_t>(p.ex.nc);
+    if (p.res_boxes) {
+        // models/yolo/jde/predict.py:52-66: boxes = cat(xyxy, argmax(states), conf, cls), embeds = the raw embedding columns
+        const int64_t row = static_cast<int64_t>(b) * p.max_det + r;
+        const int n_raw = p.res_n_raw, n_sig = p.ex.nm - n_raw;
+        float *emb = p.res_embeds + row * n_raw;
+        float best = -1.0f;  // probabilities are >= 0
+        int best_i = 0x7fffffff;
+        if (p.ex.nm > 0 && p.ex.mode == 0 && anchor >= static_cast<uint32_t>(p.ex.anchors)) {
+            for (int c = lane; c < n_raw; c += 32) emb[c] = 0.0f;  // apriori label row: zero extras (ops.py:258) -> state id 0
+            if (lane == 0 && n_sig > 0) { best = 0.0f; best_i = 0; }
+        } else if (p.ex.nm > 0) {
+            gather_extras_row(p.ex, b, anchor, lane, [&](int c, float v) {
+                if (c < n_raw) emb[c] = v;
+                else if (v > best) { best = v; best_i = c - n_raw; }  // ascending c per lane + strict > : first maximum
+            });
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+        }
+        if (lane == 0) {
+            float4 bx = p.st.box[seg + slot];
+            if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
+            float *o = p.res_boxes + row * 7;
+            o[0] = bx.x;
+            o[1] = bx.y;
+            o[2] = bx.z;
+            o[3] = bx.w;
+            o[4] = n_sig > 0 ? static_cast<float>(best_i) : -1.0f;
+            o[5] = p.st.score[seg + slot];
+            o[6] = static_cast<float>(cls);
+            if (p.kept_index) p.kept_index[row] = static_cast<int32_t>(key);
+        }
+        return;
+    }
     if (lane == 0) {
         float4 bx = p.st.box[seg + slot];
         if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);

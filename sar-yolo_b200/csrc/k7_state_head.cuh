@@ -22,9 +22,14 @@ constexpr int kStateKC = 32;       // W1 columns per shared tile
 constexpr int kStateWS = kStateKC + 4;  // shared row stride of the W1 tile (floats)
 
 struct StateHeadParams {
-    float *rows;            // [B, max_det, row_len], updated in place
+    // Row g = b*max_det + r of the batch: embedding at emb + g*emb_stride, state probabilities written to
+    // state_out + g*state_stride (nullptr: not wanted), argmax over them (first maximum, as a float — the `state_id`
+    // column of models/yolo/jde/predict.py:61-64) written to id_out + g*id_stride (nullptr: not wanted).
+    const float *emb;
+    float *state_out, *id_out;
+    int64_t emb_stride, state_stride, id_stride;
     const int32_t *counts;  // [B]
-    int32_t batch, max_det, row_len, emb_col, embed_dim, state_col, n_state, hidden;
+    int32_t batch, max_det, embed_dim, n_state, hidden;
     int32_t w1_vec;         // W1 rows are 16-byte aligned (embed_dim % 4 == 0, aligned base): 128-bit loads
     const float *w1, *b1;   // nn.Linear(E, H): weight (H, E) row-major, bias (H)
     const float *w2, *b2;   // nn.Linear(H, S): weight (S, H) row-major, bias (S)
@@ -32,7 +37,7 @@ struct StateHeadParams {
 
 __host__ __device__ inline int state_head_smem_floats(int embed_dim, int hidden, int jt) {
     const int jl = 32 * jt, hpad = ((hidden + jl - 1) / jl) * jl, epad = ((embed_dim + kStateKC - 1) / kStateKC) * kStateKC;
-    return kStateRows * epad + 2 * jl * kStateWS + kStateRows * (hpad + 1);
+    return kStateRows * epad + 2 * jl * kStateWS + kStateRows * (hpad + 1) + kStateRows * 64 /* probabilities for the argmax */;
 }
 
 // JT = hidden units per thread; one pass covers JL = 32*JT hidden units.
@@ -50,7 +55,8 @@ __global__ void __launch_bounds__(kStateThreads) k7_state_head(const __grid_cons
     float *EMB = sh_state;                 // [kStateRows][epad], zero padded
     float *WT = EMB + kStateRows * epad;   // 2 x [JL][kStateWS]
     float *HID = WT + 2 * kTileF;          // [kStateRows][hpad + 1]
-    float *img_rows = p.rows + (static_cast<int64_t>(b) * p.max_det + row0) * p.row_len;
+    float *PROB = HID + kStateRows * (hpad + 1);  // [kStateRows][64]
+    const int64_t g0 = static_cast<int64_t>(b) * p.max_det + row0;
 
     const int n_kt = epad / kStateKC, n_tiles = (hpad / JL) * n_kt;
     float4 wreg[kVPer];
@@ -78,7 +84,7 @@ __global__ void __launch_bounds__(kStateThreads) k7_state_head(const __grid_cons
     };
     load_tile(0, 0);
     for (int r = 0; r < kStateRows; ++r) {
-        const float *src = img_rows + static_cast<int64_t>(r) * p.row_len + p.emb_col;
+        const float *src = p.emb + (g0 + r) * p.emb_stride;
         for (int k = tid; k < epad; k += kStateThreads) EMB[r * epad + k] = (r < n_rows && k < E) ? src[k] : 0.0f;
     }
     store_tile(0);
@@ -142,7 +148,19 @@ __global__ void __launch_bounds__(kStateThreads) k7_state_head(const __grid_cons
         const float *w = p.w2 + static_cast<int64_t>(s) * H;
         float a = 0.0f;
         for (int j = 0; j < H; ++j) a = fmaf(__ldg(w + j), h[j], a);
-        img_rows[static_cast<int64_t>(r) * p.row_len + p.state_col + s] = sigmoid_rn(a + p.b2[s]);  // head.py:247
+        const float pr = sigmoid_rn(a + p.b2[s]);  // head.py:247
+        if (p.state_out) p.state_out[(g0 + r) * p.state_stride + s] = pr;
+        PROB[r * 64 + s] = pr;
+    }
+    if (p.id_out) {
+        __syncthreads();
+        if (tid < n_rows && tid < kStateRows) {
+            float best = PROB[tid * 64];
+            int bi = 0;
+            for (int s = 1; s < S; ++s)
+                if (PROB[tid * 64 + s] > best) { best = PROB[tid * 64 + s]; bi = s; }  // strict >: first maximum (torch.argmax)
+            p.id_out[(g0 + tid) * p.id_stride] = static_cast<float>(bi);
+        }
     }
 }
 
@@ -196,7 +214,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 1) k7_state_head_resident(cons
             row0 = (o - b * opi) * kResRows;
             n_valid = min(kResRows, min(p.counts[b], p.max_det) - row0);
         }
-        float *img_rows = p.rows + (static_cast<int64_t>(b) * p.max_det + row0) * p.row_len;
+        const int64_t g0 = static_cast<int64_t>(b) * p.max_det + row0;
         if (n_valid > 0) {
             __syncwarp();
             // the embedding columns are only read in this kernel (the state columns it writes are disjoint): read-only
@@ -206,7 +224,7 @@ __global__ void __launch_bounds__(kResWarps * 32, 1) k7_state_head_resident(cons
                 const int k = k0 + lane;
 #pragma unroll
                 for (int r = 0; r < kResRows; ++r)
-                    v[r] = (r < n_valid && k < E) ? __ldg(img_rows + static_cast<int64_t>(r) * p.row_len + p.emb_col + k) : 0.0f;
+                    v[r] = (r < n_valid && k < E) ? __ldg(p.emb + (g0 + r) * p.emb_stride + k) : 0.0f;
                 if (k < E) {
 #pragma unroll
                     for (int r = 0; r < kResRows; ++r) slab[r * E + k] = v[r];
@@ -271,11 +289,24 @@ __global__ void __launch_bounds__(kResWarps * 32, 1) k7_state_head_resident(cons
 #pragma unroll
             for (int r = 0; r < kResRows; ++r) res[r] = lane == s ? part[r] : res[r];
         }
-        if (lane < S) {
+        {
             const float b2 = B2S[lane];
 #pragma unroll
-            for (int r = 0; r < kResRows; ++r)
-                if (r < n_valid) img_rows[static_cast<int64_t>(r) * p.row_len + p.state_col + lane] = sigmoid_rn(res[r] + b2);  // head.py:247
+            for (int r = 0; r < kResRows; ++r) {
+                const float pr = lane < S ? sigmoid_rn(res[r] + b2) : -1.0f;  // head.py:247 (probabilities are >= 0: -1 never wins)
+                if (lane < S && r < n_valid && p.state_out) p.state_out[(g0 + r) * p.state_stride + lane] = pr;
+                if (p.id_out) {  // argmax over the S lanes, first maximum (torch.argmax): larger value, then lower lane
+                    float bv = pr;
+                    int bi = lane;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+                    if (lane == 0 && r < n_valid) p.id_out[(g0 + r) * p.id_stride] = static_cast<float>(bi);
+                }
+            }
         }
     }
 }

@@ -154,6 +154,8 @@ static int check_params(const sarpost_nms_params_t *p, int nc) {
     for (int q = 0; q < p->n_peers; ++q)
         if (!p->peer_out[q] || !p->peer_counts[q]) return fail(SARPOST_EINVAL, "peer buffer %d is NULL", q);
     if (p->out_tail_cols < 0 || p->out_tail_cols > 4096) return fail(SARPOST_EINVAL, "out_tail_cols %d outside [0, 4096]", p->out_tail_cols);
+    if (p->res_boxes && (p->n_peers > 0 || p->out_tail_cols > 0)) return fail(SARPOST_EINVAL, "res_boxes does not combine with peer_out / out_tail_cols");
+    if (p->res_state_cols < 0) return fail(SARPOST_EINVAL, "res_state_cols %d < 0", p->res_state_cols);
     return SARPOST_OK;
 }
 
@@ -426,6 +428,15 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     gp.tail_cols = prm->out_tail_cols;
     gp.n_peers = prm->n_peers;
     gp.peer_slot_offset = prm->peer_slot_offset;
+    gp.res_boxes = ex.mode == 2 ? nullptr : prm->res_boxes;
+    gp.res_embeds = prm->res_embeds;
+    // which extras columns are the embedding: the raw ones of a head (mode 1); for a decoded prediction the caller says
+    // how many trailing columns are state probabilities
+    gp.res_n_raw = ex.mode == 1 ? ex.n_extra_raw : ex.nm - prm->res_state_cols;
+    if (gp.res_boxes) {
+        if (gp.res_n_raw < 0) return fail(SARPOST_EINVAL, "res_state_cols %d exceeds the %d extras columns", prm->res_state_cols, ex.nm);
+        if (gp.res_n_raw > 0 && !gp.res_embeds) return fail(SARPOST_EINVAL, "res_boxes set but res_embeds is NULL (embedding has %d columns)", gp.res_n_raw);
+    }
     for (int q = 0; q < 8; ++q) {
         gp.peer_out[q] = q < prm->n_peers ? prm->peer_out[q] : nullptr;
         gp.peer_counts[q] = q < prm->n_peers ? prm->peer_counts[q] : nullptr;
@@ -537,7 +548,7 @@ int32_t sarpost_nms_decoded(const void *prediction, int32_t batch, int32_t chann
     g_launches = 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (int rc = check_params(params, nc)) return rc;
-    if (!prediction || !out || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
+    if (!prediction || (!out && !params->res_boxes) || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
     if (batch < 1 || anchors < 1) return fail(SARPOST_EINVAL, "empty prediction (batch %d, anchors %lld)", batch, (long long)anchors);
     if (channels < 4 + nc) return fail(SARPOST_EINVAL, "channels %d < 4 + nc (%d)", channels, 4 + nc);
     if (anchors * nc >= (1ll << 32)) return fail(SARPOST_EUNSUPPORTED, "anchors*nc does not fit 32 bits");
@@ -606,7 +617,7 @@ int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *pa
     int64_t anchors = 0;
     if (int rc = fill_geom(head, &g, &anchors)) return rc;
     if (int rc = check_params(params, g.nc)) return rc;
-    if ((!out && params->n_peers == 0) || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
+    if ((!out && params->n_peers == 0 && !params->res_boxes) || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
     CandFilter f;
     make_filter(params, g.nc, &f);
     const int64_t nc_eff = f.multi_label ? g.nc : 1;
@@ -631,6 +642,7 @@ int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const 
     g_launches = 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (int rc = check_params(params, 1)) return rc;
+    if (params->res_boxes) return fail(SARPOST_EUNSUPPORTED, "the results layout (res_boxes) is not available for sarpost_merge_tiles");
     if (!dets || !det_counts || !origins || (!out && params->n_peers == 0) || !counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
     if (n_frames < 1 || tiles_per_frame < 1 || dets_per_tile < 1 || row_len < 6) return fail(SARPOST_EINVAL, "bad merge geometry");
     Pipeline P;
@@ -750,43 +762,20 @@ int32_t sarpost_match_from_iou(const float *iou, int32_t n_gt, int32_t n_det, in
     return SARPOST_OK;
 }
 
-int32_t sarpost_state_head(float *rows, const int32_t *counts, int32_t batch, int32_t max_det, int32_t row_len,
-                           int32_t emb_col, int32_t embed_dim, int32_t state_col, int32_t n_state, int32_t hidden,
-                           const float *w1, const float *b1, const float *w2, const float *b2, void *stream) {
-    g_launches = 0;
-    if (!rows || !counts || !w1 || !b1 || !w2 || !b2) return fail(SARPOST_EINVAL, "NULL pointer");
+static int launch_state_head(StateHeadParams p, const float *w1, cudaStream_t s) {
+    const int embed_dim = p.embed_dim, hidden = p.hidden, n_state = p.n_state, batch = p.batch, max_det = p.max_det;
     if (batch < 1 || max_det < 1) return fail(SARPOST_EINVAL, "bad state-head geometry");
     if (embed_dim < 1 || embed_dim > 1024 || hidden < 1 || hidden > 1024 || n_state < 1 || n_state > 64)
         return fail(SARPOST_EUNSUPPORTED, "state head %d -> %d -> %d outside (<=1024, <=1024, <=64)", embed_dim, hidden, n_state);
-    if (emb_col < 0 || state_col < 0 || emb_col + embed_dim > row_len || state_col + n_state > row_len)
-        return fail(SARPOST_EINVAL, "embedding / state columns outside the row (row_len %d)", row_len);
-    if (state_col < emb_col + embed_dim && emb_col < state_col + n_state)
-        return fail(SARPOST_EINVAL, "embedding and state columns overlap");
-    StateHeadParams p;
-    p.rows = rows;
-    p.counts = counts;
-    p.batch = batch;
-    p.max_det = max_det;
-    p.row_len = row_len;
-    p.emb_col = emb_col;
-    p.embed_dim = embed_dim;
-    p.state_col = state_col;
-    p.n_state = n_state;
-    p.hidden = hidden;
-    p.w1 = w1;
-    p.b1 = b1;
-    p.w2 = w2;
-    p.b2 = b2;
     p.w1_vec = (embed_dim % 4 == 0 && reinterpret_cast<uintptr_t>(w1) % 16 == 0) ? 1 : 0;
     const int jt = hidden > 64 ? 4 : hidden > 32 ? 2 : 1;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t res_smem = static_cast<size_t>(state_head_resident_smem_floats(embed_dim, n_state, jt)) * 4;
     if (p.w1_vec && hidden <= 128 && n_state <= 32 && res_smem <= 220 * 1024 && !getenv("SARPOST_STATE_TILED")) {
-        // resident variant: W1 copied once per persistent CTA, warps own whole groups of 8 kept rows
+        // resident variant: W1 copied once per persistent CTA, warps own whole groups of kept rows
         int sms = 0, smem_optin = 0;
         if (int rc = device_sm_count(&sms, &smem_optin)) return rc;
         const int n_octs = batch * ((max_det + kResRows - 1) / kResRows);
-        const int ctas = n_octs < sms ? n_octs : sms;  // persistent: warp w of CTA c takes octs w*ctas + c, + 6*ctas, ...
+        const int ctas = n_octs < sms ? n_octs : sms;  // persistent: warp w of CTA c takes octs w*ctas + c, + 12*ctas, ...
         void (*kern)(const StateHeadParams) = jt == 4 ? k7_state_head_resident<4> : jt == 2 ? k7_state_head_resident<2> : k7_state_head_resident<1>;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         kern<<<ctas, kResWarps * 32, res_smem, s>>>(p);
@@ -797,18 +786,69 @@ int32_t sarpost_state_head(float *rows, const int32_t *counts, int32_t batch, in
     const size_t smem = static_cast<size_t>(state_head_smem_floats(embed_dim, hidden, jt)) * 4;
     if (smem > 220 * 1024) return fail(SARPOST_EUNSUPPORTED, "state head too large for one CTA's shared memory");
     const dim3 grid((max_det + kStateRows - 1) / kStateRows, batch);
-    if (jt == 4) {
-        CUDA_TRY(cudaFuncSetAttribute(k7_state_head<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        k7_state_head<4><<<grid, kStateThreads, smem, s>>>(p);
-    } else if (jt == 2) {
-        CUDA_TRY(cudaFuncSetAttribute(k7_state_head<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        k7_state_head<2><<<grid, kStateThreads, smem, s>>>(p);
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute(k7_state_head<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        k7_state_head<1><<<grid, kStateThreads, smem, s>>>(p);
-    }
+    void (*kern)(const StateHeadParams) = jt == 4 ? k7_state_head<4> : jt == 2 ? k7_state_head<2> : k7_state_head<1>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    kern<<<grid, kStateThreads, smem, s>>>(p);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
+    return SARPOST_OK;
+}
+
+int32_t sarpost_state_head(float *rows, const int32_t *counts, int32_t batch, int32_t max_det, int32_t row_len,
+                           int32_t emb_col, int32_t embed_dim, int32_t state_col, int32_t n_state, int32_t hidden,
+                           const float *w1, const float *b1, const float *w2, const float *b2, void *stream) {
+    g_launches = 0;
+    if (!rows || !counts || !w1 || !b1 || !w2 || !b2) return fail(SARPOST_EINVAL, "NULL pointer");
+    if (emb_col < 0 || state_col < 0 || emb_col + embed_dim > row_len || state_col + n_state > row_len)
+        return fail(SARPOST_EINVAL, "embedding / state columns outside the row (row_len %d)", row_len);
+    if (state_col < emb_col + embed_dim && emb_col < state_col + n_state)
+        return fail(SARPOST_EINVAL, "embedding and state columns overlap");
+    StateHeadParams p;
+    memset(&p, 0, sizeof(p));
+    p.emb = rows + emb_col;
+    p.emb_stride = row_len;
+    p.state_out = rows + state_col;
+    p.state_stride = row_len;
+    p.counts = counts;
+    p.batch = batch;
+    p.max_det = max_det;
+    p.embed_dim = embed_dim;
+    p.n_state = n_state;
+    p.hidden = hidden;
+    p.w1 = w1;
+    p.b1 = b1;
+    p.w2 = w2;
+    p.b2 = b2;
+    return launch_state_head(p, w1, static_cast<cudaStream_t>(stream));
+}
+
+int32_t sarpost_state_ids(const float *embeds, const int32_t *counts, float *boxes7, int32_t batch, int32_t max_det,
+                          int32_t embed_dim, int32_t n_state, int32_t hidden, const float *w1, const float *b1,
+                          const float *w2, const float *b2, void *stream) {
+    g_launches = 0;
+    if (!embeds || !counts || !boxes7 || !w1 || !b1 || !w2 || !b2) return fail(SARPOST_EINVAL, "NULL pointer");
+    StateHeadParams p;
+    memset(&p, 0, sizeof(p));
+    p.emb = embeds;
+    p.emb_stride = embed_dim;
+    p.id_out = boxes7 + 4;  // column 4 of x1,y1,x2,y2,state_id,conf,cls
+    p.id_stride = 7;
+    p.counts = counts;
+    p.batch = batch;
+    p.max_det = max_det;
+    p.embed_dim = embed_dim;
+    p.n_state = n_state;
+    p.hidden = hidden;
+    p.w1 = w1;
+    p.b1 = b1;
+    p.w2 = w2;
+    p.b2 = b2;
+    return launch_state_head(p, w1, static_cast<cudaStream_t>(stream));
+}
+
+int32_t sarpost_abi_sizes(int32_t *head_bytes, int32_t *params_bytes) {
+    if (head_bytes) *head_bytes = static_cast<int32_t>(sizeof(sarpost_head_t));
+    if (params_bytes) *params_bytes = static_cast<int32_t>(sizeof(sarpost_nms_params_t));
     return SARPOST_OK;
 }
 
@@ -820,6 +860,22 @@ int32_t sarpost_debug_phase_cycles(unsigned long long *out16, int32_t reset) {
     if (reset) {
         unsigned long long z[16] = {0};
         CUDA_TRY(cudaMemcpyToSymbol(g_phase, z, sizeof(z)));
+    }
+    return SARPOST_OK;
+}
+// out48 = cycles[16] | visits[16] | longest visit[16]
+int32_t sarpost_debug_phase_detail(unsigned long long *out48, int32_t reset) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (out48) {
+        CUDA_TRY(cudaMemcpyFromSymbol(out48, g_phase, sizeof(unsigned long long) * 16));
+        CUDA_TRY(cudaMemcpyFromSymbol(out48 + 16, g_phase_n, sizeof(unsigned long long) * 16));
+        CUDA_TRY(cudaMemcpyFromSymbol(out48 + 32, g_phase_max, sizeof(unsigned long long) * 16));
+    }
+    if (reset) {
+        unsigned long long z[16] = {0};
+        CUDA_TRY(cudaMemcpyToSymbol(g_phase, z, sizeof(z)));
+        CUDA_TRY(cudaMemcpyToSymbol(g_phase_n, z, sizeof(z)));
+        CUDA_TRY(cudaMemcpyToSymbol(g_phase_max, z, sizeof(z)));
     }
     return SARPOST_OK;
 }

@@ -346,6 +346,7 @@ def non_max_suppression(
     in_place=True,
     rotated=False,
     return_index=False,
+    results_state_cols=None,
 ):
     """Drop-in for `ultralytics.utils.ops.non_max_suppression` (utils/ops.py:167-316) on CUDA tensors.
 
@@ -358,6 +359,9 @@ def non_max_suppression(
     defined).  `rotated=True` raises NotImplementedError.  Apriori `labels` (save_hybrid) are supported; with
     `return_index` a label row reports anchor index `A + label_row`.
     `return_index=True` (extension) also returns per image the int32 `anchor*nc + class` of each row.
+    `results_state_cols=S` (extension, SURVEY §8f row 1): the last S of the `nm` extras columns are state probabilities;
+    returns `(boxes, embeds)` per-image lists in the layout `JDEPredictor.postprocess` builds (models/yolo/jde/predict.py:52-66):
+    boxes `(n, 7)` = x1,y1,x2,y2,argmax(state),conf,cls (6 columns when S == 0) and the contiguous `(n, nm - S)` embeddings.
     """
     # the drop-in keeps the reference's assertion texts (ops.py:217-218): callers and tests match on them
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
@@ -412,13 +416,30 @@ def non_max_suppression(
         if ws_bytes < 0:
             _lib.check(int(ws_bytes))
         ws = _Workspace(ws_bytes, bs, dev)
-        out = torch.empty((bs, int(max_det), 6 + nm), dtype=torch.float32, device=dev)
+        res = results_state_cols is not None
+        if res:
+            n_sig = int(results_state_cols)
+            if not 0 <= n_sig <= nm:
+                raise ValueError(f"sarpost: results_state_cols {n_sig} outside [0, nm={nm}]")
+            res_boxes = torch.empty((bs, int(max_det), 7), dtype=torch.float32, device=dev)
+            res_embeds = torch.empty((bs, int(max_det), nm - n_sig), dtype=torch.float32, device=dev)
+            params.res_boxes, params.res_state_cols = res_boxes.data_ptr(), n_sig
+            params.res_embeds = res_embeds.data_ptr() if nm - n_sig else None
+        out = None if res else torch.empty((bs, int(max_det), 6 + nm), dtype=torch.float32, device=dev)
         counts = torch.empty((bs,), dtype=torch.int32, device=dev)
         kidx = torch.empty((bs, int(max_det)), dtype=torch.int32, device=dev) if return_index else None
-        _lib.check(lib.sarpost_nms_decoded(pred.data_ptr(), bs, ch, na, nc, C.byref(params), out.data_ptr(),
+        _lib.check(lib.sarpost_nms_decoded(pred.data_ptr(), bs, ch, na, nc, C.byref(params), out.data_ptr() if out is not None else None,
                                            counts.data_ptr(), kidx.data_ptr() if return_index else None,
                                            ws.ptr(), ws_bytes, _stream_ptr(dev)))
         ws.release()
+    if res:
+        if n_sig == 0:
+            res_boxes = torch.cat((res_boxes[..., :4], res_boxes[..., 5:]), -1)
+        if in_dtype != torch.float32:
+            res_boxes, res_embeds = res_boxes.to(in_dtype), res_embeds.to(in_dtype)
+        n = counts.tolist()
+        bx, em = [res_boxes[b, : n[b]] for b in range(bs)], [res_embeds[b, : n[b]] for b in range(bs)]
+        return (bx, em, [kidx[b, : n[b]] for b in range(bs)]) if return_index else (bx, em)
     if in_dtype != torch.float32:
         out = out.to(in_dtype)
     rows = _split(out, counts)
@@ -445,7 +466,8 @@ def decode(levels: Sequence[torch.Tensor], spec: HeadSpec) -> torch.Tensor:
 def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres=0.25, iou_thres=0.45, classes=None,
                       agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=7680,
                       return_index=False, return_padded=False, with_extras=True, scale_to=None, peer_out=None,
-                      state_mlp: Optional[StateMLP] = None, out=None, nms_stats: Optional[torch.Tensor] = None):
+                      state_mlp: Optional[StateMLP] = None, out=None, nms_stats: Optional[torch.Tensor] = None,
+                      results: bool = False):
     """decode + non_max_suppression in one pass (never materialises y; the extras channels are read only
     for the kept rows).  `levels`: the reference's concatenated `(B, no, H_l, W_l)` tensors, or the split layout —
     per level a tuple `(box, cls[, emb[, state]])` of the branch outputs before `torch.cat` (head.py:204-206), the
@@ -465,16 +487,31 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
     `out=(rows, counts)`: write into caller-owned contiguous `(B, max_det, row_len)` fp32 / `(B,)` int32 CUDA tensors (e.g. a
     slice of a larger gather buffer) instead of allocating; implies the padded return form.
     `nms_stats`: optional `(B, 4)` int64 CUDA tensor receiving the NMS kernel's instrumentation counters
-    (`sarpost_nms_params_t.stats`)."""
+    (`sarpost_nms_params_t.stats`).
+    `results=True`: the gather kernel writes what `JDEPredictor.postprocess` assembles per image with
+    split / argmax / cat (models/yolo/jde/predict.py:52-66) — `boxes (B, max_det, 7)` = x1,y1,x2,y2,state_id,conf,cls
+    (6 columns x1,y1,x2,y2,conf,cls when the head has no state classes, :73-75) and a contiguous `embeds (B, max_det, E)` —
+    instead of the `(6+nm)`-column rows.  Returns per-image lists `(boxes, embeds)`, or with `return_padded=True` the
+    device tensors `(boxes, embeds, counts)`.  Combines with `scale_to` (boxes come out in original-image pixels,
+    :49) and `state_mlp` (the deferred MLP then only produces the state id)."""
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     levels = _prep_levels(levels)
     if int(_box_of(levels[0]).shape[0]) == 0 and peer_out is None:  # empty batch: the reference returns an empty list (ops.py:250)
         dev0, cols = _box_of(levels[0]).device, 6 + (spec.nm if with_extras else 0)
+        if results:
+            cols = 7 if (spec.state_classes > 0 or state_mlp is not None) else 6
+            if return_padded:
+                e = (torch.zeros((0, int(max_det), cols), device=dev0), torch.zeros((0, int(max_det), spec.embed_dim), device=dev0),
+                     torch.zeros((0,), dtype=torch.int32, device=dev0))
+                return e + (torch.zeros((0, int(max_det)), dtype=torch.int32, device=dev0),) if return_index else e
+            return ([], [], []) if return_index else ([], [])
         if return_padded:
             e = (torch.zeros((0, int(max_det), cols), device=dev0), torch.zeros((0,), dtype=torch.int32, device=dev0))
             return e + (torch.zeros((0, int(max_det)), dtype=torch.int32, device=dev0),) if return_index else e
         return ([], []) if return_index else []
+    if results and (peer_out is not None or out is not None or not with_extras):
+        raise ValueError("sarpost: results=True does not combine with peer_out=, out= or with_extras=False")
     tail = 0
     if state_mlp is not None:
         if not with_extras or peer_out is not None:
@@ -482,7 +519,7 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
         if (state_mlp.embed_dim, state_mlp.n_state) != (spec.embed_dim, spec.state_classes):
             raise ValueError(f"sarpost: state MLP is {state_mlp.embed_dim}->{state_mlp.n_state}, head has embed_dim "
                              f"{spec.embed_dim}, state_classes {spec.state_classes}")
-        tail = spec.state_classes
+        tail = 0 if results else spec.state_classes
         spec = HeadSpec(nc=spec.nc, strides=spec.strides, reg_max=spec.reg_max, embed_dim=spec.embed_dim, state_classes=0)
     head = _make_head(levels, spec, with_extras=with_extras)
     nm = spec.nm if with_extras else 0
@@ -509,6 +546,12 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
         if ws_bytes < 0:
             _lib.check(int(ws_bytes))
         ws = _Workspace(ws_bytes, bs, dev)
+        res_boxes = res_embeds = None
+        if results:
+            res_boxes = torch.empty((bs, int(max_det), 7), dtype=torch.float32, device=dev)
+            res_embeds = torch.empty((bs, int(max_det), spec.embed_dim), dtype=torch.float32, device=dev)
+            params.res_boxes = res_boxes.data_ptr()
+            params.res_embeds = res_embeds.data_ptr() if spec.embed_dim else None
         if out is not None:
             out, counts = out
             if peer_out is not None:
@@ -518,7 +561,7 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
                     raise ValueError(f"sarpost: out= tensors must be contiguous {shp} {dt} on {dev}")
             return_padded = True
         else:
-            out = torch.empty((bs, int(max_det), 6 + nm + tail), dtype=torch.float32, device=dev) if peer_out is None else None
+            out = torch.empty((bs, int(max_det), 6 + nm + tail), dtype=torch.float32, device=dev) if (peer_out is None and not results) else None
             counts = torch.empty((bs,), dtype=torch.int32, device=dev)
         want_idx = return_index
         kidx = torch.empty((bs, int(max_det)), dtype=torch.int32, device=dev) if want_idx else None
@@ -526,8 +569,21 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
                                      counts.data_ptr(), kidx.data_ptr() if want_idx else None, ws.ptr(), ws_bytes,
                                      _stream_ptr(dev)))
         ws.release()
-        if state_mlp is not None:
+        if state_mlp is not None and results:
+            _lib.check(lib.sarpost_state_ids(res_embeds.data_ptr(), counts.data_ptr(), res_boxes.data_ptr(), bs, int(max_det),
+                                             state_mlp.embed_dim, state_mlp.n_state, state_mlp.hidden, state_mlp.w1.data_ptr(),
+                                             state_mlp.b1.data_ptr(), state_mlp.w2.data_ptr(), state_mlp.b2.data_ptr(), _stream_ptr(dev)))
+        elif state_mlp is not None:
             state_head(out, counts, state_mlp, emb_col=6, state_col=6 + nm)
+    if results:
+        has_state = spec.state_classes > 0 or state_mlp is not None
+        if not has_state:  # no state id to show: the reference hands Boxes the plain 6 columns (predict.py:73-75)
+            res_boxes = torch.cat((res_boxes[..., :4], res_boxes[..., 5:]), -1)
+        if return_padded:
+            return (res_boxes, res_embeds, counts, kidx) if want_idx else (res_boxes, res_embeds, counts)
+        n = counts.tolist()
+        bx, em = [res_boxes[b, : n[b]] for b in range(bs)], [res_embeds[b, : n[b]] for b in range(bs)]
+        return (bx, em, [kidx[b, : n[b]] for b in range(bs)]) if want_idx else (bx, em)
     if peer_out is not None:
         return (peer_out.rows, peer_out.counts, kidx) if want_idx else (peer_out.rows, peer_out.counts)
     if return_padded:

@@ -94,7 +94,7 @@ def _make_inference(kind: str):
 
 def patch(ultralytics_ops=None, ultralytics_head=None, decode: bool = True, fused: bool = False,
           defer_state: bool = False, split: bool = False, emb_channels_last: bool = True, match: bool = False,
-          ultralytics_validator=None) -> None:
+          ultralytics_validator=None, predictor: bool = False, ultralytics_jde_predict=None) -> None:
     """Monkey-patch the reference.  Modules default to the importable `ultralytics` package.
 
     `fused=False`: API-exact — `_inference` returns the real `y` (decode kernel), `non_max_suppression` runs the
@@ -111,11 +111,15 @@ def patch(ultralytics_ops=None, ultralytics_head=None, decode: bool = True, fuse
     `(B, A, embed_dim)` embedding map (head.py:198-204) and the patched NMS evaluates that MLP only on the kept rows
     (`sarpost_state_head`).
     `match=True`: `BaseValidator.match_predictions` (engine/validator.py:222-262) runs on the GPU
-    (`sarpost_match_predictions`) for CUDA inputs with `use_scipy=False`."""
+    (`sarpost_match_predictions`) for CUDA inputs with `use_scipy=False`.
+    `predictor=True` (with `fused=True`): `JDEPredictor.postprocess` (models/yolo/jde/predict.py:29-78) —
+    NMS, then per image `scale_boxes`, split of the row, `argmax` over the states and `cat` into the 7-column boxes — becomes
+    one fused call whose gather kernel writes the boxes (already in original-image pixels, state id in column 4) and the
+    contiguous embeddings that `Results` takes."""
     if _SAVED:
         return
-    if (defer_state or split) and not fused:
-        raise ValueError("sarpost: split=True / defer_state=True need fused=True")
+    if (defer_state or split or predictor) and not fused:
+        raise ValueError("sarpost: split=True / defer_state=True / predictor=True need fused=True")
     split = split or defer_state
     ops_mod = ultralytics_ops or importlib.import_module("ultralytics.utils.ops")
     _SAVED["ops_mod"] = ops_mod
@@ -128,15 +132,20 @@ def patch(ultralytics_ops=None, ultralytics_head=None, decode: bool = True, fuse
         _SAVED["head_mod"] = head_mod
         _SAVED["detect"] = head_mod.Detect._inference
         head_mod.Detect._inference = make("detect")
-        if split:
+        if split and hasattr(head_mod.Detect, "forward"):
             _SAVED["detect_forward"] = head_mod.Detect.forward
             head_mod.Detect.forward = _detect_forward_split
         if hasattr(head_mod, "JDE"):
             _SAVED["jde"] = head_mod.JDE._inference
             head_mod.JDE._inference = make("jde")
-            if split:
+            if split and hasattr(head_mod.JDE, "forward"):
                 _SAVED["jde_forward"] = head_mod.JDE.forward
                 head_mod.JDE.forward = _jde_forward_split
+    if predictor:
+        pred_mod = ultralytics_jde_predict or importlib.import_module("ultralytics.models.yolo.jde.predict")
+        _SAVED["pred_mod"] = pred_mod
+        _SAVED["jde_post"] = pred_mod.JDEPredictor.postprocess
+        pred_mod.JDEPredictor.postprocess = _jde_predictor_postprocess
     if match:
         val_mod = ultralytics_validator or importlib.import_module("ultralytics.engine.validator")
         _SAVED["val_mod"] = val_mod
@@ -167,6 +176,8 @@ def unpatch() -> None:
             head_mod.JDE._inference = _SAVED["jde"]
         if "jde_forward" in _SAVED:
             head_mod.JDE.forward = _SAVED["jde_forward"]
+    if "jde_post" in _SAVED:
+        _SAVED["pred_mod"].JDEPredictor.postprocess = _SAVED["jde_post"]
     if "match" in _SAVED:
         _SAVED["val_mod"].BaseValidator.match_predictions = _SAVED["match"]
     if "jde_match" in _SAVED:
@@ -213,6 +224,36 @@ def _jde_match_predictions_dispatch(self, pred_classes, true_classes, true_tags,
     correct, matched = _ops.match_from_iou(pred_classes, true_classes, iou, thr, tag_threshold_index=tag_idx)
     picked = true_tags.to(pred_classes.device)[matched.clamp(min=0).long()].to(torch.int)
     return correct, torch.where(matched >= 0, picked, tags)
+
+
+def _jde_predictor_postprocess(self, preds, img, orig_imgs):
+    """`JDEPredictor.postprocess(preds, img, orig_imgs)` (models/yolo/jde/predict.py:29-78) as ONE fused call: decode + NMS
+    from the raw logits, `ops.scale_boxes` to the original image (:49), the state `argmax` and the 7-column re-pack
+    `[xyxy, state_id, conf, cls]` (:61-64) and the contiguous embeddings all come out of the gather kernel; what is left
+    here is building the `Results` objects.  Anything the fused path does not cover runs the reference's own method."""
+    pred = preds[0] if isinstance(preds, (list, tuple)) else preds
+    model = getattr(self, "model", None)
+    names = getattr(model, "names", None)
+    a = self.args
+    ok = (isinstance(pred, LazyPrediction) and pred._y is None and names is not None and len(names) == pred._spec.nc
+          and pred._spec.embed_dim > 0 and 1 <= int(a.max_det) <= 4096)
+    if not ok:
+        return _SAVED["jde_post"](self, preds, img, orig_imgs)
+    if not isinstance(orig_imgs, list):  # a tensor source: the reference converts it to a list of HWC arrays (:41-42)
+        orig_imgs = _SAVED["ops_mod"].convert_torch2numpy_batch(orig_imgs)
+    boxes, embeds = _ops.postprocess_fused(pred._levels, pred._spec, conf_thres=a.conf, iou_thres=a.iou, classes=a.classes,
+                                           agnostic=a.agnostic_nms, max_det=a.max_det, state_mlp=pred.state_mlp(), results=True,
+                                           scale_to=(tuple(img.shape[2:]), [tuple(o.shape) for o in orig_imgs]))
+    Results = importlib.import_module(_SAVED["pred_mod"].__name__.split(".models.")[0] + ".engine.results").Results \
+        if not hasattr(_SAVED["pred_mod"], "Results") else _SAVED["pred_mod"].Results
+    out = []
+    for bx, em, orig_img, img_path in zip(boxes, embeds, orig_imgs, self.batch[0]):
+        if pred.dtype != torch.float32:
+            bx, em = bx.to(pred.dtype), em.to(pred.dtype)  # the reference's rows carry the prediction's dtype
+        if bx.shape[0] == 0 and bx.shape[1] == 7:
+            bx = bx[:, :6]  # no detections: the reference skips the state column (:66-69)
+        out.append(Results(orig_img, path=img_path, names=names, person_states=getattr(model, "person_states", None), boxes=bx, embeds=em))
+    return out
 
 
 def fused_postprocess(preds, head_module, img_shape=None, orig_shapes=None, **nms_kwargs):

@@ -74,3 +74,13 @@ def load_state_case():
     t["rows"] = list(torch.split(t["rows"], z["counts"].tolist()))
     t["meta"] = meta
     return t
+
+
+def load_tail_case():
+    """tests/golden/predict_tail_jde.npz: boxes (n, 7) / embeds (n, E) per image from the live, unmodified
+    JDEPredictor.postprocess (models/yolo/jde/predict.py:29-78) on the state case's prediction."""
+    z = np.load(os.path.join(GOLDEN_DIR, "predict_tail_jde.npz"))
+    meta = json.loads(str(z["meta"]))
+    counts = z["counts"].tolist()
+    return dict(meta=meta, counts=counts, boxes=list(torch.split(torch.from_numpy(z["boxes"]), counts)),
+                embeds=list(torch.split(torch.from_numpy(z["embeds"]), counts)))

@@ -728,7 +728,8 @@ def test_patch_defer_state_runs_the_mlp_on_kept_rows_only(sarpost, cuda):
         sarpost.patch(ops_mod, head_mod, fused=True, defer_state=True)
         try:
             y, x = head([f.clone() for f in feats])
-            assert calls["mlp"] == 2 and x[0].shape[1] == 64 + 1 + 32 and tuple(y.shape) == tuple(want_y.shape)
+            # defer_state implies the split layout: per level a (box, cls, emb) tuple, no state branch
+            assert calls["mlp"] == 2 and [int(t.shape[1]) for t in x[0]] == [64, 1, 32] and tuple(y.shape) == tuple(want_y.shape)
             got = ops_mod.non_max_suppression(y, 0.3, 0.7, max_det=50, nc=1)
             assert calls["mlp"] == 2 and y._y is None
             assert sum(r.shape[0] for r in got) > 10
@@ -738,7 +739,7 @@ def test_patch_defer_state_runs_the_mlp_on_kept_rows_only(sarpost, cuda):
             assert torch.allclose(y + 0, want_y, rtol=1e-5, atol=1e-5) and calls["mlp"] == 4   # materialising y runs the module's MLP
         finally:
             sarpost.unpatch()
-    assert JDE.forward is not sarpost.plugin._jde_forward_deferred
+    assert JDE.forward is not sarpost.plugin._jde_forward_split
 
 
 def test_empty_batch_returns_empty_list(sarpost, cuda):

@@ -245,3 +245,22 @@ def test_oracle_decode_fuzz_against_live_reference(sarpost):
         st = torch.cat([torch.full((h * w,), float(s)) for (h, w), s in zip(shapes, strides)])
         assert bool(((got[:, :4] - want[:, :4]).abs() <= 2e-6 * want[:, :4].abs() + 2e-6 * st).all()), case
         assert torch.allclose(got[:, 4:], want[:, 4:], rtol=2e-6, atol=1e-9), case
+
+
+def test_jde_results_ref_matches_live_predictor_tail_golden():
+    """oracle.jde_results_ref (scale_boxes, state argmax, 7-column re-pack) applied to the reference's own NMS rows ==
+    what the live JDEPredictor.postprocess returned for the same prediction (tests/golden/predict_tail_jde.npz)."""
+    from golden_util import load_state_case, load_tail_case
+
+    st, tail = load_state_case(), load_tail_case()
+    m, t = st["meta"], tail["meta"]["tail"]
+    assert tail["meta"]["state"] == m and (t["conf"], t["iou"], t["max_det"]) == (m["kw"]["conf_thres"], m["kw"]["iou_thres"], m["kw"]["max_det"])
+    for rows, s0, bx, em in zip(st["rows"], t["orig_shapes"], tail["boxes"], tail["embeds"]):
+        b, e = R.jde_results_ref(rows, t["img_shape"], s0, m["ed"], m["sc"])
+        assert b.shape[1] == 7 and torch.equal(b, bx) and torch.equal(e, em)
+        assert float(b[:, 4].min()) >= 0 and float(b[:, 4].max()) < m["sc"]
+    # no rows: the plain 6 columns; no state head: 6 columns + every extra as the embedding
+    b, e = R.jde_results_ref(torch.zeros((0, 6 + m["ed"] + m["sc"])), t["img_shape"], t["orig_shapes"][0], m["ed"], m["sc"])
+    assert tuple(b.shape) == (0, 6) and tuple(e.shape) == (0, m["ed"])
+    b, e = R.jde_results_ref(st["rows"][0], t["img_shape"], t["orig_shapes"][0], m["ed"] + m["sc"], 0)
+    assert b.shape[1] == 6 and e.shape[1] == m["ed"] + m["sc"]
