@@ -301,7 +301,8 @@ struct NmsSmemLayout {
     static constexpr int dead = c_slot + kSub * 4;                   // i32[kSub]  master: verdicts of the incremental phase 1
     static constexpr int deadw = dead + kSub * 4;                    // u32[kShareCap / 32]  share phase 1: dead bits
     static constexpr int misc = deadw + kShareCap / 32 * 4;          // i32[64]
-    static constexpr int kept = misc + 64 * 4;                       // float4[max_det] | f32[max_det] | u32[max_det]
+    static constexpr int zstart = misc + 64 * 4;                     // i32[kBuckets + 4]  zoom: exact sub-bucket ranks of one bucket
+    static constexpr int kept = zstart + (kBuckets + 4) * 4;         // float4[max_det] | f32[max_det] | u32[max_det]
 };
 static_assert(NmsSmemLayout::radix_end >= 256 * (kNmsWarps + 1) * 4, "radix counters must fit the plist|surv|skey region");
 static_assert(kTileListCap * 4 <= 2 * kSub * 16, "tile list must fit the a_box|c_box region");
@@ -323,7 +324,8 @@ enum : int {
     kMCtl = 40,      // [40, 44) control block written by the master into every CTA: action, kept, members, survivors
     kMCtr = 48,      // [48, 56) master only: two banks (chunk parity) of {members, survivors, overflow}
 };
-enum : int { kActOk = 0, kActHalve = 1, kActCareful = 2, kActRadix = 3 };
+enum : int { kActOk = 0, kActHalve = 1, kActCareful = 2, kActRadix = 3, kActZoom = 4 };
+constexpr uint32_t kZoomSpan = (1u << kBucketShift) / kBuckets;  // float values per sub-bucket of a zoomed bucket (8)
 
 // One CTA, or a thread-block cluster of CL CTAs, per image.
 //   every CTA   collects its share (interleaved tiles) of the next run of score buckets and tests those candidates
@@ -362,6 +364,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #define S_DEAD (reinterpret_cast<int32_t *>(dyn + L::dead))
 #define S_DEADW (reinterpret_cast<uint32_t *>(dyn + L::deadw))
 #define S_MISC (reinterpret_cast<int32_t *>(dyn + L::misc))
+#define S_ZSTART (reinterpret_cast<int32_t *>(dyn + L::zstart))
 #define KEPT_BOX (reinterpret_cast<float4 *>(dyn + L::kept))
 #define KEPT_AREA (reinterpret_cast<float *>(dyn + L::kept + static_cast<size_t>(p.max_det) * 16))
 #define KEPT_SLOT (reinterpret_cast<uint32_t *>(dyn + L::kept + static_cast<size_t>(p.max_det) * 20))
@@ -372,6 +375,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     const uint32_t *tmaxv = p.st.tile_max + static_cast<int64_t>(b) * p.st.tpi;
     const float *score = p.st.score + seg;
     const float band = fmaxf(p.thr * 2e-6f, 1e-37f);
+    // IoU <= min(area)/max(area): the fp32 intersection never exceeds either fp32 area (rounding is monotone) and the
+    // union is >= the larger area up to an ulp, so a pair whose area ratio is <= thr (less a 1e-5 relative margin, far
+    // above those ulps) cannot exceed the threshold: no IoU arithmetic needed for boxes of clearly different size.
+    const float ratio_cut = p.thr * (1.0f - 1e-5f);
     const bool need_cls = p.max_wh != 0.0f && (p.cls_override != nullptr || p.nc > 1);
 #ifdef SARPOST_PHASE_PROF
     long long prof_t = clock64();
@@ -412,18 +419,21 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         bool dead = false;
         for (int k = k_lo + part; k < k_hi; k += 4 * nparts) {
             float4 kb[4];
+            float ka4[4];
             bool ov[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int ku = k + u * nparts;
                 kb[u] = KEPT_BOX[ku < k_hi ? ku : k];
-                ov[u] = valid && ku < k_hi && kb[u].z > ob.x && ob.z > kb[u].x && kb[u].w > ob.y && ob.w > kb[u].y;
+                ka4[u] = KEPT_AREA[ku < k_hi ? ku : k];
+                ov[u] = valid && ku < k_hi && kb[u].z > ob.x && ob.z > kb[u].x && kb[u].w > ob.y && ob.w > kb[u].y &&
+                        !(fminf(ka4[u], oa) <= ratio_cut * fmaxf(ka4[u], oa));
             }
             if (!__any_sync(0xffffffffu, ov[0] || ov[1] || ov[2] || ov[3])) continue;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (!ov[u]) continue;
-                const float ka = KEPT_AREA[k + u * nparts];
+                const float ka = ka4[u];
                 bool bd;
                 bool gt = iou_gt_approx(kb[u], ka, ob, oa, p.thr, band, bd);
                 if (bd) gt = iou_gt(kb[u], ka, ob, oa, p.thr);  // rare: a quotient within a few ulp of the threshold
@@ -542,7 +552,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             // Work items = (word w, row r < min(m, 32(w+1))), flattened word-major and cut into equal slices, one per warp.
             // A warp keeps the 32 column boxes of its current word in registers (lane = column) and streams rows past
             // them, four at a time: one broadcast shared load and four compares per (row, word); the IoU arithmetic runs
-            // only for rows that intersect some column of the word (disjoint boxes: inter = 0 -> IoU 0 or NaN, never > thr).
+            // only for rows that intersect some column of the word with a comparable area (disjoint boxes: inter = 0 -> IoU 0 or
+            // NaN, never > thr; area ratio <= thr: see ratio_cut).
             const int words = (m + 31) >> 5;
             {
                 const int n_items = 16 * words * (words - 1) + m;  // full words contribute 32(w+1) rows each, the last one m
@@ -559,12 +570,17 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                     const float ca = S_C_AREA[jv ? j : 0];
                     for (int r0 = r_begin; r0 < r_end; r0 += 4) {
                         float4 rb[4];
+                        float ra4[4];
                         bool ov[4], any[4];
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) rb[u] = C_BOX[min(r0 + u, r_end - 1)];
+                        for (int u = 0; u < 4; ++u) {
+                            rb[u] = C_BOX[min(r0 + u, r_end - 1)];
+                            ra4[u] = S_C_AREA[min(r0 + u, r_end - 1)];
+                        }
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
-                            ov[u] = jv && j > r0 + u && rb[u].z > cb.x && cb.z > rb[u].x && rb[u].w > cb.y && cb.w > rb[u].y;
+                            ov[u] = jv && j > r0 + u && rb[u].z > cb.x && cb.z > rb[u].x && rb[u].w > cb.y && cb.w > rb[u].y &&
+                                    !(fminf(ra4[u], ca) <= ratio_cut * fmaxf(ra4[u], ca));
 #pragma unroll
                         for (int u = 0; u < 4; ++u) any[u] = __any_sync(0xffffffffu, ov[u]);
 #pragma unroll
@@ -574,7 +590,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                             if (any[u]) {
                                 bool g = false;
                                 if (ov[u]) {
-                                    const float ra = S_C_AREA[r0 + u];
+                                    const float ra = ra4[u];
                                     bool bd;
                                     g = iou_gt_approx(rb[u], ra, cb, ca, p.thr, band, bd);
                                     if (bd) g = iou_gt(rb[u], ra, cb, ca, p.thr);  // rare: quotient within a few ulp of thr
@@ -670,9 +686,204 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     int par = 0;          // chunk parity: which bank of the master's counters this round uses
     bool careful = false; // redo of a chunk that crosses the max_nms cut: every member goes to the master (no phase 1 first)
     int last_m = 1, last_s = 1;  // members / survivors of the last committed chunk (survival rate steers the chunk size)
+    int m = 0, s_all = 0;        // members / survivors of the last attempt (cluster-uniform after barrier #2)
+    bool last_p1 = false;        // the last attempt ran phase 1 on the shares
 
-    while (d < kBuckets && pos < n_limit && kept < p.max_det) {
-        // ---- next chunk: a run of whole buckets [d, d1) whose ESTIMATED population fits the target ----
+    // One attempt at the candidates whose score bit patterns lie in [lo_bits, hi_bits]: collect, phase 1, deliver, and —
+    // on the master — sort + resolve.  Returns the cluster-uniform verdict: kActOk (committed: `kept` advanced, the range
+    // is consumed), kActCareful (the range crosses the max_nms rank cut: come back with careful = true), or `on_ovf`
+    // when the range does not fit the shared-memory lists — kActHalve / kActZoom: nothing was committed, the caller
+    // narrows the range; kActRadix: the range cannot be narrowed and was resolved here through the global radix sort.
+    auto attempt = [&](const uint32_t lo_bits, const uint32_t hi_bits, const int on_ovf) -> int {
+        int action = kActOk;
+        const int k0 = kept;
+        ++st_coll;
+        __syncthreads();
+        if (tid == 0) { S_MISC[kMShareCnt] = 0; S_MISC[kMSurvCnt] = 0; }
+        if (tid < kShareCap / 32) S_DEADW[tid] = 0u;
+        __syncthreads();
+        // ---- collect this CTA's members of the range ----
+        for_each_candidate_in(p.st, tcount, tmaxv, score, lo_bits, hi_bits, crank, CL, n_share, TILE_LIST, &S_MISC[kMListN],
+                              [&](uint32_t slot, uint32_t bits) {
+                                  const int at = atomicAdd(&S_MISC[kMShareCnt], 1);  // members are rare (a few hundred per image)
+                                  if (at < kShareCap) PLIST[at] = (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - slot);
+                              });
+        __syncthreads();
+        PROF_MARK(1);
+        const int my_cnt = S_MISC[kMShareCnt];
+        const int my_n = min(my_cnt, kShareCap);
+        // ---- phase 1 on the share: members x kept[0, k0) ----
+        const bool do_p1 = k0 > 0 && !careful;
+        last_p1 = do_p1;
+        if (do_p1) {
+            for (int base = 0; base < my_n; base += kNmsThreads) {
+                const int nb = min(kNmsThreads, my_n - base);
+                int sub_p2 = 64;
+                while (sub_p2 < nb) sub_p2 <<= 1;
+                const int ci = tid & (sub_p2 - 1), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
+                bool dead = false;
+                if (ci < nb) {
+                    const uint32_t slot = 0xffffffffu - static_cast<uint32_t>(PLIST[base + ci]);
+                    const float4 ob = offset_box(slot);
+                    dead = killed_by_kept(ob, box_area_rn(ob), 0, k0, part, nparts);
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, dead);  // a warp = 32 consecutive members, one part
+                if (lane == 0 && bal) atomicOr(&S_DEADW[(base + ci) >> 5], bal);
+            }
+            st_pairs += static_cast<long long>(my_n) * k0;
+            __syncthreads();
+            for (int i0 = warp * 32; i0 < my_n; i0 += kNmsThreads) {  // unordered compaction (the survivors get sorted anyway)
+                const int i = i0 + lane;
+                const bool alive = i < my_n && !((S_DEADW[i >> 5] >> (i & 31)) & 1u);
+                const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+                int at = 0;
+                if (lane == 0 && bal) at = atomicAdd(&S_MISC[kMSurvCnt], __popc(bal));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (alive) SURV[at + __popc(bal & lanemask_lt())] = PLIST[i];
+            }
+            __syncthreads();
+        }
+        PROF_MARK(2);
+        const unsigned long long *mine = do_p1 ? SURV : PLIST;
+        const int s_cnt = do_p1 ? S_MISC[kMSurvCnt] : my_n;
+        // ---- survivors -> master (offset from a remote atomic on the master's counters) ----
+        int32_t *ctr = &S_MISC[kMCtr + par * 4];
+        if constexpr (CL > 1) ctr = cluster.map_shared_rank(&S_MISC[kMCtr + par * 4], 0);
+        if (tid == 0) {
+            atomicAdd(ctr + 0, my_cnt);
+            S_MISC[kMOff] = atomicAdd(ctr + 1, s_cnt);
+            if (my_cnt > kShareCap) atomicOr(ctr + 2, 1);
+        }
+        __syncthreads();
+        {
+            const int off = S_MISC[kMOff];
+            unsigned long long *dst = SKEY;
+            if constexpr (CL > 1) dst = cluster.map_shared_rank(SKEY, 0);
+            for (int i = tid; i < s_cnt; i += kNmsThreads)
+                if (off + i < kSortCap) dst[off + i] = mine[i];
+        }
+        cluster_sync();  // barrier #1
+        PROF_MARK(3);
+        if (crank == 0) {
+            const int mm = S_MISC[kMCtr + par * 4 + 0];
+            const int ss = S_MISC[kMCtr + par * 4 + 1];
+            const bool share_ovf = S_MISC[kMCtr + par * 4 + 2] != 0;
+            if (share_ovf || ss > kSortCap) action = on_ovf;
+            else if (!careful && k0 > 0 && pos + mm > n_limit) action = kActCareful;  // crosses the rank cut: ranks need every member
+            else action = kActOk;
+            __syncthreads();
+            if (tid < 4) S_MISC[kMCtr + (par ^ 1) * 4 + tid] = 0;  // the other bank is idle until the next round
+            if (action == kActOk) {
+                if (ss > 0) {
+                    int lpw = 6;
+                    while ((1 << lpw) < ss) ++lpw;
+                    for (int i = ss + tid; i < (1 << lpw); i += kNmsThreads) SKEY[i] = 0ull;
+                    __syncthreads();
+                    bitonic_sort_desc(SKEY, lpw);
+                    PROF_MARK(4);
+                    // without a preceding phase 1 (first chunk, careful redo) the sorted list holds every member, so
+                    // the rank cut applies directly; after phase 1 the whole chunk is known to lie above the cut
+                    const int cnt = do_p1 ? ss : min(ss, n_limit - pos);
+                    process_sorted([&](int i) { return 0xffffffffu - static_cast<uint32_t>(SKEY[i]); }, cnt, do_p1 ? k0 : 0);
+                }
+            } else if (action == kActRadix) {
+                // ---- more equal (or nearly equal) scores than shared memory holds: collect the range to global scratch,
+                //      stable LSD radix sort on (score bits desc, slot asc), then stream it through the suppression phases
+                //      (rare path: thousands of candidates within 8 adjacent float values) ----
+                uint32_t *ka = p.tmp_key_a + seg, *va = p.tmp_val_a + seg, *kb = p.tmp_key_b + seg, *vb = p.tmp_val_b + seg;
+                const uint32_t *ik = ka, *iv = va;
+                uint32_t *ok = kb, *ov = vb;
+                int slot_bits = 1;
+                while ((static_cast<int64_t>(1) << slot_bits) < p.st.cap) ++slot_bits;
+                const int passes_slot = (slot_bits + 7) / 8;
+                // the members share every score bit above the range's span: only the bits that can differ need a pass
+                const int passes_key = (32 - __clz(static_cast<int>(lo_bits ^ hi_bits)) + 7) / 8;
+                __syncthreads();
+                if (tid == 0) S_MISC[kMShareCnt] = 0;
+                __syncthreads();
+                for_each_candidate_in(p.st, tcount, tmaxv, score, lo_bits, hi_bits, 0, 1, p.st.tpi, TILE_LIST, &S_MISC[kMListN],
+                                      [&](uint32_t slot, uint32_t bits) {
+                                          const int at = atomicAdd(&S_MISC[kMShareCnt], 1);
+                                          ka[at] = bits;
+                                          va[at] = slot;
+                                      });
+                __syncthreads();
+                int *cnt = reinterpret_cast<int *>(dyn + L::plist);  // aliases plist|surv|skey
+                int *wt = S_MISC + kMWarp;
+                for (int ps = 0; ps < passes_slot + passes_key; ++ps) {
+                    const int sh = ps < passes_slot ? ps * 8 : (ps - passes_slot) * 8;
+                    if (ps < passes_slot)
+                        radix_pass_global(ik, iv, ok, ov, mm, [sh](uint32_t, uint32_t v) { return (v >> sh) & 255u; }, cnt, wt);
+                    else
+                        radix_pass_global(ik, iv, ok, ov, mm, [sh](uint32_t k, uint32_t) { return ((~k) >> sh) & 255u; }, cnt, wt);
+                    const uint32_t *tk = ik, *tv = iv;
+                    ik = ok; iv = ov;
+                    ok = const_cast<uint32_t *>(tk); ov = const_cast<uint32_t *>(tv);
+                }
+                const uint32_t *sorted = iv;
+                const int lim = min(mm, n_limit - pos);
+                for (int piece = 0; piece < lim && kept < p.max_det; piece += kSortCap)
+                    process_sorted([&](int i) { return sorted[piece + i]; }, min(kSortCap, lim - piece), 0);
+                PROF_MARK(5);
+            }
+            // ---- replicate the new kept boxes and the verdict into the peers ----
+            if constexpr (CL > 1) {
+                __syncthreads();
+                for (int i = k0 + tid; i < kept; i += kNmsThreads) {
+                    const float4 kb4 = KEPT_BOX[i];
+                    const float ka1 = KEPT_AREA[i];
+                    for (int r2 = 1; r2 < CL; ++r2) {
+                        *cluster.map_shared_rank(&KEPT_BOX[i], r2) = kb4;
+                        *cluster.map_shared_rank(&KEPT_AREA[i], r2) = ka1;
+                    }
+                }
+                if (tid < CL) {
+                    int32_t *ctl = cluster.map_shared_rank(&S_MISC[kMCtl], tid);
+                    ctl[0] = action;
+                    ctl[1] = kept;
+                    ctl[2] = mm;
+                    ctl[3] = ss;
+                }
+            } else {
+                if (tid == 0) {
+                    S_MISC[kMCtl + 0] = action;
+                    S_MISC[kMCtl + 1] = kept;
+                    S_MISC[kMCtl + 2] = mm;
+                    S_MISC[kMCtl + 3] = ss;
+                }
+            }
+        }
+        cluster_sync();  // barrier #2
+        action = S_MISC[kMCtl + 0];
+        kept = S_MISC[kMCtl + 1];
+        m = S_MISC[kMCtl + 2];
+        s_all = S_MISC[kMCtl + 3];
+        par ^= 1;
+        PROF_MARK(9);
+        return action;
+    };
+
+    // Two levels of positions, both walked in descending score order with the same loop: the 4096 score buckets
+    // (S_BSTART: ESTIMATED ranks from K1's sampled histogram), and — when a single bucket holds more candidates than
+    // shared memory (clustered detections whose scores saturate in one 0.4 % wide bucket) — the 4096 sub-buckets of 8
+    // adjacent float values inside it (S_ZSTART: EXACT counts from one scan of the bucket).  Only a sub-bucket that still
+    // overflows (thousands of practically equal scores) takes the global radix sort.
+    bool zoom_on = false;
+    int zd = 0, z = 0;  // zoomed bucket (descending index) and position inside it
+    uint32_t z_lo = 0;  // smallest score bit pattern of the zoomed bucket
+    while (pos < n_limit && kept < p.max_det) {
+        if (zoom_on) {
+            if (z >= kBuckets || S_ZSTART[kBuckets] == S_ZSTART[z]) {  // bucket exhausted: back to the coarse walk
+                zoom_on = false;
+                d = zd + 1;
+                continue;
+            }
+        } else if (d >= kBuckets) {
+            break;
+        }
+        const int32_t *start = zoom_on ? S_ZSTART : S_BSTART;
+        const int from = zoom_on ? z : d;
+        // ---- next chunk: a run of whole (sub-)buckets [from, to) whose population (estimated / exact) fits the target ----
         if (tid == 0) {
             int target;
             if (pos == 0) {
@@ -685,206 +896,97 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 target = static_cast<int>(min(static_cast<long long>(CL) * (kShareCap * 3 / 4), max(768ll, want)));
             }
             if (careful) target = min(target, (kSortCap * 3) / 4);
-            const int base = S_BSTART[d];
-            int lo = d + 1, hi = kBuckets;
-            if (n_all - pos <= kSortCap) {
+            const int base = start[from];
+            const int rest = zoom_on ? start[kBuckets] - base : n_all - pos;  // exact in both cases
+            int lo = from + 1, hi = kBuckets;
+            if (rest <= kSortCap) {
                 lo = kBuckets;  // everything that is left fits shared memory: one chunk, no estimate needed
-            } else if (S_BSTART[lo] - base <= target) {
+            } else if (start[lo] - base <= target) {
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
-                    if (S_BSTART[mid] - base <= target) lo = mid; else hi = mid - 1;
+                    if (start[mid] - base <= target) lo = mid; else hi = mid - 1;
                 }
             }
             S_MISC[kMRunEnd] = lo;
         }
         __syncthreads();
-        int d1 = S_MISC[kMRunEnd];
-        int action = kActOk, m = 0;
-        for (;;) {  // attempt; a failed attempt (overflow / rank cut) changes d1 or `careful` and comes back here
-            const int k0 = kept;
-            ++st_coll;
-            __syncthreads();
-            if (tid == 0) { S_MISC[kMShareCnt] = 0; S_MISC[kMSurvCnt] = 0; }
-            if (tid < kShareCap / 32) S_DEADW[tid] = 0u;
-            __syncthreads();
-            // ---- collect this CTA's members of score buckets [kBuckets - d1, kBuckets - 1 - d] ----
-            {
-                const int b_lo = kBuckets - d1, b_hi = kBuckets - 1 - d;
-                const uint32_t lo_bits = bucket_floor_bits(b_lo);
-                const uint32_t hi_bits = b_hi >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_hi + 1) - 1u;
-                for_each_candidate_in(p.st, tcount, tmaxv, score, lo_bits, hi_bits, crank, CL, n_share, TILE_LIST, &S_MISC[kMListN],
-                                      [&](uint32_t slot, uint32_t bits) {
-                                          const int at = atomicAdd(&S_MISC[kMShareCnt], 1);  // members are rare (a few hundred per image)
-                                          if (at < kShareCap) PLIST[at] = (static_cast<unsigned long long>(bits) << 32) | (0xffffffffu - slot);
-                                      });
+        int to = S_MISC[kMRunEnd];
+        int action;
+        for (;;) {  // attempt; a failed attempt (overflow / rank cut) narrows [from, to) or sets `careful` and comes back here
+            uint32_t lo_bits, hi_bits;
+            int on_ovf = kActHalve;
+            if (zoom_on) {
+                lo_bits = z_lo + static_cast<uint32_t>(kBuckets - to) * kZoomSpan;
+                hi_bits = z_lo + static_cast<uint32_t>(kBuckets - from) * kZoomSpan - 1u;
+                if (to - from == 1) on_ovf = kActRadix;
+            } else {
+                const int b_lo = kBuckets - to, b_hi = kBuckets - 1 - from;
+                lo_bits = bucket_floor_bits(b_lo);
+                hi_bits = b_hi >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_hi + 1) - 1u;
+                // the clamped end buckets (everything below 2^-16, everything >= 1.0) have no fixed span to subdivide
+                if (to - from == 1) on_ovf = (b_hi >= 1 && b_hi < kBuckets - 1) ? kActZoom : kActRadix;
             }
-            __syncthreads();
-            PROF_MARK(1);
-            const int my_cnt = S_MISC[kMShareCnt];
-            const int my_n = min(my_cnt, kShareCap);
-            // ---- phase 1 on the share: members x kept[0, k0) ----
-            const bool do_p1 = k0 > 0 && !careful;
-            if (do_p1) {
-                for (int base = 0; base < my_n; base += kNmsThreads) {
-                    const int nb = min(kNmsThreads, my_n - base);
-                    int sub_p2 = 64;
-                    while (sub_p2 < nb) sub_p2 <<= 1;
-                    const int ci = tid & (sub_p2 - 1), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
-                    bool dead = false;
-                    if (ci < nb) {
-                        const uint32_t slot = 0xffffffffu - static_cast<uint32_t>(PLIST[base + ci]);
-                        const float4 ob = offset_box(slot);
-                        dead = killed_by_kept(ob, box_area_rn(ob), 0, k0, part, nparts);
-                    }
-                    const uint32_t bal = __ballot_sync(0xffffffffu, dead);  // a warp = 32 consecutive members, one part
-                    if (lane == 0 && bal) atomicOr(&S_DEADW[(base + ci) >> 5], bal);
-                }
-                st_pairs += static_cast<long long>(my_n) * k0;
-                __syncthreads();
-                for (int i0 = warp * 32; i0 < my_n; i0 += kNmsThreads) {  // unordered compaction (the survivors get sorted anyway)
-                    const int i = i0 + lane;
-                    const bool alive = i < my_n && !((S_DEADW[i >> 5] >> (i & 31)) & 1u);
-                    const uint32_t bal = __ballot_sync(0xffffffffu, alive);
-                    int at = 0;
-                    if (lane == 0 && bal) at = atomicAdd(&S_MISC[kMSurvCnt], __popc(bal));
-                    at = __shfl_sync(0xffffffffu, at, 0);
-                    if (alive) SURV[at + __popc(bal & lanemask_lt())] = PLIST[i];
-                }
-                __syncthreads();
-            }
-            PROF_MARK(2);
-            const unsigned long long *mine = do_p1 ? SURV : PLIST;
-            const int s_cnt = do_p1 ? S_MISC[kMSurvCnt] : my_n;
-            // ---- survivors -> master (offset from a remote atomic on the master's counters) ----
-            int32_t *ctr = &S_MISC[kMCtr + par * 4];
-            if constexpr (CL > 1) ctr = cluster.map_shared_rank(&S_MISC[kMCtr + par * 4], 0);
-            if (tid == 0) {
-                atomicAdd(ctr + 0, my_cnt);
-                S_MISC[kMOff] = atomicAdd(ctr + 1, s_cnt);
-                if (my_cnt > kShareCap) atomicOr(ctr + 2, 1);
-            }
-            __syncthreads();
-            {
-                const int off = S_MISC[kMOff];
-                unsigned long long *dst = SKEY;
-                if constexpr (CL > 1) dst = cluster.map_shared_rank(SKEY, 0);
-                for (int i = tid; i < s_cnt; i += kNmsThreads)
-                    if (off + i < kSortCap) dst[off + i] = mine[i];
-            }
-            cluster_sync();  // barrier #1
-            PROF_MARK(3);
-            if (crank == 0) {
-                m = S_MISC[kMCtr + par * 4 + 0];
-                const int s_all = S_MISC[kMCtr + par * 4 + 1];
-                const bool share_ovf = S_MISC[kMCtr + par * 4 + 2] != 0;
-                if (share_ovf || s_all > kSortCap) action = (d1 - d == 1) ? kActRadix : kActHalve;
-                else if (!careful && k0 > 0 && pos + m > n_limit) action = kActCareful;  // crosses the rank cut: ranks need every member
-                else action = kActOk;
-                __syncthreads();
-                if (tid < 4) S_MISC[kMCtr + (par ^ 1) * 4 + tid] = 0;  // the other bank is idle until the next round
-                if (action == kActOk) {
-                    if (s_all > 0) {
-                        int lpw = 6;
-                        while ((1 << lpw) < s_all) ++lpw;
-                        for (int i = s_all + tid; i < (1 << lpw); i += kNmsThreads) SKEY[i] = 0ull;
-                        __syncthreads();
-                        bitonic_sort_desc(SKEY, lpw);
-                        PROF_MARK(4);
-                        // without a preceding phase 1 (first chunk, careful redo) the sorted list holds every member, so
-                        // the rank cut applies directly; after phase 1 the whole chunk is known to lie above the cut
-                        const int cnt = do_p1 ? s_all : min(s_all, n_limit - pos);
-                        process_sorted([&](int i) { return 0xffffffffu - static_cast<uint32_t>(SKEY[i]); }, cnt, do_p1 ? k0 : 0);
-                    }
-                } else if (action == kActRadix) {
-                    // ---- a single bucket larger than shared memory: collect to global scratch, stable LSD radix sort
-                    //      on (score bits desc, slot asc), then stream it through the suppression phases (rare path) ----
-                    uint32_t *ka = p.tmp_key_a + seg, *va = p.tmp_val_a + seg, *kb = p.tmp_key_b + seg, *vb = p.tmp_val_b + seg;
-                    const int b_one = kBuckets - 1 - d;
-                    const uint32_t *ik = ka, *iv = va;
-                    uint32_t *ok = kb, *ov = vb;
-                    int slot_bits = 1;
-                    while ((static_cast<int64_t>(1) << slot_bits) < p.st.cap) ++slot_bits;
-                    const int passes_slot = (slot_bits + 7) / 8;
-                    __syncthreads();
-                    if (tid == 0) S_MISC[kMShareCnt] = 0;
-                    __syncthreads();
-                    for_each_candidate_in(p.st, tcount, tmaxv, score, bucket_floor_bits(b_one),
-                                          b_one >= kBuckets - 1 ? 0xffffffffu : bucket_floor_bits(b_one + 1) - 1u, 0, 1, p.st.tpi,
-                                          TILE_LIST, &S_MISC[kMListN], [&](uint32_t slot, uint32_t bits) {
-                                              const int at = atomicAdd(&S_MISC[kMShareCnt], 1);
-                                              ka[at] = bits;
-                                              va[at] = slot;
-                                          });
-                    __syncthreads();
-                    int *cnt = reinterpret_cast<int *>(dyn + L::plist);  // aliases plist|surv|skey
-                    int *wt = S_MISC + kMWarp;
-                    for (int ps = 0; ps < passes_slot + 4; ++ps) {
-                        const int sh = ps < passes_slot ? ps * 8 : (ps - passes_slot) * 8;
-                        if (ps < passes_slot)
-                            radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t, uint32_t v) { return (v >> sh) & 255u; }, cnt, wt);
-                        else
-                            radix_pass_global(ik, iv, ok, ov, m, [sh](uint32_t k, uint32_t) { return ((~k) >> sh) & 255u; }, cnt, wt);
-                        const uint32_t *tk = ik, *tv = iv;
-                        ik = ok; iv = ov;
-                        ok = const_cast<uint32_t *>(tk); ov = const_cast<uint32_t *>(tv);
-                    }
-                    const uint32_t *sorted = iv;
-                    const int lim = min(m, n_limit - pos);
-                    for (int piece = 0; piece < lim && kept < p.max_det; piece += kSortCap)
-                        process_sorted([&](int i) { return sorted[piece + i]; }, min(kSortCap, lim - piece), 0);
-                }
-                // ---- replicate the new kept boxes and the verdict into the peers ----
-                if constexpr (CL > 1) {
-                    __syncthreads();
-                    for (int i = k0 + tid; i < kept; i += kNmsThreads) {
-                        const float4 kb4 = KEPT_BOX[i];
-                        const float ka1 = KEPT_AREA[i];
-                        for (int r2 = 1; r2 < CL; ++r2) {
-                            *cluster.map_shared_rank(&KEPT_BOX[i], r2) = kb4;
-                            *cluster.map_shared_rank(&KEPT_AREA[i], r2) = ka1;
-                        }
-                    }
-                    if (tid < CL) {
-                        int32_t *ctl = cluster.map_shared_rank(&S_MISC[kMCtl], tid);
-                        ctl[0] = action;
-                        ctl[1] = kept;
-                        ctl[2] = m;
-                        ctl[3] = s_all;
-                    }
-                } else {
-                    if (tid == 0) {
-                        S_MISC[kMCtl + 0] = action;
-                        S_MISC[kMCtl + 1] = kept;
-                        S_MISC[kMCtl + 2] = m;
-                        S_MISC[kMCtl + 3] = s_all;
-                    }
-                }
-            }
-            cluster_sync();  // barrier #2
-            action = S_MISC[kMCtl + 0];
-            kept = S_MISC[kMCtl + 1];
-            m = S_MISC[kMCtl + 2];
-            const int s_all = S_MISC[kMCtl + 3];
-            par ^= 1;
-            PROF_MARK(9);
+            action = attempt(lo_bits, hi_bits, on_ovf);
             if (action == kActHalve) {
-                d1 = d + (d1 - d) / 2;
+                to = from + (to - from) / 2;
                 continue;
             }
             if (action == kActCareful) {
                 careful = true;
-                if (m > (kSortCap * 3) / 4 && d1 - d > 1) d1 = d + max(1, (d1 - d) * ((kSortCap * 3) / 4) / m);
+                if (m > (kSortCap * 3) / 4 && to - from > 1) to = from + max(1, (to - from) * ((kSortCap * 3) / 4) / m);
                 continue;
             }
-            if (action == kActOk && do_p1) {
+            if (action == kActOk && last_p1) {
                 last_m = max(m, 1);
                 last_s = max(s_all, 1);
             }
             break;
         }
         careful = false;
+        if (action == kActZoom) {
+            // ---- exact histogram of the bucket's sub-buckets (descending), every CTA of the cluster for itself ----
+            zd = from;
+            z_lo = bucket_floor_bits(kBuckets - 1 - from);
+            for (int i = tid; i <= kBuckets; i += kNmsThreads) S_ZSTART[i] = 0;
+            __syncthreads();
+            for_each_candidate_in(p.st, tcount, tmaxv, score, z_lo, z_lo + (static_cast<uint32_t>(kBuckets) * kZoomSpan - 1u), 0, 1, p.st.tpi,
+                                  TILE_LIST, &S_MISC[kMListN], [&](uint32_t, uint32_t bits) {
+                                      atomicAdd(&S_ZSTART[kBuckets - 1 - static_cast<int>((bits - z_lo) / kZoomSpan)], 1);
+                                  });
+            __syncthreads();
+            {
+                constexpr int kPer = kBuckets / kNmsThreads;
+                int loc[kPer], sum = 0;
+#pragma unroll
+                for (int i = 0; i < kPer; ++i) {
+                    loc[i] = S_ZSTART[tid * kPer + i];
+                    sum += loc[i];
+                }
+                int inc = sum;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, inc, dd);
+                    if (lane >= dd) inc += v;
+                }
+                if (lane == 31) S_MISC[kMWarp + warp] = inc;
+                __syncthreads();
+                int run = inc - sum;
+                for (int w = 0; w < warp; ++w) run += S_MISC[kMWarp + w];
+#pragma unroll
+                for (int i = 0; i < kPer; ++i) {
+                    S_ZSTART[tid * kPer + i] = run;
+                    run += loc[i];
+                }
+                if (tid == kNmsThreads - 1) S_ZSTART[kBuckets] = run;
+                __syncthreads();
+            }
+            zoom_on = true;
+            z = 0;
+            PROF_MARK(6);
+            continue;
+        }
         pos += m;
-        d = d1;
+        if (zoom_on) z = to; else d = to;
     }
     // ---- publish (master CTA) ----
     __syncthreads();
@@ -918,6 +1020,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #undef S_DEAD
 #undef S_DEADW
 #undef S_MISC
+#undef S_ZSTART
 #undef KEPT_BOX
 #undef KEPT_AREA
 #undef KEPT_SLOT

@@ -395,6 +395,10 @@ def non_max_suppression(
     dev = pred.device
     if bs == 0 or na == 0:
         empty = [torch.zeros((0, 6 + nm), device=dev)] * bs
+        if results_state_cols is not None:
+            s_ = int(results_state_cols)
+            empty = ([torch.zeros((0, 7 if s_ else 6), device=dev)] * bs, [torch.zeros((0, nm - s_), device=dev)] * bs)
+            return empty + ([torch.zeros((0,), dtype=torch.int32, device=dev)] * bs,) if return_index else empty
         return (empty, [torch.zeros((0,), dtype=torch.int32, device=dev)] * bs) if return_index else empty
 
     params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)

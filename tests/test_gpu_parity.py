@@ -622,6 +622,35 @@ def test_borderline_iou_both_directions(sarpost, cuda):
         assert rows[0].shape[0] == expect
 
 
+@pytest.mark.parametrize("spread_ulps,batch", [(20000, 1), (20000, 5), (60000, 40), (6, 2)])
+@pytest.mark.parametrize("cluster", ["", "1", "8"])
+def test_one_score_bucket_holds_thousands(sarpost, cuda, monkeypatch, spread_ulps, batch, cluster):
+    """Saturated scores (clustered detections): thousands of DISTINCT scores inside one 0.4 %-wide score bucket.  The NMS
+    kernel then zooms into the bucket (exact histogram over sub-buckets of 8 adjacent floats) instead of sorting it in
+    global memory; with `spread_ulps` = 6 nearly everything shares one sub-bucket and the radix fallback has to finish.
+    299 far-apart clusters of near-duplicates keep the walk going through all max_nms candidates."""
+    if cluster:
+        monkeypatch.setenv("SARPOST_NMS_CLUSTER", cluster)
+    a, k = 9000, 120
+    g = torch.Generator().manual_seed(spread_ulps + batch)
+    cx = (torch.arange(k) % 12) * 60.0 + 40
+    cy = (torch.arange(k) // 12) * 80.0 + 40
+    y = torch.zeros(batch, 5, a)
+    for b in range(batch):
+        pick = torch.randint(0, k, (a,), generator=g)
+        y[b, 0] = cx[pick] + torch.randn(a, generator=g) * 0.5
+        y[b, 1] = cy[pick] + torch.randn(a, generator=g) * 0.5
+        y[b, 2:4] = 30.0
+        base = torch.tensor(0.99).view(torch.int32)  # bit pattern of 0.99: consecutive patterns = consecutive floats
+        ulps = torch.randint(0, spread_ulps, (a,), generator=g, dtype=torch.int32)
+        y[b, 4] = (base + ulps).view(torch.float32)
+        y[b, 4, : a // 10] = torch.rand(a // 10, generator=g) * 0.9 + 0.05  # plus ordinary scores in the other buckets
+    kw = dict(conf_thres=0.001, iou_thres=0.5, max_nms=8000)
+    rows, idx, ref_rows, ref_idx = _nms_both(sarpost, y, cuda, **kw)
+    _assert_same(rows, idx, ref_rows, ref_idx, 1)
+    assert all(r.shape[0] <= k for r in rows) and rows[0].shape[0] > k // 2
+
+
 def test_seeded_fuzz(sarpost, cuda):
     """150 random configurations (decoded / fused, fp32 / fp16, ties, clustered boxes, odd shapes, extreme
     thresholds) against the oracle; `python tools/fuzz_parity.py 2000 <seed>` runs more."""

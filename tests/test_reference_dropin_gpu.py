@@ -25,7 +25,8 @@ def test_real_predict_under_all_patch_modes(cuda):
     assert lines, res.stdout[-1500:] + res.stderr[-3000:]
     rep = json.loads(lines[-1])
     assert res.returncode == 0 and rep.get("ok"), json.dumps(rep, indent=1) + res.stderr[-2000:]
-    for name in ("patch", "patch_fused", "patch_fused_split", "patch_fused_split_nchw_emb", "patch_fused_defer_state"):
+    for name in ("patch", "patch_fused", "patch_fused_split", "patch_fused_split_nchw_emb", "patch_fused_predictor", "patch_fused_defer_state",
+                 "patch_fused_defer_state_predictor"):
         assert rep["runs"][name]["ok"], rep["runs"][name]
         assert rep["runs"][name]["box_columns"] == 7 and sum(rep["runs"][name]["detections"]) > 0
     assert rep["runs"]["patch_fused_defer_state"]["levels_channels"] == 64 + 1 + 256  # the state MLP really was skipped in the forward

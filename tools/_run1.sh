@@ -1,6 +1,6 @@
-mkdir -p gpurun_out/r2d
-python -m pytest tests -m gpu -q -x > gpurun_out/r2d/pytest.log 2>&1; echo pytest rc=$?; tail -4 gpurun_out/r2d/pytest.log
-for cl in 0 1 2 4; do echo "== CL $cl random"; SARPOST_NMS_CLUSTER=$cl SARPOST_LIB_PATH=$PWD/sar-yolo_b200/libsarpost_prof.so python tools/phase_prof.py cfg3 0; done > gpurun_out/r2d/phase_random.txt 2>&1
-for cl in 0 1 8; do echo "== CL $cl blobs"; SARPOST_NMS_CLUSTER=$cl SARPOST_LIB_PATH=$PWD/sar-yolo_b200/libsarpost_prof.so python tools/phase_prof.py cfg3 50; done > gpurun_out/r2d/phase_blobs.txt 2>&1
-cat gpurun_out/r2d/phase_random.txt
-python tools/fuzz_parity.py 300 > gpurun_out/r2d/fuzz.txt 2>&1; tail -2 gpurun_out/r2d/fuzz.txt
+mkdir -p gpurun_out/r2g
+for cfg in "3 2" "2 2" "2 3" "1 4" "1 6" "4 1"; do set -- $cfg; echo "== K1 ctas=$1 stages=$2"; SARPOST_K1_CTAS=$1 SARPOST_K1_STAGES=$2 python bench.py --quick --steps 200 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('value %.0f single %.0f  ms %.4f single_ms %.4f stage %s' % (d['value'], d['single_stream']['value'], d['ms_per_step'], d['single_stream']['ms_per_step'], {k:round(v,4) for k,v in d['roofline']['stage_ms'].items()}))
+"; done 2>&1 | tee gpurun_out/r2g/k1_sweep.txt

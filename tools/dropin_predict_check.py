@@ -8,7 +8,8 @@ container).  What it does:
   * a forward pre-hook feeds the JDE head seeded N(0,1) feature maps (the untrained trunk kills the signal)
     and the class bias is shifted so scores spread over (0.05, 0.9); a forward hook captures the raw per-level logits the
     head returns next to `y`;
-  * runs `model.predict([ndarray, ...])` six times: reference as is (torch CUDA ops + torchvision CUDA NMS), then under
+  * runs `model.predict([ndarray, ...])` eight times (the last two modes also with `predictor=True`: JDEPredictor.postprocess
+    replaced by one fused call whose gather kernel writes the 7-column boxes and the embeddings): reference as is (torch CUDA ops + torchvision CUDA NMS), then under
     `patch()` (API-exact decode + NMS kernels), `patch(fused=True)` (LazyPrediction -> fused kernels),
     `patch(fused=True, split=True)` with a channels_last and with an NCHW embedding branch (no torch.cat in the head) and
     `patch(fused=True, defer_state=True)` (state MLP on the kept rows only);
@@ -135,16 +136,19 @@ def main():
     fused_res = None
     for name, mode in (("patch", {}), ("patch_fused", dict(fused=True)), ("patch_fused_split", dict(fused=True, split=True)),
                        ("patch_fused_split_nchw_emb", dict(fused=True, split=True, emb_channels_last=False)),
-                       ("patch_fused_defer_state", dict(fused=True, defer_state=True))):
+                       ("patch_fused_predictor", dict(fused=True, split=True, predictor=True)),
+                       ("patch_fused_defer_state", dict(fused=True, defer_state=True)),
+                       ("patch_fused_defer_state_predictor", dict(fused=True, defer_state=True, predictor=True))):
         sarpost.patch(**mode)
         try:
             res, levels = run()
             was_split = captured.pop("split", False)
+            launches = sarpost.ops.last_launch_count()
         finally:
             sarpost.unpatch()
         exp = expected(levels)
         entry = {"detections": [int(x[0].shape[0]) for x in res], "box_columns": int(res[0][0].shape[1]) if res else None,
-                 "head_returned_split_levels": bool(was_split)}
+                 "head_returned_split_levels": bool(was_split), "launches_of_last_library_call": int(launches)}
         if exp is not None:
             b, t = diff(res, exp)
             entry["vs_cpu_oracle"] = {"mismatch": b, "of": t}
