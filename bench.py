@@ -17,8 +17,9 @@ the one real exchange of the path (sliced inference: tiles of a frame on differe
 Keys of the JSON line beyond the contract:
   single_stream   the same K steps strictly one batch in flight
   roofline        K1 (fused decode) algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json
-  split_layout    the same batches handed over as separate branch tensors (no torch.cat in front of the decode kernel,
-                  channels_last embedding): what `patch(fused=True, split=True)` feeds the kernels
+  two_streams     the same K steps round-robin on two independent streams (plain sarpost_fused calls)
+  cat_layout      the same passes on the concatenated (B, no, H, W) level tensors (the headline input is the split layout:
+                  separate branch tensors, channels_last embedding — what `patch(fused=True, split=True)` feeds the kernels)
   clustered       the same shapes/thresholds on inputs whose class logits carry 50 Gaussian blobs per image: neighbouring
                   anchors fire together and overlap, so NMS has to suppress (the regime of a trained detector)
   reference_gpu   the reference's own path as a `device=0` user runs it on this GPU: JDE._inference (torch CUDA ops) +
@@ -384,11 +385,16 @@ def count_candidates(torch, levels, nc, kw):
     return n
 
 
-def leg_clustered(cx, spec, shapes, nc, ed, sc, bs, kw, cls_mean, steps):
+def leg_clustered(cx, spec, shapes, nc, ed, sc, bs, kw, cls_mean, steps, use_split=True):
     """Shapes / thresholds of the main workload on clustered inputs (synth.head_outputs(blobs=50)): the NMS kernel
     has to walk deep into the sorted candidates because most of them are suppressed."""
     torch, sarpost = cx.torch, cx.sarpost
-    levels = sarpost.synth.head_outputs(bs, shapes, nc, ed, sc, cls_mean=cls_mean, seed=3500 + cx.rank, device=cx.dev, blobs=50)
+    sets = []
+    for i in range(2):
+        lv = sarpost.synth.head_outputs(bs, shapes, nc, ed, sc, cls_mean=cls_mean, seed=3500 + cx.rank + 100 * i, device=cx.dev, blobs=50)
+        sets.append(sarpost.split_levels(lv, spec, emb_channels_last=True) if use_split else lv)
+        del lv
+    levels = sets[0]
     stats = torch.zeros((bs, 4), dtype=torch.int64, device=cx.dev)
 
     def step():
@@ -400,51 +406,36 @@ def leg_clustered(cx, spec, shapes, nc, ed, sc, bs, kw, cls_mean, steps):
     st = stage_means(cx, step, min(steps, 50))
     sarpost.postprocess_fused(levels, spec, return_padded=True, nms_stats=stats, **kw)
     torch.cuda.synchronize()
-    (ms,) = cx.max_over_ranks(ms)
+    # the same steps through the software pipeline (two input sets alternating)
+    pl = sarpost.Pipeline(cx.dev, depth=2)
+    ring = [(torch.empty((bs, kw["max_det"], 6 + spec.nm), dtype=torch.float32, device=cx.dev), torch.empty((bs,), dtype=torch.int32, device=cx.dev))
+            for _ in range(4)]
+    for i in range(4):
+        pl.submit(sets[i % 2], spec, out=ring[i % 4], **kw)
+    pl.wait()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cx.barrier()
+    ev0.record()
+    for i in range(steps):
+        pl.submit(sets[i % 2], spec, out=ring[i % 4], **kw)
+    pl.wait()
+    ev1.record()
+    cx.barrier()
+    ms_pipe = ev0.elapsed_time(ev1)
+    pl.close()
+    ms, ms_pipe = cx.max_over_ranks(ms, ms_pipe)
     s = stats.double().mean(0).tolist()
-    return {"value": bs * cx.world * steps / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / steps, "steps": steps,
+    return {"value": bs * cx.world * steps / (ms_pipe / 1e3), "unit": "images/s", "ms_per_step": ms_pipe / steps, "steps": steps,
+            "single_stream": {"value": bs * cx.world * steps / (ms / 1e3), "ms_per_step": ms / steps},
             "k1_ms": st[0], "k4_ms": st[1], "k5_ms": st[2],
             "keeps_depth": s[0], "pair_tests": s[1], "sub_chunks": s[2], "collections": s[3],
             "detections_per_image": float(counts.sum().item()) / bs,
             "input": "synth.head_outputs(blobs=50): 50 Gaussian bumps (+6 logit) per image and level on the class logits, box logits of "
-                     "fired anchors pulled to a common shape so neighbours overlap; one batch in flight",
+                     "fired anchors pulled to a common shape so neighbours overlap; `value` = software pipeline like the headline, "
+                     "`single_stream` / k*_ms = one batch in flight",
             "note": "per image means on rank 0: keeps_depth = sorted candidates NMS consumed before it had max_det keeps (or ran out), "
                     "pair_tests = IoU tests executed, sub_chunks / collections = passes of the NMS / selection loops"}
-
-
-def leg_split(cx, level_sets, spec, bs, kw, steps, streams_n):
-    """The same batches in the split layout (SARPOST_LAYOUT_SPLIT): box / class / embedding / state branch outputs as separate
-    tensors — what `patch(fused=True, split=True)` hands over instead of the per-level torch.cat of head.py:204-206 — with the
-    embedding channels_last.  Same values as the concatenated inputs (built from them), rows checked identical."""
-    torch, sarpost = cx.torch, cx.sarpost
-    split_sets = [sarpost.split_levels(lv, spec, emb_channels_last=True) for lv in level_sets]
-    nxt = rotating(split_sets)
-
-    def step():
-        return sarpost.postprocess_fused(nxt(), spec, return_padded=True, **kw)
-
-    for _ in range(3):
-        step()
-    o_s, c_s = sarpost.postprocess_fused(split_sets[0], spec, return_padded=True, **kw)
-    o_c, c_c = sarpost.postprocess_fused(level_sets[0], spec, return_padded=True, **kw)
-    same = bool(torch.equal(c_s, c_c)) and all(bool(torch.equal(o_s[b, :n], o_c[b, :n])) for b, n in enumerate(c_c.tolist()))
-    ms1 = time_steps(cx, step, steps)
-    ms = ms1
-    if streams_n > 1:
-        streams = [torch.cuda.Stream() for _ in range(streams_n)]
-        for s_ in streams:
-            with torch.cuda.stream(s_):
-                for _ in range(3):
-                    step()
-        ms = time_steps(cx, step, steps, streams)
-    st = stage_means(cx, step, min(steps, 100))
-    ms, ms1 = cx.max_over_ranks(ms, ms1)
-    return {"value": bs * cx.world * steps / (ms / 1e3), "unit": "images/s", "ms_per_step": ms / steps,
-            "single_stream": {"value": bs * cx.world * steps / (ms1 / 1e3), "ms_per_step": ms1 / steps},
-            "stage_ms": {"k1_candidates": st[0], "k2_k4_select_sort_nms": st[1], "k5_gather": st[2], "whole_call": st[3]},
-            "rows_identical_to_concatenated_layout": same, "steps": steps,
-            "layout": "per level: box (B,64,H,W), cls (B,nc,H,W), emb (B,H,W,E) channels_last, state (B,S,H,W); same values as the "
-                      "concatenated (B,no,H,W) inputs of `value`"}
 
 
 def leg_reference_gpu(cx, levels, strides, nc, ed, sc, kw, n_img, reps, our_rows):
@@ -728,36 +719,98 @@ def main():
     n_sets = 1 if hot_bytes >= 2 * L2_BYTES else min(int(math.ceil(2 * L2_BYTES / hot_bytes)), 128)
     n_sets = max(n_sets, args.streams)
     level_sets = [levels] + [[x.clone() for x in levels] for _ in range(n_sets - 1)]
-    next_levels = rotating(level_sets)
+    # The same values in the split layout (SARPOST_LAYOUT_SPLIT): box / class / embedding / state branch outputs as separate
+    # tensors, embedding channels_last — what `patch(fused=True, split=True)` hands over instead of the per-level torch.cat
+    # of head.py:204-206.  This is the headline layout (the reference legs are fed the concatenated tensors holding the same
+    # numbers); the concatenated layout is measured too (`cat_layout`).
+    use_split = not args.no_split
+    split_sets = [sarpost.split_levels(lv, spec, emb_channels_last=True) for lv in level_sets] if use_split else None
 
-    def step():
-        return sarpost.postprocess_fused(next_levels(), spec, return_padded=True, **kw)
+    def measure_layout(sets, steps, with_stage_steps):
+        """single stream / two plain streams / software pipeline over the same K steps; per-kernel event pass."""
+        nxt = rotating(sets)
 
-    for _ in range(max(args.warmup, 3)):
-        out, counts = step()
-    cx.barrier()
-    launches_per_step = sarpost.ops.last_launch_count()
+        def step():
+            return sarpost.postprocess_fused(nxt(), spec, return_padded=True, **kw)
+
+        for _ in range(max(args.warmup, 3)):
+            o_, c_ = step()
+        cx.barrier()
+        res = {"launches_per_step": sarpost.ops.last_launch_count(), "counts": c_}
+        # (a) strictly one batch in flight: K steps back to back on the current stream
+        res["ms_single"] = time_steps(cx, step, steps)
+        res["ms_two"] = res["ms_pipe"] = None
+        res["pipe_same"] = None
+        if args.streams > 1:
+            # (b) the same K steps issued round-robin on independent streams (plain sarpost_fused calls): the tails of two
+            # batches run side by side, but each still queues behind the other batch's decode kernel
+            streams = [torch.cuda.Stream() for _ in range(args.streams)]
+            for s_ in streams:  # warm up each stream (workspace per stream)
+                with torch.cuda.stream(s_):
+                    for _ in range(3):
+                        step()
+            res["ms_two"] = time_steps(cx, step, steps, streams)
+            # (c) software pipeline (sarpost_pipeline_*): the same K steps submitted back to back; batch i on stream i % 2, its
+            # decode kernel chained to the previous batch's decode kernel, so NMS + gather of batch i run under the decode of
+            # batch i+1.  Outputs rotate over 4 preallocated sets (a serving loop consumes set i while i+1.. are in flight).
+            pl = sarpost.Pipeline(dev, depth=2)
+            out_ring = [(torch.empty((bs, kw["max_det"], 6 + spec.nm), dtype=torch.float32, device=dev),
+                         torch.empty((bs,), dtype=torch.int32, device=dev)) for _ in range(4)]
+            pk = [0]
+
+            def pstep():
+                pk[0] += 1
+                return pl.submit(nxt(), spec, out=out_ring[pk[0] % len(out_ring)], **kw)
+
+            for _ in range(4):
+                pstep()
+            pl.wait()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            cx.barrier()
+            ev0.record()
+            for _ in range(steps):
+                pstep()
+            pl.wait()  # the launching stream waits (device side) for every submitted batch
+            ev1.record()
+            cx.barrier()
+            res["ms_pipe"] = ev0.elapsed_time(ev1)
+            res["launches_per_step_pipelined"] = sarpost.ops.last_launch_count()
+            p_out, p_counts = pl.submit(sets[0], spec, **kw)
+            pl.wait()
+            torch.cuda.synchronize()
+            o_ref, c_ref = sarpost.postprocess_fused(sets[0], spec, return_padded=True, **kw)
+            res["pipe_same"] = bool(torch.equal(p_counts, c_ref)) and all(bool(torch.equal(p_out[b, :n], o_ref[b, :n])) for b, n in enumerate(c_ref.tolist()))
+            pl.close()
+            del out_ring
+        # pass over the same steps with CUDA events around every kernel (recorded by the library on the launching stream, no
+        # host sync per step, mean read afterwards).  Kept out of the passes `value` comes from: timing events between
+        # kernels cost a few % by removing the overlap of consecutive launches.
+        res["stage"] = stage_means(cx, step, with_stage_steps)
+        res["step"] = step
+        return res
+
+    def summarize(res, steps):
+        vals = cx.max_over_ranks(res["ms_single"], res["ms_two"] or 0.0, res["ms_pipe"] or 0.0)
+        rate = lambda ms_: bs * n_gpus * steps / (ms_ / 1e3)  # noqa: E731
+        out_ = {"single_stream": {"value": rate(vals[0]), "unit": "images/s", "ms_per_step": vals[0] / steps,
+                                  "note": "strictly one batch in flight (all K steps on one stream)"}}
+        if res["ms_two"] is not None:
+            out_["two_streams"] = {"value": rate(vals[1]), "unit": "images/s", "ms_per_step": vals[1] / steps,
+                                   "note": f"the same K steps issued round-robin on {args.streams} independent CUDA streams through sarpost_fused"}
+            out_["pipelined"] = {"value": rate(vals[2]), "unit": "images/s", "ms_per_step": vals[2] / steps,
+                                 "rows_identical_to_plain_call": res["pipe_same"],
+                                 "note": "sarpost_pipeline_submit per step (depth 2), one sarpost_pipeline_wait at the end"}
+        st_ = res["stage"]
+        out_["stage_ms"] = {"k1_candidates": st_[0], "k2_k4_select_sort_nms": st_[1], "k5_gather": st_[2], "whole_call": st_[3]}
+        return out_
 
     # ---- timed region: K steps, CUDA events on the launching (current) stream ----
     clocks = ClockSampler(cx.local)
     clocks.start()
-    # (a) strictly one batch in flight: K steps back to back on the current stream
-    ms_single = time_steps(cx, step, args.steps)
-    ms = ms_single
-    if args.streams > 1:
-        # (b) the same K steps issued round-robin on several streams: independent batches, each stream with its own
-        # copy of the inputs and its own workspace; the NMS kernel of one batch (few SMs, latency-bound) overlaps
-        # the fused decode of the next (HBM-bound).  Every step still does the whole path for one batch.
-        streams = [torch.cuda.Stream() for _ in range(args.streams)]
-        for s_ in streams:  # warm up each stream (workspace per stream)
-            with torch.cuda.stream(s_):
-                for _ in range(3):
-                    step()
-        ms = time_steps(cx, step, args.steps, streams)
-    # second pass over the same K steps with CUDA events around every kernel (recorded by the library on the
-    # launching stream, no host sync per step, mean read afterwards).  Kept out of the pass `value` comes from:
-    # timing events between kernels cost ~8 % throughput by removing the overlap of consecutive launches.
-    stage = stage_means(cx, step, 3 if args.quick else args.steps)
+    head_sets = split_sets if use_split else level_sets
+    main = measure_layout(head_sets, args.steps, 3 if args.quick else args.steps)
+    step, counts, stage = main["step"], main["counts"], main["stage"]
     if len(clocks.samples) < 20 and not args.quick:  # short region: keep sampling over the same step to have clocks under load
         t_end = time.perf_counter() + 1.0
         while time.perf_counter() < t_end:
@@ -765,11 +818,26 @@ def main():
                 step()
             torch.cuda.synchronize()
     clocks.stop()
-    ms, ms_single = cx.max_over_ranks(ms, ms_single)
-    value = bs * n_gpus * args.steps / (ms / 1e3)
-    single = {"value": bs * n_gpus * args.steps / (ms_single / 1e3), "unit": "images/s", "ms_per_step": ms_single / args.steps,
-              "note": "strictly one batch in flight (all K steps on one stream)"}
+    main_sum = summarize(main, args.steps)
+    best = main_sum.get("pipelined") or main_sum["single_stream"]
+    value, ms = best["value"], best["ms_per_step"] * args.steps
+    single, two_streams = main_sum["single_stream"], main_sum.get("two_streams")
+    launches_per_step = main.get("launches_per_step_pipelined") or main["launches_per_step"]
+    pipe_same_main = main["pipe_same"]
     n_det = int(counts.sum().item())
+    # the concatenated layout (one (B, no, H, W) tensor per level, as the unpatched head returns them), same passes
+    cat_layout = None
+    if use_split and not args.quick:
+        cat_steps = max(10, min(args.steps, 200))
+        cat = measure_layout(level_sets, cat_steps, min(cat_steps, 100))
+        cat_layout = summarize(cat, cat_steps)
+        o_s, c_s = sarpost.postprocess_fused(split_sets[0], spec, return_padded=True, **kw)
+        o_c, c_c = sarpost.postprocess_fused(level_sets[0], spec, return_padded=True, **kw)
+        cat_layout["rows_identical_to_split_layout"] = bool(torch.equal(c_s, c_c)) and all(
+            bool(torch.equal(o_s[b, :n], o_c[b, :n])) for b, n in enumerate(c_c.tolist()))
+        cat_layout["steps"] = cat_steps
+        cat_layout["layout"] = "per level one (B, no, H, W) tensor: box | cls | emb | state concatenated (head.py:204-206)"
+        del cat
 
     # ---- K1 roofline from the evented pass ----
     n_cand = count_candidates(torch, levels, nc, kw)
@@ -793,15 +861,10 @@ def main():
         except Exception:
             pass
 
-    # ---- split layout (no torch.cat in front of K1, channels_last embedding) ----
-    split = None
-    if not args.no_split and not args.blobs:
-        split = leg_split(cx, level_sets, spec, bs, kw, max(10, min(args.steps, 200)), args.streams)
-
     # ---- clustered leg (same shapes / thresholds, suppression-heavy inputs) ----
     clustered = None
     if not args.no_clustered and not args.blobs:
-        clustered = leg_clustered(cx, spec, shapes, nc, ed, sc, bs, kw, cls_mean, max(10, min(args.steps, 100)))
+        clustered = leg_clustered(cx, spec, shapes, nc, ed, sc, bs, kw, cls_mean, max(10, min(args.steps, 100)), use_split)
 
     # ---- the reference's own GPU path on the same box (rank 0, N = 1 only) ----
     ref_gpu = None
@@ -833,7 +896,7 @@ def main():
     # ---- sliced inference (cfg4): the one exchange step of the path, measured whenever there is more than one rank ----
     sahi = None
     if world > 1 and not args.no_sahi:
-        del next_levels, levels, level_sets
+        del levels, level_sets, split_sets, head_sets, main, step
         torch.cuda.empty_cache()
         sahi = leg_sahi(cx, max(10, min(args.steps, 100)))
 
@@ -845,8 +908,16 @@ def main():
             "config": {"workload": f"{args.workload}: {desc}" + (f" [clustered inputs, blobs={args.blobs}]" if args.blobs else ""),
                        "images_per_gpu": bs, "global_batch": bs * n_gpus, "anchors": anchors, "channels": spec.no, "streams": args.streams,
                        "in_flight": ("one batch" if args.streams == 1 else
-                                     f"{args.streams} independent batches, steps issued round-robin on {args.streams} CUDA streams, "
-                                     "each with its own input buffers; `single_stream` holds the one-batch-in-flight figure"),
+                                     "software pipeline of depth 2 (sarpost_pipeline_submit per step, one sarpost_pipeline_wait at the end): every "
+                                     "step is the whole path for one batch; batch i runs on stream i % 2 and its decode kernel is chained to the "
+                                     "previous batch's decode kernel, so the NMS + gather kernels of batch i run under the decode kernel of batch "
+                                     f"i+1; steps rotate over their own input buffers; rows identical to a plain call: {pipe_same_main}; "
+                                     f"`two_streams` = round-robin on {args.streams} plain streams, `single_stream` = one batch in flight"),
+                       "input_layout": ("split (SARPOST_LAYOUT_SPLIT): per level box (B,64,H,W), cls (B,nc,H,W), emb (B,H,W,E) channels_last, state "
+                                        "(B,S,H,W) — what patch(fused=True, split=True) hands over instead of torch.cat (head.py:204-206); the "
+                                        "reference legs (reference_gpu, cpu_baseline, --impl reference) get the concatenated tensors holding the "
+                                        "same values; `cat_layout` = this arm on those concatenated tensors") if use_split else
+                                       "concatenated (B, no, H, W) tensor per level",
                        "parallelism": f"batch-sharded x{n_gpus}, no data-path collective",
                        "l2": (("one batch of inputs (hot channels %.0f MB) exceeds the 126 MB L2; no flush" % (hot_bytes / 1e6))
                               if hot_bytes >= 2 * L2_BYTES else
@@ -854,7 +925,7 @@ def main():
                                "126 MB L2), so every step reads its inputs from HBM; no flush" % (hot_bytes / 1e6, n_sets, n_sets * hot_bytes / 1e6))),
                        "input_sets": n_sets,
                        "candidates_per_image": n_cand / bs, "detections_per_image": n_det / bs},
-            "single_stream": single, "roofline": roofline, "split_layout": split, "clustered": clustered, "reference_gpu": ref_gpu, "cpu_baseline": cpu, "e2e": e2e,
+            "single_stream": single, "two_streams": two_streams, "roofline": roofline, "cat_layout": cat_layout, "clustered": clustered, "reference_gpu": ref_gpu, "cpu_baseline": cpu, "e2e": e2e,
             "sahi": sahi, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "clocks": clocks.summary(),
         }
         emit(line)

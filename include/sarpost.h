@@ -289,6 +289,25 @@ int32_t sarpost_fused_host(sarpost_host_ctx_t *ctx, const sarpost_head_t *head,
 int32_t sarpost_host_ctx_last_traffic(const sarpost_host_ctx_t *ctx, int64_t *h2d_bytes, int64_t *d2h_bytes);
 
 /*
+ * Software pipeline over successive batches held in DEVICE memory (throughput mode; bench.py's `value`).  Same arguments
+ * and results as sarpost_fused, but the work is enqueued on the pipeline's own `depth` streams (one workspace each), batch
+ * i on stream i % depth, with one extra dependency: the decode kernel of batch i+1 starts when the decode kernel of batch
+ * i is done.  The NMS kernel of batch i — same-stream successor of its decode kernel — then takes its few SMs first, and
+ * the decode of batch i+1 (tiles handed out dynamically) streams on the SMs that are left: NMS + gather of every batch
+ * are hidden under the next batch's decode (depth >= 2 for any overlap).  No host synchronisation anywhere.
+ *   submit  waits (device side) for the work enqueued so far on `in_stream` — the stream that produced the level
+ *           tensors — then enqueues the batch.  The level tensors and the outputs must stay valid until a later
+ *           sarpost_pipeline_wait has been passed.
+ *   wait    makes `stream` wait (device side) until every batch submitted so far is complete.
+ */
+typedef struct sarpost_pipeline sarpost_pipeline_t;
+int32_t sarpost_pipeline_create(int32_t device, int32_t depth, sarpost_pipeline_t **pl);
+void sarpost_pipeline_destroy(sarpost_pipeline_t *pl);
+int32_t sarpost_pipeline_submit(sarpost_pipeline_t *pl, const sarpost_head_t *head, const sarpost_nms_params_t *params,
+                                float *out, int32_t *counts, int32_t *kept_index, void *in_stream);
+int32_t sarpost_pipeline_wait(sarpost_pipeline_t *pl, void *stream);
+
+/*
  * Introspection for benchmarks/tests: number of kernels the last call on this thread launched, and
  * optional per-stage CUDA-event timing.  When stage timing is enabled the calls record events around
  * every stage on the caller's stream; sarpost_stage_times() synchronises those events and returns

@@ -79,6 +79,10 @@ SYMBOLS = {
     "sarpost_fused_host": (C.c_int32, [C.c_void_p, C.POINTER(Head), C.POINTER(NmsParams), C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
     "sarpost_host_ctx_last_traffic": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "sarpost_pipeline_create": (C.c_int32, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "sarpost_pipeline_destroy": (None, [C.c_void_p]),
+    "sarpost_pipeline_submit": (C.c_int32, [C.c_void_p, C.POINTER(Head), C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sarpost_pipeline_wait": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "sarpost_last_launch_count": (C.c_int32, []),
     "sarpost_set_stage_timing": (C.c_int32, [C.c_int32]),
     "sarpost_stage_times": (C.c_int32, [C.POINTER(C.c_float)]),

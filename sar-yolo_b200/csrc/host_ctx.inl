@@ -286,3 +286,139 @@ static int32_t fused_host_impl(sarpost_host_ctx_t *c, const sarpost_head_t *head
 }
 
 }  // extern "C"
+
+// ================================================================================================
+// Software pipeline over successive batches (device buffers): sarpost_pipeline_*
+// ================================================================================================
+// One call of sarpost_fused is three dependent kernels: the decode kernel K1 streams the logits at the HBM rate on every
+// SM, the NMS kernel is a latency chain on a handful of SMs, the gather is small.  Back to back on one stream the last two
+// leave the memory system idle; issued from two INDEPENDENT streams they still end up queued behind the other batch's K1,
+// whose persistent CTAs fill every SM the moment the previous K1 drains (measured: the only gain is that the two tails
+// run side by side).  The pipeline rotates `depth` streams (one workspace each), batch i entirely on stream i % depth, and
+// adds one dependency: K1(i+1) waits for K1(i).  When K1(i) finishes, its same-stream successor — the NMS kernel of
+// batch i — is launched at once and takes its few SMs while the cross-stream K1(i+1) is still being released; K1(i+1)
+// hands out tiles dynamically, so it simply streams on whatever is left and picks up the other SMs as the tail of batch i
+// ends.  A one-thread gate kernel in front of K1(i+1) makes "at once" certain: it returns when every CTA of that NMS
+// kernel has checked in (or after 30 us).  In steady state the NMS + gather of every batch are hidden under the next batch's decode.
+struct sarpost_pipeline {
+    int device = 0, depth = 2;
+    std::vector<cudaStream_t> streams;
+    cudaEvent_t ev_in = nullptr;
+    std::vector<cudaEvent_t> ev_mid, ev_tail;
+    std::vector<sarpost::Buf> ws;
+    std::vector<int64_t> ws_sig;   // geometry signature of the last batch that used the slot (clean-region contract)
+    std::vector<char> used;
+    int64_t n_submitted = 0;
+    unsigned int *d_resident = nullptr;  // device counter: NMS CTAs that have started, over the pipeline's lifetime
+    unsigned int nms_ctas_total = 0;     // what it will read once every NMS kernel submitted so far is resident
+};
+
+extern "C" {
+
+int32_t sarpost_pipeline_create(int32_t device, int32_t depth, sarpost_pipeline_t **pl) {
+    if (!pl) return fail(SARPOST_EINVAL, "pl is NULL");
+    if (depth < 1 || depth > 8) return fail(SARPOST_EINVAL, "depth %d outside [1, 8]", depth);
+    CUDA_TRY(cudaSetDevice(device));
+    sarpost_pipeline *c = new sarpost_pipeline();
+    c->device = device;
+    c->depth = depth;
+    c->streams.assign(depth, nullptr);
+    c->ev_mid.assign(depth, nullptr);
+    c->ev_tail.assign(depth, nullptr);
+    c->ws.resize(depth);
+    c->ws_sig.assign(depth, -1);
+    c->used.assign(depth, 0);
+    bool ok = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) == cudaSuccess &&
+              cudaMalloc(&c->d_resident, 256) == cudaSuccess && cudaMemset(c->d_resident, 0, 256) == cudaSuccess;
+    for (int i = 0; ok && i < depth; ++i)
+        ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_mid[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_tail[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        const char *msg = cudaGetErrorString(cudaGetLastError());
+        sarpost_pipeline_destroy(c);
+        return fail(SARPOST_ECUDA, "pipeline stream/event creation failed: %s", msg);
+    }
+    *pl = c;
+    return SARPOST_OK;
+}
+
+void sarpost_pipeline_destroy(sarpost_pipeline_t *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (cudaStream_t st : c->streams)
+        if (st) cudaStreamSynchronize(st);
+    for (sarpost::Buf &b : c->ws) b.release();
+    for (cudaEvent_t e : c->ev_mid) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_tail) if (e) cudaEventDestroy(e);
+    if (c->ev_in) cudaEventDestroy(c->ev_in);
+    if (c->d_resident) cudaFree(c->d_resident);
+    for (cudaStream_t st : c->streams)
+        if (st) cudaStreamDestroy(st);
+    delete c;
+}
+
+int32_t sarpost_pipeline_submit(sarpost_pipeline_t *c, const sarpost_head_t *head, const sarpost_nms_params_t *params, float *out,
+                                int32_t *counts, int32_t *kept_index, void *in_stream) {
+    NvtxRange nvtx("sarpost_pipeline_submit");
+    g_launches = 0;
+    if (!c || !head || !params) return fail(SARPOST_EINVAL, "NULL argument");
+    if (params->n_peers > 0) return fail(SARPOST_EUNSUPPORTED, "the pipeline does not combine with the peer_out exchange");
+    CUDA_TRY(cudaSetDevice(c->device));
+    HeadGeom g;
+    int64_t anchors = 0;
+    if (int rc = fill_geom(head, &g, &anchors)) return rc;
+    const int slot = static_cast<int>(c->n_submitted % c->depth);
+    cudaStream_t st = c->streams[slot];
+    const int64_t need = sarpost_workspace_bytes(g.batch, anchors, g.nc, params->multi_label, params->max_det);
+    if (need < 0) return static_cast<int32_t>(need);
+    sarpost::Buf &ws = c->ws[slot];
+    if (need > ws.bytes) {
+        CUDA_TRY(cudaStreamSynchronize(st));  // about to free memory the slot's previous batch may still be using
+        if (int rc = ws.ensure(need)) return rc;
+        c->ws_sig[slot] = -1;
+    }
+    // the inputs are produced on the caller's stream: this batch waits for what is enqueued there so far ...
+    CUDA_TRY(cudaEventRecord(c->ev_in, static_cast<cudaStream_t>(in_stream)));
+    CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in, 0));
+    // ... and its decode kernel for the decode kernel of the batch before it (on the previous stream of the rotation)
+    if (c->depth > 1 && c->n_submitted > 0) {
+        const int prev = static_cast<int>((c->n_submitted - 1) % c->depth);
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_mid[prev], 0));
+        // ... once the previous batch's NMS kernel (launched right behind that decode kernel) has taken its SMs
+        k_gate<<<1, 32, 0, st>>>(c->d_resident, c->nms_ctas_total, 30000u);
+        CUDA_TRY(cudaGetLastError());
+    }
+    sarpost_nms_params_t prm = *params;
+    const int64_t sig = (static_cast<int64_t>(g.batch) << 40) ^ (anchors << 8) ^ (g.nc & 0xff) ^ (static_cast<int64_t>(params->multi_label != 0) << 62) ^
+                        (static_cast<int64_t>(params->max_det) << 24);
+    prm.workspace_clean = c->ws_sig[slot] == sig ? 1 : 0;  // same geometry as last time: the NMS kernel left the head of the slot zeroed
+    c->ws_sig[slot] = sig;
+    // the NMS kernel shares the GPU with the next batch's decode: one CTA per image instead of a cluster when the batch is
+    // large enough to keep the latency chain off the critical path
+    const int cl_hint = (c->depth > 1 && g.batch >= 8) ? 1 : 0;
+    g_resident_counter = c->depth > 1 ? c->d_resident : nullptr;
+    g_last_nms_ctas = 0;
+    const int rc = fused_impl(head, &prm, out, counts, kept_index, ws.p, ws.bytes, st, c->ev_mid[slot], cl_hint);
+    g_resident_counter = nullptr;
+    if (c->depth > 1 && c->n_submitted > 0) ++g_launches;  // the gate kernel
+    c->nms_ctas_total += static_cast<unsigned int>(g_last_nms_ctas);  // 0 when the launch itself failed
+    if (rc != SARPOST_OK) {
+        c->ws_sig[slot] = -1;
+        return rc;
+    }
+    CUDA_TRY(cudaEventRecord(c->ev_tail[slot], st));
+    c->used[slot] = 1;
+    ++c->n_submitted;
+    return SARPOST_OK;
+}
+
+int32_t sarpost_pipeline_wait(sarpost_pipeline_t *c, void *stream) {
+    if (!c) return fail(SARPOST_EINVAL, "pl is NULL");
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (int i = 0; i < c->depth; ++i)  // the newest batch of every stream of the rotation
+        if (c->used[i]) CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->ev_tail[i], 0));
+    return SARPOST_OK;
+}
+
+}  // extern "C"

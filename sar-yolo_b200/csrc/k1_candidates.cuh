@@ -245,21 +245,33 @@ struct K1TmaParams {
     CandStore st;
     int32_t stages;
     int32_t n_tiles;  // B * tpi
+    int32_t *tile_counter;  // zero at launch: next tile to hand out (the NMS kernel zeroes it again)
 };
 
 constexpr int kMaxStages = 8;
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Tiles are handed out through an atomic counter instead of a fixed stride: CTAs that become resident late — SMs held by
+// the NMS kernel of the previous batch when batches are pipelined (sarpost_pipeline_*), or simply a partial last wave —
+// take what is left instead of owning a fixed share, so the kernel ends when the work does.  Which CTA decodes a tile
+// does not affect the result: every tile writes its own region of the candidate store.
 template <typename T>
 __global__ void __launch_bounds__(kTileA, sizeof(T) == 2 ? 6 : 3) k1_fused_tma(const __grid_constant__ K1TmaParams p) {
     extern __shared__ unsigned char dyn_smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ int ring_b[kMaxStages], ring_r[kMaxStages];  // image / tile-in-image of the tile in flight in each stage; b < 0: no more work
     __shared__ int scratch[8];
     const int tid = threadIdx.x;
     const int nch = 4 * kRegMax + p.g.nc;
     const uint32_t stage_bytes = static_cast<uint32_t>(nch) * kTileA * sizeof(T);
     unsigned char *dyn = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn_smem_raw) + 127) & ~uintptr_t(127));
 
+    int next_t = 0;  // thread 0: tile index fetched ahead of its use, so the atomic's round trip is off the issue path
     if (tid == 0) {
+        next_t = atomicAdd(p.tile_counter, 1);
         for (int s = 0; s < p.stages; ++s) mbar_init(&full_bar[s], 1);
         fence_barrier_init();
         for (int l = 0; l < p.g.nl; ++l) {
@@ -269,39 +281,39 @@ __global__ void __launch_bounds__(kTileA, sizeof(T) == 2 ? 6 : 3) k1_fused_tma(c
     }
     __syncthreads();
 
-    const int first = blockIdx.x, step = gridDim.x;
-    const int n_my = first < p.n_tiles ? (p.n_tiles - first + step - 1) / step : 0;
-    // tile k of this CTA is t = first + k*step = image b, tile r: walked incrementally (no division per tile)
-    const int step_b = step / p.g.tpi, step_r = step - step_b * p.g.tpi;
-    auto advance = [&](int &b, int &r) {
-        b += step_b;
-        r += step_r;
-        if (r >= p.g.tpi) { r -= p.g.tpi; ++b; }
-    };
-
-    auto issue = [&](int s, int b, int r) {
+    // thread 0: put the next tile into stage s (or mark the stage "no more work"), then fetch the index after it
+    auto issue = [&](int s) {
+        const int t = next_t;
+        if (t >= p.n_tiles) {
+            ring_b[s] = -1;
+            mbar_arrive(&full_bar[s]);  // completes the phase without a transfer
+            return;
+        }
+        next_t = atomicAdd(p.tile_counter, 1);
+        const int b = t / p.g.tpi, r = t - b * p.g.tpi;
+        ring_b[s] = b;
+        ring_r[s] = r;
         const int l = tile_level(p.g, r);
         const int a0 = (r - p.g.lvl_tile_begin[l]) * kTileA;
-        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);  // release: the ring entries are visible to whoever sees the phase flip
         unsigned char *dst = dyn + static_cast<size_t>(s) * stage_bytes;
         tma_load_3d(dst, &p.maps[l], a0, 0, b, &full_bar[s]);
         if (p.g.split)  // the class rows land right behind the 4*reg_max box rows: same smem[channel][anchor] tile as the cat layout
             tma_load_3d(dst + static_cast<size_t>(4 * kRegMax) * kTileA * sizeof(T), &p.maps_cls[l], a0, 0, b, &full_bar[s]);
     };
-    int ib = first / p.g.tpi, ir = first - ib * p.g.tpi;  // next tile to issue (thread 0)
     if (tid == 0)
-        for (int k = 0; k < p.stages && k < n_my; ++k) {
-            issue(k, ib, ir);
-            advance(ib, ir);
-        }
+        for (int s = 0; s < p.stages; ++s) issue(s);
 
-    int b = first / p.g.tpi, r = first - b * p.g.tpi, s = 0;
+    int s = 0;
     uint32_t phase = 0;
-    for (int k = 0; k < n_my; ++k) {
+    for (;;) {
+        mbar_wait(&full_bar[s], phase);
+        const int b = ring_b[s];
+        if (b < 0) break;  // tiles are handed out in order: every later stage is empty too, nothing is in flight
+        const int r = ring_r[s];
         const int l = tile_level(p.g, r);
         const int pos = (r - p.g.lvl_tile_begin[l]) * kTileA + tid;  // position inside the level
         const bool valid = pos < p.g.lvl_hw[l];
-        mbar_wait(&full_bar[s], phase);
         const T *buf = reinterpret_cast<const T *>(dyn + static_cast<size_t>(s) * stage_bytes) + tid;
         auto acc = [&](int c) { return to_f32(buf[c * kTileA]); };
         const int w = p.g.lvl_w[l];
@@ -309,12 +321,8 @@ __global__ void __launch_bounds__(kTileA, sizeof(T) == 2 ? 6 : 3) k1_fused_tma(c
         const float4 xyxy = xywh2xyxy_rn(decode_xywh(acc, xx, yy, p.g.lvl_stride[l]));
         auto score = [&](int j) { return sigmoid_rn(to_f32(buf[(4 * kRegMax + j) * kTileA])); };
         emit_candidates(valid, xyxy, static_cast<uint32_t>(p.g.lvl_aoff[l] + pos), p.g.nc, p.f, score, p.st, b, r, scratch);
-        // emit_candidates ended with __syncthreads(): stage s is free again
-        if (tid == 0 && k + p.stages < n_my) {
-            issue(s, ib, ir);
-            advance(ib, ir);
-        }
-        advance(b, r);
+        // emit_candidates ended with __syncthreads(): stage s (buffer and ring entry) is free again
+        if (tid == 0) issue(s);
         if (++s == p.stages) { s = 0; phase ^= 1u; }
     }
 }

@@ -131,6 +131,8 @@ struct NmsParams {
     float max_wh;                    // 0 when agnostic
     float thr;                       // largest float <= iou_thres
     long long *stats;                // [B*4] or nullptr: candidates consumed, pair tests, sub-chunks, collections (instrumentation)
+    int32_t *tile_counter;           // the decode kernel's tile counter: left zeroed for the next call (workspace_clean)
+    unsigned int *resident_counter;  // pipeline only (else nullptr): every CTA checks in here as soon as it runs (k_gate)
 };
 
 // IoU(a,b) > thr, bit-exact to the fp32 division of the reference but without paying for it on every
@@ -385,6 +387,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #endif
     if (tid < kSub) S_DEAD[tid] = 0;
     if (tid >= 32 && tid < 64) S_MISC[tid] = 0;  // control block, counters (both banks)
+    if (blockIdx.x == 0 && tid == 0) *p.tile_counter = 0;
+    if (p.resident_counter != nullptr && tid == 0) atomicAdd(p.resident_counter, 1u);
 
     // class-offset box of a candidate slot (ops.py:289,295)
     auto offset_box = [&](uint32_t slot) {
@@ -1024,6 +1028,23 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #undef KEPT_BOX
 #undef KEPT_AREA
 #undef KEPT_SLOT
+}
+
+// Pipeline gate (sarpost_pipeline_*): holds the stream — i.e. the next batch's decode kernel — until the NMS kernel of the
+// previous batch is resident (its CTAs need whole SMs: 512 threads x 124 registers; once the decode kernel's CTAs have
+// spread over every SM there is no room for them until it ends), or until `timeout_ns` has passed.  `expected` = CTAs of
+// all NMS kernels launched through the pipeline so far (the counter only ever grows; the comparison is wrap-safe).
+__global__ void k_gate(const unsigned int *counter, unsigned int expected, unsigned int timeout_ns) {
+    if (threadIdx.x != 0) return;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        const unsigned int v = *reinterpret_cast<const volatile unsigned int *>(counter);
+        if (static_cast<int>(v - expected) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) break;
+        __nanosleep(100);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

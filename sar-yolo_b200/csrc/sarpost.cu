@@ -37,6 +37,8 @@ thread_local int g_timing = 0;  // 0 off, 1 time the last call, 2 accumulate eve
 thread_local std::vector<cudaEvent_t> g_ev;  // 5 events per timed call: start, hist ready, K1, NMS, gather
 thread_local int g_ev_calls = 0;             // complete event sets recorded (mode 1 keeps only the last)
 thread_local int g_ev_valid = 0;
+thread_local int g_last_nms_ctas = 0;            // CTAs of the last NMS kernel launched on this thread (pipeline gate)
+thread_local unsigned int *g_resident_counter = nullptr;  // set by the pipeline around its call of fused_impl
 
 static int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -82,6 +84,9 @@ struct Layout {
     int64_t box, score, key, cls, key_a, val_a, key_b, val_b, tile_count, tile_max, hist, kept_slot, total;
 };
 
+// bytes at the head of a workspace that must be zero when a call starts: per-image score histograms + K1's tile counter
+static int64_t clean_region_bytes(int64_t batch) { return batch * kBuckets * 4 + 256; }
+
 static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_det, bool with_cls) {
     Layout L;
     int64_t o = 0;
@@ -91,7 +96,8 @@ static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_d
         return at;
     };
     const int64_t slots = batch * cap;
-    L.hist = take(batch * kBuckets * 4);  // first: the only region with an entry contract (see workspace_clean)
+    L.hist = take(clean_region_bytes(batch));  // first: the only region with an entry contract (see workspace_clean);
+                                               // histograms, then the decode kernel's tile counter
     L.box = take(slots * 16);
     L.score = take(slots * 4);
     L.key = take(slots * 4);
@@ -109,6 +115,7 @@ static Layout make_layout(int64_t batch, int64_t cap, int64_t tpi, int64_t max_d
 
 struct Pipeline {
     CandStore st;
+    int32_t *tile_counter;  // behind the histograms, zero on entry like them
     uint32_t *key_a, *val_a, *key_b, *val_b;
     uint32_t *kept_slot;
     float *cls;
@@ -134,6 +141,7 @@ static int bind_workspace(void *ws, int64_t ws_bytes, int64_t batch, int64_t cap
     P->key_b = reinterpret_cast<uint32_t *>(base + L.key_b);
     P->val_b = reinterpret_cast<uint32_t *>(base + L.val_b);
     P->st.hist = reinterpret_cast<int32_t *>(base + L.hist);
+    P->tile_counter = reinterpret_cast<int32_t *>(base + L.hist + batch * kBuckets * 4);
     P->kept_slot = reinterpret_cast<uint32_t *>(base + L.kept_slot);
     P->cls = with_cls ? reinterpret_cast<float *>(base + L.cls) : nullptr;
     return SARPOST_OK;
@@ -275,7 +283,7 @@ static int env_int(const char *name, int dflt) {
 // ------------------------------------------------------------------------------------------------
 // stages
 // ------------------------------------------------------------------------------------------------
-static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandStore &st, cudaStream_t s) {
+static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandStore &st, int32_t *tile_counter, cudaStream_t s) {
     NvtxRange nvtx("sarpost:K1 decode+score+compact");
     const int nch = 4 * kRegMax + g.nc;
     const int esz = g.is_half ? 2 : 4;
@@ -307,6 +315,7 @@ static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandSto
         p.st = st;
         p.stages = stages;
         p.n_tiles = g.batch * g.tpi;
+        p.tile_counter = tile_counter;
         PFN_encodeTiled enc = get_encode_fn();
         const CUtensorMapDataType dt = g.is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
         const CUtensorMapL2promotion promo = static_cast<CUtensorMapL2promotion>(env_int("SARPOST_K1_L2PROMO", CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
@@ -371,7 +380,7 @@ static void fill_extras_src(const HeadGeom &g, ExtrasSrc *ex) {
 
 // K2 + K4 + K5 on a filled candidate store.
 static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, int nc, const ExtrasSrc &ex, float *out,
-                    int32_t *counts, int32_t *kept_index, cudaStream_t s) {
+                    int32_t *counts, int32_t *kept_index, cudaStream_t s, int cl_hint = 0) {
     NvtxRange nvtx("sarpost:K2-K5 select+sort+nms+gather");
     NmsParams np;
     np.st = P.st;
@@ -388,11 +397,14 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     np.max_wh = prm->agnostic ? 0.0f : prm->max_wh;
     np.thr = iou_thr_float(prm->iou_thres);
     np.stats = reinterpret_cast<long long *>(prm->stats);
+    np.tile_counter = P.tile_counter;
+    np.resident_counter = g_resident_counter;
     const int nms_smem = static_cast<int>(nms_smem_bytes(prm->max_det));
     // one CTA per image; when the batch leaves SMs idle, a cluster of 2 or 4 CTAs per image shares the work
     int sms = 0, smem_optin = 0;
     if (int rc = device_sm_count(&sms, &smem_optin)) return rc;
     int cl = batch * 4 <= sms ? 4 : (batch * 2 <= sms ? 2 : 1);
+    if (cl_hint == 1 || cl_hint == 2 || cl_hint == 4) cl = cl_hint;
     const int forced_cl = env_int("SARPOST_NMS_CLUSTER", 0);
     if (forced_cl == 1 || forced_cl == 2 || forced_cl == 4 || forced_cl == 8) cl = forced_cl;
     cudaLaunchConfig_t cfg;
@@ -412,6 +424,7 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     void (*kern)(const NmsParams) = cl == 8 ? k4_nms<8> : cl == 4 ? k4_nms<4> : cl == 2 ? k4_nms<2> : k4_nms<1>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, np));
+    g_last_nms_ctas = batch * cl;
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     stage_mark(3, s);
@@ -451,7 +464,7 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
 // the per-image score histogram must be zero before K1 accumulates into it
 static int zero_hist(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, cudaStream_t s) {
     if (!prm->workspace_clean)
-        CUDA_TRY(cudaMemsetAsync(P.st.hist, 0, static_cast<size_t>(batch) * kBuckets * sizeof(int32_t), s));
+        CUDA_TRY(cudaMemsetAsync(P.st.hist, 0, static_cast<size_t>(clean_region_bytes(batch)), s));
     stage_mark(1, s);
     return SARPOST_OK;
 }
@@ -513,12 +526,12 @@ int64_t sarpost_merge_workspace_bytes(int32_t n_frames, int32_t tiles_per_frame,
 
 int64_t sarpost_workspace_clean_bytes(int32_t batch) {
     if (batch < 1) return fail(SARPOST_EINVAL, "batch %d < 1", batch);
-    return static_cast<int64_t>(batch) * kBuckets * 4;
+    return clean_region_bytes(batch);
 }
 
 int32_t sarpost_workspace_prepare(void *workspace, int64_t workspace_bytes, int32_t batch, void *stream) {
     if (!workspace || batch < 1) return fail(SARPOST_EINVAL, "bad workspace_prepare arguments");
-    const int64_t n = static_cast<int64_t>(batch) * kBuckets * 4;
+    const int64_t n = clean_region_bytes(batch);
     if (workspace_bytes < n) return fail(SARPOST_EWORKSPACE, "workspace too small: %lld < %lld bytes", (long long)workspace_bytes, (long long)n);
     CUDA_TRY(cudaMemsetAsync(workspace, 0, static_cast<size_t>(n), static_cast<cudaStream_t>(stream)));
     return SARPOST_OK;
@@ -608,11 +621,10 @@ int32_t sarpost_nms_decoded(const void *prediction, int32_t batch, int32_t chann
     return run_tail(P, batch, params, nc, ex, out, counts, kept_index, s);
 }
 
-int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *params, float *out, int32_t *counts,
-                      int32_t *kept_index, void *workspace, int64_t workspace_bytes, void *stream) {
-    NvtxRange nvtx("sarpost_fused");
-    g_launches = 0;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+// decode + candidates, then select/sort/NMS/gather, all on stream s; `mid` (optional) is recorded right behind the decode
+// kernel — the pipeline chains the next batch's decode kernel, on another stream, to it
+static int fused_impl(const sarpost_head_t *head, const sarpost_nms_params_t *params, float *out, int32_t *counts,
+                      int32_t *kept_index, void *workspace, int64_t workspace_bytes, cudaStream_t s, cudaEvent_t mid, int cl_hint) {
     HeadGeom g;
     int64_t anchors = 0;
     if (int rc = fill_geom(head, &g, &anchors)) return rc;
@@ -627,12 +639,20 @@ int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *pa
 
     stage_mark(0, s);
     if (int rc = zero_hist(P, g.batch, params, s)) return rc;
-    if (int rc = launch_k1_fused(g, f, P.st, s)) return rc;
+    if (int rc = launch_k1_fused(g, f, P.st, P.tile_counter, s)) return rc;
     stage_mark(2, s);
-
+    if (mid) CUDA_TRY(cudaEventRecord(mid, s));
     ExtrasSrc ex;
     fill_extras_src(g, &ex);
-    return run_tail(P, g.batch, params, g.nc, ex, out, counts, kept_index, s);
+    return run_tail(P, g.batch, params, g.nc, ex, out, counts, kept_index, s, cl_hint);
+}
+
+int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *params, float *out, int32_t *counts,
+                      int32_t *kept_index, void *workspace, int64_t workspace_bytes, void *stream) {
+    NvtxRange nvtx("sarpost_fused");
+    g_launches = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return fused_impl(head, params, out, counts, kept_index, workspace, workspace_bytes, s, nullptr, 0);
 }
 
 int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const float *origins, int32_t n_frames,

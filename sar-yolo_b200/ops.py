@@ -22,7 +22,7 @@ from . import _lib
 from ._lib import Head, NmsParams, lib
 
 __all__ = ["HeadSpec", "StateMLP", "state_head", "non_max_suppression", "decode", "postprocess_fused", "split_levels", "cat_levels", "merge_tiles", "gather_extras", "match_predictions", "match_from_iou", "postprocess_host",
-           "HostContext", "last_launch_count", "stage_timing", "stage_times"]
+           "HostContext", "Pipeline", "last_launch_count", "stage_timing", "stage_times"]
 
 
 @dataclass(frozen=True)
@@ -736,6 +736,86 @@ def match_from_iou(pred_classes: torch.Tensor, true_classes: torch.Tensor, iou: 
                                                   int(tag_threshold_index) if tag_threshold_index is not None else -1, _stream_ptr(dev)))
     correct = correct.bool()
     return (correct, matched) if matched is not None else correct
+
+
+class Pipeline:
+    """Throughput mode for a stream of batches in device memory (`sarpost_pipeline_*`): `submit()` enqueues the fused
+    decode + NMS of one batch on one of the pipeline's own `depth` streams and returns the padded output tensors
+    immediately; the decode kernels of successive batches are chained, so the NMS + gather of batch i run under the
+    decode kernel of batch i+1.  `wait()` makes the current stream wait for everything
+    submitted so far — the outputs may be read (on the current stream) after it, without any host synchronisation.
+
+        pl = sarpost.Pipeline(device)
+        for levels in batches:
+            results.append(pl.submit(levels, spec, conf_thres=0.001, iou_thres=0.7))   # (out, counts)
+        pl.wait()
+    """
+
+    def __init__(self, device=None, depth: int = 2):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("sarpost: Pipeline needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self._h = C.c_void_p()
+        self._held = []  # inputs / outputs / parameter blocks of batches in flight: alive until wait()
+        _lib.check(lib.sarpost_pipeline_create(self.device.index, int(depth), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib.sarpost_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+        self._held.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit(self, levels, spec: HeadSpec, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
+               max_det=300, max_nms=30000, max_wh=7680, return_index=False, with_extras=True, scale_to=None, out=None):
+        """Arguments as `postprocess_fused`.  Returns `(out (B, max_det, 6+nm), counts (B,) int32[, kept_index])` device
+        tensors that are being written asynchronously: call `wait()` before using them.  `out=(rows, counts)`: caller-owned
+        output tensors (a long-running loop should rotate a few preallocated sets: tensors handed out here stay referenced
+        until `wait()`, so nothing is recycled by the allocator in between)."""
+        assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+        assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+        levels = _prep_levels(levels)
+        head = _make_head(levels, spec, with_extras=with_extras)
+        dev = _box_of(levels[0]).device
+        if dev != self.device:
+            raise RuntimeError(f"sarpost: level tensors are on {dev}, the pipeline on {self.device}")
+        if head.batch == 0:
+            raise ValueError("sarpost: empty batch")
+        nm = spec.nm if with_extras else 0
+        rescale = None
+        if scale_to is not None:
+            img1_shape, img0_shapes = scale_to
+            if len(img0_shapes) != head.batch:
+                raise ValueError(f"sarpost: scale_to has {len(img0_shapes)} original shapes for a batch of {head.batch}")
+            rescale = scale_params(img1_shape, img0_shapes, dev)
+        params, keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, rescale)
+        with torch.cuda.device(dev):
+            if out is not None:
+                out, counts = out
+                for t, shp, dt in ((out, (head.batch, int(max_det), 6 + nm), torch.float32), (counts, (head.batch,), torch.int32)):
+                    if tuple(t.shape) != shp or t.dtype != dt or not t.is_contiguous() or t.device != dev:
+                        raise ValueError(f"sarpost: out= tensors must be contiguous {shp} {dt} on {dev}")
+            else:
+                out = torch.empty((head.batch, int(max_det), 6 + nm), dtype=torch.float32, device=dev)
+                counts = torch.empty((head.batch,), dtype=torch.int32, device=dev)
+            kidx = torch.empty((head.batch, int(max_det)), dtype=torch.int32, device=dev) if return_index else None
+            _lib.check(lib.sarpost_pipeline_submit(self._h, C.byref(head), C.byref(params), out.data_ptr(), counts.data_ptr(),
+                                                   kidx.data_ptr() if return_index else None, _stream_ptr(dev)))
+        self._held.append((levels, rescale, out, counts, kidx, keep))
+        return (out, counts, kidx) if return_index else (out, counts)
+
+    def wait(self) -> None:
+        """The current stream waits (device side) for every submitted batch; held references are released."""
+        with torch.cuda.device(self.device):
+            _lib.check(lib.sarpost_pipeline_wait(self._h, _stream_ptr(self.device)))
+        # the tensors were allocated on the current stream and that stream now waits for their last use: freeing is safe
+        self._held.clear()
 
 
 class HostContext:

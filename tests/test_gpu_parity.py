@@ -951,3 +951,29 @@ def test_match_from_iou_equals_reference_method(sarpost, cuda):
     finally:
         sarpost.unpatch()
     assert BaseValidator().match_predictions(None, None, None) == "ref" and JDEValidator().match_predictions(None, None, None, None) == "ref-jde"
+
+
+def test_pipeline_matches_plain_calls(sarpost, cuda):
+    """sarpost_pipeline_*: batches submitted back to back (decode of batch i+1 overlapping NMS + gather of batch i on a
+    second, high-priority stream, rotating workspaces, dynamic tile scheduling) give the very rows of one plain
+    `postprocess_fused` call per batch — also when geometry, batch size and thresholds change between submits."""
+    strides = (8, 16, 32)
+    spec = sarpost.HeadSpec(nc=2, strides=strides, embed_dim=8, state_classes=3)
+    jobs = []
+    for i, (imgsz, bs, kw) in enumerate([(320, 9, dict(conf_thres=0.25, iou_thres=0.7)), (320, 9, dict(conf_thres=0.25, iou_thres=0.7)),
+                                         (256, 3, dict(conf_thres=0.05, iou_thres=0.5, max_det=40)), (320, 9, dict(conf_thres=0.25, iou_thres=0.7, multi_label=True)),
+                                         (320, 12, dict(conf_thres=0.001, iou_thres=0.7, max_nms=500)), (320, 9, dict(conf_thres=0.25, iou_thres=0.7))] * 2):
+        shapes = sarpost.synth.level_shapes(imgsz, strides)
+        levels = [x.to(cuda) for x in sarpost.synth.head_outputs(bs, shapes, spec.nc, spec.embed_dim, spec.state_classes, seed=50 + i, cls_mean=-1.0)]
+        jobs.append((levels, kw))
+    for depth in (1, 2, 3):
+        pl = sarpost.Pipeline(cuda, depth=depth)
+        got = [pl.submit(levels, spec, return_index=True, **kw) for levels, kw in jobs]
+        pl.wait()
+        torch.cuda.current_stream().synchronize()
+        for (levels, kw), (out, counts, kidx) in zip(jobs, got):
+            want_out, want_counts, want_idx = sarpost.postprocess_fused(levels, spec, return_padded=True, return_index=True, **kw)
+            assert torch.equal(counts, want_counts)
+            for b, n in enumerate(want_counts.tolist()):
+                assert torch.equal(out[b, :n], want_out[b, :n]) and torch.equal(kidx[b, :n], want_idx[b, :n])
+        pl.close()
