@@ -686,7 +686,7 @@ def main():
         return run_reference_arm(args)
     ensure_built()
     if args.quick:
-        args.no_e2e = args.no_cpu_baseline = args.no_reference_gpu = args.no_clustered = args.no_sahi = args.no_split = True
+        args.no_e2e = args.no_cpu_baseline = args.no_reference_gpu = args.no_clustered = args.no_sahi = True
 
     cx = Ctx(args)
     torch, dist, sarpost = cx.torch, cx.dist, cx.sarpost

@@ -17,10 +17,12 @@
 //   sort      the survivors are sorted in shared memory (bitonic network on the 64-bit composite score|~slot =
 //             descending score, source order on ties); a single bucket larger than that falls back to a stable
 //             LSD radix sort in global memory;
-//   phase 2   sub-chunks of <= 256 sorted survivors: test against boxes kept since the chunk began, ordered
-//             compaction, upper-triangular suppression bitmask (warp per row, ballot per word);
+//   phase 2   sub-chunks of <= 256 sorted survivors: test against boxes kept since the chunk began + upper-triangular
+//             suppression bitmask among themselves (columns in registers, rows broadcast from shared memory, IoU only
+//             for pairs that intersect with comparable areas); big sub-chunks are shared with the idle CTAs of the
+//             cluster (candidates pushed through distributed shared memory, results stored back: 2 cluster barriers);
 //   sweep     one warp resolves the sub-chunk on the bitmask, 32 candidates per step when no two live
-//             candidates of the group overlap, else one step per KEPT box; appends to the kept list.
+//             candidates of the group overlap, else one step per KEPT box; all threads append to the kept list.
 // Small batches (B*CL <= #SMs) run a thread-block CLUSTER of CL CTAs per image: collection and phase 1 are split
 // across the CTAs (interleaved tiles), survivors travel to the master CTA through distributed shared memory, the
 // master sorts / sweeps and replicates the new kept boxes: 2 cluster barriers per chunk.
@@ -302,8 +304,8 @@ struct NmsSmemLayout {
     static constexpr int c_slot = a_slot + kSub * 4;
     static constexpr int dead = c_slot + kSub * 4;                   // i32[kSub]  master: verdicts of the incremental phase 1
     static constexpr int deadw = dead + kSub * 4;                    // u32[kShareCap / 32]  share phase 1: dead bits
-    static constexpr int misc = deadw + kShareCap / 32 * 4;          // i32[64]
-    static constexpr int zstart = misc + 64 * 4;                     // i32[kBuckets + 4]  zoom: exact sub-bucket ranks of one bucket
+    static constexpr int misc = deadw + kShareCap / 32 * 4;          // i32[96]
+    static constexpr int zstart = misc + 96 * 4;                     // i32[kBuckets + 4]  zoom: exact sub-bucket ranks of one bucket
     static constexpr int kept = zstart + (kBuckets + 4) * 4;         // float4[max_det] | f32[max_det] | u32[max_det]
 };
 static_assert(NmsSmemLayout::radix_end >= 256 * (kNmsWarps + 1) * 4, "radix counters must fit the plist|surv|skey region");
@@ -325,7 +327,13 @@ enum : int {
     kMListN = 38,    // tile list length
     kMCtl = 40,      // [40, 44) control block written by the master into every CTA: action, kept, members, survivors
     kMCtr = 48,      // [48, 56) master only: two banks (chunk parity) of {members, survivors, overflow}
+    kMKm = 56,       // [56, 64) master only: kept bits per group of the sub-chunk just swept
+    kMOrd = 64,      // [64, 68) helper CTAs: work order from the master {kOrdHelp | 0, candidates, k_from, kept}
 };
+constexpr int kOrdHelp = 1;
+// a sub-chunk's pair work (bitmask + incremental phase 1) is shared with the other CTAs of the cluster when it exceeds this
+// many IoU pairs: below, two cluster barriers cost more than the helpers save
+constexpr long long kDistPairs = 10000;
 enum : int { kActOk = 0, kActHalve = 1, kActCareful = 2, kActRadix = 3, kActZoom = 4 };
 constexpr uint32_t kZoomSpan = (1u << kBucketShift) / kBuckets;  // float values per sub-bucket of a zoomed bucket (8)
 
@@ -386,7 +394,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     long long prof_t = clock64();
 #endif
     if (tid < kSub) S_DEAD[tid] = 0;
-    if (tid >= 32 && tid < 64) S_MISC[tid] = 0;  // control block, counters (both banks)
+    if (tid >= 32 && tid < 96) S_MISC[tid] = 0;  // control block, counters (both banks), work order
     if (blockIdx.x == 0 && tid == 0) *p.tile_counter = 0;
     if (p.resident_counter != nullptr && tid == 0) atomicAdd(p.resident_counter, 1u);
 
@@ -500,8 +508,89 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
     long long st_walk = 0, st_pairs = 0;  // instrumentation (NmsParams::stats); st_walk/st_sub/st_coll uniform, st_pairs per CTA
     int st_sub = 0, st_coll = 0;
 
-    // MASTER ONLY (block-level barriers only).  Walks `cnt` sorted candidates whose slots are produced by slot_at(i);
-    // they have already been tested against kept[0, k_from).
+    // The pair work of one sub-chunk for this CTA's slice (`cpart` of `cparts` CTAs of the cluster).  A_BOX / S_A_AREA hold
+    // `sub` sorted candidates that were already tested against kept[0, k_from); boxes [k_from, k_now) have been kept since.
+    //   (a) incremental phase 1: candidates x those boxes (this CTA's share of the boxes) -> S_DEAD verdicts
+    //   (b) suppression bitmask among the candidates themselves (this CTA's share of the rows), word-major:
+    //       S_MASK[w * kSub + r] = word w (columns 32w .. 32w+31) of row r, bits j > r only
+    // Both land in the MASTER's shared memory: local stores on the master, distributed-shared-memory stores from a helper.
+    auto pair_round = [&](const int sub, const int k_from, const int k_now, const int cpart, const int cparts) {
+        int32_t *dead_out = S_DEAD;
+        uint32_t *mask_out = S_MASK;
+        if constexpr (CL > 1) {
+            if (cpart != 0) {
+                dead_out = cluster.map_shared_rank(S_DEAD, 0);
+                mask_out = cluster.map_shared_rank(S_MASK, 0);
+            }
+        }
+        if (k_now > k_from) {
+            int sub_p2 = 64;
+            while (sub_p2 < sub) sub_p2 <<= 1;
+            const int cand = tid & (sub_p2 - 1), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
+            const int cc = cand < sub ? cand : 0;
+            if (killed_by_kept_sparse(cand < sub, A_BOX[cc], S_A_AREA[cc], k_from, k_now, cpart * nparts + part, cparts * nparts)) dead_out[cand] = 1;
+            st_pairs += static_cast<long long>(sub) * (k_now - k_from) / cparts;
+        }
+        // Work items = (word w, row r < min(sub, 32(w+1))), flattened word-major and cut into equal slices: one per CTA, then
+        // one per warp.  A warp keeps the 32 column boxes of its current word in registers (lane = column) and streams rows
+        // past them, four at a time: one broadcast shared load and a few compares per (row, word); the IoU arithmetic runs
+        // only for rows that intersect some column of the word with a comparable area (disjoint boxes: inter = 0 -> IoU 0
+        // or NaN, never > thr; area ratio <= thr: see ratio_cut).
+        const int words = (sub + 31) >> 5;
+        const int n_items = 16 * words * (words - 1) + sub;  // full words contribute 32(w+1) rows each, the last one `sub`
+        const int c_lo = static_cast<int>(static_cast<long long>(n_items) * cpart / cparts);
+        const int c_hi = static_cast<int>(static_cast<long long>(n_items) * (cpart + 1) / cparts);
+        const int it_lo = c_lo + static_cast<int>(static_cast<long long>(c_hi - c_lo) * warp / kNmsWarps);
+        const int it_hi = c_lo + static_cast<int>(static_cast<long long>(c_hi - c_lo) * (warp + 1) / kNmsWarps);
+        int it = it_lo, w = 0;
+        while (w + 1 < words && 16 * (w + 1) * (w + 2) <= it) ++w;
+        while (it < it_hi) {
+            const int r_begin = it - 16 * w * (w + 1);
+            const int r_end = min(w == words - 1 ? sub : 32 * (w + 1), r_begin + (it_hi - it));
+            const int j = (w << 5) + lane;
+            const bool jv = j < sub;
+            const float4 cb = A_BOX[jv ? j : 0];
+            const float ca = S_A_AREA[jv ? j : 0];
+            for (int r0 = r_begin; r0 < r_end; r0 += 4) {
+                float4 rb[4];
+                float ra4[4];
+                bool ov[4], any[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    rb[u] = A_BOX[min(r0 + u, r_end - 1)];
+                    ra4[u] = S_A_AREA[min(r0 + u, r_end - 1)];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    ov[u] = jv && j > r0 + u && rb[u].z > cb.x && cb.z > rb[u].x && rb[u].w > cb.y && cb.w > rb[u].y &&
+                            !(fminf(ra4[u], ca) <= ratio_cut * fmaxf(ra4[u], ca));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) any[u] = __any_sync(0xffffffffu, ov[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (r0 + u >= r_end) break;
+                    uint32_t bits = 0u;
+                    if (any[u]) {
+                        bool g = false;
+                        if (ov[u]) {
+                            bool bd;
+                            g = iou_gt_approx(rb[u], ra4[u], cb, ca, p.thr, band, bd);
+                            if (bd) g = iou_gt(rb[u], ra4[u], cb, ca, p.thr);  // rare: quotient within a few ulp of thr
+                        }
+                        bits = __ballot_sync(0xffffffffu, g);
+                    }
+                    if (lane == 0) mask_out[w * kSub + r0 + u] = bits;
+                }
+            }
+            it += r_end - r_begin;
+            ++w;
+        }
+        if (cpart == 0) st_pairs += static_cast<long long>(sub) * (sub - 1) / 2;
+    };
+
+    // MASTER ONLY.  Walks `cnt` sorted candidates whose slots are produced by slot_at(i); they have already been tested
+    // against kept[0, k_from).  Sub-chunks of <= 256: load, pair work (shared with the other CTAs of the cluster when it is
+    // worth two cluster barriers), one-warp sweep over the bitmask, append to the kept list (replicated into the peers).
     auto process_sorted = [&](auto slot_at, int cnt, int k_from) {
         int pdone = 0;
         while (pdone < cnt && kept < p.max_det) {
@@ -517,107 +606,42 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             }
             __syncthreads();
             PROF_MARK(10);
-            // ---- incremental phase 1: candidates x boxes kept since they were last tested ----
-            if (kept > k_from) {
-                int sub_p2 = 64;
-                while (sub_p2 < sub) sub_p2 <<= 1;
-                const int cand = tid & (sub_p2 - 1), part = tid / sub_p2, nparts = kNmsThreads / sub_p2;
-                const int cc = cand < sub ? cand : 0;
-                if (killed_by_kept_sparse(cand < sub, A_BOX[cc], S_A_AREA[cc], k_from, kept, part, nparts)) S_DEAD[cand] = 1;
-                st_pairs += static_cast<long long>(sub) * (kept - k_from);
-                __syncthreads();
-            }
-            PROF_MARK(11);
-            // ---- ordered compaction of survivors (first kSub threads = 8 warps) ----
-            bool alive = false;
-            uint32_t bal = 0;
-            if (tid < kSub) {
-                alive = tid < sub && !S_DEAD[tid];
-                S_DEAD[tid] = 0;
-                bal = __ballot_sync(0xffffffffu, alive);
-                if (lane == 0) S_MISC[kMWarp + warp] = __popc(bal);
-            }
-            __syncthreads();
-            int m = 0;
-#pragma unroll
-            for (int w = 0; w < kSubWords; ++w) m += S_MISC[kMWarp + w];
-            if (alive) {
-                int base = 0;
-                for (int w = 0; w < warp; ++w) base += S_MISC[kMWarp + w];
-                const int at = base + __popc(bal & lanemask_lt());
-                C_BOX[at] = A_BOX[tid];
-                S_C_AREA[at] = S_A_AREA[tid];
-                S_C_SLOT[at] = S_A_SLOT[tid];
-            }
-            __syncthreads();
-            PROF_MARK(12);
-            // ---- phase 2: suppression bitmask among the m survivors (row r, bits j > r), stored word-major:
-            //      S_MASK[w * kSub + r] = word w (columns 32w .. 32w+31) of row r ----
-            // Work items = (word w, row r < min(m, 32(w+1))), flattened word-major and cut into equal slices, one per warp.
-            // A warp keeps the 32 column boxes of its current word in registers (lane = column) and streams rows past
-            // them, four at a time: one broadcast shared load and four compares per (row, word); the IoU arithmetic runs
-            // only for rows that intersect some column of the word with a comparable area (disjoint boxes: inter = 0 -> IoU 0 or
-            // NaN, never > thr; area ratio <= thr: see ratio_cut).
-            const int words = (m + 31) >> 5;
-            {
-                const int n_items = 16 * words * (words - 1) + m;  // full words contribute 32(w+1) rows each, the last one m
-                const int it_lo = static_cast<int>(static_cast<long long>(n_items) * warp / kNmsWarps);
-                const int it_hi = static_cast<int>(static_cast<long long>(n_items) * (warp + 1) / kNmsWarps);
-                int it = it_lo, w = 0;
-                while (w + 1 < words && 16 * (w + 1) * (w + 2) <= it) ++w;
-                while (it < it_hi) {
-                    const int r_begin = it - 16 * w * (w + 1);
-                    const int r_end = min(w == words - 1 ? m : 32 * (w + 1), r_begin + (it_hi - it));
-                    const int j = (w << 5) + lane;
-                    const bool jv = j < m;
-                    const float4 cb = C_BOX[jv ? j : 0];
-                    const float ca = S_C_AREA[jv ? j : 0];
-                    for (int r0 = r_begin; r0 < r_end; r0 += 4) {
-                        float4 rb[4];
-                        float ra4[4];
-                        bool ov[4], any[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            rb[u] = C_BOX[min(r0 + u, r_end - 1)];
-                            ra4[u] = S_C_AREA[min(r0 + u, r_end - 1)];
+            // ---- pair work: alone, or with the helpers (candidates + a work order pushed into their shared memory) ----
+            bool dist = false;
+            if constexpr (CL > 1) {
+                dist = static_cast<long long>(sub) * (sub / 2 + (kept - k_from)) >= kDistPairs;
+                if (dist) {
+                    for (int r2 = 1; r2 < CL; ++r2) {
+                        if (tid < sub) {
+                            cluster.map_shared_rank(A_BOX, r2)[tid] = A_BOX[tid];
+                            cluster.map_shared_rank(S_A_AREA, r2)[tid] = S_A_AREA[tid];
                         }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            ov[u] = jv && j > r0 + u && rb[u].z > cb.x && cb.z > rb[u].x && rb[u].w > cb.y && cb.w > rb[u].y &&
-                                    !(fminf(ra4[u], ca) <= ratio_cut * fmaxf(ra4[u], ca));
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) any[u] = __any_sync(0xffffffffu, ov[u]);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            if (r0 + u >= r_end) break;
-                            uint32_t bits = 0u;
-                            if (any[u]) {
-                                bool g = false;
-                                if (ov[u]) {
-                                    const float ra = ra4[u];
-                                    bool bd;
-                                    g = iou_gt_approx(rb[u], ra, cb, ca, p.thr, band, bd);
-                                    if (bd) g = iou_gt(rb[u], ra, cb, ca, p.thr);  // rare: quotient within a few ulp of thr
-                                }
-                                bits = __ballot_sync(0xffffffffu, g);
-                            }
-                            if (lane == 0) S_MASK[w * kSub + r0 + u] = bits;
+                        if (tid == 0) {
+                            int32_t *o = cluster.map_shared_rank(&S_MISC[kMOrd], r2);
+                            o[1] = sub;
+                            o[2] = k_from;
+                            o[3] = kept;
+                            o[0] = kOrdHelp;
                         }
                     }
-                    it += r_end - r_begin;
-                    ++w;
+                    cluster.sync();  // helpers start
                 }
             }
-            __syncthreads();
+            pair_round(sub, k_from, kept, 0, dist ? CL : 1);
+            if (dist) cluster_sync(); else __syncthreads();  // every verdict and mask word is in
             PROF_MARK(13);
-            // ---- sweep (warp 0) ----
+            // ---- sweep (warp 0): which candidates are kept, 32 per step ----
+            const int words = (sub + 31) >> 5;
             if (warp == 0) {
-                uint32_t km[kSubWords];  // kept bits of the groups resolved so far (warp-uniform)
+                uint32_t km[kSubWords], deadw[kSubWords];  // kept bits of the groups resolved so far / phase-1 verdicts (warp-uniform)
 #pragma unroll
-                for (int g = 0; g < kSubWords; ++g) km[g] = 0u;
+                for (int g = 0; g < kSubWords; ++g) {
+                    km[g] = 0u;
+                    deadw[g] = __ballot_sync(0xffffffffu, S_DEAD[(g << 5) + lane] != 0);
+                }
                 int kl = kept;
-                // column g of the bitmask (word g of the rows g2*32+lane, g2 <= g; word-major layout: conflict-free) is loaded one group ahead, before
-                // the dependent chain of group g-1, so the sweep never waits on shared memory
+                // column g of the bitmask (word g of the rows g2*32+lane, g2 <= g; word-major layout: conflict-free) is loaded
+                // one group ahead, before the dependent chain of group g-1, so the sweep never waits on shared memory
                 uint32_t cur[kSubWords], nxt[kSubWords];
                 cur[0] = S_MASK[lane];
 #pragma unroll
@@ -631,10 +655,9 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                         uint32_t rem = 0u;
 #pragma unroll
                         for (int g2 = 0; g2 < g; ++g2) rem |= ((km[g2] >> lane) & 1u) ? cur[g2] : 0u;
-                        rem = __reduce_or_sync(0xffffffffu, rem);
-                        const int nvalid = min(32, m - (g << 5));
+                        rem = __reduce_or_sync(0xffffffffu, rem) | deadw[g];
+                        const int nvalid = min(32, sub - (g << 5));
                         const uint32_t live = ~rem & (nvalid == 32 ? 0xffffffffu : ((1u << nvalid) - 1u));
-                        const int r = (g << 5) + lane;
                         const uint32_t diag = lane < nvalid ? cur[g] : 0u;
                         // rows that overlap a later live row of the group are the only ones whose fate matters to
                         // others: walk just those in order (usually none or a handful of the 32)
@@ -658,12 +681,6 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                             keptm = res;
                             c = allow;
                         }
-                        if ((keptm >> lane) & 1u) {
-                            const int idx = kl + __popc(keptm & lanemask_lt());
-                            KEPT_BOX[idx] = C_BOX[r];
-                            KEPT_AREA[idx] = S_C_AREA[r];
-                            KEPT_SLOT[idx] = S_C_SLOT[r];
-                        }
                         kl += c;
                         km[g] = keptm;
                     }
@@ -672,10 +689,33 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                         for (int g2 = 0; g2 <= g + 1; ++g2) cur[g2] = nxt[g2];
                     }
                 }
-                if (lane == 0) S_MISC[kMKept] = kl;
+                if (lane == 0) {
+                    S_MISC[kMKept] = kl;
+#pragma unroll
+                    for (int g = 0; g < kSubWords; ++g) S_MISC[kMKm + g] = static_cast<int32_t>(km[g]);
+                }
             }
             __syncthreads();
-            st_pairs += static_cast<long long>(m) * (m - 1) / 2;
+            // ---- append the kept candidates (in order) to the kept list, here and in every peer; clear the verdicts ----
+            if (tid < kSub) {
+                const uint32_t kmg = static_cast<uint32_t>(S_MISC[kMKm + warp]);  // tid < 256: warp == group
+                if (tid < sub && ((kmg >> lane) & 1u)) {
+                    int idx = kept + __popc(kmg & lanemask_lt());
+                    for (int g2 = 0; g2 < warp; ++g2) idx += __popc(static_cast<uint32_t>(S_MISC[kMKm + g2]));
+                    const float4 bx = A_BOX[tid];
+                    const float ar = S_A_AREA[tid];
+                    KEPT_BOX[idx] = bx;
+                    KEPT_AREA[idx] = ar;
+                    KEPT_SLOT[idx] = S_A_SLOT[tid];
+                    if constexpr (CL > 1) {
+                        for (int r2 = 1; r2 < CL; ++r2) {  // visible to the peer at the next cluster barrier
+                            cluster.map_shared_rank(KEPT_BOX, r2)[idx] = bx;
+                            cluster.map_shared_rank(KEPT_AREA, r2)[idx] = ar;
+                        }
+                    }
+                }
+                S_DEAD[tid] = 0;
+            }
             ++st_sub;
             st_walk += sub;
             kept = S_MISC[kMKept];
@@ -830,23 +870,16 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                     process_sorted([&](int i) { return sorted[piece + i]; }, min(kSortCap, lim - piece), 0);
                 PROF_MARK(5);
             }
-            // ---- replicate the new kept boxes and the verdict into the peers ----
+            // ---- the verdict into every CTA (the kept boxes were replicated sub-chunk by sub-chunk); helpers are released ----
             if constexpr (CL > 1) {
                 __syncthreads();
-                for (int i = k0 + tid; i < kept; i += kNmsThreads) {
-                    const float4 kb4 = KEPT_BOX[i];
-                    const float ka1 = KEPT_AREA[i];
-                    for (int r2 = 1; r2 < CL; ++r2) {
-                        *cluster.map_shared_rank(&KEPT_BOX[i], r2) = kb4;
-                        *cluster.map_shared_rank(&KEPT_AREA[i], r2) = ka1;
-                    }
-                }
                 if (tid < CL) {
                     int32_t *ctl = cluster.map_shared_rank(&S_MISC[kMCtl], tid);
                     ctl[0] = action;
                     ctl[1] = kept;
                     ctl[2] = mm;
                     ctl[3] = ss;
+                    *cluster.map_shared_rank(&S_MISC[kMOrd], tid) = 0;
                 }
             } else {
                 if (tid == 0) {
@@ -857,7 +890,21 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
                 }
             }
         }
-        cluster_sync();  // barrier #2
+        if constexpr (CL > 1) {
+            if (crank != 0) {
+                // helper: every cluster barrier here is either the start of a pair round (work order present) or barrier #2
+                for (;;) {
+                    cluster.sync();
+                    if (S_MISC[kMOrd] != kOrdHelp) break;
+                    pair_round(S_MISC[kMOrd + 1], S_MISC[kMOrd + 2], S_MISC[kMOrd + 3], crank, CL);
+                    cluster.sync();  // results delivered
+                }
+            } else {
+                cluster.sync();  // barrier #2
+            }
+        } else {
+            __syncthreads();  // barrier #2
+        }
         action = S_MISC[kMCtl + 0];
         kept = S_MISC[kMCtl + 1];
         m = S_MISC[kMCtl + 2];

@@ -1,12 +1,12 @@
-mkdir -p gpurun_out/r2i
-python bench.py > gpurun_out/r2i/bench.json 2> gpurun_out/r2i/bench.err; echo bench rc=$?; tail -3 gpurun_out/r2i/bench.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r2i/bench.json'))
-print('value', d['value'], d['ms_per_step'], 'launches', d['launches_per_step']); print('two', d['two_streams']); print('single', d['single_stream'])
-print(d['roofline']['frac'], d['roofline']['stage_ms'])
-print('cat', json.dumps(d['cat_layout'])[:900])
-print('clustered', {k:d['clustered'][k] for k in ('value','ms_per_step','single_stream','k1_ms','k4_ms','k5_ms')})
-print('refgpu', d['reference_gpu']['value'], 'e2e', d['e2e']['value'], d['e2e']['frac_of_h2d_ceiling'], 'cpu', d['cpu_baseline']['value'])
-PY
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2i/ref_arm.json 2> gpurun_out/r2i/ref_arm.err; tail -c 600 gpurun_out/r2i/ref_arm.json
+mkdir -p gpurun_out/r2l
+python -m pytest tests -m gpu -q -x > gpurun_out/r2l/pytest.log 2>&1; echo pytest rc=$?; tail -4 gpurun_out/r2l/pytest.log
+python tools/fuzz_parity.py 600 31 > gpurun_out/r2l/fuzz.txt 2>&1; tail -2 gpurun_out/r2l/fuzz.txt
+for cl in 1 2 8; do SARPOST_NMS_CLUSTER=$cl python tools/fuzz_parity.py 200 4$cl 2>&1 | tail -1; done
+python tools/worstcase_probe.py > gpurun_out/r2l/worst.txt 2>&1; cat gpurun_out/r2l/worst.txt
+python sar-yolo_b200/build.py --prof > /dev/null
+for b in 0 50; do SARPOST_LIB_PATH=$PWD/sar-yolo_b200/libsarpost_prof.so python tools/phase_prof.py cfg3 $b; done > gpurun_out/r2l/phase.txt 2>&1; cat gpurun_out/r2l/phase.txt
+for w in cfg3 cfg1 cfg5 cfg2; do python bench.py --workload $w --quick --steps 200 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read())
+print('$w value %.0f ms %.4f single %.4f' % (d['value'], d['ms_per_step'], d['single_stream']['ms_per_step']), {k:round(v,4) for k,v in d['roofline']['stage_ms'].items()})
+"; done
