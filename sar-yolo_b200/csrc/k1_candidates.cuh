@@ -269,9 +269,11 @@ __global__ void __launch_bounds__(kTileA, sizeof(T) == 2 ? 6 : 3) k1_fused_tma(c
     const uint32_t stage_bytes = static_cast<uint32_t>(nch) * kTileA * sizeof(T);
     unsigned char *dyn = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(dyn_smem_raw) + 127) & ~uintptr_t(127));
 
-    int next_t = 0;  // thread 0: tile index fetched ahead of its use, so the atomic's round trip is off the issue path
+    // thread 0: tile index fetched ahead of its use, so the atomic's round trip is off the issue path.  The first tile of a
+    // CTA is its block index (no round trip before the first load is in flight); the counter hands out the tiles behind
+    // the first wave: counter value v = tile gridDim.x + v.
+    int next_t = blockIdx.x;
     if (tid == 0) {
-        next_t = atomicAdd(p.tile_counter, 1);
         for (int s = 0; s < p.stages; ++s) mbar_init(&full_bar[s], 1);
         fence_barrier_init();
         for (int l = 0; l < p.g.nl; ++l) {
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(kTileA, sizeof(T) == 2 ? 6 : 3) k1_fused_tma(c
             mbar_arrive(&full_bar[s]);  // completes the phase without a transfer
             return;
         }
-        next_t = atomicAdd(p.tile_counter, 1);
+        next_t = static_cast<int>(gridDim.x) + atomicAdd(p.tile_counter, 1);
         const int b = t / p.g.tpi, r = t - b * p.g.tpi;
         ring_b[s] = b;
         ring_r[s] = r;

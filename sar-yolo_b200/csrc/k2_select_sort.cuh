@@ -54,13 +54,18 @@ __device__ __forceinline__ void for_each_candidate_in(const CandStore &st, const
         for (int tb = t0 + warp * 32; tb < t1; tb += nwarps * 32) {
             const int v = tb + lane;
             const int t = tile_first + v * tile_step;
-            const int c = (v < t1 && tmax[t] >= lo_bits) ? tcount[t] : 0;
+            // both loads are issued together (one round trip to L2, not two)
+            const uint32_t tm = v < t1 ? tmax[t] : 0u;
+            const int tc = v < t1 ? tcount[t] : 0;
+            const int c = tm >= lo_bits ? tc : 0;
             const uint32_t bal = __ballot_sync(0xffffffffu, c > 0);
             if (bal) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(list_n, __popc(bal));
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (c > 0) tile_list[base + __popc(bal & lanemask_lt())] = static_cast<uint32_t>(t);
+                // the tile's population travels with its id (regions of kTileA slots: count <= 128), so the scan below
+                // does not have to fetch it again
+                if (c > 0) tile_list[base + __popc(bal & lanemask_lt())] = static_cast<uint32_t>(t) | (st.region == kTileA ? static_cast<uint32_t>(c) << 24 : 0u);
             }
         }
         __syncthreads();
@@ -74,8 +79,9 @@ __device__ __forceinline__ void for_each_candidate_in(const CandStore &st, const
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
                     const bool on = e0 + u < n_act;
-                    tt[u] = on ? tile_list[e0 + u] : 0u;
-                    c[u] = on ? tcount[tt[u]] - lane * 4 : 0;  // valid entries of this lane
+                    const uint32_t ent = on ? tile_list[e0 + u] : 0u;
+                    tt[u] = ent & 0xffffffu;
+                    c[u] = static_cast<int>(ent >> 24) - lane * 4;  // valid entries of this lane (0 - ... when the entry is off)
                     v[u] = make_uint4(0u, 0u, 0u, 0u);
                     if (c[u] > 0) v[u] = *reinterpret_cast<const uint4 *>(score + static_cast<size_t>(tt[u]) * kTileA + lane * 4);
                 }

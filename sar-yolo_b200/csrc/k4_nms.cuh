@@ -38,7 +38,8 @@ namespace sarpost {
 #ifdef SARPOST_PHASE_PROF
 __device__ unsigned long long g_phase_n[16], g_phase_max[16];  // visits / longest single visit per phase
 __device__ unsigned long long g_phase[16];  // cycles of block 0 per phase: 0 prologue, 1 collect, 2 share phase 1, 3 deliver + barrier 1,
-// 4 sort, 9 master tail + replicate + barrier 2, 8 publish; inside process_sorted: 10 load, 11 incremental phase 1, 12 compaction, 13 bitmask, 14 sweep
+// 4 sort, 5 radix fallback, 6 zoom histogram, 9 master tail + barrier 2, 8 publish; inside process_sorted: 10 load, 13 pair round (phase 1 +
+// bitmask, incl. its cluster barriers), 11 sweep (warp 0), 14 append to the kept list + barriers
 #define PROF_MARK(i)                                                         \
     do {                                                                     \
         if (blockIdx.x == 0 && threadIdx.x == 0) {                           \
@@ -495,11 +496,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         if (tid == 0) S_MISC[kMNAll] = tot;
     }
     __syncthreads();
-    if constexpr (CL > 1) {  // every CTA of the cluster has read the histogram: the master zeroes it
-        cluster.sync();
-        if (crank == 0)
-            for (int i = tid; i < kBuckets; i += kNmsThreads) p.st.hist[static_cast<int64_t>(b) * kBuckets + i] = 0;
-    }
+    // Distributed shared memory may only be touched once every CTA of the cluster runs and has initialised its control
+    // block: each CTA arrives here and waits right before its first remote access (by then the barrier is long complete)
+    if constexpr (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    bool cluster_ready = CL == 1;
     PROF_MARK(0);
     const int n_all = S_MISC[kMNAll];
     const int n_limit = min(n_all, p.max_nms);  // ops.py:285-286: only the top max_nms ranks are eligible
@@ -694,6 +694,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #pragma unroll
                     for (int g = 0; g < kSubWords; ++g) S_MISC[kMKm + g] = static_cast<int32_t>(km[g]);
                 }
+                PROF_MARK(11);
             }
             __syncthreads();
             // ---- append the kept candidates (in order) to the kept list, here and in every peer; clear the verdicts ----
@@ -791,6 +792,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         const unsigned long long *mine = do_p1 ? SURV : PLIST;
         const int s_cnt = do_p1 ? S_MISC[kMSurvCnt] : my_n;
         // ---- survivors -> master (offset from a remote atomic on the master's counters) ----
+        if constexpr (CL > 1) {
+            if (!cluster_ready) {
+                asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+                cluster_ready = true;
+            }
+        }
         int32_t *ctr = &S_MISC[kMCtr + par * 4];
         if constexpr (CL > 1) ctr = cluster.map_shared_rank(&S_MISC[kMCtr + par * 4], 0);
         if (tid == 0) {
@@ -1054,7 +1061,13 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
         }
         atomicAdd(o + 1, static_cast<unsigned long long>(st_pairs));
     }
-    if constexpr (CL > 1) cluster.sync();  // no CTA may exit while a peer can still address its shared memory
+    if constexpr (CL > 1) {
+        if (!cluster_ready) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // no attempt ran (nothing to do)
+        cluster.sync();  // no CTA may exit while a peer can still address its shared memory
+        // every CTA read the score histogram in its prologue: leave it zeroed for the next call (workspace_clean)
+        if (crank == 0)
+            for (int i = tid; i < kBuckets; i += kNmsThreads) p.st.hist[static_cast<int64_t>(b) * kBuckets + i] = 0;
+    }
     PROF_MARK(8);
 #undef PLIST
 #undef SURV

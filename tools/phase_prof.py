@@ -17,7 +17,7 @@ N=20
 for _ in range(N): sarpost.postprocess_fused(levels,spec,return_padded=True,**kw)
 f(buf,1)
 names={0:'prologue(hist scan)',1:'collect',2:'share phase1',3:'deliver+barrier1',4:'sort',5:'radix fallback',6:'zoom histogram',9:'tail+replicate+barrier2',8:'publish',
-       10:'ps: load',11:'ps: incr phase1',12:'ps: compaction',13:'ps: bitmask',14:'ps: sweep'}
+       10:'ps: load',13:'ps: pair round',11:'ps: sweep (warp 0)',14:'ps: append+barriers'}
 tot=sum(buf[i] for i in range(16))
 print(wl, 'blobs', blobs)
 for i,n in names.items(): print(f"{n:26s} {buf[i]/N:10.0f} cyc  {buf[i]/tot*100:5.1f}%   visits/launch {buf[16+i]/N:6.2f}  mean {buf[i]/max(buf[16+i],1):8.0f}  max {buf[32+i]:8d}")
