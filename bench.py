@@ -369,6 +369,11 @@ def time_steps(cx, step, n, streams=None):
 def stage_means(cx, step, n):
     """Per-kernel CUDA-event durations recorded by the library on the launching stream (mean over n steps)."""
     ops = cx.sarpost.ops
+    cx.torch.cuda.synchronize()
+    # a spin kernel first, long enough for the host to get ahead of the device: the events then bracket back-to-back kernels
+    # and an event-to-event span is the kernel's duration, not the host's launch cadence (small workloads: the host needs
+    # longer per call than the device)
+    cx.torch.cuda._sleep(int(min(n, 400) * 200_000))
     ops.stage_timing(True, accumulate=True)
     for _ in range(n):
         step()
@@ -737,8 +742,27 @@ def main():
             o_, c_ = step()
         cx.barrier()
         res = {"launches_per_step": sarpost.ops.last_launch_count(), "counts": c_}
-        # (a) strictly one batch in flight: K steps back to back on the current stream
-        res["ms_single"] = time_steps(cx, step, steps)
+        # (a) strictly one batch in flight: K steps back to back on the current stream, through a prepared plan
+        # (sarpost.FusedPlan / sarpost_plan_*: the serving-loop form of the same call — geometry validated and tensor maps
+        # encoded once, outputs rotating over 4 preallocated sets) and through the general entry point
+        plan = sarpost.FusedPlan(sets[0], spec, **kw)
+        plan_ring = [(torch.empty((bs, kw["max_det"], 6 + spec.nm), dtype=torch.float32, device=dev),
+                      torch.empty((bs,), dtype=torch.int32, device=dev)) for _ in range(4)]
+        qk = [0]
+
+        def plan_step():
+            qk[0] += 1
+            return plan(nxt(), out=plan_ring[qk[0] & 3])
+
+        for _ in range(4):
+            o_p, c_p = plan_step()
+        torch.cuda.synchronize()
+        o_g, c_g = sarpost.postprocess_fused(sets[0], spec, return_padded=True, **kw)
+        o_p, c_p = plan(sets[0])
+        res["plan_same"] = bool(torch.equal(c_p, c_g)) and all(bool(torch.equal(o_p[b, :n], o_g[b, :n])) for b, n in enumerate(c_g.tolist()))
+        res["ms_general"] = time_steps(cx, step, steps)
+        res["ms_single"] = time_steps(cx, plan_step, steps)
+        res["launches_per_step_plan"] = sarpost.ops.last_launch_count()
         res["ms_two"] = res["ms_pipe"] = None
         res["pipe_same"] = None
         if args.streams > 1:
@@ -786,15 +810,21 @@ def main():
         # pass over the same steps with CUDA events around every kernel (recorded by the library on the launching stream, no
         # host sync per step, mean read afterwards).  Kept out of the passes `value` comes from: timing events between
         # kernels cost a few % by removing the overlap of consecutive launches.
-        res["stage"] = stage_means(cx, step, with_stage_steps)
-        res["step"] = step
+        res["stage"] = stage_means(cx, plan_step, with_stage_steps)
+        res["step"] = plan_step
+        res["plan"] = plan
         return res
 
     def summarize(res, steps):
-        vals = cx.max_over_ranks(res["ms_single"], res["ms_two"] or 0.0, res["ms_pipe"] or 0.0)
+        vals = cx.max_over_ranks(res["ms_single"], res["ms_two"] or 0.0, res["ms_pipe"] or 0.0, res["ms_general"])
         rate = lambda ms_: bs * n_gpus * steps / (ms_ / 1e3)  # noqa: E731
         out_ = {"single_stream": {"value": rate(vals[0]), "unit": "images/s", "ms_per_step": vals[0] / steps,
-                                  "note": "strictly one batch in flight (all K steps on one stream)"}}
+                                  "rows_identical_to_general_call": res["plan_same"],
+                                  "note": "strictly one batch in flight (all K steps on one stream), each step one call of a prepared "
+                                          "plan (sarpost.FusedPlan -> sarpost_plan_run)"},
+                "single_stream_general": {"value": rate(vals[3]), "unit": "images/s", "ms_per_step": vals[3] / steps,
+                                          "note": "the same through the general entry point (sarpost.postprocess_fused -> sarpost_fused: "
+                                                  "arguments validated, tensor maps encoded, outputs allocated on every call)"}}
         if res["ms_two"] is not None:
             out_["two_streams"] = {"value": rate(vals[1]), "unit": "images/s", "ms_per_step": vals[1] / steps,
                                    "note": f"the same K steps issued round-robin on {args.streams} independent CUDA streams through sarpost_fused"}
@@ -820,9 +850,12 @@ def main():
     clocks.stop()
     main_sum = summarize(main, args.steps)
     best = main_sum.get("pipelined") or main_sum["single_stream"]
+    headline_mode = "pipelined" if best is not main_sum["single_stream"] else "single_stream"
+    if main_sum["single_stream"]["value"] > best["value"]:
+        best, headline_mode = main_sum["single_stream"], "single_stream"  # small workloads: one prepared call per step beats the pipeline's stream hops
     value, ms = best["value"], best["ms_per_step"] * args.steps
     single, two_streams = main_sum["single_stream"], main_sum.get("two_streams")
-    launches_per_step = main.get("launches_per_step_pipelined") or main["launches_per_step"]
+    launches_per_step = (main.get("launches_per_step_pipelined") if headline_mode == "pipelined" else None) or main["launches_per_step_plan"]
     pipe_same_main = main["pipe_same"]
     n_det = int(counts.sum().item())
     # the concatenated layout (one (B, no, H, W) tensor per level, as the unpatched head returns them), same passes
@@ -907,6 +940,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}" + (f" [clustered inputs, blobs={args.blobs}]" if args.blobs else ""),
                        "images_per_gpu": bs, "global_batch": bs * n_gpus, "anchors": anchors, "channels": spec.no, "streams": args.streams,
+                       "value_is": headline_mode,
                        "in_flight": ("one batch" if args.streams == 1 else
                                      "software pipeline of depth 2 (sarpost_pipeline_submit per step, one sarpost_pipeline_wait at the end): every "
                                      "step is the whole path for one batch; batch i runs on stream i % 2 and its decode kernel is chained to the "
@@ -925,7 +959,7 @@ def main():
                                "126 MB L2), so every step reads its inputs from HBM; no flush" % (hot_bytes / 1e6, n_sets, n_sets * hot_bytes / 1e6))),
                        "input_sets": n_sets,
                        "candidates_per_image": n_cand / bs, "detections_per_image": n_det / bs},
-            "single_stream": single, "two_streams": two_streams, "roofline": roofline, "cat_layout": cat_layout, "clustered": clustered, "reference_gpu": ref_gpu, "cpu_baseline": cpu, "e2e": e2e,
+            "single_stream": single, "single_stream_general": main_sum.get("single_stream_general"), "two_streams": two_streams, "roofline": roofline, "cat_layout": cat_layout, "clustered": clustered, "reference_gpu": ref_gpu, "cpu_baseline": cpu, "e2e": e2e,
             "sahi": sahi, "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step, "clocks": clocks.summary(),
         }
         emit(line)

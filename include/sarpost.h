@@ -181,6 +181,39 @@ int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *pa
                       int32_t *counts, int32_t *kept_index, void *workspace, int64_t workspace_bytes,
                       void *stream);
 
+
+/*
+ * Plans.  A serving loop calls sarpost_fused with the same geometry and thresholds thousands of times; only the
+ * addresses change.  A plan freezes everything else — validated geometry, candidate filter (the `classes` list is
+ * folded in at creation), workspace binding, launch configuration, the TMA tensor maps (re-encoded only for a level
+ * whose address changed) — so a run is three kernel launches and nothing more on the host: the cached form SURVEY §7
+ * (hard part 7) asks for.  Results are those of sarpost_fused on the same inputs, bit for bit.
+ *   create   `head` gives geometry, dtype and layout (its pointers are only checked for alignment class); `params` as for
+ *            sarpost_fused with workspace_clean = 1: `workspace` (>= sarpost_workspace_bytes) must have been prepared with
+ *            sarpost_workspace_prepare and belongs to the plan until it is destroyed.  Peer buffers (n_peers > 0) are fixed
+ *            at creation; rescale / stats / res_* pointers of `params` are ignored — they travel in the io block.
+ *   run      all work on `stream`.  Runs of one plan must be stream-ordered (one plan per stream); the plan is updated in
+ *            place, so it must not be run from two threads at once.
+ */
+typedef struct sarpost_plan sarpost_plan_t;
+typedef struct sarpost_plan_io {
+    const void *data[SARPOST_MAX_LEVELS];  /* as sarpost_head_t.data / cls / emb / state */
+    const void *cls[SARPOST_MAX_LEVELS];
+    const void *emb[SARPOST_MAX_LEVELS];
+    const void *state[SARPOST_MAX_LEVELS];
+    float *out;            /* as sarpost_fused */
+    int32_t *counts;
+    int32_t *kept_index;   /* or NULL */
+    const float *rescale;  /* as sarpost_nms_params_t.rescale, or NULL */
+    int64_t *stats;        /* as sarpost_nms_params_t.stats, or NULL */
+    float *res_boxes;      /* as sarpost_nms_params_t.res_boxes / res_embeds, or NULL */
+    float *res_embeds;
+} sarpost_plan_io_t;
+int32_t sarpost_plan_create(const sarpost_head_t *head, const sarpost_nms_params_t *params, void *workspace,
+                            int64_t workspace_bytes, sarpost_plan_t **plan);
+int32_t sarpost_plan_run(sarpost_plan_t *plan, const sarpost_plan_io_t *io, void *stream);
+void sarpost_plan_destroy(sarpost_plan_t *plan);
+
 /*
  * Extras (raw embedding + sigmoid state, head.py:247) of an explicit list of n (image, anchor) pairs,
  * for callers that learn which rows need them only later (e.g. after sarpost_merge_tiles).

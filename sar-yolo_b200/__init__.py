@@ -13,7 +13,7 @@ the alias module at the repo root, or `importlib.import_module("sar-yolo_b200")`
 from . import synth  # noqa: F401  (pure torch, no native code)
 from . import _lib  # noqa: F401  (raises if libsarpost.so is missing)
 from . import ops, plugin, dist  # noqa: F401
-from .ops import (HeadSpec, HostContext, Pipeline, StateMLP, state_head, decode, gather_extras, match_predictions, match_from_iou, split_levels, cat_levels, merge_tiles, non_max_suppression, postprocess_fused,  # noqa: F401
+from .ops import (HeadSpec, HostContext, Pipeline, FusedPlan, StateMLP, state_head, decode, gather_extras, match_predictions, match_from_iou, split_levels, cat_levels, merge_tiles, non_max_suppression, postprocess_fused,  # noqa: F401
                   postprocess_host)
 from .plugin import patch, unpatch  # noqa: F401
 from ._lib import SarpostError  # noqa: F401

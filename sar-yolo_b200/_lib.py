@@ -43,6 +43,16 @@ class NmsParams(C.Structure):
     ]
 
 
+class PlanIO(C.Structure):
+    """sarpost_plan_io_t"""
+    _fields_ = [
+        ("data", C.c_void_p * MAX_LEVELS), ("cls", C.c_void_p * MAX_LEVELS), ("emb", C.c_void_p * MAX_LEVELS),
+        ("state", C.c_void_p * MAX_LEVELS),
+        ("out", C.c_void_p), ("counts", C.c_void_p), ("kept_index", C.c_void_p), ("rescale", C.c_void_p), ("stats", C.c_void_p),
+        ("res_boxes", C.c_void_p), ("res_embeds", C.c_void_p),
+    ]
+
+
 class SarpostError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libsarpost error {code}: {msg}")
@@ -62,6 +72,9 @@ SYMBOLS = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "sarpost_fused": (C.c_int32, [C.POINTER(Head), C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int64, C.c_void_p]),
+    "sarpost_plan_create": (C.c_int32, [C.POINTER(Head), C.POINTER(NmsParams), C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "sarpost_plan_run": (C.c_int32, [C.c_void_p, C.POINTER(PlanIO), C.c_void_p]),
+    "sarpost_plan_destroy": (None, [C.c_void_p]),
     "sarpost_gather_extras": (C.c_int32, [C.POINTER(Head), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "sarpost_merge_tiles": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(NmsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

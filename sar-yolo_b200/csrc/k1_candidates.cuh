@@ -117,20 +117,32 @@ __device__ __forceinline__ float4 xywh2xyxy_rn(const float4 c) {
     return make_float4(__fsub_rn(c.x, hw), __fsub_rn(c.y, hh), __fadd_rn(c.x, hw), __fadd_rn(c.y, hh));
 }
 
+// Staging area of the multi-label emission (below): the tile's boxes by thread, and per compacted slot the score and
+// its source (thread << 3 | class).
+constexpr int kClsCache = 8;
+constexpr int kStageEmitBytes = kTileA * 16 + kTileA * kClsCache * (4 + 2);
+
 // Block-wide (kTileA threads) ordered emission of this tile's candidates.
 //   score(j): class probability j of this thread's anchor.
-// scratch: int[8] shared.  Contains two __syncthreads().
+//   anchor0:  anchor index of thread 0 of the tile (thread t of a valid tile holds anchor0 + t).
+//   stg:      kStageEmitBytes of 16-byte aligned shared memory that no thread reads through score() any more once every
+//             thread has evaluated its classes (the TMA kernel passes the tile's own stage buffer), or nullptr.
+// scratch: int[8] shared.  Contains two __syncthreads() (three on the staged multi-label path).
+//
+// Multi-label rows (ops.py:268-270) of one anchor are adjacent slots, so thread t's stores start at a slot that depends
+// on every earlier thread: written straight from the registers a warp's 32 stores hit 32 different sectors for every one
+// of the <= nc rounds (3 arrays each).  With `stg` the compacted tile is assembled in shared memory first and then
+// copied out slot-per-thread: fully coalesced 512 B / 128 B / 128 B warp stores.
 template <class ScoreFn>
-__device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, uint32_t anchor, int nc,
+__device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, uint32_t anchor, uint32_t anchor0, int nc,
                                                 const CandFilter &f, const ScoreFn &score, const CandStore &st,
-                                                int b, int tile_in_image, int *scratch) {
+                                                int b, int tile_in_image, int *scratch, unsigned char *stg) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int cnt = 0;
     float best = 0.0f;
     int bj = 0;
     // multi-label with few classes (the SAR posture heads have nc = 6): every probability is evaluated once and
     // kept in registers across the block scan; larger heads re-evaluate in the write loop
-    constexpr int kClsCache = 8;
     float pc[kClsCache];
     uint32_t pass = 0u;
     const bool cached = f.multi_label && nc <= kClsCache;
@@ -191,7 +203,39 @@ __device__ __forceinline__ void emit_candidates(bool valid, const float4 xyxy, u
     int64_t pos = static_cast<int64_t>(b) * st.cap + static_cast<int64_t>(tile_in_image) * st.region + base + (inc - cnt);
     int32_t *hist = st.hist + static_cast<int64_t>(b) * kBuckets;
     const bool sampled = (anchor % kHistSample) == 0;  // 1-in-8 sample keeps the RED traffic negligible
-    if (cnt) {
+    if (cached && stg != nullptr) {
+        // every thread is past its last score() read (the barrier above): the staging area may be overwritten
+        float4 *sx = reinterpret_cast<float4 *>(stg);
+        float *sscore = reinterpret_cast<float *>(stg + kTileA * 16);
+        uint16_t *ssrc = reinterpret_cast<uint16_t *>(stg + kTileA * 16 + kTileA * kClsCache * 4);
+        int tot = 0;
+#pragma unroll
+        for (int w = 0; w < kTileA / 32; ++w) tot += scratch[w];
+        if (cnt) {
+            sx[tid] = xyxy;
+            int o = base + (inc - cnt);
+#pragma unroll
+            for (int j = 0; j < kClsCache; ++j) {
+                if ((pass >> j) & 1u) {
+                    sscore[o] = pc[j];
+                    ssrc[o] = static_cast<uint16_t>((tid << 3) | j);
+                    ++o;
+                }
+            }
+        }
+        __syncthreads();
+        const int64_t g0 = static_cast<int64_t>(b) * st.cap + static_cast<int64_t>(tile_in_image) * st.region;
+        for (int k = tid; k < tot; k += kTileA) {
+            const uint32_t src = ssrc[k];
+            const uint32_t t = src >> 3, j = src & 7u;
+            const float sc = sscore[k];
+            st.box[g0 + k] = sx[t];
+            st.score[g0 + k] = sc;
+            st.key[g0 + k] = (anchor0 + t) * static_cast<uint32_t>(nc) + j;
+            if (((anchor0 + t) % kHistSample) == 0) atomicAdd(hist + score_bucket(__float_as_uint(sc)), 1);
+        }
+        fence_proxy_async();  // TMA kernel: the staging area is the stage buffer the next bulk load lands in
+    } else if (cnt) {
         if (cached) {
 #pragma unroll
             for (int j = 0; j < kClsCache; ++j) {
@@ -322,7 +366,8 @@ __global__ void __launch_bounds__(kTileA, sizeof(T) == 2 ? 6 : 3) k1_fused_tma(c
         const int yy = fast_div(pos, w, p.g.lvl_w_magic[l]), xx = pos - yy * w;
         const float4 xyxy = xywh2xyxy_rn(decode_xywh(acc, xx, yy, p.g.lvl_stride[l]));
         auto score = [&](int j) { return sigmoid_rn(to_f32(buf[(4 * kRegMax + j) * kTileA])); };
-        emit_candidates(valid, xyxy, static_cast<uint32_t>(p.g.lvl_aoff[l] + pos), p.g.nc, p.f, score, p.st, b, r, scratch);
+        emit_candidates(valid, xyxy, static_cast<uint32_t>(p.g.lvl_aoff[l] + pos), static_cast<uint32_t>(p.g.lvl_aoff[l] + pos - tid), p.g.nc, p.f,
+                        score, p.st, b, r, scratch, dyn + static_cast<size_t>(s) * stage_bytes);
         // emit_candidates ended with __syncthreads(): stage s (buffer and ring entry) is free again
         if (tid == 0) issue(s);
         if (++s == p.stages) { s = 0; phase ^= 1u; }
@@ -343,6 +388,7 @@ struct K1LdgParams {
 template <typename T>
 __global__ void __launch_bounds__(kTileA) k1_fused_ldg(const __grid_constant__ K1LdgParams p) {
     __shared__ int scratch[8];
+    __shared__ __align__(16) unsigned char stg[kStageEmitBytes];
     const int r = blockIdx.x, b = blockIdx.y;
     const int l = tile_level(p.g, r);
     const int hw = p.g.lvl_hw[l];
@@ -355,7 +401,8 @@ __global__ void __launch_bounds__(kTileA) k1_fused_ldg(const __grid_constant__ K
     const int yy = fast_div(pc, w, p.g.lvl_w_magic[l]), xx = pc - yy * w;
     const float4 xyxy = xywh2xyxy_rn(decode_xywh(acc, xx, yy, p.g.lvl_stride[l]));
     auto score = [&](int j) { return sigmoid_rn(to_f32(__ldg(base_cls + static_cast<int64_t>(j) * hw))); };
-    emit_candidates(valid, xyxy, static_cast<uint32_t>(p.g.lvl_aoff[l] + pc), p.g.nc, p.f, score, p.st, b, r, scratch);
+    emit_candidates(valid, xyxy, static_cast<uint32_t>(p.g.lvl_aoff[l] + pc), static_cast<uint32_t>(p.g.lvl_aoff[l] + pos - threadIdx.x), p.g.nc,
+                    p.f, score, p.st, b, r, scratch, stg);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -373,6 +420,7 @@ struct K1DecodedParams {
 template <typename T>
 __global__ void __launch_bounds__(kTileA) k1_decoded(const __grid_constant__ K1DecodedParams p) {
     __shared__ int scratch[8];
+    __shared__ __align__(16) unsigned char stg[kStageEmitBytes];
     const int r = blockIdx.x, b = blockIdx.y;
     const int64_t a = static_cast<int64_t>(r) * kTileA + threadIdx.x;
     const bool valid = a < p.anchors;
@@ -382,7 +430,7 @@ __global__ void __launch_bounds__(kTileA) k1_decoded(const __grid_constant__ K1D
                                     to_f32(__ldg(base + 3 * p.anchors)));
     const float4 xyxy = xywh2xyxy_rn(xywh);
     auto score = [&](int j) { return to_f32(__ldg(base + static_cast<int64_t>(4 + j) * p.anchors)); };
-    emit_candidates(valid, xyxy, static_cast<uint32_t>(ac), p.nc, p.f, score, p.st, b, r, scratch);
+    emit_candidates(valid, xyxy, static_cast<uint32_t>(ac), static_cast<uint32_t>(r) * kTileA, p.nc, p.f, score, p.st, b, r, scratch, stg);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -412,8 +460,8 @@ __global__ void __launch_bounds__(kTileA) k1_labels(const __grid_constant__ K1La
     const int cls = valid ? static_cast<int>(row[0]) : -1;  // lb[:, 0].long()
     const float4 xyxy = xywh2xyxy_rn(make_float4(row[1], row[2], row[3], row[4]));
     auto score = [&](int j) { return j == cls ? 1.0f : 0.0f; };
-    emit_candidates(valid && cls >= 0 && cls < p.nc, xyxy, p.first_anchor + static_cast<uint32_t>(i), p.nc, p.f, score, p.st, b,
-                    p.first_tile + lt, scratch);
+    emit_candidates(valid && cls >= 0 && cls < p.nc, xyxy, p.first_anchor + static_cast<uint32_t>(i),
+                    p.first_anchor + static_cast<uint32_t>(lt) * kTileA, p.nc, p.f, score, p.st, b, p.first_tile + lt, scratch, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -87,14 +87,41 @@ __device__ __forceinline__ float load_elem(const void *base, int64_t idx, bool i
     return is_half ? __half2float(__ldg(static_cast<const __half *>(base) + idx)) : __ldg(static_cast<const float *>(base) + idx);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// n columns by one warp, lane-strided: up to eight independent loads per lane are in flight before the first store (a
+// plain load/store loop serialises on the possible aliasing of source and destination).  `ld(c)` returns column c,
+// `st(c, v)` consumes it.
+template <class Load, class Store>
+__device__ __forceinline__ void copy_cols(int n, int lane, const Load &ld, const Store &st) {
+    for (int c0 = lane; c0 < n; c0 += 256) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (c0 + 32 * u < n) v[u] = ld(c0 + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (c0 + 32 * u < n) st(c0 + 32 * u, v[u]);
+    }
+}
+
 // Extras of (image b, anchor) for modes 0 and 1: store(c, value) for c = lane, lane + 32, ... < nm.  Raw embedding
 // columns are copied, state columns pass through the sigmoid (head.py:247); a decoded prediction is copied verbatim.
-template <class Store>
+// kPrefetch: nothing is loaded or stored, the lines are only requested into the L2 (the caller comes back for them).
+template <bool kPrefetch = false, class Store>
 __device__ __forceinline__ void gather_extras_row(const ExtrasSrc &e, int b, uint32_t anchor, int lane, const Store &store) {
     const bool hf = e.is_half != 0;
+    const int esz = hf ? 2 : 4;
+    auto run = [&](const void *base, int64_t at, int64_t cstride, int n, int c_out, bool sig) {
+        if constexpr (kPrefetch) {
+            for (int c = lane; c < n; c += 32) prefetch_l2(static_cast<const char *>(base) + (at + c * cstride) * esz);
+        } else {
+            copy_cols(n, lane, [&](int c) { return load_elem(base, at + c * cstride, hf); },
+                      [&](int c, float v) { store(c_out + c, sig ? sigmoid_rn(v) : v); });
+        }
+    };
     if (e.mode == 0) {
-        const int64_t at = (static_cast<int64_t>(b) * e.channels + 4 + e.nc) * e.anchors + anchor;
-        for (int c = lane; c < e.nm; c += 32) store(c, load_elem(e.pred, at + c * e.anchors, hf));
+        run(e.pred, (static_cast<int64_t>(b) * e.channels + 4 + e.nc) * e.anchors + anchor, e.anchors, e.nm, 0, false);
         return;
     }
     int l = 0;
@@ -102,24 +129,143 @@ __device__ __forceinline__ void gather_extras_row(const ExtrasSrc &e, int b, uin
     for (int i = 1; i < kMaxLevels; ++i) l += (i < e.nl && anchor >= static_cast<uint32_t>(e.lvl_aoff[i])) ? 1 : 0;
     const int64_t hw = e.lvl_hw[l];
     const int64_t pos = anchor - e.lvl_aoff[l];
+    const int n_raw = e.n_extra_raw, n_sig = e.nm - e.n_extra_raw;
     if (!e.split) {
         const int64_t at = (static_cast<int64_t>(b) * e.no + 4 * kRegMax + e.nc) * hw + pos;
-        for (int c = lane; c < e.nm; c += 32) {
-            const float v = load_elem(e.lvl_ptr[l], at + c * hw, hf);
-            store(c, c < e.n_extra_raw ? v : sigmoid_rn(v));
+        run(e.lvl_ptr[l], at, hw, n_raw, 0, false);
+        run(e.lvl_ptr[l], at + n_raw * hw, hw, n_sig, n_raw, true);
+        return;
+    }
+    if (e.emb_cl) {  // one contiguous run of n_raw elements per kept row
+        if constexpr (kPrefetch) {
+            const char *row = static_cast<const char *>(e.lvl_emb[l]) + (static_cast<int64_t>(b) * hw + pos) * n_raw * esz;
+            for (int o = lane * 128; o < n_raw * esz; o += 32 * 128) prefetch_l2(row + o);
+        } else {
+            run(e.lvl_emb[l], (static_cast<int64_t>(b) * hw + pos) * n_raw, 1, n_raw, 0, false);
+        }
+    } else {
+        run(e.lvl_emb[l], static_cast<int64_t>(b) * n_raw * hw + pos, hw, n_raw, 0, false);
+    }
+    run(e.lvl_state[l], static_cast<int64_t>(b) * n_sig * hw + pos, hw, n_sig, n_raw, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: one warp per output row.  Row = x1,y1,x2,y2,conf,cls,extras (ops.py:272/275, :311).
+// Extras come from the decoded prediction (nms_decoded), from the raw level tensors (fused: raw
+// embedding, sigmoid state — head.py:247), or from the source detection rows (merge).
+// ---------------------------------------------------------------------------------------------
+struct GatherParams {
+    CandStore st;
+    ExtrasSrc ex;
+    const uint32_t *kept_slot;  // [B*max_det]
+    const int32_t *counts;      // [B]
+    float *out;                 // [B, max_det, 6+nm]
+    int32_t *kept_index;        // [B*max_det] or nullptr
+    const float *rescale;       // [B,5] pad_x, pad_y, gain, w0, h0 or nullptr (ops.scale_boxes + clip_boxes)
+    int32_t max_det;
+    int32_t tail_cols;          // columns reserved (unwritten) at the end of every output row
+    // fused gather + exchange: rows/counts are stored into every rank's buffer (P2P-mapped pointers over NVLink)
+    float *peer_out[8];
+    int32_t *peer_counts[8];
+    int32_t n_peers, peer_slot_offset;
+    // results layout (sarpost_nms_params_t.res_boxes): 7-column boxes with the state id + contiguous embeddings
+    float *res_boxes;    // [B, max_det, 7] x1,y1,x2,y2,state_id,conf,cls or nullptr
+    float *res_embeds;   // [B, max_det, res_n_raw]
+    int32_t res_n_raw;   // leading extras columns that are the embedding; the remaining nm - res_n_raw are state probabilities
+};
+
+// ops.scale_boxes (utils/ops.py:92-127, padding=True, xyxy) followed by clip_boxes (:319-338), in torch's fp32
+// operation order: subtract the pad, true division by the gain, clamp to the original image.
+__device__ __forceinline__ float4 rescale_box(float4 b, const float *rs) {
+    const float px = rs[0], py = rs[1], gain = rs[2], w0 = rs[3], h0 = rs[4];
+    b.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.x, px), gain), 0.0f), w0);
+    b.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.y, py), gain), 0.0f), h0);
+    b.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.z, px), gain), 0.0f), w0);
+    b.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.w, py), gain), 0.0f), h0);
+    return b;
+}
+
+constexpr int kGatherWarps = 8;
+
+// One output row (image b, row r) by one warp: candidate `slot` with key `key`.
+__device__ __forceinline__ void gather_row(const GatherParams &p, int b, int r, int lane, uint32_t slot, uint32_t key) {
+    const int row_len = 6 + p.ex.nm + p.tail_cols;
+    // destinations of this row: the local output, or the same slot in every rank's buffer (peer stores)
+    const int n_dst = p.n_peers > 0 ? p.n_peers : 1;
+    const int64_t img = p.n_peers > 0 ? p.peer_slot_offset + b : b;
+    auto dst = [&](int q) { return (p.n_peers > 0 ? p.peer_out[q] : p.out) + (img * p.max_det + r) * row_len; };
+    const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
+    if (p.ex.mode == 2) {
+        const float *src = p.ex.dets + (static_cast<int64_t>(b) * p.st.tpi * p.ex.dets_per_tile + key) * p.ex.row_len;
+        const float4 bx = p.st.box[seg + slot];
+        for (int c = lane; c < 6 + p.ex.nm; c += 32) {
+            const float v = c == 0 ? bx.x : c == 1 ? bx.y : c == 2 ? bx.z : c == 3 ? bx.w : src[c];
+            for (int q = 0; q < n_dst; ++q) dst(q)[c] = v;
+        }
+        if (lane == 0 && p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
+        return;
+    }
+    const uint32_t anchor = key / static_cast<uint32_t>(p.ex.nc), cls = key - anchor * static_cast<uint32_t>(p.ex.nc);
+    if (p.res_boxes) {
+        // models/yolo/jde/predict.py:52-66: boxes = cat(xyxy, argmax(states), conf, cls), embeds = the raw embedding columns
+        const int64_t row = static_cast<int64_t>(b) * p.max_det + r;
+        const int n_raw = p.res_n_raw, n_sig = p.ex.nm - n_raw;
+        float *emb = p.res_embeds + row * n_raw;
+        float best = -1.0f;  // probabilities are >= 0
+        int best_i = 0x7fffffff;
+        if (p.ex.nm > 0 && p.ex.mode == 0 && anchor >= static_cast<uint32_t>(p.ex.anchors)) {
+            for (int c = lane; c < n_raw; c += 32) emb[c] = 0.0f;  // apriori label row: zero extras (ops.py:258) -> state id 0
+            if (lane == 0 && n_sig > 0) { best = 0.0f; best_i = 0; }
+        } else if (p.ex.nm > 0) {
+            gather_extras_row(p.ex, b, anchor, lane, [&](int c, float v) {
+                if (c < n_raw) emb[c] = v;
+                else if (v > best) { best = v; best_i = c - n_raw; }  // ascending c per lane + strict > : first maximum
+            });
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+        }
+        if (lane == 0) {
+            float4 bx = p.st.box[seg + slot];
+            if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
+            float *o = p.res_boxes + row * 7;
+            o[0] = bx.x;
+            o[1] = bx.y;
+            o[2] = bx.z;
+            o[3] = bx.w;
+            o[4] = n_sig > 0 ? static_cast<float>(best_i) : -1.0f;
+            o[5] = p.st.score[seg + slot];
+            o[6] = static_cast<float>(cls);
+            if (p.kept_index) p.kept_index[row] = static_cast<int32_t>(key);
         }
         return;
     }
-    const int n_raw = e.n_extra_raw, n_sig = e.nm - e.n_extra_raw;
-    if (e.emb_cl) {  // one contiguous run of n_raw elements per kept row
-        const int64_t at = (static_cast<int64_t>(b) * hw + pos) * n_raw;
-        for (int c = lane; c < n_raw; c += 32) store(c, load_elem(e.lvl_emb[l], at + c, hf));
-    } else {
-        const int64_t at = static_cast<int64_t>(b) * n_raw * hw + pos;
-        for (int c = lane; c < n_raw; c += 32) store(c, load_elem(e.lvl_emb[l], at + c * hw, hf));
+    if (lane == 0) {
+        float4 bx = p.st.box[seg + slot];
+        if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
+        const float sc = p.st.score[seg + slot];
+        for (int q = 0; q < n_dst; ++q) {
+            float *o = dst(q);
+            o[0] = bx.x;
+            o[1] = bx.y;
+            o[2] = bx.z;
+            o[3] = bx.w;
+            o[4] = sc;
+            o[5] = static_cast<float>(cls);
+        }
+        if (p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
     }
-    const int64_t at_s = static_cast<int64_t>(b) * n_sig * hw + pos;
-    for (int c = lane; c < n_sig; c += 32) store(n_raw + c, sigmoid_rn(load_elem(e.lvl_state[l], at_s + c * hw, hf)));
+    if (p.ex.nm > 0 && p.ex.mode == 0 && anchor >= static_cast<uint32_t>(p.ex.anchors)) {
+        for (int c = lane; c < p.ex.nm; c += 32)
+            for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = 0.0f;  // apriori label row: no extras (ops.py:258)
+    } else if (p.ex.nm > 0) {
+        gather_extras_row(p.ex, b, anchor, lane, [&](int c, float v) {
+            for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = v;
+        });
+    }
 }
 
 struct NmsParams {
@@ -1069,6 +1215,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
             for (int i = tid; i < kBuckets; i += kNmsThreads) p.st.hist[static_cast<int64_t>(b) * kBuckets + i] = 0;
     }
     PROF_MARK(8);
+
 #undef PLIST
 #undef SURV
 #undef SKEY
@@ -1107,130 +1254,19 @@ __global__ void k_gate(const unsigned int *counter, unsigned int expected, unsig
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// K5: one warp per output row.  Row = x1,y1,x2,y2,conf,cls,extras (ops.py:272/275, :311).
-// Extras come from the decoded prediction (nms_decoded), from the raw level tensors (fused: raw
-// embedding, sigmoid state — head.py:247), or from the source detection rows (merge).
-// ---------------------------------------------------------------------------------------------
-struct GatherParams {
-    CandStore st;
-    ExtrasSrc ex;
-    const uint32_t *kept_slot;  // [B*max_det]
-    const int32_t *counts;      // [B]
-    float *out;                 // [B, max_det, 6+nm]
-    int32_t *kept_index;        // [B*max_det] or nullptr
-    const float *rescale;       // [B,5] pad_x, pad_y, gain, w0, h0 or nullptr (ops.scale_boxes + clip_boxes)
-    int32_t max_det;
-    int32_t tail_cols;          // columns reserved (unwritten) at the end of every output row
-    // fused gather + exchange: rows/counts are stored into every rank's buffer (P2P-mapped pointers over NVLink)
-    float *peer_out[8];
-    int32_t *peer_counts[8];
-    int32_t n_peers, peer_slot_offset;
-    // results layout (sarpost_nms_params_t.res_boxes): 7-column boxes with the state id + contiguous embeddings
-    float *res_boxes;    // [B, max_det, 7] x1,y1,x2,y2,state_id,conf,cls or nullptr
-    float *res_embeds;   // [B, max_det, res_n_raw]
-    int32_t res_n_raw;   // leading extras columns that are the embedding; the remaining nm - res_n_raw are state probabilities
-};
-
-// ops.scale_boxes (utils/ops.py:92-127, padding=True, xyxy) followed by clip_boxes (:319-338), in torch's fp32
-// operation order: subtract the pad, true division by the gain, clamp to the original image.
-__device__ __forceinline__ float4 rescale_box(float4 b, const float *rs) {
-    const float px = rs[0], py = rs[1], gain = rs[2], w0 = rs[3], h0 = rs[4];
-    b.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.x, px), gain), 0.0f), w0);
-    b.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.y, py), gain), 0.0f), h0);
-    b.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.z, px), gain), 0.0f), w0);
-    b.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.w, py), gain), 0.0f), h0);
-    return b;
-}
-
-constexpr int kGatherWarps = 8;
-
+// K5.  Launched as a programmatic dependent of the NMS kernel (cudaLaunchAttributeProgrammaticStreamSerialization): its
+// CTAs are scheduled while that kernel is still finishing and wait here until its results are visible, so the launch
+// latency is off the critical path (griddepcontrol.wait returns at once for a plain launch).
 __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_constant__ GatherParams p) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int b = blockIdx.y;
     const int r = blockIdx.x * kGatherWarps + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     const int n_rows = p.counts[b];
-    const int row_len = 6 + p.ex.nm + p.tail_cols;
-    // destinations of this row: the local output, or the same slot in every rank's buffer (peer stores)
-    const int n_dst = p.n_peers > 0 ? p.n_peers : 1;
-    const int64_t img = p.n_peers > 0 ? p.peer_slot_offset + b : b;
-    if (p.n_peers > 0 && r == 0 && lane < p.n_peers) p.peer_counts[lane][img] = n_rows;  // the counts travel with the rows
+    if (p.n_peers > 0 && r == 0 && lane < p.n_peers) p.peer_counts[lane][p.peer_slot_offset + b] = n_rows;  // the counts travel with the rows
     if (r >= n_rows) return;
-    auto dst = [&](int q) { return (p.n_peers > 0 ? p.peer_out[q] : p.out) + (img * p.max_det + r) * row_len; };
-    const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
     const uint32_t slot = p.kept_slot[static_cast<int64_t>(b) * p.max_det + r];
-    const uint32_t key = p.st.key[seg + slot];
-    if (p.ex.mode == 2) {
-        const float *src = p.ex.dets + (static_cast<int64_t>(b) * p.st.tpi * p.ex.dets_per_tile + key) * p.ex.row_len;
-        const float4 bx = p.st.box[seg + slot];
-        for (int c = lane; c < 6 + p.ex.nm; c += 32) {
-            const float v = c == 0 ? bx.x : c == 1 ? bx.y : c == 2 ? bx.z : c == 3 ? bx.w : src[c];
-            for (int q = 0; q < n_dst; ++q) dst(q)[c] = v;
-        }
-        if (lane == 0 && p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
-        return;
-    }
-    const uint32_t anchor = key / static_cast<uint32_t>(p.ex.nc), cls = key - anchor * static_cast<uint32_t>(p.ex.nc);
-    if (p.res_boxes) {
-        // models/yolo/jde/predict.py:52-66: boxes = cat(xyxy, argmax(states), conf, cls), embeds = the raw embedding columns
-        const int64_t row = static_cast<int64_t>(b) * p.max_det + r;
-        const int n_raw = p.res_n_raw, n_sig = p.ex.nm - n_raw;
-        float *emb = p.res_embeds + row * n_raw;
-        float best = -1.0f;  // probabilities are >= 0
-        int best_i = 0x7fffffff;
-        if (p.ex.nm > 0 && p.ex.mode == 0 && anchor >= static_cast<uint32_t>(p.ex.anchors)) {
-            for (int c = lane; c < n_raw; c += 32) emb[c] = 0.0f;  // apriori label row: zero extras (ops.py:258) -> state id 0
-            if (lane == 0 && n_sig > 0) { best = 0.0f; best_i = 0; }
-        } else if (p.ex.nm > 0) {
-            gather_extras_row(p.ex, b, anchor, lane, [&](int c, float v) {
-                if (c < n_raw) emb[c] = v;
-                else if (v > best) { best = v; best_i = c - n_raw; }  // ascending c per lane + strict > : first maximum
-            });
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
-            if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
-        }
-        if (lane == 0) {
-            float4 bx = p.st.box[seg + slot];
-            if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
-            float *o = p.res_boxes + row * 7;
-            o[0] = bx.x;
-            o[1] = bx.y;
-            o[2] = bx.z;
-            o[3] = bx.w;
-            o[4] = n_sig > 0 ? static_cast<float>(best_i) : -1.0f;
-            o[5] = p.st.score[seg + slot];
-            o[6] = static_cast<float>(cls);
-            if (p.kept_index) p.kept_index[row] = static_cast<int32_t>(key);
-        }
-        return;
-    }
-    if (lane == 0) {
-        float4 bx = p.st.box[seg + slot];
-        if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
-        const float sc = p.st.score[seg + slot];
-        for (int q = 0; q < n_dst; ++q) {
-            float *o = dst(q);
-            o[0] = bx.x;
-            o[1] = bx.y;
-            o[2] = bx.z;
-            o[3] = bx.w;
-            o[4] = sc;
-            o[5] = static_cast<float>(cls);
-        }
-        if (p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
-    }
-    if (p.ex.nm > 0 && p.ex.mode == 0 && anchor >= static_cast<uint32_t>(p.ex.anchors)) {
-        for (int c = lane; c < p.ex.nm; c += 32)
-            for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = 0.0f;  // apriori label row: no extras (ops.py:258)
-    } else if (p.ex.nm > 0) {
-        gather_extras_row(p.ex, b, anchor, lane, [&](int c, float v) {
-            for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = v;
-        });
-    }
+    gather_row(p, b, r, lane, slot, p.st.key[static_cast<int64_t>(b) * p.st.cap + slot]);
 }
 
 // Extras (raw embedding, sigmoid state; head.py:247) of an explicit list of (image, anchor) pairs — used when

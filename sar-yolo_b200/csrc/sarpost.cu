@@ -13,6 +13,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <new>
 #include <vector>
 
 #include <omp.h>
@@ -267,11 +269,49 @@ static bool tma_eligible(const HeadGeom &g) {
     return get_encode_fn() != nullptr;
 }
 
-static int device_sm_count(int *sms, int *smem_optin) {
+// Per-device facts and one-time kernel attributes: queried / set on the first call that touches a device, so the
+// launch path of every later call is free of cudaDeviceGetAttribute / cudaFuncSetAttribute round trips.
+constexpr int kK1StaticSmemReserve = 1024;  // >= static shared memory of k1_fused_tma (barriers, ring, scan scratch)
+struct DevInfo {
+    int sms = 0, smem_optin = 0;
+    bool ready = false;
+};
+constexpr int kMaxDevices = 64;
+static DevInfo g_dev[kMaxDevices];
+static std::mutex g_dev_mutex;
+
+static int device_info(const DevInfo **out) {
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
-    CUDA_TRY(cudaDeviceGetAttribute(smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (dev < 0 || dev >= kMaxDevices) return fail(SARPOST_EUNSUPPORTED, "device ordinal %d outside [0, %d)", dev, kMaxDevices);
+    DevInfo &d = g_dev[dev];
+    if (!__atomic_load_n(&d.ready, __ATOMIC_ACQUIRE)) {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        if (!d.ready) {
+            CUDA_TRY(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+            CUDA_TRY(cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+            // dynamic shared memory ceilings, once per device: the decode kernel may take everything the SM offers, the NMS
+            // kernel what max_det = 4096 needs
+            // (the opt-in limit covers static + dynamic shared memory: leave room for the kernel's static arrays)
+            CUDA_TRY(cudaFuncSetAttribute(k1_fused_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - kK1StaticSmemReserve));
+            CUDA_TRY(cudaFuncSetAttribute(k1_fused_tma<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - kK1StaticSmemReserve));
+            const int nms_max = static_cast<int>(nms_smem_bytes(4096));
+            CUDA_TRY(cudaFuncSetAttribute(k4_nms<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, nms_max));
+            CUDA_TRY(cudaFuncSetAttribute(k4_nms<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, nms_max));
+            CUDA_TRY(cudaFuncSetAttribute(k4_nms<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, nms_max));
+            CUDA_TRY(cudaFuncSetAttribute(k4_nms<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, nms_max));
+            __atomic_store_n(&d.ready, true, __ATOMIC_RELEASE);
+        }
+    }
+    *out = &d;
+    return SARPOST_OK;
+}
+
+static int device_sm_count(int *sms, int *smem_optin) {
+    const DevInfo *d = nullptr;
+    if (int rc = device_info(&d)) return rc;
+    *sms = d->sms;
+    *smem_optin = d->smem_optin;
     return SARPOST_OK;
 }
 
@@ -281,80 +321,133 @@ static int env_int(const char *name, int dflt) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// stages
+// stages.  Every stage is split into `*_prepare` (decide the launch geometry, encode tensor maps, fill the parameter
+// blocks) and `*_launch` (enqueue): a one-off call does both, a plan (sarpost_plan_*) prepares once and only refreshes
+// the addresses afterwards.
 // ------------------------------------------------------------------------------------------------
-static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandStore &st, int32_t *tile_counter, cudaStream_t s) {
-    NvtxRange nvtx("sarpost:K1 decode+score+compact");
+struct EnvK1 {
+    int force_ldg, ctas, stages, l2promo;
+};
+static EnvK1 read_env_k1() {
+    EnvK1 e;
+    e.force_ldg = env_int("SARPOST_K1_FORCE_LDG", 0);
+    e.ctas = env_int("SARPOST_K1_CTAS", 0);
+    e.stages = env_int("SARPOST_K1_STAGES", 0);
+    e.l2promo = env_int("SARPOST_K1_L2PROMO", CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    return e;
+}
+
+struct K1Launch {
+    bool use_tma;
+    int grid, smem, l2promo;
+    K1TmaParams tp;
+    K1LdgParams lp;
+    const void *enc_box[kMaxLevels], *enc_cls[kMaxLevels];  // addresses the tensor maps in `tp` were encoded for
+};
+
+// one 3-D map (anchors of the level, channels, images) per tensor the tile is assembled from; box = {kTileA, rows, 1}
+static int k1_encode_level(K1Launch *k, int l) {
+    const HeadGeom &g = k->tp.g;
+    const int nch = 4 * kRegMax + g.nc;
+    const int esz = g.is_half ? 2 : 4;
+    PFN_encodeTiled enc = get_encode_fn();
+    const CUtensorMapDataType dt = g.is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapL2promotion promo = static_cast<CUtensorMapL2promotion>(k->l2promo);
+    auto encode = [&](CUtensorMap *m, const void *ptr, int channels_in_tensor, int rows) -> CUresult {
+        const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.lvl_hw[l]), static_cast<cuuint64_t>(channels_in_tensor), static_cast<cuuint64_t>(g.batch)};
+        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lvl_hw[l]) * esz, static_cast<cuuint64_t>(g.lvl_hw[l]) * channels_in_tensor * esz};
+        const cuuint32_t box[3] = {kTileA, static_cast<cuuint32_t>(rows), 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        return enc(m, dt, 3, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    CUresult r = g.split ? encode(&k->tp.maps[l], g.lvl_ptr[l], 4 * kRegMax, 4 * kRegMax) : encode(&k->tp.maps[l], g.lvl_ptr[l], g.no, nch);
+    if (r == CUDA_SUCCESS && g.split) r = encode(&k->tp.maps_cls[l], g.lvl_cls[l], g.nc, g.nc);
+    if (r != CUDA_SUCCESS) return fail(SARPOST_ECUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, static_cast<int>(r));
+    k->enc_box[l] = g.lvl_ptr[l];
+    k->enc_cls[l] = g.lvl_cls[l];
+    return SARPOST_OK;
+}
+
+static int k1_prepare(const HeadGeom &g, const CandFilter &f, const CandStore &st, int32_t *tile_counter, const EnvK1 &env, K1Launch *k) {
     const int nch = 4 * kRegMax + g.nc;
     const int esz = g.is_half ? 2 : 4;
     const int64_t stage_bytes = static_cast<int64_t>(nch) * kTileA * esz;
     int sms = 0, smem_optin = 0;
     if (int rc = device_sm_count(&sms, &smem_optin)) return rc;
-    bool use_tma = tma_eligible(g) && !env_int("SARPOST_K1_FORCE_LDG", 0);
+    bool use_tma = tma_eligible(g) && !env.force_ldg;
     int stages = 0, ctas = 0;
     if (use_tma) {
         const int64_t sm_smem = 228 * 1024;
         // fp32 tiles: 3 CTAs x 2 stages of 33 KB fill the SM's shared memory and reach the HBM roofline; fp16 tiles
         // are half the size and the kernel turns issue-bound, so more resident warps (6 CTAs) pay off (measured)
-        const int want_ctas = env_int("SARPOST_K1_CTAS", g.is_half ? 6 : 3);
+        const int want_ctas = env.ctas > 0 ? env.ctas : (g.is_half ? 6 : 3);
         for (ctas = want_ctas; ctas >= 1; --ctas) {
             const int64_t per_cta = sm_smem / ctas - 1024 /*driver reserve*/ - 512 /*static + align*/;
             stages = static_cast<int>(per_cta / stage_bytes);
             if (stages > kMaxStages) stages = kMaxStages;
             if (stages >= 2) break;
         }
-        const int forced = env_int("SARPOST_K1_STAGES", 0);
-        if (forced > 0) stages = forced > kMaxStages ? kMaxStages : forced;
-        if (ctas < 1 || stages < 2 || stages * stage_bytes + 128 > smem_optin) use_tma = false;
+        if (env.stages > 0) stages = env.stages > kMaxStages ? kMaxStages : env.stages;
+        if (ctas < 1 || stages < 1 || (stages < 2 && env.stages <= 0) || stages * stage_bytes + 128 > smem_optin - kK1StaticSmemReserve) use_tma = false;
     }
+    memset(k, 0, sizeof(*k));
+    k->use_tma = use_tma;
+    k->l2promo = env.l2promo;
     if (use_tma) {
-        K1TmaParams p;
-        memset(&p, 0, sizeof(p));
+        K1TmaParams &p = k->tp;
         p.g = g;
         p.f = f;
         p.st = st;
         p.stages = stages;
         p.n_tiles = g.batch * g.tpi;
         p.tile_counter = tile_counter;
-        PFN_encodeTiled enc = get_encode_fn();
-        const CUtensorMapDataType dt = g.is_half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-        const CUtensorMapL2promotion promo = static_cast<CUtensorMapL2promotion>(env_int("SARPOST_K1_L2PROMO", CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
-        // one 3-D map (anchors of the level, channels, images) per tensor the tile is assembled from; box = {kTileA, rows, 1}
-        auto encode = [&](CUtensorMap *m, const void *ptr, int l, int channels_in_tensor, int rows) -> CUresult {
-            const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.lvl_hw[l]), static_cast<cuuint64_t>(channels_in_tensor), static_cast<cuuint64_t>(g.batch)};
-            const cuuint64_t strides[2] = {static_cast<cuuint64_t>(g.lvl_hw[l]) * esz, static_cast<cuuint64_t>(g.lvl_hw[l]) * channels_in_tensor * esz};
-            const cuuint32_t box[3] = {kTileA, static_cast<cuuint32_t>(rows), 1};
-            const cuuint32_t estr[3] = {1, 1, 1};
-            return enc(m, dt, 3, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        };
-        for (int l = 0; l < g.nl; ++l) {
-            CUresult r = g.split ? encode(&p.maps[l], g.lvl_ptr[l], l, 4 * kRegMax, 4 * kRegMax) : encode(&p.maps[l], g.lvl_ptr[l], l, g.no, nch);
-            if (r == CUDA_SUCCESS && g.split) r = encode(&p.maps_cls[l], g.lvl_cls[l], l, g.nc, g.nc);
-            if (r != CUDA_SUCCESS) return fail(SARPOST_ECUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, static_cast<int>(r));
-        }
-        const int smem = static_cast<int>(stages * stage_bytes + 128);
-        int grid = sms * ctas;
-        if (grid > p.n_tiles) grid = p.n_tiles;
-        if (g.is_half) {
-            CUDA_TRY(cudaFuncSetAttribute(k1_fused_tma<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            k1_fused_tma<__half><<<grid, kTileA, smem, s>>>(p);
-        } else {
-            CUDA_TRY(cudaFuncSetAttribute(k1_fused_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            k1_fused_tma<float><<<grid, kTileA, smem, s>>>(p);
-        }
+        for (int l = 0; l < g.nl; ++l)
+            if (int rc = k1_encode_level(k, l)) return rc;
+        k->smem = static_cast<int>(stages * stage_bytes + 128);
+        k->grid = sms * ctas;
+        if (k->grid > p.n_tiles) k->grid = p.n_tiles;
     } else {
-        K1LdgParams p;
-        memset(&p, 0, sizeof(p));
-        p.g = g;
-        p.f = f;
-        p.st = st;
-        if (g.is_half) k1_fused_ldg<__half><<<dim3(g.tpi, g.batch), kTileA, 0, s>>>(p);
-        else k1_fused_ldg<float><<<dim3(g.tpi, g.batch), kTileA, 0, s>>>(p);
+        k->lp.g = g;
+        k->lp.f = f;
+        k->lp.st = st;
+    }
+    return SARPOST_OK;
+}
+
+// New level addresses for a prepared launch (same geometry): only the tensor maps whose address changed are re-encoded.
+static int k1_refresh(K1Launch *k, const HeadGeom &g) {
+    if (!k->use_tma) {
+        k->lp.g = g;
+        return SARPOST_OK;
+    }
+    if (!tma_eligible(g)) return fail(SARPOST_EINVAL, "plan: a level address is not 16-byte aligned (the plan was created for aligned tensors)");
+    k->tp.g = g;
+    for (int l = 0; l < g.nl; ++l)
+        if (k->enc_box[l] != g.lvl_ptr[l] || k->enc_cls[l] != g.lvl_cls[l])
+            if (int rc = k1_encode_level(k, l)) return rc;
+    return SARPOST_OK;
+}
+
+static int k1_launch(const K1Launch &k, cudaStream_t s) {
+    NvtxRange nvtx("sarpost:K1 decode+score+compact");
+    if (k.use_tma) {
+        if (k.tp.g.is_half) k1_fused_tma<__half><<<k.grid, kTileA, k.smem, s>>>(k.tp);
+        else k1_fused_tma<float><<<k.grid, kTileA, k.smem, s>>>(k.tp);
+    } else {
+        const HeadGeom &g = k.lp.g;
+        if (g.is_half) k1_fused_ldg<__half><<<dim3(g.tpi, g.batch), kTileA, 0, s>>>(k.lp);
+        else k1_fused_ldg<float><<<dim3(g.tpi, g.batch), kTileA, 0, s>>>(k.lp);
     }
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     return SARPOST_OK;
+}
+
+static int launch_k1_fused(const HeadGeom &g, const CandFilter &f, const CandStore &st, int32_t *tile_counter, cudaStream_t s) {
+    K1Launch k;
+    if (int rc = k1_prepare(g, f, st, tile_counter, read_env_k1(), &k)) return rc;
+    return k1_launch(k, s);
 }
 
 // where the gather kernel finds the extras of a kept row when the input is the raw level tensors (mode 1)
@@ -379,10 +472,20 @@ static void fill_extras_src(const HeadGeom &g, ExtrasSrc *ex) {
 }
 
 // K2 + K4 + K5 on a filled candidate store.
-static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, int nc, const ExtrasSrc &ex, float *out,
-                    int32_t *counts, int32_t *kept_index, cudaStream_t s, int cl_hint = 0) {
-    NvtxRange nvtx("sarpost:K2-K5 select+sort+nms+gather");
+typedef void (*NmsKernel)(const NmsParams);
+
+struct TailLaunch {
     NmsParams np;
+    GatherParams gp;
+    NmsKernel kern;
+    int cl, nms_grid, nms_smem;
+    bool pdl;
+    dim3 gather_grid;
+};
+
+static int tail_prepare(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, int nc, const ExtrasSrc &ex, float *out,
+                        int32_t *counts, int32_t *kept_index, int cl_hint, int forced_cl, TailLaunch *t) {
+    NmsParams &np = t->np;
     np.st = P.st;
     np.tmp_key_a = P.key_a;
     np.tmp_val_a = P.val_a;
@@ -399,37 +502,18 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
     np.stats = reinterpret_cast<long long *>(prm->stats);
     np.tile_counter = P.tile_counter;
     np.resident_counter = g_resident_counter;
-    const int nms_smem = static_cast<int>(nms_smem_bytes(prm->max_det));
+    t->nms_smem = static_cast<int>(nms_smem_bytes(prm->max_det));
     // one CTA per image; when the batch leaves SMs idle, a cluster of 2 or 4 CTAs per image shares the work
     int sms = 0, smem_optin = 0;
     if (int rc = device_sm_count(&sms, &smem_optin)) return rc;
     int cl = batch * 4 <= sms ? 4 : (batch * 2 <= sms ? 2 : 1);
     if (cl_hint == 1 || cl_hint == 2 || cl_hint == 4) cl = cl_hint;
-    const int forced_cl = env_int("SARPOST_NMS_CLUSTER", 0);
     if (forced_cl == 1 || forced_cl == 2 || forced_cl == 4 || forced_cl == 8) cl = forced_cl;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(batch * cl);
-    cfg.blockDim = dim3(kNmsThreads);
-    cfg.dynamicSmemBytes = nms_smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = cl;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    const int max_smem = static_cast<int>(nms_smem_bytes(4096));
-    void (*kern)(const NmsParams) = cl == 8 ? k4_nms<8> : cl == 4 ? k4_nms<4> : cl == 2 ? k4_nms<2> : k4_nms<1>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, np));
-    g_last_nms_ctas = batch * cl;
-    ++g_launches;
-    CUDA_TRY(cudaGetLastError());
-    stage_mark(3, s);
+    t->cl = cl;
+    t->nms_grid = batch * cl;
+    t->kern = cl == 8 ? k4_nms<8> : cl == 4 ? k4_nms<4> : cl == 2 ? k4_nms<2> : k4_nms<1>;
 
-    GatherParams gp;
+    GatherParams &gp = t->gp;
     gp.st = P.st;
     gp.ex = ex;
     gp.kept_slot = P.kept_slot;
@@ -454,11 +538,55 @@ static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *pr
         gp.peer_out[q] = q < prm->n_peers ? prm->peer_out[q] : nullptr;
         gp.peer_counts[q] = q < prm->n_peers ? prm->peer_counts[q] : nullptr;
     }
-    k5_gather<<<dim3((prm->max_det + kGatherWarps - 1) / kGatherWarps, batch), kGatherWarps * 32, 0, s>>>(gp);
+    t->gather_grid = dim3((prm->max_det + kGatherWarps - 1) / kGatherWarps, batch);
+    t->pdl = !env_int("SARPOST_NO_PDL", 0);
+    return SARPOST_OK;
+}
+
+static int tail_launch(const TailLaunch &t, cudaStream_t s) {
+    NvtxRange nvtx("sarpost:K2-K5 select+sort+nms+gather");
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(t.nms_grid);
+    cfg.blockDim = dim3(kNmsThreads);
+    cfg.dynamicSmemBytes = t.nms_smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = t.cl;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, t.kern, t.np));
+    g_last_nms_ctas = t.nms_grid;
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    stage_mark(3, s);
+    // the gather as a programmatic dependent of the NMS kernel (see k5_gather); per-stage timing puts an event record
+    // between the two, which makes it an ordinary launch again
+    cudaLaunchConfig_t gcfg;
+    memset(&gcfg, 0, sizeof(gcfg));
+    gcfg.gridDim = t.gather_grid;
+    gcfg.blockDim = dim3(kGatherWarps * 32);
+    gcfg.stream = s;
+    cudaLaunchAttribute gattr;
+    gattr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    gattr.val.programmaticStreamSerializationAllowed = 1;
+    gcfg.attrs = &gattr;
+    gcfg.numAttrs = t.pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&gcfg, k5_gather, t.gp));
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     stage_mark(4, s);
     return SARPOST_OK;
+}
+
+static int run_tail(const Pipeline &P, int batch, const sarpost_nms_params_t *prm, int nc, const ExtrasSrc &ex, float *out,
+                    int32_t *counts, int32_t *kept_index, cudaStream_t s, int cl_hint = 0) {
+    TailLaunch t;
+    if (int rc = tail_prepare(P, batch, prm, nc, ex, out, counts, kept_index, cl_hint, env_int("SARPOST_NMS_CLUSTER", 0), &t)) return rc;
+    return tail_launch(t, s);
 }
 
 // the per-image score histogram must be zero before K1 accumulates into it
@@ -654,6 +782,93 @@ int32_t sarpost_fused(const sarpost_head_t *head, const sarpost_nms_params_t *pa
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return fused_impl(head, params, out, counts, kept_index, workspace, workspace_bytes, s, nullptr, 0);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Plans: sarpost_fused with everything that does not change between calls prepared once
+// ------------------------------------------------------------------------------------------------
+struct sarpost_plan {
+    HeadGeom g;
+    sarpost_nms_params_t prm;  // a copy; `classes` already folded into the candidate filter
+    Pipeline P;
+    K1Launch k1;
+    TailLaunch tail;
+};
+
+int32_t sarpost_plan_create(const sarpost_head_t *head, const sarpost_nms_params_t *params, void *workspace,
+                            int64_t workspace_bytes, sarpost_plan_t **plan) {
+    if (!plan) return fail(SARPOST_EINVAL, "plan is NULL");
+    *plan = nullptr;
+    HeadGeom g;
+    int64_t anchors = 0;
+    if (int rc = fill_geom(head, &g, &anchors)) return rc;
+    if (int rc = check_params(params, g.nc)) return rc;
+    if (!params->workspace_clean) return fail(SARPOST_EINVAL, "a plan needs a prepared workspace (sarpost_workspace_prepare, workspace_clean = 1)");
+    CandFilter f;
+    make_filter(params, g.nc, &f);
+    const int64_t region = kTileA * (f.multi_label ? g.nc : 1);
+    sarpost_plan *pl = new (std::nothrow) sarpost_plan;
+    if (!pl) return fail(SARPOST_EINVAL, "out of host memory");
+    pl->g = g;
+    pl->prm = *params;
+    pl->prm.classes = nullptr;
+    pl->prm.n_classes = 0;
+    pl->prm.rescale = nullptr;  // per-run addresses travel in the io block
+    pl->prm.stats = nullptr;
+    pl->prm.res_boxes = pl->prm.res_embeds = nullptr;
+    int rc = bind_workspace(workspace, workspace_bytes, g.batch, g.tpi * region, g.tpi, region, params->max_det, false, &pl->P);
+    if (!rc) rc = k1_prepare(g, f, pl->P.st, pl->P.tile_counter, read_env_k1(), &pl->k1);
+    ExtrasSrc ex;
+    fill_extras_src(g, &ex);
+    float dummy_out = 0.f;  // the real addresses arrive with every run; the consistency checks of the parameter block run here
+    if (!rc) rc = tail_prepare(pl->P, g.batch, &pl->prm, g.nc, ex, &dummy_out, nullptr, nullptr, 0, env_int("SARPOST_NMS_CLUSTER", 0), &pl->tail);
+    if (rc) {
+        delete pl;
+        return rc;
+    }
+    *plan = pl;
+    return SARPOST_OK;
+}
+
+int32_t sarpost_plan_run(sarpost_plan_t *pl, const sarpost_plan_io_t *io, void *stream) {
+    NvtxRange nvtx("sarpost_plan_run");
+    g_launches = 0;
+    if (!pl || !io) return fail(SARPOST_EINVAL, "plan / io is NULL");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    HeadGeom &g = pl->g;
+    if ((!io->out && pl->prm.n_peers == 0 && !io->res_boxes) || !io->counts) return fail(SARPOST_EINVAL, "NULL tensor pointer");
+    for (int l = 0; l < g.nl; ++l) {
+        if (!io->data[l]) return fail(SARPOST_EINVAL, "level %d data pointer is NULL", l);
+        g.lvl_ptr[l] = io->data[l];
+        if (g.split) {
+            if (!io->cls[l] || (g.n_extra_raw > 0 && !io->emb[l]) || (g.n_extra_sig > 0 && !io->state[l]))
+                return fail(SARPOST_EINVAL, "level %d: a branch pointer is NULL (split layout)", l);
+            g.lvl_cls[l] = io->cls[l];
+            g.lvl_emb[l] = io->emb[l];
+            g.lvl_state[l] = io->state[l];
+        }
+    }
+    if (int rc = k1_refresh(&pl->k1, g)) return rc;
+    TailLaunch &t = pl->tail;
+    fill_extras_src(g, &t.gp.ex);
+    t.np.counts = io->counts;
+    t.np.stats = reinterpret_cast<long long *>(io->stats);
+    t.np.resident_counter = nullptr;
+    t.gp.counts = io->counts;
+    t.gp.out = io->out;
+    t.gp.kept_index = io->kept_index;
+    t.gp.rescale = io->rescale;
+    t.gp.res_boxes = io->res_boxes;
+    t.gp.res_embeds = io->res_embeds;
+    if (t.gp.res_boxes && t.gp.res_n_raw > 0 && !t.gp.res_embeds) return fail(SARPOST_EINVAL, "res_boxes set but res_embeds is NULL");
+    if (t.gp.res_boxes && (pl->prm.n_peers > 0 || pl->prm.out_tail_cols > 0)) return fail(SARPOST_EINVAL, "res_boxes does not combine with peer_out / out_tail_cols");
+    stage_mark(0, s);
+    stage_mark(1, s);  // the workspace is clean by contract: no memset
+    if (int rc = k1_launch(pl->k1, s)) return rc;
+    stage_mark(2, s);
+    return tail_launch(t, s);
+}
+
+void sarpost_plan_destroy(sarpost_plan_t *pl) { delete pl; }
 
 int32_t sarpost_merge_tiles(const float *dets, const int32_t *det_counts, const float *origins, int32_t n_frames,
                             int32_t tiles_per_frame, int32_t dets_per_tile, int32_t row_len,

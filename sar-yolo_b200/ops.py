@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from ._lib import Head, NmsParams, lib
 
-__all__ = ["HeadSpec", "StateMLP", "state_head", "non_max_suppression", "decode", "postprocess_fused", "split_levels", "cat_levels", "merge_tiles", "gather_extras", "match_predictions", "match_from_iou", "postprocess_host",
+__all__ = ["HeadSpec", "FusedPlan", "StateMLP", "state_head", "non_max_suppression", "decode", "postprocess_fused", "split_levels", "cat_levels", "merge_tiles", "gather_extras", "match_predictions", "match_from_iou", "postprocess_host",
            "HostContext", "Pipeline", "last_launch_count", "stage_timing", "stage_times"]
 
 
@@ -738,6 +738,169 @@ def match_from_iou(pred_classes: torch.Tensor, true_classes: torch.Tensor, iou: 
     return (correct, matched) if matched is not None else correct
 
 
+class _LevelSig:
+    """What a set of level tensors has to reproduce for a prepared `sarpost_head_t` to stay valid with new addresses only:
+    layout, and per tensor shape / dtype / memory format / device."""
+
+    def __init__(self, levels):
+        self.split = _is_split(levels)
+        flat = [t for lv in levels for t in lv] if self.split else list(levels)
+        self.device = _box_of(levels[0]).device
+        self.sig = [None if t is None else (t.shape, t.dtype, _emb_channels_last(t)) for t in flat]
+
+    def matches(self, levels) -> bool:
+        if _is_split(levels) != self.split:
+            return False
+        flat = [t for lv in levels for t in lv] if self.split else levels
+        sig, dev = self.sig, self.device
+        if len(flat) != len(sig):
+            return False
+        for t, want in zip(flat, sig):
+            if want is None:
+                if t is not None:
+                    return False
+                continue
+            if t is None or t.shape != want[0] or t.dtype != want[1] or t.device != dev:
+                return False
+            if not (t.is_contiguous(memory_format=torch.channels_last) if want[2] else t.is_contiguous()):
+                return False
+        return True
+
+    def fill(self, levels, io) -> None:
+        """Addresses into `io.data / cls / emb / state` (a sarpost_head_t or sarpost_plan_io_t)."""
+        if self.split:
+            for i, lv in enumerate(levels):
+                io.data[i] = lv[0].data_ptr()
+                io.cls[i] = lv[1].data_ptr()
+                io.emb[i] = lv[2].data_ptr() if len(lv) > 2 and lv[2] is not None else None
+                io.state[i] = lv[3].data_ptr() if len(lv) > 3 and lv[3] is not None else None
+        else:
+            for i, x in enumerate(levels):
+                io.data[i] = x.data_ptr()
+
+
+class FusedPlan:
+    """`postprocess_fused` for a serving loop (`sarpost_plan_*`): geometry, thresholds, workspace, launch configuration and
+    the TMA tensor maps are prepared once from a first set of level tensors; a call then only hands over the addresses
+    of tensors with the SAME shapes, dtype, layout and device — three kernel launches, no validation beyond a shape /
+    dtype / contiguity comparison, no allocation when `out=` is given.  Rows are bit-identical to `postprocess_fused`.
+
+        plan = sarpost.FusedPlan(levels, spec, conf_thres=0.25, iou_thres=0.7)
+        for levels in stream_of_batches:
+            out, counts = plan(levels)            # (B, max_det, 6+nm) padded rows, (B,) int32 — no host sync
+
+    One plan belongs to one CUDA stream at a time (its workspace is reused in stream order)."""
+
+    def __init__(self, levels, spec: HeadSpec, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
+                 max_det=300, max_nms=30000, max_wh=7680, with_extras=True, results: bool = False):
+        assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+        assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+        levels = _prep_levels(levels)
+        head = _make_head(levels, spec, with_extras=with_extras)
+        if head.batch == 0:
+            raise ValueError("sarpost: a plan needs a non-empty batch")
+        self.spec, self.with_extras, self.results = spec, with_extras, bool(results)
+        self.split = _is_split(levels)
+        self.device = _box_of(levels[0]).device
+        self.batch, self.max_det = head.batch, int(max_det)
+        self.nm = spec.nm if with_extras else 0
+        if results and not with_extras:
+            raise ValueError("sarpost: results=True needs with_extras=True")
+        self._sig = _LevelSig(levels)
+        params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+        anchors = sum(int(_box_of(x).shape[2]) * int(_box_of(x).shape[3]) for x in levels)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            ws_bytes = lib.sarpost_workspace_bytes(self.batch, anchors, spec.nc, int(bool(multi_label)), self.max_det)
+            if ws_bytes < 0:
+                _lib.check(int(ws_bytes))
+            self._ws = torch.empty(int(ws_bytes), dtype=torch.uint8, device=self.device)
+            _lib.check(lib.sarpost_workspace_prepare(self._ws.data_ptr(), int(ws_bytes), self.batch, _stream_ptr(self.device)))
+            _lib.check(lib.sarpost_plan_create(C.byref(head), C.byref(params), self._ws.data_ptr(), int(ws_bytes), C.byref(self._h)))
+        self._io = _lib.PlanIO()
+        self._nl = len(levels)
+        self._dev_index = self.device.index
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.sarpost_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __call__(self, levels, out=None, return_index: bool = False, scale_to=None, nms_stats: Optional[torch.Tensor] = None):
+        """`levels` as at creation (same shapes / dtype / strides / device; anything else raises).  Returns the padded device
+        tensors `(out, counts[, kept_index])`, or with `results=True` `(boxes (B, max_det, 7), embeds (B, max_det, E), counts
+        [, kept_index])`.  `out=` caller-owned tensors of exactly those shapes (the same tuple without kept_index)."""
+        if not self._sig.matches(levels):
+            raise ValueError("sarpost: level tensors differ from the ones the plan was created for (layout / shape / dtype / "
+                             "memory format); a plan takes tensors as `postprocess_fused` would pass them on unchanged")
+        io, dev, bs, md = self._io, self.device, self.batch, self.max_det
+        self._sig.fill(levels, io)
+        cur = torch.cuda.current_device()
+        if cur != self._dev_index:
+            torch.cuda.set_device(self._dev_index)
+        try:
+            rescale = None
+            if scale_to is not None:
+                img1_shape, img0_shapes = scale_to
+                if len(img0_shapes) != bs:
+                    raise ValueError(f"sarpost: scale_to has {len(img0_shapes)} original shapes for a batch of {bs}")
+                rescale = scale_params(img1_shape, img0_shapes, dev)
+            io.rescale = rescale.data_ptr() if rescale is not None else None
+            if nms_stats is not None:
+                nms_stats.zero_()
+                io.stats = nms_stats.data_ptr()
+            else:
+                io.stats = None
+            if out is not None:
+                want = ((bs, md, 7), (bs, md, self.spec.embed_dim), (bs,)) if self.results else ((bs, md, 6 + self.nm), (bs,))
+                if len(out) != len(want):
+                    raise ValueError(f"sarpost: out= must hold {len(want)} tensors")
+                for t, shp in zip(out, want):
+                    dt = torch.int32 if len(shp) == 1 else torch.float32
+                    if tuple(t.shape) != shp or t.dtype != dt or not t.is_contiguous() or t.device != dev:
+                        raise ValueError(f"sarpost: out= tensors must be contiguous {shp} {dt} on {dev}")
+            if self.results:
+                if out is not None:
+                    boxes, embeds, counts = out
+                else:
+                    boxes = torch.empty((bs, md, 7), dtype=torch.float32, device=dev)
+                    embeds = torch.empty((bs, md, self.spec.embed_dim), dtype=torch.float32, device=dev)
+                    counts = torch.empty((bs,), dtype=torch.int32, device=dev)
+                io.out = None
+                io.res_boxes = boxes.data_ptr()
+                io.res_embeds = embeds.data_ptr() if self.spec.embed_dim else None
+            else:
+                if out is not None:
+                    rows, counts = out
+                else:
+                    rows = torch.empty((bs, md, 6 + self.nm), dtype=torch.float32, device=dev)
+                    counts = torch.empty((bs,), dtype=torch.int32, device=dev)
+                io.out = rows.data_ptr()
+                io.res_boxes = io.res_embeds = None
+            io.counts = counts.data_ptr()
+            kidx = torch.empty((bs, md), dtype=torch.int32, device=dev) if return_index else None
+            io.kept_index = kidx.data_ptr() if return_index else None
+            rc = lib.sarpost_plan_run(self._h, C.byref(io), torch.cuda.current_stream().cuda_stream)
+            if rc != 0:
+                _lib.check(rc)
+            if self.results:
+                if self.spec.state_classes == 0:  # no state id to show: the plain 6 columns (predict.py:73-75)
+                    boxes = torch.cat((boxes[..., :4], boxes[..., 5:]), -1)
+                ret = (boxes, embeds, counts)
+            else:
+                ret = (rows, counts)
+        finally:
+            if cur != self._dev_index:
+                torch.cuda.set_device(cur)
+        return ret + (kidx,) if return_index else ret
+
+
 class Pipeline:
     """Throughput mode for a stream of batches in device memory (`sarpost_pipeline_*`): `submit()` enqueues the fused
     decode + NMS of one batch on one of the pipeline's own `depth` streams and returns the padded output tensors
@@ -758,6 +921,7 @@ class Pipeline:
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self._h = C.c_void_p()
         self._held = []  # inputs / outputs / parameter blocks of batches in flight: alive until wait()
+        self._head_cache = None  # (_LevelSig, spec, with_extras, Head) of the last submit
         _lib.check(lib.sarpost_pipeline_create(self.device.index, int(depth), C.byref(self._h)))
 
     def close(self):
@@ -780,13 +944,22 @@ class Pipeline:
         until `wait()`, so nothing is recycled by the allocator in between)."""
         assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
         assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
-        levels = _prep_levels(levels)
-        head = _make_head(levels, spec, with_extras=with_extras)
-        dev = _box_of(levels[0]).device
-        if dev != self.device:
-            raise RuntimeError(f"sarpost: level tensors are on {dev}, the pipeline on {self.device}")
-        if head.batch == 0:
-            raise ValueError("sarpost: empty batch")
+        # steady state of a serving loop: the same geometry as the previous submit -> the validated head block is reused
+        # with new addresses only
+        ent = self._head_cache
+        if ent is not None and ent[1] == spec and ent[2] == with_extras and ent[0].matches(levels):
+            head = ent[3]
+            ent[0].fill(levels, head)
+            dev = ent[0].device
+        else:
+            levels = _prep_levels(levels)
+            head = _make_head(levels, spec, with_extras=with_extras)
+            dev = _box_of(levels[0]).device
+            if dev != self.device:
+                raise RuntimeError(f"sarpost: level tensors are on {dev}, the pipeline on {self.device}")
+            if head.batch == 0:
+                raise ValueError("sarpost: empty batch")
+            self._head_cache = (_LevelSig(levels), spec, with_extras, head)
         nm = spec.nm if with_extras else 0
         rescale = None
         if scale_to is not None:

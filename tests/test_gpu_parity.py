@@ -977,3 +977,78 @@ def test_pipeline_matches_plain_calls(sarpost, cuda):
             for b, n in enumerate(want_counts.tolist()):
                 assert torch.equal(out[b, :n], want_out[b, :n]) and torch.equal(kidx[b, :n], want_idx[b, :n])
         pl.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("imgsz,strides,nc,ed,sc,bs", HEADS)
+@pytest.mark.parametrize("layout", ["cat", "split", "split_cl", "half"])
+def test_plan_runs_equal_plain_calls(sarpost, cuda, imgsz, strides, nc, ed, sc, bs, layout):
+    """sarpost_plan_*: a plan prepared from one set of level tensors and then run on OTHER tensors of the same geometry
+    (new addresses -> tensor maps re-encoded, new values) gives the very rows of a plain `postprocess_fused` call, in every
+    layout / dtype, with and without kept indices, caller-owned outputs, the results layout and fused scale_boxes."""
+    spec = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=sc)
+    shapes = sarpost.synth.level_shapes(imgsz, strides)
+    kw = dict(conf_thres=0.05, iou_thres=0.6, multi_label=nc > 1, max_det=50)
+
+    def make(seed):
+        lv = [x.to(cuda) for x in sarpost.synth.head_outputs(bs, shapes, nc, ed, sc, seed=seed, cls_mean=-1.0)]
+        if layout == "half":
+            lv = [x.half() for x in lv]
+        if layout.startswith("split"):
+            lv = sarpost.split_levels(lv, spec, emb_channels_last=layout == "split_cl")
+        return lv
+
+    plan = sarpost.FusedPlan(make(1), spec, **kw)
+    keep_alive = []
+    for seed in (1, 2, 3, 2):
+        lv = make(seed)
+        keep_alive.append(lv)  # keep earlier inputs allocated so that every round sees new addresses
+        want_out, want_counts, want_idx = sarpost.postprocess_fused(lv, spec, return_padded=True, return_index=True, **kw)
+        out, counts, kidx = plan(lv, return_index=True)
+        assert torch.equal(counts, want_counts)
+        for b, n in enumerate(want_counts.tolist()):
+            assert torch.equal(out[b, :n], want_out[b, :n]) and torch.equal(kidx[b, :n], want_idx[b, :n])
+        # caller-owned outputs, no kept indices
+        mine = (torch.full_like(want_out, -7.0), torch.zeros_like(want_counts))
+        out2, counts2 = plan(lv, out=mine)
+        assert out2 is mine[0] and torch.equal(counts2, want_counts)
+        for b, n in enumerate(want_counts.tolist()):
+            assert torch.equal(out2[b, :n], want_out[b, :n]) and bool((out2[b, n:] == -7.0).all())
+    # fused scale_boxes + clip through the plan
+    h0 = imgsz if isinstance(imgsz, int) else imgsz[0]
+    w0 = imgsz if isinstance(imgsz, int) else imgsz[1]
+    scale_to = ((h0, w0), [(h0 * 2 + 3 * i, w0 * 2 - 5 * i) for i in range(bs)])
+    lv = make(5)
+    want_out, want_counts = sarpost.postprocess_fused(lv, spec, return_padded=True, scale_to=scale_to, **kw)
+    out, counts = plan(lv, scale_to=scale_to)
+    assert torch.equal(counts, want_counts)
+    for b, n in enumerate(want_counts.tolist()):
+        assert torch.equal(out[b, :n], want_out[b, :n])
+    plan.close()
+    if ed:  # results layout (7-column boxes + contiguous embeddings)
+        rplan = sarpost.FusedPlan(make(1), spec, results=True, **kw)
+        lv = make(6)
+        wb, we, wc = sarpost.postprocess_fused(lv, spec, return_padded=True, results=True, **kw)
+        gb, ge, gc = rplan(lv)
+        assert torch.equal(gc, wc)
+        for b, n in enumerate(wc.tolist()):
+            assert torch.equal(gb[b, :n], wb[b, :n]) and torch.equal(ge[b, :n], we[b, :n])
+        rplan.close()
+
+
+@pytest.mark.gpu
+def test_plan_rejects_other_geometry(sarpost, cuda):
+    strides = (8, 16, 32)
+    spec = sarpost.HeadSpec(nc=2, strides=strides)
+    mk = lambda imgsz, bs: [x.to(cuda) for x in sarpost.synth.head_outputs(bs, sarpost.synth.level_shapes(imgsz, strides), 2, 0, 0, seed=3)]  # noqa: E731
+    plan = sarpost.FusedPlan(mk(320, 2), spec, conf_thres=0.25, iou_thres=0.7)
+    for bad in (mk(320, 3), mk(256, 2), [x.half() for x in mk(320, 2)], sarpost.split_levels(mk(320, 2), spec),
+                [x.permute(0, 1, 3, 2) for x in mk(320, 2)]):
+        with pytest.raises(ValueError):
+            plan(bad)
+    with pytest.raises(RuntimeError):
+        sarpost.FusedPlan([x.cpu() for x in mk(320, 2)], spec)
+    out, counts = plan(mk(320, 2))  # still usable after the rejected calls
+    want_out, want_counts = sarpost.postprocess_fused(mk(320, 2), spec, return_padded=True, conf_thres=0.25, iou_thres=0.7)
+    assert torch.equal(counts, want_counts)
+    plan.close()

@@ -16,7 +16,7 @@ buf=(C.c_ulonglong*48)(); f(buf,1)
 N=20
 for _ in range(N): sarpost.postprocess_fused(levels,spec,return_padded=True,**kw)
 f(buf,1)
-names={0:'prologue(hist scan)',1:'collect',2:'share phase1',3:'deliver+barrier1',4:'sort',5:'radix fallback',6:'zoom histogram',9:'tail+replicate+barrier2',8:'publish',
+names={0:'prologue(hist scan)',1:'collect',2:'share phase1',3:'deliver+barrier1',4:'sort',5:'radix fallback',6:'zoom histogram',9:'tail+replicate+barrier2',8:'publish',7:'fused gather',
        10:'ps: load',13:'ps: pair round',11:'ps: sweep (warp 0)',14:'ps: append+barriers'}
 tot=sum(buf[i] for i in range(16))
 print(wl, 'blobs', blobs)
