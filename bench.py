@@ -555,7 +555,7 @@ def leg_sahi(cx, steps):
     n_frames = -(-total_tiles // tpf)
     max_det = kw["max_det"]
     res = {}
-    n_in_flight = 2 if world > 1 else 1
+    n_in_flight = int(os.environ.get("SARPOST_BENCH_SAHI_INFLIGHT", "0")) or 4
 
     class Marks:
         def __init__(self, on):
@@ -593,7 +593,44 @@ def leg_sahi(cx, steps):
             pipes[(k[0] - 1) % n_in_flight](nxt())
 
         ms2 = time_steps(cx, one, steps, streams) if n_in_flight > 1 else ms1
-        ms1, ms2 = cx.max_over_ranks(ms1, ms2)
+        # the same steps replayed from CUDA graphs (one graph per pipeline = two consecutive steps, i.e. both exchange
+        # buffers of its double-buffered PeerGatherBuffer): every kernel, the signal-pad barrier and the allocations of a
+        # step are captured once, so the host spends a graph launch per two steps instead of ~100 us of Python + launch
+        # calls per step — which is what bounds the eager loop once a rank's share of the tiles takes less than that
+        ms3, graph_err = None, None
+        if os.environ.get("SARPOST_BENCH_SAHI_GRAPH", "1") != "0":
+            graphs = []
+            try:
+                for i, s_ in enumerate(streams):
+                    g = torch.cuda.CUDAGraph()
+                    a, b = sets[(2 * i) % n_sets], sets[(2 * i + 1) % n_sets]
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(g, stream=s_):
+                        pipes[i](a)
+                        pipes[i](b)
+                    graphs.append(g)
+            except Exception as e:  # noqa: BLE001  (capture support of the symmetric-memory barrier varies with the torch build)
+                graph_err = f"{type(e).__name__}: {str(e)[:200]}"
+            ok = cx.max_over_ranks(0.0 if graph_err is None else 1.0)[0] == 0.0  # all ranks or none: the steps contain a barrier
+            if ok:
+                kg = [0]
+
+                def two_steps():
+                    kg[0] += 1
+                    graphs[(kg[0] - 1) % len(graphs)].replay()
+
+                for s_ in streams:
+                    with torch.cuda.stream(s_):
+                        two_steps()
+                torch.cuda.synchronize()
+                cx.barrier()
+                ms3 = time_steps(cx, two_steps, max(steps // 2, 1), streams) * steps / (2 * max(steps // 2, 1))
+            torch.cuda.synchronize()
+            del graphs
+        ms1, ms2, ms3v = cx.max_over_ranks(ms1, ms2, ms3 or 0.0)
+        eager_ms = ms2
+        if ms3 is not None and ms3v < ms2:
+            ms2 = ms3v
         # per-phase breakdown (one step in flight, events between the phases, mean over a few steps)
         reps, acc = 20, None
         for _ in range(reps):
@@ -603,6 +640,10 @@ def leg_sahi(cx, steps):
             acc = d if acc is None else [a + b for a, b in zip(acc, d)]
         acc = cx.max_over_ranks(*[a / reps for a in acc])
         res[name] = {"tiles_per_s": total_tiles * steps / (ms2 / 1e3), "ms_per_step": ms2 / steps,
+                     "launch": "cuda graphs (two steps per replay)" if ms2 != eager_ms else "eager",
+                     "eager": {"tiles_per_s": total_tiles * steps / (eager_ms / 1e3), "ms_per_step": eager_ms / steps},
+                     "graphs": ({"tiles_per_s": total_tiles * steps / (ms3v / 1e3), "ms_per_step": ms3v / steps} if ms3 is not None else
+                                {"unavailable": graph_err or "capture failed on another rank"}),
                      "one_in_flight": {"tiles_per_s": total_tiles * steps / (ms1 / 1e3), "ms_per_step": ms1 / steps},
                      "tiles_on_rank0": n_local, "input_sets": n_sets, "hot_mb_in_rotation": n_sets * hot / 1e6,
                      "phase_ms_max_over_ranks": dict(zip(phase_names, acc))}
@@ -928,7 +969,7 @@ def main():
 
     # ---- sliced inference (cfg4): the one exchange step of the path, measured whenever there is more than one rank ----
     sahi = None
-    if world > 1 and not args.no_sahi:
+    if not args.no_sahi:
         del levels, level_sets, split_sets, head_sets, main, step
         torch.cuda.empty_cache()
         sahi = leg_sahi(cx, max(10, min(args.steps, 100)))

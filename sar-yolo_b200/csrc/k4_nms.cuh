@@ -87,66 +87,68 @@ __device__ __forceinline__ float load_elem(const void *base, int64_t idx, bool i
     return is_half ? __half2float(__ldg(static_cast<const __half *>(base) + idx)) : __ldg(static_cast<const float *>(base) + idx);
 }
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// n columns by one warp, lane-strided: up to eight independent loads per lane are in flight before the first store (a
-// plain load/store loop serialises on the possible aliasing of source and destination).  `ld(c)` returns column c,
-// `st(c, v)` consumes it.
-template <class Load, class Store>
-__device__ __forceinline__ void copy_cols(int n, int lane, const Load &ld, const Store &st) {
-    for (int c0 = lane; c0 < n; c0 += 256) {
+// Extras of (image b, anchor) for modes 0 and 1: store(c, value) for c = lane, lane + 32, ... < nm.  Raw embedding
+// columns are copied, state columns pass through the sigmoid (head.py:247); a decoded prediction is copied verbatim.
+// Every source layout reduces to at most two strided column segments, walked by ONE copy loop (the kernel is a few
+// hundred instructions per warp: code size — instruction-cache misses — is what it pays for).  Up to eight independent
+// loads per lane are in flight before the first store (a plain load/store loop would serialise on the possible
+// aliasing of source and destination).
+template <class Store>
+__device__ __forceinline__ void gather_extras_row(const ExtrasSrc &e, int b, uint32_t anchor, int lane, const Store &store) {
+    const bool hf = e.is_half != 0;
+    const void *base[2];
+    int64_t at[2], cstride[2];
+    int n[2];
+    if (e.mode == 0) {
+        base[0] = e.pred;
+        at[0] = (static_cast<int64_t>(b) * e.channels + 4 + e.nc) * e.anchors + anchor;
+        cstride[0] = e.anchors;
+        n[0] = e.nm;
+        base[1] = nullptr; at[1] = 0; cstride[1] = 0; n[1] = 0;
+    } else {
+        int l = 0;
+#pragma unroll
+        for (int i = 1; i < kMaxLevels; ++i) l += (i < e.nl && anchor >= static_cast<uint32_t>(e.lvl_aoff[i])) ? 1 : 0;
+        const int64_t hw = e.lvl_hw[l];
+        const int64_t pos = anchor - e.lvl_aoff[l];
+        n[0] = e.n_extra_raw;
+        n[1] = e.nm - e.n_extra_raw;
+        cstride[0] = cstride[1] = hw;
+        if (!e.split) {
+            base[0] = base[1] = e.lvl_ptr[l];
+            at[0] = (static_cast<int64_t>(b) * e.no + 4 * kRegMax + e.nc) * hw + pos;
+            at[1] = at[0] + n[0] * hw;
+        } else {
+            base[0] = e.lvl_emb[l];
+            base[1] = e.lvl_state[l];
+            if (e.emb_cl) {  // one contiguous run of n_raw elements per kept row
+                at[0] = (static_cast<int64_t>(b) * hw + pos) * n[0];
+                cstride[0] = 1;
+            } else {
+                at[0] = static_cast<int64_t>(b) * n[0] * hw + pos;
+            }
+            at[1] = static_cast<int64_t>(b) * n[1] * hw + pos;
+        }
+    }
+    // segment 1 (state columns: a handful) is fetched first so that its latency overlaps segment 0's
+    const bool sig = e.mode != 0;
+    float s1 = 0.0f;
+    if (lane < n[1]) s1 = load_elem(base[1], at[1] + lane * cstride[1], hf);
+#pragma unroll 1
+    for (int c0 = lane; c0 < n[0]; c0 += 256) {
         float v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            if (c0 + 32 * u < n) v[u] = ld(c0 + 32 * u);
+            if (c0 + 32 * u < n[0]) v[u] = load_elem(base[0], at[0] + (c0 + 32 * u) * cstride[0], hf);
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            if (c0 + 32 * u < n) st(c0 + 32 * u, v[u]);
+            if (c0 + 32 * u < n[0]) store(c0 + 32 * u, v[u]);
     }
-}
-
-// Extras of (image b, anchor) for modes 0 and 1: store(c, value) for c = lane, lane + 32, ... < nm.  Raw embedding
-// columns are copied, state columns pass through the sigmoid (head.py:247); a decoded prediction is copied verbatim.
-// kPrefetch: nothing is loaded or stored, the lines are only requested into the L2 (the caller comes back for them).
-template <bool kPrefetch = false, class Store>
-__device__ __forceinline__ void gather_extras_row(const ExtrasSrc &e, int b, uint32_t anchor, int lane, const Store &store) {
-    const bool hf = e.is_half != 0;
-    const int esz = hf ? 2 : 4;
-    auto run = [&](const void *base, int64_t at, int64_t cstride, int n, int c_out, bool sig) {
-        if constexpr (kPrefetch) {
-            for (int c = lane; c < n; c += 32) prefetch_l2(static_cast<const char *>(base) + (at + c * cstride) * esz);
-        } else {
-            copy_cols(n, lane, [&](int c) { return load_elem(base, at + c * cstride, hf); },
-                      [&](int c, float v) { store(c_out + c, sig ? sigmoid_rn(v) : v); });
-        }
-    };
-    if (e.mode == 0) {
-        run(e.pred, (static_cast<int64_t>(b) * e.channels + 4 + e.nc) * e.anchors + anchor, e.anchors, e.nm, 0, false);
-        return;
+#pragma unroll 1
+    for (int c = lane; c < n[1]; c += 32) {
+        const float v = c < 32 ? s1 : load_elem(base[1], at[1] + c * cstride[1], hf);
+        store(n[0] + c, sig ? sigmoid_rn(v) : v);
     }
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < kMaxLevels; ++i) l += (i < e.nl && anchor >= static_cast<uint32_t>(e.lvl_aoff[i])) ? 1 : 0;
-    const int64_t hw = e.lvl_hw[l];
-    const int64_t pos = anchor - e.lvl_aoff[l];
-    const int n_raw = e.n_extra_raw, n_sig = e.nm - e.n_extra_raw;
-    if (!e.split) {
-        const int64_t at = (static_cast<int64_t>(b) * e.no + 4 * kRegMax + e.nc) * hw + pos;
-        run(e.lvl_ptr[l], at, hw, n_raw, 0, false);
-        run(e.lvl_ptr[l], at + n_raw * hw, hw, n_sig, n_raw, true);
-        return;
-    }
-    if (e.emb_cl) {  // one contiguous run of n_raw elements per kept row
-        if constexpr (kPrefetch) {
-            const char *row = static_cast<const char *>(e.lvl_emb[l]) + (static_cast<int64_t>(b) * hw + pos) * n_raw * esz;
-            for (int o = lane * 128; o < n_raw * esz; o += 32 * 128) prefetch_l2(row + o);
-        } else {
-            run(e.lvl_emb[l], (static_cast<int64_t>(b) * hw + pos) * n_raw, 1, n_raw, 0, false);
-        }
-    } else {
-        run(e.lvl_emb[l], static_cast<int64_t>(b) * n_raw * hw + pos, hw, n_raw, 0, false);
-    }
-    run(e.lvl_state[l], static_cast<int64_t>(b) * n_sig * hw + pos, hw, n_sig, n_raw, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -206,65 +208,67 @@ __device__ __forceinline__ void gather_row(const GatherParams &p, int b, int r, 
         return;
     }
     const uint32_t anchor = key / static_cast<uint32_t>(p.ex.nc), cls = key - anchor * static_cast<uint32_t>(p.ex.nc);
-    if (p.res_boxes) {
-        // models/yolo/jde/predict.py:52-66: boxes = cat(xyxy, argmax(states), conf, cls), embeds = the raw embedding columns
-        const int64_t row = static_cast<int64_t>(b) * p.max_det + r;
-        const int n_raw = p.res_n_raw, n_sig = p.ex.nm - n_raw;
-        float *emb = p.res_embeds + row * n_raw;
-        float best = -1.0f;  // probabilities are >= 0
-        int best_i = 0x7fffffff;
-        if (p.ex.nm > 0 && p.ex.mode == 0 && anchor >= static_cast<uint32_t>(p.ex.anchors)) {
-            for (int c = lane; c < n_raw; c += 32) emb[c] = 0.0f;  // apriori label row: zero extras (ops.py:258) -> state id 0
-            if (lane == 0 && n_sig > 0) { best = 0.0f; best_i = 0; }
-        } else if (p.ex.nm > 0) {
-            gather_extras_row(p.ex, b, anchor, lane, [&](int c, float v) {
-                if (c < n_raw) emb[c] = v;
-                else if (v > best) { best = v; best_i = c - n_raw; }  // ascending c per lane + strict > : first maximum
-            });
+    // Two output forms share one pass over the extras: the (6 + nm)-column row, or — results layout,
+    // models/yolo/jde/predict.py:52-66 — boxes = cat(xyxy, argmax(states), conf, cls) + the raw embedding columns
+    const bool res = p.res_boxes != nullptr;
+    const int64_t row = static_cast<int64_t>(b) * p.max_det + r;
+    const int n_raw = p.res_n_raw, n_sig = p.ex.nm - n_raw;
+    float *emb = res ? p.res_embeds + row * n_raw : nullptr;
+    float best = -1.0f;  // probabilities are >= 0
+    int best_i = 0x7fffffff;
+    const bool label_row = p.ex.mode == 0 && anchor >= static_cast<uint32_t>(p.ex.anchors);  // apriori label: zero extras (ops.py:258)
+    if (p.ex.nm > 0 && label_row) {
+        for (int c = lane; c < (res ? n_raw : p.ex.nm); c += 32) {
+            if (res) emb[c] = 0.0f;
+            else
+                for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = 0.0f;
         }
+        if (res && lane == 0 && n_sig > 0) { best = 0.0f; best_i = 0; }  // -> state id 0
+    } else if (p.ex.nm > 0) {
+        gather_extras_row(p.ex, b, anchor, lane, [&](int c, float v) {
+            if (!res) {
+                for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = v;
+            } else if (c < n_raw) {
+                emb[c] = v;
+            } else if (v > best) {  // ascending c per lane + strict > : first maximum
+                best = v;
+                best_i = c - n_raw;
+            }
+        });
+    }
+    if (res) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, off);
             const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
             if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
         }
-        if (lane == 0) {
-            float4 bx = p.st.box[seg + slot];
-            if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
+    }
+    if (lane == 0) {
+        float4 bx = p.st.box[seg + slot];
+        if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
+        const float sc = p.st.score[seg + slot];
+        if (res) {
             float *o = p.res_boxes + row * 7;
             o[0] = bx.x;
             o[1] = bx.y;
             o[2] = bx.z;
             o[3] = bx.w;
             o[4] = n_sig > 0 ? static_cast<float>(best_i) : -1.0f;
-            o[5] = p.st.score[seg + slot];
+            o[5] = sc;
             o[6] = static_cast<float>(cls);
-            if (p.kept_index) p.kept_index[row] = static_cast<int32_t>(key);
+        } else {
+            for (int q = 0; q < n_dst; ++q) {
+                float *o = dst(q);
+                o[0] = bx.x;
+                o[1] = bx.y;
+                o[2] = bx.z;
+                o[3] = bx.w;
+                o[4] = sc;
+                o[5] = static_cast<float>(cls);
+            }
         }
-        return;
-    }
-    if (lane == 0) {
-        float4 bx = p.st.box[seg + slot];
-        if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
-        const float sc = p.st.score[seg + slot];
-        for (int q = 0; q < n_dst; ++q) {
-            float *o = dst(q);
-            o[0] = bx.x;
-            o[1] = bx.y;
-            o[2] = bx.z;
-            o[3] = bx.w;
-            o[4] = sc;
-            o[5] = static_cast<float>(cls);
-        }
-        if (p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
-    }
-    if (p.ex.nm > 0 && p.ex.mode == 0 && anchor >= static_cast<uint32_t>(p.ex.anchors)) {
-        for (int c = lane; c < p.ex.nm; c += 32)
-            for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = 0.0f;  // apriori label row: no extras (ops.py:258)
-    } else if (p.ex.nm > 0) {
-        gather_extras_row(p.ex, b, anchor, lane, [&](int c, float v) {
-            for (int q = 0; q < n_dst; ++q) dst(q)[6 + c] = v;
-        });
+        if (p.kept_index) p.kept_index[row] = static_cast<int32_t>(key);
     }
 }
 

@@ -349,3 +349,33 @@ def test_product_code_never_touches_the_oracle_or_a_cpu_fallback():
     for m in re.finditer(r"ReferencePath\(", bench):
         fn = re.findall(r"\ndef (\w+)\(", bench[:m.start()])[-1]
         assert fn in ("run_reference_arm", "leg_reference_gpu", "main"), fn
+
+
+def test_level_signature_tracks_layout_shape_dtype_and_memory_format():
+    """`_LevelSig` (the check a prepared plan / the pipeline's head cache runs instead of full validation): same geometry
+    with new storage matches; another batch, dtype, layout, memory format or a missing branch does not."""
+    import torch
+
+    import sarpost
+    from sarpost.ops import _LevelSig
+
+    spec = sarpost.HeadSpec(nc=2, strides=(8, 16), embed_dim=4, state_classes=3)
+    mk = lambda bs=2, dt=torch.float32: [torch.zeros(bs, spec.no, h, w, dtype=dt) for h, w in ((4, 6), (2, 3))]  # noqa: E731
+    cat = mk()
+    sig = _LevelSig(cat)
+    assert sig.matches(mk()) and not sig.split
+    assert not sig.matches(mk(bs=3)) and not sig.matches(mk(dt=torch.float16)) and not sig.matches(mk()[:1])
+    assert not sig.matches([x.permute(0, 1, 3, 2) for x in mk()])            # same numel, other shape / strides
+    assert not sig.matches([x[:, :, :, ::2] for x in mk()])
+    split = sarpost.split_levels(cat, spec, emb_channels_last=True)
+    assert not sig.matches(split)
+    ssig = _LevelSig(split)
+    assert ssig.split and ssig.matches(sarpost.split_levels(mk(), spec, emb_channels_last=True))
+    assert not ssig.matches(sarpost.split_levels(mk(), spec, emb_channels_last=False))  # NCHW embedding where channels_last was prepared
+    assert not ssig.matches([lv[:2] + (None, lv[3]) for lv in split])
+    # addresses land in the right arrays of a head / io block
+    io = sarpost._lib.PlanIO()
+    ssig.fill(split, io)
+    for i, lv in enumerate(split):
+        assert (io.data[i], io.cls[i], io.emb[i], io.state[i]) == tuple(t.data_ptr() for t in lv)
+    assert io.data[len(split)] is None
