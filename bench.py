@@ -634,6 +634,7 @@ def leg_sahi(cx, steps):
         # per-phase breakdown (one step in flight, events between the phases, mean over a few steps)
         reps, acc = 20, None
         for _ in range(reps):
+            torch.cuda._sleep(1_000_000)  # ~0.5 ms spin first: the step is fully enqueued before it starts, the events bracket device time
             ev = pipes[0](nxt(), phases=True)
             torch.cuda.synchronize()
             d = [ev[i].elapsed_time(ev[i + 1]) for i in range(len(ev) - 1)]
@@ -670,12 +671,12 @@ def leg_sahi(cx, steps):
                 mark = Marks(phases)
                 mark()
                 if peer is not None:
-                    rows_all, cnt_all = sarpost.postprocess_fused(levels, spec, with_extras=False, peer_out=peer.next(), **kw)
+                    rows_all, cnt_all = sarpost.postprocess_fused(levels, spec, with_extras=False, peer_out=peer.next(), nms_cluster=1, **kw)
                     mark()
                     peer.barrier()
                 else:
                     rows_all, cnt_all = g_rows, g_cnt
-                    sarpost.postprocess_fused(levels, spec, with_extras=False, return_padded=True, out=(g_rows[:per], g_cnt[:per]), **kw)
+                    sarpost.postprocess_fused(levels, spec, with_extras=False, return_padded=True, out=(g_rows[:per], g_cnt[:per]), nms_cluster=1, **kw)
                     mark()
                 mark()
                 if f_hi > f_lo:
@@ -704,7 +705,7 @@ def leg_sahi(cx, steps):
             def step(levels, phases=False):
                 mark = Marks(phases)
                 mark()
-                sarpost.postprocess_fused(levels, spec, with_extras=False, return_padded=True, out=(rows[:n_local], cnt[:n_local]), **kw)
+                sarpost.postprocess_fused(levels, spec, with_extras=False, return_padded=True, out=(rows[:n_local], cnt[:n_local]), nms_cluster=1, **kw)
                 mark()
                 sarpost.merge_tiles(rows, cnt, org, tpf, iou_thres=kw["iou_thres"], max_det=max_det, peer_out=peer.next())
                 mark()

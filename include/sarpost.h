@@ -130,6 +130,10 @@ typedef struct sarpost_nms_params {
     float *res_boxes;
     float *res_embeds;
     int32_t res_state_cols; /* sarpost_nms_decoded only: how many of the trailing extras columns are state probabilities */
+    int32_t nms_cluster;    /* CTAs (of 512 threads, one per SM) the NMS kernel spends per image: 0 = automatic (the largest of
+                              4 / 2 / 1 with batch * CTAs <= #SMs: lowest latency for one call), or 1 / 2 / 4 / 8.  Callers that
+                              keep several calls in flight on different streams pass 1, so that the NMS kernels of
+                              consecutive calls fit next to each other.  Results do not depend on it. */
 } sarpost_nms_params_t;
 
 /* Last error message of the calling thread ("" if none). */

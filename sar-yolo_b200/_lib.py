@@ -39,7 +39,7 @@ class NmsParams(C.Structure):
         ("peer_out", C.c_void_p * 8), ("peer_counts", C.c_void_p * 8), ("n_peers", C.c_int32),
         ("peer_slot_offset", C.c_int32), ("prediction_dtype", C.c_int32), ("workspace_clean", C.c_int32), ("out_tail_cols", C.c_int32),
         ("stats", C.c_void_p),
-        ("res_boxes", C.c_void_p), ("res_embeds", C.c_void_p), ("res_state_cols", C.c_int32),
+        ("res_boxes", C.c_void_p), ("res_embeds", C.c_void_p), ("res_state_cols", C.c_int32), ("nms_cluster", C.c_int32),
     ]
 
 

@@ -166,6 +166,8 @@ static int check_params(const sarpost_nms_params_t *p, int nc) {
     if (p->out_tail_cols < 0 || p->out_tail_cols > 4096) return fail(SARPOST_EINVAL, "out_tail_cols %d outside [0, 4096]", p->out_tail_cols);
     if (p->res_boxes && (p->n_peers > 0 || p->out_tail_cols > 0)) return fail(SARPOST_EINVAL, "res_boxes does not combine with peer_out / out_tail_cols");
     if (p->res_state_cols < 0) return fail(SARPOST_EINVAL, "res_state_cols %d < 0", p->res_state_cols);
+    if (p->nms_cluster != 0 && p->nms_cluster != 1 && p->nms_cluster != 2 && p->nms_cluster != 4 && p->nms_cluster != 8)
+        return fail(SARPOST_EINVAL, "nms_cluster %d is not one of 0, 1, 2, 4, 8", p->nms_cluster);
     return SARPOST_OK;
 }
 
@@ -507,6 +509,7 @@ static int tail_prepare(const Pipeline &P, int batch, const sarpost_nms_params_t
     int sms = 0, smem_optin = 0;
     if (int rc = device_sm_count(&sms, &smem_optin)) return rc;
     int cl = batch * 4 <= sms ? 4 : (batch * 2 <= sms ? 2 : 1);
+    if (prm->nms_cluster > 0) cl = prm->nms_cluster;
     if (cl_hint == 1 || cl_hint == 2 || cl_hint == 4) cl = cl_hint;
     if (forced_cl == 1 || forced_cl == 2 || forced_cl == 4 || forced_cl == 8) cl = forced_cl;
     t->cl = cl;

@@ -143,8 +143,9 @@ def scale_params(img1_shape, img0_shapes, device) -> torch.Tensor:
     return torch.tensor(rows, dtype=torch.float32).to(device, non_blocking=True)
 
 
-def _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, rescale=None):
+def _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, rescale=None, nms_cluster=0):
     p = NmsParams()
+    p.nms_cluster = int(nms_cluster)
     p.rescale = rescale.data_ptr() if rescale is not None else None
     p.conf_thres = float(conf_thres)
     p.iou_thres = float(iou_thres)
@@ -471,7 +472,7 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
                       agnostic=False, multi_label=False, max_det=300, max_nms=30000, max_wh=7680,
                       return_index=False, return_padded=False, with_extras=True, scale_to=None, peer_out=None,
                       state_mlp: Optional[StateMLP] = None, out=None, nms_stats: Optional[torch.Tensor] = None,
-                      results: bool = False):
+                      results: bool = False, nms_cluster: int = 0):
     """decode + non_max_suppression in one pass (never materialises y; the extras channels are read only
     for the kept rows).  `levels`: the reference's concatenated `(B, no, H_l, W_l)` tensors, or the split layout —
     per level a tuple `(box, cls[, emb[, state]])` of the branch outputs before `torch.cat` (head.py:204-206), the
@@ -497,7 +498,9 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
     (6 columns x1,y1,x2,y2,conf,cls when the head has no state classes, :73-75) and a contiguous `embeds (B, max_det, E)` —
     instead of the `(6+nm)`-column rows.  Returns per-image lists `(boxes, embeds)`, or with `return_padded=True` the
     device tensors `(boxes, embeds, counts)`.  Combines with `scale_to` (boxes come out in original-image pixels,
-    :49) and `state_mlp` (the deferred MLP then only produces the state id)."""
+    :49) and `state_mlp` (the deferred MLP then only produces the state id).
+    `nms_cluster` (`sarpost_nms_params_t.nms_cluster`): CTAs the NMS kernel spends per image, 0 = automatic; pass 1 when
+    several calls are kept in flight on different streams."""
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
     levels = _prep_levels(levels)
@@ -536,7 +539,7 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
         if len(img0_shapes) != bs:
             raise ValueError(f"sarpost: scale_to has {len(img0_shapes)} original shapes for a batch of {bs}")
         rescale = scale_params(img1_shape, img0_shapes, dev)
-    params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, rescale)
+    params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, rescale, nms_cluster)
     params.out_tail_cols = tail
     if nms_stats is not None:
         if nms_stats.dtype != torch.int64 or tuple(nms_stats.shape) != (bs, 4) or not nms_stats.is_contiguous() or nms_stats.device != dev:
@@ -630,7 +633,7 @@ def _bind_peer(params, peer_out, bs: int, max_det: int, row_len: int) -> None:
 
 def merge_tiles(dets: torch.Tensor, det_counts: torch.Tensor, origins: torch.Tensor, tiles_per_frame: int,
                 iou_thres=0.45, agnostic=False, max_det=300, max_nms=30000, max_wh=7680, return_index=False,
-                return_padded=False, peer_out=None):
+                return_padded=False, peer_out=None, nms_cluster: int = 0):
     """Cross-tile merge of sliced inference: `dets (T, D, row_len)` padded per-tile detections
     (x1,y1,x2,y2,conf,cls,extras...), `det_counts (T,)` int32, `origins (T, 2)` tile offsets in frame
     pixels; T = n_frames * tiles_per_frame with the tiles of a frame contiguous.  Per frame: shift by
@@ -647,7 +650,7 @@ def merge_tiles(dets: torch.Tensor, det_counts: torch.Tensor, origins: torch.Ten
         raise ValueError("sarpost: number of tiles is not a multiple of tiles_per_frame")
     nf = t // tiles_per_frame
     dev = dets.device
-    params, _keep = _make_params(0.0, iou_thres, None, agnostic, False, max_det, max_nms, max_wh)
+    params, _keep = _make_params(0.0, iou_thres, None, agnostic, False, max_det, max_nms, max_wh, None, nms_cluster)
     if peer_out is not None:
         _bind_peer(params, peer_out, nf, max_det, row_len)
     with torch.cuda.device(dev):
@@ -792,7 +795,7 @@ class FusedPlan:
     One plan belongs to one CUDA stream at a time (its workspace is reused in stream order)."""
 
     def __init__(self, levels, spec: HeadSpec, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
-                 max_det=300, max_nms=30000, max_wh=7680, with_extras=True, results: bool = False):
+                 max_det=300, max_nms=30000, max_wh=7680, with_extras=True, results: bool = False, nms_cluster: int = 0):
         assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
         assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
         levels = _prep_levels(levels)
@@ -807,7 +810,7 @@ class FusedPlan:
         if results and not with_extras:
             raise ValueError("sarpost: results=True needs with_extras=True")
         self._sig = _LevelSig(levels)
-        params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh)
+        params, _keep = _make_params(conf_thres, iou_thres, classes, agnostic, multi_label, max_det, max_nms, max_wh, None, nms_cluster)
         anchors = sum(int(_box_of(x).shape[2]) * int(_box_of(x).shape[3]) for x in levels)
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):

@@ -1052,3 +1052,40 @@ def test_plan_rejects_other_geometry(sarpost, cuda):
     want_out, want_counts = sarpost.postprocess_fused(mk(320, 2), spec, return_padded=True, conf_thres=0.25, iou_thres=0.7)
     assert torch.equal(counts, want_counts)
     plan.close()
+
+
+@pytest.mark.gpu
+def test_nms_cluster_parameter_does_not_change_results(sarpost, cuda):
+    """`sarpost_nms_params_t.nms_cluster`: 1 / 2 / 4 / 8 CTAs per image give the rows of the automatic choice, through the
+    general call, a plan and the merge; any other value is rejected."""
+    strides = (8, 16, 32)
+    spec = sarpost.HeadSpec(nc=3, strides=strides, embed_dim=8, state_classes=2)
+    lv = [x.to(cuda) for x in sarpost.synth.head_outputs(3, sarpost.synth.level_shapes(320, strides), 3, 8, 2, seed=11, cls_mean=-1.0, blobs=4)]
+    kw = dict(conf_thres=0.01, iou_thres=0.6, multi_label=True, max_det=120)
+    want_out, want_counts, want_idx = sarpost.postprocess_fused(lv, spec, return_padded=True, return_index=True, **kw)
+    for cl in (1, 2, 4, 8):
+        out, counts, kidx = sarpost.postprocess_fused(lv, spec, return_padded=True, return_index=True, nms_cluster=cl, **kw)
+        assert torch.equal(counts, want_counts)
+        for b, n in enumerate(want_counts.tolist()):
+            assert torch.equal(out[b, :n], want_out[b, :n]) and torch.equal(kidx[b, :n], want_idx[b, :n])
+        plan = sarpost.FusedPlan(lv, spec, nms_cluster=cl, **kw)
+        p_out, p_counts = plan(lv)
+        assert torch.equal(p_counts, want_counts)
+        for b, n in enumerate(want_counts.tolist()):
+            assert torch.equal(p_out[b, :n], want_out[b, :n])
+        plan.close()
+    with pytest.raises(sarpost.SarpostError):
+        sarpost.postprocess_fused(lv, spec, nms_cluster=3, **kw)
+    # merge: two frames of 3 tiles each
+    dets = torch.zeros(6, 50, 6, device=cuda)
+    g = torch.Generator().manual_seed(5)
+    xy = torch.rand(6, 50, 2, generator=g) * 200
+    wh = torch.rand(6, 50, 2, generator=g) * 60 + 5
+    dets[..., :2], dets[..., 2:4] = xy.to(cuda), (xy + wh).to(cuda)
+    dets[..., 4] = torch.rand(6, 50, generator=g).to(cuda)
+    cnt = torch.tensor([50, 20, 0, 50, 50, 7], dtype=torch.int32, device=cuda)
+    org = torch.tensor([[0.0, 0.0], [100.0, 0.0], [0.0, 100.0]] * 2, device=cuda)
+    want = sarpost.merge_tiles(dets, cnt, org, 3, iou_thres=0.5)
+    for cl in (1, 2, 8):
+        got = sarpost.merge_tiles(dets, cnt, org, 3, iou_thres=0.5, nms_cluster=cl)
+        assert all(torch.equal(a, b) for a, b in zip(got, want))

@@ -8,7 +8,10 @@ import json
 d=json.loads(open('gpurun_out/r2mg/bench_cfg3_x$N.json').read().strip().splitlines()[-1])
 print('value', d['value'], 'ms', d['ms_per_step'], 'single', d['single_stream']['value'])
 print('e2e', {k:v for k,v in d['e2e'].items() if k!='api'})
-print('sahi', json.dumps(d['sahi'])[:3000])
+s=d['sahi']
+print('sahi value %.0f tiles/s ms %.4f sharding %s' % (s['value'], s['ms_per_step'], s['sharding']))
+for k,v in s['by_sharding'].items():
+    print(' ', k, 'launch', v['launch'], 'best %.4f ms' % v['ms_per_step'], 'eager %.4f' % v['eager']['ms_per_step'], 'graphs', v['graphs'], 'one %.4f' % v['one_in_flight']['ms_per_step'], {a:round(b,4) for a,b in v['phase_ms_max_over_ranks'].items()})
 print('clocks', d['clocks'])
 PY
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --impl reference --steps 2 --warmup 1 > gpurun_out/r2mg/bench_ref_x$N.json 2> gpurun_out/r2mg/bench_ref_x$N.err; echo ref rc=$?; tail -c 600 gpurun_out/r2mg/bench_ref_x$N.json
+[ $N -le 2 ] && python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --impl reference --steps 2 --warmup 1 > gpurun_out/r2mg/bench_ref_x$N.json 2> gpurun_out/r2mg/bench_ref_x$N.err; echo ref rc=$?; tail -c 600 gpurun_out/r2mg/bench_ref_x$N.json

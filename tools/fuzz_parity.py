@@ -161,7 +161,30 @@ def run(n_cases: int, seed: int) -> int:
                   wts = (torch.randn(hd, ed, generator=g), torch.randn(hd, generator=g), torch.randn(sc, hd, generator=g), torch.randn(sc, generator=g))
                   mlp = sarpost.StateMLP.from_tensors(*wts, device=dev)
                   lvd = [x[:, : 64 + nc + ed].contiguous() for x in lvd]
-              rows, idx = sarpost.postprocess_fused(lvd, spec, return_index=True, scale_to=scale_to, state_mlp=mlp, **kw)
+              lv_cat = lvd
+              via = "plain"
+              if mlp is None:  # the same call through the other host-side forms: split layout, a prepared plan, the batch pipeline
+                  if rng.random() < 0.4:
+                      lvd = sarpost.split_levels(lvd, spec, emb_channels_last=rng.random() < 0.5)
+                  via = rng.choice(["plain", "plain", "plan", "pipeline"])
+              if via == "plan":  # prepared from OTHER tensors of the same geometry, so every address is new at run time
+                  warm = [tuple(None if t is None else t.clone(memory_format=torch.preserve_format) for t in x) if isinstance(x, tuple) else x.clone() for x in lvd]
+                  plan = sarpost.FusedPlan(warm, spec, **kw)
+                  out_, cnt_, kidx_ = plan(lvd, return_index=True, scale_to=scale_to)
+                  n_ = cnt_.tolist()
+                  rows, idx = [out_[b_, :n_[b_]] for b_ in range(bs)], [kidx_[b_, :n_[b_]] for b_ in range(bs)]
+                  plan.close()
+              elif via == "pipeline":
+                  pl = sarpost.Pipeline(dev, depth=rng.choice([1, 2]))
+                  pl.submit(lvd, spec, **kw)  # a batch in front, so the measured one runs in the chained steady state
+                  out_, cnt_, kidx_ = pl.submit(lvd, spec, return_index=True, scale_to=scale_to, **kw)
+                  pl.wait()
+                  n_ = cnt_.tolist()
+                  rows, idx = [out_[b_, :n_[b_]] for b_ in range(bs)], [kidx_[b_, :n_[b_]] for b_ in range(bs)]
+                  pl.close()
+              else:
+                  rows, idx = sarpost.postprocess_fused(lvd, spec, return_index=True, scale_to=scale_to, state_mlp=mlp, **kw)
+              lvd = lv_cat
               if mlp is not None:
                   spec_ns = sarpost.HeadSpec(nc=nc, strides=strides, embed_dim=ed, state_classes=0)
                   y = sarpost.decode([x.float() for x in lvd], spec_ns).cpu()
