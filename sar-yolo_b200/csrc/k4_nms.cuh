@@ -200,9 +200,13 @@ __device__ __forceinline__ void gather_row(const GatherParams &p, int b, int r, 
     if (p.ex.mode == 2) {
         const float *src = p.ex.dets + (static_cast<int64_t>(b) * p.st.tpi * p.ex.dets_per_tile + key) * p.ex.row_len;
         const float4 bx = p.st.box[seg + slot];
-        for (int c = lane; c < 6 + p.ex.nm; c += 32) {
+        // (destination, column) pairs spread over the lanes: with peer stores every lane talks to its own peer instead of
+        // one lane writing to eight of them in turn
+        const int ncols = 6 + p.ex.nm;
+        for (int idx = lane; idx < ncols * n_dst; idx += 32) {
+            const int q = idx / ncols, c = idx - q * ncols;
             const float v = c == 0 ? bx.x : c == 1 ? bx.y : c == 2 ? bx.z : c == 3 ? bx.w : src[c];
-            for (int q = 0; q < n_dst; ++q) dst(q)[c] = v;
+            dst(q)[c] = v;
         }
         if (lane == 0 && p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
         return;
@@ -244,7 +248,7 @@ __device__ __forceinline__ void gather_row(const GatherParams &p, int b, int r, 
             if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
         }
     }
-    if (lane == 0) {
+    if (res ? lane == 0 : lane < 6 * n_dst) {
         float4 bx = p.st.box[seg + slot];
         if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
         const float sc = p.st.score[seg + slot];
@@ -258,17 +262,13 @@ __device__ __forceinline__ void gather_row(const GatherParams &p, int b, int r, 
             o[5] = sc;
             o[6] = static_cast<float>(cls);
         } else {
-            for (int q = 0; q < n_dst; ++q) {
-                float *o = dst(q);
-                o[0] = bx.x;
-                o[1] = bx.y;
-                o[2] = bx.z;
-                o[3] = bx.w;
-                o[4] = sc;
-                o[5] = static_cast<float>(cls);
+            // the six leading columns, one (destination, column) pair per lane (peer stores: every lane its own peer)
+            for (int idx = lane; idx < 6 * n_dst; idx += 32) {
+                const int q = idx / 6, c = idx - q * 6;
+                dst(q)[c] = c == 0 ? bx.x : c == 1 ? bx.y : c == 2 ? bx.z : c == 3 ? bx.w : c == 4 ? sc : static_cast<float>(cls);
             }
         }
-        if (p.kept_index) p.kept_index[row] = static_cast<int32_t>(key);
+        if (lane == 0 && p.kept_index) p.kept_index[row] = static_cast<int32_t>(key);
     }
 }
 
@@ -1268,6 +1268,45 @@ __global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_cons
     const int lane = threadIdx.x & 31;
     const int n_rows = p.counts[b];
     if (p.n_peers > 0 && r == 0 && lane < p.n_peers) p.peer_counts[lane][p.peer_slot_offset + b] = n_rows;  // the counts travel with the rows
+    if (p.n_peers > 0 && p.ex.nm == 0 && p.tail_cols == 0 && p.res_boxes == nullptr && (p.max_det & 1) == 0) {
+        // Exchange of plain 6-column rows (sliced inference: tile detections / merged frames): the block's rows are
+        // assembled in shared memory and go out as 16-byte stores of one contiguous run per peer.  Written row by row, every
+        // 24-byte row is its own NVLink write to each of the peers, and the exchange becomes bound by the packet rate
+        // (8 GPUs: 134 k packets per rank and step) instead of by anything the rows weigh.
+        __shared__ __align__(16) float srow[kGatherWarps * 6];
+        const int warp = threadIdx.x >> 5;
+        if (r < n_rows) {
+            const int64_t seg = static_cast<int64_t>(b) * p.st.cap;
+            const uint32_t slot = p.kept_slot[static_cast<int64_t>(b) * p.max_det + r];
+            const uint32_t key = p.st.key[seg + slot];
+            float4 bx = p.st.box[seg + slot];
+            float c4, c5;
+            if (p.ex.mode == 2) {
+                const float *src = p.ex.dets + (static_cast<int64_t>(b) * p.st.tpi * p.ex.dets_per_tile + key) * p.ex.row_len;
+                c4 = src[4];
+                c5 = src[5];
+            } else {
+                if (p.rescale) bx = rescale_box(bx, p.rescale + 5 * b);
+                c4 = p.st.score[seg + slot];
+                c5 = static_cast<float>(key % static_cast<uint32_t>(p.ex.nc));
+            }
+            if (lane < 6) srow[warp * 6 + lane] = lane == 0 ? bx.x : lane == 1 ? bx.y : lane == 2 ? bx.z : lane == 3 ? bx.w : lane == 4 ? c4 : c5;
+            if (lane == 0 && p.kept_index) p.kept_index[static_cast<int64_t>(b) * p.max_det + r] = static_cast<int32_t>(key);
+        }
+        __syncthreads();
+        const int r0 = blockIdx.x * kGatherWarps;
+        const int nf = 6 * min(max(n_rows - r0, 0), kGatherWarps);  // valid floats of this block
+        const int64_t base = ((static_cast<int64_t>(p.peer_slot_offset) + b) * p.max_det + r0) * 6;  // 16-byte aligned: max_det and r0 are even
+        constexpr int kChunks = kGatherWarps * 6 / 4;
+        for (int t = threadIdx.x; t < p.n_peers * kChunks; t += kGatherWarps * 32) {
+            const int q = t / kChunks, f0 = (t - q * kChunks) * 4;
+            float *d = p.peer_out[q] + base;
+            if (f0 + 4 <= nf) *reinterpret_cast<float4 *>(d + f0) = *reinterpret_cast<const float4 *>(srow + f0);
+            else
+                for (int f = f0; f < nf; ++f) d[f] = srow[f];  // rows beyond counts[b] stay untouched
+        }
+        return;
+    }
     if (r >= n_rows) return;
     const uint32_t slot = p.kept_slot[static_cast<int64_t>(b) * p.max_det + r];
     gather_row(p, b, r, lane, slot, p.st.key[static_cast<int64_t>(b) * p.st.cap + slot]);
