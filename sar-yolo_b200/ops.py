@@ -299,7 +299,7 @@ def _split(out: torch.Tensor, counts: torch.Tensor) -> List[torch.Tensor]:
 
 
 _WS_CACHE = {}  # (device index, stream, nbytes, batch) -> persistent workspace whose histogram head is clean
-_WS_CACHE_MAX = 8
+_WS_CACHE_MAX = 32  # e.g. 4 steps in flight x (per-tile + merge workspace) x 2 streams each, without evicting a live entry
 
 
 class _Workspace:
