@@ -333,6 +333,15 @@ class Ctx:
         return [float(v) for v in t.tolist()]
 
 
+def guarded(name, fn):
+    """An optional leg must not take the headline down with it: its failure is reported in its place in the line."""
+    try:
+        return fn()
+    except Exception as e:  # noqa: BLE001
+        print(f"bench: leg `{name}` failed: {type(e).__name__}: {e}", file=sys.stderr)
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
 def rotating(level_sets):
     it = [0]
 
@@ -939,41 +948,49 @@ def main():
     # ---- clustered leg (same shapes / thresholds, suppression-heavy inputs) ----
     clustered = None
     if not args.no_clustered and not args.blobs:
-        clustered = leg_clustered(cx, spec, shapes, nc, ed, sc, bs, kw, cls_mean, max(10, min(args.steps, 100)), use_split)
+        clustered = guarded("clustered", lambda: leg_clustered(cx, spec, shapes, nc, ed, sc, bs, kw, cls_mean, max(10, min(args.steps, 100)), use_split))
 
     # ---- the reference's own GPU path on the same box (rank 0, N = 1 only) ----
     ref_gpu = None
     if rank == 0 and n_gpus == 1 and not args.no_reference_gpu:
         n_img = min(bs, 4)
-        ours = sarpost.postprocess_fused([x[:n_img].contiguous() for x in levels], spec, **kw)
-        ref_gpu = leg_reference_gpu(cx, levels, strides, nc, ed, sc, kw, n_img, 5, ours)
-        ref_gpu["sarpost_over_reference_gpu"] = {"device_value": value / ref_gpu["value"], "single_stream": single["value"] / ref_gpu["value"]}
+
+        def _ref_gpu():
+            ours = sarpost.postprocess_fused([x[:n_img].contiguous() for x in levels], spec, **kw)
+            r_ = leg_reference_gpu(cx, levels, strides, nc, ed, sc, kw, n_img, 5, ours)
+            r_["sarpost_over_reference_gpu"] = {"device_value": value / r_["value"], "single_stream": single["value"] / r_["value"]}
+            return r_
+
+        ref_gpu = guarded("reference_gpu", _ref_gpu)
 
     # ---- e2e: HOST buffers through the C-ABI host entry (H2D + D2H inside the timed region) ----
-    e2e = None if args.no_e2e else leg_e2e(cx, levels, spec, bs, kw)
+    e2e = None if args.no_e2e else guarded("e2e", lambda: leg_e2e(cx, levels, spec, bs, kw))
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         n_img = args.cpu_images or (4 if args.workload == "cfg3" else min(bs, 16))
         n_img = min(n_img, bs)
-        levels_cpu = [x[:n_img].cpu() for x in levels]
-        torch.set_num_threads(cpu_threads())
-        ref = ReferencePath(strides, nc, ed, sc, "cpu")
-        ref.step([x[:1] for x in levels_cpu], kw)  # warm-up (lazy torchvision import)
-        t0 = time.perf_counter()
-        ref.step(levels_cpu, kw)
-        secs = time.perf_counter() - t0
-        cpu = {"value": n_img / secs, "unit": "images/s", "cores": cpu_threads(), "kind": ref.kind,
-               "sample": f"first {n_img} images of the GPU batch, {secs:.1f} s; {ref.describe()}; {cpu_threads()} torch threads, host has {os.cpu_count()} cpus"}
-        del levels_cpu
+
+        def _cpu():
+            levels_cpu = [x[:n_img].cpu() for x in levels]
+            torch.set_num_threads(cpu_threads())
+            ref = ReferencePath(strides, nc, ed, sc, "cpu")
+            ref.step([x[:1] for x in levels_cpu], kw)  # warm-up (lazy torchvision import)
+            t0 = time.perf_counter()
+            ref.step(levels_cpu, kw)
+            secs = time.perf_counter() - t0
+            return {"value": n_img / secs, "unit": "images/s", "cores": cpu_threads(), "kind": ref.kind,
+                    "sample": f"first {n_img} images of the GPU batch, {secs:.1f} s; {ref.describe()}; {cpu_threads()} torch threads, host has {os.cpu_count()} cpus"}
+
+        cpu = guarded("cpu_baseline", _cpu)
 
     # ---- sliced inference (cfg4): the one exchange step of the path, measured whenever there is more than one rank ----
     sahi = None
     if not args.no_sahi:
         del levels, level_sets, split_sets, head_sets, main, step
         torch.cuda.empty_cache()
-        sahi = leg_sahi(cx, max(10, min(args.steps, 100)))
+        sahi = guarded("sahi", lambda: leg_sahi(cx, max(10, min(args.steps, 100))))
 
     if rank == 0:
         line = {
