@@ -333,6 +333,10 @@ __global__ void __launch_bounds__(kTileA, sizeof(T) == 2 ? 6 : 3) k1_fused_tma(c
         if (t >= p.n_tiles) {
             ring_b[s] = -1;
             mbar_arrive(&full_bar[s]);  // completes the phase without a transfer
+            // out of tiles: at most stages-1 are left in this CTA's ring.  Once every CTA has said so the NMS kernel (a
+            // programmatic dependent) may start placing its CTAs on the SMs that fall free; it still waits for this grid
+            // to complete before it reads anything (griddepcontrol.wait in k4_nms).
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
             return;
         }
         next_t = static_cast<int>(gridDim.x) + atomicAdd(p.tile_counter, 1);

@@ -546,8 +546,12 @@ __global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__
 #endif
     if (tid < kSub) S_DEAD[tid] = 0;
     if (tid >= 32 && tid < 96) S_MISC[tid] = 0;  // control block, counters (both banks), work order
-    if (blockIdx.x == 0 && tid == 0) *p.tile_counter = 0;
     if (p.resident_counter != nullptr && tid == 0) atomicAdd(p.resident_counter, 1u);
+    // The kernel is launched as a programmatic dependent of the candidate kernel (cudaLaunchAttributeProgrammaticStream-
+    // Serialization): its CTAs — each needs a whole SM — are placed while that kernel drains and wait here until all of its
+    // results are visible.  Nothing above touches global memory the candidate kernel uses (a plain launch passes at once).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (blockIdx.x == 0 && tid == 0) *p.tile_counter = 0;
 
     // class-offset box of a candidate slot (ops.py:289,295)
     auto offset_box = [&](uint32_t slot) {

@@ -554,13 +554,16 @@ static int tail_launch(const TailLaunch &t, cudaStream_t s) {
     cfg.blockDim = dim3(kNmsThreads);
     cfg.dynamicSmemBytes = t.nms_smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = t.cl;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = t.cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    // a programmatic dependent of the candidate kernel in front of it (see k4_nms: griddepcontrol.wait)
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (t.pdl && !env_int("SARPOST_NO_PDL_NMS", 0)) ? 2 : 1;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, t.kern, t.np));
     g_last_nms_ctas = t.nms_grid;
     ++g_launches;
