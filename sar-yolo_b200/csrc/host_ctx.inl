@@ -291,15 +291,21 @@ static int32_t fused_host_impl(sarpost_host_ctx_t *c, const sarpost_head_t *head
 // Software pipeline over successive batches (device buffers): sarpost_pipeline_*
 // ================================================================================================
 // One call of sarpost_fused is three dependent kernels: the decode kernel K1 streams the logits at the HBM rate on every
-// SM, the NMS kernel is a latency chain on a handful of SMs, the gather is small.  Back to back on one stream the last two
-// leave the memory system idle; issued from two INDEPENDENT streams they still end up queued behind the other batch's K1,
-// whose persistent CTAs fill every SM the moment the previous K1 drains (measured: the only gain is that the two tails
-// run side by side).  The pipeline rotates `depth` streams (one workspace each), batch i entirely on stream i % depth, and
-// adds one dependency: K1(i+1) waits for K1(i).  When K1(i) finishes, its same-stream successor — the NMS kernel of
-// batch i — is launched at once and takes its few SMs while the cross-stream K1(i+1) is still being released; K1(i+1)
-// hands out tiles dynamically, so it simply streams on whatever is left and picks up the other SMs as the tail of batch i
-// ends.  A one-thread gate kernel in front of K1(i+1) makes "at once" certain: it returns when every CTA of that NMS
-// kernel has checked in (or after 30 us).  In steady state the NMS + gather of every batch are hidden under the next batch's decode.
+// SM, the NMS kernel is a latency chain on a handful of SMs (its CTAs need a whole SM each), the gather is small.  Back to
+// back on one stream the last two leave the memory system idle; issued from two INDEPENDENT streams they still end up
+// queued behind the other batch's K1, whose persistent CTAs fill every SM the moment the previous K1 drains.
+//
+// Scheme A ("lagged tails", the default for depth >= 2): every decode kernel goes to ONE stream, back to back — nothing
+// ever sits between K1(i) and K1(i+1).  The NMS + gather of batch i go to a high-priority stream of their own behind an
+// event recorded after K1(i).  By the time that event fires K1(i+1) already holds every SM, so the NMS kernel of batch i
+// is launched and stays PENDING through K1(i+1); its CTAs take the first SMs that fall free when K1(i+1) drains — before
+// K1(i+2), which only becomes eligible once K1(i+1) has completed — and K1(i+2) streams on what is left (tiles are handed
+// out dynamically).  Results lag one decode kernel behind; throughput is one decode kernel per batch, with no gate kernel
+// and no cross-stream hop on the decode path.  depth + 1 workspaces rotate (batch i+depth+1 waits for the tail of batch i).
+//
+// Scheme B ("gated", SARPOST_PIPE_GATED=1, and depth 1): batch i entirely on stream i % depth, K1(i+1) chained to K1(i)
+// through an event plus a one-thread gate kernel that returns when every CTA of NMS(i) has checked in (or after 30 us),
+// so that NMS(i) takes its SMs before K1(i+1) floods the GPU.  Costs an event hop + the gate + a launch per batch.
 struct sarpost_pipeline {
     int device = 0, depth = 2;
     std::vector<cudaStream_t> streams;
@@ -311,6 +317,9 @@ struct sarpost_pipeline {
     int64_t n_submitted = 0;
     unsigned int *d_resident = nullptr;  // device counter: NMS CTAs that have started, over the pipeline's lifetime
     unsigned int nms_ctas_total = 0;     // what it will read once every NMS kernel submitted so far is resident
+    cudaStream_t s_k1 = nullptr;         // scheme A: the decode stream
+    bool lagged = false;
+    int slots = 1;                       // workspaces / tail streams in rotation: depth (scheme B) or depth + 1 (scheme A)
 };
 
 extern "C" {
@@ -322,16 +331,24 @@ int32_t sarpost_pipeline_create(int32_t device, int32_t depth, sarpost_pipeline_
     sarpost_pipeline *c = new sarpost_pipeline();
     c->device = device;
     c->depth = depth;
-    c->streams.assign(depth, nullptr);
-    c->ev_mid.assign(depth, nullptr);
-    c->ev_tail.assign(depth, nullptr);
-    c->ws.resize(depth);
-    c->ws_sig.assign(depth, -1);
-    c->used.assign(depth, 0);
-    bool ok = cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) == cudaSuccess &&
+    c->lagged = depth > 1 && !env_int("SARPOST_PIPE_GATED", 0);
+    const int slots = c->lagged ? depth + 1 : depth;
+    c->slots = slots;
+    c->streams.assign(slots, nullptr);
+    c->ev_mid.assign(slots, nullptr);
+    c->ev_tail.assign(slots, nullptr);
+    c->ws.resize(slots);
+    c->ws_sig.assign(slots, -1);
+    c->used.assign(slots, 0);
+    int prio_lo = 0, prio_hi = 0;
+    bool ok = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) == cudaSuccess &&
               cudaMalloc(&c->d_resident, 256) == cudaSuccess && cudaMemset(c->d_resident, 0, 256) == cudaSuccess;
-    for (int i = 0; ok && i < depth; ++i)
-        ok = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) == cudaSuccess &&
+    // scheme A: the tails outrank the decode stream, so a pending NMS kernel is placed before anything else when SMs fall free
+    if (ok && c->lagged) ok = cudaStreamCreateWithPriority(&c->s_k1, cudaStreamNonBlocking, prio_lo) == cudaSuccess;
+    for (int i = 0; ok && i < slots; ++i)
+        ok = (c->lagged ? cudaStreamCreateWithPriority(&c->streams[i], cudaStreamNonBlocking, prio_hi)
+                        : cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking)) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_mid[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_tail[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
@@ -346,6 +363,7 @@ int32_t sarpost_pipeline_create(int32_t device, int32_t depth, sarpost_pipeline_
 void sarpost_pipeline_destroy(sarpost_pipeline_t *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->s_k1) cudaStreamSynchronize(c->s_k1);
     for (cudaStream_t st : c->streams)
         if (st) cudaStreamSynchronize(st);
     for (sarpost::Buf &b : c->ws) b.release();
@@ -353,6 +371,7 @@ void sarpost_pipeline_destroy(sarpost_pipeline_t *c) {
     for (cudaEvent_t e : c->ev_tail) if (e) cudaEventDestroy(e);
     if (c->ev_in) cudaEventDestroy(c->ev_in);
     if (c->d_resident) cudaFree(c->d_resident);
+    if (c->s_k1) cudaStreamDestroy(c->s_k1);
     for (cudaStream_t st : c->streams)
         if (st) cudaStreamDestroy(st);
     delete c;
@@ -368,41 +387,52 @@ int32_t sarpost_pipeline_submit(sarpost_pipeline_t *c, const sarpost_head_t *hea
     HeadGeom g;
     int64_t anchors = 0;
     if (int rc = fill_geom(head, &g, &anchors)) return rc;
-    const int slot = static_cast<int>(c->n_submitted % c->depth);
+    const int slot = static_cast<int>(c->n_submitted % c->slots);
     cudaStream_t st = c->streams[slot];
     const int64_t need = sarpost_workspace_bytes(g.batch, anchors, g.nc, params->multi_label, params->max_det);
     if (need < 0) return static_cast<int32_t>(need);
     sarpost::Buf &ws = c->ws[slot];
     if (need > ws.bytes) {
         CUDA_TRY(cudaStreamSynchronize(st));  // about to free memory the slot's previous batch may still be using
+        if (c->s_k1) CUDA_TRY(cudaStreamSynchronize(c->s_k1));
         if (int rc = ws.ensure(need)) return rc;
         c->ws_sig[slot] = -1;
-    }
-    // the inputs are produced on the caller's stream: this batch waits for what is enqueued there so far ...
-    CUDA_TRY(cudaEventRecord(c->ev_in, static_cast<cudaStream_t>(in_stream)));
-    CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in, 0));
-    // ... and its decode kernel for the decode kernel of the batch before it (on the previous stream of the rotation)
-    if (c->depth > 1 && c->n_submitted > 0) {
-        const int prev = static_cast<int>((c->n_submitted - 1) % c->depth);
-        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_mid[prev], 0));
-        // ... once the previous batch's NMS kernel (launched right behind that decode kernel) has taken its SMs
-        k_gate<<<1, 32, 0, st>>>(c->d_resident, c->nms_ctas_total, 30000u);
-        CUDA_TRY(cudaGetLastError());
     }
     sarpost_nms_params_t prm = *params;
     const int64_t sig = (static_cast<int64_t>(g.batch) << 40) ^ (anchors << 8) ^ (g.nc & 0xff) ^ (static_cast<int64_t>(params->multi_label != 0) << 62) ^
                         (static_cast<int64_t>(params->max_det) << 24);
     prm.workspace_clean = c->ws_sig[slot] == sig ? 1 : 0;  // same geometry as last time: the NMS kernel left the head of the slot zeroed
     c->ws_sig[slot] = sig;
-    // the NMS kernel shares the GPU with the next batch's decode: one CTA per image instead of a cluster when the batch is
+    // the NMS kernel shares the GPU with a later batch's decode: one CTA per image instead of a cluster when the batch is
     // large enough to keep the latency chain off the critical path
     const int cl_hint = (c->depth > 1 && g.batch >= 8) ? 1 : 0;
-    g_resident_counter = c->depth > 1 ? c->d_resident : nullptr;
-    g_last_nms_ctas = 0;
-    const int rc = fused_impl(head, &prm, out, counts, kept_index, ws.p, ws.bytes, st, c->ev_mid[slot], cl_hint);
-    g_resident_counter = nullptr;
-    if (c->depth > 1 && c->n_submitted > 0) ++g_launches;  // the gate kernel
-    c->nms_ctas_total += static_cast<unsigned int>(g_last_nms_ctas);  // 0 when the launch itself failed
+    // the inputs are produced on the caller's stream: this batch waits for what is enqueued there so far
+    CUDA_TRY(cudaEventRecord(c->ev_in, static_cast<cudaStream_t>(in_stream)));
+    int rc;
+    if (c->lagged) {
+        // scheme A: decode on the decode stream (behind the previous batch's decode kernel by stream order), tail on the slot's
+        // own stream behind ev_mid[slot]
+        CUDA_TRY(cudaStreamWaitEvent(c->s_k1, c->ev_in, 0));
+        if (c->used[slot]) CUDA_TRY(cudaStreamWaitEvent(c->s_k1, c->ev_tail[slot], 0));  // the slot's workspace is free again
+        g_resident_counter = nullptr;
+        rc = fused_impl(head, &prm, out, counts, kept_index, ws.p, ws.bytes, c->s_k1, c->ev_mid[slot], cl_hint, st);
+    } else {
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_in, 0));
+        // ... and its decode kernel for the decode kernel of the batch before it (on the previous stream of the rotation)
+        if (c->depth > 1 && c->n_submitted > 0) {
+            const int prev = static_cast<int>((c->n_submitted - 1) % c->slots);
+            CUDA_TRY(cudaStreamWaitEvent(st, c->ev_mid[prev], 0));
+            // ... once the previous batch's NMS kernel (launched right behind that decode kernel) has taken its SMs
+            k_gate<<<1, 32, 0, st>>>(c->d_resident, c->nms_ctas_total, 30000u);
+            CUDA_TRY(cudaGetLastError());
+        }
+        g_resident_counter = c->depth > 1 ? c->d_resident : nullptr;
+        g_last_nms_ctas = 0;
+        rc = fused_impl(head, &prm, out, counts, kept_index, ws.p, ws.bytes, st, c->ev_mid[slot], cl_hint);
+        g_resident_counter = nullptr;
+        if (c->depth > 1 && c->n_submitted > 0) ++g_launches;  // the gate kernel
+        c->nms_ctas_total += static_cast<unsigned int>(g_last_nms_ctas);  // 0 when the launch itself failed
+    }
     if (rc != SARPOST_OK) {
         c->ws_sig[slot] = -1;
         return rc;
@@ -416,7 +446,7 @@ int32_t sarpost_pipeline_submit(sarpost_pipeline_t *c, const sarpost_head_t *hea
 int32_t sarpost_pipeline_wait(sarpost_pipeline_t *c, void *stream) {
     if (!c) return fail(SARPOST_EINVAL, "pl is NULL");
     CUDA_TRY(cudaSetDevice(c->device));
-    for (int i = 0; i < c->depth; ++i)  // the newest batch of every stream of the rotation
+    for (int i = 0; i < c->slots; ++i)  // the newest batch of every stream of the rotation
         if (c->used[i]) CUDA_TRY(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), c->ev_tail[i], 0));
     return SARPOST_OK;
 }

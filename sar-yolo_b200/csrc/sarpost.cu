@@ -757,8 +757,10 @@ int32_t sarpost_nms_decoded(const void *prediction, int32_t batch, int32_t chann
 
 // decode + candidates, then select/sort/NMS/gather, all on stream s; `mid` (optional) is recorded right behind the decode
 // kernel — the pipeline chains the next batch's decode kernel, on another stream, to it
+// `s_tail` (optional, needs `mid`): the NMS + gather kernels go to that stream, ordered behind the decode kernel through `mid`.
 static int fused_impl(const sarpost_head_t *head, const sarpost_nms_params_t *params, float *out, int32_t *counts,
-                      int32_t *kept_index, void *workspace, int64_t workspace_bytes, cudaStream_t s, cudaEvent_t mid, int cl_hint) {
+                      int32_t *kept_index, void *workspace, int64_t workspace_bytes, cudaStream_t s, cudaEvent_t mid, int cl_hint,
+                      cudaStream_t s_tail = nullptr) {
     HeadGeom g;
     int64_t anchors = 0;
     if (int rc = fill_geom(head, &g, &anchors)) return rc;
@@ -776,6 +778,10 @@ static int fused_impl(const sarpost_head_t *head, const sarpost_nms_params_t *pa
     if (int rc = launch_k1_fused(g, f, P.st, P.tile_counter, s)) return rc;
     stage_mark(2, s);
     if (mid) CUDA_TRY(cudaEventRecord(mid, s));
+    if (s_tail && mid) {
+        CUDA_TRY(cudaStreamWaitEvent(s_tail, mid, 0));
+        s = s_tail;
+    }
     ExtrasSrc ex;
     fill_extras_src(g, &ex);
     return run_tail(P, g.batch, params, g.nc, ex, out, counts, kept_index, s, cl_hint);
