@@ -333,6 +333,9 @@ class Ctx:
         return [float(v) for v in t.tolist()]
 
 
+PIPE_DEPTH = int(os.environ.get("SARPOST_BENCH_PIPE_DEPTH", "2"))  # batches whose tails may be pending / running behind the decode stream
+
+
 def guarded(name, fn):
     """An optional leg must not take the headline down with it: its failure is reported in its place in the line."""
     try:
@@ -421,7 +424,7 @@ def leg_clustered(cx, spec, shapes, nc, ed, sc, bs, kw, cls_mean, steps, use_spl
     sarpost.postprocess_fused(levels, spec, return_padded=True, nms_stats=stats, **kw)
     torch.cuda.synchronize()
     # the same steps through the software pipeline (two input sets alternating)
-    pl = sarpost.Pipeline(cx.dev, depth=2)
+    pl = sarpost.Pipeline(cx.dev, depth=PIPE_DEPTH)
     ring = [(torch.empty((bs, kw["max_det"], 6 + spec.nm), dtype=torch.float32, device=cx.dev), torch.empty((bs,), dtype=torch.int32, device=cx.dev))
             for _ in range(4)]
     for i in range(4):
@@ -828,7 +831,7 @@ def main():
             # (c) software pipeline (sarpost_pipeline_*): the same K steps submitted back to back; batch i on stream i % 2, its
             # decode kernel chained to the previous batch's decode kernel, so NMS + gather of batch i run under the decode of
             # batch i+1.  Outputs rotate over 4 preallocated sets (a serving loop consumes set i while i+1.. are in flight).
-            pl = sarpost.Pipeline(dev, depth=2)
+            pl = sarpost.Pipeline(dev, depth=PIPE_DEPTH)
             out_ring = [(torch.empty((bs, kw["max_det"], 6 + spec.nm), dtype=torch.float32, device=dev),
                          torch.empty((bs,), dtype=torch.int32, device=dev)) for _ in range(4)]
             pk = [0]
@@ -1001,10 +1004,10 @@ def main():
                        "images_per_gpu": bs, "global_batch": bs * n_gpus, "anchors": anchors, "channels": spec.no, "streams": args.streams,
                        "value_is": headline_mode,
                        "in_flight": ("one batch" if args.streams == 1 else
-                                     "software pipeline of depth 2 (sarpost_pipeline_submit per step, one sarpost_pipeline_wait at the end): every "
-                                     "step is the whole path for one batch; batch i runs on stream i % 2 and its decode kernel is chained to the "
-                                     "previous batch's decode kernel, so the NMS + gather kernels of batch i run under the decode kernel of batch "
-                                     f"i+1; steps rotate over their own input buffers; rows identical to a plain call: {pipe_same_main}; "
+                                     f"software pipeline of depth {PIPE_DEPTH} (sarpost_pipeline_submit per step, one sarpost_pipeline_wait at the end): every "
+                                     "step is the whole path for one batch; the decode kernels of successive batches run back to back on one "
+                                     "stream, the NMS + gather kernels of batch i on a high-priority stream of their own under the decode kernel "
+                                     f"of a later batch; steps rotate over their own input buffers; rows identical to a plain call: {pipe_same_main}; "
                                      f"`two_streams` = round-robin on {args.streams} plain streams, `single_stream` = one batch in flight"),
                        "input_layout": ("split (SARPOST_LAYOUT_SPLIT): per level box (B,64,H,W), cls (B,nc,H,W), emb (B,H,W,E) channels_last, state "
                                         "(B,S,H,W) — what patch(fused=True, split=True) hands over instead of torch.cat (head.py:204-206); the "
