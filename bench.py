@@ -333,7 +333,7 @@ class Ctx:
         return [float(v) for v in t.tolist()]
 
 
-PIPE_DEPTH = int(os.environ.get("SARPOST_BENCH_PIPE_DEPTH", "2"))  # batches whose tails may be pending / running behind the decode stream
+PIPE_DEPTH = int(os.environ.get("SARPOST_BENCH_PIPE_DEPTH", "3"))  # batches whose tails may be pending / running behind the decode stream
 
 
 def guarded(name, fn):

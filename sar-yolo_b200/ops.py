@@ -917,7 +917,7 @@ class Pipeline:
         pl.wait()
     """
 
-    def __init__(self, device=None, depth: int = 2):
+    def __init__(self, device=None, depth: int = 3):
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("sarpost: Pipeline needs a CUDA device (no CPU fallback)")
