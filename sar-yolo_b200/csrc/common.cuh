@@ -48,9 +48,11 @@ __host__ __device__ __forceinline__ uint32_t bucket_floor_bits(int b) {
     return b <= 0 ? 0u : static_cast<uint32_t>(b + kBucketBase) << kBucketShift;
 }
 
-// fp32 sigmoid as torch computes it: 1 / (1 + exp(-x)), each step rounded (head.py:131,249).
+// fp32 sigmoid as torch computes it: 1 / (1 + exp(-x)), each step rounded (head.py:131,249).  The correctly rounded
+// reciprocal IS the correctly rounded quotient 1 / d (same real number, same rounding), without the general division's
+// scaling and slow-path checks.
 __device__ __forceinline__ float sigmoid_rn(float x) {
-    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+    return __frcp_rn(__fadd_rn(1.0f, expf(-x)));
 }
 
 // IoU(a,b) > thr with torchvision CPU nms semantics (see oracle/nms_greedy.c): every op an
