@@ -856,7 +856,9 @@ class FusedPlan:
                 rescale = scale_params(img1_shape, img0_shapes, dev)
             io.rescale = rescale.data_ptr() if rescale is not None else None
             if nms_stats is not None:
-                nms_stats.zero_()
+                if nms_stats.dtype != torch.int64 or tuple(nms_stats.shape) != (bs, 4) or not nms_stats.is_contiguous() or nms_stats.device != dev:
+                    raise ValueError("sarpost: nms_stats must be a contiguous (B, 4) int64 tensor on the levels' device")
+                nms_stats.zero_()  # the kernel accumulates into it
                 io.stats = nms_stats.data_ptr()
             else:
                 io.stats = None
