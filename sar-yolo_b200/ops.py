@@ -13,6 +13,7 @@ required: there is no CPU fallback (`RuntimeError`).
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -503,7 +504,9 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
     several calls are kept in flight on different streams."""
     assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
     assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
-    levels = _prep_levels(levels)
+    if len(levels) == 0:
+        raise ValueError("sarpost: no level tensors")
+    _require_cuda(_box_of(levels[0]), "level tensor")
     if int(_box_of(levels[0]).shape[0]) == 0 and peer_out is None:  # empty batch: the reference returns an empty list (ops.py:250)
         dev0, cols = _box_of(levels[0]).device, 6 + (spec.nm if with_extras else 0)
         if results:
@@ -528,7 +531,7 @@ def postprocess_fused(levels: Sequence[torch.Tensor], spec: HeadSpec, conf_thres
                              f"{spec.embed_dim}, state_classes {spec.state_classes}")
         tail = 0 if results else spec.state_classes
         spec = HeadSpec(nc=spec.nc, strides=spec.strides, reg_max=spec.reg_max, embed_dim=spec.embed_dim, state_classes=0)
-    head = _make_head(levels, spec, with_extras=with_extras)
+    levels, head = _head_for(levels, spec, with_extras)
     nm = spec.nm if with_extras else 0
     dev = _box_of(levels[0]).device
     anchors = sum(int(_box_of(x).shape[2]) * int(_box_of(x).shape[3]) for x in levels)
@@ -780,6 +783,24 @@ class _LevelSig:
         else:
             for i, x in enumerate(levels):
                 io.data[i] = x.data_ptr()
+
+
+_TLS = threading.local()  # per-thread: the cached head block is updated in place right before the library reads it
+
+
+def _head_for(levels, spec: HeadSpec, with_extras: bool):
+    """`(levels, sarpost_head_t)` for a device call.  A loop that hands over the same geometry every time (a predictor, a
+    validator) pays the full normalisation + validation once: while layout / shapes / dtype / memory format / device match
+    the previous call of this thread, the validated block is reused with the new addresses."""
+    ent = getattr(_TLS, "head", None)
+    if ent is not None and ent[1] == spec and ent[2] == with_extras and ent[0].matches(levels):
+        ent[0].fill(levels, ent[3])
+        return levels, ent[3]
+    levels = _prep_levels(levels)
+    head = _make_head(levels, spec, with_extras=with_extras)
+    if head.batch > 0:
+        _TLS.head = (_LevelSig(levels), spec, with_extras, head)
+    return levels, head
 
 
 class FusedPlan:
