@@ -1265,7 +1265,9 @@ __global__ void k_gate(const unsigned int *counter, unsigned int expected, unsig
 // K5.  Launched as a programmatic dependent of the NMS kernel (cudaLaunchAttributeProgrammaticStreamSerialization): its
 // CTAs are scheduled while that kernel is still finishing and wait here until its results are visible, so the launch
 // latency is off the critical path (griddepcontrol.wait returns at once for a plain launch).
-__global__ void __launch_bounds__(kGatherWarps * 32) k5_gather(const __grid_constant__ GatherParams p) {
+// (5 CTAs per SM: 16 images x 300 rows = 608 CTAs then fit one wave; at 4 per SM the last 16 CTAs ran as a second wave
+// that doubled the kernel's tail)
+__global__ void __launch_bounds__(kGatherWarps * 32, 5) k5_gather(const __grid_constant__ GatherParams p) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int b = blockIdx.y;
     const int r = blockIdx.x * kGatherWarps + (threadIdx.x >> 5);
