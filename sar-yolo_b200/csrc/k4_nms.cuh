@@ -498,8 +498,10 @@ constexpr uint32_t kZoomSpan = (1u << kBucketShift) / kBuckets;  // float values
 //               new kept boxes and a control block into the peers — cluster barrier #2.
 // A chunk that would cross the max_nms rank cut, overflow the master's list or a CTA's share is redone (all members to
 // the master / half the bucket run / radix fallback): phase 1 is idempotent and nothing is committed before barrier #2.
-template <int CL>
-__global__ void __launch_bounds__(kNmsThreads, 1) k4_nms(const __grid_constant__ NmsParams p) {
+// MINB = 2 (one CTA per image only): the register budget is halved so that two CTAs share an SM — for batches with more
+// images than SMs, where what the kernel costs is SM-time (it is a latency chain at an IPC of ~0.4), not its own duration.
+template <int CL, int MINB = 1>
+__global__ void __launch_bounds__(kNmsThreads, MINB) k4_nms(const __grid_constant__ NmsParams p) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = CL > 1 ? static_cast<int>(cluster.block_rank()) : 0;
