@@ -516,11 +516,12 @@ static int tail_prepare(const Pipeline &P, int batch, const sarpost_nms_params_t
     t->cl = cl;
     t->nms_grid = batch * cl;
     t->kern = cl == 8 ? k4_nms<8> : cl == 4 ? k4_nms<4> : cl == 2 ? k4_nms<2> : k4_nms<1>;
-    // One CTA per image where the kernel shares the GPU (more images than SMs, or a caller that keeps several calls in
-    // flight: pipeline hint / nms_cluster = 1): the 64-register build lets two CTAs share an SM.  Measured: cfg4 on one GPU
-    // (512 tiles) 1.29 -> 1.42 M tiles/s, cfg2 / cfg5 through the pipeline +4 % / +3.5 %, cfg3 unchanged.
-    const bool shares_gpu = batch > sms || cl_hint == 1 || prm->nms_cluster == 1;
-    if (cl == 1 && shares_gpu && env_int("SARPOST_NMS_TWO_PER_SM", 1) && 2 * (t->nms_smem + 1024) <= smem_optin) t->kern = k4_nms<1, 2>;
+    // More images than SMs (one CTA per image): the 64-register build lets two CTAs share an SM, which is worth its spills
+    // only when CTAs would otherwise queue for SMs — cfg4 on one GPU (512 tiles) 1.29 -> 1.42 M tiles/s.  With SMs to spare
+    // it is a loss where the NMS has real work (pipelined, clustered inputs: cfg3 136 k -> 127 k img/s, cfg5 425 k -> 327 k),
+    // so smaller batches keep a whole SM per CTA.  SARPOST_NMS_TWO_PER_SM=0 / 2 turns it off / forces it for CL = 1.
+    const int two = env_int("SARPOST_NMS_TWO_PER_SM", 1);
+    if (cl == 1 && (two == 2 || (two == 1 && batch > sms)) && 2 * (t->nms_smem + 1024) <= smem_optin) t->kern = k4_nms<1, 2>;
 
     GatherParams &gp = t->gp;
     gp.st = P.st;
