@@ -327,11 +327,14 @@ int32_t sarpost_host_ctx_last_traffic(const sarpost_host_ctx_t *ctx, int64_t *h2
 
 /*
  * Software pipeline over successive batches held in DEVICE memory (throughput mode; bench.py's `value`).  Same arguments
- * and results as sarpost_fused, but the work is enqueued on the pipeline's own `depth` streams (one workspace each), batch
- * i on stream i % depth, with one extra dependency: the decode kernel of batch i+1 starts when the decode kernel of batch
- * i is done.  The NMS kernel of batch i — same-stream successor of its decode kernel — then takes its few SMs first, and
- * the decode of batch i+1 (tiles handed out dynamically) streams on the SMs that are left: NMS + gather of every batch
- * are hidden under the next batch's decode (depth >= 2 for any overlap).  No host synchronisation anywhere.
+ * and results as sarpost_fused, but the work is enqueued on the pipeline's own streams: every decode kernel on one
+ * low-priority stream, back to back; the NMS + gather kernels of batch i on a high-priority stream of their own, released
+ * when the decode kernel of batch i ends — by then the decode kernel of batch i+1 holds every SM, so they stay pending and
+ * take the first SMs that fall free when it drains, ahead of the decode kernel of batch i+2, which streams on what is left
+ * (tiles are handed out dynamically).  NMS + gather of every batch are hidden under a later batch's decode; results lag one
+ * decode kernel behind.  `depth` (1..8) = batches whose NMS + gather may be pending or running behind the decode stream
+ * (depth + 1 workspaces rotate; depth 1 = plain stream order, no overlap; 3 is a good default).  No host synchronisation
+ * anywhere.
  *   submit  waits (device side) for the work enqueued so far on `in_stream` — the stream that produced the level
  *           tensors — then enqueues the batch.  The level tensors and the outputs must stay valid until a later
  *           sarpost_pipeline_wait has been passed.
