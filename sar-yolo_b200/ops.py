@@ -929,9 +929,10 @@ class FusedPlan:
 
 class Pipeline:
     """Throughput mode for a stream of batches in device memory (`sarpost_pipeline_*`): `submit()` enqueues the fused
-    decode + NMS of one batch on one of the pipeline's own `depth` streams and returns the padded output tensors
-    immediately; the decode kernels of successive batches are chained, so the NMS + gather of batch i run under the
-    decode kernel of batch i+1.  `wait()` makes the current stream wait for everything
+    decode + NMS of one batch on the pipeline's own streams and returns the padded output tensors immediately; the
+    decode kernels of successive batches run back to back on one stream, the NMS + gather of batch i on a high-priority
+    stream of their own under the decode kernel of a later batch (`depth` = batches whose NMS + gather may be pending or
+    running behind the decode stream).  `wait()` makes the current stream wait for everything
     submitted so far — the outputs may be read (on the current stream) after it, without any host synchronisation.
 
         pl = sarpost.Pipeline(device)
