@@ -9,15 +9,15 @@ def last(name):
     return json.loads(open(os.path.join(R, name)).read().strip().splitlines()[-1])
 
 
-x1, x2, x8 = last("bench_cfg3.json"), last("bench_cfg3_x2.json"), last("bench_cfg3_x8.json")
-s1, s2, s8 = last("bench_cfg4_x1.json")["sahi"], x2["sahi"], last("bench_cfg4_x8.json")["sahi"]
+x1, x2, x4, x8 = last("bench_cfg3.json"), last("bench_cfg3_x2.json"), last("bench_cfg3_x4.json"), last("bench_cfg3_x8.json")
+s1, s2, s4, s8 = last("bench_cfg4_x1.json")["sahi"], x2["sahi"], x4["sahi"], last("bench_cfg4_x8.json")["sahi"]
 L = ["# Scaling on one box of B200s (round 2; torchrun, one rank per GPU; see the bench_*_x*.json next to this file)", "",
      "## cfg3 (weak scaling: 16 images per GPU per step, no data-path collective)",
      f"{'GPUs':>4s} {'img/s (device-resident)':>24s} {'per GPU':>9s} {'e2e img/s (host buffers)':>25s} {'H2D ceiling img/s':>18s} {'e2e/ceiling':>12s} {'GB/s per GPU at the ceiling':>28s}"]
-for n, d in ((1, x1), (2, x2), (8, x8)):
+for n, d in ((1, x1), (2, x2), (4, x4), (8, x8)):
     e, c = d["e2e"], d["e2e"]["h2d_ceiling"]
     L.append(f"{n:4d} {d['value']:24.0f} {d['value'] / n:9.0f} {e['value']:25.0f} {c['value']:18.0f} {e['value'] / c['value']:12.3f} {c['gbytes_per_s_per_gpu']:28.1f}")
-L += ["(N = 1 and 2 with the final library; N = 8 was measured earlier in the round with the gated pipeline, 147-150 k img/s per GPU on one GPU then:",
+L += ["(N = 1, 2 and 4 with the final library, N = 4 with the driver's --steps 20 [the drain of the last batches weighs more]; N = 8 was measured earlier in the round with the gated pipeline, 147-150 k img/s per GPU on one GPU then:",
       " 0.98 of 8 x that.  The ranks do not interact on this path.",
       " The e2e figure is bounded by what the host can feed: the aggregate pinned->device rate of 8 concurrent ranks is 187 GB/s = 23.4 GB/s per",
       " GPU against 54 GB/s for one rank alone - measured in the same run, `e2e.h2d_ceiling`.  Round 1: e2e 1 459 / 2 902 / 3 180 / 2 439 img/s at",
@@ -26,7 +26,7 @@ L += ["(N = 1 and 2 with the final library; N = 8 was measured earlier in the ro
       "##       peer memory -> cross-tile merge per frame; 4 steps in flight)",
       f"{'GPUs':>4s} {'tiles/s':>12s} {'ms/step':>9s} {'eff':>6s} {'sharding':>9s} {'launch':>8s} {'eager ms/step':>14s}   phases of one step in flight (ms, max over ranks)"]
 t1 = s1["value"]
-for n, s in ((1, s1), (2, s2), (8, s8)):
+for n, s in ((1, s1), (2, s2), (4, s4), (8, s8)):
     b = s["by_sharding"][s["sharding"]]
     L.append(f"{n:4d} {s['value']:12.0f} {s['ms_per_step']:9.4f} {s['value'] / (n * t1):6.3f} {s['sharding']:>9s} {('graphs' if 'graph' in b['launch'] else 'eager'):>8s} "
              f"{b['eager']['ms_per_step']:14.4f}   " + ", ".join(f"{k} {v:.3f}" for k, v in b["phase_ms_max_over_ranks"].items()))
