@@ -94,3 +94,23 @@ def test_cpp_example_builds_and_links(sarpost, tmp_path):
         assert run.returncode == 0 and "detections" in run.stdout, run.stdout + run.stderr
     else:
         assert run.returncode == 2 and "no usable CUDA device" in run.stderr
+
+
+def test_cpp_plan_example_builds_and_links(sarpost, tmp_path):
+    """examples/cpp_plan_serving_loop.cpp: the plan API (sarpost_plan_create / _run / _destroy) from plain C++ with the CUDA
+    runtime — a per-frame loop on device buffers.  Without a GPU the program says so and exits 2."""
+    import subprocess
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = tmp_path / "cpp_plan_serving_loop"
+    libdir = os.path.dirname(sarpost._lib.LIB_PATH)
+    cmd = ["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(cuda, "include"),
+           os.path.join(ROOT, "examples", "cpp_plan_serving_loop.cpp"), "-L" + libdir, "-lsarpost", "-L" + os.path.join(cuda, "lib64"), "-lcudart",
+           "-Wl,-rpath," + libdir, "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", str(exe)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe), "12"], capture_output=True, text=True, timeout=120)
+    import torch
+    if torch.cuda.is_available():
+        assert run.returncode == 0 and "detections" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode == 2 and "no usable CUDA device" in run.stderr
