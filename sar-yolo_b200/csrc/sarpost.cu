@@ -161,8 +161,11 @@ static int check_params(const sarpost_nms_params_t *p, int nc) {
     if (nc < 1 || nc > SARPOST_MAX_CLASSES) return fail(SARPOST_EUNSUPPORTED, "nc %d outside [1, %d]", nc, SARPOST_MAX_CLASSES);
     if (p->n_classes < 0 || (p->n_classes > 0 && !p->classes)) return fail(SARPOST_EINVAL, "classes pointer/count mismatch");
     if (p->n_peers < 0 || p->n_peers > 8) return fail(SARPOST_EINVAL, "n_peers %d outside [0, 8]", p->n_peers);
-    for (int q = 0; q < p->n_peers; ++q)
+    for (int q = 0; q < p->n_peers; ++q) {
         if (!p->peer_out[q] || !p->peer_counts[q]) return fail(SARPOST_EINVAL, "peer buffer %d is NULL", q);
+        // the exchange of 6-column rows goes out as 16-byte stores (k5_gather)
+        if (reinterpret_cast<uintptr_t>(p->peer_out[q]) % 16) return fail(SARPOST_EINVAL, "peer_out[%d] is not 16-byte aligned", q);
+    }
     if (p->out_tail_cols < 0 || p->out_tail_cols > 4096) return fail(SARPOST_EINVAL, "out_tail_cols %d outside [0, 4096]", p->out_tail_cols);
     if (p->res_boxes && (p->n_peers > 0 || p->out_tail_cols > 0)) return fail(SARPOST_EINVAL, "res_boxes does not combine with peer_out / out_tail_cols");
     if (p->res_state_cols < 0) return fail(SARPOST_EINVAL, "res_state_cols %d < 0", p->res_state_cols);
