@@ -101,7 +101,7 @@ typedef struct sarpost_nms_params {
      * kernel stores every output row — and every image's count — into the buffers of ALL n_peers ranks (P2P-mapped
      * device pointers, e.g. torch symmetric memory), at image slot peer_slot_offset + b, instead of `out`/`counts`:
      * the all-gather of SURVEY §8e happens inside K5.  The caller runs a cross-rank barrier afterwards. */
-    float *peer_out[8];      /* each (total_images, max_det, 6 + nm) */
+    float *peer_out[8];      /* each (total_images, max_det, 6 + nm); 16-byte aligned (6-column rows leave as 16-byte stores) */
     int32_t *peer_counts[8]; /* each (total_images) */
     int32_t n_peers;
     int32_t peer_slot_offset;
